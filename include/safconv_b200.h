@@ -1,0 +1,184 @@
+/*
+ * safconv_b200.h -- C ABI of libsafconv_b200.so
+ *
+ * B200 (sm_100a) implementation of the Spatial_Audio_Framework multichannel
+ * convolution path.  The first block of declarations is a DROP-IN for the
+ * reference header
+ *
+ *   /root/reference/framework/modules/saf_utilities/saf_utility_matrixConv.h
+ *
+ * (same symbol names, same signatures, same data layouts, same ownership
+ * rules); a program that links libsafconv_b200.so instead of the reference's
+ * saf_utility_matrixConv.o needs no source change.  The second block is an
+ * additive extension surface (device-pointer apply, batched frames, sharding,
+ * error query, timing) that the reference does not have.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable, `*_create` stores NULL
+ * in *phMC, records an error (see safconv_last_error_string) and returns;
+ * `*_apply` on a NULL handle is a no-op, exactly like the reference's callers
+ * already assume (examples/src/matrixconv/matrixconv.c:141-145).
+ *
+ * All pointers are plain host pointers to contiguous float32 unless a function
+ * name ends in `_device`.
+ */
+#ifndef SAFCONV_B200_H_INCLUDED
+#define SAFCONV_B200_H_INCLUDED
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ========================================================================== */
+/*            Drop-in block (reference: saf_utility_matrixConv.h)             */
+/* ========================================================================== */
+
+/**
+ * Matrix convolver: nCHout x nCHin FIR matrix, block-by-block.
+ * Replaces saf_matrixConv_create, saf_utility_matrixConv.h:55-62
+ * (implementation saf_utility_matrixConv.c:49-130).
+ *
+ * @param phMC        (&) handle; overwritten (NULL on failure)
+ * @param hopSize     block length in samples (1..8192; TVConv: 1..4096)
+ * @param H           time-domain filters, FLAT nCHout x nCHin x length_h; only
+ *                    read during this call (caller may free it afterwards)
+ * @param usePartFLAG 0/1 as in the reference.  Both modes produce the same causal
+ *                    linear convolution; this library serves both with its
+ *                    uniformly-partitioned engine (outputs equal to rounding).
+ */
+void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_h,
+                           int nCHin, int nCHout, int usePartFLAG);
+
+/** Replaces saf_matrixConv_destroy, saf_utility_matrixConv.h:69-70 (.c:132-161).
+ *  Safe on *phMC == NULL.  Additionally sets *phMC = NULL (harmless superset). */
+void saf_matrixConv_destroy(void** const phMC);
+
+/**
+ * Replaces saf_matrixConv_apply, saf_utility_matrixConv.h:82-86 (.c:163-236).
+ * Synchronous: outputSigs (FLAT nCHout x hopSize) is complete on return.
+ * inputSigs is FLAT nCHin x hopSize.
+ */
+void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs);
+
+/**
+ * Multi-channel (diagonal) convolver: nCH independent FIRs.
+ * Replaces saf_multiConv_create, saf_utility_matrixConv.h:109-115 (.c:257-328).
+ * H is FLAT nCH x length_h.
+ */
+void saf_multiConv_create(void** const phMC, int hopSize, float* H, int length_h,
+                          int nCH, int usePartFLAG);
+
+/** Replaces saf_multiConv_destroy, saf_utility_matrixConv.h:122-123 (.c:330-355). */
+void saf_multiConv_destroy(void** const phMC);
+
+/** Replaces saf_multiConv_apply, saf_utility_matrixConv.h:132-136 (.c:357-414).
+ *  inputSigs / outputSigs are FLAT nCH x hopSize. */
+void saf_multiConv_apply(void* const hMC, float* inputSigs, float* outputSigs);
+
+/**
+ * Time-varying convolver (1 input -> nCHout, nIRs selectable impulse responses,
+ * 3-way cross-fade on IR changes).
+ * Replaces saf_TVConv_create / _destroy / _apply,
+ * saf_utility_matrixConv.h:157-190 (.c:423-620).
+ * H: nIRs pointers, each to FLAT nCHout x length_h.
+ */
+void saf_TVConv_create(void** const phTVC, int hopSize, float** H, int length_h,
+                       int nIRs, int nCHout, int initIdx);
+void saf_TVConv_destroy(void** const phTVC);
+void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int irIdx);
+
+/* ========================================================================== */
+/*                 Extension block (not present in the reference)             */
+/* ========================================================================== */
+
+/** Error codes stored per handle / per thread. 0 means OK. */
+enum {
+    SAFCONV_OK            = 0,
+    SAFCONV_ERR_ARG       = 1,  /* invalid argument (sizes <= 0, NULL pointers, hop > 8192 ...) */
+    SAFCONV_ERR_NO_DEVICE = 2,  /* no usable CUDA device / driver */
+    SAFCONV_ERR_CUDA      = 3,  /* a CUDA runtime call or kernel failed */
+    SAFCONV_ERR_NOMEM     = 4   /* host or device allocation failed */
+};
+
+/** Last error of a handle (or of the calling thread's most recent create if h == NULL). */
+int         safconv_last_error(void* h);
+const char* safconv_last_error_string(void* h);
+
+/** Library build string, e.g. "safconv-b200 0.1 (sm_100a)". */
+const char* safconv_version(void);
+
+/** Select the CUDA device used by subsequent `*_create` calls of this thread (default: current device). */
+int safconv_set_device(int device);
+
+/**
+ * Sharded create: this handle owns output channels [outBegin, outBegin+outCount) of an
+ * nCHout-wide problem (output channels are independent: saf_utility_matrixConv.c:218-234).
+ * H is still the FULL FLAT nCHout x nCHin x length_h array; apply() then produces
+ * outCount x hopSize.  Used for output-channel sharding across GPUs.
+ */
+void safconv_matrixConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
+                                     int nCHin, int nCHout, int outBegin, int outCount);
+
+/** As saf_multiConv_create for channels [chBegin, chBegin+chCount) of H (FLAT nCH x length_h). */
+void safconv_multiConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
+                                    int nCH, int chBegin, int chCount);
+
+/**
+ * Device-pointer apply: d_in (nCHin x hop) and d_out (nOutLocal x hop) are device
+ * pointers on the handle's device.  Enqueues on the handle's stream and returns
+ * without synchronising.  Works for matrixConv and multiConv handles.
+ */
+int safconv_apply_device(void* h, const float* d_in, float* d_out);
+
+/**
+ * Enqueue `nBlocks` consecutive blocks: d_in is [nBlocks][nCHin][hop], d_out is
+ * [nBlocks][nOutLocal][hop] (device pointers).  No host synchronisation.
+ */
+int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nBlocks);
+
+/** Use an external CUDA stream (cudaStream_t passed as void*) for this handle; NULL restores its own stream. */
+int safconv_set_stream(void* h, void* cudaStream);
+/** The stream (cudaStream_t as void*) the handle currently enqueues on. */
+void* safconv_get_stream(void* h);
+/** Block the host until everything enqueued by this handle has finished. */
+int safconv_synchronize(void* h);
+
+/** Reset the convolver state (delay line + overlap tails) to zero without re-transforming the filters. */
+int safconv_reset_state(void* h);
+
+/** Introspection of a handle's plan (any out-pointer may be NULL). */
+typedef struct safconv_info {
+    int kind;              /* 0 matrix, 1 multi, 2 time-varying */
+    int hopSize, length_h, nCHin, nCHout, nOutLocal, outBegin;
+    int fftSize, nBinsPacked, numFilterBlocks;
+    int macGrid, macStages, macThreads;     /* launch geometry of the filter-streaming MAC */
+    int device;
+    size_t bytesFilters, bytesDelayLine;    /* resident device bytes */
+    double algBytesPerBlock;                /* SURVEY.md §8(d) algorithmic bytes per block for this handle */
+    double macAlgBytesPerBlock;             /* H + delay-line bytes read by the MAC per block */
+} safconv_info;
+int safconv_get_info(void* h, safconv_info* info);
+
+/**
+ * Timing helper for benchmarks.  safconv_enable_kernel_timing(h, nBlocks) allocates a ring of CUDA
+ * events for up to nBlocks blocks (0 disables); while enabled, every block enqueued by
+ * saf_*_apply / safconv_apply_device* records events between its kernels on the handle's stream.
+ * safconv_get_kernel_times synchronises on the last recorded block, returns the AVERAGE per-block
+ * durations over the recorded blocks (ms[0] = forward FFT, ms[1] = filter-streaming MAC [or the fused
+ * multiConv kernel], ms[2] = inverse FFT + overlap-add), how many blocks were averaged, and restarts
+ * the ring.
+ */
+int safconv_enable_kernel_timing(void* h, int nBlocks);
+int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
+
+/** Tuning knobs (mostly for benchmarks / tests). Returns 0 on success.
+ *    "mac_hints"    0/1 L2 eviction-priority hints on the H / delay-line streams
+ *    "use_graph"    0/1 replay the per-block launch sequence of saf_*_apply from a CUDA graph
+ */
+int safconv_set_option(void* h, const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFCONV_B200_H_INCLUDED */

@@ -1,0 +1,23 @@
+"""spatial_audio_framework_b200 -- host-side mirror of the reference convolver API.
+
+The product is ``libsafconv_b200.so`` (C host layer + hand-written sm_100a CUDA kernels,
+``csrc/``), whose exported symbols are a drop-in for the reference's
+``saf_utility_matrixConv.h`` (``/root/reference/framework/modules/saf_utilities/
+saf_utility_matrixConv.h:55-190``).  This package only *binds* that C ABI with
+ctypes so that tests and ``bench.py`` can call it; it contains no compute path of
+its own and there is no CPU fallback: importing works anywhere, but creating a
+convolver without the built library or without a CUDA device raises.
+"""
+from ._capi import (  # noqa: F401
+    LIB_PATH,
+    SafConvError,
+    MatrixConv,
+    MultiConv,
+    TVConv,
+    build,
+    lib,
+    version,
+)
+from . import synth  # noqa: F401
+
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "lib", "version", "synth"]

@@ -1,0 +1,292 @@
+"""ctypes binding of libsafconv_b200.so (declarations: include/safconv_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libsafconv_b200.so"
+
+_f32p = C.POINTER(C.c_float)
+_vpp = C.POINTER(C.c_void_p)
+
+
+class SafConvError(RuntimeError):
+    pass
+
+
+class SafConvInfo(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("hopSize", C.c_int), ("length_h", C.c_int), ("nCHin", C.c_int),
+        ("nCHout", C.c_int), ("nOutLocal", C.c_int), ("outBegin", C.c_int),
+        ("fftSize", C.c_int), ("nBinsPacked", C.c_int), ("numFilterBlocks", C.c_int),
+        ("macGrid", C.c_int), ("macStages", C.c_int), ("macThreads", C.c_int),
+        ("device", C.c_int),
+        ("bytesFilters", C.c_size_t), ("bytesDelayLine", C.c_size_t),
+        ("algBytesPerBlock", C.c_double), ("macAlgBytesPerBlock", C.c_double),
+    ]
+
+
+# every symbol include/safconv_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "saf_matrixConv_create", "saf_matrixConv_destroy", "saf_matrixConv_apply",
+    "saf_multiConv_create", "saf_multiConv_destroy", "saf_multiConv_apply",
+    "saf_TVConv_create", "saf_TVConv_destroy", "saf_TVConv_apply",
+    "safconv_last_error", "safconv_last_error_string", "safconv_version", "safconv_set_device",
+    "safconv_matrixConv_create_shard", "safconv_multiConv_create_shard",
+    "safconv_apply_device", "safconv_apply_device_blocks",
+    "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
+    "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_set_option",
+]
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libsafconv_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", str(PKG_DIR / "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0 or not LIB_PATH.exists():
+        raise SafConvError("building libsafconv_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the product library.  Fails loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SafConvError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    L.saf_matrixConv_create.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.saf_matrixConv_destroy.argtypes = [_vpp]
+    L.saf_matrixConv_apply.argtypes = [C.c_void_p, _f32p, _f32p]
+    L.saf_multiConv_create.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int]
+    L.saf_multiConv_destroy.argtypes = [_vpp]
+    L.saf_multiConv_apply.argtypes = [C.c_void_p, _f32p, _f32p]
+    L.saf_TVConv_create.argtypes = [_vpp, C.c_int, C.POINTER(_f32p), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.saf_TVConv_destroy.argtypes = [_vpp]
+    L.saf_TVConv_apply.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
+    for f in ("saf_matrixConv_create", "saf_matrixConv_destroy", "saf_matrixConv_apply",
+              "saf_multiConv_create", "saf_multiConv_destroy", "saf_multiConv_apply",
+              "saf_TVConv_create", "saf_TVConv_destroy", "saf_TVConv_apply"):
+        getattr(L, f).restype = None
+    L.safconv_last_error.argtypes = [C.c_void_p]
+    L.safconv_last_error.restype = C.c_int
+    L.safconv_last_error_string.argtypes = [C.c_void_p]
+    L.safconv_last_error_string.restype = C.c_char_p
+    L.safconv_version.restype = C.c_char_p
+    L.safconv_set_device.argtypes = [C.c_int]
+    L.safconv_matrixConv_create_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.safconv_matrixConv_create_shard.restype = None
+    L.safconv_multiConv_create_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.safconv_multiConv_create_shard.restype = None
+    L.safconv_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.safconv_apply_device_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.safconv_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.safconv_get_stream.argtypes = [C.c_void_p]
+    L.safconv_get_stream.restype = C.c_void_p
+    L.safconv_synchronize.argtypes = [C.c_void_p]
+    L.safconv_reset_state.argtypes = [C.c_void_p]
+    L.safconv_get_info.argtypes = [C.c_void_p, C.POINTER(SafConvInfo)]
+    L.safconv_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    L.safconv_get_kernel_times.argtypes = [C.c_void_p, _f32p, C.POINTER(C.c_int)]
+    L.safconv_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    _lib = L
+    return L
+
+
+def version() -> str:
+    return lib().safconv_version().decode()
+
+
+def _fp(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_f32p)
+
+
+class _Base:
+    """Common part of the three convolver wrappers (handle lifetime, errors, extension calls)."""
+
+    _destroy_name = ""
+
+    def __init__(self):
+        self._lib = lib()
+        self._h = C.c_void_p()
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def _check_created(self, what: str):
+        if not self._h:
+            msg = self._lib.safconv_last_error_string(None).decode()
+            raise SafConvError(f"{what} failed: {msg}")
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            getattr(self._lib, self._destroy_name)(C.byref(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def _raise_if_error(self):
+        code = self._lib.safconv_last_error(self._h)
+        if code:
+            raise SafConvError(self._lib.safconv_last_error_string(self._h).decode())
+
+    # -- extension surface ------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> SafConvInfo:
+        i = SafConvInfo()
+        if self._lib.safconv_get_info(self._h, C.byref(i)):
+            raise SafConvError("safconv_get_info failed")
+        return i
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._lib.safconv_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0))
+
+    def synchronize(self):
+        if self._lib.safconv_synchronize(self._h):
+            self._raise_if_error()
+
+    def reset_state(self):
+        if self._lib.safconv_reset_state(self._h):
+            self._raise_if_error()
+
+    def set_option(self, name: str, value: int):
+        if self._lib.safconv_set_option(self._h, name.encode(), int(value)):
+            raise SafConvError(f"unknown option {name}")
+
+    def apply_device(self, d_in_ptr: int, d_out_ptr: int, n_blocks: int = 1):
+        """Enqueue n_blocks blocks on device pointers (no host sync)."""
+        if self._lib.safconv_apply_device_blocks(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr), n_blocks):
+            self._raise_if_error()
+
+    def enable_kernel_timing(self, n_blocks: int):
+        """Record CUDA events around the kernels of the next n_blocks blocks (0 disables)."""
+        if self._lib.safconv_enable_kernel_timing(self._h, int(n_blocks)):
+            self._raise_if_error()
+
+    def kernel_times_ms(self):
+        """(avg ms [fwd FFT, MAC, iFFT+OLA], number of blocks averaged); restarts the event ring."""
+        ms = (C.c_float * 3)()
+        n = C.c_int(0)
+        if self._lib.safconv_get_kernel_times(self._h, ms, C.byref(n)):
+            self._raise_if_error()
+        return [ms[0], ms[1], ms[2]], n.value
+
+    def run(self, x: np.ndarray) -> np.ndarray:
+        """Block-by-block processing of a whole signal x[nIn, T] -> y[nOut, T] via the host API."""
+        hop = self.hop
+        nblk = x.shape[1] // hop
+        y = np.empty((self.nOutLocal, nblk * hop), np.float32)
+        for b in range(nblk):
+            y[:, b * hop:(b + 1) * hop] = self.apply(np.ascontiguousarray(x[:, b * hop:(b + 1) * hop]))
+        return y
+
+
+class MatrixConv(_Base):
+    """saf_matrixConv_create/apply/destroy (reference saf_utility_matrixConv.h:55-86).
+
+    H: [nCHout, nCHin, length_h] float32.  ``shard=(outBegin, outCount)`` builds a handle that owns
+    only those output channels (safconv_matrixConv_create_shard).
+    """
+
+    _destroy_name = "saf_matrixConv_destroy"
+
+    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None):
+        super().__init__()
+        H = np.ascontiguousarray(H, np.float32)
+        self.nCHout, self.nCHin, self.length_h = H.shape
+        self.hop = int(hopSize)
+        if device is not None:
+            self._lib.safconv_set_device(int(device))
+        if shard is None:
+            self.nOutLocal = self.nCHout
+            self._lib.saf_matrixConv_create(C.byref(self._h), self.hop, _fp(H), self.length_h,
+                                            self.nCHin, self.nCHout, int(usePartFLAG))
+        else:
+            ob, oc = shard
+            self.nOutLocal = oc
+            self._lib.safconv_matrixConv_create_shard(C.byref(self._h), self.hop, _fp(H), self.length_h,
+                                                      self.nCHin, self.nCHout, int(ob), int(oc))
+        self._check_created("saf_matrixConv_create")
+
+    def apply(self, inputSigs: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(inputSigs, np.float32)
+        assert x.shape == (self.nCHin, self.hop)
+        y = np.empty((self.nOutLocal, self.hop), np.float32)
+        self._lib.saf_matrixConv_apply(self._h, _fp(x), _fp(y))
+        self._raise_if_error()
+        return y
+
+
+class MultiConv(_Base):
+    """saf_multiConv_create/apply/destroy (reference saf_utility_matrixConv.h:109-136).  H: [nCH, length_h]."""
+
+    _destroy_name = "saf_multiConv_destroy"
+
+    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None):
+        super().__init__()
+        H = np.ascontiguousarray(H, np.float32)
+        self.nCH, self.length_h = H.shape
+        self.hop = int(hopSize)
+        if device is not None:
+            self._lib.safconv_set_device(int(device))
+        if shard is None:
+            self.nOutLocal = self.nCH
+            self._lib.saf_multiConv_create(C.byref(self._h), self.hop, _fp(H), self.length_h, self.nCH, int(usePartFLAG))
+        else:
+            cb, cc = shard
+            self.nOutLocal = cc
+            self._lib.safconv_multiConv_create_shard(C.byref(self._h), self.hop, _fp(H), self.length_h,
+                                                     self.nCH, int(cb), int(cc))
+        self.nCHin = self.nOutLocal
+        self._check_created("saf_multiConv_create")
+
+    def apply(self, inputSigs: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(inputSigs, np.float32)
+        assert x.shape == (self.nOutLocal, self.hop)
+        y = np.empty((self.nOutLocal, self.hop), np.float32)
+        self._lib.saf_multiConv_apply(self._h, _fp(x), _fp(y))
+        self._raise_if_error()
+        return y
+
+
+class TVConv(_Base):
+    """saf_TVConv_create/apply/destroy (reference saf_utility_matrixConv.h:157-190).  H: [nIRs, nCHout, length_h]."""
+
+    _destroy_name = "saf_TVConv_destroy"
+
+    def __init__(self, hopSize: int, H: np.ndarray, initIdx: int = 0, device: int | None = None):
+        super().__init__()
+        H = np.ascontiguousarray(H, np.float32)
+        self.nIRs, self.nCHout, self.length_h = H.shape
+        self.nOutLocal = self.nCHout
+        self.hop = int(hopSize)
+        self._H = H
+        if device is not None:
+            self._lib.safconv_set_device(int(device))
+        rows = (_f32p * self.nIRs)(*[_fp(H[i]) for i in range(self.nIRs)])
+        self._lib.saf_TVConv_create(C.byref(self._h), self.hop, rows, self.length_h, self.nIRs, self.nCHout, int(initIdx))
+        self._check_created("saf_TVConv_create")
+
+    def apply(self, inputSigs: np.ndarray, irIdx: int) -> np.ndarray:
+        x = np.ascontiguousarray(inputSigs, np.float32).reshape(-1)
+        assert x.shape == (self.hop,)
+        y = np.empty((self.nCHout, self.hop), np.float32)
+        self._lib.saf_TVConv_apply(self._h, _fp(x), _fp(y), int(irIdx))
+        self._raise_if_error()
+        return y

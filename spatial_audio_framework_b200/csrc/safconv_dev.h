@@ -1,0 +1,118 @@
+/*
+ * safconv_dev.h -- internal, thin C ABI between the C host layer (safconv_host.c)
+ * and the CUDA layer (safconv_kernels.cu).  Plain ints, sizes and pointers only.
+ *
+ * Terminology:
+ *   N      FFT size (power of two >= max(64, 2*hop)); M = N/2 = complex FFT length
+ *          = number of PACKED bins: bin 0 carries (DC, Nyquist) in (re, im) - both are
+ *          purely real for real signals (reference: kiss_fftr.c:99-104, 137-138).
+ *   kt     bin tile of SC_BK = 32 packed bins (256 bytes of float2)
+ *   p      filter partition (0 = newest), P = ceil(length_h / hop)
+ *   slot   ring position of a block spectrum in the frequency-domain delay line (FDL)
+ *   ot     output tile (<= 64 output channels), OTsz outputs per tile
+ *   unit   one (ot, kt, p): nIn x OTsz rows of 32 bins of H, contiguous in memory
+ *   stage  SNI input channels of a unit = one TMA transaction of the MAC pipeline
+ *   group  one (ot, kt): the P*SPU stages whose sum is one tile of the output spectrum
+ */
+#ifndef SAFCONV_DEV_H_INCLUDED
+#define SAFCONV_DEV_H_INCLUDED
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_BK            32      /* packed bins per tile                                   */
+#define SC_MAX_OT        64      /* output channels per tile                               */
+#define SC_MAC_CWARPS    8       /* consumer warps of the MAC kernel (+1 producer warp)    */
+#define SC_MAC_NSTAGES   4       /* TMA pipeline depth                                     */
+#define SC_STAGE_H_BYTES 32768   /* target bytes of H per stage                            */
+#define SC_MAX_SNI       32      /* max input channels per stage                           */
+#define SC_MAX_M         8192    /* max complex FFT length (hop <= 8192)                   */
+
+enum { SC_KIND_MATRIX = 0, SC_KIND_MULTI = 1, SC_KIND_TV = 2 };
+
+typedef struct scdev_plan {
+    int kind;
+    int hop, len, nIn, nOutLocal;
+    int N, M, logM, P;
+    int fftThreads;
+    /* matrix MAC geometry */
+    int nKT, nOT, OTsz;
+    int SNI, SPU;            /* inputs per stage, stages per unit            */
+    int R, WGo, WGk;         /* outputs per thread, warp groups over outputs / over rows */
+    long long totalStages;
+    int macGrid;
+    int nGroups, nSlots;
+    int macHints;            /* 0/1: L2 eviction-priority hints              */
+    int macSmemBytes;
+    /* time-varying convolver */
+    int nIRs;
+} scdev_plan;
+
+typedef struct scdev_bufs {
+    /* all device pointers */
+    void*  tw;        /* float2[M]        W_N^j                                            */
+    void*  H;         /* float2: matrix [nOT][nKT][P][nIn][OTsz][32]; multi [nCH][P][M];    */
+                      /*         tv     [nIRs][nOut][P][M]                                  */
+    void*  X;         /* float2: matrix [nKT][P][nIn][32];            multi [nCH][P][M];    */
+                      /*         tv     [P][M]                                              */
+    void*  Zp;        /* float2[nSlots][OTsz][32]  split-K partial output spectra (matrix)  */
+    float* tail;      /* float[nOutLocal][hop]     overlap-add tails                        */
+    float* tail2;     /* tv only: y_n_overlap_last                                          */
+    unsigned int* counters; /* [0] block counter, [1] last-CTA ticket                       */
+    int*   ctaBase;   /* int[macGrid]   first partial slot of each MAC CTA                  */
+    int*   grpStart;  /* int[nGroups+1]                                                     */
+    int*   grpList;   /* int[nSlots]    partial slots contributing to each group            */
+} scdev_bufs;
+
+/* --- device / memory / stream plumbing (all return 0 on success, else a cudaError_t value) --- */
+int  scdev_device_count(int* n);
+int  scdev_set_device(int dev);
+int  scdev_get_device(int* dev);
+int  scdev_device_props(int dev, int* smCount, int* maxSmemOptin, int* ccMajor, int* ccMinor);
+int  scdev_malloc(void** p, size_t bytes);
+int  scdev_free(void* p);
+int  scdev_host_alloc(void** p, size_t bytes);
+int  scdev_host_free(void* p);
+int  scdev_memset_async(void* p, int v, size_t bytes, void* stream);
+int  scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream);
+int  scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream);
+int  scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes);
+int  scdev_stream_create(void** s);
+int  scdev_stream_destroy(void* s);
+int  scdev_stream_sync(void* s);
+int  scdev_event_create(void** e);
+int  scdev_event_destroy(void* e);
+int  scdev_event_record(void* e, void* stream);
+int  scdev_event_sync(void* e);
+int  scdev_event_elapsed_ms(void* e0, void* e1, float* ms);
+int  scdev_graph_begin(void* stream);
+int  scdev_graph_end(void* stream, void** graphExec);
+int  scdev_graph_launch(void* graphExec, void* stream);
+int  scdev_graph_destroy(void* graphExec);
+const char* scdev_error_string(int err);
+
+/* --- kernels --- */
+/* one-time opt-in of >48 KB dynamic shared memory etc. for this plan */
+int  scdev_prepare(const scdev_plan* pl);
+/* K0: partition + forward real FFT of the time-domain filters d_h (matrix: [nOutLocal][nIn][len],
+ * multi: [nCH][len], tv: [nIRs][nOut][len]) into bufs->H */
+int  scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const float* d_h, void* stream);
+/* K1: forward real FFT of the new input block d_in [nIn][hop] into FDL slot (counter % P) */
+int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, void* stream);
+/* K2: filter-streaming complex multiply-accumulate over partitions x inputs (matrix) */
+int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, void* stream);
+/* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ */
+int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
+/* multiConv: K1+K2+K3 fused, one CTA per channel */
+int  scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream);
+/* TVConv: 1-input FFT + (1..3) IR MACs + cross-fade, one CTA per output channel */
+int  scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out,
+                    int irIdx, int irLast, int irLast2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,673 @@
+/*
+ * safconv_host.c -- C host layer of libsafconv_b200.so
+ *
+ * Implements the reference's convolver API
+ *   /root/reference/framework/modules/saf_utilities/saf_utility_matrixConv.h:55-190
+ * (saf_matrixConv_*, saf_multiConv_*, saf_TVConv_*) on top of the thin C-ABI CUDA
+ * layer declared in safconv_dev.h.  This file contains no CUDA code: it validates
+ * arguments, derives the execution plan (FFT size, partition count, MAC tiling and
+ * split-K work distribution), owns the handle and its device buffers, and sequences
+ * the per-block launches.  There is no CPU compute path: if the device layer fails,
+ * the error is recorded and create() leaves *phMC == NULL.
+ */
+#include "../../include/safconv_b200.h"
+#include "safconv_dev.h"
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SAFCONV_MAGIC 0x5AFC0B20u
+#define SAFCONV_VERSION_STRING "safconv-b200 0.1 (sm_100a; matrixConv/multiConv/TVConv)"
+
+typedef struct safconv_handle {
+    uint32_t   magic;
+    int        err;
+    char       errmsg[256];
+    scdev_plan pl;
+    scdev_bufs b;
+    int        device, smCount, maxSmem;
+    int        nCHoutTotal, outBegin;
+    void*      streamOwn;
+    void*      stream;
+    float     *d_in, *d_out;         /* device staging for the host-pointer API  */
+    float     *h_in, *h_out;         /* pinned host staging                      */
+    size_t     inBytes, outBytes;
+    size_t     bytesH, bytesX, bytesZp;
+    int        useGraph;
+    void*      graphExec;
+    int        timingCap, timingCount;   /* ring of 4 CUDA events per block while kernel timing is enabled */
+    void**     evRing;
+    int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
+} safconv_handle;
+
+static __thread int  tl_err = 0;
+static __thread char tl_msg[256] = "";
+static __thread int  tl_device = -1;
+
+static void set_tl_error(int code, const char* fmt, const char* detail)
+{
+    tl_err = code;
+    snprintf(tl_msg, sizeof tl_msg, fmt, detail ? detail : "");
+}
+
+static int h_fail(safconv_handle* h, int code, const char* what, int cudaErr)
+{
+    char buf[256];
+    if (cudaErr) snprintf(buf, sizeof buf, "%s: %s", what, scdev_error_string(cudaErr));
+    else         snprintf(buf, sizeof buf, "%s", what);
+    if (h) { h->err = code; snprintf(h->errmsg, sizeof h->errmsg, "%s", buf); }
+    set_tl_error(code, "%s", buf);
+    return code;
+}
+
+#define DEV_TRY(h, call, what) do { int e__ = (call); if (e__) { h_fail((h), SAFCONV_ERR_CUDA, (what), e__); goto fail; } } while (0)
+
+static safconv_handle* as_handle(void* p)
+{
+    safconv_handle* h = (safconv_handle*)p;
+    return (h && h->magic == SAFCONV_MAGIC) ? h : NULL;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  planning                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+/* FFT size: the reference uses exactly 2*hop (saf_utility_matrixConv.c:100); we need a power of two,
+ * so N = nextpow2(max(64, 2*hop)).  For a power-of-two hop >= 32 this is the reference's size; for any
+ * other hop the transform is longer than needed, which leaves the linear convolution unchanged
+ * (hop + hop - 1 <= N) -- only the first 2*hop output samples are used. */
+static void plan_fft(scdev_plan* pl, int hop, int len)
+{
+    int N = 64;
+    while (N < 2 * hop) N <<= 1;
+    pl->hop = hop; pl->len = len;
+    pl->N = N; pl->M = N / 2; pl->logM = ilog2(pl->M);
+    pl->P = (int)ceilf((float)len / (float)hop);           /* reference .c:102 */
+    if (pl->P < 1) pl->P = 1;
+    int t = pl->M / 4;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    pl->fftThreads = t;
+}
+
+/* MAC tiling + even split of all pipeline stages over `grid` CTAs */
+static void plan_mac(scdev_plan* pl, int smCount)
+{
+    const int nOut = pl->nOutLocal;
+    pl->nKT  = pl->M / SC_BK;
+    pl->nOT  = (nOut + SC_MAX_OT - 1) / SC_MAX_OT;
+    pl->OTsz = (nOut + pl->nOT - 1) / pl->nOT;
+    int R = 1;
+    while (SC_MAC_CWARPS * R < pl->OTsz) R <<= 1;
+    pl->R   = R;
+    pl->WGo = (pl->OTsz + R - 1) / R;
+    int sni = SC_STAGE_H_BYTES / (pl->OTsz * SC_BK * 8);
+    if (sni < 1) sni = 1;
+    if (sni > SC_MAX_SNI) sni = SC_MAX_SNI;
+    if (sni > pl->nIn) sni = pl->nIn;
+    pl->SNI = sni;
+    pl->SPU = (pl->nIn + sni - 1) / sni;
+    int wgk = SC_MAC_CWARPS / pl->WGo;
+    if (wgk < 1) wgk = 1;
+    if (wgk > sni) wgk = sni;
+    pl->WGk = wgk;
+    pl->nGroups = pl->nOT * pl->nKT;
+    pl->totalStages = (long long)pl->nGroups * pl->P * pl->SPU;
+    long long g = smCount;
+    if (g > pl->totalStages) g = pl->totalStages;
+    pl->macGrid = (int)g;
+    pl->macSmemBytes = SC_MAC_NSTAGES * (pl->SNI * pl->OTsz * SC_BK * 8 + pl->SNI * SC_BK * 8)
+                     + SC_MAC_CWARPS * R * 32 * 8 + 2 * SC_MAC_NSTAGES * 8;
+}
+
+/* split-K bookkeeping: CTA c streams stages [c*T/G, (c+1)*T/G); every (ot,kt) group it touches gets
+ * one partial tile.  ctaBase[c] = first partial slot of CTA c; grpStart/grpList = CSR list of the
+ * partial slots that K3 sums for each group.  Returns the number of slots, or -1 on malloc failure. */
+static int build_split_tables(const scdev_plan* pl, int** ctaBaseOut, int** grpStartOut, int** grpListOut)
+{
+    const long long T = pl->totalStages, spg = (long long)pl->P * pl->SPU;
+    const int G = pl->macGrid, nG = pl->nGroups;
+    int* ctaBase = (int*)malloc(sizeof(int) * (size_t)(G + 1));
+    int* cnt     = (int*)calloc((size_t)nG + 1, sizeof(int));
+    if (!ctaBase || !cnt) { free(ctaBase); free(cnt); return -1; }
+    int slots = 0;
+    for (int c = 0; c < G; c++) {
+        const long long s0 = T * c / G, s1 = T * (c + 1) / G;
+        ctaBase[c] = slots;
+        if (s1 > s0) {
+            const long long g0 = s0 / spg, g1 = (s1 - 1) / spg;
+            for (long long g = g0; g <= g1; g++) cnt[g]++;
+            slots += (int)(g1 - g0 + 1);
+        }
+    }
+    ctaBase[G] = slots;
+    int* grpStart = (int*)malloc(sizeof(int) * (size_t)(nG + 1));
+    int* grpList  = (int*)malloc(sizeof(int) * (size_t)(slots > 0 ? slots : 1));
+    int* fill     = (int*)calloc((size_t)nG + 1, sizeof(int));
+    if (!grpStart || !grpList || !fill) { free(ctaBase); free(cnt); free(grpStart); free(grpList); free(fill); return -1; }
+    grpStart[0] = 0;
+    for (int g = 0; g < nG; g++) grpStart[g + 1] = grpStart[g] + cnt[g];
+    for (int c = 0; c < G; c++) {
+        const long long s0 = T * c / G, s1 = T * (c + 1) / G;
+        if (s1 <= s0) continue;
+        const long long g0 = s0 / spg, g1 = (s1 - 1) / spg;
+        for (long long g = g0; g <= g1; g++) grpList[grpStart[g] + fill[g]++] = ctaBase[c] + (int)(g - g0);
+    }
+    free(cnt); free(fill);
+    *ctaBaseOut = ctaBase; *grpStartOut = grpStart; *grpListOut = grpList;
+    return slots;
+}
+
+/* exported for the host-logic unit tests (tests/test_plan.py): fills the plan exactly as create() does */
+int safconv_debug_plan(int kind, int hop, int len, int nIn, int nOutLocal, int smCount, scdev_plan* out,
+                       int* ctaBase /* >= smCount+1 */, int* grpStart, int* grpList, int cap)
+{
+    scdev_plan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.kind = kind; pl.nIn = nIn; pl.nOutLocal = nOutLocal;
+    plan_fft(&pl, hop, len);
+    if (kind == SC_KIND_MATRIX) {
+        plan_mac(&pl, smCount);
+        int *a = NULL, *b = NULL, *c = NULL;
+        const int slots = build_split_tables(&pl, &a, &b, &c);
+        if (slots < 0) return -1;
+        pl.nSlots = slots;
+        if (ctaBase && grpStart && grpList && slots <= cap && pl.nGroups + 1 <= cap && pl.macGrid + 1 <= cap) {
+            memcpy(ctaBase, a, sizeof(int) * (size_t)(pl.macGrid + 1));
+            memcpy(grpStart, b, sizeof(int) * (size_t)(pl.nGroups + 1));
+            memcpy(grpList, c, sizeof(int) * (size_t)slots);
+        }
+        free(a); free(b); free(c);
+    }
+    *out = pl;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  create / destroy                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+static void handle_free(safconv_handle* h)
+{
+    if (!h) return;
+    if (h->device >= 0) scdev_set_device(h->device);
+    if (h->stream) scdev_stream_sync(h->stream);
+    scdev_graph_destroy(h->graphExec);
+    if (h->evRing) { for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]); free(h->evRing); }
+    scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp);
+    scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
+    scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart); scdev_free(h->b.grpList);
+    scdev_free(h->d_in); scdev_free(h->d_out);
+    scdev_host_free(h->h_in); scdev_host_free(h->h_out);
+    scdev_stream_destroy(h->streamOwn);
+    h->magic = 0;
+    free(h);
+}
+
+static int upload(safconv_handle* h, void** dptr, const void* src, size_t bytes, const char* what)
+{
+    int e = scdev_malloc(dptr, bytes);
+    if (e) return h_fail(h, SAFCONV_ERR_NOMEM, what, e);
+    e = scdev_memcpy_h2d_sync(*dptr, src, bytes);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, what, e);
+    return 0;
+}
+
+static int zalloc(safconv_handle* h, void** dptr, size_t bytes, const char* what)
+{
+    int e = scdev_malloc(dptr, bytes);
+    if (e) return h_fail(h, SAFCONV_ERR_NOMEM, what, e);
+    e = scdev_memset_async(*dptr, 0, bytes ? bytes : 16, h->stream);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, what, e);
+    return 0;
+}
+
+/* Common constructor.  `rows` time-domain FIRs of `len` taps are given as `nChunks` host chunks
+ * (chunk i holds rowsPerChunk rows) so that TVConv's float** and the flat layouts share one path. */
+static safconv_handle* conv_create(int kind, int hop, const float* const* chunks, int nChunks, size_t rowsPerChunk,
+                                   int len, int nIn, int nOutLocal, int nOutTotal, int outBegin, int nIRs)
+{
+    tl_err = 0; tl_msg[0] = 0;
+    if (hop < 1 || hop > SC_MAX_M || (kind == SC_KIND_TV && hop > SC_MAX_M / 2) || len < 1 || nIn < 1 || nOutLocal < 1 || !chunks) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s (need 1 <= hopSize <= 8192, length_h >= 1, channels >= 1, H != NULL)", "");
+        return NULL;
+    }
+    int ndev = 0;
+    if (scdev_device_count(&ndev) != 0 || ndev < 1) {
+        set_tl_error(SAFCONV_ERR_NO_DEVICE, "no usable CUDA device%s (libsafconv_b200 has no CPU fallback)", "");
+        return NULL;
+    }
+    safconv_handle* h = (safconv_handle*)calloc(1, sizeof *h);
+    if (!h) { set_tl_error(SAFCONV_ERR_NOMEM, "out of host memory%s", ""); return NULL; }
+    h->magic = SAFCONV_MAGIC;
+    h->device = -1;
+    h->nCHoutTotal = nOutTotal; h->outBegin = outBegin;
+
+    int dev = tl_device;
+    if (dev < 0) DEV_TRY(h, scdev_get_device(&dev), "cudaGetDevice");
+    DEV_TRY(h, scdev_set_device(dev), "cudaSetDevice");
+    h->device = dev;
+    int ccMaj = 0, ccMin = 0;
+    DEV_TRY(h, scdev_device_props(dev, &h->smCount, &h->maxSmem, &ccMaj, &ccMin), "device properties");
+    DEV_TRY(h, scdev_stream_create(&h->streamOwn), "cudaStreamCreate");
+    h->stream = h->streamOwn;
+
+    scdev_plan* pl = &h->pl;
+    pl->kind = kind; pl->nIn = nIn; pl->nOutLocal = nOutLocal; pl->nIRs = nIRs;
+    plan_fft(pl, hop, len);
+    pl->macHints = 1;
+
+    const size_t M = (size_t)pl->M, P = (size_t)pl->P;
+    /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
+    {
+        float* tw = (float*)malloc(sizeof(float) * 2 * M);
+        if (!tw) { h_fail(h, SAFCONV_ERR_NOMEM, "twiddle table", 0); goto fail; }
+        for (size_t j = 0; j < M; j++) {
+            const double ph = -2.0 * 3.141592653589793238462643383279502884 * (double)j / (double)pl->N;
+            tw[2 * j] = (float)cos(ph);
+            tw[2 * j + 1] = (float)sin(ph);
+        }
+        int e = upload(h, &h->b.tw, tw, sizeof(float) * 2 * M, "twiddle upload");
+        free(tw);
+        if (e) goto fail;
+    }
+
+    size_t rowsTotal;
+    if (kind == SC_KIND_MATRIX) {
+        plan_mac(pl, h->smCount);
+        if (pl->macSmemBytes > h->maxSmem) { h_fail(h, SAFCONV_ERR_CUDA, "MAC pipeline does not fit in shared memory", 0); goto fail; }
+        int *ctaBase = NULL, *grpStart = NULL, *grpList = NULL;
+        const int slots = build_split_tables(pl, &ctaBase, &grpStart, &grpList);
+        if (slots < 0) { h_fail(h, SAFCONV_ERR_NOMEM, "split tables", 0); goto fail; }
+        pl->nSlots = slots;
+        int e = upload(h, (void**)&h->b.ctaBase, ctaBase, sizeof(int) * (size_t)(pl->macGrid + 1), "ctaBase upload");
+        if (!e) e = upload(h, (void**)&h->b.grpStart, grpStart, sizeof(int) * (size_t)(pl->nGroups + 1), "grpStart upload");
+        if (!e) e = upload(h, (void**)&h->b.grpList, grpList, sizeof(int) * (size_t)(slots > 0 ? slots : 1), "grpList upload");
+        free(ctaBase); free(grpStart); free(grpList);
+        if (e) goto fail;
+        h->bytesH  = (size_t)pl->nOT * pl->nKT * P * nIn * pl->OTsz * SC_BK * 8;
+        h->bytesX  = (size_t)pl->nKT * P * nIn * SC_BK * 8;
+        h->bytesZp = (size_t)slots * pl->OTsz * SC_BK * 8;
+        rowsTotal  = (size_t)nOutLocal * nIn;
+    } else if (kind == SC_KIND_MULTI) {
+        h->bytesH = (size_t)nOutLocal * P * M * 8;
+        h->bytesX = h->bytesH;
+        rowsTotal = (size_t)nOutLocal;
+    } else {
+        h->bytesH = (size_t)nIRs * nOutLocal * P * M * 8;
+        h->bytesX = P * M * 8;
+        rowsTotal = (size_t)nIRs * nOutLocal;
+    }
+    DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
+
+    if (zalloc(h, &h->b.H, h->bytesH, "filter spectra allocation")) goto fail;
+    if (zalloc(h, &h->b.X, h->bytesX, "delay line allocation")) goto fail;
+    if (kind == SC_KIND_MATRIX && zalloc(h, &h->b.Zp, h->bytesZp, "partial spectra allocation")) goto fail;
+    if (zalloc(h, (void**)&h->b.tail, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails")) goto fail;
+    if (kind == SC_KIND_TV && zalloc(h, (void**)&h->b.tail2, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails (last)")) goto fail;
+    if (zalloc(h, (void**)&h->b.counters, 4 * sizeof(unsigned int), "counters")) goto fail;
+
+    h->inBytes  = sizeof(float) * (size_t)nIn * hop;
+    h->outBytes = sizeof(float) * (size_t)nOutLocal * hop;
+    if (kind == SC_KIND_TV) h->inBytes = sizeof(float) * (size_t)hop;
+    if (zalloc(h, (void**)&h->d_in, h->inBytes, "input staging")) goto fail;
+    if (zalloc(h, (void**)&h->d_out, h->outBytes, "output staging")) goto fail;
+    DEV_TRY(h, scdev_host_alloc((void**)&h->h_in, h->inBytes), "pinned input staging");
+    DEV_TRY(h, scdev_host_alloc((void**)&h->h_out, h->outBytes), "pinned output staging");
+
+    /* K0: upload the time-domain filters once and transform them on the device (reference .c:116-125) */
+    {
+        float* d_h = NULL;
+        const size_t rowBytes = sizeof(float) * (size_t)len;
+        int e = scdev_malloc((void**)&d_h, rowsTotal * rowBytes);
+        if (e) { h_fail(h, SAFCONV_ERR_NOMEM, "time-domain filter upload buffer", e); goto fail; }
+        for (int c = 0; c < nChunks && !e; c++)
+            e = scdev_memcpy_h2d_sync((char*)d_h + (size_t)c * rowsPerChunk * rowBytes, chunks[c], rowsPerChunk * rowBytes);
+        if (!e) e = scdev_filter_transform(pl, &h->b, d_h, h->stream);
+        if (!e) e = scdev_stream_sync(h->stream);
+        scdev_free(d_h);
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "filter transform", e); goto fail; }
+    }
+    return h;
+
+fail:
+    handle_free(h);
+    return NULL;
+}
+
+static void conv_destroy(void** const ph)
+{
+    if (!ph) return;
+    safconv_handle* h = as_handle(*ph);
+    if (h) handle_free(h);
+    *ph = NULL;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  per-block sequencing                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out)
+{
+    const scdev_plan* pl = &h->pl;
+    void** ev = NULL;
+    if (h->timingCap && h->timingCount < h->timingCap) ev = h->evRing + 4 * (size_t)(h->timingCount++);
+    int e = 0;
+    if (pl->kind == SC_KIND_MATRIX) {
+        if (ev) scdev_event_record(ev[0], h->stream);
+        e = scdev_input_fft(pl, &h->b, d_in, h->stream);
+        if (ev) scdev_event_record(ev[1], h->stream);
+        if (!e) e = scdev_mac(pl, &h->b, h->stream);
+        if (ev) scdev_event_record(ev[2], h->stream);
+        if (!e) e = scdev_ifft_ola(pl, &h->b, d_out, h->stream);
+        if (ev) scdev_event_record(ev[3], h->stream);
+    } else if (pl->kind == SC_KIND_MULTI) {
+        if (ev) scdev_event_record(ev[1], h->stream);
+        e = scdev_multi_fused(pl, &h->b, d_in, d_out, h->stream);
+        if (ev) scdev_event_record(ev[2], h->stream);
+    } else {
+        return (int)SAFCONV_ERR_ARG;
+    }
+    return e;
+}
+
+/* host-pointer apply: pinned staging -> H2D -> kernels -> D2H -> sync (reference semantics: synchronous) */
+static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
+{
+    int e = scdev_set_device(h->device);
+    if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
+    memcpy(h->h_in, in, h->inBytes);
+    if (h->useGraph && h->pl.kind != SC_KIND_TV) {
+        if (!h->graphExec) {
+            e = scdev_graph_begin(h->stream);
+            if (!e) e = scdev_memcpy_h2d_async(h->d_in, h->h_in, h->inBytes, h->stream);
+            if (!e) e = enqueue_block(h, h->d_in, h->d_out);
+            if (!e) e = scdev_memcpy_d2h_async(h->h_out, h->d_out, h->outBytes, h->stream);
+            int e2 = scdev_graph_end(h->stream, &h->graphExec);
+            if (!e) e = e2;
+            if (e) { h->graphExec = NULL; h->useGraph = 0; h_fail(h, SAFCONV_ERR_CUDA, "graph capture", e); return; }
+        }
+        e = scdev_graph_launch(h->graphExec, h->stream);
+    } else {
+        e = scdev_memcpy_h2d_async(h->d_in, h->h_in, h->inBytes, h->stream);
+        if (!e) {
+            if (h->pl.kind == SC_KIND_TV) {
+                e = scdev_tv_fused(&h->pl, &h->b, h->d_in, h->d_out, irIdx, h->tvLast, h->tvLast2, h->stream);
+                h->tvLast2 = h->tvLast;                      /* reference .c:618-619 */
+                h->tvLast  = irIdx;
+            } else {
+                e = enqueue_block(h, h->d_in, h->d_out);
+            }
+        }
+        if (!e) e = scdev_memcpy_d2h_async(h->h_out, h->d_out, h->outBytes, h->stream);
+    }
+    if (!e) e = scdev_stream_sync(h->stream);
+    if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
+    memcpy(out, h->h_out, h->outBytes);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  drop-in API                                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCHin, int nCHout, int usePartFLAG)
+{
+    (void)usePartFLAG;   /* both reference modes compute the same linear convolution; one engine serves both */
+    if (!phMC) return;
+    const float* chunk = H;
+    *phMC = conv_create(SC_KIND_MATRIX, hopSize, H ? &chunk : NULL, 1,
+                        (size_t)(nCHout > 0 ? nCHout : 0) * (size_t)(nCHin > 0 ? nCHin : 0),
+                        length_h, nCHin, nCHout, nCHout, 0, 0);
+}
+
+void safconv_matrixConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
+                                     int nCHin, int nCHout, int outBegin, int outCount)
+{
+    if (!phMC) return;
+    if (!H || outBegin < 0 || outCount < 1 || outBegin + outCount > nCHout || nCHin < 1 || length_h < 1) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid shard%s", "");
+        *phMC = NULL;
+        return;
+    }
+    const float* chunk = H + (size_t)outBegin * nCHin * length_h;
+    *phMC = conv_create(SC_KIND_MATRIX, hopSize, &chunk, 1, (size_t)outCount * nCHin,
+                        length_h, nCHin, outCount, nCHout, outBegin, 0);
+}
+
+void saf_matrixConv_destroy(void** const phMC) { conv_destroy(phMC); }
+
+void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
+{
+    safconv_handle* h = as_handle(hMC);
+    if (!h || h->pl.kind != SC_KIND_MATRIX || !inputSigs || !outputSigs) return;
+    conv_apply_host(h, inputSigs, outputSigs, 0);
+}
+
+void saf_multiConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCH, int usePartFLAG)
+{
+    (void)usePartFLAG;
+    if (!phMC) return;
+    const float* chunk = H;
+    *phMC = conv_create(SC_KIND_MULTI, hopSize, H ? &chunk : NULL, 1, (size_t)(nCH > 0 ? nCH : 0),
+                        length_h, nCH, nCH, nCH, 0, 0);
+}
+
+void safconv_multiConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
+                                    int nCH, int chBegin, int chCount)
+{
+    if (!phMC) return;
+    if (!H || chBegin < 0 || chCount < 1 || chBegin + chCount > nCH || length_h < 1) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid shard%s", "");
+        *phMC = NULL;
+        return;
+    }
+    const float* chunk = H + (size_t)chBegin * length_h;
+    *phMC = conv_create(SC_KIND_MULTI, hopSize, &chunk, 1, (size_t)chCount, length_h, chCount, chCount, nCH, chBegin, 0);
+}
+
+void saf_multiConv_destroy(void** const phMC) { conv_destroy(phMC); }
+
+void saf_multiConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
+{
+    safconv_handle* h = as_handle(hMC);
+    if (!h || h->pl.kind != SC_KIND_MULTI || !inputSigs || !outputSigs) return;
+    conv_apply_host(h, inputSigs, outputSigs, 0);
+}
+
+void saf_TVConv_create(void** const phTVC, int hopSize, float** H, int length_h, int nIRs, int nCHout, int initIdx)
+{
+    if (!phTVC) return;
+    if (!H || nIRs < 1 || nCHout < 1) { set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s", ""); *phTVC = NULL; return; }
+    for (int i = 0; i < nIRs; i++)
+        if (!H[i]) { set_tl_error(SAFCONV_ERR_ARG, "H[i] is NULL%s", ""); *phTVC = NULL; return; }
+    safconv_handle* h = conv_create(SC_KIND_TV, hopSize, (const float* const*)H, nIRs, (size_t)nCHout,
+                                    length_h, 1, nCHout, nCHout, 0, nIRs);
+    if (h) h->tvLast = h->tvLast2 = (initIdx >= 0 && initIdx < nIRs) ? initIdx : 0;   /* reference .c:459-465 */
+    *phTVC = h;
+}
+
+void saf_TVConv_destroy(void** const phTVC) { conv_destroy(phTVC); }
+
+void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int irIdx)
+{
+    safconv_handle* h = as_handle(hTVC);
+    if (!h || h->pl.kind != SC_KIND_TV || !inputSigs || !outputSigs) return;
+    if (irIdx < 0 || irIdx >= h->pl.nIRs) { h_fail(h, SAFCONV_ERR_ARG, "irIdx out of range", 0); return; }
+    conv_apply_host(h, inputSigs, outputSigs, irIdx);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  extension API                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+int safconv_last_error(void* hp)
+{
+    safconv_handle* h = as_handle(hp);
+    return h ? h->err : tl_err;
+}
+
+const char* safconv_last_error_string(void* hp)
+{
+    safconv_handle* h = as_handle(hp);
+    return h ? h->errmsg : tl_msg;
+}
+
+const char* safconv_version(void) { return SAFCONV_VERSION_STRING; }
+
+int safconv_set_device(int device)
+{
+    int n = 0;
+    if (scdev_device_count(&n) != 0 || device < 0 || device >= n) return SAFCONV_ERR_NO_DEVICE;
+    tl_device = device;
+    return SAFCONV_OK;
+}
+
+int safconv_apply_device(void* hp, const float* d_in, float* d_out)
+{
+    return safconv_apply_device_blocks(hp, d_in, d_out, 1);
+}
+
+int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int nBlocks)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
+    int e = scdev_set_device(h->device);
+    const size_t inStride = (size_t)h->pl.nIn * h->pl.hop, outStride = (size_t)h->pl.nOutLocal * h->pl.hop;
+    for (int b = 0; b < nBlocks && !e; b++)
+        e = enqueue_block(h, d_in + (size_t)b * inStride, d_out + (size_t)b * outStride);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "apply_device", e);
+    return SAFCONV_OK;
+}
+
+int safconv_set_stream(void* hp, void* cudaStream)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    scdev_stream_sync(h->stream);
+    if (h->graphExec) { scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }
+    h->stream = cudaStream ? cudaStream : h->streamOwn;
+    return SAFCONV_OK;
+}
+
+void* safconv_get_stream(void* hp)
+{
+    safconv_handle* h = as_handle(hp);
+    return h ? h->stream : NULL;
+}
+
+int safconv_synchronize(void* hp)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    int e = scdev_stream_sync(h->stream);
+    return e ? h_fail(h, SAFCONV_ERR_CUDA, "synchronize", e) : SAFCONV_OK;
+}
+
+int safconv_reset_state(void* hp)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    int e = scdev_memset_async(h->b.X, 0, h->bytesX, h->stream);
+    if (!e) e = scdev_memset_async(h->b.tail, 0, sizeof(float) * (size_t)h->pl.nOutLocal * h->pl.hop, h->stream);
+    if (!e && h->b.tail2) e = scdev_memset_async(h->b.tail2, 0, sizeof(float) * (size_t)h->pl.nOutLocal * h->pl.hop, h->stream);
+    if (!e) e = scdev_memset_async(h->b.counters, 0, 4 * sizeof(unsigned int), h->stream);
+    if (!e) e = scdev_stream_sync(h->stream);
+    return e ? h_fail(h, SAFCONV_ERR_CUDA, "reset_state", e) : SAFCONV_OK;
+}
+
+int safconv_get_info(void* hp, safconv_info* info)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !info) return SAFCONV_ERR_ARG;
+    const scdev_plan* pl = &h->pl;
+    memset(info, 0, sizeof *info);
+    info->kind = pl->kind; info->hopSize = pl->hop; info->length_h = pl->len;
+    info->nCHin = pl->nIn; info->nCHout = h->nCHoutTotal; info->nOutLocal = pl->nOutLocal; info->outBegin = h->outBegin;
+    info->fftSize = pl->N; info->nBinsPacked = pl->M; info->numFilterBlocks = pl->P;
+    info->macGrid = pl->macGrid; info->macStages = SC_MAC_NSTAGES; info->macThreads = (SC_MAC_CWARPS + 1) * 32;
+    info->device = h->device;
+    info->bytesFilters = h->bytesH; info->bytesDelayLine = h->bytesX;
+    /* algorithmic bytes per block, nBins = hop + 1 complex bins of 8 bytes */
+    const double nb = (double)pl->hop + 1.0, P = pl->P, hop = pl->hop;
+    if (pl->kind == SC_KIND_MATRIX) {
+        const double nIn = pl->nIn, nOut = pl->nOutLocal;
+        info->algBytesPerBlock    = 8.0 * nb * nIn * (nOut * P + P + 1.0) + 4.0 * hop * (nIn + nOut) + 8.0 * hop * nOut;
+        info->macAlgBytesPerBlock = 8.0 * nb * nIn * (nOut * P + P);
+    } else if (pl->kind == SC_KIND_MULTI) {
+        const double nCH = pl->nOutLocal;
+        info->algBytesPerBlock    = 8.0 * nb * nCH * (2.0 * P + 1.0) + 4.0 * hop * nCH * 4.0;
+        info->macAlgBytesPerBlock = 8.0 * nb * nCH * 2.0 * P;
+    }
+    return SAFCONV_OK;
+}
+
+int safconv_enable_kernel_timing(void* hp, int nBlocks)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || nBlocks < 0) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    scdev_stream_sync(h->stream);
+    if (h->evRing) {
+        for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]);
+        free(h->evRing);
+        h->evRing = NULL;
+    }
+    h->timingCap = h->timingCount = 0;
+    if (nBlocks == 0) return SAFCONV_OK;
+    h->evRing = (void**)calloc((size_t)4 * nBlocks, sizeof(void*));
+    if (!h->evRing) return h_fail(h, SAFCONV_ERR_NOMEM, "event ring", 0);
+    for (int i = 0; i < 4 * nBlocks; i++) {
+        int e = scdev_event_create(&h->evRing[i]);
+        if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaEventCreate", e);
+    }
+    h->timingCap = nBlocks;
+    return SAFCONV_OK;
+}
+
+int safconv_get_kernel_times(void* hp, float ms[3], int* nBlocksOut)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !ms || !h->timingCap) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    ms[0] = ms[1] = ms[2] = 0.f;
+    const int n = h->timingCount;
+    if (nBlocksOut) *nBlocksOut = n;
+    if (n == 0) return SAFCONV_OK;
+    const int matrix = (h->pl.kind == SC_KIND_MATRIX);
+    int e = scdev_event_sync(h->evRing[4 * (size_t)(n - 1) + (matrix ? 3 : 2)]);
+    double acc[3] = { 0, 0, 0 };
+    for (int b = 0; b < n && !e; b++) {
+        void** ev = h->evRing + 4 * (size_t)b;
+        float t = 0.f;
+        if (matrix) {
+            e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t;
+            if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
+            if (!e) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
+        } else {
+            e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t;
+        }
+    }
+    h->timingCount = 0;
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "kernel timing", e);
+    for (int i = 0; i < 3; i++) ms[i] = (float)(acc[i] / n);
+    return SAFCONV_OK;
+}
+
+int safconv_set_option(void* hp, const char* name, int value)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !name) return SAFCONV_ERR_ARG;
+    if (!strcmp(name, "mac_hints")) { h->pl.macHints = value ? 1 : 0; }
+    else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
+    else return SAFCONV_ERR_ARG;
+    if (h->graphExec) { scdev_set_device(h->device); scdev_stream_sync(h->stream); scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }
+    return SAFCONV_OK;
+}

@@ -1,0 +1,898 @@
+/*
+ * safconv_kernels.cu -- sm_100a kernels + thin C-ABI CUDA layer of libsafconv_b200.so
+ *
+ * Hot path of saf_matrixConv_apply / saf_multiConv_apply / saf_TVConv_apply
+ * (reference: /root/reference/framework/modules/saf_utilities/saf_utility_matrixConv.c:209-235,
+ * 388-413, 546-620), re-designed for B200:
+ *
+ *   K0  filter_fft_kernel   create-time: partition the FIRs, forward real FFT, store the
+ *                           spectra in the streaming layout of the MAC          (.c:116-125)
+ *   K1  input_fft_kernel    per block: forward real FFT of the nIn input blocks into the
+ *                           newest slot of the frequency-domain delay line ring (.c:211-215)
+ *   K2  mac_kernel          per block: Z[no][k] = sum_p sum_ni H[no][p][ni][k] * X[t-p][ni][k]
+ *                           H streamed once from HBM with TMA bulk copies through a 4-stage
+ *                           mbarrier pipeline; split over (bin tile, partition range) so that
+ *                           every SM streams an equal, contiguous part of H   (.c:219, 225-227)
+ *   K3  ifft_ola_kernel     per block: sum the split-K partial spectra, ONE inverse real FFT per
+ *                           output channel (the reference does P*nIn of them, .c:220-222),
+ *                           1/N, overlap-add, tail save                        (.c:230-233)
+ *   multi_fused_kernel      multiConv: K1+K2+K3 in one launch, one CTA per channel
+ *   tv_fused_kernel         TVConv: one CTA per output channel, up to three IR sets + cross-fade
+ *
+ * The real FFT of size N is an M = N/2 point complex FFT (radix-4/2 decimation-in-frequency
+ * passes in shared memory, the last five radix-2 stages as warp-shuffle butterflies) plus a
+ * split pass; spectra are kept PACKED (M complex values, bin 0 = (DC, Nyquist)).
+ *
+ * No CPU fallback exists: every entry point returns a CUDA error code if the device path fails.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "safconv_dev.h"
+
+#define SC_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+/* ------------------------------------------------------------------------------------------ */
+/*  small device helpers                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conjb(float2 a, float2 b)   /* a * conj(b) */
+{
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((unsigned)v) >> (32 - logM)); }
+
+/* ------------------------------------------------------------------------------------------ */
+/*  M-point complex FFT in shared memory, decimation in frequency                              */
+/*  input: natural order in s[0..M) ; output: s[bitrev(k)] holds bin k                          */
+/*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)])                        */
+/*  INV conjugates every twiddle (unnormalised inverse transform).                              */
+/*  Requires M >= 32, blockDim.x a multiple of 32; ends with __syncthreads().                   */
+/* ------------------------------------------------------------------------------------------ */
+template <bool INV>
+__device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
+{
+    float2 w = __ldg(tw + idx);
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+template <bool INV>
+__device__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    int L = M;                 /* current sub-transform length */
+    int nsm = logM - 5;        /* radix-2 stages done through shared memory (spans M/2 .. 32) */
+
+    /* two radix-2 stages fused per pass */
+    while (nsm >= 2) {
+        const int q = L >> 2;
+        const int tstr = (2 * M) / L;
+        for (int i = tid; i < (M >> 2); i += T) {
+            const int j = i & (q - 1);
+            const int base = ((i - j) << 2) + j;
+            const float2 a0 = s[base], a1 = s[base + q], a2 = s[base + 2 * q], a3 = s[base + 3 * q];
+            const float2 w1 = twd<INV>(tw, j * tstr);
+            const float2 w2 = twd<INV>(tw, 2 * j * tstr);
+            const float2 u0 = caddf(a0, a2);
+            const float2 u1 = caddf(a1, a3);
+            const float2 v0 = cmulf(csubf(a0, a2), w1);
+            float2 d1 = csubf(a1, a3);
+            /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
+            d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
+            const float2 v1 = cmulf(d1, w1);
+            s[base]         = caddf(u0, u1);
+            s[base + q]     = cmulf(csubf(u0, u1), w2);
+            s[base + 2 * q] = caddf(v0, v1);
+            s[base + 3 * q] = cmulf(csubf(v0, v1), w2);
+        }
+        __syncthreads();
+        L >>= 2;
+        nsm -= 2;
+    }
+    if (nsm == 1) {
+        const int half = L >> 1;
+        const int tstr = (2 * M) / L;
+        for (int i = tid; i < (M >> 1); i += T) {
+            const int j = i & (half - 1);
+            const int base = ((i - j) << 1) + j;
+            const float2 a = s[base], b = s[base + half];
+            const float2 w = twd<INV>(tw, j * tstr);
+            s[base]        = caddf(a, b);
+            s[base + half] = cmulf(csubf(a, b), w);
+        }
+        __syncthreads();
+        L >>= 1;
+    }
+    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp */
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+        float2 w16 = twd<INV>(tw, (lane & 15) * (M >> 4));
+        float2 w8  = twd<INV>(tw, (lane & 7)  * (M >> 3));
+        float2 w4  = twd<INV>(tw, (lane & 3)  * (M >> 2));
+        float2 w2  = twd<INV>(tw, (lane & 1)  * (M >> 1));
+        for (int row = warp; row < (M >> 5); row += nwarps) {
+            float2 v = s[row * 32 + lane];
+#define SC_SHFL_STAGE(HALF, W)                                                       \
+            {                                                                        \
+                float2 o;                                                            \
+                o.x = __shfl_xor_sync(0xffffffffu, v.x, HALF);                       \
+                o.y = __shfl_xor_sync(0xffffffffu, v.y, HALF);                       \
+                if (lane & HALF) v = cmulf(csubf(o, v), W);                          \
+                else             v = caddf(v, o);                                    \
+            }
+            SC_SHFL_STAGE(16, w16)
+            SC_SHFL_STAGE(8,  w8)
+            SC_SHFL_STAGE(4,  w4)
+            SC_SHFL_STAGE(2,  w2)
+            {   /* span 1: twiddle is 1 */
+                float2 o;
+                o.x = __shfl_xor_sync(0xffffffffu, v.x, 1);
+                o.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
+                v = (lane & 1) ? csubf(o, v) : caddf(v, o);
+            }
+#undef SC_SHFL_STAGE
+            s[row * 32 + lane] = v;
+        }
+        __syncthreads();
+    }
+}
+
+/* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
+__device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    if ((hop & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        const int h2 = hop >> 1;
+        for (int n = tid; n < M; n += T) s[n] = (n < h2) ? __ldg(x2 + n) : make_float2(0.f, 0.f);
+    } else {
+        for (int n = tid; n < M; n += T) {
+            const int i = 2 * n;
+            float2 v;
+            v.x = (i < hop) ? __ldg(x + i) : 0.f;
+            v.y = (i + 1 < hop) ? __ldg(x + i + 1) : 0.f;
+            s[n] = v;
+        }
+    }
+}
+
+/* forward split pass for the bin pair (k, M-k), 1 <= k <= M/2, from the bit-reversed complex FFT in s.
+ * X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),  E = (a + conj b)/2, O = -i (a - conj b)/2 */
+__device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, int logM,
+                                               const float2* __restrict__ tw, float2& Xk, float2& Xmk)
+{
+    const float2 a = s[bitrev(k, logM)];
+    const float2 b = s[bitrev(M - k, logM)];
+    const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+    const float2 t = cmulf(__ldg(tw + k), O);
+    Xk  = make_float2(E.x + t.x, E.y + t.y);
+    Xmk = make_float2(E.x - t.x, t.y - E.y);
+}
+
+/* inverse split pass, in place on the packed natural-order spectrum Z (pair k, M-k; 1 <= k <= M/2):
+ * Zc[k] = E + iO, Zc[M-k] = conj(E) + i conj(O), E = A + conj B, O = (A - conj B) W_N^-k  (the 1/2 is folded into 1/N) */
+__device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, const float2* __restrict__ tw)
+{
+    const float2 A = Z[k], B = Z[M - k];
+    const float2 E = make_float2(A.x + B.x, A.y - B.y);
+    const float2 D = make_float2(A.x - B.x, A.y + B.y);
+    const float2 O = cmul_conjb(D, __ldg(tw + k));
+    Z[k]     = make_float2(E.x - O.y, E.y + O.x);
+    Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
+}
+
+__device__ __forceinline__ void inv_split_all(float2* Z, int M, const float2* __restrict__ tw)
+{
+    for (int k = threadIdx.x; k <= (M >> 1); k += blockDim.x) {
+        if (k == 0) {
+            const float2 A = Z[0];                       /* (DC, Nyquist) */
+            Z[0] = make_float2(A.x + A.y, A.x - A.y);
+        } else {
+            inv_split_pair(Z, k, M, tw);
+        }
+    }
+    __syncthreads();
+}
+
+/* time sample j of the (bit-reversed) inverse transform result */
+__device__ __forceinline__ float time_sample(const float2* s, int j, int logM)
+{
+    const float2 v = s[bitrev(j >> 1, logM)];
+    return (j & 1) ? v.y : v.x;
+}
+
+/* overlap-add epilogue (reference .c:230-233): out[i] = z[i]/N + tail[i]; tail[i] = z[i+hop]/N */
+__device__ __forceinline__ void ola_store(const float2* s, int hop, int logM, float scale,
+                                          float* __restrict__ out, float* __restrict__ tail)
+{
+    for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+        const float z0 = time_sample(s, i, logM) * scale;
+        const float z1 = time_sample(s, i + hop, logM) * scale;
+        out[i]  = z0 + tail[i];
+        tail[i] = z1;
+    }
+}
+
+/* "last CTA increments the block counter" : counters[0] = block counter, counters[1] = ticket */
+__device__ __forceinline__ void advance_block_counter(unsigned int* counters, unsigned int nCtas)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&counters[1], 1u);
+        if (t == nCtas - 1) {
+            counters[1] = 0;
+            __threadfence();
+            atomicAdd(&counters[0], 1u);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  K0: filter partition + forward FFT                                                         */
+/*  grid (P, nIn or 1, nOutLocal), one CTA per (partition, input, output)                       */
+/* ------------------------------------------------------------------------------------------ */
+struct FilterArgs {
+    const float* h;        /* time-domain filters */
+    float2*      H;
+    const float2* tw;
+    int kind, hop, len, nIn, M, logM, P, nKT, OTsz;
+};
+
+__global__ void filter_fft_kernel(FilterArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
+    const float* src;
+    if (a.kind == SC_KIND_MATRIX) src = a.h + ((size_t)no * a.nIn + ni) * a.len;
+    else                          src = a.h + (size_t)no * a.len;        /* multi: [ch][len]; tv: [ir*nOut+no][len] */
+    /* taps [p*hop, p*hop+hop) of this FIR, zero beyond length_h (reference .c:119-121) */
+    const int t0 = p * a.hop;
+    for (int n = threadIdx.x; n < a.M; n += blockDim.x) {
+        const int i = t0 + 2 * n;
+        float2 v;
+        v.x = (2 * n < a.hop && i < a.len) ? __ldg(src + i) : 0.f;
+        v.y = (2 * n + 1 < a.hop && i + 1 < a.len) ? __ldg(src + i + 1) : 0.f;
+        sm[n] = v;
+    }
+    __syncthreads();
+    cfft_dif<false>(sm, a.M, a.logM, a.tw);
+
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = sm[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);      /* packed (DC, Nyquist) */
+            k2 = 0;
+            Xmk = Xk;
+        } else {
+            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+        }
+        if (a.kind == SC_KIND_MATRIX) {
+            const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+            /* [ot][kt][p][ni][nl][32] */
+            size_t o1 = (((((size_t)ot * a.nKT + (k >> 5)) * a.P + p) * a.nIn + ni) * a.OTsz + nl) * SC_BK + (k & 31);
+            size_t o2 = (((((size_t)ot * a.nKT + (k2 >> 5)) * a.P + p) * a.nIn + ni) * a.OTsz + nl) * SC_BK + (k2 & 31);
+            a.H[o1] = Xk;
+            a.H[o2] = Xmk;
+        } else {
+            /* [ch][p][M] */
+            float2* dst = a.H + ((size_t)no * a.P + p) * a.M;
+            dst[k] = Xk;
+            dst[k2] = Xmk;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  K1: forward FFT of the new input block into the newest FDL slot (matrix layout)             */
+/*  grid (nIn)                                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+struct InFftArgs {
+    const float* in;       /* [nIn][hop] */
+    float2*      X;        /* [nKT][P][nIn][32] */
+    const float2* tw;
+    const unsigned int* counters;
+    int hop, nIn, M, logM, P;
+};
+
+__global__ void input_fft_kernel(InFftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int ni = blockIdx.x;
+    const int slot = (int)(a.counters[0] % (unsigned)a.P);
+    load_real_block(sm, a.in + (size_t)ni * a.hop, a.hop, a.M);
+    __syncthreads();
+    cfft_dif<false>(sm, a.M, a.logM, a.tw);
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = sm[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);
+            k2 = 0; Xmk = Xk;
+        } else {
+            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+        }
+        a.X[(((size_t)(k >> 5) * a.P + slot) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
+        a.X[(((size_t)(k2 >> 5) * a.P + slot) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  K2: filter-streaming complex MAC  (the HBM-roofline kernel)                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+/* TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+
+struct MacArgs {
+    const float2* H;               /* [unit][nIn][OTsz][32], unit = (ot*nKT + kt)*P + p */
+    const float2* X;               /* [kt][slot][nIn][32] */
+    float2*       Zp;              /* [partial slot][OTsz][32] */
+    const unsigned int* counters;
+    const int*    ctaBase;
+    long long totalStages;
+    int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
+    int stageHBytes, stageXBytes;  /* shared-memory bytes reserved per stage */
+};
+
+#define SC_MAC_THREADS ((SC_MAC_CWARPS + 1) * 32)
+
+template <int R>
+__global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    /* carve: [NS][stageH] [NS][stageX] [reduce 8*R*32 float2] [barriers] */
+    unsigned char* smH = smraw;
+    unsigned char* smX = smH + (size_t)SC_MAC_NSTAGES * a.stageHBytes;
+    float2*   red  = reinterpret_cast<float2*>(smX + (size_t)SC_MAC_NSTAGES * a.stageXBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + SC_MAC_CWARPS * R * 32);
+    uint64_t* empt = full + SC_MAC_NSTAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long s0 = (a.totalStages * (long long)blockIdx.x) / gridDim.x;
+    const long long s1 = (a.totalStages * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const int spg = a.P * a.SPU;                       /* stages per (ot,kt) group */
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SC_MAC_NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empt[s], SC_MAC_CWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == SC_MAC_CWARPS) {
+        /* ===================== TMA producer (one elected lane) ===================== */
+        if (lane == 0) {
+            const int head = (int)(a.counters[0] % (unsigned)a.P);      /* slot of the newest block */
+            const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
+            const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
+            for (long long it = s0; it < s1; ++it) {
+                const int li = (int)(it - s0);
+                const int s = li % SC_MAC_NSTAGES;
+                const uint32_t round = (uint32_t)(li / SC_MAC_NSTAGES);
+                mbar_wait(&empt[s], (round & 1u) ^ 1u);
+                const long long unit = it / a.SPU;
+                const int sidx = (int)(it - unit * a.SPU);
+                const int p    = (int)(unit % a.P);
+                const int kt   = (int)((unit / a.P) % a.nKT);
+                const int ni0  = sidx * a.SNI;
+                const int cnt  = min(a.SNI, a.nIn - ni0);
+                const uint32_t bytesH = (uint32_t)cnt * a.OTsz * (SC_BK * 8);
+                const uint32_t bytesX = (uint32_t)cnt * (SC_BK * 8);
+                int slot = head - p; if (slot < 0) slot += a.P;
+                const float2* srcH = a.H + ((size_t)unit * a.nIn + ni0) * a.OTsz * SC_BK;
+                const float2* srcX = a.X + (((size_t)kt * a.P + slot) * a.nIn + ni0) * SC_BK;
+                mbar_expect_tx(&full[s], bytesH + bytesX);
+                if (a.hints) {
+                    tma_bulk_g2s_hint(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s], polH);
+                    tma_bulk_g2s_hint(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s], polX);
+                } else {
+                    tma_bulk_g2s(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s]);
+                    tma_bulk_g2s(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    /* ===================== consumers: 8 warps, lane = bin inside the tile ===================== */
+    const int  wo     = warp % a.WGo;                  /* which group of R outputs */
+    const int  wk     = warp / a.WGo;                  /* which share of the rows  */
+    const bool active = warp < a.WGo * a.WGk;
+    float2 acc[R], tot[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { acc[j] = make_float2(0.f, 0.f); tot[j] = make_float2(0.f, 0.f); }
+
+    for (long long it = s0; it < s1; ++it) {
+        const int li = (int)(it - s0);
+        const int s = li % SC_MAC_NSTAGES;
+        const uint32_t round = (uint32_t)(li / SC_MAC_NSTAGES);
+        const long long unit = it / a.SPU;
+        const int sidx = (int)(it - unit * a.SPU);
+        const long long grp = unit / a.P;
+        const int kt   = (int)(grp % a.nKT);
+        const int cnt  = min(a.SNI, a.nIn - sidx * a.SNI);
+        const bool packed = (kt == 0) && (lane == 0);  /* bin 0 holds (DC, Nyquist): two real products */
+
+        mbar_wait(&full[s], round & 1u);
+        if (active) {
+            const float2* Hs = reinterpret_cast<const float2*>(smH + (size_t)s * a.stageHBytes);
+            const float2* Xs = reinterpret_cast<const float2*>(smX + (size_t)s * a.stageXBytes);
+            for (int r = wk; r < cnt; r += a.WGk) {
+                const float2 x = Xs[r * SC_BK + lane];
+                const float xb = packed ? 0.f : x.y;   /* re -= h.y*xb ; im += h.x*xb */
+                const float xd = packed ? x.y : x.x;   /* im += h.y*xd                */
+                const float2* hrow = Hs + ((size_t)r * a.OTsz + wo * R) * SC_BK + lane;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    if (wo * R + j < a.OTsz) {
+                        const float2 h = hrow[j * SC_BK];
+                        acc[j].x = fmaf(h.x, x.x, acc[j].x);
+                        acc[j].x = fmaf(-h.y, xb, acc[j].x);
+                        acc[j].y = fmaf(h.x, xb, acc[j].y);
+                        acc[j].y = fmaf(h.y, xd, acc[j].y);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empt[s]);
+
+        const bool last = (it + 1 == s1);
+        if (sidx == a.SPU - 1 || last) {
+            /* two-level accumulation: per-unit sums are folded into the running total */
+#pragma unroll
+            for (int j = 0; j < R; ++j) { tot[j] = caddf(tot[j], acc[j]); acc[j] = make_float2(0.f, 0.f); }
+        }
+        if (((it + 1) % spg) == 0 || last) {
+            /* end of this CTA's share of group (ot,kt): emit one partial tile */
+            const int seg = (int)(it / spg - s0 / spg);
+            float2* dst = a.Zp + ((size_t)(a.ctaBase[blockIdx.x] + seg) * a.OTsz) * SC_BK;
+            if (a.WGk > 1) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) red[(warp * R + j) * 32 + lane] = tot[j];
+                asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
+                if (active && wk == 0) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        float2 v = tot[j];
+                        for (int g = 1; g < a.WGk; ++g) v = caddf(v, red[((g * a.WGo + wo) * R + j) * 32 + lane]);
+                        tot[j] = v;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
+            }
+            if (active && wk == 0) {
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if (wo * R + j < a.OTsz) dst[(size_t)(wo * R + j) * SC_BK + lane] = tot[j];
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) tot[j] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  K3: gather split-K partials, inverse FFT, overlap-add                                        */
+/*  grid (nOutLocal)                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+struct IfftArgs {
+    const float2* Zp;
+    const int* grpStart;
+    const int* grpList;
+    const float2* tw;
+    float* out;            /* [nOutLocal][hop] */
+    float* tail;           /* [nOutLocal][hop] */
+    unsigned int* counters;
+    int hop, M, logM, nKT, OTsz;
+    float scale;           /* 1/N */
+};
+
+__global__ void ifft_ola_kernel(IfftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int no = blockIdx.x;
+    const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const int g = ot * a.nKT + (k >> 5);
+        const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
+        float2 z = make_float2(0.f, 0.f);
+        for (int q = q0; q < q1; ++q) {
+            const int slot = __ldg(a.grpList + q);
+            z = caddf(z, a.Zp[((size_t)slot * a.OTsz + nl) * SC_BK + (k & 31)]);
+        }
+        sm[k] = z;
+    }
+    __syncthreads();
+    inv_split_all(sm, a.M, a.tw);
+    cfft_dif<true>(sm, a.M, a.logM, a.tw);
+    ola_store(sm, a.hop, a.logM, a.scale, a.out + (size_t)no * a.hop, a.tail + (size_t)no * a.hop);
+    advance_block_counter(a.counters, gridDim.x);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  multiConv: everything for one channel in one CTA  (reference .c:388-413)                    */
+/*  grid (nCH) ; shared memory: 2*M float2                                                      */
+/* ------------------------------------------------------------------------------------------ */
+struct MultiArgs {
+    const float* in;       /* [nCH][hop] */
+    float* out;            /* [nCH][hop] */
+    const float2* H;       /* [nCH][P][M] */
+    float2* X;             /* [nCH][P][M] ring */
+    const float2* tw;
+    float* tail;
+    unsigned int* counters;
+    int hop, M, logM, P;
+    float scale;
+};
+
+/* packed-bin-aware complex multiply-accumulate */
+__device__ __forceinline__ void cmac_packed(float2& acc, float2 h, float2 x, bool packed)
+{
+    const float xb = packed ? 0.f : x.y;
+    const float xd = packed ? x.y : x.x;
+    acc.x = fmaf(h.x, x.x, acc.x);
+    acc.x = fmaf(-h.y, xb, acc.x);
+    acc.y = fmaf(h.x, xb, acc.y);
+    acc.y = fmaf(h.y, xd, acc.y);
+}
+
+__global__ void multi_fused_kernel(MultiArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* A = sm;
+    float2* B = sm + a.M;
+    const int c = blockIdx.x;
+    const int head = (int)(a.counters[0] % (unsigned)a.P);
+    float2* Xc = a.X + (size_t)c * a.P * a.M;
+    const float2* Hc = a.H + (size_t)c * a.P * a.M;
+
+    load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M);
+    __syncthreads();
+    cfft_dif<false>(A, a.M, a.logM, a.tw);
+    float2* Xnew = Xc + (size_t)head * a.M;
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = A[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);
+            k2 = 0; Xmk = Xk;
+        } else {
+            fwd_split_pair(A, k, a.M, a.logM, a.tw, Xk, Xmk);
+        }
+        B[k] = Xk;  B[k2] = Xmk;
+        Xnew[k] = Xk;  Xnew[k2] = Xmk;
+    }
+    __syncthreads();
+    /* Z[k] = sum_p H[p][k] * X[t-p][k] ; slot(p) = head - p (mod P) */
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const bool packed = (k == 0);
+        float2 acc = make_float2(0.f, 0.f);
+        cmac_packed(acc, __ldg(Hc + k), B[k], packed);
+        int slot = head;
+#pragma unroll 4
+        for (int p = 1; p < a.P; ++p) {
+            slot = (slot == 0) ? a.P - 1 : slot - 1;
+            cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
+        }
+        A[k] = acc;
+    }
+    __syncthreads();
+    inv_split_all(A, a.M, a.tw);
+    cfft_dif<true>(A, a.M, a.logM, a.tw);
+    ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
+    advance_block_counter(a.counters, gridDim.x);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  TVConv: one CTA per output channel (reference .c:546-620)                                   */
+/*  shared memory: 4*M float2  (X spectrum, three output frames)                                */
+/* ------------------------------------------------------------------------------------------ */
+struct TvArgs {
+    const float* in;       /* [hop] */
+    float* out;            /* [nOut][hop] */
+    const float2* H;       /* [nIRs][nOut][P][M] */
+    float2* X;             /* [P][M] ring */
+    const float2* tw;
+    float* tail0;          /* y_n_overlap      [nOut][hop] */
+    float* tail1;          /* y_n_overlap_last [nOut][hop] */
+    unsigned int* counters;
+    int hop, M, logM, P, nOut;
+    int ir0, ir1, ir2;     /* irIdx, posIdx_last, posIdx_last2 */
+    float scale;
+};
+
+__global__ void tv_fused_kernel(TvArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* Xs = sm;                 /* packed spectrum of the new block */
+    float2* Z0 = sm + a.M;
+    float2* Z1 = sm + 2 * a.M;
+    float2* Z2 = sm + 3 * a.M;
+    const int no = blockIdx.x;
+    const int head = (int)(a.counters[0] % (unsigned)a.P);
+    const bool need1 = (a.ir0 != a.ir1);
+    const bool need2 = (a.ir1 != a.ir2);
+
+    /* every CTA transforms the (single) input block; CTA 0 also stores it in the ring */
+    load_real_block(Z0, a.in, a.hop, a.M);
+    __syncthreads();
+    cfft_dif<false>(Z0, a.M, a.logM, a.tw);
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = Z0[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);
+            k2 = 0; Xmk = Xk;
+        } else {
+            fwd_split_pair(Z0, k, a.M, a.logM, a.tw, Xk, Xmk);
+        }
+        Xs[k] = Xk;  Xs[k2] = Xmk;
+        if (no == 0) {
+            a.X[(size_t)head * a.M + k] = Xk;
+            a.X[(size_t)head * a.M + k2] = Xmk;
+        }
+    }
+    __syncthreads();
+    const size_t pm = (size_t)a.P * a.M;
+    const float2* H0 = a.H + ((size_t)a.ir0 * a.nOut + no) * pm;
+    const float2* H1 = a.H + ((size_t)a.ir1 * a.nOut + no) * pm;
+    const float2* H2 = a.H + ((size_t)a.ir2 * a.nOut + no) * pm;
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const bool packed = (k == 0);
+        float2 z0 = make_float2(0.f, 0.f), z1 = z0, z2 = z0;
+        int slot = head;
+        for (int p = 0; p < a.P; ++p) {
+            const float2 x = (p == 0) ? Xs[k] : a.X[(size_t)slot * a.M + k];
+            cmac_packed(z0, __ldg(H0 + (size_t)p * a.M + k), x, packed);
+            if (need1) cmac_packed(z1, __ldg(H1 + (size_t)p * a.M + k), x, packed);
+            if (need2) cmac_packed(z2, __ldg(H2 + (size_t)p * a.M + k), x, packed);
+            slot = (slot == 0) ? a.P - 1 : slot - 1;
+        }
+        if (!need1) z1 = z0;                  /* .c:587 */
+        if (!need2) z2 = z1;                  /* .c:601 */
+        Z0[k] = z0; Z1[k] = z1; Z2[k] = z2;
+    }
+    __syncthreads();
+    inv_split_all(Z0, a.M, a.tw);  cfft_dif<true>(Z0, a.M, a.logM, a.tw);
+    inv_split_all(Z1, a.M, a.tw);  cfft_dif<true>(Z1, a.M, a.logM, a.tw);
+    inv_split_all(Z2, a.M, a.tw);  cfft_dif<true>(Z2, a.M, a.logM, a.tw);
+    /* cross-fade (reference .c:494-497, 605-615) */
+    float* t0 = a.tail0 + (size_t)no * a.hop;
+    float* t1 = a.tail1 + (size_t)no * a.hop;
+    float* o  = a.out + (size_t)no * a.hop;
+    const float den = (float)(a.hop - 1);
+    for (int i = threadIdx.x; i < a.hop; i += blockDim.x) {
+        const float fin  = (float)i / den;
+        const float fout = (float)(a.hop - 1 - i) / den;
+        const float o1 = time_sample(Z1, i, a.logM) * a.scale + t0[i];
+        const float o2 = time_sample(Z2, i, a.logM) * a.scale + t1[i];
+        o[i]  = o1 * fin + o2 * fout;
+        t0[i] = time_sample(Z0, i + a.hop, a.logM) * a.scale;
+        t1[i] = time_sample(Z1, i + a.hop, a.logM) * a.scale;
+    }
+    advance_block_counter(a.counters, gridDim.x);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  C-ABI: plumbing                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+int scdev_device_count(int* n) { return (int)cudaGetDeviceCount(n); }
+int scdev_set_device(int dev) { return (int)cudaSetDevice(dev); }
+int scdev_get_device(int* dev) { return (int)cudaGetDevice(dev); }
+int scdev_device_props(int dev, int* smCount, int* maxSmemOptin, int* ccMajor, int* ccMinor)
+{
+    SC_CHECK(cudaDeviceGetAttribute(smCount, cudaDevAttrMultiProcessorCount, dev));
+    SC_CHECK(cudaDeviceGetAttribute(maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SC_CHECK(cudaDeviceGetAttribute(ccMajor, cudaDevAttrComputeCapabilityMajor, dev));
+    SC_CHECK(cudaDeviceGetAttribute(ccMinor, cudaDevAttrComputeCapabilityMinor, dev));
+    return 0;
+}
+int scdev_malloc(void** p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 16); }
+int scdev_free(void* p) { return p ? (int)cudaFree(p) : 0; }
+int scdev_host_alloc(void** p, size_t bytes) { return (int)cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault); }
+int scdev_host_free(void* p) { return p ? (int)cudaFreeHost(p) : 0; }
+int scdev_memset_async(void* p, int v, size_t bytes, void* stream) { return (int)cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream); }
+int scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream)
+{ return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream); }
+int scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream)
+{ return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream); }
+int scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes)
+{ return (int)cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); }
+int scdev_stream_create(void** s)
+{ cudaStream_t st; cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); *s = (void*)st; return (int)e; }
+int scdev_stream_destroy(void* s) { return s ? (int)cudaStreamDestroy((cudaStream_t)s) : 0; }
+int scdev_stream_sync(void* s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
+int scdev_event_create(void** e) { cudaEvent_t ev; cudaError_t r = cudaEventCreate(&ev); *e = (void*)ev; return (int)r; }
+int scdev_event_destroy(void* e) { return e ? (int)cudaEventDestroy((cudaEvent_t)e) : 0; }
+int scdev_event_record(void* e, void* stream) { return (int)cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream); }
+int scdev_event_sync(void* e) { return (int)cudaEventSynchronize((cudaEvent_t)e); }
+int scdev_event_elapsed_ms(void* e0, void* e1, float* ms) { return (int)cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1); }
+int scdev_graph_begin(void* stream) { return (int)cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal); }
+int scdev_graph_end(void* stream, void** graphExec)
+{
+    cudaGraph_t g = nullptr;
+    SC_CHECK(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    *graphExec = (void*)ge;
+    return (int)e;
+}
+int scdev_graph_launch(void* graphExec, void* stream) { return (int)cudaGraphLaunch((cudaGraphExec_t)graphExec, (cudaStream_t)stream); }
+int scdev_graph_destroy(void* graphExec) { return graphExec ? (int)cudaGraphExecDestroy((cudaGraphExec_t)graphExec) : 0; }
+const char* scdev_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+
+/* ------------------------------------------------------------------------------------------ */
+/*  C-ABI: kernel launchers                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+static size_t fft_smem(const scdev_plan* pl, int nbuf) { return (size_t)nbuf * pl->M * sizeof(float2); }
+
+typedef void (*mac_fn_t)(MacArgs);
+static mac_fn_t mac_fn(int R)
+{
+    switch (R) {
+        case 1: return mac_kernel<1>;
+        case 2: return mac_kernel<2>;
+        case 4: return mac_kernel<4>;
+        default: return mac_kernel<8>;
+    }
+}
+
+int scdev_prepare(const scdev_plan* pl)
+{
+    const int big = 1 << 16;
+    if (fft_smem(pl, 1) > 48 * 1024) {
+        SC_CHECK(cudaFuncSetAttribute(filter_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        SC_CHECK(cudaFuncSetAttribute(input_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
+    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 2) > 48 * 1024)
+        SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
+    if (pl->kind == SC_KIND_TV && fft_smem(pl, 4) > 48 * 1024)
+        SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 4)));
+    if (pl->kind == SC_KIND_MATRIX)
+        SC_CHECK(cudaFuncSetAttribute(mac_fn(pl->R), cudaFuncAttributeMaxDynamicSharedMemorySize, pl->macSmemBytes));
+    return 0;
+}
+
+int scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const float* d_h, void* stream)
+{
+    FilterArgs a;
+    a.h = d_h; a.H = (float2*)b->H; a.tw = (const float2*)b->tw;
+    a.kind = pl->kind; a.hop = pl->hop; a.len = pl->len; a.nIn = pl->nIn;
+    a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
+    if (pl->kind == SC_KIND_MATRIX) {
+        if (pl->nOutLocal > 65535 || pl->nIn > 65535) return (int)cudaErrorInvalidValue;   /* grid.y / grid.z limits */
+        dim3 grid(pl->P, pl->nIn, pl->nOutLocal);
+        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    } else {
+        const int rows = (pl->kind == SC_KIND_TV) ? pl->nIRs * pl->nOutLocal : pl->nOutLocal;
+        if (rows > 65535) return (int)cudaErrorInvalidValue;
+        dim3 grid(pl->P, 1, rows);
+        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+int scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, void* stream)
+{
+    InFftArgs a;
+    a.in = d_in; a.X = (float2*)b->X; a.tw = (const float2*)b->tw; a.counters = b->counters;
+    a.hop = pl->hop; a.nIn = pl->nIn; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
+    input_fft_kernel<<<pl->nIn, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, void* stream)
+{
+    MacArgs a;
+    a.H = (const float2*)b->H; a.X = (const float2*)b->X; a.Zp = (float2*)b->Zp;
+    a.counters = b->counters; a.ctaBase = b->ctaBase;
+    a.totalStages = pl->totalStages;
+    a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.P = pl->P; a.nKT = pl->nKT;
+    a.SNI = pl->SNI; a.SPU = pl->SPU; a.WGo = pl->WGo; a.WGk = pl->WGk; a.hints = pl->macHints;
+    a.stageHBytes = pl->SNI * pl->OTsz * SC_BK * 8;
+    a.stageXBytes = pl->SNI * SC_BK * 8;
+    mac_fn(pl->R)<<<pl->macGrid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream)
+{
+    IfftArgs a;
+    a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart; a.grpList = b->grpList;
+    a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.counters = b->counters;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
+    a.scale = 1.0f / (float)pl->N;
+    ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream)
+{
+    MultiArgs a;
+    a.in = d_in; a.out = d_out; a.H = (const float2*)b->H; a.X = (float2*)b->X;
+    a.tw = (const float2*)b->tw; a.tail = b->tail; a.counters = b->counters;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
+    a.scale = 1.0f / (float)pl->N;
+    multi_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out,
+                   int irIdx, int irLast, int irLast2, void* stream)
+{
+    TvArgs a;
+    a.in = d_in; a.out = d_out; a.H = (const float2*)b->H; a.X = (float2*)b->X;
+    a.tw = (const float2*)b->tw; a.tail0 = b->tail; a.tail1 = b->tail2; a.counters = b->counters;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nOut = pl->nOutLocal;
+    a.ir0 = irIdx; a.ir1 = irLast; a.ir2 = irLast2;
+    a.scale = 1.0f / (float)pl->N;
+    tv_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 4), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+} /* extern "C" */

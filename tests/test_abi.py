@@ -1,0 +1,80 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/safconv_b200.h declares."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    txt = (ROOT / "include" / "safconv_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b((?:saf|safconv)_\w+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_header_symbols_all_exported(saf):
+    lib = saf.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/safconv_b200.h but not exported"
+    # and the binding's own list agrees with the header
+    from spatial_audio_framework_b200._capi import EXPORTED_SYMBOLS
+    assert sorted(EXPORTED_SYMBOLS) == syms
+
+
+def test_reference_signatures_are_drop_in(saf):
+    """Same six (+3 TVConv) names as the reference header saf_utility_matrixConv.h:55-190."""
+    for s in ["saf_matrixConv_create", "saf_matrixConv_destroy", "saf_matrixConv_apply",
+              "saf_multiConv_create", "saf_multiConv_destroy", "saf_multiConv_apply",
+              "saf_TVConv_create", "saf_TVConv_destroy", "saf_TVConv_apply"]:
+        assert s in declared_symbols()
+
+
+def test_version_and_null_safety(saf):
+    lib = saf.lib()
+    assert b"sm_100a" in lib.safconv_version()
+    h = C.c_void_p()
+    lib.saf_matrixConv_destroy(C.byref(h))      # destroy(NULL handle) is a no-op (reference .c:140)
+    lib.saf_multiConv_destroy(C.byref(h))
+    lib.saf_TVConv_destroy(C.byref(h))
+    x = np.zeros(8, np.float32)
+    p = x.ctypes.data_as(C.POINTER(C.c_float))
+    lib.saf_matrixConv_apply(None, p, p)        # apply on NULL handle: no-op, no crash
+    lib.saf_multiConv_apply(None, p, p)
+
+
+def test_invalid_arguments_leave_null_handle(saf):
+    lib = saf.lib()
+    H = np.zeros((2, 2, 16), np.float32)
+    hp = H.ctypes.data_as(C.POINTER(C.c_float))
+    for args in [(0, hp, 16, 2, 2, 1), (64, hp, 0, 2, 2, 1), (64, hp, 16, 0, 2, 1), (64, hp, 16, 2, 0, 1),
+                 (16384, hp, 16, 2, 2, 1), (64, None, 16, 2, 2, 1)]:
+        h = C.c_void_p(123)
+        lib.saf_matrixConv_create(C.byref(h), *args)
+        assert not h.value
+        assert lib.safconv_last_error(None) == 1
+        assert b"invalid" in lib.safconv_last_error_string(None)
+
+
+def test_no_cpu_fallback_without_device(saf):
+    """Without a CUDA device create() must fail loudly (NULL handle + error), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        saf.MatrixConv(64, np.zeros((1, 1, 64), np.float32))
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        saf.MultiConv(64, np.zeros((1, 64), np.float32))
+
+
+def test_product_does_not_reference_oracle():
+    """The product sources must not import/link anything under oracle/."""
+    pkg = ROOT / "spatial_audio_framework_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.c")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + list(pkg.rglob("Makefile")):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, p
