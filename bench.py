@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SAF multichannel-convolution hot path on B200.
+
+Workload (BASELINE.json `metric` is quoted on configs[3]): saf_matrixConv 64-in x 64-out, hop 1024,
+96000-tap synthetic (exponentially decaying noise) RIRs, output channels sharded over N GPUs.
+One "step" = `--blocks` consecutive hop-sized blocks through the hot path (K1 input FFT ->
+K2 filter-streaming MAC -> K3 inverse FFT + overlap-add).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU code (oracle/_ref) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = output-channel*samples per second, whole job, inputs resident
+in HBM; `e2e` = the same through the reference-facing host-pointer API (H2D / D2H inside the timed region);
+`roofline` = the MAC kernel's algorithmic (H + delay line) bytes / its CUDA-event duration against the
+measured HBM copy peak; `cpu_baseline` = the compiled reference timed on this box's host cores on a
+bounded sample of the same workload.
+
+PyTorch is used for plumbing only (device buffers, events, torch.distributed/NCCL); every kernel on the
+path is ours (libsafconv_b200.so).  oracle/ is touched only by the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: kind, nIn, nOut, hop, L
+    "C4": dict(kind="matrix", nIn=64, nOut=64, hop=1024, L=96000,
+               desc="saf_matrixConv 64-in x 64-out, hop 1024, 96000-tap RIRs (BASELINE.json configs[3])"),
+    "C4s": dict(kind="matrix", nIn=64, nOut=64, hop=1024, L=8192,
+                desc="C4 scaled down to 8192 taps (debug only)"),
+    "UT": dict(kind="matrix", nIn=32, nOut=40, hop=2048, L=512,
+               desc="test__saf_matrixConv shape 32x40, hop 2048, 512 taps"),
+    "C3": dict(kind="multi", nIn=256, nOut=256, hop=512, L=4096,
+               desc="saf_multiConv 256 ch, hop 512, 4096 taps (BASELINE.json configs[2])"),
+    "C2": dict(kind="matrix", nIn=25, nOut=2, hop=128, L=512,
+               desc="saf_matrixConv 25x2, hop 128, 512 taps (BASELINE.json configs[1])"),
+    "C1": dict(kind="matrix", nIn=4, nOut=2, hop=256, L=1024,
+               desc="saf_matrixConv 4x2, hop 256, 1024 taps (BASELINE.json configs[0])"),
+}
+METRIC = "convolved out-ch*samples/sec"
+UNIT = "out-ch*samples/s"
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def filters_for(w, out_begin, out_count, seed=0x5AF0C0DE):
+    """Deterministic per-output-channel filters so that every rank can build its own shard."""
+    from spatial_audio_framework_b200 import synth
+    if w["kind"] == "matrix":
+        H = np.empty((out_count, w["nIn"], w["L"]), np.float32)
+        for i in range(out_count):
+            H[i] = synth.decaying_rir((w["nIn"], w["L"]), seed=seed + out_begin + i)
+    else:
+        H = np.empty((out_count, w["L"]), np.float32)
+        for i in range(out_count):
+            H[i] = synth.decaying_rir((w["L"],), seed=seed + out_begin + i)
+    return H
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference (CPU) leg: the compiled, unmodified reference convolver (oracle/_ref), one handle per thread,
+# each owning a disjoint slice of output channels of the same problem
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=1, ch_per_thread=1):
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    import oracle as O
+    try:
+        O.load_reference()
+        kind = "reference"
+        mk_matrix, mk_multi = O.RefMatrixConv, O.RefMultiConv
+    except Exception:
+        kind = "port"
+        mk_matrix, mk_multi = O.OracleMatrixConv, O.OracleMultiConv
+    cores = threads or os.cpu_count() or 1
+    total_out = w["nOut"]
+    cores = max(1, min(cores, total_out // ch_per_thread))
+    hop, nIn = w["hop"], w["nIn"]
+    convs, xs = [], []
+    rng = np.random.default_rng(1)
+    for t in range(cores):
+        H = filters_for(w, t * ch_per_thread, ch_per_thread)
+        if w["kind"] == "matrix":
+            convs.append(mk_matrix(hop, H, 1))
+            xs.append(rng.uniform(-1, 1, (nIn, hop)).astype(np.float32))
+        else:
+            convs.append(mk_multi(hop, H, 1))
+            xs.append(rng.uniform(-1, 1, (ch_per_thread, hop)).astype(np.float32))
+
+    def one_step():
+        def work(i):
+            for _ in range(blocks_per_step):
+                convs[i].apply(xs[i])
+        th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    units = cores * ch_per_thread * hop * blocks_per_step * steps
+    sample = (f"{cores} threads x {ch_per_thread} of {total_out} output channels each (independent per reference .c:218-234), "
+              f"full {nIn}-input x {w['L']}-tap filters, {blocks_per_step} block(s)/step x {steps} steps after {warmup} warm-up; "
+              f"{'compiled unmodified reference (KissFFT + ' + O.load_reference()[1] + ' level-1 BLAS)' if kind == 'reference' else 'oracle port'}")
+    return dict(value=units / dt, unit=UNIT, cores=cores, kind=kind, sample=sample, seconds=dt,
+                ms_per_step=1e3 * dt / steps)
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(w, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "nIn": w["nIn"], "nOut": w["nOut"], "hop": w["hop"], "length_h": w["L"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_own_arm(args, w):
+    import torch
+    import spatial_audio_framework_b200 as saf
+    from spatial_audio_framework_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    hop, nIn, nOut, B = w["hop"], w["nIn"], w["nOut"], args.blocks
+    ob, oc = sharding.shard_range(nOut, world, rank)
+    H = filters_for(w, ob, oc)
+    t_c0 = time.perf_counter()
+    if w["kind"] == "matrix":
+        conv = saf.MatrixConv(hop, H, 1, device=local) if world == 1 else \
+            saf.MatrixConv.from_shard(hop, H, nOut, ob, device=local)
+    else:
+        conv = saf.MultiConv(hop, H, 1, device=local)
+    create_s = time.perf_counter() - t_c0
+    del H
+    info = conv.info()
+    stream = torch.cuda.Stream(device=dev)
+    conv.set_stream(stream.cuda_stream)
+    nInLocal = nIn if w["kind"] == "matrix" else oc
+
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x_host = (torch.rand((B, nIn, hop), generator=g) * 2 - 1).pin_memory()          # one step of input, pinned
+    y_host = torch.empty((B, nOut, hop), dtype=torch.float32).pin_memory()
+    engine = sharding.ShardedStep(conv, w["kind"], nIn, nOut, hop, B, world, rank, dev, stream, dist)
+
+    # ---------------- device-resident timing (value) ----------------
+    engine.load_input(x_host)                      # inputs resident in HBM before the timed region
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        engine.step_device()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    conv.enable_kernel_timing(B * args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(args.steps):
+            engine.step_device()
+        engine.drain()
+        e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    kms, nk = conv.kernel_times_ms()
+    conv.enable_kernel_timing(0)
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    units = float(nOut) * hop * B * args.steps
+    value = units / (ms_total * 1e-3)
+
+    # ---------------- end-to-end through the host-pointer API ----------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(2, args.warmup)):
+        engine.step_host(x_host, y_host)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.step_host(x_host, y_host)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = float(nOut) * hop * B * e2e_steps / float(t.item())
+    lat = engine.latency_ms
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(B * nIn * hop * 4),
+           "d2h_bytes_per_step": int(B * nOut * hop * 4), "steps": e2e_steps,
+           "api": engine.host_api_name}
+    if lat:
+        e2e["block_latency_ms_p50"] = float(np.percentile(lat, 50))
+        e2e["block_latency_ms_p99"] = float(np.percentile(lat, 99))
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = measured_peak_gbs()
+    mac_ms = kms[1]
+    mac_bytes = float(info.macAlgBytesPerBlock)
+    achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "mac_kernel (K2 filter-streaming complex MAC)" if w["kind"] == "matrix" else "multi_fused_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": args.traffic, "alg_bytes_per_launch": mac_bytes, "avg_launch_ms": mac_ms,
+                "launches_timed": nk, "rank": 0,
+                "whole_block": {"alg_bytes": float(info.algBytesPerBlock),
+                                "achieved_GBps": float(info.algBytesPerBlock) * B * args.steps / (ms_total * 1e-3) / 1e9},
+                "kernel_ms_per_block": {"input_fft": kms[0], "mac": kms[1], "ifft_ola": kms[2]}}
+    roofline["whole_block"]["frac"] = roofline["whole_block"]["achieved_GBps"] / peak
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        c = cpu_reference_run(w, steps=args.cpu_steps, warmup=1)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    kernels_per_block = 3 if w["kind"] == "matrix" else 1
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"],
+                   "blocks_per_step": B, "partitions": int(info.numFilterBlocks),
+                   "sharding": f"output channels over {world} GPU(s), {oc} per GPU; input batch NCCL-broadcast, output shards all-gathered" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: %.0f MB of filter spectra streamed per block per GPU (L2 = 126 MB)" % (info.bytesFilters / 1e6),
+                   "filters": "exponentially decaying uniform noise (-60 dB at the last tap), seeded per output channel",
+                   "create_seconds_rank0": create_s},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": kernels_per_block * B * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "ms_per_block": ms_total / (args.steps * B),
+        "realtime_factor_48k": (hop * B * args.steps / (ms_total * 1e-3)) / 48000.0,
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--blocks", type=int, default=32, help="hop-sized blocks per step")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per MAC launch from the committed ncu capture (profiles/), echoed into roofline.traffic")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+    else:
+        run_own_arm(args, w)
+
+
+if __name__ == "__main__":
+    main()

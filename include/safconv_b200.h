@@ -120,6 +120,14 @@ int safconv_set_device(int device);
 void safconv_matrixConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
                                      int nCHin, int nCHout, int outBegin, int outCount);
 
+/**
+ * As safconv_matrixConv_create_shard, but Hshard holds ONLY this shard's filters
+ * (FLAT outCount x nCHin x length_h), so that each process of a one-process-per-GPU job needs
+ * just its own part of the filter matrix in host memory.
+ */
+void safconv_matrixConv_create_from_shard(void** const phMC, int hopSize, const float* Hshard, int length_h,
+                                          int nCHin, int nCHout, int outBegin, int outCount);
+
 /** As saf_multiConv_create for channels [chBegin, chBegin+chCount) of H (FLAT nCH x length_h). */
 void safconv_multiConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,
                                     int nCH, int chBegin, int chCount);

@@ -19,5 +19,6 @@ from ._capi import (  # noqa: F401
     version,
 )
 from . import synth  # noqa: F401
+from . import sharding  # noqa: F401
 
-__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "lib", "version", "synth"]
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "lib", "version", "synth", "sharding"]

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "saf_multiConv_create", "saf_multiConv_destroy", "saf_multiConv_apply",
     "saf_TVConv_create", "saf_TVConv_destroy", "saf_TVConv_apply",
     "safconv_last_error", "safconv_last_error_string", "safconv_version", "safconv_set_device",
-    "safconv_matrixConv_create_shard", "safconv_multiConv_create_shard",
+    "safconv_matrixConv_create_shard", "safconv_matrixConv_create_from_shard", "safconv_multiConv_create_shard",
     "safconv_apply_device", "safconv_apply_device_blocks",
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
     "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_set_option",
@@ -86,6 +86,8 @@ def lib():
     L.safconv_set_device.argtypes = [C.c_int]
     L.safconv_matrixConv_create_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.safconv_matrixConv_create_shard.restype = None
+    L.safconv_matrixConv_create_from_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.safconv_matrixConv_create_from_shard.restype = None
     L.safconv_multiConv_create_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.safconv_multiConv_create_shard.restype = None
     L.safconv_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -206,14 +208,20 @@ class MatrixConv(_Base):
 
     _destroy_name = "saf_matrixConv_destroy"
 
-    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None):
+    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None,
+                 _from_shard=None):
         super().__init__()
         H = np.ascontiguousarray(H, np.float32)
         self.nCHout, self.nCHin, self.length_h = H.shape
         self.hop = int(hopSize)
         if device is not None:
             self._lib.safconv_set_device(int(device))
-        if shard is None:
+        if _from_shard is not None:
+            nOutTotal, ob = _from_shard
+            self.nOutLocal, self.nCHout = H.shape[0], int(nOutTotal)
+            self._lib.safconv_matrixConv_create_from_shard(C.byref(self._h), self.hop, _fp(H), self.length_h,
+                                                           self.nCHin, self.nCHout, int(ob), self.nOutLocal)
+        elif shard is None:
             self.nOutLocal = self.nCHout
             self._lib.saf_matrixConv_create(C.byref(self._h), self.hop, _fp(H), self.length_h,
                                             self.nCHin, self.nCHout, int(usePartFLAG))
@@ -223,6 +231,11 @@ class MatrixConv(_Base):
             self._lib.safconv_matrixConv_create_shard(C.byref(self._h), self.hop, _fp(H), self.length_h,
                                                       self.nCHin, self.nCHout, int(ob), int(oc))
         self._check_created("saf_matrixConv_create")
+
+    @classmethod
+    def from_shard(cls, hopSize: int, Hshard: np.ndarray, nCHoutTotal: int, outBegin: int, device: int | None = None):
+        """Hshard: [outCount, nCHin, length_h] = this rank's output channels only (safconv_matrixConv_create_from_shard)."""
+        return cls(hopSize, Hshard, 1, device=device, _from_shard=(nCHoutTotal, outBegin))
 
     def apply(self, inputSigs: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(inputSigs, np.float32)

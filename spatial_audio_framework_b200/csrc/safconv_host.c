@@ -439,6 +439,20 @@ void safconv_matrixConv_create_shard(void** const phMC, int hopSize, const float
                         length_h, nCHin, outCount, nCHout, outBegin, 0);
 }
 
+void safconv_matrixConv_create_from_shard(void** const phMC, int hopSize, const float* Hshard, int length_h,
+                                          int nCHin, int nCHout, int outBegin, int outCount)
+{
+    if (!phMC) return;
+    if (!Hshard || outBegin < 0 || outCount < 1 || outBegin + outCount > nCHout || nCHin < 1 || length_h < 1) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid shard%s", "");
+        *phMC = NULL;
+        return;
+    }
+    const float* chunk = Hshard;
+    *phMC = conv_create(SC_KIND_MATRIX, hopSize, &chunk, 1, (size_t)outCount * nCHin,
+                        length_h, nCHin, outCount, nCHout, outBegin, 0);
+}
+
 void saf_matrixConv_destroy(void** const phMC) { conv_destroy(phMC); }
 
 void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)

@@ -1,0 +1,211 @@
+"""Output-channel sharding of the matrix convolver over the GPUs of one box (one process per GPU).
+
+Output channels are independent in the reference (each iteration of the `no` loop of
+saf_matrixConv_apply reads its own filters and overlap tail and the shared delay line:
+/root/reference/framework/modules/saf_utilities/saf_utility_matrixConv.c:218-234), so rank r of G owns a
+contiguous range of output channels, a full replica of the frequency-domain delay line, and no partial
+sums ever cross GPUs.  The only exchange per step is
+
+    input batch  [B][nIn][hop]      rank 0 -> all ranks     (broadcast)
+    output shard [B][nOut/G][hop]   all ranks -> everyone   (all-gather)
+
+Both run on a side stream and are software-pipelined against the local convolution: the broadcast of
+step t+1 is issued before the all-gather of step t, so it overlaps the compute of step t, and the
+all-gather of step t overlaps the compute of step t+1.  multiConv channels are fully independent and are
+sharded the same way (each rank only needs its own channels' input, but the broadcast of the whole batch
+is kept so that both kinds share one code path).
+
+torch / torch.distributed is plumbing only (buffers, streams, NCCL); the compute is `compute_fn`, which on
+a GPU is libsafconv_b200's safconv_apply_device_blocks.  With device="cpu" and the gloo backend the same
+exchange logic runs without a GPU (tests/test_sharding_gloo.py supplies a CPU checker as compute_fn).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+
+def shard_range(n_out: int, world: int, rank: int):
+    """Contiguous, balanced split: the first (n_out % world) ranks get one extra channel.
+    Returns (begin, count); count may be 0 when world > n_out."""
+    base, extra = divmod(n_out, world)
+    begin = rank * base + min(rank, extra)
+    return begin, base + (1 if rank < extra else 0)
+
+
+def gathered_to_channel_major(y_all, n_out: int, world: int):
+    """[sum_r (B * count_r * hop)] flat gather buffer -> [B][nOut][hop] tensor (a copy)."""
+    import torch
+    parts, off = [], 0
+    B, hop = y_all["B"], y_all["hop"]
+    flat = y_all["flat"]
+    for r in range(world):
+        _, cnt = shard_range(n_out, world, r)
+        n = B * cnt * hop
+        parts.append(flat[off:off + n].view(B, cnt, hop))
+        off += n
+    return torch.cat(parts, dim=1)
+
+
+class ShardedStep:
+    """One benchmark/processing step = B consecutive hop-sized blocks through this rank's shard.
+
+    compute_fn(x, y): x is a [B][nIn][hop] tensor on `device`, y a [B][count][hop] tensor to fill
+    (enqueued on `stream` when on CUDA).
+    """
+
+    def __init__(self, conv, kind, n_in, n_out, hop, B, world, rank, device, stream=None, dist=None, compute_fn=None):
+        import torch
+        self.torch = torch
+        self.conv, self.kind = conv, kind
+        self.n_in, self.n_out, self.hop, self.B = n_in, n_out, hop, B
+        self.world, self.rank, self.device, self.stream, self.dist = world, rank, device, stream, dist
+        self.cuda = (getattr(device, "type", str(device)) == "cuda")
+        self.begin, self.count = shard_range(n_out, world, rank)
+        self.counts = [shard_range(n_out, world, r)[1] for r in range(world)]
+        self.latency_ms = []
+        self.host_api_name = ("saf_matrixConv_apply" if kind == "matrix" else "saf_multiConv_apply") + \
+            " (one synchronous host-pointer call per block)"
+        if compute_fn is None:
+            def compute_fn(x, y, _c=conv, _B=B):
+                _c.apply_device(x.data_ptr(), y.data_ptr(), _B)
+        self.compute_fn = compute_fn
+        f32 = torch.float32
+        nbuf = 2 if world > 1 else 1
+        self.x = [torch.empty((B, n_in, hop), dtype=f32, device=device) for _ in range(nbuf)]
+        self.y = [torch.empty((B, self.count, hop), dtype=f32, device=device) for _ in range(nbuf)]
+        self.t = 0
+        if world > 1:
+            self.host_api_name = "ShardedStep.step_host (pinned H2D on rank 0, NCCL broadcast, shard compute, all-gather, D2H on rank 0)"
+            self.equal = len(set(self.counts)) == 1
+            self.y_all = [torch.empty((B * n_out * hop,), dtype=f32, device=device) for _ in range(nbuf)]
+            self.comm = torch.cuda.Stream(device=device) if self.cuda else None
+            self.ev_b = [torch.cuda.Event() for _ in range(nbuf)] if self.cuda else None
+            self.ev_c = [torch.cuda.Event() for _ in range(nbuf)] if self.cuda else None
+            self.ev_g = [torch.cuda.Event() for _ in range(nbuf)] if self.cuda else None
+            self.pending_bcast = False
+
+    # ------------------------------------------------------------------ single-GPU paths
+    def load_input(self, x_host):
+        """Make one step of input resident on the device (rank 0's copy is the source of truth)."""
+        self.x[0].copy_(x_host)
+        if self.world > 1:
+            self.x[1].copy_(x_host)
+
+    def _compute(self, buf):
+        if self.count > 0:
+            self.compute_fn(self.x[buf], self.y[buf])
+
+    # ------------------------------------------------------------------ exchange helpers
+    def _bcast(self, buf):
+        self.dist.broadcast(self.x[buf], src=0)
+
+    def _gather(self, buf):
+        torch, dist = self.torch, self.dist
+        if self.equal and self.cuda:
+            dist.all_gather_into_tensor(self.y_all[buf], self.y[buf].view(-1))
+        else:
+            # ragged shards (nOut % world != 0) or gloo: gather equal-sized padded pieces, then compact
+            n_max = self.B * max(self.counts) * self.hop
+            pad = torch.zeros((n_max,), dtype=self.y[buf].dtype, device=self.device)
+            mine = self.y[buf].reshape(-1)
+            pad[:mine.numel()] = mine
+            pieces = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(pieces, pad)
+            off = 0
+            for cnt, piece in zip(self.counts, pieces):
+                n = self.B * cnt * self.hop
+                self.y_all[buf][off:off + n] = piece[:n]
+                off += n
+
+    def step_device(self):
+        """Inputs already resident in HBM (on rank 0 for world > 1)."""
+        torch = self.torch
+        if self.world == 1:
+            self._compute(0)
+            return
+        buf, nxt = self.t % 2, (self.t + 1) % 2
+        if not self.cuda:
+            self._bcast(buf)
+            self._compute(buf)
+            self._gather(buf)
+            self.t += 1
+            return
+        comm, cs = self.comm, self.stream
+        if not self.pending_bcast:                         # pipeline prologue
+            comm.wait_stream(cs)
+            with torch.cuda.stream(comm):
+                self._bcast(buf)
+                self.ev_b[buf].record(comm)
+        # prefetch the next step's input while this step computes (x[nxt] was last read by compute t-1)
+        with torch.cuda.stream(comm):
+            if self.t > 0:
+                comm.wait_event(self.ev_c[nxt])
+            self._bcast(nxt)
+            self.ev_b[nxt].record(comm)
+        self.pending_bcast = True
+        with torch.cuda.stream(cs):
+            cs.wait_event(self.ev_b[buf])
+            if self.t > 1:
+                cs.wait_event(self.ev_g[buf])              # y[buf] was read by the all-gather of step t-2
+            self._compute(buf)
+            self.ev_c[buf].record(cs)
+        with torch.cuda.stream(comm):
+            comm.wait_event(self.ev_c[buf])
+            self._gather(buf)
+            self.ev_g[buf].record(comm)
+        self.t += 1
+
+    def drain(self):
+        """Make the compute stream wait for every outstanding exchange (call before the closing event)."""
+        if self.world > 1 and self.cuda:
+            self.stream.wait_stream(self.comm)
+
+    def last_output(self):
+        """[B][nOut][hop] result of the most recent step (copy)."""
+        if self.world == 1:
+            return self.y[0]
+        buf = (self.t - 1) % 2
+        return gathered_to_channel_major({"flat": self.y_all[buf], "B": self.B, "hop": self.hop}, self.n_out, self.world)
+
+    # ------------------------------------------------------------------ host-pointer (end-to-end) path
+    def step_host(self, x_host, y_host):
+        """x_host [B][nIn][hop] pinned -> y_host [B][nOut][hop] pinned, H2D and D2H included."""
+        torch = self.torch
+        if self.world == 1:
+            lib, h = self.conv._lib, self.conv.handle
+            fn = lib.saf_matrixConv_apply if self.kind == "matrix" else lib.saf_multiConv_apply
+            xin, yout = x_host.data_ptr(), y_host.data_ptr()
+            sx, sy = self.n_in * self.hop * 4, self.n_out * self.hop * 4
+            fp = C.POINTER(C.c_float)
+            for b in range(self.B):
+                t0 = time.perf_counter()
+                fn(h, C.cast(xin + b * sx, fp), C.cast(yout + b * sy, fp))
+                self.latency_ms.append(1e3 * (time.perf_counter() - t0))
+            return
+        cs = self.stream
+        self.pending_bcast = False                          # host steps are not pipelined across steps
+        buf = self.t % 2
+        if self.cuda:
+            with torch.cuda.stream(cs):
+                if self.rank == 0:
+                    self.x[buf].copy_(x_host, non_blocking=True)
+                self._bcast(buf)
+                self._compute(buf)
+                self._gather(buf)
+                if self.rank == 0:
+                    out = self.last_output_from(buf)
+                    y_host.copy_(out, non_blocking=True)
+            cs.synchronize()
+        else:
+            if self.rank == 0:
+                self.x[buf].copy_(x_host)
+            self._bcast(buf)
+            self._compute(buf)
+            self._gather(buf)
+            if self.rank == 0:
+                y_host.copy_(self.last_output_from(buf))
+        self.t += 1
+
+    def last_output_from(self, buf):
+        return gathered_to_channel_major({"flat": self.y_all[buf], "B": self.B, "hop": self.hop}, self.n_out, self.world)
