@@ -26,8 +26,9 @@ extern "C" {
 #define SC_BK            32      /* packed bins per tile                                   */
 #define SC_MAX_OT        64      /* output channels per tile                               */
 #define SC_MAC_CWARPS    8       /* consumer warps of the MAC kernel (+1 producer warp)    */
-#define SC_MAC_NSTAGES   4       /* TMA pipeline depth                                     */
-#define SC_STAGE_H_BYTES 32768   /* target bytes of H per stage                            */
+#define SC_MAC_NSTAGES   4       /* default TMA pipeline depth                             */
+#define SC_MAC_MAX_STAGES 16
+#define SC_STAGE_H_BYTES 32768   /* default target bytes of H per stage                    */
 #define SC_MAX_SNI       32      /* max input channels per stage                           */
 #define SC_MAX_M         8192    /* max complex FFT length (hop <= 8192)                   */
 
@@ -47,6 +48,8 @@ typedef struct scdev_plan {
     int nGroups, nSlots;
     int macHints;            /* 0/1: L2 eviction-priority hints              */
     int macSmemBytes;
+    int macStages;           /* TMA pipeline depth                           */
+    int macStageBytes;       /* target bytes of H per stage                  */
     /* time-varying convolver */
     int nIRs;
 } scdev_plan;

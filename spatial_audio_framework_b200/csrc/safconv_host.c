@@ -96,17 +96,31 @@ static void plan_fft(scdev_plan* pl, int hop, int len)
 }
 
 /* MAC tiling + even split of all pipeline stages over `grid` CTAs */
+static int env_int(const char* name, int dflt, int lo, int hi)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    int x = atoi(v);
+    return (x < lo || x > hi) ? dflt : x;
+}
+
 static void plan_mac(scdev_plan* pl, int smCount)
 {
     const int nOut = pl->nOutLocal;
+    /* tuning knobs (benchmarks only): pipeline depth and bytes of H per stage */
+    pl->macStages     = env_int("SAFCONV_MAC_STAGES", SC_MAC_NSTAGES, 2, SC_MAC_MAX_STAGES);
+    pl->macStageBytes = 1024 * env_int("SAFCONV_MAC_STAGE_KB", SC_STAGE_H_BYTES / 1024, 1, 96);
     pl->nKT  = pl->M / SC_BK;
     pl->nOT  = (nOut + SC_MAX_OT - 1) / SC_MAX_OT;
     pl->OTsz = (nOut + pl->nOT - 1) / pl->nOT;
-    int R = 1;
-    while (SC_MAC_CWARPS * R < pl->OTsz) R <<= 1;
-    pl->R   = R;
-    pl->WGo = (pl->OTsz + R - 1) / R;
-    int sni = SC_STAGE_H_BYTES / (pl->OTsz * SC_BK * 8);
+    /* warp roles: WGo warp groups over outputs (R outputs each, held in registers so that one delay-line
+     * load feeds R filters), WGk = 8 / WGo groups over the input rows of a stage.  Smallest WGo with R <= 8. */
+    int wgo = 1;
+    while ((pl->OTsz + wgo - 1) / wgo > 8) wgo <<= 1;
+    pl->WGo = wgo;
+    pl->R   = (pl->OTsz + wgo - 1) / wgo;
+    const int R = pl->R;
+    int sni = pl->macStageBytes / (pl->OTsz * SC_BK * 8);
     if (sni < 1) sni = 1;
     if (sni > SC_MAX_SNI) sni = SC_MAX_SNI;
     if (sni > pl->nIn) sni = pl->nIn;
@@ -121,8 +135,8 @@ static void plan_mac(scdev_plan* pl, int smCount)
     long long g = smCount;
     if (g > pl->totalStages) g = pl->totalStages;
     pl->macGrid = (int)g;
-    pl->macSmemBytes = SC_MAC_NSTAGES * (pl->SNI * pl->OTsz * SC_BK * 8 + pl->SNI * SC_BK * 8)
-                     + SC_MAC_CWARPS * R * 32 * 8 + 2 * SC_MAC_NSTAGES * 8;
+    pl->macSmemBytes = pl->macStages * (pl->SNI * pl->OTsz * SC_BK * 8 + pl->SNI * SC_BK * 8)
+                     + SC_MAC_CWARPS * R * 32 * 8 + 2 * pl->macStages * 8;
 }
 
 /* split-K bookkeeping: CTA c streams stages [c*T/G, (c+1)*T/G); every (ot,kt) group it touches gets
@@ -606,7 +620,7 @@ int safconv_get_info(void* hp, safconv_info* info)
     info->kind = pl->kind; info->hopSize = pl->hop; info->length_h = pl->len;
     info->nCHin = pl->nIn; info->nCHout = h->nCHoutTotal; info->nOutLocal = pl->nOutLocal; info->outBegin = h->outBegin;
     info->fftSize = pl->N; info->nBinsPacked = pl->M; info->numFilterBlocks = pl->P;
-    info->macGrid = pl->macGrid; info->macStages = SC_MAC_NSTAGES; info->macThreads = (SC_MAC_CWARPS + 1) * 32;
+    info->macGrid = pl->macGrid; info->macStages = pl->macStages; info->macThreads = (SC_MAC_CWARPS + 1) * 32;
     info->device = h->device;
     info->bytesFilters = h->bytesH; info->bytesDelayLine = h->bytesX;
     /* algorithmic bytes per block, nBins = hop + 1 complex bins of 8 bytes */

@@ -389,6 +389,7 @@ struct MacArgs {
     const int*    ctaBase;
     long long totalStages;
     int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
+    int NS;                        /* pipeline depth (stages)                */
     int stageHBytes, stageXBytes;  /* shared-memory bytes reserved per stage */
 };
 
@@ -399,19 +400,27 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     /* carve: [NS][stageH] [NS][stageX] [reduce 8*R*32 float2] [barriers] */
+    const int NS = a.NS;
     unsigned char* smH = smraw;
-    unsigned char* smX = smH + (size_t)SC_MAC_NSTAGES * a.stageHBytes;
-    float2*   red  = reinterpret_cast<float2*>(smX + (size_t)SC_MAC_NSTAGES * a.stageXBytes);
+    unsigned char* smX = smH + (size_t)NS * a.stageHBytes;
+    float2*   red  = reinterpret_cast<float2*>(smX + (size_t)NS * a.stageXBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(red + SC_MAC_CWARPS * R * 32);
-    uint64_t* empt = full + SC_MAC_NSTAGES;
+    uint64_t* empt = full + NS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long s0 = (a.totalStages * (long long)blockIdx.x) / gridDim.x;
     const long long s1 = (a.totalStages * (long long)(blockIdx.x + 1)) / gridDim.x;
-    const int spg = a.P * a.SPU;                       /* stages per (ot,kt) group */
+    const int nIt = (int)(s1 - s0);
+    /* decompose the first stage index ONCE; afterwards (sidx, p, kt) are advanced incrementally
+     * (no integer division inside the streaming loop) */
+    const long long unit0 = s0 / a.SPU;
+    int sidx = (int)(s0 - unit0 * a.SPU);              /* stage inside the unit          */
+    const long long grp0 = unit0 / a.P;
+    int p  = (int)(unit0 - grp0 * a.P);                /* filter partition               */
+    int kt = (int)(grp0 % a.nKT);                      /* bin tile                       */
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SC_MAC_NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empt[s], SC_MAC_CWARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empt[s], SC_MAC_CWARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -422,21 +431,16 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
             const int head = (int)(a.counters[0] % (unsigned)a.P);      /* slot of the newest block */
             const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
             const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
-            for (long long it = s0; it < s1; ++it) {
-                const int li = (int)(it - s0);
-                const int s = li % SC_MAC_NSTAGES;
-                const uint32_t round = (uint32_t)(li / SC_MAC_NSTAGES);
-                mbar_wait(&empt[s], (round & 1u) ^ 1u);
-                const long long unit = it / a.SPU;
-                const int sidx = (int)(it - unit * a.SPU);
-                const int p    = (int)(unit % a.P);
-                const int kt   = (int)((unit / a.P) % a.nKT);
+            const float2* srcH = a.H + ((size_t)unit0 * a.nIn + (size_t)sidx * a.SNI) * a.OTsz * SC_BK;
+            const uint32_t rowH = (uint32_t)a.OTsz * (SC_BK * 8);
+            int s = 0; uint32_t par = 1;
+            for (int i = 0; i < nIt; ++i) {
+                mbar_wait(&empt[s], par);
                 const int ni0  = sidx * a.SNI;
                 const int cnt  = min(a.SNI, a.nIn - ni0);
-                const uint32_t bytesH = (uint32_t)cnt * a.OTsz * (SC_BK * 8);
+                const uint32_t bytesH = (uint32_t)cnt * rowH;
                 const uint32_t bytesX = (uint32_t)cnt * (SC_BK * 8);
                 int slot = head - p; if (slot < 0) slot += a.P;
-                const float2* srcH = a.H + ((size_t)unit * a.nIn + ni0) * a.OTsz * SC_BK;
                 const float2* srcX = a.X + (((size_t)kt * a.P + slot) * a.nIn + ni0) * SC_BK;
                 mbar_expect_tx(&full[s], bytesH + bytesX);
                 if (a.hints) {
@@ -446,6 +450,9 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
                     tma_bulk_g2s(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s]);
                     tma_bulk_g2s(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s]);
                 }
+                srcH += (size_t)cnt * a.OTsz * SC_BK;               /* stages are contiguous in H */
+                if (++sidx == a.SPU) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+                if (++s == NS) { s = 0; par ^= 1u; }
             }
         }
         return;
@@ -454,34 +461,31 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     /* ===================== consumers: 8 warps, lane = bin inside the tile ===================== */
     const int  wo     = warp % a.WGo;                  /* which group of R outputs */
     const int  wk     = warp / a.WGo;                  /* which share of the rows  */
-    const bool active = warp < a.WGo * a.WGk;
+    const int  nvalid = min(R, a.OTsz - wo * R);       /* outputs this warp really owns */
+    const bool active = (wk < a.WGk) && (nvalid > 0);
+    const int  rowStride = a.OTsz * SC_BK;             /* float2 per input row of a stage */
     float2 acc[R], tot[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) { acc[j] = make_float2(0.f, 0.f); tot[j] = make_float2(0.f, 0.f); }
 
-    for (long long it = s0; it < s1; ++it) {
-        const int li = (int)(it - s0);
-        const int s = li % SC_MAC_NSTAGES;
-        const uint32_t round = (uint32_t)(li / SC_MAC_NSTAGES);
-        const long long unit = it / a.SPU;
-        const int sidx = (int)(it - unit * a.SPU);
-        const long long grp = unit / a.P;
-        const int kt   = (int)(grp % a.nKT);
-        const int cnt  = min(a.SNI, a.nIn - sidx * a.SNI);
+    int s = 0, seg = 0; uint32_t par = 0;
+    float2* dstBase = a.Zp + (size_t)a.ctaBase[blockIdx.x] * a.OTsz * SC_BK;
+    for (int i = 0; i < nIt; ++i) {
+        const int  cnt    = min(a.SNI, a.nIn - sidx * a.SNI);
         const bool packed = (kt == 0) && (lane == 0);  /* bin 0 holds (DC, Nyquist): two real products */
 
-        mbar_wait(&full[s], round & 1u);
+        mbar_wait(&full[s], par);
         if (active) {
-            const float2* Hs = reinterpret_cast<const float2*>(smH + (size_t)s * a.stageHBytes);
-            const float2* Xs = reinterpret_cast<const float2*>(smX + (size_t)s * a.stageXBytes);
+            const float2* Hs = reinterpret_cast<const float2*>(smH + (size_t)s * a.stageHBytes) + wo * R * SC_BK + lane;
+            const float2* Xs = reinterpret_cast<const float2*>(smX + (size_t)s * a.stageXBytes) + lane;
             for (int r = wk; r < cnt; r += a.WGk) {
-                const float2 x = Xs[r * SC_BK + lane];
+                const float2 x = Xs[r * SC_BK];
                 const float xb = packed ? 0.f : x.y;   /* re -= h.y*xb ; im += h.x*xb */
                 const float xd = packed ? x.y : x.x;   /* im += h.y*xd                */
-                const float2* hrow = Hs + ((size_t)r * a.OTsz + wo * R) * SC_BK + lane;
+                const float2* hrow = Hs + (size_t)r * rowStride;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    if (wo * R + j < a.OTsz) {
+                    if (j < nvalid) {
                         const float2 h = hrow[j * SC_BK];
                         acc[j].x = fmaf(h.x, x.x, acc[j].x);
                         acc[j].x = fmaf(-h.y, xb, acc[j].x);
@@ -493,17 +497,20 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empt[s]);
+        if (++s == NS) { s = 0; par ^= 1u; }
 
-        const bool last = (it + 1 == s1);
-        if (sidx == a.SPU - 1 || last) {
+        const bool last     = (i + 1 == nIt);
+        const bool endUnit  = (sidx == a.SPU - 1);
+        const bool endGroup = endUnit && (p == a.P - 1);
+        if (endUnit || last) {
             /* two-level accumulation: per-unit sums are folded into the running total */
 #pragma unroll
             for (int j = 0; j < R; ++j) { tot[j] = caddf(tot[j], acc[j]); acc[j] = make_float2(0.f, 0.f); }
         }
-        if (((it + 1) % spg) == 0 || last) {
+        if (endGroup || last) {
             /* end of this CTA's share of group (ot,kt): emit one partial tile */
-            const int seg = (int)(it / spg - s0 / spg);
-            float2* dst = a.Zp + ((size_t)(a.ctaBase[blockIdx.x] + seg) * a.OTsz) * SC_BK;
+            float2* dst = dstBase + (size_t)seg * a.OTsz * SC_BK;
+            ++seg;
             if (a.WGk > 1) {
 #pragma unroll
                 for (int j = 0; j < R; ++j) red[(warp * R + j) * 32 + lane] = tot[j];
@@ -521,11 +528,13 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
             if (active && wk == 0) {
 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if (wo * R + j < a.OTsz) dst[(size_t)(wo * R + j) * SC_BK + lane] = tot[j];
+                    if (j < nvalid) dst[(size_t)(wo * R + j) * SC_BK + lane] = tot[j];
             }
 #pragma unroll
             for (int j = 0; j < R; ++j) tot[j] = make_float2(0.f, 0.f);
         }
+        if (endUnit) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+        else ++sidx;
     }
 }
 
@@ -796,7 +805,11 @@ static mac_fn_t mac_fn(int R)
     switch (R) {
         case 1: return mac_kernel<1>;
         case 2: return mac_kernel<2>;
+        case 3: return mac_kernel<3>;
         case 4: return mac_kernel<4>;
+        case 5: return mac_kernel<5>;
+        case 6: return mac_kernel<6>;
+        case 7: return mac_kernel<7>;
         default: return mac_kernel<8>;
     }
 }
@@ -854,6 +867,7 @@ int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, void* stream)
     a.totalStages = pl->totalStages;
     a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.P = pl->P; a.nKT = pl->nKT;
     a.SNI = pl->SNI; a.SPU = pl->SPU; a.WGo = pl->WGo; a.WGk = pl->WGk; a.hints = pl->macHints;
+    a.NS = pl->macStages;
     a.stageHBytes = pl->SNI * pl->OTsz * SC_BK * 8;
     a.stageXBytes = pl->SNI * SC_BK * 8;
     mac_fn(pl->R)<<<pl->macGrid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);

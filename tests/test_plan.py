@@ -12,7 +12,8 @@ class Plan(C.Structure):   # mirrors scdev_plan in csrc/safconv_dev.h
                 ("nKT", C.c_int), ("nOT", C.c_int), ("OTsz", C.c_int), ("SNI", C.c_int), ("SPU", C.c_int),
                 ("R", C.c_int), ("WGo", C.c_int), ("WGk", C.c_int), ("totalStages", C.c_longlong),
                 ("macGrid", C.c_int), ("nGroups", C.c_int), ("nSlots", C.c_int), ("macHints", C.c_int),
-                ("macSmemBytes", C.c_int), ("nIRs", C.c_int)]
+                ("macSmemBytes", C.c_int), ("macStages", C.c_int), ("macStageBytes", C.c_int),
+                ("nIRs", C.c_int)]
 
 
 def plan(saf, hop, L, nIn, nOut, sms=148, kind=0):
@@ -50,9 +51,9 @@ def test_mac_tiling_and_split_tables(saf, hop, L, nIn, nOut, sms):
     pl, ctaBase, grpStart, grpList = plan(saf, hop, L, nIn, nOut, sms)
     # tiling covers all outputs / inputs
     assert pl.nOT * pl.OTsz >= nOut and pl.OTsz <= 64
-    assert pl.R in (1, 2, 4, 8) and pl.WGo * pl.R >= pl.OTsz and pl.WGo * pl.WGk <= 8 and pl.WGk >= 1
+    assert 1 <= pl.R <= 8 and pl.WGo in (1, 2, 4, 8) and pl.WGo * pl.R >= pl.OTsz and pl.WGo * pl.WGk <= 8 and pl.WGk >= 1
     assert pl.SNI * pl.SPU >= nIn and (pl.SPU - 1) * pl.SNI < nIn
-    assert pl.SNI * pl.OTsz * 256 <= 32768 or pl.SNI == 1
+    assert pl.SNI * pl.OTsz * 256 <= pl.macStageBytes or pl.SNI == 1
     assert pl.nKT * 32 == pl.M and pl.nGroups == pl.nOT * pl.nKT
     assert pl.totalStages == pl.nGroups * pl.P * pl.SPU
     assert 1 <= pl.macGrid <= min(sms, pl.totalStages)
