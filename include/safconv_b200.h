@@ -174,8 +174,8 @@ int safconv_get_info(void* h, safconv_info* info);
  * saf_*_apply / safconv_apply_device* records events between its kernels on the handle's stream.
  * safconv_get_kernel_times synchronises on the last recorded block, returns the AVERAGE per-block
  * durations over the recorded blocks (ms[0] = forward FFT, ms[1] = filter-streaming MAC [or the fused
- * multiConv kernel], ms[2] = inverse FFT + overlap-add), how many blocks were averaged, and restarts
- * the ring.
+ * multiConv kernel], ms[2] = inverse FFT + overlap-add; FFT launches shared by a batch of blocks are
+ * divided by the number of blocks), how many blocks were averaged, and restarts the ring.
  */
 int safconv_enable_kernel_timing(void* h, int nBlocks);
 int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
@@ -183,6 +183,10 @@ int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
 /** Tuning knobs (mostly for benchmarks / tests). Returns 0 on success.
  *    "mac_hints"    0/1 L2 eviction-priority hints on the H / delay-line streams
  *    "use_graph"    0/1 replay the per-block launch sequence of saf_*_apply from a CUDA graph
+ *    "batching"     0/1 (default 1) safconv_apply_device_blocks shares one forward-FFT and one inverse-FFT
+ *                   launch across the blocks handed over together (outputs are bit-identical either way)
+ *    "detect_pinned" 0/1 (default 1) saf_*_apply copies straight from/to caller buffers that are already
+ *                   page-locked instead of going through the handle's own pinned staging buffers
  */
 int safconv_set_option(void* h, const char* name, int value);
 

@@ -101,6 +101,7 @@ def lib():
     L.safconv_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.safconv_get_kernel_times.argtypes = [C.c_void_p, _f32p, C.POINTER(C.c_int)]
     L.safconv_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.safconv_debug_plan_size.restype = C.c_int
     _lib = L
     return L
 

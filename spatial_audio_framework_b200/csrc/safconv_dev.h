@@ -46,6 +46,8 @@ typedef struct scdev_plan {
     long long totalStages;
     int macGrid;
     int nGroups, nSlots;
+    int RS;                  /* delay-line ring slots = P + maxBatch            */
+    int maxBatch;            /* blocks per batched launch group (>= 1)          */
     int macHints;            /* 0/1: L2 eviction-priority hints              */
     int macSmemBytes;
     int macStages;           /* TMA pipeline depth                           */
@@ -59,15 +61,15 @@ typedef struct scdev_bufs {
     void*  tw;        /* float2[M]        W_N^j                                            */
     void*  H;         /* float2: matrix [nOT][nKT][P][nIn][OTsz][32]; multi [nCH][P][M];    */
                       /*         tv     [nIRs][nOut][P][M]                                  */
-    void*  X;         /* float2: matrix [nKT][P][nIn][32];            multi [nCH][P][M];    */
+    void*  X;         /* float2: matrix [nKT][RS][nIn][32];           multi [nCH][P][M];    */
                       /*         tv     [P][M]                                              */
-    void*  Zp;        /* float2[nSlots][OTsz][32]  split-K partial output spectra (matrix)  */
+    void*  Zp;        /* float2[maxBatch][nSlots][OTsz][32]  split-K partial output spectra */
+    float* zt;        /* float[maxBatch][nOutLocal][2*hop]   batched inverse transforms     */
     float* tail;      /* float[nOutLocal][hop]     overlap-add tails                        */
     float* tail2;     /* tv only: y_n_overlap_last                                          */
     unsigned int* counters; /* [0] block counter, [1] last-CTA ticket                       */
     int*   ctaBase;   /* int[macGrid]   first partial slot of each MAC CTA                  */
-    int*   grpStart;  /* int[nGroups+1]                                                     */
-    int*   grpList;   /* int[nSlots]    partial slots contributing to each group            */
+    int*   grpStart;  /* int[nGroups+1] partial slots of group g: grpStart[g]..grpStart[g+1]-1 */
 } scdev_bufs;
 
 /* --- device / memory / stream plumbing (all return 0 on success, else a cudaError_t value) --- */
@@ -82,7 +84,7 @@ int  scdev_host_free(void* p);
 int  scdev_memset_async(void* p, int v, size_t bytes, void* stream);
 int  scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream);
 int  scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream);
-int  scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes);
+int  scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes, void* stream);
 int  scdev_stream_create(void** s);
 int  scdev_stream_destroy(void* s);
 int  scdev_stream_sync(void* s);
@@ -103,12 +105,16 @@ int  scdev_prepare(const scdev_plan* pl);
 /* K0: partition + forward real FFT of the time-domain filters d_h (matrix: [nOutLocal][nIn][len],
  * multi: [nCH][len], tv: [nIRs][nOut][len]) into bufs->H */
 int  scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const float* d_h, void* stream);
-/* K1: forward real FFT of the new input block d_in [nIn][hop] into FDL slot (counter % P) */
-int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, void* stream);
-/* K2: filter-streaming complex multiply-accumulate over partitions x inputs (matrix) */
-int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, void* stream);
-/* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ */
+/* K1: forward real FFT of nBlocks new input blocks d_in [nBlocks][nIn][hop] into ring slots (counter + b) % RS */
+int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, int nBlocks, void* stream);
+/* K2: filter-streaming complex multiply-accumulate over partitions x inputs for block `blk` of the batch */
+int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, void* stream);
+/* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ (one block) */
 int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
+/* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */
+int  scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream);
+/* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */
+int  scdev_is_pinned_host(const void* p);
 /* multiConv: K1+K2+K3 fused, one CTA per channel */
 int  scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream);
 /* TVConv: 1-input FFT + (1..3) IR MACs + cross-fade, one CTA per output channel */

@@ -37,9 +37,13 @@ typedef struct safconv_handle {
     size_t     inBytes, outBytes;
     size_t     bytesH, bytesX, bytesZp;
     int        useGraph;
+    int        batching;             /* 1: safconv_apply_device_blocks shares the FFT launches across a batch */
+    int        detectPinned;         /* 1: DMA straight from/to caller buffers that are already page-locked */
     void*      graphExec;
     int        timingCap, timingCount;   /* ring of 4 CUDA events per block while kernel timing is enabled */
     void**     evRing;
+    unsigned char* evMask;           /* per block: bit0 = (ev0,ev1) brackets a K1 launch, bit1 = (ev2,ev3) brackets K3 */
+    void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
 } safconv_handle;
 
@@ -132,6 +136,17 @@ static void plan_mac(scdev_plan* pl, int smCount)
     pl->WGk = wgk;
     pl->nGroups = pl->nOT * pl->nKT;
     pl->totalStages = (long long)pl->nGroups * pl->P * pl->SPU;
+    /* blocks handed over together (safconv_apply_device_blocks) share one forward-FFT launch and one
+     * inverse-FFT launch; the delay line then needs maxBatch extra ring slots (the FFTs of the whole batch
+     * are written before the first MAC runs).  Keep the extra memory below ~256 MB. */
+    {
+        int mb = env_int("SAFCONV_MAX_BATCH", 32, 1, 256);
+        const double slotBytes = (double)pl->M * pl->nIn * 8.0;
+        const double ztBytes   = (double)nOut * pl->hop * 8.0;
+        while (mb > 1 && mb * (slotBytes + ztBytes) > 256e6) mb >>= 1;
+        pl->maxBatch = mb;
+        pl->RS = pl->P + mb;
+    }
     long long g = smCount;
     if (g > pl->totalStages) g = pl->totalStages;
     pl->macGrid = (int)g;
@@ -177,6 +192,8 @@ static int build_split_tables(const scdev_plan* pl, int** ctaBaseOut, int** grpS
     return slots;
 }
 
+int safconv_debug_plan_size(void) { return (int)sizeof(scdev_plan); }
+
 /* exported for the host-logic unit tests (tests/test_plan.py): fills the plan exactly as create() does */
 int safconv_debug_plan(int kind, int hop, int len, int nIn, int nOutLocal, int smCount, scdev_plan* out,
                        int* ctaBase /* >= smCount+1 */, int* grpStart, int* grpList, int cap)
@@ -213,9 +230,10 @@ static void handle_free(safconv_handle* h)
     if (h->stream) scdev_stream_sync(h->stream);
     scdev_graph_destroy(h->graphExec);
     if (h->evRing) { for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]); free(h->evRing); }
-    scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp);
+    free(h->evMask);
+    scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
-    scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart); scdev_free(h->b.grpList);
+    scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart);
     scdev_free(h->d_in); scdev_free(h->d_out);
     scdev_host_free(h->h_in); scdev_host_free(h->h_out);
     scdev_stream_destroy(h->streamOwn);
@@ -227,7 +245,7 @@ static int upload(safconv_handle* h, void** dptr, const void* src, size_t bytes,
 {
     int e = scdev_malloc(dptr, bytes);
     if (e) return h_fail(h, SAFCONV_ERR_NOMEM, what, e);
-    e = scdev_memcpy_h2d_sync(*dptr, src, bytes);
+    e = scdev_memcpy_h2d_sync(*dptr, src, bytes, h->stream);
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, what, e);
     return 0;
 }
@@ -275,6 +293,8 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     pl->kind = kind; pl->nIn = nIn; pl->nOutLocal = nOutLocal; pl->nIRs = nIRs;
     plan_fft(pl, hop, len);
     pl->macHints = 1;
+    h->detectPinned = 1;
+    h->batching = 1;
 
     const size_t M = (size_t)pl->M, P = (size_t)pl->P;
     /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
@@ -301,12 +321,16 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         pl->nSlots = slots;
         int e = upload(h, (void**)&h->b.ctaBase, ctaBase, sizeof(int) * (size_t)(pl->macGrid + 1), "ctaBase upload");
         if (!e) e = upload(h, (void**)&h->b.grpStart, grpStart, sizeof(int) * (size_t)(pl->nGroups + 1), "grpStart upload");
-        if (!e) e = upload(h, (void**)&h->b.grpList, grpList, sizeof(int) * (size_t)(slots > 0 ? slots : 1), "grpList upload");
+        /* the partial slots of a group are consecutive by construction (slots are numbered in (CTA, segment)
+         * order and that order is monotone in the group index): K3 only needs grpStart */
+        for (int q = 0; q < slots; q++) if (grpList[q] != q) e = -1;
         free(ctaBase); free(grpStart); free(grpList);
-        if (e) goto fail;
+        if (e) { h_fail(h, SAFCONV_ERR_ARG, "internal: split-K slot order", 0); goto fail; }
+        while (pl->maxBatch > 1 && (double)pl->maxBatch * slots * pl->OTsz * SC_BK * 8.0 > 256e6) pl->maxBatch >>= 1;
+        pl->RS = pl->P + pl->maxBatch;
         h->bytesH  = (size_t)pl->nOT * pl->nKT * P * nIn * pl->OTsz * SC_BK * 8;
-        h->bytesX  = (size_t)pl->nKT * P * nIn * SC_BK * 8;
-        h->bytesZp = (size_t)slots * pl->OTsz * SC_BK * 8;
+        h->bytesX  = (size_t)pl->nKT * pl->RS * nIn * SC_BK * 8;
+        h->bytesZp = (size_t)pl->maxBatch * slots * pl->OTsz * SC_BK * 8;
         rowsTotal  = (size_t)nOutLocal * nIn;
     } else if (kind == SC_KIND_MULTI) {
         h->bytesH = (size_t)nOutLocal * P * M * 8;
@@ -322,6 +346,8 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     if (zalloc(h, &h->b.H, h->bytesH, "filter spectra allocation")) goto fail;
     if (zalloc(h, &h->b.X, h->bytesX, "delay line allocation")) goto fail;
     if (kind == SC_KIND_MATRIX && zalloc(h, &h->b.Zp, h->bytesZp, "partial spectra allocation")) goto fail;
+    if (kind == SC_KIND_MATRIX && pl->maxBatch > 1 &&
+        zalloc(h, (void**)&h->b.zt, sizeof(float) * (size_t)pl->maxBatch * nOutLocal * 2 * hop, "batched inverse-transform buffer")) goto fail;
     if (zalloc(h, (void**)&h->b.tail, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails")) goto fail;
     if (kind == SC_KIND_TV && zalloc(h, (void**)&h->b.tail2, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails (last)")) goto fail;
     if (zalloc(h, (void**)&h->b.counters, 4 * sizeof(unsigned int), "counters")) goto fail;
@@ -341,7 +367,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         int e = scdev_malloc((void**)&d_h, rowsTotal * rowBytes);
         if (e) { h_fail(h, SAFCONV_ERR_NOMEM, "time-domain filter upload buffer", e); goto fail; }
         for (int c = 0; c < nChunks && !e; c++)
-            e = scdev_memcpy_h2d_sync((char*)d_h + (size_t)c * rowsPerChunk * rowBytes, chunks[c], rowsPerChunk * rowBytes);
+            e = scdev_memcpy_h2d_sync((char*)d_h + (size_t)c * rowsPerChunk * rowBytes, chunks[c], rowsPerChunk * rowBytes, h->stream);
         if (!e) e = scdev_filter_transform(pl, &h->b, d_h, h->stream);
         if (!e) e = scdev_stream_sync(h->stream);
         scdev_free(d_h);
@@ -366,49 +392,76 @@ static void conv_destroy(void** const ph)
 /*  per-block sequencing                                                                        */
 /* ------------------------------------------------------------------------------------------ */
 
-static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out)
+/* nBlocks (<= maxBatch) consecutive blocks: d_in [nBlocks][nIn][hop] -> d_out [nBlocks][nOutLocal][hop].
+ * matrix: K1 for all blocks in one launch, one MAC launch per block (each streams the filters once),
+ * K3 for all blocks (one block: the fused inverse-FFT + overlap-add kernel). */
+static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, int nBlocks)
 {
     const scdev_plan* pl = &h->pl;
     void** ev = NULL;
-    if (h->timingCap && h->timingCount < h->timingCap) ev = h->evRing + 4 * (size_t)(h->timingCount++);
+    unsigned char* mask = NULL;
+    if (h->timingCap && h->timingCount + nBlocks <= h->timingCap) {
+        ev = h->evRing + 4 * (size_t)h->timingCount;
+        mask = h->evMask + h->timingCount;
+        h->timingCount += nBlocks;
+        memset(mask, 0, (size_t)nBlocks);
+    }
     int e = 0;
     if (pl->kind == SC_KIND_MATRIX) {
-        if (ev) scdev_event_record(ev[0], h->stream);
-        e = scdev_input_fft(pl, &h->b, d_in, h->stream);
-        if (ev) scdev_event_record(ev[1], h->stream);
-        if (!e) e = scdev_mac(pl, &h->b, h->stream);
-        if (ev) scdev_event_record(ev[2], h->stream);
-        if (!e) e = scdev_ifft_ola(pl, &h->b, d_out, h->stream);
-        if (ev) scdev_event_record(ev[3], h->stream);
+        if (ev) { scdev_event_record(ev[0], h->stream); mask[0] |= 1; }
+        e = scdev_input_fft(pl, &h->b, d_in, nBlocks, h->stream);
+        for (int b = 0; b < nBlocks && !e; b++) {
+            if (ev) scdev_event_record(ev[4 * b + 1], h->stream);
+            e = scdev_mac(pl, &h->b, b, h->stream);
+            if (ev) scdev_event_record(ev[4 * b + 2], h->stream);
+        }
+        if (!e) e = (nBlocks == 1) ? scdev_ifft_ola(pl, &h->b, d_out, h->stream)
+                                   : scdev_ifft_ola_batch(pl, &h->b, d_out, nBlocks, h->stream);
+        if (ev) { scdev_event_record(ev[4 * (nBlocks - 1) + 3], h->stream); mask[nBlocks - 1] |= 2; }
     } else if (pl->kind == SC_KIND_MULTI) {
-        if (ev) scdev_event_record(ev[1], h->stream);
-        e = scdev_multi_fused(pl, &h->b, d_in, d_out, h->stream);
-        if (ev) scdev_event_record(ev[2], h->stream);
+        const size_t inStride = (size_t)pl->nIn * pl->hop, outStride = (size_t)pl->nOutLocal * pl->hop;
+        for (int b = 0; b < nBlocks && !e; b++) {
+            if (ev) scdev_event_record(ev[4 * b + 1], h->stream);
+            e = scdev_multi_fused(pl, &h->b, d_in + b * inStride, d_out + b * outStride, h->stream);
+            if (ev) scdev_event_record(ev[4 * b + 2], h->stream);
+        }
     } else {
         return (int)SAFCONV_ERR_ARG;
     }
     return e;
 }
 
+static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out) { return enqueue_blocks(h, d_in, d_out, 1); }
+
 /* host-pointer apply: pinned staging -> H2D -> kernels -> D2H -> sync (reference semantics: synchronous) */
 static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
 {
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
-    memcpy(h->h_in, in, h->inBytes);
+    /* caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are DMA'd directly;
+     * ordinary malloc'd buffers go through the handle's pinned staging buffers */
+    const int direct = h->detectPinned && scdev_is_pinned_host(in) && scdev_is_pinned_host(out);
+    const float* src = direct ? in : h->h_in;
+    float*       dst = direct ? out : h->h_out;
+    if (!direct) memcpy(h->h_in, in, h->inBytes);
     if (h->useGraph && h->pl.kind != SC_KIND_TV) {
+        if (h->graphExec && (h->graphIn != (void*)src || h->graphOut != (void*)dst)) {
+            scdev_graph_destroy(h->graphExec);
+            h->graphExec = NULL;
+        }
         if (!h->graphExec) {
             e = scdev_graph_begin(h->stream);
-            if (!e) e = scdev_memcpy_h2d_async(h->d_in, h->h_in, h->inBytes, h->stream);
+            if (!e) e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
             if (!e) e = enqueue_block(h, h->d_in, h->d_out);
-            if (!e) e = scdev_memcpy_d2h_async(h->h_out, h->d_out, h->outBytes, h->stream);
+            if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
             int e2 = scdev_graph_end(h->stream, &h->graphExec);
             if (!e) e = e2;
             if (e) { h->graphExec = NULL; h->useGraph = 0; h_fail(h, SAFCONV_ERR_CUDA, "graph capture", e); return; }
+            h->graphIn = (void*)src; h->graphOut = (void*)dst;
         }
         e = scdev_graph_launch(h->graphExec, h->stream);
     } else {
-        e = scdev_memcpy_h2d_async(h->d_in, h->h_in, h->inBytes, h->stream);
+        e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
         if (!e) {
             if (h->pl.kind == SC_KIND_TV) {
                 e = scdev_tv_fused(&h->pl, &h->b, h->d_in, h->d_out, irIdx, h->tvLast, h->tvLast2, h->stream);
@@ -418,11 +471,11 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
                 e = enqueue_block(h, h->d_in, h->d_out);
             }
         }
-        if (!e) e = scdev_memcpy_d2h_async(h->h_out, h->d_out, h->outBytes, h->stream);
+        if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
     }
     if (!e) e = scdev_stream_sync(h->stream);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
-    memcpy(out, h->h_out, h->outBytes);
+    if (!direct) memcpy(out, h->h_out, h->outBytes);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -566,8 +619,11 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
     int e = scdev_set_device(h->device);
     const size_t inStride = (size_t)h->pl.nIn * h->pl.hop, outStride = (size_t)h->pl.nOutLocal * h->pl.hop;
-    for (int b = 0; b < nBlocks && !e; b++)
-        e = enqueue_block(h, d_in + (size_t)b * inStride, d_out + (size_t)b * outStride);
+    const int mb = (h->pl.kind == SC_KIND_MATRIX && h->batching) ? h->pl.maxBatch : 1;
+    for (int b = 0; b < nBlocks && !e; b += mb) {
+        const int n = (nBlocks - b < mb) ? nBlocks - b : mb;
+        e = enqueue_blocks(h, d_in + (size_t)b * inStride, d_out + (size_t)b * outStride, n);
+    }
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "apply_device", e);
     return SAFCONV_OK;
 }
@@ -648,10 +704,12 @@ int safconv_enable_kernel_timing(void* hp, int nBlocks)
         free(h->evRing);
         h->evRing = NULL;
     }
+    free(h->evMask); h->evMask = NULL;
     h->timingCap = h->timingCount = 0;
     if (nBlocks == 0) return SAFCONV_OK;
     h->evRing = (void**)calloc((size_t)4 * nBlocks, sizeof(void*));
-    if (!h->evRing) return h_fail(h, SAFCONV_ERR_NOMEM, "event ring", 0);
+    h->evMask = (unsigned char*)calloc((size_t)nBlocks, 1);
+    if (!h->evRing || !h->evMask) return h_fail(h, SAFCONV_ERR_NOMEM, "event ring", 0);
     for (int i = 0; i < 4 * nBlocks; i++) {
         int e = scdev_event_create(&h->evRing[i]);
         if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaEventCreate", e);
@@ -670,18 +728,16 @@ int safconv_get_kernel_times(void* hp, float ms[3], int* nBlocksOut)
     if (nBlocksOut) *nBlocksOut = n;
     if (n == 0) return SAFCONV_OK;
     const int matrix = (h->pl.kind == SC_KIND_MATRIX);
-    int e = scdev_event_sync(h->evRing[4 * (size_t)(n - 1) + (matrix ? 3 : 2)]);
+    int e = scdev_stream_sync(h->stream);
     double acc[3] = { 0, 0, 0 };
     for (int b = 0; b < n && !e; b++) {
         void** ev = h->evRing + 4 * (size_t)b;
         float t = 0.f;
-        if (matrix) {
-            e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t;
-            if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
-            if (!e) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
-        } else {
-            e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t;
-        }
+        /* batched launches: one forward-FFT interval (first block of a batch) and one inverse-FFT interval
+         * (last block of a batch) cover the whole batch; the totals are averaged per block below */
+        if (matrix && (h->evMask[b] & 1)) { e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t; }
+        if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
+        if (!e && matrix && (h->evMask[b] & 2)) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
     }
     h->timingCount = 0;
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "kernel timing", e);
@@ -695,6 +751,8 @@ int safconv_set_option(void* hp, const char* name, int value)
     if (!h || !name) return SAFCONV_ERR_ARG;
     if (!strcmp(name, "mac_hints")) { h->pl.macHints = value ? 1 : 0; }
     else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
+    else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
+    else if (!strcmp(name, "detect_pinned")) { h->detectPinned = value ? 1 : 0; }
     else return SAFCONV_ERR_ARG;
     if (h->graphExec) { scdev_set_device(h->device); scdev_stream_sync(h->stream); scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }
     return SAFCONV_OK;

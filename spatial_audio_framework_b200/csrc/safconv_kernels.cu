@@ -52,14 +52,15 @@ __device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((un
 /* ------------------------------------------------------------------------------------------ */
 /*  M-point complex FFT in shared memory, decimation in frequency                              */
 /*  input: natural order in s[0..M) ; output: s[bitrev(k)] holds bin k                          */
-/*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)])                        */
+/*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)]); the kernels copy the    */
+/*  table into shared memory first (load_twiddles) so that no pass waits on an L2 round trip.    */
 /*  INV conjugates every twiddle (unnormalised inverse transform).                              */
 /*  Requires M >= 32, blockDim.x a multiple of 32; ends with __syncthreads().                   */
 /* ------------------------------------------------------------------------------------------ */
 template <bool INV>
 __device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
 {
-    float2 w = __ldg(tw + idx);
+    float2 w = tw[idx];
     if (INV) w.y = -w.y;
     return w;
 }
@@ -145,6 +146,12 @@ __device__ void cfft_dif(float2* s, const int M, const int logM, const float2* _
     }
 }
 
+/* copy the twiddle table into shared memory (coalesced; overlaps the input load that follows) */
+__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M)
+{
+    for (int n = threadIdx.x; n < M; n += blockDim.x) stw[n] = __ldg(gtw + n);
+}
+
 /* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
 __device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M)
 {
@@ -173,7 +180,7 @@ __device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, in
     const float2 b = s[bitrev(M - k, logM)];
     const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-    const float2 t = cmulf(__ldg(tw + k), O);
+    const float2 t = cmulf(tw[k], O);
     Xk  = make_float2(E.x + t.x, E.y + t.y);
     Xmk = make_float2(E.x - t.x, t.y - E.y);
 }
@@ -185,7 +192,7 @@ __device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, const fl
     const float2 A = Z[k], B = Z[M - k];
     const float2 E = make_float2(A.x + B.x, A.y - B.y);
     const float2 D = make_float2(A.x - B.x, A.y + B.y);
-    const float2 O = cmul_conjb(D, __ldg(tw + k));
+    const float2 O = cmul_conjb(D, tw[k]);
     Z[k]     = make_float2(E.x - O.y, E.y + O.x);
     Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
 }
@@ -251,6 +258,8 @@ struct FilterArgs {
 __global__ void filter_fft_kernel(FilterArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + a.M;
+    load_twiddles(stw, a.tw, a.M);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
     const float* src;
     if (a.kind == SC_KIND_MATRIX) src = a.h + ((size_t)no * a.nIn + ni) * a.len;
@@ -265,7 +274,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
         sm[n] = v;
     }
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, a.tw);
+    cfft_dif<false>(sm, a.M, a.logM, stw);
 
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
@@ -276,7 +285,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
             k2 = 0;
             Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, stw, Xk, Xmk);
         }
         if (a.kind == SC_KIND_MATRIX) {
             const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
@@ -299,21 +308,23 @@ __global__ void filter_fft_kernel(FilterArgs a)
 /*  grid (nIn)                                                                                  */
 /* ------------------------------------------------------------------------------------------ */
 struct InFftArgs {
-    const float* in;       /* [nIn][hop] */
-    float2*      X;        /* [nKT][P][nIn][32] */
+    const float* in;       /* [B][nIn][hop] */
+    float2*      X;        /* [nKT][RS][nIn][32] */
     const float2* tw;
     const unsigned int* counters;
-    int hop, nIn, M, logM, P;
+    int hop, nIn, M, logM, RS;
 };
 
 __global__ void input_fft_kernel(InFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const int ni = blockIdx.x;
-    const int slot = (int)(a.counters[0] % (unsigned)a.P);
-    load_real_block(sm, a.in + (size_t)ni * a.hop, a.hop, a.M);
+    float2* stw = sm + a.M;
+    const int ni = blockIdx.x, b = blockIdx.y;
+    const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
+    load_twiddles(stw, a.tw, a.M);
+    load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M);
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, a.tw);
+    cfft_dif<false>(sm, a.M, a.logM, stw);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
         int k2 = a.M - k;
@@ -322,10 +333,10 @@ __global__ void input_fft_kernel(InFftArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, stw, Xk, Xmk);
         }
-        a.X[(((size_t)(k >> 5) * a.P + slot) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
-        a.X[(((size_t)(k2 >> 5) * a.P + slot) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
+        a.X[(((size_t)(k >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
+        a.X[(((size_t)(k2 >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
     }
 }
 
@@ -383,13 +394,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
 
 struct MacArgs {
     const float2* H;               /* [unit][nIn][OTsz][32], unit = (ot*nKT + kt)*P + p */
-    const float2* X;               /* [kt][slot][nIn][32] */
-    float2*       Zp;              /* [partial slot][OTsz][32] */
+    const float2* X;               /* [kt][RS ring slots][nIn][32] */
+    float2*       Zp;              /* [partial slot][OTsz][32] (of this block) */
     const unsigned int* counters;
     const int*    ctaBase;
     long long totalStages;
     int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
     int NS;                        /* pipeline depth (stages)                */
+    int RS, blk;                   /* delay-line ring size; block offset inside the current batch */
     int stageHBytes, stageXBytes;  /* shared-memory bytes reserved per stage */
 };
 
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     if (warp == SC_MAC_CWARPS) {
         /* ===================== TMA producer (one elected lane) ===================== */
         if (lane == 0) {
-            const int head = (int)(a.counters[0] % (unsigned)a.P);      /* slot of the newest block */
+            const int head = (int)((a.counters[0] + (unsigned)a.blk) % (unsigned)a.RS);   /* slot of the newest block */
             const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
             const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
             const float2* srcH = a.H + ((size_t)unit0 * a.nIn + (size_t)sidx * a.SNI) * a.OTsz * SC_BK;
@@ -440,8 +452,8 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
                 const int cnt  = min(a.SNI, a.nIn - ni0);
                 const uint32_t bytesH = (uint32_t)cnt * rowH;
                 const uint32_t bytesX = (uint32_t)cnt * (SC_BK * 8);
-                int slot = head - p; if (slot < 0) slot += a.P;
-                const float2* srcX = a.X + (((size_t)kt * a.P + slot) * a.nIn + ni0) * SC_BK;
+                int slot = head - p; if (slot < 0) slot += a.RS;
+                const float2* srcX = a.X + (((size_t)kt * a.RS + slot) * a.nIn + ni0) * SC_BK;
                 mbar_expect_tx(&full[s], bytesH + bytesX);
                 if (a.hints) {
                     tma_bulk_g2s_hint(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s], polH);
@@ -543,42 +555,95 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 /*  grid (nOutLocal)                                                                             */
 /* ------------------------------------------------------------------------------------------ */
 struct IfftArgs {
-    const float2* Zp;
-    const int* grpStart;
-    const int* grpList;
+    const float2* Zp;      /* [B][nSlots][OTsz][32] */
+    const int* grpStart;   /* partial slots of group g are grpStart[g] .. grpStart[g+1]-1 (consecutive) */
     const float2* tw;
-    float* out;            /* [nOutLocal][hop] */
+    float* out;            /* [B][nOutLocal][hop] */
     float* tail;           /* [nOutLocal][hop] */
+    float* zt;             /* batched path: [B][nOutLocal][2*hop] scaled inverse transforms */
     unsigned int* counters;
-    int hop, M, logM, nKT, OTsz;
+    size_t zpStride;       /* float2 elements of Zp per block */
+    int hop, M, logM, nKT, OTsz, nOutLocal, B;
     float scale;           /* 1/N */
 };
 
+/* sum the split-K partial tiles of output `no` into sm[0..M) and run the inverse real FFT (bit-reversed result) */
+__device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2* Zp, int no, float2* sm, float2* stw)
+{
+    const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+    load_twiddles(stw, a.tw, a.M);
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const int g = ot * a.nKT + (k >> 5);
+        const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
+        const float2* src = Zp + ((size_t)q0 * a.OTsz + nl) * SC_BK + (k & 31);
+        const size_t qs = (size_t)a.OTsz * SC_BK;
+        float2 z = make_float2(0.f, 0.f);
+        int q = q0;
+        /* fixed summation order (ascending slot), four independent loads in flight */
+        for (; q + 4 <= q1; q += 4, src += 4 * qs) {
+            const float2 v0 = src[0], v1 = src[qs], v2 = src[2 * qs], v3 = src[3 * qs];
+            z = caddf(caddf(caddf(caddf(z, v0), v1), v2), v3);
+        }
+        for (; q < q1; ++q, src += qs) z = caddf(z, src[0]);
+        sm[k] = z;
+    }
+    __syncthreads();
+    inv_split_all(sm, a.M, stw);
+    cfft_dif<true>(sm, a.M, a.logM, stw);
+}
+
+/* one block: grid (nOutLocal) */
 __global__ void ifft_ola_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x;
-    const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
-    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
-        const int g = ot * a.nKT + (k >> 5);
-        const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
-        float2 z = make_float2(0.f, 0.f);
-        for (int q = q0; q < q1; ++q) {
-            const int slot = __ldg(a.grpList + q);
-            z = caddf(z, a.Zp[((size_t)slot * a.OTsz + nl) * SC_BK + (k & 31)]);
-        }
-        sm[k] = z;
-    }
-    __syncthreads();
-    inv_split_all(sm, a.M, a.tw);
-    cfft_dif<true>(sm, a.M, a.logM, a.tw);
+    gather_and_ifft(a, a.Zp, no, sm, sm + a.M);
     ola_store(sm, a.hop, a.logM, a.scale, a.out + (size_t)no * a.hop, a.tail + (size_t)no * a.hop);
     advance_block_counter(a.counters, gridDim.x);
 }
 
+/* batch of B blocks, step 1: grid (nOutLocal, B) -> zt[b][no][0..2*hop) = z/N */
+__global__ void ifft_batch_kernel(IfftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int no = blockIdx.x, b = blockIdx.y;
+    gather_and_ifft(a, a.Zp + (size_t)b * a.zpStride, no, sm, sm + a.M);
+    float* z = a.zt + ((size_t)b * a.nOutLocal + no) * 2 * a.hop;
+    for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
+}
+
+/* batch step 2: overlap-add along the batch (reference .c:230-233), one thread per (no, i); same two
+ * addends per sample as the one-block kernel, so both paths give identical bits */
+__global__ void ola_batch_kernel(IfftArgs a)
+{
+    const size_t n = (size_t)a.nOutLocal * a.hop;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) {
+        const int no = (int)(idx / a.hop), i = (int)(idx - (size_t)no * a.hop);
+        float prev = a.tail[idx];
+        for (int b = 0; b < a.B; ++b) {
+            const float* z = a.zt + ((size_t)b * a.nOutLocal + no) * 2 * a.hop;
+            a.out[(size_t)b * n + idx] = z[i] + prev;
+            prev = z[i + a.hop];
+        }
+        a.tail[idx] = prev;
+    }
+    /* last CTA advances the block counter by B */
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&a.counters[1], 1u);
+        if (t == gridDim.x - 1) {
+            a.counters[1] = 0;
+            __threadfence();
+            atomicAdd(&a.counters[0], (unsigned)a.B);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /*  multiConv: everything for one channel in one CTA  (reference .c:388-413)                    */
-/*  grid (nCH) ; shared memory: 2*M float2                                                      */
+/*  grid (nCH) ; shared memory: 3*M float2 (two work buffers + twiddles)                        */
 /* ------------------------------------------------------------------------------------------ */
 struct MultiArgs {
     const float* in;       /* [nCH][hop] */
@@ -608,14 +673,16 @@ __global__ void multi_fused_kernel(MultiArgs a)
     extern __shared__ __align__(16) float2 sm[];
     float2* A = sm;
     float2* B = sm + a.M;
+    float2* stw = sm + 2 * a.M;
     const int c = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
     float2* Xc = a.X + (size_t)c * a.P * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
+    load_twiddles(stw, a.tw, a.M);
     load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M);
     __syncthreads();
-    cfft_dif<false>(A, a.M, a.logM, a.tw);
+    cfft_dif<false>(A, a.M, a.logM, stw);
     float2* Xnew = Xc + (size_t)head * a.M;
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
@@ -625,7 +692,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(A, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(A, k, a.M, a.logM, stw, Xk, Xmk);
         }
         B[k] = Xk;  B[k2] = Xmk;
         Xnew[k] = Xk;  Xnew[k2] = Xmk;
@@ -645,15 +712,15 @@ __global__ void multi_fused_kernel(MultiArgs a)
         A[k] = acc;
     }
     __syncthreads();
-    inv_split_all(A, a.M, a.tw);
-    cfft_dif<true>(A, a.M, a.logM, a.tw);
+    inv_split_all(A, a.M, stw);
+    cfft_dif<true>(A, a.M, a.logM, stw);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
 }
 
 /* ------------------------------------------------------------------------------------------ */
 /*  TVConv: one CTA per output channel (reference .c:546-620)                                   */
-/*  shared memory: 4*M float2  (X spectrum, three output frames)                                */
+/*  shared memory: 5*M float2  (X spectrum, three output frames, twiddles)                       */
 /* ------------------------------------------------------------------------------------------ */
 struct TvArgs {
     const float* in;       /* [hop] */
@@ -676,6 +743,8 @@ __global__ void tv_fused_kernel(TvArgs a)
     float2* Z0 = sm + a.M;
     float2* Z1 = sm + 2 * a.M;
     float2* Z2 = sm + 3 * a.M;
+    float2* stw = sm + 4 * a.M;
+    load_twiddles(stw, a.tw, a.M);
     const int no = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
     const bool need1 = (a.ir0 != a.ir1);
@@ -684,7 +753,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     /* every CTA transforms the (single) input block; CTA 0 also stores it in the ring */
     load_real_block(Z0, a.in, a.hop, a.M);
     __syncthreads();
-    cfft_dif<false>(Z0, a.M, a.logM, a.tw);
+    cfft_dif<false>(Z0, a.M, a.logM, stw);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
         int k2 = a.M - k;
@@ -693,7 +762,7 @@ __global__ void tv_fused_kernel(TvArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(Z0, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(Z0, k, a.M, a.logM, stw, Xk, Xmk);
         }
         Xs[k] = Xk;  Xs[k2] = Xmk;
         if (no == 0) {
@@ -722,9 +791,9 @@ __global__ void tv_fused_kernel(TvArgs a)
         Z0[k] = z0; Z1[k] = z1; Z2[k] = z2;
     }
     __syncthreads();
-    inv_split_all(Z0, a.M, a.tw);  cfft_dif<true>(Z0, a.M, a.logM, a.tw);
-    inv_split_all(Z1, a.M, a.tw);  cfft_dif<true>(Z1, a.M, a.logM, a.tw);
-    inv_split_all(Z2, a.M, a.tw);  cfft_dif<true>(Z2, a.M, a.logM, a.tw);
+    inv_split_all(Z0, a.M, stw);  cfft_dif<true>(Z0, a.M, a.logM, stw);
+    inv_split_all(Z1, a.M, stw);  cfft_dif<true>(Z1, a.M, a.logM, stw);
+    inv_split_all(Z2, a.M, stw);  cfft_dif<true>(Z2, a.M, a.logM, stw);
     /* cross-fade (reference .c:494-497, 605-615) */
     float* t0 = a.tail0 + (size_t)no * a.hop;
     float* t1 = a.tail1 + (size_t)no * a.hop;
@@ -767,8 +836,14 @@ int scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream)
 { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream); }
 int scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream)
 { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream); }
-int scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes)
-{ return (int)cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); }
+/* Stream-ordered upload that has fully landed on return.  (A plain cudaMemcpy from pageable memory may
+ * return while the last staged chunk is still in flight and is only ordered against the legacy default
+ * stream -- not against the handle's non-blocking stream that the create-time kernels run on.) */
+int scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes, void* stream)
+{
+    SC_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
 int scdev_stream_create(void** s)
 { cudaStream_t st; cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); *s = (void*)st; return (int)e; }
 int scdev_stream_destroy(void* s) { return s ? (int)cudaStreamDestroy((cudaStream_t)s) : 0; }
@@ -816,16 +891,18 @@ static mac_fn_t mac_fn(int R)
 
 int scdev_prepare(const scdev_plan* pl)
 {
-    const int big = 1 << 16;
-    if (fft_smem(pl, 1) > 48 * 1024) {
+    /* FFT kernels hold the data and the twiddle table in shared memory: 2*M float2 (<= 128 KB) */
+    if (fft_smem(pl, 2) > 48 * 1024) {
+        const int big = (int)fft_smem(pl, 2);
         SC_CHECK(cudaFuncSetAttribute(filter_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SC_CHECK(cudaFuncSetAttribute(input_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        SC_CHECK(cudaFuncSetAttribute(ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
-    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 2) > 48 * 1024)
-        SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
-    if (pl->kind == SC_KIND_TV && fft_smem(pl, 4) > 48 * 1024)
-        SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 4)));
+    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 3) > 48 * 1024)
+        SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 3)));
+    if (pl->kind == SC_KIND_TV && fft_smem(pl, 5) > 48 * 1024)
+        SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 5)));
     if (pl->kind == SC_KIND_MATRIX)
         SC_CHECK(cudaFuncSetAttribute(mac_fn(pl->R), cudaFuncAttributeMaxDynamicSharedMemorySize, pl->macSmemBytes));
     return 0;
@@ -840,48 +917,69 @@ int scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const floa
     if (pl->kind == SC_KIND_MATRIX) {
         if (pl->nOutLocal > 65535 || pl->nIn > 65535) return (int)cudaErrorInvalidValue;   /* grid.y / grid.z limits */
         dim3 grid(pl->P, pl->nIn, pl->nOutLocal);
-        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     } else {
         const int rows = (pl->kind == SC_KIND_TV) ? pl->nIRs * pl->nOutLocal : pl->nOutLocal;
         if (rows > 65535) return (int)cudaErrorInvalidValue;
         dim3 grid(pl->P, 1, rows);
-        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     }
     return (int)cudaGetLastError();
 }
 
-int scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, void* stream)
+int scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, int nBlocks, void* stream)
 {
     InFftArgs a;
     a.in = d_in; a.X = (float2*)b->X; a.tw = (const float2*)b->tw; a.counters = b->counters;
-    a.hop = pl->hop; a.nIn = pl->nIn; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
-    input_fft_kernel<<<pl->nIn, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    a.hop = pl->hop; a.nIn = pl->nIn; a.M = pl->M; a.logM = pl->logM; a.RS = pl->RS;
+    dim3 grid(pl->nIn, nBlocks);
+    input_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
-int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, void* stream)
+int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, void* stream)
 {
     MacArgs a;
-    a.H = (const float2*)b->H; a.X = (const float2*)b->X; a.Zp = (float2*)b->Zp;
+    a.H = (const float2*)b->H; a.X = (const float2*)b->X;
+    a.Zp = (float2*)b->Zp + (size_t)blk * pl->nSlots * pl->OTsz * SC_BK;
     a.counters = b->counters; a.ctaBase = b->ctaBase;
     a.totalStages = pl->totalStages;
     a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.P = pl->P; a.nKT = pl->nKT;
     a.SNI = pl->SNI; a.SPU = pl->SPU; a.WGo = pl->WGo; a.WGk = pl->WGk; a.hints = pl->macHints;
-    a.NS = pl->macStages;
+    a.NS = pl->macStages; a.RS = pl->RS; a.blk = blk;
     a.stageHBytes = pl->SNI * pl->OTsz * SC_BK * 8;
     a.stageXBytes = pl->SNI * SC_BK * 8;
     mac_fn(pl->R)<<<pl->macGrid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
+static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks)
+{
+    a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart;
+    a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
+    a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
+    a.nOutLocal = pl->nOutLocal; a.B = nBlocks;
+    a.scale = 1.0f / (float)pl->N;
+}
+
 int scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream)
 {
     IfftArgs a;
-    a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart; a.grpList = b->grpList;
-    a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.counters = b->counters;
-    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
-    a.scale = 1.0f / (float)pl->N;
-    ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 1), (cudaStream_t)stream>>>(a);
+    fill_ifft_args(a, pl, b, d_out, 1);
+    ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream)
+{
+    IfftArgs a;
+    fill_ifft_args(a, pl, b, d_out, nBlocks);
+    dim3 grid(pl->nOutLocal, nBlocks);
+    ifft_batch_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    SC_CHECK(cudaGetLastError());
+    const size_t n = (size_t)pl->nOutLocal * pl->hop;
+    ola_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -892,7 +990,7 @@ int scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_
     a.tw = (const float2*)b->tw; a.tail = b->tail; a.counters = b->counters;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
     a.scale = 1.0f / (float)pl->N;
-    multi_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    multi_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 3), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -905,8 +1003,15 @@ int scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in,
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nOut = pl->nOutLocal;
     a.ir0 = irIdx; a.ir1 = irLast; a.ir2 = irLast2;
     a.scale = 1.0f / (float)pl->N;
-    tv_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 4), (cudaStream_t)stream>>>(a);
+    tv_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 5), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
+}
+
+int scdev_is_pinned_host(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeHost;
 }
 
 } /* extern "C" */

@@ -11,13 +11,15 @@ class Plan(C.Structure):   # mirrors scdev_plan in csrc/safconv_dev.h
                 ("N", C.c_int), ("M", C.c_int), ("logM", C.c_int), ("P", C.c_int), ("fftThreads", C.c_int),
                 ("nKT", C.c_int), ("nOT", C.c_int), ("OTsz", C.c_int), ("SNI", C.c_int), ("SPU", C.c_int),
                 ("R", C.c_int), ("WGo", C.c_int), ("WGk", C.c_int), ("totalStages", C.c_longlong),
-                ("macGrid", C.c_int), ("nGroups", C.c_int), ("nSlots", C.c_int), ("macHints", C.c_int),
+                ("macGrid", C.c_int), ("nGroups", C.c_int), ("nSlots", C.c_int), ("RS", C.c_int), ("maxBatch", C.c_int),
+                ("macHints", C.c_int),
                 ("macSmemBytes", C.c_int), ("macStages", C.c_int), ("macStageBytes", C.c_int),
                 ("nIRs", C.c_int)]
 
 
 def plan(saf, hop, L, nIn, nOut, sms=148, kind=0):
     lib = saf.lib()
+    assert lib.safconv_debug_plan_size() == C.sizeof(Plan), "tests/test_plan.py Plan mirror is out of date"
     cap = 1 << 16
     pl = Plan()
     cta = (C.c_int * cap)()
@@ -81,4 +83,6 @@ def test_mac_tiling_and_split_tables(saf, hop, L, nIn, nOut, sms):
         slots = grpList[grpStart[g]:grpStart[g + 1]]
         assert len(slots) >= 1
         assert all(produced[s] == g for s in slots)
-    assert sorted(grpList.tolist()) == list(range(pl.nSlots))
+    # the slots of a group are consecutive: K3 sums slots grpStart[g] .. grpStart[g+1]-1 in ascending order
+    assert grpList.tolist() == list(range(pl.nSlots))
+    assert pl.maxBatch >= 1 and pl.RS == pl.P + pl.maxBatch
