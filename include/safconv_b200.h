@@ -161,6 +161,7 @@ typedef struct safconv_info {
     int hopSize, length_h, nCHin, nCHout, nOutLocal, outBegin;
     int fftSize, nBinsPacked, numFilterBlocks;
     int macGrid, macStages, macThreads;     /* launch geometry of the filter-streaming MAC */
+    int maxBatch;                           /* blocks per launch group of safconv_apply_device_blocks */
     int device;
     size_t bytesFilters, bytesDelayLine;    /* resident device bytes */
     double algBytesPerBlock;                /* SURVEY.md §8(d) algorithmic bytes per block for this handle */
@@ -169,15 +170,18 @@ typedef struct safconv_info {
 int safconv_get_info(void* h, safconv_info* info);
 
 /**
- * Timing helper for benchmarks.  safconv_enable_kernel_timing(h, nBlocks) allocates a ring of CUDA
- * events for up to nBlocks blocks (0 disables); while enabled, every block enqueued by
- * saf_*_apply / safconv_apply_device* records events between its kernels on the handle's stream.
- * safconv_get_kernel_times synchronises on the last recorded block, returns the AVERAGE per-block
- * durations over the recorded blocks (ms[0] = forward FFT, ms[1] = filter-streaming MAC [or the fused
- * multiConv kernel], ms[2] = inverse FFT + overlap-add; FFT launches shared by a batch of blocks are
- * divided by the number of blocks), how many blocks were averaged, and restarts the ring.
+ * Timing helper for benchmarks.  safconv_enable_kernel_timing(h, nGroups) allocates CUDA events for up to
+ * nGroups launch groups (0 disables).  A launch group is what one saf_*_apply call or one batch of
+ * safconv_apply_device_blocks enqueues: [forward FFT launch][ONE filter-streaming MAC launch covering all
+ * blocks of the group][inverse FFT + overlap-add launch(es)]; while enabled, events are recorded between
+ * those launches on the handle's stream.
+ * safconv_get_kernel_totals synchronises the stream and returns the TOTAL milliseconds per kernel class
+ * (msTotal[0] forward FFT, [1] MAC [or the fused multiConv kernel], [2] inverse FFT + overlap-add), the number
+ * of launch groups and the number of blocks they covered, and restarts the recording.
+ * safconv_get_kernel_times is the same divided by the number of blocks (average per block).
  */
-int safconv_enable_kernel_timing(void* h, int nBlocks);
+int safconv_enable_kernel_timing(void* h, int nGroups);
+int safconv_get_kernel_totals(void* h, float msTotal[3], int* nLaunchGroups, int* nBlocks);
 int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
 
 /** Tuning knobs (mostly for benchmarks / tests). Returns 0 on success.

@@ -24,7 +24,7 @@ class SafConvInfo(C.Structure):
         ("nCHout", C.c_int), ("nOutLocal", C.c_int), ("outBegin", C.c_int),
         ("fftSize", C.c_int), ("nBinsPacked", C.c_int), ("numFilterBlocks", C.c_int),
         ("macGrid", C.c_int), ("macStages", C.c_int), ("macThreads", C.c_int),
-        ("device", C.c_int),
+        ("maxBatch", C.c_int), ("device", C.c_int),
         ("bytesFilters", C.c_size_t), ("bytesDelayLine", C.c_size_t),
         ("algBytesPerBlock", C.c_double), ("macAlgBytesPerBlock", C.c_double),
     ]
@@ -39,7 +39,8 @@ EXPORTED_SYMBOLS = [
     "safconv_matrixConv_create_shard", "safconv_matrixConv_create_from_shard", "safconv_multiConv_create_shard",
     "safconv_apply_device", "safconv_apply_device_blocks",
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
-    "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_set_option",
+    "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_get_kernel_totals",
+    "safconv_set_option",
 ]
 
 
@@ -100,6 +101,7 @@ def lib():
     L.safconv_get_info.argtypes = [C.c_void_p, C.POINTER(SafConvInfo)]
     L.safconv_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.safconv_get_kernel_times.argtypes = [C.c_void_p, _f32p, C.POINTER(C.c_int)]
+    L.safconv_get_kernel_totals.argtypes = [C.c_void_p, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.safconv_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.safconv_debug_plan_size.restype = C.c_int
     _lib = L
@@ -189,6 +191,14 @@ class _Base:
         if self._lib.safconv_get_kernel_times(self._h, ms, C.byref(n)):
             self._raise_if_error()
         return [ms[0], ms[1], ms[2]], n.value
+
+    def kernel_totals_ms(self):
+        """(total ms [fwd FFT, MAC, iFFT+OLA], launch groups, blocks covered); restarts the recording."""
+        ms = (C.c_float * 3)()
+        g, n = C.c_int(0), C.c_int(0)
+        if self._lib.safconv_get_kernel_totals(self._h, ms, C.byref(g), C.byref(n)):
+            self._raise_if_error()
+        return [ms[0], ms[1], ms[2]], g.value, n.value
 
     def run(self, x: np.ndarray) -> np.ndarray:
         """Block-by-block processing of a whole signal x[nIn, T] -> y[nOut, T] via the host API."""

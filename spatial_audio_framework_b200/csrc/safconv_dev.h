@@ -107,8 +107,9 @@ int  scdev_prepare(const scdev_plan* pl);
 int  scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const float* d_h, void* stream);
 /* K1: forward real FFT of nBlocks new input blocks d_in [nBlocks][nIn][hop] into ring slots (counter + b) % RS */
 int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, int nBlocks, void* stream);
-/* K2: filter-streaming complex multiply-accumulate over partitions x inputs for block `blk` of the batch */
-int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, void* stream);
+/* K2: filter-streaming complex multiply-accumulate over partitions x inputs for blocks blk .. blk+nBlocks-1 of
+ * the batch, streamed back to back inside ONE launch (every block streams the filter spectra once) */
+int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, void* stream);
 /* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ (one block) */
 int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
 /* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */

@@ -40,9 +40,9 @@ typedef struct safconv_handle {
     int        batching;             /* 1: safconv_apply_device_blocks shares the FFT launches across a batch */
     int        detectPinned;         /* 1: DMA straight from/to caller buffers that are already page-locked */
     void*      graphExec;
-    int        timingCap, timingCount;   /* ring of 4 CUDA events per block while kernel timing is enabled */
+    int        timingCap, timingCount;   /* 4 CUDA events per enqueued launch group while kernel timing is enabled */
     void**     evRing;
-    unsigned char* evMask;           /* per block: bit0 = (ev0,ev1) brackets a K1 launch, bit1 = (ev2,ev3) brackets K3 */
+    int*       evBlocks;             /* blocks covered by each launch group */
     void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
 } safconv_handle;
@@ -230,7 +230,7 @@ static void handle_free(safconv_handle* h)
     if (h->stream) scdev_stream_sync(h->stream);
     scdev_graph_destroy(h->graphExec);
     if (h->evRing) { for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]); free(h->evRing); }
-    free(h->evMask);
+    free(h->evBlocks);
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
     scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart);
@@ -399,31 +399,31 @@ static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, in
 {
     const scdev_plan* pl = &h->pl;
     void** ev = NULL;
-    unsigned char* mask = NULL;
-    if (h->timingCap && h->timingCount + nBlocks <= h->timingCap) {
-        ev = h->evRing + 4 * (size_t)h->timingCount;
-        mask = h->evMask + h->timingCount;
-        h->timingCount += nBlocks;
-        memset(mask, 0, (size_t)nBlocks);
-    }
     int e = 0;
     if (pl->kind == SC_KIND_MATRIX) {
-        if (ev) { scdev_event_record(ev[0], h->stream); mask[0] |= 1; }
-        e = scdev_input_fft(pl, &h->b, d_in, nBlocks, h->stream);
-        for (int b = 0; b < nBlocks && !e; b++) {
-            if (ev) scdev_event_record(ev[4 * b + 1], h->stream);
-            e = scdev_mac(pl, &h->b, b, h->stream);
-            if (ev) scdev_event_record(ev[4 * b + 2], h->stream);
+        if (h->timingCap && h->timingCount < h->timingCap) {
+            ev = h->evRing + 4 * (size_t)h->timingCount;
+            h->evBlocks[h->timingCount++] = nBlocks;
         }
+        if (ev) scdev_event_record(ev[0], h->stream);
+        e = scdev_input_fft(pl, &h->b, d_in, nBlocks, h->stream);
+        if (ev) scdev_event_record(ev[1], h->stream);
+        if (!e) e = scdev_mac(pl, &h->b, 0, nBlocks, h->stream);
+        if (ev) scdev_event_record(ev[2], h->stream);
         if (!e) e = (nBlocks == 1) ? scdev_ifft_ola(pl, &h->b, d_out, h->stream)
                                    : scdev_ifft_ola_batch(pl, &h->b, d_out, nBlocks, h->stream);
-        if (ev) { scdev_event_record(ev[4 * (nBlocks - 1) + 3], h->stream); mask[nBlocks - 1] |= 2; }
+        if (ev) scdev_event_record(ev[3], h->stream);
     } else if (pl->kind == SC_KIND_MULTI) {
         const size_t inStride = (size_t)pl->nIn * pl->hop, outStride = (size_t)pl->nOutLocal * pl->hop;
         for (int b = 0; b < nBlocks && !e; b++) {
-            if (ev) scdev_event_record(ev[4 * b + 1], h->stream);
+            ev = NULL;
+            if (h->timingCap && h->timingCount < h->timingCap) {
+                ev = h->evRing + 4 * (size_t)h->timingCount;
+                h->evBlocks[h->timingCount++] = 1;
+            }
+            if (ev) scdev_event_record(ev[1], h->stream);
             e = scdev_multi_fused(pl, &h->b, d_in + b * inStride, d_out + b * outStride, h->stream);
-            if (ev) scdev_event_record(ev[4 * b + 2], h->stream);
+            if (ev) scdev_event_record(ev[2], h->stream);
         }
     } else {
         return (int)SAFCONV_ERR_ARG;
@@ -677,6 +677,7 @@ int safconv_get_info(void* hp, safconv_info* info)
     info->nCHin = pl->nIn; info->nCHout = h->nCHoutTotal; info->nOutLocal = pl->nOutLocal; info->outBegin = h->outBegin;
     info->fftSize = pl->N; info->nBinsPacked = pl->M; info->numFilterBlocks = pl->P;
     info->macGrid = pl->macGrid; info->macStages = pl->macStages; info->macThreads = (SC_MAC_CWARPS + 1) * 32;
+    info->maxBatch = (pl->kind == SC_KIND_MATRIX) ? pl->maxBatch : 1;
     info->device = h->device;
     info->bytesFilters = h->bytesH; info->bytesDelayLine = h->bytesX;
     /* algorithmic bytes per block, nBins = hop + 1 complex bins of 8 bytes */
@@ -693,10 +694,10 @@ int safconv_get_info(void* hp, safconv_info* info)
     return SAFCONV_OK;
 }
 
-int safconv_enable_kernel_timing(void* hp, int nBlocks)
+int safconv_enable_kernel_timing(void* hp, int nGroups)
 {
     safconv_handle* h = as_handle(hp);
-    if (!h || nBlocks < 0) return SAFCONV_ERR_ARG;
+    if (!h || nGroups < 0) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     scdev_stream_sync(h->stream);
     if (h->evRing) {
@@ -704,44 +705,56 @@ int safconv_enable_kernel_timing(void* hp, int nBlocks)
         free(h->evRing);
         h->evRing = NULL;
     }
-    free(h->evMask); h->evMask = NULL;
+    free(h->evBlocks); h->evBlocks = NULL;
     h->timingCap = h->timingCount = 0;
-    if (nBlocks == 0) return SAFCONV_OK;
-    h->evRing = (void**)calloc((size_t)4 * nBlocks, sizeof(void*));
-    h->evMask = (unsigned char*)calloc((size_t)nBlocks, 1);
-    if (!h->evRing || !h->evMask) return h_fail(h, SAFCONV_ERR_NOMEM, "event ring", 0);
-    for (int i = 0; i < 4 * nBlocks; i++) {
+    if (nGroups == 0) return SAFCONV_OK;
+    h->evRing = (void**)calloc((size_t)4 * nGroups, sizeof(void*));
+    h->evBlocks = (int*)calloc((size_t)nGroups, sizeof(int));
+    if (!h->evRing || !h->evBlocks) return h_fail(h, SAFCONV_ERR_NOMEM, "event ring", 0);
+    for (int i = 0; i < 4 * nGroups; i++) {
         int e = scdev_event_create(&h->evRing[i]);
         if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaEventCreate", e);
     }
-    h->timingCap = nBlocks;
+    h->timingCap = nGroups;
+    return SAFCONV_OK;
+}
+
+int safconv_get_kernel_totals(void* hp, float msTotal[3], int* nLaunchGroups, int* nBlocksOut)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !msTotal || !h->timingCap) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    msTotal[0] = msTotal[1] = msTotal[2] = 0.f;
+    const int n = h->timingCount;
+    if (nLaunchGroups) *nLaunchGroups = n;
+    if (nBlocksOut) *nBlocksOut = 0;
+    if (n == 0) return SAFCONV_OK;
+    const int matrix = (h->pl.kind == SC_KIND_MATRIX);
+    int e = scdev_stream_sync(h->stream);
+    double acc[3] = { 0, 0, 0 };
+    int blocks = 0;
+    for (int g = 0; g < n && !e; g++) {
+        void** ev = h->evRing + 4 * (size_t)g;
+        float t = 0.f;
+        if (matrix) { e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t; }
+        if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
+        if (!e && matrix) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
+        blocks += h->evBlocks[g];
+    }
+    h->timingCount = 0;
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "kernel timing", e);
+    for (int i = 0; i < 3; i++) msTotal[i] = (float)acc[i];
+    if (nBlocksOut) *nBlocksOut = blocks;
     return SAFCONV_OK;
 }
 
 int safconv_get_kernel_times(void* hp, float ms[3], int* nBlocksOut)
 {
-    safconv_handle* h = as_handle(hp);
-    if (!h || !ms || !h->timingCap) return SAFCONV_ERR_ARG;
-    scdev_set_device(h->device);
-    ms[0] = ms[1] = ms[2] = 0.f;
-    const int n = h->timingCount;
-    if (nBlocksOut) *nBlocksOut = n;
-    if (n == 0) return SAFCONV_OK;
-    const int matrix = (h->pl.kind == SC_KIND_MATRIX);
-    int e = scdev_stream_sync(h->stream);
-    double acc[3] = { 0, 0, 0 };
-    for (int b = 0; b < n && !e; b++) {
-        void** ev = h->evRing + 4 * (size_t)b;
-        float t = 0.f;
-        /* batched launches: one forward-FFT interval (first block of a batch) and one inverse-FFT interval
-         * (last block of a batch) cover the whole batch; the totals are averaged per block below */
-        if (matrix && (h->evMask[b] & 1)) { e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t; }
-        if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
-        if (!e && matrix && (h->evMask[b] & 2)) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
-    }
-    h->timingCount = 0;
-    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "kernel timing", e);
-    for (int i = 0; i < 3; i++) ms[i] = (float)(acc[i] / n);
+    int groups = 0, blocks = 0;
+    int rc = safconv_get_kernel_totals(hp, ms, &groups, &blocks);
+    if (rc) return rc;
+    if (nBlocksOut) *nBlocksOut = blocks;
+    if (blocks > 0) for (int i = 0; i < 3; i++) ms[i] /= (float)blocks;
     return SAFCONV_OK;
 }
 

@@ -401,7 +401,8 @@ struct MacArgs {
     long long totalStages;
     int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
     int NS;                        /* pipeline depth (stages)                */
-    int RS, blk;                   /* delay-line ring size; block offset inside the current batch */
+    int RS, blk, nB;               /* delay-line ring size; first block of this launch inside the batch; blocks in this launch */
+    size_t zpStride;               /* float2 elements of Zp per block */
     int stageHBytes, stageXBytes;  /* shared-memory bytes reserved per stage */
 };
 
@@ -426,10 +427,10 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     /* decompose the first stage index ONCE; afterwards (sidx, p, kt) are advanced incrementally
      * (no integer division inside the streaming loop) */
     const long long unit0 = s0 / a.SPU;
-    int sidx = (int)(s0 - unit0 * a.SPU);              /* stage inside the unit          */
+    const int sidx0 = (int)(s0 - unit0 * a.SPU);       /* stage inside the unit          */
     const long long grp0 = unit0 / a.P;
-    int p  = (int)(unit0 - grp0 * a.P);                /* filter partition               */
-    int kt = (int)(grp0 % a.nKT);                      /* bin tile                       */
+    const int p0  = (int)(unit0 - grp0 * a.P);         /* filter partition               */
+    const int kt0 = (int)(grp0 % a.nKT);               /* bin tile                       */
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empt[s], SC_MAC_CWARPS); }
@@ -440,31 +441,36 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     if (warp == SC_MAC_CWARPS) {
         /* ===================== TMA producer (one elected lane) ===================== */
         if (lane == 0) {
-            const int head = (int)((a.counters[0] + (unsigned)a.blk) % (unsigned)a.RS);   /* slot of the newest block */
             const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
             const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
-            const float2* srcH = a.H + ((size_t)unit0 * a.nIn + (size_t)sidx * a.SNI) * a.OTsz * SC_BK;
+            const float2* srcH0 = a.H + ((size_t)unit0 * a.nIn + (size_t)sidx0 * a.SNI) * a.OTsz * SC_BK;
             const uint32_t rowH = (uint32_t)a.OTsz * (SC_BK * 8);
             int s = 0; uint32_t par = 1;
-            for (int i = 0; i < nIt; ++i) {
-                mbar_wait(&empt[s], par);
-                const int ni0  = sidx * a.SNI;
-                const int cnt  = min(a.SNI, a.nIn - ni0);
-                const uint32_t bytesH = (uint32_t)cnt * rowH;
-                const uint32_t bytesX = (uint32_t)cnt * (SC_BK * 8);
-                int slot = head - p; if (slot < 0) slot += a.RS;
-                const float2* srcX = a.X + (((size_t)kt * a.RS + slot) * a.nIn + ni0) * SC_BK;
-                mbar_expect_tx(&full[s], bytesH + bytesX);
-                if (a.hints) {
-                    tma_bulk_g2s_hint(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s], polH);
-                    tma_bulk_g2s_hint(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s], polX);
-                } else {
-                    tma_bulk_g2s(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s]);
-                    tma_bulk_g2s(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s]);
+            /* the blocks of a batch are streamed back to back: the pipeline never drains between blocks */
+            for (int blk = 0; blk < a.nB; ++blk) {
+                const int head = (int)((a.counters[0] + (unsigned)(a.blk + blk)) % (unsigned)a.RS);   /* newest slot */
+                const float2* srcH = srcH0;
+                int sidx = sidx0, p = p0, kt = kt0;
+                for (int i = 0; i < nIt; ++i) {
+                    mbar_wait(&empt[s], par);
+                    const int ni0  = sidx * a.SNI;
+                    const int cnt  = min(a.SNI, a.nIn - ni0);
+                    const uint32_t bytesH = (uint32_t)cnt * rowH;
+                    const uint32_t bytesX = (uint32_t)cnt * (SC_BK * 8);
+                    int slot = head - p; if (slot < 0) slot += a.RS;
+                    const float2* srcX = a.X + (((size_t)kt * a.RS + slot) * a.nIn + ni0) * SC_BK;
+                    mbar_expect_tx(&full[s], bytesH + bytesX);
+                    if (a.hints) {
+                        tma_bulk_g2s_hint(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s], polH);
+                        tma_bulk_g2s_hint(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s], polX);
+                    } else {
+                        tma_bulk_g2s(smH + (size_t)s * a.stageHBytes, srcH, bytesH, &full[s]);
+                        tma_bulk_g2s(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s]);
+                    }
+                    srcH += (size_t)cnt * a.OTsz * SC_BK;               /* stages are contiguous in H */
+                    if (++sidx == a.SPU) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+                    if (++s == NS) { s = 0; par ^= 1u; }
                 }
-                srcH += (size_t)cnt * a.OTsz * SC_BK;               /* stages are contiguous in H */
-                if (++sidx == a.SPU) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
-                if (++s == NS) { s = 0; par ^= 1u; }
             }
         }
         return;
@@ -480,73 +486,75 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 #pragma unroll
     for (int j = 0; j < R; ++j) { acc[j] = make_float2(0.f, 0.f); tot[j] = make_float2(0.f, 0.f); }
 
-    int s = 0, seg = 0; uint32_t par = 0;
-    float2* dstBase = a.Zp + (size_t)a.ctaBase[blockIdx.x] * a.OTsz * SC_BK;
-    for (int i = 0; i < nIt; ++i) {
-        const int  cnt    = min(a.SNI, a.nIn - sidx * a.SNI);
-        const bool packed = (kt == 0) && (lane == 0);  /* bin 0 holds (DC, Nyquist): two real products */
+    int s = 0; uint32_t par = 0;
+    for (int blk = 0; blk < a.nB; ++blk) {
+        float2* dst = a.Zp + ((size_t)blk * a.zpStride) + (size_t)a.ctaBase[blockIdx.x] * a.OTsz * SC_BK;
+        int sidx = sidx0, p = p0, kt = kt0;
+        for (int i = 0; i < nIt; ++i) {
+            const int  cnt    = min(a.SNI, a.nIn - sidx * a.SNI);
+            const bool packed = (kt == 0) && (lane == 0);  /* bin 0 holds (DC, Nyquist): two real products */
 
-        mbar_wait(&full[s], par);
-        if (active) {
-            const float2* Hs = reinterpret_cast<const float2*>(smH + (size_t)s * a.stageHBytes) + wo * R * SC_BK + lane;
-            const float2* Xs = reinterpret_cast<const float2*>(smX + (size_t)s * a.stageXBytes) + lane;
-            for (int r = wk; r < cnt; r += a.WGk) {
-                const float2 x = Xs[r * SC_BK];
-                const float xb = packed ? 0.f : x.y;   /* re -= h.y*xb ; im += h.x*xb */
-                const float xd = packed ? x.y : x.x;   /* im += h.y*xd                */
-                const float2* hrow = Hs + (size_t)r * rowStride;
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    if (j < nvalid) {
-                        const float2 h = hrow[j * SC_BK];
-                        acc[j].x = fmaf(h.x, x.x, acc[j].x);
-                        acc[j].x = fmaf(-h.y, xb, acc[j].x);
-                        acc[j].y = fmaf(h.x, xb, acc[j].y);
-                        acc[j].y = fmaf(h.y, xd, acc[j].y);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empt[s]);
-        if (++s == NS) { s = 0; par ^= 1u; }
-
-        const bool last     = (i + 1 == nIt);
-        const bool endUnit  = (sidx == a.SPU - 1);
-        const bool endGroup = endUnit && (p == a.P - 1);
-        if (endUnit || last) {
-            /* two-level accumulation: per-unit sums are folded into the running total */
-#pragma unroll
-            for (int j = 0; j < R; ++j) { tot[j] = caddf(tot[j], acc[j]); acc[j] = make_float2(0.f, 0.f); }
-        }
-        if (endGroup || last) {
-            /* end of this CTA's share of group (ot,kt): emit one partial tile */
-            float2* dst = dstBase + (size_t)seg * a.OTsz * SC_BK;
-            ++seg;
-            if (a.WGk > 1) {
-#pragma unroll
-                for (int j = 0; j < R; ++j) red[(warp * R + j) * 32 + lane] = tot[j];
-                asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
-                if (active && wk == 0) {
+            mbar_wait(&full[s], par);
+            if (active) {
+                const float2* Hs = reinterpret_cast<const float2*>(smH + (size_t)s * a.stageHBytes) + wo * R * SC_BK + lane;
+                const float2* Xs = reinterpret_cast<const float2*>(smX + (size_t)s * a.stageXBytes) + lane;
+                for (int r = wk; r < cnt; r += a.WGk) {
+                    const float2 x = Xs[r * SC_BK];
+                    const float xb = packed ? 0.f : x.y;   /* re -= h.y*xb ; im += h.x*xb */
+                    const float xd = packed ? x.y : x.x;   /* im += h.y*xd                */
+                    const float2* hrow = Hs + (size_t)r * rowStride;
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        float2 v = tot[j];
-                        for (int g = 1; g < a.WGk; ++g) v = caddf(v, red[((g * a.WGo + wo) * R + j) * 32 + lane]);
-                        tot[j] = v;
+                        if (j < nvalid) {
+                            const float2 h = hrow[j * SC_BK];
+                            acc[j].x = fmaf(h.x, x.x, acc[j].x);
+                            acc[j].x = fmaf(-h.y, xb, acc[j].x);
+                            acc[j].y = fmaf(h.x, xb, acc[j].y);
+                            acc[j].y = fmaf(h.y, xd, acc[j].y);
+                        }
                     }
                 }
-                asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
             }
-            if (active && wk == 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empt[s]);
+            if (++s == NS) { s = 0; par ^= 1u; }
+
+            const bool last     = (i + 1 == nIt);
+            const bool endUnit  = (sidx == a.SPU - 1);
+            const bool endGroup = endUnit && (p == a.P - 1);
+            if (endUnit || last) {
+                /* two-level accumulation: per-unit sums are folded into the running total */
 #pragma unroll
-                for (int j = 0; j < R; ++j)
-                    if (j < nvalid) dst[(size_t)(wo * R + j) * SC_BK + lane] = tot[j];
+                for (int j = 0; j < R; ++j) { tot[j] = caddf(tot[j], acc[j]); acc[j] = make_float2(0.f, 0.f); }
             }
+            if (endGroup || last) {
+                /* end of this CTA's share of group (ot,kt): emit one partial tile */
+                if (a.WGk > 1) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) tot[j] = make_float2(0.f, 0.f);
+                    for (int j = 0; j < R; ++j) red[(warp * R + j) * 32 + lane] = tot[j];
+                    asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
+                    if (active && wk == 0) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j) {
+                            float2 v = tot[j];
+                            for (int g = 1; g < a.WGk; ++g) v = caddf(v, red[((g * a.WGo + wo) * R + j) * 32 + lane]);
+                            tot[j] = v;
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" :: "n"(SC_MAC_CWARPS * 32) : "memory");
+                }
+                if (active && wk == 0) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (j < nvalid) dst[(size_t)(wo * R + j) * SC_BK + lane] = tot[j];
+                }
+                dst += (size_t)a.OTsz * SC_BK;
+#pragma unroll
+                for (int j = 0; j < R; ++j) tot[j] = make_float2(0.f, 0.f);
+            }
+            if (endUnit) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+            else ++sidx;
         }
-        if (endUnit) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
-        else ++sidx;
     }
 }
 
@@ -937,11 +945,13 @@ int scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in
     return (int)cudaGetLastError();
 }
 
-int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, void* stream)
+int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, void* stream)
 {
     MacArgs a;
     a.H = (const float2*)b->H; a.X = (const float2*)b->X;
-    a.Zp = (float2*)b->Zp + (size_t)blk * pl->nSlots * pl->OTsz * SC_BK;
+    a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
+    a.Zp = (float2*)b->Zp + (size_t)blk * a.zpStride;
+    a.nB = nBlocks;
     a.counters = b->counters; a.ctaBase = b->ctaBase;
     a.totalStages = pl->totalStages;
     a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.P = pl->P; a.nKT = pl->nKT;
