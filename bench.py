@@ -133,7 +133,7 @@ class ClockSampler:
 # reference (CPU) leg: the compiled, unmodified reference convolver (oracle/_ref), one handle per thread,
 # each owning a disjoint slice of output channels of the same problem
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=1, ch_per_thread=1):
+def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=None, ch_per_thread=1):
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     import oracle as O
     try:
@@ -160,7 +160,7 @@ def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=1, ch_per_
 
     def one_step():
         def work(i):
-            for _ in range(blocks_per_step):
+            for _ in range(blocks_per_step or 1):
                 convs[i].apply(xs[i])
         th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
         for t_ in th:
@@ -168,6 +168,13 @@ def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=1, ch_per_
         for t_ in th:
             t_.join()
 
+    # bound the sample: blocks per step chosen so that one step is ~0.25 s of CPU work (1 block for C4)
+    if blocks_per_step is None:
+        blocks_per_step = 1
+        t0 = time.perf_counter()
+        one_step()
+        t1 = time.perf_counter() - t0
+        blocks_per_step = int(max(1, min(4096, 0.25 / max(t1, 1e-6))))
     for _ in range(warmup):
         one_step()
     t0 = time.perf_counter()
@@ -196,7 +203,7 @@ def run_reference_arm(args, w):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -348,13 +355,31 @@ def run_own_arm(args, w):
         "ms_per_block": ms_total / (args.steps * B),
         "realtime_factor_48k": (hop * B * args.steps / (ms_total * 1e-3)) / 48000.0,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything except the final JSON line goes to stderr (NCCL / torchrun banners print to fd 1)."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
