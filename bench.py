@@ -47,6 +47,10 @@ WORKLOADS = {
                desc="test__saf_matrixConv shape 32x40, hop 2048, 512 taps"),
     "C3": dict(kind="multi", nIn=256, nOut=256, hop=512, L=4096,
                desc="saf_multiConv 256 ch, hop 512, 4096 taps (BASELINE.json configs[2])"),
+    "C5": dict(kind="offline", nIn=121, nOut=64, hop=1024, L=8192, seconds=60.0,
+               desc="offline batched render: 121 SH x 64 out, 8192 taps, hop 1024, 60 s of audio in one call (BASELINE.json configs[4])"),
+    "C5s": dict(kind="offline", nIn=121, nOut=64, hop=1024, L=8192, seconds=6.0,
+                desc="C5 on a 6 s signal (debug)"),
     "C2": dict(kind="matrix", nIn=25, nOut=2, hop=128, L=512,
                desc="saf_matrixConv 25x2, hop 128, 512 taps (BASELINE.json configs[1])"),
     "C1": dict(kind="matrix", nIn=4, nOut=2, hop=256, L=1024,
@@ -69,7 +73,7 @@ def measured_peak_gbs():
 def filters_for(w, out_begin, out_count, seed=0x5AF0C0DE):
     """Deterministic per-output-channel filters so that every rank can build its own shard."""
     from spatial_audio_framework_b200 import synth
-    if w["kind"] == "matrix":
+    if w["kind"] in ("matrix", "offline"):
         H = np.empty((out_count, w["nIn"], w["L"]), np.float32)
         for i in range(out_count):
             H[i] = synth.decaying_rir((w["nIn"], w["L"]), seed=seed + out_begin + i)
@@ -151,7 +155,7 @@ def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=None, ch_p
     rng = np.random.default_rng(1)
     for t in range(cores):
         H = filters_for(w, t * ch_per_thread, ch_per_thread)
-        if w["kind"] == "matrix":
+        if w["kind"] in ("matrix", "offline"):
             convs.append(mk_matrix(hop, H, 1))
             xs.append(rng.uniform(-1, 1, (nIn, hop)).astype(np.float32))
         else:
@@ -207,9 +211,157 @@ def run_reference_arm(args, w):
 
 
 # ------------------------------------------------------------------------------------------------
+# our arm, offline workload (configs[4]): one step = one safconv_render_offline of the whole signal
+# ------------------------------------------------------------------------------------------------
+def run_offline_arm(args, w):
+    import torch
+    import spatial_audio_framework_b200 as saf
+    from spatial_audio_framework_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    hop, nIn, nOut = w["hop"], w["nIn"], w["nOut"]
+    T = int(np.ceil(w["seconds"] * 48000.0 / hop))
+    ob, oc = sharding.shard_range(nOut, world, rank)
+    H = filters_for(w, ob, oc)
+    conv = saf.MatrixConv(hop, H, 1, device=local) if world == 1 else saf.MatrixConv.from_shard(hop, H, nOut, ob, device=local)
+    del H
+    info = conv.info()
+    stream = torch.cuda.Stream(device=dev)
+    conv.set_stream(stream.cuda_stream)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x_host = (torch.rand((nIn, T * hop), generator=g) * 2 - 1).pin_memory()
+    y_host = torch.empty((nOut, T * hop), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty((nIn, T * hop), dtype=torch.float32, device=dev)
+    y_dev = torch.empty((oc, T * hop), dtype=torch.float32, device=dev)
+    y_all = torch.empty((world, oc, T * hop), dtype=torch.float32, device=dev) if world > 1 else None
+    if rank == 0:
+        x_dev.copy_(x_host)
+
+    def step_device():
+        with torch.cuda.stream(stream):
+            if dist:
+                dist.broadcast(x_dev, src=0)
+            conv.render_offline_device(x_dev.data_ptr(), y_dev.data_ptr(), T)
+            if dist:
+                dist.all_gather_into_tensor(y_all, y_dev)
+
+    def step_host():
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                x_dev.copy_(x_host, non_blocking=True)
+        step_device()
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                y_host.copy_(y_all.view(nOut, T * hop) if dist else y_dev, non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    kms = np.zeros(3)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        step_device()
+        kms += np.array(conv.offline_times_ms())        # syncs the stream; per-kernel events of this render
+    with torch.cuda.stream(stream):
+        e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    units = float(nOut) * T * hop * args.steps
+    value = units / (ms_total * 1e-3)
+    kms /= args.steps
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    step_host()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    if dist:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": float(nOut) * T * hop * e2e_steps / float(t.item()), "unit": UNIT,
+           "h2d_bytes_per_step": int(nIn * T * hop * 4), "d2h_bytes_per_step": int(nOut * T * hop * 4), "steps": e2e_steps,
+           "api": "pinned H2D of the whole signal -> safconv_render_offline_device -> D2H" + (" (+ NCCL broadcast / all-gather)" if dist else "")}
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    P = int(info.numFilterBlocks)
+    alg_flops = 8.0 * oc * P * nIn * (hop + 1) * T                 # complex MACs as real flops, this rank
+    gemm_ms = float(kms[1])
+    achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "offline_gemm_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32 accuracy)",
+                "achieved": achieved, "peak": bf16 / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16 / 2.0),
+                "peak_source": "tf32 dense = half of the measured bf16 peak (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1590/2",
+                "traffic": None, "alg_flops_per_launch": alg_flops, "issued_flops_per_launch": 3.0 * alg_flops,
+                "avg_launch_ms": gemm_ms, "launches_timed": args.steps, "rank": 0,
+                "kernel_ms_per_render": {"forward_fft": float(kms[0]), "gemm": gemm_ms, "ifft_ola": float(kms[2])}}
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        c = cpu_reference_run(w, steps=args.cpu_steps, warmup=1)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (tf32x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"], "frames": T,
+                   "partitions": P, "sharding": f"output channels over {world} GPU(s), {oc} per GPU" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: %.1f GB of operands per render" % ((nIn * T * hop * 4 * 3 + info.bytesFilters * 2) / 1e9)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        "realtime_factor_48k": (T * hop * args.steps / (ms_total * 1e-3)) / 48000.0,
+    }
+    emit(line)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_own_arm(args, w):
+    if w["kind"] == "offline":
+        return run_offline_arm(args, w)
     import torch
     import spatial_audio_framework_b200 as saf
     from spatial_audio_framework_b200 import sharding

@@ -145,6 +145,21 @@ int safconv_apply_device(void* h, const float* d_in, float* d_out);
  */
 int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nBlocks);
 
+/**
+ * Offline rendering of a whole signal (BASELINE.json configs[4]): all nFrames blocks are available at once,
+ * so the per-bin sum over partitions x inputs becomes a dense contraction that re-uses every filter value
+ * for all frames and runs on the tensor cores (tcgen05, tf32 operands split hi+lo, fp32 accumulation).
+ * Equal (to fp32 rounding) to a fresh handle's saf_matrixConv_apply called nFrames times:
+ * the state before the first frame is zero and the handle's streaming state is neither used nor changed.
+ * Layouts are channel-major whole signals: in [nCHin][nFrames*hopSize], out [nOutLocal][nFrames*hopSize].
+ * matrixConv handles only; needs nOutLocal <= 64 and hopSize <= 2048.
+ * _device: device pointers, enqueued on the handle's stream without synchronising.
+ */
+int safconv_render_offline(void* h, const float* in, float* out, int nFrames);
+int safconv_render_offline_device(void* h, const float* d_in, float* d_out, int nFrames);
+/** Milliseconds of the last offline render: ms[0] forward FFTs, ms[1] tensor-core GEMM, ms[2] inverse FFTs + overlap-add. */
+int safconv_get_offline_times(void* h, float ms[3]);
+
 /** Use an external CUDA stream (cudaStream_t passed as void*) for this handle; NULL restores its own stream. */
 int safconv_set_stream(void* h, void* cudaStream);
 /** The stream (cudaStream_t as void*) the handle currently enqueues on. */

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = [
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
     "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_get_kernel_totals",
     "safconv_set_option",
+    "safconv_render_offline", "safconv_render_offline_device", "safconv_get_offline_times",
 ]
 
 
@@ -104,6 +105,9 @@ def lib():
     L.safconv_get_kernel_totals.argtypes = [C.c_void_p, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.safconv_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.safconv_debug_plan_size.restype = C.c_int
+    L.safconv_render_offline.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
+    L.safconv_render_offline_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.safconv_get_offline_times.argtypes = [C.c_void_p, _f32p]
     _lib = L
     return L
 
@@ -247,6 +251,26 @@ class MatrixConv(_Base):
     def from_shard(cls, hopSize: int, Hshard: np.ndarray, nCHoutTotal: int, outBegin: int, device: int | None = None):
         """Hshard: [outCount, nCHin, length_h] = this rank's output channels only (safconv_matrixConv_create_from_shard)."""
         return cls(hopSize, Hshard, 1, device=device, _from_shard=(nCHoutTotal, outBegin))
+
+    def render_offline(self, x: np.ndarray) -> np.ndarray:
+        """Whole signal x[nCHin, nFrames*hop] -> y[nOutLocal, nFrames*hop] on the tensor-core offline path."""
+        x = np.ascontiguousarray(x, np.float32)
+        nfr = x.shape[1] // self.hop
+        assert x.shape == (self.nCHin, nfr * self.hop)
+        y = np.empty((self.nOutLocal, nfr * self.hop), np.float32)
+        if self._lib.safconv_render_offline(self._h, _fp(x), _fp(y), nfr):
+            self._raise_if_error()
+        return y
+
+    def render_offline_device(self, d_in_ptr: int, d_out_ptr: int, n_frames: int):
+        if self._lib.safconv_render_offline_device(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr), n_frames):
+            self._raise_if_error()
+
+    def offline_times_ms(self):
+        ms = (C.c_float * 3)()
+        if self._lib.safconv_get_offline_times(self._h, ms):
+            self._raise_if_error()
+        return [ms[0], ms[1], ms[2]]
 
     def apply(self, inputSigs: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(inputSigs, np.float32)

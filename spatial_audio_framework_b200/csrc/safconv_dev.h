@@ -72,6 +72,16 @@ typedef struct scdev_bufs {
     int*   grpStart;  /* int[nGroups+1] partial slots of group g: grpStart[g]..grpStart[g+1]-1 */
 } scdev_bufs;
 
+/* workspace of the offline (batched frames, tensor-core) path, see safconv_offline.cu */
+typedef struct scdev_offline {
+    float *XGhi, *XGlo;      /* A operand  [bin][kg][rows][4]  (frames x (input, re/im)), tf32 hi / lo parts   */
+    float *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][4] ((output, re/im) x (input, re/im))               */
+    float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
+    float *zt;               /* inverse transforms [T][nOut][2*hop]                                             */
+    int capFrames, capTpad, capRows, packed;
+    int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush;
+} scdev_offline;
+
 /* --- device / memory / stream plumbing (all return 0 on success, else a cudaError_t value) --- */
 int  scdev_device_count(int* n);
 int  scdev_set_device(int dev);
@@ -114,6 +124,13 @@ int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, 
 int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
 /* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */
 int  scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream);
+/* offline path: allocate / grow the workspace for T frames (and build the filter operand on first use),
+ * render d_in [nIn][T*hop] -> d_out [nOutLocal][T*hop] from a zero state, free.  `events` (4 CUDA events or
+ * NULL) are recorded before the forward FFTs, before the GEMM, after the GEMM, and at the end. */
+int  scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o, int T, void* stream);
+int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
+                       const float* d_in, float* d_out, int T, void** events, void* stream);
+int  scdev_offline_free(scdev_offline* o);
 /* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */
 int  scdev_is_pinned_host(const void* p);
 /* multiConv: K1+K2+K3 fused, one CTA per channel */

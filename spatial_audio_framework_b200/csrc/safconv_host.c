@@ -44,6 +44,8 @@ typedef struct safconv_handle {
     void**     evRing;
     int*       evBlocks;             /* blocks covered by each launch group */
     void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
+    scdev_offline off;               /* offline (batched frames) workspace, allocated on first use */
+    void*      offEv[4];
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
 } safconv_handle;
 
@@ -231,6 +233,8 @@ static void handle_free(safconv_handle* h)
     scdev_graph_destroy(h->graphExec);
     if (h->evRing) { for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]); free(h->evRing); }
     free(h->evBlocks);
+    scdev_offline_free(&h->off);
+    for (int i = 0; i < 4; i++) scdev_event_destroy(h->offEv[i]);
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
     scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart);
@@ -626,6 +630,49 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     }
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "apply_device", e);
     return SAFCONV_OK;
+}
+
+/* ---- offline rendering: all frames at once, tensor-core per-bin contraction (safconv_offline.cu) ---- */
+int safconv_render_offline_device(void* hp, const float* d_in, float* d_out, int nFrames)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !d_in || !d_out || nFrames < 1 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
+    int e = scdev_set_device(h->device);
+    if (!e && !h->offEv[0]) for (int i = 0; i < 4 && !e; i++) e = scdev_event_create(&h->offEv[i]);
+    if (!e) e = scdev_offline_prepare(&h->pl, &h->b, &h->off, nFrames, h->stream);
+    if (!e) e = scdev_offline_run(&h->pl, &h->b, &h->off, d_in, d_out, nFrames, h->offEv, h->stream);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline", e);
+    return SAFCONV_OK;
+}
+
+int safconv_render_offline(void* hp, const float* in, float* out, int nFrames)
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !in || !out || nFrames < 1 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
+    int e = scdev_set_device(h->device);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e);
+    const size_t nIn = (size_t)h->pl.nIn, nOut = (size_t)h->pl.nOutLocal, len = (size_t)nFrames * h->pl.hop;
+    float *d_in = NULL, *d_out = NULL;
+    e = scdev_malloc((void**)&d_in, sizeof(float) * nIn * len);
+    if (!e) e = scdev_malloc((void**)&d_out, sizeof(float) * nOut * len);
+    if (!e) e = scdev_memcpy_h2d_async(d_in, in, sizeof(float) * nIn * len, h->stream);
+    int rc = SAFCONV_OK;
+    if (!e) rc = safconv_render_offline_device(hp, d_in, d_out, nFrames);
+    if (!e && !rc) e = scdev_memcpy_d2h_async(out, d_out, sizeof(float) * nOut * len, h->stream);
+    if (!e && !rc) e = scdev_stream_sync(h->stream); else scdev_stream_sync(h->stream);
+    scdev_free(d_in); scdev_free(d_out);
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (host buffers)", e);
+    return rc;
+}
+
+int safconv_get_offline_times(void* hp, float ms[3])
+{
+    safconv_handle* h = as_handle(hp);
+    if (!h || !ms || !h->offEv[0]) return SAFCONV_ERR_ARG;
+    scdev_set_device(h->device);
+    int e = scdev_stream_sync(h->stream);
+    for (int i = 0; i < 3 && !e; i++) e = scdev_event_elapsed_ms(h->offEv[i], h->offEv[i + 1], &ms[i]);
+    return e ? h_fail(h, SAFCONV_ERR_CUDA, "offline timing", e) : SAFCONV_OK;
 }
 
 int safconv_set_stream(void* hp, void* cudaStream)

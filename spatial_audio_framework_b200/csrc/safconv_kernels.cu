@@ -29,220 +29,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "safconv_dev.h"
-
-#define SC_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
-
-/* ------------------------------------------------------------------------------------------ */
-/*  small device helpers                                                                      */
-/* ------------------------------------------------------------------------------------------ */
-
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
-{
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cmul_conjb(float2 a, float2 b)   /* a * conj(b) */
-{
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-
-__device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((unsigned)v) >> (32 - logM)); }
-
-/* ------------------------------------------------------------------------------------------ */
-/*  M-point complex FFT in shared memory, decimation in frequency                              */
-/*  input: natural order in s[0..M) ; output: s[bitrev(k)] holds bin k                          */
-/*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)]); the kernels copy the    */
-/*  table into shared memory first (load_twiddles) so that no pass waits on an L2 round trip.    */
-/*  INV conjugates every twiddle (unnormalised inverse transform).                              */
-/*  Requires M >= 32, blockDim.x a multiple of 32; ends with __syncthreads().                   */
-/* ------------------------------------------------------------------------------------------ */
-template <bool INV>
-__device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
-{
-    float2 w = tw[idx];
-    if (INV) w.y = -w.y;
-    return w;
-}
-
-template <bool INV>
-__device__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw)
-{
-    const int tid = threadIdx.x, T = blockDim.x;
-    int L = M;                 /* current sub-transform length */
-    int nsm = logM - 5;        /* radix-2 stages done through shared memory (spans M/2 .. 32) */
-
-    /* two radix-2 stages fused per pass */
-    while (nsm >= 2) {
-        const int q = L >> 2;
-        const int tstr = (2 * M) / L;
-        for (int i = tid; i < (M >> 2); i += T) {
-            const int j = i & (q - 1);
-            const int base = ((i - j) << 2) + j;
-            const float2 a0 = s[base], a1 = s[base + q], a2 = s[base + 2 * q], a3 = s[base + 3 * q];
-            const float2 w1 = twd<INV>(tw, j * tstr);
-            const float2 w2 = twd<INV>(tw, 2 * j * tstr);
-            const float2 u0 = caddf(a0, a2);
-            const float2 u1 = caddf(a1, a3);
-            const float2 v0 = cmulf(csubf(a0, a2), w1);
-            float2 d1 = csubf(a1, a3);
-            /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
-            d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
-            const float2 v1 = cmulf(d1, w1);
-            s[base]         = caddf(u0, u1);
-            s[base + q]     = cmulf(csubf(u0, u1), w2);
-            s[base + 2 * q] = caddf(v0, v1);
-            s[base + 3 * q] = cmulf(csubf(v0, v1), w2);
-        }
-        __syncthreads();
-        L >>= 2;
-        nsm -= 2;
-    }
-    if (nsm == 1) {
-        const int half = L >> 1;
-        const int tstr = (2 * M) / L;
-        for (int i = tid; i < (M >> 1); i += T) {
-            const int j = i & (half - 1);
-            const int base = ((i - j) << 1) + j;
-            const float2 a = s[base], b = s[base + half];
-            const float2 w = twd<INV>(tw, j * tstr);
-            s[base]        = caddf(a, b);
-            s[base + half] = cmulf(csubf(a, b), w);
-        }
-        __syncthreads();
-        L >>= 1;
-    }
-    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp */
-    {
-        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-        float2 w16 = twd<INV>(tw, (lane & 15) * (M >> 4));
-        float2 w8  = twd<INV>(tw, (lane & 7)  * (M >> 3));
-        float2 w4  = twd<INV>(tw, (lane & 3)  * (M >> 2));
-        float2 w2  = twd<INV>(tw, (lane & 1)  * (M >> 1));
-        for (int row = warp; row < (M >> 5); row += nwarps) {
-            float2 v = s[row * 32 + lane];
-#define SC_SHFL_STAGE(HALF, W)                                                       \
-            {                                                                        \
-                float2 o;                                                            \
-                o.x = __shfl_xor_sync(0xffffffffu, v.x, HALF);                       \
-                o.y = __shfl_xor_sync(0xffffffffu, v.y, HALF);                       \
-                if (lane & HALF) v = cmulf(csubf(o, v), W);                          \
-                else             v = caddf(v, o);                                    \
-            }
-            SC_SHFL_STAGE(16, w16)
-            SC_SHFL_STAGE(8,  w8)
-            SC_SHFL_STAGE(4,  w4)
-            SC_SHFL_STAGE(2,  w2)
-            {   /* span 1: twiddle is 1 */
-                float2 o;
-                o.x = __shfl_xor_sync(0xffffffffu, v.x, 1);
-                o.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
-                v = (lane & 1) ? csubf(o, v) : caddf(v, o);
-            }
-#undef SC_SHFL_STAGE
-            s[row * 32 + lane] = v;
-        }
-        __syncthreads();
-    }
-}
-
-/* copy the twiddle table into shared memory (coalesced; overlaps the input load that follows) */
-__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M)
-{
-    for (int n = threadIdx.x; n < M; n += blockDim.x) stw[n] = __ldg(gtw + n);
-}
-
-/* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
-__device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M)
-{
-    const int tid = threadIdx.x, T = blockDim.x;
-    if ((hop & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
-        const float2* x2 = reinterpret_cast<const float2*>(x);
-        const int h2 = hop >> 1;
-        for (int n = tid; n < M; n += T) s[n] = (n < h2) ? __ldg(x2 + n) : make_float2(0.f, 0.f);
-    } else {
-        for (int n = tid; n < M; n += T) {
-            const int i = 2 * n;
-            float2 v;
-            v.x = (i < hop) ? __ldg(x + i) : 0.f;
-            v.y = (i + 1 < hop) ? __ldg(x + i + 1) : 0.f;
-            s[n] = v;
-        }
-    }
-}
-
-/* forward split pass for the bin pair (k, M-k), 1 <= k <= M/2, from the bit-reversed complex FFT in s.
- * X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),  E = (a + conj b)/2, O = -i (a - conj b)/2 */
-__device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, int logM,
-                                               const float2* __restrict__ tw, float2& Xk, float2& Xmk)
-{
-    const float2 a = s[bitrev(k, logM)];
-    const float2 b = s[bitrev(M - k, logM)];
-    const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-    const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-    const float2 t = cmulf(tw[k], O);
-    Xk  = make_float2(E.x + t.x, E.y + t.y);
-    Xmk = make_float2(E.x - t.x, t.y - E.y);
-}
-
-/* inverse split pass, in place on the packed natural-order spectrum Z (pair k, M-k; 1 <= k <= M/2):
- * Zc[k] = E + iO, Zc[M-k] = conj(E) + i conj(O), E = A + conj B, O = (A - conj B) W_N^-k  (the 1/2 is folded into 1/N) */
-__device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, const float2* __restrict__ tw)
-{
-    const float2 A = Z[k], B = Z[M - k];
-    const float2 E = make_float2(A.x + B.x, A.y - B.y);
-    const float2 D = make_float2(A.x - B.x, A.y + B.y);
-    const float2 O = cmul_conjb(D, tw[k]);
-    Z[k]     = make_float2(E.x - O.y, E.y + O.x);
-    Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
-}
-
-__device__ __forceinline__ void inv_split_all(float2* Z, int M, const float2* __restrict__ tw)
-{
-    for (int k = threadIdx.x; k <= (M >> 1); k += blockDim.x) {
-        if (k == 0) {
-            const float2 A = Z[0];                       /* (DC, Nyquist) */
-            Z[0] = make_float2(A.x + A.y, A.x - A.y);
-        } else {
-            inv_split_pair(Z, k, M, tw);
-        }
-    }
-    __syncthreads();
-}
-
-/* time sample j of the (bit-reversed) inverse transform result */
-__device__ __forceinline__ float time_sample(const float2* s, int j, int logM)
-{
-    const float2 v = s[bitrev(j >> 1, logM)];
-    return (j & 1) ? v.y : v.x;
-}
-
-/* overlap-add epilogue (reference .c:230-233): out[i] = z[i]/N + tail[i]; tail[i] = z[i+hop]/N */
-__device__ __forceinline__ void ola_store(const float2* s, int hop, int logM, float scale,
-                                          float* __restrict__ out, float* __restrict__ tail)
-{
-    for (int i = threadIdx.x; i < hop; i += blockDim.x) {
-        const float z0 = time_sample(s, i, logM) * scale;
-        const float z1 = time_sample(s, i + hop, logM) * scale;
-        out[i]  = z0 + tail[i];
-        tail[i] = z1;
-    }
-}
-
-/* "last CTA increments the block counter" : counters[0] = block counter, counters[1] = ticket */
-__device__ __forceinline__ void advance_block_counter(unsigned int* counters, unsigned int nCtas)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(&counters[1], 1u);
-        if (t == nCtas - 1) {
-            counters[1] = 0;
-            __threadfence();
-            atomicAdd(&counters[0], 1u);
-        }
-    }
-}
+#include "safconv_fft.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /*  K0: filter partition + forward FFT                                                         */
@@ -343,54 +130,6 @@ __global__ void input_fft_kernel(InFftArgs a)
 /* ------------------------------------------------------------------------------------------ */
 /*  K2: filter-streaming complex MAC  (the HBM-roofline kernel)                                 */
 /* ------------------------------------------------------------------------------------------ */
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) { }
-}
-/* TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP) */
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
 
 struct MacArgs {
     const float2* H;               /* [unit][nIn][OTsz][32], unit = (ot*nKT + kt)*P + p */

@@ -1,0 +1,575 @@
+/*
+ * safconv_offline.cu -- offline (many frames at once) rendering path of the matrix convolver.
+ *
+ * Same convolution as saf_matrixConv_apply called once per block from a zero state
+ * (reference: /root/reference/framework/modules/saf_utilities/saf_utility_matrixConv.c:209-235), but with
+ * ALL T frames of the signal available up front (BASELINE.json configs[4]: "offline batched render").
+ * Then the per-bin sum over partitions x inputs
+ *
+ *     Y_t[no][k] = sum_p sum_ni H_p[no][ni][k] * X_{t-p}[ni][k]
+ *
+ * re-uses every filter value for all T frames: per bin it is a dense complex contraction, written here as
+ * a REAL GEMM with fp32 accumulation on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * accumulators in TMEM):
+ *
+ *     D[frame t][(no,c)] += A[frame t][(p, ni, c')] * B[(no,c)][(p, ni, c')]
+ *     A = X (frames on the UMMA M axis, 128 rows per accumulator; the partition shift t-p is a ROW OFFSET
+ *         of the shared-memory operand descriptor -- the Toeplitz matrix is never materialised)
+ *     B = [Hr -Hi; Hi Hr] (complex product as real 2x2 blocks), N = 2*nOut columns
+ *
+ * fp32 accuracy on tf32 tensor cores: both operands are split x = hi + lo (hi = rn_tf32(x), lo = rn_tf32(x - hi))
+ * and every product is issued as three MMAs  lo*hi + hi*lo + hi*hi  (dropped lo*lo ~2^-24 per product); the
+ * tensor core's truncating accumulation is kept short by promoting TMEM chains into fp32 registers (see the GEMM).
+ *
+ * Operands are kept in global memory already in the UMMA canonical K-major / no-swizzle core-matrix order
+ * ([k-group of 4 floats][row][4]) so that one plain TMA bulk copy (cp.async.bulk, 1-D) per k-group lands a
+ * ready-to-use shared-memory image: no tensor maps, no swizzle, and a row shift is just +16 bytes per row.
+ *
+ * Kernels:  offline_pack_filters_kernel  H spectra (streaming layout) -> B operand hi/lo       (once per handle)
+ *           offline_fft_kernel           forward real FFT of all frames -> A operand hi/lo
+ *           offline_gemm_kernel          the tcgen05 GEMM, one CTA per (256-frame tile, bin)
+ *           offline_ifft_kernel          inverse real FFT per (frame, output)
+ *           offline_ola_kernel           overlap-add of consecutive frames (reference .c:230-233)
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "safconv_dev.h"
+#include "safconv_fft.cuh"
+
+#define OFF_MT   256     /* frames per CTA tile = two M=128 accumulators                     */
+#define OFF_KG   4       /* k-groups (of 4 floats) per pipeline chunk: K = 16 per chunk      */
+#define OFF_NH   4       /* filter-operand pipeline stages                                   */
+#define OFF_FPC  4       /* frames per forward-FFT CTA (64-byte contiguous operand writes)    */
+#define OFF_OPC  8       /* outputs per inverse-FFT CTA (64-byte contiguous spectrum reads)   */
+#define OFF_GEMM_THREADS 320   /* warps 0-7 epilogue (accumulator promotion), warp 8 TMA producer, warp 9 MMA issuer */
+
+/* round-to-nearest tf32 (10 explicit mantissa bits) of an fp32 value, returned in an fp32 container */
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+/* x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi): |x - hi - lo| <= 2^-24 |x|, both exactly representable
+ * as tf32 so the tensor core's own truncation of the low 13 container bits changes nothing */
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
+
+/* ------------------------------------------------------------------------------------------ */
+/*  B operand: HG[hi|lo][bin][p][kg][n][4],  n = 2*no + c_out,  k = 2*ni + c_in                  */
+/* ------------------------------------------------------------------------------------------ */
+struct PackArgs {
+    const float2* H;       /* [ot][kt][p][ni][OTsz][32] */
+    float* HGhi; float* HGlo;
+    size_t total;          /* elements of H */
+    int nKT, P, nIn, OTsz, nOutLocal, nKG, Nn;
+};
+
+__global__ void offline_pack_filters_kernel(PackArgs a)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.total; e += stride) {
+        size_t r = e;
+        const int b  = (int)(r & 31); r >>= 5;
+        const int nl = (int)(r % a.OTsz); r /= a.OTsz;
+        const int ni = (int)(r % a.nIn);  r /= a.nIn;
+        const int p  = (int)(r % a.P);    r /= a.P;
+        const int kt = (int)(r % a.nKT);  r /= a.nKT;
+        const int ot = (int)r;
+        const int no = ot * a.OTsz + nl;
+        if (no >= a.nOutLocal) continue;
+        const int bin = kt * 32 + b;
+        const float2 h = a.H[e];
+        /* complex product as a real 2x2 block; bin 0 is the packed (DC, Nyquist) pair: two real products */
+        float2 rowRe, rowIm;            /* (k = 2ni, k = 2ni+1) entries of rows n = 2no and n = 2no+1 */
+        if (bin == 0) { rowRe = make_float2(h.x, 0.f);  rowIm = make_float2(0.f, h.y); }
+        else          { rowRe = make_float2(h.x, -h.y); rowIm = make_float2(h.y, h.x); }
+        const int k = 2 * ni;
+        const size_t base = ((((size_t)bin * a.P + p) * a.nKG + (k >> 2)) * a.Nn) * 4 + (k & 3);
+        const size_t iRe = base + (size_t)(2 * no) * 4, iIm = base + (size_t)(2 * no + 1) * 4;
+        const float2 reHi = make_float2(tf32_hi(rowRe.x), tf32_hi(rowRe.y));
+        const float2 imHi = make_float2(tf32_hi(rowIm.x), tf32_hi(rowIm.y));
+        *reinterpret_cast<float2*>(a.HGhi + iRe) = reHi;
+        *reinterpret_cast<float2*>(a.HGhi + iIm) = imHi;
+        *reinterpret_cast<float2*>(a.HGlo + iRe) = make_float2(tf32_lo(rowRe.x, reHi.x), tf32_lo(rowRe.y, reHi.y));
+        *reinterpret_cast<float2*>(a.HGlo + iIm) = make_float2(tf32_lo(rowIm.x, imHi.x), tf32_lo(rowIm.y, imHi.y));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  A operand: XG[hi|lo][bin][kg][row][4], row = (P-1) + frame (P-1 leading zero rows = silence    */
+/*  before the first frame), the 4 floats = (re, im) of inputs 2kg and 2kg+1                      */
+/*  grid (ceil(nIn/2), rowsAlloc / OFF_FPC)                                                       */
+/* ------------------------------------------------------------------------------------------ */
+struct OffFftArgs {
+    const float* in;       /* [nIn][T*hop] */
+    float* XGhi; float* XGlo;
+    const float2* tw;
+    size_t inStride;       /* T*hop */
+    int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
+};
+
+__global__ void offline_fft_kernel(OffFftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + (size_t)(2 * OFF_FPC) * a.M;
+    const int kg = blockIdx.x;
+    const int row0 = blockIdx.y * OFF_FPC;
+    load_twiddles(stw, a.tw, a.M);
+    for (int q = 0; q < 2 * OFF_FPC; ++q) {            /* q = 2*f + j : frame f, input 2kg+j */
+        const int ni = 2 * kg + (q & 1);
+        const int t = row0 + (q >> 1) - (a.P - 1);
+        float2* s = sm + (size_t)q * a.M;
+        if (ni < a.nIn && t >= 0 && t < a.T) {
+            load_real_block(s, a.in + (size_t)ni * a.inStride + (size_t)t * a.hop, a.hop, a.M);
+        } else {
+            for (int n = threadIdx.x; n < a.M; n += blockDim.x) s[n] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < 2 * OFF_FPC; ++q) cfft_dif<false>(sm + (size_t)q * a.M, a.M, a.logM, stw);
+
+    const int half = a.M >> 1;
+    for (int idx = threadIdx.x; idx < (half + 1) * OFF_FPC; idx += blockDim.x) {
+        const int f = idx % OFF_FPC, k = idx / OFF_FPC;
+        const float2* s0 = sm + (size_t)(2 * f) * a.M;
+        const float2* s1 = s0 + a.M;
+        float2 x0, x0m, x1, x1m;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z0 = s0[0], z1 = s1[0];
+            x0 = make_float2(z0.x + z0.y, z0.x - z0.y);  x0m = x0;
+            x1 = make_float2(z1.x + z1.y, z1.x - z1.y);  x1m = x1;
+            k2 = 0;
+        } else {
+            fwd_split_pair(s0, k, a.M, a.logM, stw, x0, x0m);
+            fwd_split_pair(s1, k, a.M, a.logM, stw, x1, x1m);
+        }
+        const size_t row = (size_t)row0 + f;
+        {
+            const float4 v = make_float4(x0.x, x0.y, x1.x, x1.y);
+            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row) * 4;
+            *reinterpret_cast<float4*>(a.XGhi + o) = hi;
+            *reinterpret_cast<float4*>(a.XGlo + o) = make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w));
+        }
+        {
+            const float4 v = make_float4(x0m.x, x0m.y, x1m.x, x1m.y);
+            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const size_t o = (((size_t)k2 * a.nKG + kg) * a.rowsAlloc + row) * 4;
+            *reinterpret_cast<float4*>(a.XGhi + o) = hi;
+            *reinterpret_cast<float4*>(a.XGlo + o) = make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w));
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  tcgen05 helpers                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+/* shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleaved" core matrices of 8 rows x 16 bytes):
+ * element (row i, 16-byte k-chunk j) lives at  start + (i/8)*SBO + (i%8)*16 + j*LBO.
+ * With SBO = 128 rows are uniformly 16 bytes apart, so shifting the start address by 16*s selects rows s.. */
+__device__ __forceinline__ uint64_t umma_sdesc(uint32_t saddr, uint32_t lboBytes, uint32_t sboBytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lboBytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sboBytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                         /* descriptor version for sm_100 */
+    return d;                                       /* base offset 0, layout type 0 = no swizzle */
+}
+
+/* instruction descriptor: D = F32, A = B = TF32, both K-major, dense, M x N */
+__host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int Mdim, int Ndim)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmemD, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmemD), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+/* arrive on an mbarrier once all previously issued MMAs of this thread have completed */
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  the GEMM: grid (Tpad / 256, M bins), 320 threads                                            */
+/*                                                                                              */
+/*  Accumulator promotion: the tensor core adds each MMA result into its TMEM accumulator with  */
+/*  truncation, which over the hundreds of chained MMAs of one output (C5: 256 k-steps x 3)       */
+/*  costs ~1e-5 relative -- far outside the 1e-6 parity tolerance.  So TMEM only holds SHORT      */
+/*  chains (`flush` partition steps = 6*flush MMAs per accumulator); 8 epilogue warps keep the     */
+/*  running sums in registers (fp32, round-to-nearest adds) and drain one TMEM buffer set while    */
+/*  the MMA thread fills the other.                                                              */
+/* ------------------------------------------------------------------------------------------ */
+struct OffGemmArgs {
+    const float *XGhi, *XGlo, *HGhi, *HGlo;
+    float* Ys;             /* [bin][Tpad][Nn] */
+    int P, nKG, nKC, Nn, rowsAlloc, Tpad, rowsX, tmemCols, flush;
+    uint32_t idesc;
+};
+
+#define OFF_EPI_WARPS 8
+#define OFF_MAX_HALF  64     /* columns per epilogue thread and frame tile: Nn/2 <= 64 */
+
+__global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGemmArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * OFF_MT, bin = blockIdx.y;
+    const uint32_t xPlane = (uint32_t)a.rowsX * 16u;        /* one k-group column of the frame tile   */
+    const uint32_t xStage = 2u * OFF_KG * xPlane;           /* hi + lo                                */
+    const uint32_t hPlane = (uint32_t)a.Nn * 16u;
+    const uint32_t hStage = 2u * OFF_KG * hPlane;
+    unsigned char* smX = smraw;                             /* [2][hi|lo][kg][rowsX][16 B]            */
+    unsigned char* smH = smX + 2u * xStage;                 /* [NH][hi|lo][kg][Nn][16 B]              */
+    uint64_t* xfull   = reinterpret_cast<uint64_t*>(smH + (size_t)OFF_NH * hStage);
+    uint64_t* xempty  = xfull + 2;
+    uint64_t* hfull   = xempty + 2;
+    uint64_t* hempty  = hfull + OFF_NH;
+    uint64_t* tfull   = hempty + OFF_NH;                    /* TMEM buffer set b holds a finished chain */
+    uint64_t* tempty  = tfull + 2;                          /* ... has been drained by all epilogue warps */
+    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int steps = a.nKC * a.P;                          /* partition steps of this tile           */
+    const int nFlush = (steps + a.flush - 1) / a.flush;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1);
+            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], OFF_EPI_WARPS);
+        }
+        for (int i = 0; i < OFF_NH; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == OFF_EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmemPtr)), "r"((uint32_t)a.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemPtr;
+
+    if (warp == OFF_EPI_WARPS) {
+        /* ===================== TMA producer ===================== */
+        if (lane == 0) {
+            int hs = 0; uint32_t hpar = 1;
+            for (int kc = 0; kc < a.nKC; ++kc) {
+                const int xs = kc & 1;
+                mbar_wait(&xempty[xs], (((uint32_t)kc >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&xfull[xs], xStage);
+                for (int hl = 0; hl < 2; ++hl)
+                    for (int g = 0; g < OFF_KG; ++g) {
+                        const float* src = (hl ? a.XGlo : a.XGhi)
+                                         + (((size_t)bin * a.nKG + (size_t)kc * OFF_KG + g) * a.rowsAlloc + t0) * 4;
+                        tma_bulk_g2s(smX + (size_t)xs * xStage + (size_t)(hl * OFF_KG + g) * xPlane, src, xPlane, &xfull[xs]);
+                    }
+                for (int p = 0; p < a.P; ++p) {
+                    mbar_wait(&hempty[hs], hpar);
+                    mbar_expect_tx(&hfull[hs], hStage);
+                    for (int hl = 0; hl < 2; ++hl) {
+                        const float* src = (hl ? a.HGlo : a.HGhi)
+                                         + ((((size_t)bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 4;
+                        tma_bulk_g2s(smH + (size_t)hs * hStage + (size_t)hl * OFF_KG * hPlane, src, OFF_KG * hPlane, &hfull[hs]);
+                    }
+                    if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == OFF_EPI_WARPS + 1) {
+        /* ===================== MMA issuer (one thread) ===================== */
+        if (lane == 0) {
+            int hs = 0; uint32_t hpar = 0;
+            int inChain = 0, nf = 0, step = 0;
+            for (int kc = 0; kc < a.nKC; ++kc) {
+                const int xs = kc & 1;
+                mbar_wait(&xfull[xs], ((uint32_t)kc >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t xBase = smem_u32(smX + (size_t)xs * xStage);
+                for (int p = 0; p < a.P; ++p, ++step) {
+                    const int tb = nf & 1;
+                    if (inChain == 0) {                                 /* new chain: its TMEM buffer set must be drained */
+                        mbar_wait(&tempty[tb], (((uint32_t)nf >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                    }
+                    mbar_wait(&hfull[hs], hpar);
+                    tc_fence_after();
+                    const uint32_t hBase = smem_u32(smH + (size_t)hs * hStage);
+                    const uint32_t shift = (uint32_t)(a.P - 1 - p) * 16u;       /* frame t-p = tile row +(P-1-p) */
+#pragma unroll
+                    for (int acc = 0; acc < 2; ++acc) {
+#pragma unroll
+                        for (int ks = 0; ks < OFF_KG / 2; ++ks) {
+                            const uint32_t aOff = (uint32_t)(2 * ks) * xPlane + (uint32_t)acc * 128u * 16u + shift;
+                            const uint32_t bOff = (uint32_t)(2 * ks) * hPlane;
+                            const uint64_t aHi = umma_sdesc(xBase + aOff, xPlane, 128);
+                            const uint64_t aLo = umma_sdesc(xBase + OFF_KG * xPlane + aOff, xPlane, 128);
+                            const uint64_t bHi = umma_sdesc(hBase + bOff, hPlane, 128);
+                            const uint64_t bLo = umma_sdesc(hBase + OFF_KG * hPlane + bOff, hPlane, 128);
+                            const uint32_t d = tmem + (uint32_t)((tb * 2 + acc) * a.Nn);
+                            /* small cross terms first, the large hi*hi term last */
+                            umma_tf32(d, aLo, bHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
+                            umma_tf32(d, aHi, bLo, a.idesc, 1u);                         /* hi*lo */
+                            umma_tf32(d, aHi, bHi, a.idesc, 1u);                         /* hi*hi */
+                        }
+                    }
+                    umma_commit(&hempty[hs]);                           /* filter stage free once these MMAs retire */
+                    if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
+                    if (++inChain == a.flush || step + 1 == steps) {
+                        umma_commit(&tfull[tb]);                        /* chain complete -> epilogue may drain it */
+                        ++nf; inChain = 0;
+                    }
+                }
+                umma_commit(&xempty[xs]);
+            }
+        }
+    } else {
+        /* ===================== epilogue warps: promote TMEM chains into fp32 register sums ===================== */
+        const int q = warp & 3, hh = warp >> 2;            /* TMEM lane quarter (= warp % 4), column half */
+        const int halfN = a.Nn >> 1;
+        float sum[2][OFF_MAX_HALF];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < OFF_MAX_HALF; ++c) sum[t][c] = 0.f;
+        for (int f = 0; f < nFlush; ++f) {
+            const int tb = f & 1;
+            mbar_wait(&tfull[tb], ((uint32_t)f >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 16) {
+                    if (c0 < halfN) {
+                        float v[16];
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0), v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sum[t][c0 + i] += v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[tb]);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int row = t0 + t * 128 + q * 32 + lane;
+            float* dst = a.Ys + ((size_t)bin * a.Tpad + row) * a.Nn + hh * halfN;
+#pragma unroll
+            for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 4)
+                if (c0 < halfN)
+                    *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[t][c0], sum[t][c0 + 1], sum[t][c0 + 2], sum[t][c0 + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == OFF_EPI_WARPS + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)a.tmemCols) : "memory");
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  inverse FFT per (frame, output): grid (ceil(nOut/8), T)                                      */
+/* ------------------------------------------------------------------------------------------ */
+struct OffIfftArgs {
+    const float2* Ys;      /* [bin][Tpad][Nn/2] complex */
+    float* zt;             /* [T][nOut][2*hop] */
+    float* out;            /* [nOut][T*hop] */
+    const float2* tw;
+    int hop, M, logM, nOut, Nn2, Tpad, T;
+    float scale;
+};
+
+__global__ void offline_ifft_kernel(OffIfftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + (size_t)OFF_OPC * a.M;
+    const int og = blockIdx.x, t = blockIdx.y;
+    load_twiddles(stw, a.tw, a.M);
+    for (int idx = threadIdx.x; idx < a.M * OFF_OPC; idx += blockDim.x) {
+        const int j = idx & (OFF_OPC - 1), k = idx / OFF_OPC;
+        const int no = og * OFF_OPC + j;
+        sm[(size_t)j * a.M + k] = (no < a.nOut) ? a.Ys[((size_t)k * a.Tpad + t) * a.Nn2 + no] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int j = 0; j < OFF_OPC; ++j) {
+        if (og * OFF_OPC + j >= a.nOut) break;
+        inv_split_all(sm + (size_t)j * a.M, a.M, stw);
+        cfft_dif<true>(sm + (size_t)j * a.M, a.M, a.logM, stw);
+    }
+    for (int j = 0; j < OFF_OPC; ++j) {
+        const int no = og * OFF_OPC + j;
+        if (no >= a.nOut) break;
+        float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
+        const float2* s = sm + (size_t)j * a.M;
+        for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(s, i, a.logM) * a.scale;
+    }
+}
+
+/* out[no][t*hop + i] = z_t[i] + z_{t-1}[hop + i]  (zero state before the first frame) */
+__global__ void offline_ola_kernel(OffIfftArgs a)
+{
+    const size_t n = (size_t)a.T * a.nOut * a.hop;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int i = (int)(e % a.hop);
+        size_t r = e / a.hop;
+        const int t = (int)(r % a.T);
+        const int no = (int)(r / a.T);
+        const float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
+        float v = z[i];
+        if (t > 0) v += a.zt[((size_t)(t - 1) * a.nOut + no) * 2 * a.hop + a.hop + i];
+        a.out[(size_t)no * a.T * a.hop + (size_t)t * a.hop + i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  C-ABI                                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+static size_t roundup(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+int scdev_offline_free(scdev_offline* o)
+{
+    if (!o) return 0;
+    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys); cudaFree(o->zt);
+    o->XGhi = o->XGlo = o->HGhi = o->HGlo = o->Ys = o->zt = NULL;
+    o->capFrames = 0; o->packed = 0;
+    return 0;
+}
+
+/* (re)allocate the workspace for T frames and build the filter operand once */
+int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o, int T, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->kind != SC_KIND_MATRIX) return (int)cudaErrorInvalidValue;
+    int Nn = 32;                                                     /* UMMA N: 2*nOut padded to 32 / 64 / 128 */
+    while (Nn < 2 * pl->nOutLocal) Nn <<= 1;
+    if (Nn > 2 * OFF_MAX_HALF) return (int)cudaErrorInvalidValue;    /* one N tile: nOutLocal <= 64 */
+    if (pl->P - 1 > 1024) return (int)cudaErrorInvalidValue;
+    o->Nn = Nn;
+    o->Kp = (int)roundup((size_t)2 * pl->nIn, 4 * OFF_KG);
+    o->nKG = o->Kp / 4;
+    o->nKC = o->nKG / OFF_KG;
+    o->rowsX = OFF_MT + pl->P - 1;
+    o->tmemCols = 4 * Nn;                                            /* two buffer sets x two frame tiles */
+    o->gemmSmem = 2 * (2 * OFF_KG * o->rowsX * 16) + OFF_NH * (2 * OFF_KG * Nn * 16) + (8 + 2 * OFF_NH) * 8 + 16;
+    {
+        const char* v = getenv("SAFCONV_OFF_FLUSH");
+        int fl = v ? atoi(v) : 1;
+        o->flush = fl < 1 ? 1 : fl;
+    }
+    if (!o->packed) {
+        const size_t hgFloats = (size_t)pl->M * pl->P * o->nKG * Nn * 4;
+        SC_CHECK(cudaMalloc((void**)&o->HGhi, hgFloats * sizeof(float)));
+        SC_CHECK(cudaMalloc((void**)&o->HGlo, hgFloats * sizeof(float)));
+        SC_CHECK(cudaMemsetAsync(o->HGhi, 0, hgFloats * sizeof(float), st));
+        SC_CHECK(cudaMemsetAsync(o->HGlo, 0, hgFloats * sizeof(float), st));
+        PackArgs a;
+        a.H = (const float2*)b->H; a.HGhi = o->HGhi; a.HGlo = o->HGlo;
+        a.total = (size_t)pl->nOT * pl->nKT * pl->P * pl->nIn * pl->OTsz * SC_BK;
+        a.nKT = pl->nKT; a.P = pl->P; a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.nOutLocal = pl->nOutLocal;
+        a.nKG = o->nKG; a.Nn = Nn;
+        offline_pack_filters_kernel<<<148 * 8, 256, 0, st>>>(a);
+        SC_CHECK(cudaGetLastError());
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        const int fftSmem = (2 * OFF_FPC + 1) * pl->M * 8, ifftSmem = (OFF_OPC + 1) * pl->M * 8;
+        if (fftSmem > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
+        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ifftSmem));
+        o->packed = 1;
+    }
+    if (T > o->capFrames) {
+        SC_CHECK(cudaStreamSynchronize(st));
+        cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->Ys); cudaFree(o->zt);
+        o->XGhi = o->XGlo = o->Ys = o->zt = NULL; o->capFrames = 0;
+        const size_t Tpad = roundup((size_t)T, OFF_MT);
+        const size_t rowsAlloc = roundup(Tpad + pl->P - 1, OFF_FPC);
+        const size_t xgFloats = (size_t)pl->M * o->nKG * rowsAlloc * 4;
+        SC_CHECK(cudaMalloc((void**)&o->XGhi, xgFloats * sizeof(float)));
+        SC_CHECK(cudaMalloc((void**)&o->XGlo, xgFloats * sizeof(float)));
+        SC_CHECK(cudaMalloc((void**)&o->Ys, (size_t)pl->M * Tpad * Nn * sizeof(float)));
+        SC_CHECK(cudaMalloc((void**)&o->zt, (size_t)T * pl->nOutLocal * 2 * pl->hop * sizeof(float)));
+        /* padding k-groups (odd nIn / K padding) are never written by the FFT kernel: zero them once */
+        SC_CHECK(cudaMemsetAsync(o->XGhi, 0, xgFloats * sizeof(float), st));
+        SC_CHECK(cudaMemsetAsync(o->XGlo, 0, xgFloats * sizeof(float), st));
+        o->capFrames = T; o->capTpad = (int)Tpad; o->capRows = (int)rowsAlloc;
+    }
+    return 0;
+}
+
+/* d_in [nIn][T*hop] -> d_out [nOutLocal][T*hop]; zero state before the first frame */
+int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
+                      const float* d_in, float* d_out, int T, void** events, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T < 1 || T > o->capFrames) return (int)cudaErrorInvalidValue;
+    const int Tpad = (int)roundup((size_t)T, OFF_MT);
+    const int rowsAlloc = o->capRows;           /* row stride of the operand as allocated */
+    const int rowsUsed = (int)roundup((size_t)Tpad + pl->P - 1, OFF_FPC);
+
+    if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[0], st));
+    OffFftArgs f;
+    f.in = d_in; f.XGhi = o->XGhi; f.XGlo = o->XGlo; f.tw = (const float2*)b->tw;
+    f.inStride = (size_t)T * pl->hop;
+    f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
+    f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
+    {
+        dim3 grid((pl->nIn + 1) / 2, rowsUsed / OFF_FPC);
+        offline_fft_kernel<<<grid, 256, (size_t)(2 * OFF_FPC + 1) * pl->M * 8, st>>>(f);
+        SC_CHECK(cudaGetLastError());
+    }
+    if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[1], st));
+    OffGemmArgs g;
+    g.XGhi = o->XGhi; g.XGlo = o->XGlo; g.HGhi = o->HGhi; g.HGlo = o->HGlo; g.Ys = o->Ys;
+    g.P = pl->P; g.nKG = o->nKG; g.nKC = o->nKC; g.Nn = o->Nn; g.rowsAlloc = rowsAlloc; g.Tpad = o->capTpad;
+    g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush; g.idesc = umma_idesc_tf32(128, o->Nn);
+    {
+        dim3 grid(Tpad / OFF_MT, pl->M);
+        offline_gemm_kernel<<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+        SC_CHECK(cudaGetLastError());
+    }
+    if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[2], st));
+    OffIfftArgs i;
+    i.Ys = (const float2*)o->Ys; i.zt = o->zt; i.out = d_out; i.tw = (const float2*)b->tw;
+    i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
+    i.Tpad = o->capTpad; i.T = T; i.scale = 1.0f / (float)pl->N;
+    {
+        dim3 grid((pl->nOutLocal + OFF_OPC - 1) / OFF_OPC, T);
+        offline_ifft_kernel<<<grid, 256, (size_t)(OFF_OPC + 1) * pl->M * 8, st>>>(i);
+        SC_CHECK(cudaGetLastError());
+        offline_ola_kernel<<<148 * 8, 256, 0, st>>>(i);
+        SC_CHECK(cudaGetLastError());
+    }
+    if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[3], st));
+    return 0;
+}
+
+} /* extern "C" */

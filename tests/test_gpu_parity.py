@@ -211,6 +211,44 @@ def test_batched_device_blocks_equal_block_by_block(saf, orc, hop, L, nIn, nOut,
     assert np.array_equal(yh, outs[0])
 
 
+@pytest.mark.parametrize("hop,L,nIn,nOut,T", [(64, 200, 3, 2, 20), (128, 128, 1, 1, 5), (256, 2048, 11, 5, 300),
+                                               (32, 1000, 2, 3, 270), (512, 3000, 4, 9, 40)])
+def test_offline_tensor_core_render_vs_oracle(saf, orc, hop, L, nIn, nOut, T):
+    """safconv_render_offline (tcgen05 per-bin GEMM, 3xTF32 split, fp32 accumulate in TMEM) == the reference's
+    block-by-block convolution from a zero state, within the north_star tolerance."""
+    rng = np.random.default_rng(hop + L + T)
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * T)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H)
+    y = mc.render_offline(x)
+    ma, l2 = check(y, ref, "offline render")
+    t = orc.truth_matrix(H, x, np.arange(nOut), 0, hop * T)
+    _, l2_gt = err_metrics(y, t)
+    _, l2_rt = err_metrics(ref, t)
+    print(f"offline: gpu-ref {l2:.3g}  gpu-truth {l2_gt:.3g}  ref-truth {l2_rt:.3g}")
+    assert l2_gt <= TOL_REL_L2
+    # a second render on the same handle (workspace re-use, shorter signal) and the streaming path still agree
+    y2 = mc.render_offline(x[:, :hop * (T // 2)])
+    check(y2, ref[:, :hop * (T // 2)], "offline render, shorter")
+    ys = mc.run(x)
+    check(ys, y, "streaming vs offline")
+
+
+def test_offline_render_c5_shape_vs_streaming(saf):
+    """configs[4] channel counts (121 in x 64 out, hop 1024, 8192 taps) on a shortened signal: the offline
+    tensor-core path against the (oracle-verified) streaming path on the same handle."""
+    from spatial_audio_framework_b200 import synth
+    hop, L, nIn, nOut, T = 1024, 8192, 121, 64, 300
+    H = synth.decaying_rir((nOut, nIn, L), seed=5)
+    x = synth.uniform((nIn, hop * T), seed=6)
+    mc = saf.MatrixConv(hop, H)
+    y = mc.render_offline(x)
+    ys = mc.run(x)
+    ma, l2 = check(y, ys, "C5 offline vs streaming")
+    print("C5-shape offline vs streaming", ma, l2, mc.offline_times_ms())
+
+
 def test_pinned_caller_buffers_are_used_directly(saf, orc):
     import torch
     rng = np.random.default_rng(8)
