@@ -44,8 +44,10 @@ __device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
     return w;
 }
 
+/* nArr independent transforms stored back to back (array a at s + a*M) advance together, pass by pass:
+ * one __syncthreads per pass for the whole batch instead of one per pass per transform */
 template <bool INV>
-__device__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw)
+__device__ void cfft_dif_batch(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     int L = M;                 /* current sub-transform length */
@@ -55,10 +57,13 @@ __device__ void cfft_dif(float2* s, const int M, const int logM, const float2* _
     while (nsm >= 2) {
         const int q = L >> 2;
         const int tstr = (2 * M) / L;
-        for (int i = tid; i < (M >> 2); i += T) {
+        const int per = M >> 2;                    /* butterflies per transform */
+        for (int it = tid; it < nArr * per; it += T) {
+            const int arr = it >> (logM - 2), i = it & (per - 1);
+            float2* sa = s + (size_t)arr * M;
             const int j = i & (q - 1);
             const int base = ((i - j) << 2) + j;
-            const float2 a0 = s[base], a1 = s[base + q], a2 = s[base + 2 * q], a3 = s[base + 3 * q];
+            const float2 a0 = sa[base], a1 = sa[base + q], a2 = sa[base + 2 * q], a3 = sa[base + 3 * q];
             const float2 w1 = twd<INV>(tw, j * tstr);
             const float2 w2 = twd<INV>(tw, 2 * j * tstr);
             const float2 u0 = caddf(a0, a2);
@@ -68,10 +73,10 @@ __device__ void cfft_dif(float2* s, const int M, const int logM, const float2* _
             /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
             d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
             const float2 v1 = cmulf(d1, w1);
-            s[base]         = caddf(u0, u1);
-            s[base + q]     = cmulf(csubf(u0, u1), w2);
-            s[base + 2 * q] = caddf(v0, v1);
-            s[base + 3 * q] = cmulf(csubf(v0, v1), w2);
+            sa[base]         = caddf(u0, u1);
+            sa[base + q]     = cmulf(csubf(u0, u1), w2);
+            sa[base + 2 * q] = caddf(v0, v1);
+            sa[base + 3 * q] = cmulf(csubf(v0, v1), w2);
         }
         __syncthreads();
         L >>= 2;
@@ -80,26 +85,30 @@ __device__ void cfft_dif(float2* s, const int M, const int logM, const float2* _
     if (nsm == 1) {
         const int half = L >> 1;
         const int tstr = (2 * M) / L;
-        for (int i = tid; i < (M >> 1); i += T) {
+        const int per = M >> 1;
+        for (int it = tid; it < nArr * per; it += T) {
+            const int arr = it >> (logM - 1), i = it & (per - 1);
+            float2* sa = s + (size_t)arr * M;
             const int j = i & (half - 1);
             const int base = ((i - j) << 1) + j;
-            const float2 a = s[base], b = s[base + half];
+            const float2 a = sa[base], b = sa[base + half];
             const float2 w = twd<INV>(tw, j * tstr);
-            s[base]        = caddf(a, b);
-            s[base + half] = cmulf(csubf(a, b), w);
+            sa[base]        = caddf(a, b);
+            sa[base + half] = cmulf(csubf(a, b), w);
         }
         __syncthreads();
         L >>= 1;
     }
-    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp */
+    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp; rows of 32 points of all
+     * transforms are contiguous, so the batch is just more rows */
     {
         const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
         float2 w16 = twd<INV>(tw, (lane & 15) * (M >> 4));
         float2 w8  = twd<INV>(tw, (lane & 7)  * (M >> 3));
         float2 w4  = twd<INV>(tw, (lane & 3)  * (M >> 2));
         float2 w2  = twd<INV>(tw, (lane & 1)  * (M >> 1));
-        for (int row = warp; row < (M >> 5); row += nwarps) {
-            float2 v = s[row * 32 + lane];
+        for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
+            float2 v = s[(size_t)row * 32 + lane];
 #define SC_SHFL_STAGE(HALF, W)                                                       \
             {                                                                        \
                 float2 o;                                                            \
@@ -119,10 +128,16 @@ __device__ void cfft_dif(float2* s, const int M, const int logM, const float2* _
                 v = (lane & 1) ? csubf(o, v) : caddf(v, o);
             }
 #undef SC_SHFL_STAGE
-            s[row * 32 + lane] = v;
+            s[(size_t)row * 32 + lane] = v;
         }
         __syncthreads();
     }
+}
+
+template <bool INV>
+__device__ __forceinline__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw)
+{
+    cfft_dif_batch<INV>(s, M, logM, tw, 1);
 }
 
 /* copy the twiddle table into shared memory (coalesced; overlaps the input load that follows) */
@@ -174,6 +189,24 @@ __device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, const fl
     const float2 O = cmul_conjb(D, tw[k]);
     Z[k]     = make_float2(E.x - O.y, E.y + O.x);
     Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
+}
+
+/* inverse split pass of nArr packed spectra stored back to back */
+__device__ __forceinline__ void inv_split_batch(float2* Z, int M, int logM, const float2* __restrict__ tw, int nArr)
+{
+    const int per = (M >> 1) + 1;
+    for (int it = threadIdx.x; it < nArr * per; it += blockDim.x) {
+        const int arr = it / per, k = it - arr * per;
+        float2* Za = Z + (size_t)arr * M;
+        if (k == 0) {
+            const float2 A = Za[0];                      /* (DC, Nyquist) */
+            Za[0] = make_float2(A.x + A.y, A.x - A.y);
+        } else {
+            inv_split_pair(Za, k, M, tw);
+        }
+    }
+    (void)logM;
+    __syncthreads();
 }
 
 __device__ __forceinline__ void inv_split_all(float2* Z, int M, const float2* __restrict__ tw)

@@ -538,9 +538,8 @@ __global__ void tv_fused_kernel(TvArgs a)
         Z0[k] = z0; Z1[k] = z1; Z2[k] = z2;
     }
     __syncthreads();
-    inv_split_all(Z0, a.M, stw);  cfft_dif<true>(Z0, a.M, a.logM, stw);
-    inv_split_all(Z1, a.M, stw);  cfft_dif<true>(Z1, a.M, a.logM, stw);
-    inv_split_all(Z2, a.M, stw);  cfft_dif<true>(Z2, a.M, a.logM, stw);
+    inv_split_batch(Z0, a.M, a.logM, stw, 3);           /* Z0, Z1, Z2 are contiguous */
+    cfft_dif_batch<true>(Z0, a.M, a.logM, stw, 3);
     /* cross-fade (reference .c:494-497, 605-615) */
     float* t0 = a.tail0 + (size_t)no * a.hop;
     float* t1 = a.tail1 + (size_t)no * a.hop;

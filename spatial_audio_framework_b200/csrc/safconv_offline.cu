@@ -128,7 +128,7 @@ __global__ void offline_fft_kernel(OffFftArgs a)
         }
     }
     __syncthreads();
-    for (int q = 0; q < 2 * OFF_FPC; ++q) cfft_dif<false>(sm + (size_t)q * a.M, a.M, a.logM, stw);
+    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * OFF_FPC);
 
     const int half = a.M >> 1;
     for (int idx = threadIdx.x; idx < (half + 1) * OFF_FPC; idx += blockDim.x) {
@@ -418,10 +418,10 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
         sm[(size_t)j * a.M + k] = (no < a.nOut) ? a.Ys[((size_t)k * a.Tpad + t) * a.Nn2 + no] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    for (int j = 0; j < OFF_OPC; ++j) {
-        if (og * OFF_OPC + j >= a.nOut) break;
-        inv_split_all(sm + (size_t)j * a.M, a.M, stw);
-        cfft_dif<true>(sm + (size_t)j * a.M, a.M, a.logM, stw);
+    {
+        const int nArr = min(OFF_OPC, a.nOut - og * OFF_OPC);
+        inv_split_batch(sm, a.M, a.logM, stw, nArr);
+        cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
     }
     for (int j = 0; j < OFF_OPC; ++j) {
         const int no = og * OFF_OPC + j;
