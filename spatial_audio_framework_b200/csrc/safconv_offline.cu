@@ -201,6 +201,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  :: "r"(smem_u32(bar)) : "memory");
 }
+/* one lane of the (fully active) warp */
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -302,35 +309,37 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
             }
         }
     } else if (warp == OFF_EPI_WARPS + 1) {
-        /* ===================== MMA issuer (one thread) ===================== */
-        if (lane == 0) {
-            int hs = 0; uint32_t hpar = 0;
-            int inChain = 0, nf = 0, step = 0;
-            for (int kc = 0; kc < a.nKC; ++kc) {
-                const int xs = kc & 1;
-                mbar_wait(&xfull[xs], ((uint32_t)kc >> 1) & 1u);
+        /* ===================== MMA issuer ===================== */
+        /* The whole warp runs the (uniform) control flow; one elected lane issues the tcgen05 instructions.
+         * Descriptors are a per-kernel constant plus the 16-byte-unit start address, so each MMA costs a
+         * couple of integer adds on the issuing thread, not a descriptor rebuild. */
+        const bool leader = elect_one();
+        const uint64_t aDesc0 = umma_sdesc(0, xPlane, 128);
+        const uint64_t bDesc0 = umma_sdesc(0, hPlane, 128);
+        const uint32_t xPlane16 = xPlane >> 4, hPlane16 = hPlane >> 4;
+        int hs = 0; uint32_t hpar = 0;
+        int inChain = 0, nf = 0, step = 0;
+        for (int kc = 0; kc < a.nKC; ++kc) {
+            const int xs = kc & 1;
+            mbar_wait(&xfull[xs], ((uint32_t)kc >> 1) & 1u);
+            const uint32_t xBase16 = smem_u32(smX + (size_t)xs * xStage) >> 4;
+            for (int p = 0; p < a.P; ++p, ++step) {
+                const int tb = nf & 1;
+                if (inChain == 0)                                       /* new chain: its TMEM buffer set must be drained */
+                    mbar_wait(&tempty[tb], (((uint32_t)nf >> 1) & 1u) ^ 1u);
+                mbar_wait(&hfull[hs], hpar);
                 tc_fence_after();
-                const uint32_t xBase = smem_u32(smX + (size_t)xs * xStage);
-                for (int p = 0; p < a.P; ++p, ++step) {
-                    const int tb = nf & 1;
-                    if (inChain == 0) {                                 /* new chain: its TMEM buffer set must be drained */
-                        mbar_wait(&tempty[tb], (((uint32_t)nf >> 1) & 1u) ^ 1u);
-                        tc_fence_after();
-                    }
-                    mbar_wait(&hfull[hs], hpar);
-                    tc_fence_after();
-                    const uint32_t hBase = smem_u32(smH + (size_t)hs * hStage);
-                    const uint32_t shift = (uint32_t)(a.P - 1 - p) * 16u;       /* frame t-p = tile row +(P-1-p) */
+                if (leader) {
+                    const uint32_t hBase16 = smem_u32(smH + (size_t)hs * hStage) >> 4;
+                    const uint32_t rowShift = (uint32_t)(a.P - 1 - p);  /* frame t-p = tile row +(P-1-p); 16 B per row */
 #pragma unroll
                     for (int acc = 0; acc < 2; ++acc) {
 #pragma unroll
                         for (int ks = 0; ks < OFF_KG / 2; ++ks) {
-                            const uint32_t aOff = (uint32_t)(2 * ks) * xPlane + (uint32_t)acc * 128u * 16u + shift;
-                            const uint32_t bOff = (uint32_t)(2 * ks) * hPlane;
-                            const uint64_t aHi = umma_sdesc(xBase + aOff, xPlane, 128);
-                            const uint64_t aLo = umma_sdesc(xBase + OFF_KG * xPlane + aOff, xPlane, 128);
-                            const uint64_t bHi = umma_sdesc(hBase + bOff, hPlane, 128);
-                            const uint64_t bLo = umma_sdesc(hBase + OFF_KG * hPlane + bOff, hPlane, 128);
+                            const uint32_t a16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + (uint32_t)acc * 128u + rowShift;
+                            const uint32_t b16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
+                            const uint64_t aHi = aDesc0 + a16, aLo = aDesc0 + a16 + OFF_KG * xPlane16;
+                            const uint64_t bHi = bDesc0 + b16, bLo = bDesc0 + b16 + OFF_KG * hPlane16;
                             const uint32_t d = tmem + (uint32_t)((tb * 2 + acc) * a.Nn);
                             /* small cross terms first, the large hi*hi term last */
                             umma_tf32(d, aLo, bHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
@@ -339,14 +348,16 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                         }
                     }
                     umma_commit(&hempty[hs]);                           /* filter stage free once these MMAs retire */
-                    if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
-                    if (++inChain == a.flush || step + 1 == steps) {
-                        umma_commit(&tfull[tb]);                        /* chain complete -> epilogue may drain it */
-                        ++nf; inChain = 0;
-                    }
                 }
-                umma_commit(&xempty[xs]);
+                if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
+                if (++inChain == a.flush || step + 1 == steps) {
+                    if (leader) umma_commit(&tfull[tb]);                /* chain complete -> epilogue may drain it */
+                    ++nf; inChain = 0;
+                }
+                __syncwarp();
             }
+            if (leader) umma_commit(&xempty[xs]);
+            __syncwarp();
         }
     } else {
         /* ===================== epilogue warps: promote TMEM chains into fp32 register sums ===================== */
