@@ -28,9 +28,17 @@ __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2
 
 __device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((unsigned)v) >> (32 - logM)); }
 
+/* FFT work arrays in shared memory are PADDED: element i of an M-point array lives at i + (i >> (logM-4)),
+ * i.e. one extra float2 after every M/16 elements (array length M + SC_PAD).  The FFT leaves its result in
+ * bit-reversed order; the epilogues read s[bitrev(k)] for consecutive k, which without padding puts all 32
+ * lanes on one bank (stride M/32 elements).  With the padding those reads are conflict-free, and the
+ * unit-stride accesses of the FFT passes stay (almost) unit-stride. */
+#define SC_PAD 16
+__device__ __forceinline__ int padi(int i, int logM) { return i + (i >> (logM - 4)); }
+
 /* ------------------------------------------------------------------------------------------ */
 /*  M-point complex FFT in shared memory, decimation in frequency                              */
-/*  input: natural order in s[0..M) ; output: s[bitrev(k)] holds bin k                          */
+/*  input: natural order (padded indexing) ; output: element padi(bitrev(k)) holds bin k          */
 /*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)]); the kernels copy the    */
 /*  table into shared memory first (load_twiddles) so that no pass waits on an L2 round trip.    */
 /*  INV conjugates every twiddle (unnormalised inverse transform).                              */
@@ -44,7 +52,7 @@ __device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
     return w;
 }
 
-/* nArr independent transforms stored back to back (array a at s + a*M) advance together, pass by pass:
+/* nArr independent transforms stored back to back (array a at s + a*(M+SC_PAD)) advance together, pass by pass:
  * one __syncthreads per pass for the whole batch instead of one per pass per transform */
 template <bool INV>
 __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
@@ -60,10 +68,11 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
         const int per = M >> 2;                    /* butterflies per transform */
         for (int it = tid; it < nArr * per; it += T) {
             const int arr = it >> (logM - 2), i = it & (per - 1);
-            float2* sa = s + (size_t)arr * M;
+            float2* sa = s + (size_t)arr * (M + SC_PAD);
             const int j = i & (q - 1);
             const int base = ((i - j) << 2) + j;
-            const float2 a0 = sa[base], a1 = sa[base + q], a2 = sa[base + 2 * q], a3 = sa[base + 3 * q];
+            const int i0 = padi(base, logM), i1 = padi(base + q, logM), i2 = padi(base + 2 * q, logM), i3 = padi(base + 3 * q, logM);
+            const float2 a0 = sa[i0], a1 = sa[i1], a2 = sa[i2], a3 = sa[i3];
             const float2 w1 = twd<INV>(tw, j * tstr);
             const float2 w2 = twd<INV>(tw, 2 * j * tstr);
             const float2 u0 = caddf(a0, a2);
@@ -73,10 +82,10 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
             /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
             d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
             const float2 v1 = cmulf(d1, w1);
-            sa[base]         = caddf(u0, u1);
-            sa[base + q]     = cmulf(csubf(u0, u1), w2);
-            sa[base + 2 * q] = caddf(v0, v1);
-            sa[base + 3 * q] = cmulf(csubf(v0, v1), w2);
+            sa[i0] = caddf(u0, u1);
+            sa[i1] = cmulf(csubf(u0, u1), w2);
+            sa[i2] = caddf(v0, v1);
+            sa[i3] = cmulf(csubf(v0, v1), w2);
         }
         __syncthreads();
         L >>= 2;
@@ -88,13 +97,14 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
         const int per = M >> 1;
         for (int it = tid; it < nArr * per; it += T) {
             const int arr = it >> (logM - 1), i = it & (per - 1);
-            float2* sa = s + (size_t)arr * M;
+            float2* sa = s + (size_t)arr * (M + SC_PAD);
             const int j = i & (half - 1);
             const int base = ((i - j) << 1) + j;
-            const float2 a = sa[base], b = sa[base + half];
+            const int i0 = padi(base, logM), i1 = padi(base + half, logM);
+            const float2 a = sa[i0], b = sa[i1];
             const float2 w = twd<INV>(tw, j * tstr);
-            sa[base]        = caddf(a, b);
-            sa[base + half] = cmulf(csubf(a, b), w);
+            sa[i0] = caddf(a, b);
+            sa[i1] = cmulf(csubf(a, b), w);
         }
         __syncthreads();
         L >>= 1;
@@ -108,7 +118,9 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
         float2 w4  = twd<INV>(tw, (lane & 3)  * (M >> 2));
         float2 w2  = twd<INV>(tw, (lane & 1)  * (M >> 1));
         for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
-            float2 v = s[(size_t)row * 32 + lane];
+            const int arr = row >> (logM - 5), rr = row & ((M >> 5) - 1);
+            float2* sp = s + (size_t)arr * (M + SC_PAD) + padi(rr * 32 + lane, logM);
+            float2 v = *sp;
 #define SC_SHFL_STAGE(HALF, W)                                                       \
             {                                                                        \
                 float2 o;                                                            \
@@ -128,7 +140,7 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
                 v = (lane & 1) ? csubf(o, v) : caddf(v, o);
             }
 #undef SC_SHFL_STAGE
-            s[(size_t)row * 32 + lane] = v;
+            *sp = v;
         }
         __syncthreads();
     }
@@ -147,20 +159,20 @@ __device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restr
 }
 
 /* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
-__device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M)
+__device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M, int logM)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     if ((hop & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
         const float2* x2 = reinterpret_cast<const float2*>(x);
         const int h2 = hop >> 1;
-        for (int n = tid; n < M; n += T) s[n] = (n < h2) ? __ldg(x2 + n) : make_float2(0.f, 0.f);
+        for (int n = tid; n < M; n += T) s[padi(n, logM)] = (n < h2) ? __ldg(x2 + n) : make_float2(0.f, 0.f);
     } else {
         for (int n = tid; n < M; n += T) {
             const int i = 2 * n;
             float2 v;
             v.x = (i < hop) ? __ldg(x + i) : 0.f;
             v.y = (i + 1 < hop) ? __ldg(x + i + 1) : 0.f;
-            s[n] = v;
+            s[padi(n, logM)] = v;
         }
     }
 }
@@ -170,8 +182,8 @@ __device__ __forceinline__ void load_real_block(float2* s, const float* __restri
 __device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, int logM,
                                                const float2* __restrict__ tw, float2& Xk, float2& Xmk)
 {
-    const float2 a = s[bitrev(k, logM)];
-    const float2 b = s[bitrev(M - k, logM)];
+    const float2 a = s[padi(bitrev(k, logM), logM)];
+    const float2 b = s[padi(bitrev(M - k, logM), logM)];
     const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
     const float2 t = cmulf(tw[k], O);
@@ -181,14 +193,15 @@ __device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, in
 
 /* inverse split pass, in place on the packed natural-order spectrum Z (pair k, M-k; 1 <= k <= M/2):
  * Zc[k] = E + iO, Zc[M-k] = conj(E) + i conj(O), E = A + conj B, O = (A - conj B) W_N^-k  (the 1/2 is folded into 1/N) */
-__device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, const float2* __restrict__ tw)
+__device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, int logM, const float2* __restrict__ tw)
 {
-    const float2 A = Z[k], B = Z[M - k];
+    const int ik = padi(k, logM), im = padi(M - k, logM);
+    const float2 A = Z[ik], B = Z[im];
     const float2 E = make_float2(A.x + B.x, A.y - B.y);
     const float2 D = make_float2(A.x - B.x, A.y + B.y);
     const float2 O = cmul_conjb(D, tw[k]);
-    Z[k]     = make_float2(E.x - O.y, E.y + O.x);
-    Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
+    Z[ik] = make_float2(E.x - O.y, E.y + O.x);
+    Z[im] = make_float2(E.x + O.y, O.x - E.y);
 }
 
 /* inverse split pass of nArr packed spectra stored back to back */
@@ -197,35 +210,26 @@ __device__ __forceinline__ void inv_split_batch(float2* Z, int M, int logM, cons
     const int per = (M >> 1) + 1;
     for (int it = threadIdx.x; it < nArr * per; it += blockDim.x) {
         const int arr = it / per, k = it - arr * per;
-        float2* Za = Z + (size_t)arr * M;
+        float2* Za = Z + (size_t)arr * (M + SC_PAD);
         if (k == 0) {
             const float2 A = Za[0];                      /* (DC, Nyquist) */
             Za[0] = make_float2(A.x + A.y, A.x - A.y);
         } else {
-            inv_split_pair(Za, k, M, tw);
+            inv_split_pair(Za, k, M, logM, tw);
         }
     }
-    (void)logM;
     __syncthreads();
 }
 
-__device__ __forceinline__ void inv_split_all(float2* Z, int M, const float2* __restrict__ tw)
+__device__ __forceinline__ void inv_split_all(float2* Z, int M, int logM, const float2* __restrict__ tw)
 {
-    for (int k = threadIdx.x; k <= (M >> 1); k += blockDim.x) {
-        if (k == 0) {
-            const float2 A = Z[0];                       /* (DC, Nyquist) */
-            Z[0] = make_float2(A.x + A.y, A.x - A.y);
-        } else {
-            inv_split_pair(Z, k, M, tw);
-        }
-    }
-    __syncthreads();
+    inv_split_batch(Z, M, logM, tw, 1);
 }
 
 /* time sample j of the (bit-reversed) inverse transform result */
 __device__ __forceinline__ float time_sample(const float2* s, int j, int logM)
 {
-    const float2 v = s[bitrev(j >> 1, logM)];
+    const float2 v = s[padi(bitrev(j >> 1, logM), logM)];
     return (j & 1) ? v.y : v.x;
 }
 

@@ -45,7 +45,7 @@ struct FilterArgs {
 __global__ void filter_fft_kernel(FilterArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M;
+    float2* stw = sm + a.M + SC_PAD;
     load_twiddles(stw, a.tw, a.M);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
     const float* src;
@@ -58,7 +58,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
         float2 v;
         v.x = (2 * n < a.hop && i < a.len) ? __ldg(src + i) : 0.f;
         v.y = (2 * n + 1 < a.hop && i + 1 < a.len) ? __ldg(src + i + 1) : 0.f;
-        sm[n] = v;
+        sm[padi(n, a.logM)] = v;
     }
     __syncthreads();
     cfft_dif<false>(sm, a.M, a.logM, stw);
@@ -105,11 +105,11 @@ struct InFftArgs {
 __global__ void input_fft_kernel(InFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M;
+    float2* stw = sm + a.M + SC_PAD;
     const int ni = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     load_twiddles(stw, a.tw, a.M);
-    load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M);
+    load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(sm, a.M, a.logM, stw);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
@@ -332,10 +332,10 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
             z = caddf(caddf(caddf(caddf(z, v0), v1), v2), v3);
         }
         for (; q < q1; ++q, src += qs) z = caddf(z, src[0]);
-        sm[k] = z;
+        sm[padi(k, a.logM)] = z;
     }
     __syncthreads();
-    inv_split_all(sm, a.M, stw);
+    inv_split_all(sm, a.M, a.logM, stw);
     cfft_dif<true>(sm, a.M, a.logM, stw);
 }
 
@@ -344,7 +344,7 @@ __global__ void ifft_ola_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x;
-    gather_and_ifft(a, a.Zp, no, sm, sm + a.M);
+    gather_and_ifft(a, a.Zp, no, sm, sm + a.M + SC_PAD);
     ola_store(sm, a.hop, a.logM, a.scale, a.out + (size_t)no * a.hop, a.tail + (size_t)no * a.hop);
     advance_block_counter(a.counters, gridDim.x);
 }
@@ -354,7 +354,7 @@ __global__ void ifft_batch_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x, b = blockIdx.y;
-    gather_and_ifft(a, a.Zp + (size_t)b * a.zpStride, no, sm, sm + a.M);
+    gather_and_ifft(a, a.Zp + (size_t)b * a.zpStride, no, sm, sm + a.M + SC_PAD);
     float* z = a.zt + ((size_t)b * a.nOutLocal + no) * 2 * a.hop;
     for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
 }
@@ -418,16 +418,16 @@ __device__ __forceinline__ void cmac_packed(float2& acc, float2 h, float2 x, boo
 __global__ void multi_fused_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* A = sm;
-    float2* B = sm + a.M;
-    float2* stw = sm + 2 * a.M;
+    float2* A = sm;                       /* FFT work array (padded) */
+    float2* B = sm + a.M + SC_PAD;        /* spectrum of the new block, natural order */
+    float2* stw = B + a.M;
     const int c = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
     float2* Xc = a.X + (size_t)c * a.P * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
     load_twiddles(stw, a.tw, a.M);
-    load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M);
+    load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(A, a.M, a.logM, stw);
     float2* Xnew = Xc + (size_t)head * a.M;
@@ -456,10 +456,10 @@ __global__ void multi_fused_kernel(MultiArgs a)
             slot = (slot == 0) ? a.P - 1 : slot - 1;
             cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
         }
-        A[k] = acc;
+        A[padi(k, a.logM)] = acc;
     }
     __syncthreads();
-    inv_split_all(A, a.M, stw);
+    inv_split_all(A, a.M, a.logM, stw);
     cfft_dif<true>(A, a.M, a.logM, stw);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
@@ -486,11 +486,12 @@ struct TvArgs {
 __global__ void tv_fused_kernel(TvArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* Xs = sm;                 /* packed spectrum of the new block */
-    float2* Z0 = sm + a.M;
-    float2* Z1 = sm + 2 * a.M;
-    float2* Z2 = sm + 3 * a.M;
-    float2* stw = sm + 4 * a.M;
+    const int MP = a.M + SC_PAD;     /* padded FFT work arrays Z0, Z1, Z2 stored back to back */
+    float2* Z0 = sm;
+    float2* Z1 = sm + MP;
+    float2* Z2 = sm + 2 * MP;
+    float2* Xs = sm + 3 * MP;        /* packed spectrum of the new block, natural order */
+    float2* stw = Xs + a.M;
     load_twiddles(stw, a.tw, a.M);
     const int no = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
@@ -498,7 +499,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     const bool need2 = (a.ir1 != a.ir2);
 
     /* every CTA transforms the (single) input block; CTA 0 also stores it in the ring */
-    load_real_block(Z0, a.in, a.hop, a.M);
+    load_real_block(Z0, a.in, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(Z0, a.M, a.logM, stw);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
@@ -535,7 +536,8 @@ __global__ void tv_fused_kernel(TvArgs a)
         }
         if (!need1) z1 = z0;                  /* .c:587 */
         if (!need2) z2 = z1;                  /* .c:601 */
-        Z0[k] = z0; Z1[k] = z1; Z2[k] = z2;
+        const int ik = padi(k, a.logM);
+        Z0[ik] = z0; Z1[ik] = z1; Z2[ik] = z2;
     }
     __syncthreads();
     inv_split_batch(Z0, a.M, a.logM, stw, 3);           /* Z0, Z1, Z2 are contiguous */
@@ -618,7 +620,7 @@ const char* scdev_error_string(int err) { return cudaGetErrorString((cudaError_t
 /*  C-ABI: kernel launchers                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
-static size_t fft_smem(const scdev_plan* pl, int nbuf) { return (size_t)nbuf * pl->M * sizeof(float2); }
+static size_t fft_smem(const scdev_plan* pl, int nbuf) { return (size_t)nbuf * (pl->M + SC_PAD) * sizeof(float2); }
 
 typedef void (*mac_fn_t)(MacArgs);
 static mac_fn_t mac_fn(int R)

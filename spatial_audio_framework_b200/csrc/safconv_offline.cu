@@ -113,18 +113,19 @@ struct OffFftArgs {
 __global__ void offline_fft_kernel(OffFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + (size_t)(2 * OFF_FPC) * a.M;
+    const int MP = a.M + SC_PAD;                       /* padded FFT work arrays */
+    float2* stw = sm + (size_t)(2 * OFF_FPC) * MP;
     const int kg = blockIdx.x;
     const int row0 = blockIdx.y * OFF_FPC;
     load_twiddles(stw, a.tw, a.M);
     for (int q = 0; q < 2 * OFF_FPC; ++q) {            /* q = 2*f + j : frame f, input 2kg+j */
         const int ni = 2 * kg + (q & 1);
         const int t = row0 + (q >> 1) - (a.P - 1);
-        float2* s = sm + (size_t)q * a.M;
+        float2* s = sm + (size_t)q * MP;
         if (ni < a.nIn && t >= 0 && t < a.T) {
-            load_real_block(s, a.in + (size_t)ni * a.inStride + (size_t)t * a.hop, a.hop, a.M);
+            load_real_block(s, a.in + (size_t)ni * a.inStride + (size_t)t * a.hop, a.hop, a.M, a.logM);
         } else {
-            for (int n = threadIdx.x; n < a.M; n += blockDim.x) s[n] = make_float2(0.f, 0.f);
+            for (int n = threadIdx.x; n < MP; n += blockDim.x) s[n] = make_float2(0.f, 0.f);
         }
     }
     __syncthreads();
@@ -133,8 +134,8 @@ __global__ void offline_fft_kernel(OffFftArgs a)
     const int half = a.M >> 1;
     for (int idx = threadIdx.x; idx < (half + 1) * OFF_FPC; idx += blockDim.x) {
         const int f = idx % OFF_FPC, k = idx / OFF_FPC;
-        const float2* s0 = sm + (size_t)(2 * f) * a.M;
-        const float2* s1 = s0 + a.M;
+        const float2* s0 = sm + (size_t)(2 * f) * MP;
+        const float2* s1 = s0 + MP;
         float2 x0, x0m, x1, x1m;
         int k2 = a.M - k;
         if (k == 0) {
@@ -420,13 +421,14 @@ struct OffIfftArgs {
 __global__ void offline_ifft_kernel(OffIfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + (size_t)OFF_OPC * a.M;
+    const int MP = a.M + SC_PAD;
+    float2* stw = sm + (size_t)OFF_OPC * MP;
     const int og = blockIdx.x, t = blockIdx.y;
     load_twiddles(stw, a.tw, a.M);
     for (int idx = threadIdx.x; idx < a.M * OFF_OPC; idx += blockDim.x) {
         const int j = idx & (OFF_OPC - 1), k = idx / OFF_OPC;
         const int no = og * OFF_OPC + j;
-        sm[(size_t)j * a.M + k] = (no < a.nOut) ? a.Ys[((size_t)k * a.Tpad + t) * a.Nn2 + no] : make_float2(0.f, 0.f);
+        sm[(size_t)j * MP + padi(k, a.logM)] = (no < a.nOut) ? a.Ys[((size_t)k * a.Tpad + t) * a.Nn2 + no] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     {
@@ -438,7 +440,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
         const int no = og * OFF_OPC + j;
         if (no >= a.nOut) break;
         float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
-        const float2* s = sm + (size_t)j * a.M;
+        const float2* s = sm + (size_t)j * MP;
         for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(s, i, a.logM) * a.scale;
     }
 }
@@ -511,7 +513,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         offline_pack_filters_kernel<<<148 * 8, 256, 0, st>>>(a);
         SC_CHECK(cudaGetLastError());
         SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        const int fftSmem = (2 * OFF_FPC + 1) * pl->M * 8, ifftSmem = (OFF_OPC + 1) * pl->M * 8;
+        const int fftSmem = (2 * OFF_FPC + 1) * (pl->M + SC_PAD) * 8, ifftSmem = (OFF_OPC + 1) * (pl->M + SC_PAD) * 8;
         if (fftSmem > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
         SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem));
         SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ifftSmem));
@@ -554,7 +556,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
     {
         dim3 grid((pl->nIn + 1) / 2, rowsUsed / OFF_FPC);
-        offline_fft_kernel<<<grid, 256, (size_t)(2 * OFF_FPC + 1) * pl->M * 8, st>>>(f);
+        offline_fft_kernel<<<grid, 256, (size_t)(2 * OFF_FPC + 1) * (pl->M + SC_PAD) * 8, st>>>(f);
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[1], st));
@@ -574,7 +576,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     i.Tpad = o->capTpad; i.T = T; i.scale = 1.0f / (float)pl->N;
     {
         dim3 grid((pl->nOutLocal + OFF_OPC - 1) / OFF_OPC, T);
-        offline_ifft_kernel<<<grid, 256, (size_t)(OFF_OPC + 1) * pl->M * 8, st>>>(i);
+        offline_ifft_kernel<<<grid, 256, (size_t)(OFF_OPC + 1) * (pl->M + SC_PAD) * 8, st>>>(i);
         SC_CHECK(cudaGetLastError());
         offline_ola_kernel<<<148 * 8, 256, 0, st>>>(i);
         SC_CHECK(cudaGetLastError());
