@@ -33,14 +33,15 @@ __device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((un
  * bit-reversed order; the epilogues read s[bitrev(k)] for consecutive k, which without padding puts all 32
  * lanes on one bank (stride M/32 elements).  With the padding those reads are conflict-free, and the
  * unit-stride accesses of the FFT passes stay (almost) unit-stride. */
-#define SC_PAD 16
+#define SC_PAD 18      /* 16 padding slots + 2: array stride = 2 (mod 16) elements, so 8 arrays x 2 bins hit 16 distinct banks */
 __device__ __forceinline__ int padi(int i, int logM) { return i + (i >> (logM - 4)); }
 
 /* ------------------------------------------------------------------------------------------ */
 /*  M-point complex FFT in shared memory, decimation in frequency                              */
 /*  input: natural order (padded indexing) ; output: element padi(bitrev(k)) holds bin k          */
-/*  tw[j] = exp(-2*pi*i*j/N), N = 2M, j < M   (so W_L^j = tw[j * (2M/L)]); the kernels copy the    */
-/*  table into shared memory first (load_twiddles) so that no pass waits on an L2 round trip.    */
+/*  tw = the per-pass twiddle tables that load_twiddles() builds in shared memory from the global   */
+/*  table gtw[j] = exp(-2*pi*i*j/N), N = 2M, j < M  (W_L^j = gtw[j * (2M/L)]): every pass reads its     */
+/*  twiddles with unit stride (no bank conflicts, no L2 round trip).                                 */
 /*  INV conjugates every twiddle (unnormalised inverse transform).                              */
 /*  Requires M >= 32, blockDim.x a multiple of 32; ends with __syncthreads().                   */
 /* ------------------------------------------------------------------------------------------ */
@@ -60,11 +61,11 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
     const int tid = threadIdx.x, T = blockDim.x;
     int L = M;                 /* current sub-transform length */
     int nsm = logM - 5;        /* radix-2 stages done through shared memory (spans M/2 .. 32) */
+    int off = 0;               /* start of this pass's twiddle table inside tw (see load_twiddles) */
 
     /* two radix-2 stages fused per pass */
     while (nsm >= 2) {
         const int q = L >> 2;
-        const int tstr = (2 * M) / L;
         const int per = M >> 2;                    /* butterflies per transform */
         for (int it = tid; it < nArr * per; it += T) {
             const int arr = it >> (logM - 2), i = it & (per - 1);
@@ -73,8 +74,8 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
             const int base = ((i - j) << 2) + j;
             const int i0 = padi(base, logM), i1 = padi(base + q, logM), i2 = padi(base + 2 * q, logM), i3 = padi(base + 3 * q, logM);
             const float2 a0 = sa[i0], a1 = sa[i1], a2 = sa[i2], a3 = sa[i3];
-            const float2 w1 = twd<INV>(tw, j * tstr);
-            const float2 w2 = twd<INV>(tw, 2 * j * tstr);
+            const float2 w1 = twd<INV>(tw, off + j);         /* W_L^j  */
+            const float2 w2 = twd<INV>(tw, off + q + j);     /* W_L^2j */
             const float2 u0 = caddf(a0, a2);
             const float2 u1 = caddf(a1, a3);
             const float2 v0 = cmulf(csubf(a0, a2), w1);
@@ -88,12 +89,12 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
             sa[i3] = cmulf(csubf(v0, v1), w2);
         }
         __syncthreads();
+        off += 2 * q;
         L >>= 2;
         nsm -= 2;
     }
     if (nsm == 1) {
         const int half = L >> 1;
-        const int tstr = (2 * M) / L;
         const int per = M >> 1;
         for (int it = tid; it < nArr * per; it += T) {
             const int arr = it >> (logM - 1), i = it & (per - 1);
@@ -102,21 +103,23 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
             const int base = ((i - j) << 1) + j;
             const int i0 = padi(base, logM), i1 = padi(base + half, logM);
             const float2 a = sa[i0], b = sa[i1];
-            const float2 w = twd<INV>(tw, j * tstr);
+            const float2 w = twd<INV>(tw, off + j);
             sa[i0] = caddf(a, b);
             sa[i1] = cmulf(csubf(a, b), w);
         }
         __syncthreads();
+        off += half;
         L >>= 1;
     }
     /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp; rows of 32 points of all
      * transforms are contiguous, so the batch is just more rows */
     {
         const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-        float2 w16 = twd<INV>(tw, (lane & 15) * (M >> 4));
-        float2 w8  = twd<INV>(tw, (lane & 7)  * (M >> 3));
-        float2 w4  = twd<INV>(tw, (lane & 3)  * (M >> 2));
-        float2 w2  = twd<INV>(tw, (lane & 1)  * (M >> 1));
+        /* tw + off : the 16-entry table W_32^j, j < 16 */
+        float2 w16 = twd<INV>(tw, off + (lane & 15));
+        float2 w8  = twd<INV>(tw, off + 2 * (lane & 7));
+        float2 w4  = twd<INV>(tw, off + 4 * (lane & 3));
+        float2 w2  = twd<INV>(tw, off + 8 * (lane & 1));
         for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
             const int arr = row >> (logM - 5), rr = row & ((M >> 5) - 1);
             float2* sp = s + (size_t)arr * (M + SC_PAD) + padi(rr * 32 + lane, logM);
@@ -152,10 +155,27 @@ __device__ __forceinline__ void cfft_dif(float2* s, const int M, const int logM,
     cfft_dif_batch<INV>(s, M, logM, tw, 1);
 }
 
-/* copy the twiddle table into shared memory (coalesced; overlaps the input load that follows) */
-__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M)
+/* Build the per-pass twiddle tables of cfft_dif_batch in shared memory (at most M float2), same pass
+ * structure: for every radix-4 pass of sub-length L: W_L^j (j < L/4) then W_L^2j; for the radix-2 pass W_L^j
+ * (j < L/2); finally W_32^j (j < 16) for the warp-shuffle stages.  Strided reads of the global table hit L2. */
+__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M, int logM)
 {
-    for (int n = threadIdx.x; n < M; n += blockDim.x) stw[n] = __ldg(gtw + n);
+    const int tid = threadIdx.x, T = blockDim.x;
+    int L = M, nsm = logM - 5, off = 0;
+    while (nsm >= 2) {
+        const int q = L >> 2, tstr = (2 * M) / L;
+        for (int j = tid; j < q; j += T) {
+            stw[off + j]     = __ldg(gtw + j * tstr);
+            stw[off + q + j] = __ldg(gtw + 2 * j * tstr);
+        }
+        off += 2 * q; L >>= 2; nsm -= 2;
+    }
+    if (nsm == 1) {
+        const int half = L >> 1, tstr = (2 * M) / L;
+        for (int j = tid; j < half; j += T) stw[off + j] = __ldg(gtw + j * tstr);
+        off += half;
+    }
+    if (tid < 16) stw[off + tid] = __ldg(gtw + tid * (M >> 4));
 }
 
 /* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
@@ -186,7 +206,7 @@ __device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, in
     const float2 b = s[padi(bitrev(M - k, logM), logM)];
     const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-    const float2 t = cmulf(tw[k], O);
+    const float2 t = cmulf(__ldg(tw + k), O);        /* tw: GLOBAL table W_N^k */
     Xk  = make_float2(E.x + t.x, E.y + t.y);
     Xmk = make_float2(E.x - t.x, t.y - E.y);
 }
@@ -199,7 +219,7 @@ __device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, int logM
     const float2 A = Z[ik], B = Z[im];
     const float2 E = make_float2(A.x + B.x, A.y - B.y);
     const float2 D = make_float2(A.x - B.x, A.y + B.y);
-    const float2 O = cmul_conjb(D, tw[k]);
+    const float2 O = cmul_conjb(D, __ldg(tw + k));   /* tw: GLOBAL table W_N^k */
     Z[ik] = make_float2(E.x - O.y, E.y + O.x);
     Z[im] = make_float2(E.x + O.y, O.x - E.y);
 }

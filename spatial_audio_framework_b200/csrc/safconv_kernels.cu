@@ -46,7 +46,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     float2* stw = sm + a.M + SC_PAD;
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
     const float* src;
     if (a.kind == SC_KIND_MATRIX) src = a.h + ((size_t)no * a.nIn + ni) * a.len;
@@ -72,7 +72,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
             k2 = 0;
             Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, stw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
         }
         if (a.kind == SC_KIND_MATRIX) {
             const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
@@ -108,7 +108,7 @@ __global__ void input_fft_kernel(InFftArgs a)
     float2* stw = sm + a.M + SC_PAD;
     const int ni = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(sm, a.M, a.logM, stw);
@@ -120,7 +120,7 @@ __global__ void input_fft_kernel(InFftArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, stw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
         }
         a.X[(((size_t)(k >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
         a.X[(((size_t)(k2 >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
@@ -318,7 +318,7 @@ struct IfftArgs {
 __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2* Zp, int no, float2* sm, float2* stw)
 {
     const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
         const int g = ot * a.nKT + (k >> 5);
         const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
@@ -335,7 +335,7 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
         sm[padi(k, a.logM)] = z;
     }
     __syncthreads();
-    inv_split_all(sm, a.M, a.logM, stw);
+    inv_split_all(sm, a.M, a.logM, a.tw);
     cfft_dif<true>(sm, a.M, a.logM, stw);
 }
 
@@ -426,7 +426,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
     float2* Xc = a.X + (size_t)c * a.P * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(A, a.M, a.logM, stw);
@@ -439,7 +439,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(A, k, a.M, a.logM, stw, Xk, Xmk);
+            fwd_split_pair(A, k, a.M, a.logM, a.tw, Xk, Xmk);
         }
         B[k] = Xk;  B[k2] = Xmk;
         Xnew[k] = Xk;  Xnew[k2] = Xmk;
@@ -459,7 +459,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
         A[padi(k, a.logM)] = acc;
     }
     __syncthreads();
-    inv_split_all(A, a.M, a.logM, stw);
+    inv_split_all(A, a.M, a.logM, a.tw);
     cfft_dif<true>(A, a.M, a.logM, stw);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
@@ -492,7 +492,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     float2* Z2 = sm + 2 * MP;
     float2* Xs = sm + 3 * MP;        /* packed spectrum of the new block, natural order */
     float2* stw = Xs + a.M;
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     const int no = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
     const bool need1 = (a.ir0 != a.ir1);
@@ -510,7 +510,7 @@ __global__ void tv_fused_kernel(TvArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(Z0, k, a.M, a.logM, stw, Xk, Xmk);
+            fwd_split_pair(Z0, k, a.M, a.logM, a.tw, Xk, Xmk);
         }
         Xs[k] = Xk;  Xs[k2] = Xmk;
         if (no == 0) {
@@ -540,7 +540,7 @@ __global__ void tv_fused_kernel(TvArgs a)
         Z0[ik] = z0; Z1[ik] = z1; Z2[ik] = z2;
     }
     __syncthreads();
-    inv_split_batch(Z0, a.M, a.logM, stw, 3);           /* Z0, Z1, Z2 are contiguous */
+    inv_split_batch(Z0, a.M, a.logM, a.tw, 3);           /* Z0, Z1, Z2 are contiguous */
     cfft_dif_batch<true>(Z0, a.M, a.logM, stw, 3);
     /* cross-fade (reference .c:494-497, 605-615) */
     float* t0 = a.tail0 + (size_t)no * a.hop;

@@ -117,7 +117,7 @@ __global__ void offline_fft_kernel(OffFftArgs a)
     float2* stw = sm + (size_t)(2 * OFF_FPC) * MP;
     const int kg = blockIdx.x;
     const int row0 = blockIdx.y * OFF_FPC;
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     for (int q = 0; q < 2 * OFF_FPC; ++q) {            /* q = 2*f + j : frame f, input 2kg+j */
         const int ni = 2 * kg + (q & 1);
         const int t = row0 + (q >> 1) - (a.P - 1);
@@ -144,8 +144,8 @@ __global__ void offline_fft_kernel(OffFftArgs a)
             x1 = make_float2(z1.x + z1.y, z1.x - z1.y);  x1m = x1;
             k2 = 0;
         } else {
-            fwd_split_pair(s0, k, a.M, a.logM, stw, x0, x0m);
-            fwd_split_pair(s1, k, a.M, a.logM, stw, x1, x1m);
+            fwd_split_pair(s0, k, a.M, a.logM, a.tw, x0, x0m);
+            fwd_split_pair(s1, k, a.M, a.logM, a.tw, x1, x1m);
         }
         const size_t row = (size_t)row0 + f;
         {
@@ -424,7 +424,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     const int MP = a.M + SC_PAD;
     float2* stw = sm + (size_t)OFF_OPC * MP;
     const int og = blockIdx.x, t = blockIdx.y;
-    load_twiddles(stw, a.tw, a.M);
+    load_twiddles(stw, a.tw, a.M, a.logM);
     for (int idx = threadIdx.x; idx < a.M * OFF_OPC; idx += blockDim.x) {
         const int j = idx & (OFF_OPC - 1), k = idx / OFF_OPC;
         const int no = og * OFF_OPC + j;
@@ -433,7 +433,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     __syncthreads();
     {
         const int nArr = min(OFF_OPC, a.nOut - og * OFF_OPC);
-        inv_split_batch(sm, a.M, a.logM, stw, nArr);
+        inv_split_batch(sm, a.M, a.logM, a.tw, nArr);
         cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
     }
     for (int j = 0; j < OFF_OPC; ++j) {
