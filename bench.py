@@ -232,38 +232,35 @@ def run_offline_arm(args, w):
     dev = torch.device("cuda", local)
     hop, nIn, nOut = w["hop"], w["nIn"], w["nOut"]
     T = int(np.ceil(w["seconds"] * 48000.0 / hop))
-    ob, oc = sharding.shard_range(nOut, world, rank)
-    H = filters_for(w, ob, oc)
-    conv = saf.MatrixConv(hop, H, 1, device=local) if world == 1 else saf.MatrixConv.from_shard(hop, H, nOut, ob, device=local)
+    P = int(np.ceil(np.float32(w["L"]) / np.float32(hop)))
+    # offline rendering shards the signal in TIME (each rank: all output channels of its own stretch of audio,
+    # plus a P-frame input halo); nothing is exchanged between GPUs
+    t0, t1, halo = sharding.time_segment(T, world, rank, P)
+    Tr = t1 - t0
+    H = filters_for(w, 0, nOut)
+    conv = saf.MatrixConv(hop, H, 1, device=local)
     del H
     info = conv.info()
     stream = torch.cuda.Stream(device=dev)
     conv.set_stream(stream.cuda_stream)
     g = torch.Generator(device="cpu").manual_seed(1234)
-    x_host = (torch.rand((nIn, T * hop), generator=g) * 2 - 1).pin_memory()
-    y_host = torch.empty((nOut, T * hop), dtype=torch.float32).pin_memory()
-    x_dev = torch.empty((nIn, T * hop), dtype=torch.float32, device=dev)
-    y_dev = torch.empty((oc, T * hop), dtype=torch.float32, device=dev)
-    y_all = torch.empty((world, oc, T * hop), dtype=torch.float32, device=dev) if world > 1 else None
-    if rank == 0:
-        x_dev.copy_(x_host)
+    x_full = torch.rand((nIn, T * hop), generator=g) * 2 - 1                      # same signal on every rank
+    x_host = x_full[:, (t0 - halo) * hop:t1 * hop].contiguous().pin_memory()      # this rank's stretch + halo
+    del x_full
+    y_host = torch.empty((nOut, Tr * hop), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty((nIn, (Tr + halo) * hop), dtype=torch.float32, device=dev)
+    y_dev = torch.empty((nOut, Tr * hop), dtype=torch.float32, device=dev)
+    x_dev.copy_(x_host)
 
     def step_device():
-        with torch.cuda.stream(stream):
-            if dist:
-                dist.broadcast(x_dev, src=0)
-            conv.render_offline_device(x_dev.data_ptr(), y_dev.data_ptr(), T)
-            if dist:
-                dist.all_gather_into_tensor(y_all, y_dev)
+        conv.render_offline_segment_device(x_dev.data_ptr(), y_dev.data_ptr(), Tr, halo)
 
     def step_host():
         with torch.cuda.stream(stream):
-            if rank == 0:
-                x_dev.copy_(x_host, non_blocking=True)
+            x_dev.copy_(x_host, non_blocking=True)
         step_device()
         with torch.cuda.stream(stream):
-            if rank == 0:
-                y_host.copy_(y_all.view(nOut, T * hop) if dist else y_dev, non_blocking=True)
+            y_host.copy_(y_dev, non_blocking=True)
         stream.synchronize()
 
     for _ in range(args.warmup):
@@ -302,18 +299,19 @@ def run_offline_arm(args, w):
     step_host()
     if dist:
         dist.barrier()
-    t0 = time.perf_counter()
+    t0w = time.perf_counter()
     for _ in range(e2e_steps):
         step_host()
     if dist:
         dist.barrier()
-    dt = time.perf_counter() - t0
+    dt = time.perf_counter() - t0w
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = {"value": float(nOut) * T * hop * e2e_steps / float(t.item()), "unit": UNIT,
-           "h2d_bytes_per_step": int(nIn * T * hop * 4), "d2h_bytes_per_step": int(nOut * T * hop * 4), "steps": e2e_steps,
-           "api": "pinned H2D of the whole signal -> safconv_render_offline_device -> D2H" + (" (+ NCCL broadcast / all-gather)" if dist else "")}
+           "h2d_bytes_per_step": int(nIn * (T + P * (world - 1)) * hop * 4), "d2h_bytes_per_step": int(nOut * T * hop * 4),
+           "steps": e2e_steps,
+           "api": "per rank: pinned H2D of its stretch of the signal (+halo) -> safconv_render_offline_segment_device -> D2H"}
 
     peaks = {}
     try:
@@ -321,8 +319,7 @@ def run_offline_arm(args, w):
     except Exception:
         pass
     bf16 = float(peaks.get("bf16_tflops", 1590.0))
-    P = int(info.numFilterBlocks)
-    alg_flops = 8.0 * oc * P * nIn * (hop + 1) * T                 # complex MACs as real flops, this rank
+    alg_flops = 8.0 * nOut * P * nIn * (hop + 1) * (Tr + halo)     # complex MACs as real flops, this rank's launch
     gemm_ms = float(kms[1])
     achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "offline_gemm_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32 accuracy)",
@@ -345,8 +342,10 @@ def run_offline_arm(args, w):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (tf32x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"], "frames": T,
-                   "partitions": P, "sharding": f"output channels over {world} GPU(s), {oc} per GPU" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2: %.1f GB of operands per render" % ((nIn * T * hop * 4 * 3 + info.bytesFilters * 2) / 1e9)},
+                   "partitions": P,
+                   "sharding": (f"time: {world} GPUs x ~{Tr} frames (+{P}-frame input halo), no exchange between GPUs"
+                                if world > 1 else "single GPU"),
+                   "l2": "inputs larger than L2: %.1f GB of operands per render" % ((nIn * (Tr + halo) * hop * 4 * 3 + info.bytesFilters * 2) / 1e9)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "realtime_factor_48k": (T * hop * args.steps / (ms_total * 1e-3)) / 48000.0,
     }

@@ -157,6 +157,14 @@ int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nB
  */
 int safconv_render_offline(void* h, const float* in, float* out, int nFrames);
 int safconv_render_offline_device(void* h, const float* d_in, float* d_out, int nFrames);
+/**
+ * One TIME SEGMENT of an offline render (multi-GPU: each GPU renders its own stretch of the signal, no
+ * exchange between GPUs).  d_in holds nHaloFrames + nFrames frames per channel: the halo is the audio that
+ * precedes the segment (numFilterBlocks frames are enough: the block convolution of frame t reads frames
+ * t-P+1..t and the overlap tail of frame t-1; silence for the start of the signal).  Only the nFrames frames
+ * of the segment are written: d_out [nOutLocal][nFrames*hopSize].
+ */
+int safconv_render_offline_segment_device(void* h, const float* d_in, float* d_out, int nFrames, int nHaloFrames);
 /** Milliseconds of the last offline render: ms[0] forward FFTs, ms[1] tensor-core GEMM, ms[2] inverse FFTs + overlap-add. */
 int safconv_get_offline_times(void* h, float ms[3]);
 

@@ -41,7 +41,8 @@ EXPORTED_SYMBOLS = [
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
     "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_get_kernel_totals",
     "safconv_set_option",
-    "safconv_render_offline", "safconv_render_offline_device", "safconv_get_offline_times",
+    "safconv_render_offline", "safconv_render_offline_device", "safconv_render_offline_segment_device",
+    "safconv_get_offline_times",
 ]
 
 
@@ -107,6 +108,7 @@ def lib():
     L.safconv_debug_plan_size.restype = C.c_int
     L.safconv_render_offline.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
     L.safconv_render_offline_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.safconv_render_offline_segment_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.safconv_get_offline_times.argtypes = [C.c_void_p, _f32p]
     _lib = L
     return L
@@ -264,6 +266,11 @@ class MatrixConv(_Base):
 
     def render_offline_device(self, d_in_ptr: int, d_out_ptr: int, n_frames: int):
         if self._lib.safconv_render_offline_device(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr), n_frames):
+            self._raise_if_error()
+
+    def render_offline_segment_device(self, d_in_ptr: int, d_out_ptr: int, n_frames: int, n_halo: int):
+        if self._lib.safconv_render_offline_segment_device(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr),
+                                                           n_frames, n_halo):
             self._raise_if_error()
 
     def offline_times_ms(self):

@@ -125,11 +125,12 @@ int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, voi
 /* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */
 int  scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream);
 /* offline path: allocate / grow the workspace for T frames (and build the filter operand on first use),
- * render d_in [nIn][T*hop] -> d_out [nOutLocal][T*hop] from a zero state, free.  `events` (4 CUDA events or
+ * render d_in [nIn][T*hop] -> d_out [nOutLocal][(T-skip)*hop] from a zero state (the first `skip` frames are
+ * history only), free.  `events` (4 CUDA events or
  * NULL) are recorded before the forward FFTs, before the GEMM, after the GEMM, and at the end. */
 int  scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o, int T, void* stream);
 int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
-                       const float* d_in, float* d_out, int T, void** events, void* stream);
+                       const float* d_in, float* d_out, int T, int skip, void** events, void* stream);
 int  scdev_offline_free(scdev_offline* o);
 /* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */
 int  scdev_is_pinned_host(const void* p);

@@ -633,16 +633,22 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
 }
 
 /* ---- offline rendering: all frames at once, tensor-core per-bin contraction (safconv_offline.cu) ---- */
-int safconv_render_offline_device(void* hp, const float* d_in, float* d_out, int nFrames)
+int safconv_render_offline_segment_device(void* hp, const float* d_in, float* d_out, int nFrames, int nHaloFrames)
 {
     safconv_handle* h = as_handle(hp);
-    if (!h || !d_in || !d_out || nFrames < 1 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
+    if (!h || !d_in || !d_out || nFrames < 1 || nHaloFrames < 0 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
+    const int T = nFrames + nHaloFrames;
     int e = scdev_set_device(h->device);
     if (!e && !h->offEv[0]) for (int i = 0; i < 4 && !e; i++) e = scdev_event_create(&h->offEv[i]);
-    if (!e) e = scdev_offline_prepare(&h->pl, &h->b, &h->off, nFrames, h->stream);
-    if (!e) e = scdev_offline_run(&h->pl, &h->b, &h->off, d_in, d_out, nFrames, h->offEv, h->stream);
+    if (!e) e = scdev_offline_prepare(&h->pl, &h->b, &h->off, T, h->stream);
+    if (!e) e = scdev_offline_run(&h->pl, &h->b, &h->off, d_in, d_out, T, nHaloFrames, h->offEv, h->stream);
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline", e);
     return SAFCONV_OK;
+}
+
+int safconv_render_offline_device(void* hp, const float* d_in, float* d_out, int nFrames)
+{
+    return safconv_render_offline_segment_device(hp, d_in, d_out, nFrames, 0);
 }
 
 int safconv_render_offline(void* hp, const float* in, float* out, int nFrames)

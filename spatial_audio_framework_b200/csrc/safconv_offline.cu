@@ -415,6 +415,7 @@ struct OffIfftArgs {
     float* out;            /* [nOut][T*hop] */
     const float2* tw;
     int hop, M, logM, nOut, Nn2, Tpad, T;
+    int skip;              /* leading halo frames that are transformed but not written to `out` */
     float scale;
 };
 
@@ -445,20 +446,22 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     }
 }
 
-/* out[no][t*hop + i] = z_t[i] + z_{t-1}[hop + i]  (zero state before the first frame) */
+/* out[no][(t-skip)*hop + i] = z_t[i] + z_{t-1}[hop + i]  for frames t >= skip (zero state before frame 0) */
 __global__ void offline_ola_kernel(OffIfftArgs a)
 {
-    const size_t n = (size_t)a.T * a.nOut * a.hop;
+    const int To = a.T - a.skip;                           /* frames written */
+    const size_t n = (size_t)To * a.nOut * a.hop;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const int i = (int)(e % a.hop);
         size_t r = e / a.hop;
-        const int t = (int)(r % a.T);
-        const int no = (int)(r / a.T);
+        const int to = (int)(r % To);
+        const int no = (int)(r / To);
+        const int t = to + a.skip;
         const float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
         float v = z[i];
         if (t > 0) v += a.zt[((size_t)(t - 1) * a.nOut + no) * 2 * a.hop + a.hop + i];
-        a.out[(size_t)no * a.T * a.hop + (size_t)t * a.hop + i] = v;
+        a.out[(size_t)no * To * a.hop + (size_t)to * a.hop + i] = v;
     }
 }
 
@@ -538,12 +541,13 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
     return 0;
 }
 
-/* d_in [nIn][T*hop] -> d_out [nOutLocal][T*hop]; zero state before the first frame */
+/* d_in [nIn][T*hop] -> d_out [nOutLocal][(T-skip)*hop]; zero state before the first frame; the first `skip`
+ * frames are a halo (history for the frames that follow) whose output is not written */
 int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
-                      const float* d_in, float* d_out, int T, void** events, void* stream)
+                      const float* d_in, float* d_out, int T, int skip, void** events, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (T < 1 || T > o->capFrames) return (int)cudaErrorInvalidValue;
+    if (T < 1 || T > o->capFrames || skip < 0 || skip >= T) return (int)cudaErrorInvalidValue;
     const int Tpad = (int)roundup((size_t)T, OFF_MT);
     const int rowsAlloc = o->capRows;           /* row stride of the operand as allocated */
     const int rowsUsed = (int)roundup((size_t)Tpad + pl->P - 1, OFF_FPC);
@@ -573,7 +577,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     OffIfftArgs i;
     i.Ys = (const float2*)o->Ys; i.zt = o->zt; i.out = d_out; i.tw = (const float2*)b->tw;
     i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
-    i.Tpad = o->capTpad; i.T = T; i.scale = 1.0f / (float)pl->N;
+    i.Tpad = o->capTpad; i.T = T; i.skip = skip; i.scale = 1.0f / (float)pl->N;
     {
         dim3 grid((pl->nOutLocal + OFF_OPC - 1) / OFF_OPC, T);
         offline_ifft_kernel<<<grid, 256, (size_t)(OFF_OPC + 1) * (pl->M + SC_PAD) * 8, st>>>(i);

@@ -33,6 +33,15 @@ def shard_range(n_out: int, world: int, rank: int):
     return begin, base + (1 if rank < extra else 0)
 
 
+def time_segment(n_frames: int, world: int, rank: int, n_partitions: int):
+    """Offline rendering shards the signal in TIME: rank r renders frames [t0, t1) and needs `halo` frames of
+    input before t0 (the block convolution of frame t reads frames t-P+1..t, and its overlap-add needs the tail of
+    frame t-1, which reads back to t-P): halo = min(P, t0).  No exchange between ranks.
+    Returns (t0, t1, halo)."""
+    t0, cnt = shard_range(n_frames, world, rank)
+    return t0, t0 + cnt, min(int(n_partitions), t0)
+
+
 def gathered_to_channel_major(y_all, n_out: int, world: int):
     """[sum_r (B * count_r * hop)] flat gather buffer -> [B][nOut][hop] tensor (a copy)."""
     import torch

@@ -235,6 +235,31 @@ def test_offline_tensor_core_render_vs_oracle(saf, orc, hop, L, nIn, nOut, T):
     check(ys, y, "streaming vs offline")
 
 
+def test_offline_time_segments_equal_full_render(saf):
+    """Multi-GPU offline sharding is by time: every segment rendered on its own (with a P-frame input halo,
+    sharding.time_segment) reproduces the full render exactly -- no exchange between the GPUs is needed."""
+    import torch
+    from spatial_audio_framework_b200 import sharding
+    rng = np.random.default_rng(17)
+    hop, L, nIn, nOut, T = 128, 1000, 4, 3, 301
+    P = (L + hop - 1) // hop
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * T)).astype(np.float32)
+    mc = saf.MatrixConv(hop, H)
+    full = mc.render_offline(x)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            t0, t1, halo = sharding.time_segment(T, world, r, P)
+            xs = torch.from_numpy(np.ascontiguousarray(x[:, (t0 - halo) * hop:t1 * hop])).cuda()
+            ys = torch.empty((nOut, (t1 - t0) * hop), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            mc.render_offline_segment_device(xs.data_ptr(), ys.data_ptr(), t1 - t0, halo)
+            mc.synchronize()
+            parts.append(ys.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts, 1), full), world
+
+
 def test_offline_render_c5_shape_vs_streaming(saf):
     """configs[4] channel counts (121 in x 64 out, hop 1024, 8192 taps) on a shortened signal: the offline
     tensor-core path against the (oracle-verified) streaming path on the same handle."""
