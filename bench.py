@@ -468,9 +468,19 @@ def run_own_arm(args, w):
     mac_ms = ktot[1] / max(ngroups, 1)
     mac_bytes = float(info.macAlgBytesPerBlock) * blocks_per_launch
     achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (per block; a launch covers blocks_per_launch)
+    traffic, traffic_src = args.traffic, "--traffic" if args.traffic else None
+    if traffic is None and world == 1:
+        try:
+            tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(args.workload)
+            if tj:
+                traffic = float(tj["dram_bytes_per_block"]) * blocks_per_launch
+                traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per block x blocks per launch)"
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": "mac_kernel (K2 filter-streaming complex MAC)" if w["kind"] == "matrix" else "multi_fused_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": args.traffic, "alg_bytes_per_launch": mac_bytes, "avg_launch_ms": mac_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": mac_bytes, "avg_launch_ms": mac_ms,
                 "launches_timed": ngroups, "blocks_per_launch": blocks_per_launch, "rank": 0,
                 "whole_block": {"alg_bytes": float(info.algBytesPerBlock),
                                 "achieved_GBps": float(info.algBytesPerBlock) * B * args.steps / (ms_total * 1e-3) / 1e9},
