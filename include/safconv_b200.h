@@ -212,6 +212,9 @@ int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
  *    "use_graph"    0/1 replay the per-block launch sequence of saf_*_apply from a CUDA graph
  *    "batching"     0/1 (default 1) safconv_apply_device_blocks shares one forward-FFT and one inverse-FFT
  *                   launch across the blocks handed over together (outputs are bit-identical either way)
+ *    "small_fused"  0/1 (default 1) saf_matrixConv_apply of a small problem (few inputs x outputs, filter spectra
+ *                   that stay in L2) runs as ONE fused kernel that reads / writes the page-locked host buffers
+ *                   directly: one launch + one synchronisation per block (real-time latency path)
  *    "detect_pinned" 0/1 (default 1) saf_*_apply copies straight from/to caller buffers that are already
  *                   page-locked instead of going through the handle's own pinned staging buffers
  */

@@ -134,6 +134,9 @@ int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline*
 int  scdev_offline_free(scdev_offline* o);
 /* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */
 int  scdev_is_pinned_host(const void* p);
+/* small matrix problems: K1+K2+K3 in one launch, one CTA per output channel; in/out may be mapped host memory */
+int  scdev_small_fits(const scdev_plan* pl, int maxSmemOptin);
+int  scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream);
 /* multiConv: K1+K2+K3 fused, one CTA per channel */
 int  scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream);
 /* TVConv: 1-input FFT + (1..3) IR MACs + cross-fade, one CTA per output channel */

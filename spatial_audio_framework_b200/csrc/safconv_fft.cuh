@@ -178,6 +178,18 @@ __device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restr
     if (tid < 16) stw[off + tid] = __ldg(gtw + tid * (M >> 4));
 }
 
+/* The real-FFT split passes need W_N^k, k <= M/2 (unit stride).  For M <= 4096 the kernels keep a copy in shared
+ * memory right after the M-entry pass-table region (one L2 round trip less in the middle of the kernel); for
+ * larger M they read the global table. */
+__host__ __device__ __forceinline__ int sc_split_len(int M) { return M <= 4096 ? (M / 2 + 2) : 0; }
+__device__ __forceinline__ const float2* load_split_twiddles(float2* stw, const float2* __restrict__ gtw, int M)
+{
+    if (!sc_split_len(M)) return gtw;
+    float2* spl = stw + M;
+    for (int k = threadIdx.x; k <= (M >> 1); k += blockDim.x) spl[k] = __ldg(gtw + k);
+    return spl;
+}
+
 /* load one real block of `hop` samples (zero-padded to N = 2M) as M complex values z[n] = x[2n] + i x[2n+1] */
 __device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M, int logM)
 {
@@ -206,7 +218,7 @@ __device__ __forceinline__ void fwd_split_pair(const float2* s, int k, int M, in
     const float2 b = s[padi(bitrev(M - k, logM), logM)];
     const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-    const float2 t = cmulf(__ldg(tw + k), O);        /* tw: GLOBAL table W_N^k */
+    const float2 t = cmulf(tw[k], O);                /* tw: split table W_N^k (shared copy or the global table) */
     Xk  = make_float2(E.x + t.x, E.y + t.y);
     Xmk = make_float2(E.x - t.x, t.y - E.y);
 }
@@ -219,7 +231,7 @@ __device__ __forceinline__ void inv_split_pair(float2* Z, int k, int M, int logM
     const float2 A = Z[ik], B = Z[im];
     const float2 E = make_float2(A.x + B.x, A.y - B.y);
     const float2 D = make_float2(A.x - B.x, A.y + B.y);
-    const float2 O = cmul_conjb(D, __ldg(tw + k));   /* tw: GLOBAL table W_N^k */
+    const float2 O = cmul_conjb(D, tw[k]);           /* tw: split table W_N^k (shared copy or the global table) */
     Z[ik] = make_float2(E.x - O.y, E.y + O.x);
     Z[im] = make_float2(E.x + O.y, O.x - E.y);
 }

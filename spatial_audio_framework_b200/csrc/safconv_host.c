@@ -37,6 +37,8 @@ typedef struct safconv_handle {
     size_t     inBytes, outBytes;
     size_t     bytesH, bytesX, bytesZp;
     int        useGraph;
+    int        smallOk;              /* the plan qualifies for the fused small-problem kernel */
+    int        smallFused;           /* 1: saf_matrixConv_apply of a small problem = ONE fused kernel on mapped host buffers */
     int        batching;             /* 1: safconv_apply_device_blocks shares the FFT launches across a batch */
     int        detectPinned;         /* 1: DMA straight from/to caller buffers that are already page-locked */
     void*      graphExec;
@@ -299,6 +301,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     pl->macHints = 1;
     h->detectPinned = 1;
     h->batching = 1;
+    h->smallFused = env_int("SAFCONV_SMALL_FUSED", 1, 0, 1);
 
     const size_t M = (size_t)pl->M, P = (size_t)pl->P;
     /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
@@ -346,6 +349,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         rowsTotal = (size_t)nIRs * nOutLocal;
     }
     DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
+    h->smallOk = (kind == SC_KIND_MATRIX) ? scdev_small_fits(pl, h->maxSmem) : 0;
 
     if (zalloc(h, &h->b.H, h->bytesH, "filter spectra allocation")) goto fail;
     if (zalloc(h, &h->b.X, h->bytesX, "delay line allocation")) goto fail;
@@ -404,6 +408,9 @@ static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, in
     const scdev_plan* pl = &h->pl;
     void** ev = NULL;
     int e = 0;
+    if (pl->kind == SC_KIND_MATRIX && nBlocks == 1 && h->smallFused && h->smallOk && !h->useGraph && !h->timingCap) {
+        return scdev_small_fused(pl, &h->b, d_in, d_out, h->stream);     /* one launch instead of three */
+    }
     if (pl->kind == SC_KIND_MATRIX) {
         if (h->timingCap && h->timingCount < h->timingCap) {
             ev = h->evRing + 4 * (size_t)h->timingCount;
@@ -448,6 +455,14 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
     const float* src = direct ? in : h->h_in;
     float*       dst = direct ? out : h->h_out;
     if (!direct) memcpy(h->h_in, in, h->inBytes);
+    if (h->smallFused && h->smallOk && !h->useGraph && !h->timingCap) {
+        /* latency path: one launch, the kernel reads / writes the page-locked host buffers directly */
+        e = scdev_small_fused(&h->pl, &h->b, src, dst, h->stream);
+        if (!e) e = scdev_stream_sync(h->stream);
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (fused)", e); return; }
+        if (!direct) memcpy(out, h->h_out, h->outBytes);
+        return;
+    }
     if (h->useGraph && h->pl.kind != SC_KIND_TV) {
         if (h->graphExec && (h->graphIn != (void*)src || h->graphOut != (void*)dst)) {
             scdev_graph_destroy(h->graphExec);
@@ -818,6 +833,7 @@ int safconv_set_option(void* hp, const char* name, int value)
     if (!strcmp(name, "mac_hints")) { h->pl.macHints = value ? 1 : 0; }
     else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
     else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
+    else if (!strcmp(name, "small_fused")) { h->smallFused = value ? 1 : 0; }
     else if (!strcmp(name, "detect_pinned")) { h->detectPinned = value ? 1 : 0; }
     else return SAFCONV_ERR_ARG;
     if (h->graphExec) { scdev_set_device(h->device); scdev_stream_sync(h->stream); scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }

@@ -47,6 +47,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
     extern __shared__ __align__(16) float2 sm[];
     float2* stw = sm + a.M + SC_PAD;
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
     const float* src;
     if (a.kind == SC_KIND_MATRIX) src = a.h + ((size_t)no * a.nIn + ni) * a.len;
@@ -72,7 +73,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
             k2 = 0;
             Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
         }
         if (a.kind == SC_KIND_MATRIX) {
             const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
@@ -109,6 +110,7 @@ __global__ void input_fft_kernel(InFftArgs a)
     const int ni = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(sm, a.M, a.logM, stw);
@@ -120,7 +122,7 @@ __global__ void input_fft_kernel(InFftArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
         }
         a.X[(((size_t)(k >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
         a.X[(((size_t)(k2 >> 5) * a.RS + slot) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
@@ -319,6 +321,7 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
 {
     const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
         const int g = ot * a.nKT + (k >> 5);
         const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
@@ -335,7 +338,7 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
         sm[padi(k, a.logM)] = z;
     }
     __syncthreads();
-    inv_split_all(sm, a.M, a.logM, a.tw);
+    inv_split_all(sm, a.M, a.logM, spl);
     cfft_dif<true>(sm, a.M, a.logM, stw);
 }
 
@@ -427,6 +430,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
     cfft_dif<false>(A, a.M, a.logM, stw);
@@ -439,7 +443,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(A, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(A, k, a.M, a.logM, spl, Xk, Xmk);
         }
         B[k] = Xk;  B[k2] = Xmk;
         Xnew[k] = Xk;  Xnew[k2] = Xmk;
@@ -459,10 +463,163 @@ __global__ void multi_fused_kernel(MultiArgs a)
         A[padi(k, a.logM)] = acc;
     }
     __syncthreads();
-    inv_split_all(A, a.M, a.logM, a.tw);
+    inv_split_all(A, a.M, a.logM, spl);
     cfft_dif<true>(A, a.M, a.logM, stw);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/*  small_fused_kernel: K1 + K2 + K3 of the MATRIX convolver in ONE launch for small real-time    */
+/*  problems (C1 / C2 class: a few hundred KB of filter spectra, latency- not bandwidth-bound).   */
+/*  One CTA per output channel: forward FFTs of all nIn inputs (redundant across the few CTAs,     */
+/*  CTA 0 also stores them in the delay-line ring), the sum over partitions x inputs straight out  */
+/*  of L2, one inverse FFT, overlap-add.  `in` / `out` may be page-locked HOST memory (zero-copy): */
+/*  then a whole saf_matrixConv_apply is one kernel launch and one stream synchronisation.        */
+/*  Works on the same H / delay-line layouts as the three-kernel path.                             */
+/*  shared memory: nIn padded FFT arrays | nIn natural-order spectra | twiddles | reduction        */
+/* ------------------------------------------------------------------------------------------ */
+struct SmallArgs {
+    const float* in;       /* [nIn][hop]      (device or mapped host) */
+    float* out;            /* [nOutLocal][hop] (device or mapped host) */
+    const float2* H;       /* [ot][kt][p][ni][OTsz][32] */
+    float2* X;             /* [kt][RS][nIn][32] ring */
+    const float2* tw;
+    float* tail;
+    unsigned int* counters;
+    int hop, M, logM, P, nIn, nKT, OTsz, RS;
+    float scale;
+};
+
+__global__ void small_fused_kernel(SmallArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int MP = a.M + SC_PAD;
+    float2* W   = sm;                                  /* nIn padded FFT work arrays (array 0 is re-used for Z) */
+    float2* Xn  = sm + (size_t)a.nIn * MP;             /* nIn packed spectra of the new block, natural order    */
+    float2* stw = Xn + (size_t)a.nIn * a.M;
+    float2* red = stw + a.M + sc_split_len(a.M);       /* [groups][M] partial sums                              */
+    const int no = blockIdx.x;
+    const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+    const unsigned int count = a.counters[0];          /* issued with the input loads below; graph-replay safe */
+    const int head = (int)(count % (unsigned)a.RS);
+    const int tid = threadIdx.x, T = blockDim.x;
+    /* overlap tails are fetched now, used at the very end (hop <= 4 * blockDim) */
+    float tl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = tid + u * T; tl[u] = (i < a.hop) ? a.tail[(size_t)no * a.hop + i] : 0.f; }
+
+    /* input block: all loads of a thread are issued before the first store (the source may be mapped host
+     * memory: one PCIe round trip for the whole block instead of one per channel) */
+    {
+        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
+        const int total = a.nIn * a.M;
+        for (int base = tid; base < total; base += 4 * T) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * T;
+                v[u] = make_float2(0.f, 0.f);
+                if (idx < total) {
+                    const int ni = idx >> a.logM, n = idx & (a.M - 1);
+                    const float* x = a.in + (size_t)ni * a.hop;
+                    if (vec) { if (2 * n < a.hop) v[u] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                    else {
+                        if (2 * n < a.hop)     v[u].x = __ldg(x + 2 * n);
+                        if (2 * n + 1 < a.hop) v[u].y = __ldg(x + 2 * n + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * T;
+                if (idx < total) W[(size_t)(idx >> a.logM) * MP + padi(idx & (a.M - 1), a.logM)] = v[u];
+            }
+        }
+    }
+    load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    __syncthreads();
+    cfft_dif_batch<false>(W, a.M, a.logM, stw, a.nIn);
+    {
+        const int per = (a.M >> 1) + 1;
+        for (int it = tid; it < a.nIn * per; it += T) {
+            const int ni = it / per, k = it - ni * per;
+            const float2* s = W + (size_t)ni * MP;
+            float2 Xk, Xmk;
+            int k2 = a.M - k;
+            if (k == 0) {
+                const float2 z = s[0];
+                Xk = make_float2(z.x + z.y, z.x - z.y);
+                k2 = 0; Xmk = Xk;
+            } else {
+                fwd_split_pair(s, k, a.M, a.logM, spl, Xk, Xmk);
+            }
+            Xn[(size_t)ni * a.M + k] = Xk;  Xn[(size_t)ni * a.M + k2] = Xmk;
+            if (no == 0) {
+                a.X[(((size_t)(k >> 5) * a.RS + head) * a.nIn + ni) * SC_BK + (k & 31)] = Xk;
+                a.X[(((size_t)(k2 >> 5) * a.RS + head) * a.nIn + ni) * SC_BK + (k2 & 31)] = Xmk;
+            }
+        }
+    }
+    __syncthreads();
+    /* Z[k] = sum_p sum_ni H_p[no][ni][k] * X_{t-p}[ni][k]; the (p, ni) list is split over G = T / M thread groups */
+    {
+        const int G = (T >= a.M) ? T / a.M : 1;
+        const int nTerms = a.P * a.nIn;
+        for (int k0 = 0; k0 < a.M; k0 += T) {                      /* one round unless M > T */
+            const int g = (T >= a.M) ? tid / a.M : 0;
+            const int k = (T >= a.M) ? tid - g * a.M : k0 + tid;
+            if (g < G && k < a.M) {
+                const bool packed = (k == 0);
+                const int kt = k >> 5, b = k & 31;
+                float2 acc = make_float2(0.f, 0.f);
+                const int t0 = (int)(((long long)nTerms * g) / G), t1 = (int)(((long long)nTerms * (g + 1)) / G);
+                int p = t0 / a.nIn, ni = t0 - p * a.nIn;
+                int slot = head - p; if (slot < 0) slot += a.RS;
+                const float2* Hk = a.H + ((size_t)(ot * a.nKT + kt) * a.P * a.nIn * a.OTsz + nl) * SC_BK + b;
+                const float2* Xk = a.X + (size_t)kt * a.RS * a.nIn * SC_BK + b;
+#pragma unroll 8
+                for (int t = t0; t < t1; ++t) {
+                    const float2 h = __ldg(Hk + (size_t)(p * a.nIn + ni) * a.OTsz * SC_BK);
+                    const float2 x = (p == 0) ? Xn[(size_t)ni * a.M + k] : Xk[((size_t)slot * a.nIn + ni) * SC_BK];
+                    cmac_packed(acc, h, x, packed);
+                    if (++ni == a.nIn) { ni = 0; ++p; slot = (slot == 0) ? a.RS - 1 : slot - 1; }
+                }
+                if (G > 1) red[(size_t)g * a.M + k] = acc;
+                else W[padi(k, a.logM)] = acc;
+            }
+        }
+        if (G > 1) {
+            __syncthreads();
+            for (int k = tid; k < a.M; k += T) {
+                float2 z = red[k];
+                for (int g = 1; g < G; ++g) z = caddf(z, red[(size_t)g * a.M + k]);
+                W[padi(k, a.logM)] = z;
+            }
+        }
+    }
+    __syncthreads();
+    inv_split_all(W, a.M, a.logM, spl);
+    cfft_dif<true>(W, a.M, a.logM, stw);
+    {   /* overlap-add (reference .c:230-233) */
+        float* out = a.out + (size_t)no * a.hop;
+        float* tail = a.tail + (size_t)no * a.hop;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + u * T;
+            if (i < a.hop) {
+                out[i]  = time_sample(W, i, a.logM) * a.scale + tl[u];
+                tail[i] = time_sample(W, i + a.hop, a.logM) * a.scale;
+            }
+        }
+    }
+    /* block counter: the last CTA to get here bumps it (every CTA has read it long before; the kernel boundary
+     * publishes the store, so no fences are needed) */
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&a.counters[1], 1u);
+        if (t == gridDim.x - 1) { a.counters[1] = 0; a.counters[0] = count + 1u; }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -493,6 +650,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     float2* Xs = sm + 3 * MP;        /* packed spectrum of the new block, natural order */
     float2* stw = Xs + a.M;
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     const int no = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
     const bool need1 = (a.ir0 != a.ir1);
@@ -510,7 +668,7 @@ __global__ void tv_fused_kernel(TvArgs a)
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(Z0, k, a.M, a.logM, a.tw, Xk, Xmk);
+            fwd_split_pair(Z0, k, a.M, a.logM, spl, Xk, Xmk);
         }
         Xs[k] = Xk;  Xs[k2] = Xmk;
         if (no == 0) {
@@ -540,7 +698,7 @@ __global__ void tv_fused_kernel(TvArgs a)
         Z0[ik] = z0; Z1[ik] = z1; Z2[ik] = z2;
     }
     __syncthreads();
-    inv_split_batch(Z0, a.M, a.logM, a.tw, 3);           /* Z0, Z1, Z2 are contiguous */
+    inv_split_batch(Z0, a.M, a.logM, spl, 3);           /* Z0, Z1, Z2 are contiguous */
     cfft_dif_batch<true>(Z0, a.M, a.logM, stw, 3);
     /* cross-fade (reference .c:494-497, 605-615) */
     float* t0 = a.tail0 + (size_t)no * a.hop;
@@ -620,7 +778,10 @@ const char* scdev_error_string(int err) { return cudaGetErrorString((cudaError_t
 /*  C-ABI: kernel launchers                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
-static size_t fft_smem(const scdev_plan* pl, int nbuf) { return (size_t)nbuf * (pl->M + SC_PAD) * sizeof(float2); }
+static size_t fft_smem(const scdev_plan* pl, int nbuf)
+{
+    return ((size_t)nbuf * (pl->M + SC_PAD) + sc_split_len(pl->M)) * sizeof(float2);
+}
 
 typedef void (*mac_fn_t)(MacArgs);
 static mac_fn_t mac_fn(int R)
@@ -754,6 +915,39 @@ int scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in,
     a.ir0 = irIdx; a.ir1 = irLast; a.ir2 = irLast2;
     a.scale = 1.0f / (float)pl->N;
     tv_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 5), (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+#define SC_SMALL_THREADS 512
+/* bytes of shared memory small_fused_kernel needs for this plan with `threads` threads */
+static size_t small_smem(const scdev_plan* pl, int threads)
+{
+    const int G = threads >= pl->M ? threads / pl->M : 1;
+    return ((size_t)pl->nIn * (pl->M + SC_PAD) + (size_t)pl->nIn * pl->M + pl->M + sc_split_len(pl->M)
+            + (G > 1 ? (size_t)G * pl->M : 0)) * sizeof(float2);
+}
+
+int scdev_small_fits(const scdev_plan* pl, int maxSmemOptin)
+{
+    if (pl->kind != SC_KIND_MATRIX) return 0;
+    if (small_smem(pl, SC_SMALL_THREADS) > (size_t)maxSmemOptin || small_smem(pl, SC_SMALL_THREADS) > 160 * 1024) return 0;
+    if (pl->hop > 4 * SC_SMALL_THREADS) return 0;
+    if ((long long)pl->nOutLocal * pl->nIn > 256) return 0;                       /* redundant forward FFTs stay cheap */
+    if ((double)pl->P * pl->nIn * pl->M * 8.0 > 4.0 * 1024 * 1024) return 0;       /* per-output filter bytes: L2-resident */
+    return 1;
+}
+
+int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream)
+{
+    SmallArgs a;
+    a.in = in; a.out = out; a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
+    a.tail = b->tail; a.counters = b->counters;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nIn = pl->nIn; a.nKT = pl->nKT;
+    a.OTsz = pl->OTsz; a.RS = pl->RS;
+    a.scale = 1.0f / (float)pl->N;
+    const size_t smem = small_smem(pl, SC_SMALL_THREADS);
+    if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    small_fused_kernel<<<pl->nOutLocal, SC_SMALL_THREADS, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

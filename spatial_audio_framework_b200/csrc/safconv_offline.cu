@@ -118,6 +118,7 @@ __global__ void offline_fft_kernel(OffFftArgs a)
     const int kg = blockIdx.x;
     const int row0 = blockIdx.y * OFF_FPC;
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
     for (int q = 0; q < 2 * OFF_FPC; ++q) {            /* q = 2*f + j : frame f, input 2kg+j */
         const int ni = 2 * kg + (q & 1);
         const int t = row0 + (q >> 1) - (a.P - 1);
@@ -144,8 +145,8 @@ __global__ void offline_fft_kernel(OffFftArgs a)
             x1 = make_float2(z1.x + z1.y, z1.x - z1.y);  x1m = x1;
             k2 = 0;
         } else {
-            fwd_split_pair(s0, k, a.M, a.logM, a.tw, x0, x0m);
-            fwd_split_pair(s1, k, a.M, a.logM, a.tw, x1, x1m);
+            fwd_split_pair(s0, k, a.M, a.logM, spl, x0, x0m);
+            fwd_split_pair(s1, k, a.M, a.logM, spl, x1, x1m);
         }
         const size_t row = (size_t)row0 + f;
         {
@@ -426,6 +427,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     float2* stw = sm + (size_t)OFF_OPC * MP;
     const int og = blockIdx.x, t = blockIdx.y;
     load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
     for (int idx = threadIdx.x; idx < a.M * OFF_OPC; idx += blockDim.x) {
         const int j = idx & (OFF_OPC - 1), k = idx / OFF_OPC;
         const int no = og * OFF_OPC + j;
@@ -434,7 +436,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     __syncthreads();
     {
         const int nArr = min(OFF_OPC, a.nOut - og * OFF_OPC);
-        inv_split_batch(sm, a.M, a.logM, a.tw, nArr);
+        inv_split_batch(sm, a.M, a.logM, spl, nArr);
         cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
     }
     for (int j = 0; j < OFF_OPC; ++j) {

@@ -41,13 +41,18 @@ MATRIX_CASES = [
 ]
 
 
+@pytest.mark.parametrize("path", ["default", "three_kernels"])
 @pytest.mark.parametrize("hop,L,nIn,nOut,part,nblk", MATRIX_CASES)
-def test_matrixconv_vs_oracle(saf, orc, hop, L, nIn, nOut, part, nblk):
+def test_matrixconv_vs_oracle(saf, orc, hop, L, nIn, nOut, part, nblk, path):
+    """path "default": small problems take the one-launch fused latency kernel, the rest K1 -> K2 -> K3;
+    "three_kernels": the fused kernel is switched off so every shape also runs through K1 -> K2 -> K3."""
     rng = np.random.default_rng(hop * 31 + L + nIn)
     H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
     x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
     ref = orc.OracleMatrixConv(hop, H, part).run(x)
     mc = saf.MatrixConv(hop, H, part)
+    if path == "three_kernels":
+        mc.set_option("small_fused", 0)
     y = mc.run(x)
     check(y, ref, "matrixConv")
     mc.destroy()
@@ -122,6 +127,31 @@ def test_closer_to_truth_than_needed(saf, orc):
     assert l2_gt <= 5e-7
 
 
+@pytest.mark.parametrize("hop,L,nIn,nOut,nblk", [(256, 1024, 4, 2, 50), (128, 512, 25, 2, 60), (512, 2000, 2, 2, 12),
+                                                  (100, 900, 3, 4, 70), (1024, 1024, 8, 8, 5), (64, 640, 16, 16, 45)])
+def test_fused_small_problem_kernel(saf, orc, hop, L, nIn, nOut, nblk):
+    """The one-launch latency path (small_fused_kernel on mapped host buffers): C1 / C2 and neighbours, more
+    blocks than ring slots (wrap-around), thread-group splits G > 1 and G = 1, interleaved with the device API."""
+    import torch
+    rng = np.random.default_rng(hop + nIn)
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H)
+    half = nblk // 2
+    y1 = mc.run(x[:, :half * hop])                                   # fused kernel, block by block
+    xb = np.ascontiguousarray(x[:, half * hop:].reshape(nIn, nblk - half, hop).transpose(1, 0, 2))
+    d_in = torch.from_numpy(xb).cuda()
+    d_out = torch.empty((nblk - half, nOut, hop), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    mc.apply_device(d_in.data_ptr(), d_out.data_ptr(), nblk - half)  # same handle continues on the batched path
+    mc.synchronize()
+    y2 = d_out.cpu().numpy().transpose(1, 0, 2).reshape(nOut, (nblk - half) * hop)
+    check(np.concatenate([y1, y2], 1), ref, "fused then batched")
+    mc.reset_state()
+    check(mc.run(x), ref, "fused only")
+
+
 def test_state_api(saf, orc):
     """destroy/NULL semantics, reset_state, re-create = zero state (reference .c:109,113)."""
     rng = np.random.default_rng(3)
@@ -159,7 +189,7 @@ def test_device_pointer_api_and_graph(saf, orc):
     y = d_out.cpu().numpy().transpose(1, 0, 2).reshape(nOut, nblk * hop)
     check(y, ref, "device API")
     mc.reset_state()
-    mc.set_option("use_graph", 1)
+    mc.set_option("use_graph", 1)                    # explicit graph replay of K1 -> K2 -> K3 (takes precedence over the fused kernel)
     yg = mc.run(x)
     assert np.array_equal(yg, y)
     # kernel timing hooks
@@ -195,6 +225,7 @@ def test_batched_device_blocks_equal_block_by_block(saf, orc, hop, L, nIn, nOut,
     for batching, splits in ((1, [nblk]), (0, [nblk]), (1, [1, 7, 2, nblk - 10])):
         mc = saf.MatrixConv(hop, H)
         mc.set_option("batching", batching)
+        mc.set_option("small_fused", 0)      # the bit-equality below is a property of the K1 -> K2 -> K3 path
         d_out = torch.zeros((nblk, nOut, hop), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
         b0 = 0
@@ -206,9 +237,12 @@ def test_batched_device_blocks_equal_block_by_block(saf, orc, hop, L, nIn, nOut,
         mc.destroy()
     check(outs[0], ref, "batched device blocks")
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
-    # host-pointer API (one block per call) gives the same bits as well
-    yh = saf.MatrixConv(hop, H).run(x)
-    assert np.array_equal(yh, outs[0])
+    # host-pointer API (one block per call) through the same three kernels gives the same bits as well
+    mh = saf.MatrixConv(hop, H)
+    mh.set_option("small_fused", 0)
+    assert np.array_equal(mh.run(x), outs[0])
+    # ... and through the fused small-problem kernel (different summation order) the same values to rounding
+    check(saf.MatrixConv(hop, H).run(x), ref, "host API, default path")
 
 
 @pytest.mark.parametrize("hop,L,nIn,nOut,T", [(64, 200, 3, 2, 20), (128, 128, 1, 1, 5), (256, 2048, 11, 5, 300),
@@ -280,10 +314,12 @@ def test_pinned_caller_buffers_are_used_directly(saf, orc):
     hop, L, nIn, nOut, nblk = 128, 900, 4, 3, 10
     H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
     x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
-    ref = saf.MatrixConv(hop, H).run(x)
     lib = saf.lib()
     fp = C.POINTER(C.c_float)
     for graph in (0, 1):
+        mr = saf.MatrixConv(hop, H)                   # same launch path, ordinary (pageable) caller buffers
+        mr.set_option("use_graph", graph)
+        ref = mr.run(x)
         mc = saf.MatrixConv(hop, H)
         mc.set_option("use_graph", graph)
         xin = torch.empty((nIn, hop)).pin_memory()
