@@ -455,7 +455,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
         float2 acc = make_float2(0.f, 0.f);
         cmac_packed(acc, __ldg(Hc + k), B[k], packed);
         int slot = head;
-#pragma unroll 4
+#pragma unroll 8
         for (int p = 1; p < a.P; ++p) {
             slot = (slot == 0) ? a.P - 1 : slot - 1;
             cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
@@ -901,7 +901,9 @@ int scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_
     a.tw = (const float2*)b->tw; a.tail = b->tail; a.counters = b->counters;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
     a.scale = 1.0f / (float)pl->N;
-    multi_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 3), (cudaStream_t)stream>>>(a);
+    /* one thread per bin (up to 512): the P filter / delay-line loads of a bin are the latency chain of this kernel */
+    int threads = pl->M < 64 ? 64 : (pl->M > 512 ? 512 : pl->M);
+    multi_fused_kernel<<<pl->nOutLocal, threads, fft_smem(pl, 3), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
