@@ -112,37 +112,42 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
         L >>= 1;
     }
     /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp; rows of 32 points of all
-     * transforms are contiguous, so the batch is just more rows */
+     * transforms are contiguous, so the batch is just more rows.
+     * Branch-free butterflies: lane l (partner l^h) computes  t = o + sg*v  (lower half: v+o, upper half: o-v)
+     * and multiplies by its own per-lane factor (1 in the lower half, the twiddle in the upper half). */
     {
         const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+        const float2 one = make_float2(1.f, 0.f);
         /* tw + off : the 16-entry table W_32^j, j < 16 */
-        float2 w16 = twd<INV>(tw, off + (lane & 15));
-        float2 w8  = twd<INV>(tw, off + 2 * (lane & 7));
-        float2 w4  = twd<INV>(tw, off + 4 * (lane & 3));
-        float2 w2  = twd<INV>(tw, off + 8 * (lane & 1));
+        const float2 w16 = (lane & 16) ? twd<INV>(tw, off + (lane & 15))     : one;
+        const float2 w8  = (lane & 8)  ? twd<INV>(tw, off + 2 * (lane & 7)) : one;
+        const float2 w4  = (lane & 4)  ? twd<INV>(tw, off + 4 * (lane & 3)) : one;
+        const float2 w2  = (lane & 2)  ? twd<INV>(tw, off + 8 * (lane & 1)) : one;
+        const float s16 = (lane & 16) ? -1.f : 1.f, s8 = (lane & 8) ? -1.f : 1.f, s4 = (lane & 4) ? -1.f : 1.f,
+                    s2 = (lane & 2) ? -1.f : 1.f, s1 = (lane & 1) ? -1.f : 1.f;
         for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
             const int arr = row >> (logM - 5), rr = row & ((M >> 5) - 1);
             float2* sp = s + (size_t)arr * (M + SC_PAD) + padi(rr * 32 + lane, logM);
             float2 v = *sp;
-#define SC_SHFL_STAGE(HALF, W)                                                       \
+#define SC_SHFL_STAGE(HALF, SG, W)                                                   \
             {                                                                        \
-                float2 o;                                                            \
-                o.x = __shfl_xor_sync(0xffffffffu, v.x, HALF);                       \
-                o.y = __shfl_xor_sync(0xffffffffu, v.y, HALF);                       \
-                if (lane & HALF) v = cmulf(csubf(o, v), W);                          \
-                else             v = caddf(v, o);                                    \
+                const float ox = __shfl_xor_sync(0xffffffffu, v.x, HALF);            \
+                const float oy = __shfl_xor_sync(0xffffffffu, v.y, HALF);            \
+                const float tx = fmaf(SG, v.x, ox), ty = fmaf(SG, v.y, oy);          \
+                v.x = tx * W.x - ty * W.y;                                           \
+                v.y = tx * W.y + ty * W.x;                                           \
             }
-            SC_SHFL_STAGE(16, w16)
-            SC_SHFL_STAGE(8,  w8)
-            SC_SHFL_STAGE(4,  w4)
-            SC_SHFL_STAGE(2,  w2)
-            {   /* span 1: twiddle is 1 */
-                float2 o;
-                o.x = __shfl_xor_sync(0xffffffffu, v.x, 1);
-                o.y = __shfl_xor_sync(0xffffffffu, v.y, 1);
-                v = (lane & 1) ? csubf(o, v) : caddf(v, o);
-            }
+            SC_SHFL_STAGE(16, s16, w16)
+            SC_SHFL_STAGE(8,  s8,  w8)
+            SC_SHFL_STAGE(4,  s4,  w4)
+            SC_SHFL_STAGE(2,  s2,  w2)
 #undef SC_SHFL_STAGE
+            {   /* span 1: twiddle is 1 */
+                const float ox = __shfl_xor_sync(0xffffffffu, v.x, 1);
+                const float oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
+                v.x = fmaf(s1, v.x, ox);
+                v.y = fmaf(s1, v.y, oy);
+            }
             *sp = v;
         }
         __syncthreads();
