@@ -61,7 +61,7 @@ typedef struct scdev_bufs {
     void*  tw;        /* float2[M]        W_N^j                                            */
     void*  H;         /* float2: matrix [nOT][nKT][P][nIn][OTsz][32]; multi [nCH][P][M];    */
                       /*         tv     [nIRs][nOut][P][M]                                  */
-    void*  X;         /* float2: matrix [nKT][RS][nIn][32];           multi [nCH][P][M];    */
+    void*  X;         /* float2: matrix [nKT][RS][nIn][32];           multi [nCH][RS][M];   */
                       /*         tv     [P][M]                                              */
     void*  Zp;        /* float2[maxBatch][nSlots][OTsz][32]  split-K partial output spectra */
     float* zt;        /* float[maxBatch][nOutLocal][2*hop]   batched inverse transforms     */
@@ -137,6 +137,9 @@ int  scdev_is_pinned_host(const void* p);
 /* small matrix problems: K1+K2+K3 in one launch, one CTA per output channel; in/out may be mapped host memory */
 int  scdev_small_fits(const scdev_plan* pl, int maxSmemOptin);
 int  scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream);
+/* multiConv, nBlocks device-resident blocks d_in [nBlocks][nCH][hop] -> d_out [nBlocks][nCH][hop]:
+ * which = 0 forward FFTs of all blocks, 1 MAC + inverse FFTs of all blocks, 2 overlap-add chain (+ counter += nBlocks) */
+int  scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, int nBlocks, int which, void* stream);
 /* multiConv: K1+K2+K3 fused, one CTA per channel */
 int  scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream);
 /* TVConv: 1-input FFT + (1..3) IR MACs + cross-fade, one CTA per output channel */

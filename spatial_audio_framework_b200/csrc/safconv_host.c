@@ -340,8 +340,13 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         h->bytesZp = (size_t)pl->maxBatch * slots * pl->OTsz * SC_BK * 8;
         rowsTotal  = (size_t)nOutLocal * nIn;
     } else if (kind == SC_KIND_MULTI) {
+        /* blocks handed over together are transformed ahead of their MAC: maxBatch extra ring slots (<= ~256 MB) */
+        int mb = env_int("SAFCONV_MAX_BATCH", 32, 1, 256);
+        while (mb > 1 && (double)mb * nOutLocal * ((double)M * 8.0 + (double)hop * 8.0) > 256e6) mb >>= 1;
+        pl->maxBatch = mb;
+        pl->RS = pl->P + mb;
         h->bytesH = (size_t)nOutLocal * P * M * 8;
-        h->bytesX = h->bytesH;
+        h->bytesX = (size_t)nOutLocal * pl->RS * M * 8;
         rowsTotal = (size_t)nOutLocal;
     } else {
         h->bytesH = (size_t)nIRs * nOutLocal * P * M * 8;
@@ -354,7 +359,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     if (zalloc(h, &h->b.H, h->bytesH, "filter spectra allocation")) goto fail;
     if (zalloc(h, &h->b.X, h->bytesX, "delay line allocation")) goto fail;
     if (kind == SC_KIND_MATRIX && zalloc(h, &h->b.Zp, h->bytesZp, "partial spectra allocation")) goto fail;
-    if (kind == SC_KIND_MATRIX && pl->maxBatch > 1 &&
+    if ((kind == SC_KIND_MATRIX || kind == SC_KIND_MULTI) && pl->maxBatch > 1 &&
         zalloc(h, (void**)&h->b.zt, sizeof(float) * (size_t)pl->maxBatch * nOutLocal * 2 * hop, "batched inverse-transform buffer")) goto fail;
     if (zalloc(h, (void**)&h->b.tail, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails")) goto fail;
     if (kind == SC_KIND_TV && zalloc(h, (void**)&h->b.tail2, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails (last)")) goto fail;
@@ -423,6 +428,19 @@ static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, in
         if (ev) scdev_event_record(ev[2], h->stream);
         if (!e) e = (nBlocks == 1) ? scdev_ifft_ola(pl, &h->b, d_out, h->stream)
                                    : scdev_ifft_ola_batch(pl, &h->b, d_out, nBlocks, h->stream);
+        if (ev) scdev_event_record(ev[3], h->stream);
+    } else if (pl->kind == SC_KIND_MULTI && nBlocks > 1) {
+        /* batch: forward FFTs of all blocks, then all (channel, block) MACs + inverse FFTs, then the overlap-add chain */
+        if (h->timingCap && h->timingCount < h->timingCap) {
+            ev = h->evRing + 4 * (size_t)h->timingCount;
+            h->evBlocks[h->timingCount++] = nBlocks;
+        }
+        if (ev) scdev_event_record(ev[0], h->stream);
+        e = scdev_multi_batch(pl, &h->b, d_in, d_out, nBlocks, 0, h->stream);
+        if (ev) scdev_event_record(ev[1], h->stream);
+        if (!e) e = scdev_multi_batch(pl, &h->b, d_in, d_out, nBlocks, 1, h->stream);
+        if (ev) scdev_event_record(ev[2], h->stream);
+        if (!e) e = scdev_multi_batch(pl, &h->b, d_in, d_out, nBlocks, 2, h->stream);
         if (ev) scdev_event_record(ev[3], h->stream);
     } else if (pl->kind == SC_KIND_MULTI) {
         const size_t inStride = (size_t)pl->nIn * pl->hop, outStride = (size_t)pl->nOutLocal * pl->hop;
@@ -638,7 +656,7 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
     int e = scdev_set_device(h->device);
     const size_t inStride = (size_t)h->pl.nIn * h->pl.hop, outStride = (size_t)h->pl.nOutLocal * h->pl.hop;
-    const int mb = (h->pl.kind == SC_KIND_MATRIX && h->batching) ? h->pl.maxBatch : 1;
+    const int mb = (h->batching && h->pl.maxBatch > 1) ? h->pl.maxBatch : 1;
     for (int b = 0; b < nBlocks && !e; b += mb) {
         const int n = (nBlocks - b < mb) ? nBlocks - b : mb;
         e = enqueue_blocks(h, d_in + (size_t)b * inStride, d_out + (size_t)b * outStride, n);
@@ -745,7 +763,7 @@ int safconv_get_info(void* hp, safconv_info* info)
     info->nCHin = pl->nIn; info->nCHout = h->nCHoutTotal; info->nOutLocal = pl->nOutLocal; info->outBegin = h->outBegin;
     info->fftSize = pl->N; info->nBinsPacked = pl->M; info->numFilterBlocks = pl->P;
     info->macGrid = pl->macGrid; info->macStages = pl->macStages; info->macThreads = (SC_MAC_CWARPS + 1) * 32;
-    info->maxBatch = (pl->kind == SC_KIND_MATRIX) ? pl->maxBatch : 1;
+    info->maxBatch = (pl->kind == SC_KIND_TV || pl->maxBatch < 1) ? 1 : pl->maxBatch;
     info->device = h->device;
     info->bytesFilters = h->bytesH; info->bytesDelayLine = h->bytesX;
     /* algorithmic bytes per block, nBins = hop + 1 complex bins of 8 bytes */
@@ -804,9 +822,10 @@ int safconv_get_kernel_totals(void* hp, float msTotal[3], int* nLaunchGroups, in
     for (int g = 0; g < n && !e; g++) {
         void** ev = h->evRing + 4 * (size_t)g;
         float t = 0.f;
-        if (matrix) { e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t; }
+        const int full = matrix || h->evBlocks[g] > 1;          /* multiConv: only batched groups record all four events */
+        if (full) { e = scdev_event_elapsed_ms(ev[0], ev[1], &t); acc[0] += t; }
         if (!e) { e = scdev_event_elapsed_ms(ev[1], ev[2], &t); acc[1] += t; }
-        if (!e && matrix) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
+        if (!e && full) { e = scdev_event_elapsed_ms(ev[2], ev[3], &t); acc[2] += t; }
         blocks += h->evBlocks[g];
     }
     h->timingCount = 0;

@@ -399,11 +399,12 @@ struct MultiArgs {
     const float* in;       /* [nCH][hop] */
     float* out;            /* [nCH][hop] */
     const float2* H;       /* [nCH][P][M] */
-    float2* X;             /* [nCH][P][M] ring */
+    float2* X;             /* [nCH][RS][M] ring, RS = P + maxBatch */
     const float2* tw;
     float* tail;
+    float* zt;             /* batched path: [B][nCH][2*hop] */
     unsigned int* counters;
-    int hop, M, logM, P;
+    int hop, M, logM, P, RS, nCH;
     float scale;
 };
 
@@ -425,8 +426,8 @@ __global__ void multi_fused_kernel(MultiArgs a)
     float2* B = sm + a.M + SC_PAD;        /* spectrum of the new block, natural order */
     float2* stw = B + a.M;
     const int c = blockIdx.x;
-    const int head = (int)(a.counters[0] % (unsigned)a.P);
-    float2* Xc = a.X + (size_t)c * a.P * a.M;
+    const int head = (int)(a.counters[0] % (unsigned)a.RS);
+    float2* Xc = a.X + (size_t)c * a.RS * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
     load_twiddles(stw, a.tw, a.M, a.logM);
@@ -457,7 +458,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
         int slot = head;
 #pragma unroll 8
         for (int p = 1; p < a.P; ++p) {
-            slot = (slot == 0) ? a.P - 1 : slot - 1;
+            slot = (slot == 0) ? a.RS - 1 : slot - 1;
             cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
         }
         A[padi(k, a.logM)] = acc;
@@ -467,6 +468,65 @@ __global__ void multi_fused_kernel(MultiArgs a)
     cfft_dif<true>(A, a.M, a.logM, stw);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
+}
+
+/* ---- multiConv, batch of B device-resident blocks: every (channel, block) pair is independent once the
+ * spectra of all B blocks are in the ring, so the work is two fully parallel launches + the overlap-add chain ---- */
+
+/* grid (nCH, B): forward FFT of block b of channel c into ring slot (counter + b) % RS */
+__global__ void multi_fft_batch_kernel(MultiArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + a.M + SC_PAD;
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
+    load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    load_real_block(sm, a.in + ((size_t)b * a.nCH + c) * a.hop, a.hop, a.M, a.logM);
+    __syncthreads();
+    cfft_dif<false>(sm, a.M, a.logM, stw);
+    float2* Xnew = a.X + ((size_t)c * a.RS + slot) * a.M;
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = sm[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);
+            k2 = 0; Xmk = Xk;
+        } else {
+            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
+        }
+        Xnew[k] = Xk;  Xnew[k2] = Xmk;
+    }
+}
+
+/* grid (nCH, B): Z = sum_p H_p * X_{t_b - p} (same order as the one-block kernel), inverse FFT -> zt[b][c][0..2*hop) */
+__global__ void multi_mac_ifft_batch_kernel(MultiArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + a.M + SC_PAD;
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int head = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
+    const float2* Xc = a.X + (size_t)c * a.RS * a.M;
+    const float2* Hc = a.H + (size_t)c * a.P * a.M;
+    load_twiddles(stw, a.tw, a.M, a.logM);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const bool packed = (k == 0);
+        float2 acc = make_float2(0.f, 0.f);
+        int slot = head;
+#pragma unroll 8
+        for (int p = 0; p < a.P; ++p) {
+            cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
+            slot = (slot == 0) ? a.RS - 1 : slot - 1;
+        }
+        sm[padi(k, a.logM)] = acc;
+    }
+    __syncthreads();
+    inv_split_all(sm, a.M, a.logM, spl);
+    cfft_dif<true>(sm, a.M, a.logM, stw);
+    float* z = a.zt + ((size_t)b * a.nCH + c) * 2 * a.hop;
+    for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -808,8 +868,11 @@ int scdev_prepare(const scdev_plan* pl)
         SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SC_CHECK(cudaFuncSetAttribute(ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
-    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 3) > 48 * 1024)
+    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 3) > 48 * 1024) {
         SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 3)));
+        SC_CHECK(cudaFuncSetAttribute(multi_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
+        SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
+    }
     if (pl->kind == SC_KIND_TV && fft_smem(pl, 5) > 48 * 1024)
         SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 5)));
     if (pl->kind == SC_KIND_MATRIX)
@@ -894,13 +957,40 @@ int scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out
     return (int)cudaGetLastError();
 }
 
+static void fill_multi_args(MultiArgs& a, const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out)
+{
+    a.in = d_in; a.out = d_out; a.H = (const float2*)b->H; a.X = (float2*)b->X;
+    a.tw = (const float2*)b->tw; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
+    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.RS = pl->RS; a.nCH = pl->nOutLocal;
+    a.scale = 1.0f / (float)pl->N;
+}
+
+/* multiConv, nBlocks device-resident blocks: which = 0 forward FFTs, 1 MAC + inverse FFTs, 2 overlap-add chain */
+int scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, int nBlocks, int which, void* stream)
+{
+    MultiArgs a;
+    fill_multi_args(a, pl, b, d_in, d_out);
+    const int threads = pl->M < 64 ? 64 : (pl->M > 512 ? 512 : pl->M);
+    dim3 grid(pl->nOutLocal, nBlocks);
+    if (which == 0) {
+        multi_fft_batch_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    } else if (which == 1) {
+        multi_mac_ifft_batch_kernel<<<grid, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+    } else {
+        IfftArgs o;
+        o.Zp = NULL; o.grpStart = NULL; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
+        o.zpStride = 0; o.hop = pl->hop; o.M = pl->M; o.logM = pl->logM; o.nKT = 0; o.OTsz = 0;
+        o.nOutLocal = pl->nOutLocal; o.B = nBlocks; o.scale = 0.f;
+        const size_t n = (size_t)pl->nOutLocal * pl->hop;
+        ola_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o);
+    }
+    return (int)cudaGetLastError();
+}
+
 int scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out, void* stream)
 {
     MultiArgs a;
-    a.in = d_in; a.out = d_out; a.H = (const float2*)b->H; a.X = (float2*)b->X;
-    a.tw = (const float2*)b->tw; a.tail = b->tail; a.counters = b->counters;
-    a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P;
-    a.scale = 1.0f / (float)pl->N;
+    fill_multi_args(a, pl, b, d_in, d_out);
     /* one thread per bin (up to 512): the P filter / delay-line loads of a bin are the latency chain of this kernel */
     int threads = pl->M < 64 ? 64 : (pl->M > 512 ? 512 : pl->M);
     multi_fused_kernel<<<pl->nOutLocal, threads, fft_smem(pl, 3), (cudaStream_t)stream>>>(a);

@@ -308,6 +308,33 @@ def test_offline_render_c5_shape_vs_streaming(saf):
     print("C5-shape offline vs streaming", ma, l2, mc.offline_times_ms())
 
 
+@pytest.mark.parametrize("hop,L,nCH,nblk", [(512, 4096, 16, 70), (64, 300, 3, 41), (2048, 9000, 2, 9)])
+def test_multiconv_batched_device_blocks(saf, orc, hop, L, nCH, nblk):
+    """multiConv on device-resident blocks: all forward FFTs, then all (channel, block) MACs + inverse FFTs, then
+    the overlap-add chain -- bit-identical to one fused launch per block, across batch and ring boundaries."""
+    import torch
+    rng = np.random.default_rng(hop + nCH)
+    H = rng.uniform(-1, 1, (nCH, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nCH, hop * nblk)).astype(np.float32)
+    ref = orc.OracleMultiConv(hop, H, 1).run(x)
+    d_in = torch.from_numpy(np.ascontiguousarray(x.reshape(nCH, nblk, hop).transpose(1, 0, 2))).cuda()
+    outs = []
+    for batching, splits in ((1, [nblk]), (0, [nblk]), (1, [3, 1, nblk - 4])):
+        mc = saf.MultiConv(hop, H)
+        mc.set_option("batching", batching)
+        d_out = torch.zeros((nblk, nCH, hop), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        b0 = 0
+        for n in splits:
+            mc.apply_device(d_in[b0:].data_ptr(), d_out[b0:].data_ptr(), n)
+            b0 += n
+        mc.synchronize()
+        outs.append(d_out.cpu().numpy().transpose(1, 0, 2).reshape(nCH, nblk * hop))
+    check(outs[0], ref, "multiConv batched")
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(saf.MultiConv(hop, H).run(x), outs[0])
+
+
 def test_pinned_caller_buffers_are_used_directly(saf, orc):
     import torch
     rng = np.random.default_rng(8)
