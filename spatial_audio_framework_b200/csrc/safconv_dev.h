@@ -79,7 +79,7 @@ typedef struct scdev_offline {
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
     float *zt;               /* inverse transforms [T][nOut][2*hop]                                             */
     int capFrames, capTpad, capRows, packed;
-    int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush;
+    int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush, fpc, opc, fftThreads;
 } scdev_offline;
 
 /* --- device / memory / stream plumbing (all return 0 on success, else a cudaError_t value) --- */

@@ -28,130 +28,125 @@ __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2
 
 __device__ __forceinline__ int bitrev(int v, int logM) { return (int)(__brev((unsigned)v) >> (32 - logM)); }
 
-/* FFT work arrays in shared memory are PADDED: element i of an M-point array lives at i + (i >> (logM-4)),
- * i.e. one extra float2 after every M/16 elements (array length M + SC_PAD).  The FFT leaves its result in
- * bit-reversed order; the epilogues read s[bitrev(k)] for consecutive k, which without padding puts all 32
- * lanes on one bank (stride M/32 elements).  With the padding those reads are conflict-free, and the
- * unit-stride accesses of the FFT passes stay (almost) unit-stride. */
-#define SC_PAD 18      /* 16 padding slots + 2: array stride = 2 (mod 16) elements, so 8 arrays x 2 bins hit 16 distinct banks */
-__device__ __forceinline__ int padi(int i, int logM) { return i + (i >> (logM - 4)); }
+/* FFT work arrays in shared memory are PADDED: element i of an M-point array lives at
+ *     padi(i) = i + (i >> 4) + (i >> (logM-4))
+ * (one extra float2 after every 16 elements and one after every M/16; array length SC_ALEN(M)).
+ *  - the register passes let a thread own 2..16 CONSECUTIVE elements (stride-1 final pass) or elements at a
+ *    small stride: the per-16 skew puts the 16 lanes of a half-warp on 16 different banks in every case;
+ *  - the FFT leaves its result in bit-reversed order and the epilogues read s[bitrev(k)] for consecutive k,
+ *    i.e. lane stride M/32 elements: the two skews together make those reads conflict-free as well;
+ *  - SC_ALEN(M) = 2 (mod 16) elements, so consecutive arrays of a batch start on different banks. */
+#define SC_ALEN(M) ((M) + ((M) >> 4) + 18)
+__device__ __forceinline__ int padi(int i, int logM) { return i + (i >> 4) + (i >> (logM - 4)); }
 
 /* ------------------------------------------------------------------------------------------ */
-/*  M-point complex FFT in shared memory, decimation in frequency                              */
+/*  M-point complex FFT in shared memory, decimation in frequency, in place                     */
 /*  input: natural order (padded indexing) ; output: element padi(bitrev(k)) holds bin k          */
-/*  tw = the per-pass twiddle tables that load_twiddles() builds in shared memory from the global   */
-/*  table gtw[j] = exp(-2*pi*i*j/N), N = 2M, j < M  (W_L^j = gtw[j * (2M/L)]): every pass reads its     */
-/*  twiddles with unit stride (no bank conflicts, no L2 round trip).                                 */
-/*  INV conjugates every twiddle (unnormalised inverse transform).                              */
-/*  Requires M >= 32, blockDim.x a multiple of 32; ends with __syncthreads().                   */
+/*                                                                                              */
+/*  Register passes: a pass of radix R = 16 on sub-transforms of length L lets one thread own the  */
+/*  16 elements j + i*(L/16) of a sub-transform, run the complete 16-point DIF butterfly (four      */
+/*  radix-2 stages, internal twiddles W_16^k are compile-time constants) in registers, multiply     */
+/*  output q by the external twiddle W_L^(j*q) and store in place: four FFT stages per trip         */
+/*  through shared memory.  log2(M) mod 4 left-over stages run as a final radix-2/4/8 register      */
+/*  pass over consecutive elements.  All transforms of a CTA advance together (one barrier per pass).*/
+/*  tw = the per-pass tables load_twiddles() builds in shared memory: for every radix-16 pass with   */
+/*  L > 16, W_L^(j*q) at [(q-1)*(L/16) + j], q = 1..15 (unit stride in j).                           */
+/*  INV conjugates every twiddle (unnormalised inverse transform).                                */
+/*  Requires M >= 32; ends with __syncthreads().                                                  */
 /* ------------------------------------------------------------------------------------------ */
+
+/* d * W_16^k  (forward: exp(-2 pi i k / 16); INV: the conjugate), k a compile-time constant after unrolling */
 template <bool INV>
-__device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
+__device__ __forceinline__ float2 mul_w16(float2 d, int k)
 {
-    float2 w = tw[idx];
-    if (INV) w.y = -w.y;
-    return w;
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    if (k == 0) return d;
+    if (k == 4) return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    float wx, wy;                                   /* W_16^k = (wx, -wy) forward */
+    switch (k) {
+        case 1: wx = C1;  wy = S1; break;
+        case 2: wx = R2;  wy = R2; break;
+        case 3: wx = S1;  wy = C1; break;
+        case 5: wx = -S1; wy = C1; break;
+        case 6: wx = -R2; wy = R2; break;
+        default: wx = -C1; wy = S1; break;          /* 7 */
+    }
+    if (INV) wy = -wy;
+    /* d * (wx - i wy) */
+    return make_float2(d.x * wx + d.y * wy, d.y * wx - d.x * wy);
 }
 
-/* nArr independent transforms stored back to back (array a at s + a*(M+SC_PAD)) advance together, pass by pass:
- * one __syncthreads per pass for the whole batch instead of one per pass per transform */
+/* complete R-point DIF butterfly on registers; v[i] ends up holding output bitrev_R(i), exactly like the
+ * in-place radix-2 DIF would leave it at position i */
+template <int R, bool INV>
+__device__ __forceinline__ void dif_regs(float2 (&v)[R])
+{
+#pragma unroll
+    for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & h) == 0) {
+                const float2 a = v[i], b = v[i + h];
+                v[i] = caddf(a, b);
+                v[i + h] = mul_w16<INV>(csubf(a, b), (i & (h - 1)) * (8 / h));
+            }
+        }
+    }
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void final_pass(float2* s, const int M, const int logM, const int nArr)
+{
+    const int per = M / R;                          /* threads' worth of work per transform */
+    for (int it = threadIdx.x; it < nArr * per; it += blockDim.x) {
+        const int arr = it / per, t = it - arr * per;
+        float2* sa = s + (size_t)arr * SC_ALEN(M);
+        float2 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = sa[padi(t * R + i, logM)];
+        dif_regs<R, INV>(v);
+#pragma unroll
+        for (int i = 0; i < R; ++i) sa[padi(t * R + i, logM)] = v[i];
+    }
+    __syncthreads();
+}
+
 template <bool INV>
 __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    int L = M;                 /* current sub-transform length */
-    int nsm = logM - 5;        /* radix-2 stages done through shared memory (spans M/2 .. 32) */
-    int off = 0;               /* start of this pass's twiddle table inside tw (see load_twiddles) */
-
-    /* two radix-2 stages fused per pass */
-    while (nsm >= 2) {
-        const int q = L >> 2;
-        const int per = M >> 2;                    /* butterflies per transform */
+    int logL = logM, off = 0;
+    while (logL >= 4) {
+        const int logSt = logL - 4, st = 1 << logSt;                /* element stride inside a butterfly */
+        const int per = M >> 4;                                     /* butterflies per transform */
         for (int it = tid; it < nArr * per; it += T) {
-            const int arr = it >> (logM - 2), i = it & (per - 1);
-            float2* sa = s + (size_t)arr * (M + SC_PAD);
-            const int j = i & (q - 1);
-            const int base = ((i - j) << 2) + j;
-            const int i0 = padi(base, logM), i1 = padi(base + q, logM), i2 = padi(base + 2 * q, logM), i3 = padi(base + 3 * q, logM);
-            const float2 a0 = sa[i0], a1 = sa[i1], a2 = sa[i2], a3 = sa[i3];
-            const float2 w1 = twd<INV>(tw, off + j);         /* W_L^j  */
-            const float2 w2 = twd<INV>(tw, off + q + j);     /* W_L^2j */
-            const float2 u0 = caddf(a0, a2);
-            const float2 u1 = caddf(a1, a3);
-            const float2 v0 = cmulf(csubf(a0, a2), w1);
-            float2 d1 = csubf(a1, a3);
-            /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
-            d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
-            const float2 v1 = cmulf(d1, w1);
-            sa[i0] = caddf(u0, u1);
-            sa[i1] = cmulf(csubf(u0, u1), w2);
-            sa[i2] = caddf(v0, v1);
-            sa[i3] = cmulf(csubf(v0, v1), w2);
-        }
-        __syncthreads();
-        off += 2 * q;
-        L >>= 2;
-        nsm -= 2;
-    }
-    if (nsm == 1) {
-        const int half = L >> 1;
-        const int per = M >> 1;
-        for (int it = tid; it < nArr * per; it += T) {
-            const int arr = it >> (logM - 1), i = it & (per - 1);
-            float2* sa = s + (size_t)arr * (M + SC_PAD);
-            const int j = i & (half - 1);
-            const int base = ((i - j) << 1) + j;
-            const int i0 = padi(base, logM), i1 = padi(base + half, logM);
-            const float2 a = sa[i0], b = sa[i1];
-            const float2 w = twd<INV>(tw, off + j);
-            sa[i0] = caddf(a, b);
-            sa[i1] = cmulf(csubf(a, b), w);
-        }
-        __syncthreads();
-        off += half;
-        L >>= 1;
-    }
-    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp; rows of 32 points of all
-     * transforms are contiguous, so the batch is just more rows.
-     * Branch-free butterflies: lane l (partner l^h) computes  t = o + sg*v  (lower half: v+o, upper half: o-v)
-     * and multiplies by its own per-lane factor (1 in the lower half, the twiddle in the upper half). */
-    {
-        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-        const float2 one = make_float2(1.f, 0.f);
-        /* tw + off : the 16-entry table W_32^j, j < 16 */
-        const float2 w16 = (lane & 16) ? twd<INV>(tw, off + (lane & 15))     : one;
-        const float2 w8  = (lane & 8)  ? twd<INV>(tw, off + 2 * (lane & 7)) : one;
-        const float2 w4  = (lane & 4)  ? twd<INV>(tw, off + 4 * (lane & 3)) : one;
-        const float2 w2  = (lane & 2)  ? twd<INV>(tw, off + 8 * (lane & 1)) : one;
-        const float s16 = (lane & 16) ? -1.f : 1.f, s8 = (lane & 8) ? -1.f : 1.f, s4 = (lane & 4) ? -1.f : 1.f,
-                    s2 = (lane & 2) ? -1.f : 1.f, s1 = (lane & 1) ? -1.f : 1.f;
-        for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
-            const int arr = row >> (logM - 5), rr = row & ((M >> 5) - 1);
-            float2* sp = s + (size_t)arr * (M + SC_PAD) + padi(rr * 32 + lane, logM);
-            float2 v = *sp;
-#define SC_SHFL_STAGE(HALF, SG, W)                                                   \
-            {                                                                        \
-                const float ox = __shfl_xor_sync(0xffffffffu, v.x, HALF);            \
-                const float oy = __shfl_xor_sync(0xffffffffu, v.y, HALF);            \
-                const float tx = fmaf(SG, v.x, ox), ty = fmaf(SG, v.y, oy);          \
-                v.x = tx * W.x - ty * W.y;                                           \
-                v.y = tx * W.y + ty * W.x;                                           \
+            const int arr = it >> (logM - 4), t = it & (per - 1);
+            float2* sa = s + (size_t)arr * SC_ALEN(M);
+            const int j = t & (st - 1);
+            const int base = ((t >> logSt) << logL) + j;            /* sub-transform start + j */
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = sa[padi(base + (i << logSt), logM)];
+            dif_regs<16, INV>(v);
+            if (logSt > 0) {
+#pragma unroll
+                for (int i = 1; i < 16; ++i) {
+                    const int q = ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);   /* bitrev4(i) */
+                    float2 w = tw[off + (q - 1) * st + j];
+                    if (INV) w.y = -w.y;
+                    v[i] = cmulf(v[i], w);
+                }
             }
-            SC_SHFL_STAGE(16, s16, w16)
-            SC_SHFL_STAGE(8,  s8,  w8)
-            SC_SHFL_STAGE(4,  s4,  w4)
-            SC_SHFL_STAGE(2,  s2,  w2)
-#undef SC_SHFL_STAGE
-            {   /* span 1: twiddle is 1 */
-                const float ox = __shfl_xor_sync(0xffffffffu, v.x, 1);
-                const float oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
-                v.x = fmaf(s1, v.x, ox);
-                v.y = fmaf(s1, v.y, oy);
-            }
-            *sp = v;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sa[padi(base + (i << logSt), logM)] = v[i];
         }
         __syncthreads();
+        if (logSt > 0) off += 15 * st;
+        logL -= 4;
     }
+    if (logL == 1) final_pass<2, INV>(s, M, logM, nArr);
+    else if (logL == 2) final_pass<4, INV>(s, M, logM, nArr);
+    else if (logL == 3) final_pass<8, INV>(s, M, logM, nArr);
 }
 
 template <bool INV>
@@ -160,27 +155,27 @@ __device__ __forceinline__ void cfft_dif(float2* s, const int M, const int logM,
     cfft_dif_batch<INV>(s, M, logM, tw, 1);
 }
 
-/* Build the per-pass twiddle tables of cfft_dif_batch in shared memory (at most M float2), same pass
- * structure: for every radix-4 pass of sub-length L: W_L^j (j < L/4) then W_L^2j; for the radix-2 pass W_L^j
- * (j < L/2); finally W_32^j (j < 16) for the warp-shuffle stages.  Strided reads of the global table hit L2. */
+/* Build the per-pass twiddle tables of cfft_dif_batch in shared memory (fewer than M float2 in total): for every
+ * radix-16 pass of sub-length L > 16 the table W_L^(j*q) at [(q-1)*(L/16) + j], q = 1..15, j < L/16, taken from the
+ * global table gtw[e] = exp(-2 pi i e / 2M), e < M  (W_L^x = W_2M^(x * 2M/L); the upper half by W^(M+e) = -W^e). */
 __device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M, int logM)
 {
-    const int tid = threadIdx.x, T = blockDim.x;
-    int L = M, nsm = logM - 5, off = 0;
-    while (nsm >= 2) {
-        const int q = L >> 2, tstr = (2 * M) / L;
-        for (int j = tid; j < q; j += T) {
-            stw[off + j]     = __ldg(gtw + j * tstr);
-            stw[off + q + j] = __ldg(gtw + 2 * j * tstr);
+    int logL = logM, off = 0;
+    while (logL >= 4) {
+        const int logSt = logL - 4, st = 1 << logSt;
+        if (logSt > 0) {
+            const int sh = logM + 1 - logL;                              /* 2M / L = 2^sh */
+            for (int idx = threadIdx.x; idx < 15 * st; idx += blockDim.x) {
+                const int q = (idx >> logSt) + 1, j = idx & (st - 1);
+                const int e = (j * q) << sh;                             /* < 2M */
+                float2 w = __ldg(gtw + (e & (M - 1)));
+                if (e >= M) { w.x = -w.x; w.y = -w.y; }
+                stw[off + idx] = w;
+            }
+            off += 15 * st;
         }
-        off += 2 * q; L >>= 2; nsm -= 2;
+        logL -= 4;
     }
-    if (nsm == 1) {
-        const int half = L >> 1, tstr = (2 * M) / L;
-        for (int j = tid; j < half; j += T) stw[off + j] = __ldg(gtw + j * tstr);
-        off += half;
-    }
-    if (tid < 16) stw[off + tid] = __ldg(gtw + tid * (M >> 4));
 }
 
 /* The real-FFT split passes need W_N^k, k <= M/2 (unit stride).  For M <= 4096 the kernels keep a copy in shared
@@ -247,7 +242,7 @@ __device__ __forceinline__ void inv_split_batch(float2* Z, int M, int logM, cons
     const int per = (M >> 1) + 1;
     for (int it = threadIdx.x; it < nArr * per; it += blockDim.x) {
         const int arr = it / per, k = it - arr * per;
-        float2* Za = Z + (size_t)arr * (M + SC_PAD);
+        float2* Za = Z + (size_t)arr * SC_ALEN(M);
         if (k == 0) {
             const float2 A = Za[0];                      /* (DC, Nyquist) */
             Za[0] = make_float2(A.x + A.y, A.x - A.y);

@@ -45,7 +45,7 @@ struct FilterArgs {
 __global__ void filter_fft_kernel(FilterArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M + SC_PAD;
+    float2* stw = sm + SC_ALEN(a.M);
     load_twiddles(stw, a.tw, a.M, a.logM);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
@@ -106,7 +106,7 @@ struct InFftArgs {
 __global__ void input_fft_kernel(InFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M + SC_PAD;
+    float2* stw = sm + SC_ALEN(a.M);
     const int ni = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     load_twiddles(stw, a.tw, a.M, a.logM);
@@ -347,7 +347,7 @@ __global__ void ifft_ola_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x;
-    gather_and_ifft(a, a.Zp, no, sm, sm + a.M + SC_PAD);
+    gather_and_ifft(a, a.Zp, no, sm, sm + SC_ALEN(a.M));
     ola_store(sm, a.hop, a.logM, a.scale, a.out + (size_t)no * a.hop, a.tail + (size_t)no * a.hop);
     advance_block_counter(a.counters, gridDim.x);
 }
@@ -357,7 +357,7 @@ __global__ void ifft_batch_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x, b = blockIdx.y;
-    gather_and_ifft(a, a.Zp + (size_t)b * a.zpStride, no, sm, sm + a.M + SC_PAD);
+    gather_and_ifft(a, a.Zp + (size_t)b * a.zpStride, no, sm, sm + SC_ALEN(a.M));
     float* z = a.zt + ((size_t)b * a.nOutLocal + no) * 2 * a.hop;
     for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
 }
@@ -423,7 +423,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     float2* A = sm;                       /* FFT work array (padded) */
-    float2* B = sm + a.M + SC_PAD;        /* spectrum of the new block, natural order */
+    float2* B = sm + SC_ALEN(a.M);        /* spectrum of the new block, natural order */
     float2* stw = B + a.M;
     const int c = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.RS);
@@ -477,7 +477,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
 __global__ void multi_fft_batch_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M + SC_PAD;
+    float2* stw = sm + SC_ALEN(a.M);
     const int c = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     load_twiddles(stw, a.tw, a.M, a.logM);
@@ -504,7 +504,7 @@ __global__ void multi_fft_batch_kernel(MultiArgs a)
 __global__ void multi_mac_ifft_batch_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + a.M + SC_PAD;
+    float2* stw = sm + SC_ALEN(a.M);
     const int c = blockIdx.x, b = blockIdx.y;
     const int head = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     const float2* Xc = a.X + (size_t)c * a.RS * a.M;
@@ -554,7 +554,7 @@ struct SmallArgs {
 __global__ void small_fused_kernel(SmallArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const int MP = a.M + SC_PAD;
+    const int MP = SC_ALEN(a.M);
     float2* W   = sm;                                  /* nIn padded FFT work arrays (array 0 is re-used for Z) */
     float2* Xn  = sm + (size_t)a.nIn * MP;             /* nIn packed spectra of the new block, natural order    */
     float2* stw = Xn + (size_t)a.nIn * a.M;
@@ -703,7 +703,7 @@ struct TvArgs {
 __global__ void tv_fused_kernel(TvArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const int MP = a.M + SC_PAD;     /* padded FFT work arrays Z0, Z1, Z2 stored back to back */
+    const int MP = SC_ALEN(a.M);     /* padded FFT work arrays Z0, Z1, Z2 stored back to back */
     float2* Z0 = sm;
     float2* Z1 = sm + MP;
     float2* Z2 = sm + 2 * MP;
@@ -840,7 +840,7 @@ const char* scdev_error_string(int err) { return cudaGetErrorString((cudaError_t
 
 static size_t fft_smem(const scdev_plan* pl, int nbuf)
 {
-    return ((size_t)nbuf * (pl->M + SC_PAD) + sc_split_len(pl->M)) * sizeof(float2);
+    return ((size_t)nbuf * SC_ALEN(pl->M) + sc_split_len(pl->M)) * sizeof(float2);
 }
 
 typedef void (*mac_fn_t)(MacArgs);
@@ -1015,7 +1015,7 @@ int scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in,
 static size_t small_smem(const scdev_plan* pl, int threads)
 {
     const int G = threads >= pl->M ? threads / pl->M : 1;
-    return ((size_t)pl->nIn * (pl->M + SC_PAD) + (size_t)pl->nIn * pl->M + pl->M + sc_split_len(pl->M)
+    return ((size_t)pl->nIn * SC_ALEN(pl->M) + (size_t)pl->nIn * pl->M + pl->M + sc_split_len(pl->M)
             + (G > 1 ? (size_t)G * pl->M : 0)) * sizeof(float2);
 }
 

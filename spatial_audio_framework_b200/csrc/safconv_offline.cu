@@ -100,7 +100,7 @@ __global__ void offline_pack_filters_kernel(PackArgs a)
 /* ------------------------------------------------------------------------------------------ */
 /*  A operand: XG[hi|lo][bin][kg][row][4], row = (P-1) + frame (P-1 leading zero rows = silence    */
 /*  before the first frame), the 4 floats = (re, im) of inputs 2kg and 2kg+1                      */
-/*  grid (ceil(nIn/2), rowsAlloc / OFF_FPC)                                                       */
+/*  grid (rows / FPC, ceil(nIn/2))                                                                */
 /* ------------------------------------------------------------------------------------------ */
 struct OffFftArgs {
     const float* in;       /* [nIn][T*hop] */
@@ -108,33 +108,56 @@ struct OffFftArgs {
     const float2* tw;
     size_t inStride;       /* T*hop */
     int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
+    int fpc;               /* frames per CTA (2 or 4): 32- or 64-byte contiguous operand stores */
 };
 
 __global__ void offline_fft_kernel(OffFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const int MP = a.M + SC_PAD;                       /* padded FFT work arrays */
-    float2* stw = sm + (size_t)(2 * OFF_FPC) * MP;
-    const int kg = blockIdx.x;
-    const int row0 = blockIdx.y * OFF_FPC;
+    const int MP = SC_ALEN(a.M);                       /* padded FFT work arrays */
+    const int FPC = a.fpc;
+    float2* stw = sm + (size_t)(2 * FPC) * MP;
+    /* blockIdx.x walks along the frames: CTAs that run at the same time store ADJACENT 32/64-byte pieces of the
+     * same operand rows, so L2 merges them into full lines and DRAM sees long bursts (the first version had the
+     * input pair on x and was bound by scattered 64-byte DRAM writes, not by the FFT) */
+    const int kg = blockIdx.y;
+    const int row0 = blockIdx.x * FPC;
     load_twiddles(stw, a.tw, a.M, a.logM);
     const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
-    for (int q = 0; q < 2 * OFF_FPC; ++q) {            /* q = 2*f + j : frame f, input 2kg+j */
-        const int ni = 2 * kg + (q & 1);
-        const int t = row0 + (q >> 1) - (a.P - 1);
-        float2* s = sm + (size_t)q * MP;
-        if (ni < a.nIn && t >= 0 && t < a.T) {
-            load_real_block(s, a.in + (size_t)ni * a.inStride + (size_t)t * a.hop, a.hop, a.M, a.logM);
-        } else {
-            for (int n = threadIdx.x; n < MP; n += blockDim.x) s[n] = make_float2(0.f, 0.f);
+    /* input blocks of the 2*FPC transforms (q = 2*f + j : frame f, input 2kg+j): for every chunk of samples the
+     * loads of ALL transforms are issued before the first store, so one DRAM round trip covers the whole batch */
+    {
+        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0) && ((a.inStride & 1) == 0);
+        for (int n0 = 0; n0 < a.M; n0 += blockDim.x) {
+            const int n = n0 + threadIdx.x;
+            float2 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                v[q] = make_float2(0.f, 0.f);
+                if (q < 2 * FPC && n < a.M) {
+                    const int ni = 2 * kg + (q & 1);
+                    const int t = row0 + (q >> 1) - (a.P - 1);
+                    if (ni < a.nIn && t >= 0 && t < a.T) {
+                        const float* x = a.in + (size_t)ni * a.inStride + (size_t)t * a.hop;
+                        if (vec) { if (2 * n < a.hop) v[q] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                        else {
+                            if (2 * n < a.hop)     v[q].x = __ldg(x + 2 * n);
+                            if (2 * n + 1 < a.hop) v[q].y = __ldg(x + 2 * n + 1);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < 2 * FPC && n < a.M) sm[(size_t)q * MP + padi(n, a.logM)] = v[q];
         }
     }
     __syncthreads();
-    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * OFF_FPC);
+    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * FPC);
 
     const int half = a.M >> 1;
-    for (int idx = threadIdx.x; idx < (half + 1) * OFF_FPC; idx += blockDim.x) {
-        const int f = idx % OFF_FPC, k = idx / OFF_FPC;
+    for (int idx = threadIdx.x; idx < (half + 1) * FPC; idx += blockDim.x) {
+        const int f = idx & (FPC - 1), k = idx / FPC;
         const float2* s0 = sm + (size_t)(2 * f) * MP;
         const float2* s1 = s0 + MP;
         float2 x0, x0m, x1, x1m;
@@ -416,6 +439,7 @@ struct OffIfftArgs {
     float* out;            /* [nOut][T*hop] */
     const float2* tw;
     int hop, M, logM, nOut, Nn2, Tpad, T;
+    int opc;               /* outputs per inverse-FFT CTA (4 or 8): 32- or 64-byte contiguous spectrum loads */
     int skip;              /* leading halo frames that are transformed but not written to `out` */
     float scale;
 };
@@ -423,24 +447,40 @@ struct OffIfftArgs {
 __global__ void offline_ifft_kernel(OffIfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const int MP = a.M + SC_PAD;
-    float2* stw = sm + (size_t)OFF_OPC * MP;
+    const int MP = SC_ALEN(a.M);
+    const int OPC = a.opc;
+    float2* stw = sm + (size_t)OPC * MP;
     const int og = blockIdx.x, t = blockIdx.y;
     load_twiddles(stw, a.tw, a.M, a.logM);
     const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
-    for (int idx = threadIdx.x; idx < a.M * OFF_OPC; idx += blockDim.x) {
-        const int j = idx & (OFF_OPC - 1), k = idx / OFF_OPC;
-        const int no = og * OFF_OPC + j;
-        sm[(size_t)j * MP + padi(k, a.logM)] = (no < a.nOut) ? a.Ys[((size_t)k * a.Tpad + t) * a.Nn2 + no] : make_float2(0.f, 0.f);
+    /* spectra of the OPC outputs of this frame: eight independent loads in flight per thread */
+    {
+        const int logOPC = (OPC == 8) ? 3 : 2;
+        const int total = a.M << logOPC;
+        for (int base = threadIdx.x; base < total; base += 8 * blockDim.x) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * blockDim.x;
+                const int j = idx & (OPC - 1), k = idx >> logOPC;
+                const int no = og * OPC + j;
+                v[u] = (idx < total && no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) sm[(size_t)(idx & (OPC - 1)) * MP + padi(idx >> logOPC, a.logM)] = v[u];
+            }
+        }
     }
     __syncthreads();
     {
-        const int nArr = min(OFF_OPC, a.nOut - og * OFF_OPC);
+        const int nArr = min(OPC, a.nOut - og * OPC);
         inv_split_batch(sm, a.M, a.logM, spl, nArr);
         cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
     }
-    for (int j = 0; j < OFF_OPC; ++j) {
-        const int no = og * OFF_OPC + j;
+    for (int j = 0; j < OPC; ++j) {
+        const int no = og * OPC + j;
         if (no >= a.nOut) break;
         float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
         const float2* s = sm + (size_t)j * MP;
@@ -503,6 +543,9 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         const char* v = getenv("SAFCONV_OFF_FLUSH");
         int fl = v ? atoi(v) : 1;
         o->flush = fl < 1 ? 1 : fl;
+        v = getenv("SAFCONV_OFF_FPC");      o->fpc = (v && atoi(v) == 2) ? 2 : 4;
+        v = getenv("SAFCONV_OFF_OPC");      o->opc = (v && atoi(v) == 8) ? 8 : 4;
+        v = getenv("SAFCONV_OFF_THREADS");  o->fftThreads = (v && atoi(v) == 128) ? 128 : 256;
     }
     if (!o->packed) {
         const size_t hgFloats = (size_t)pl->M * pl->P * o->nKG * Nn * 4;
@@ -518,7 +561,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         offline_pack_filters_kernel<<<148 * 8, 256, 0, st>>>(a);
         SC_CHECK(cudaGetLastError());
         SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        const int fftSmem = (2 * OFF_FPC + 1) * (pl->M + SC_PAD) * 8, ifftSmem = (OFF_OPC + 1) * (pl->M + SC_PAD) * 8;
+        const int fftSmem = (2 * OFF_FPC + 1) * SC_ALEN(pl->M) * 8, ifftSmem = (OFF_OPC + 1) * SC_ALEN(pl->M) * 8;
         if (fftSmem > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
         SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem));
         SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ifftSmem));
@@ -561,8 +604,9 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
     {
-        dim3 grid((pl->nIn + 1) / 2, rowsUsed / OFF_FPC);
-        offline_fft_kernel<<<grid, 256, (size_t)(2 * OFF_FPC + 1) * (pl->M + SC_PAD) * 8, st>>>(f);
+        f.fpc = o->fpc;
+        dim3 grid(rowsUsed / o->fpc, (pl->nIn + 1) / 2);
+        offline_fft_kernel<<<grid, o->fftThreads, (size_t)(2 * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[1], st));
@@ -581,8 +625,9 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
     i.Tpad = o->capTpad; i.T = T; i.skip = skip; i.scale = 1.0f / (float)pl->N;
     {
-        dim3 grid((pl->nOutLocal + OFF_OPC - 1) / OFF_OPC, T);
-        offline_ifft_kernel<<<grid, 256, (size_t)(OFF_OPC + 1) * (pl->M + SC_PAD) * 8, st>>>(i);
+        i.opc = o->opc;
+        dim3 grid((pl->nOutLocal + o->opc - 1) / o->opc, T);
+        offline_ifft_kernel<<<grid, o->fftThreads, (size_t)(o->opc + 1) * SC_ALEN(pl->M) * 8, st>>>(i);
         SC_CHECK(cudaGetLastError());
         offline_ola_kernel<<<148 * 8, 256, 0, st>>>(i);
         SC_CHECK(cudaGetLastError());
