@@ -77,7 +77,6 @@ typedef struct scdev_offline {
     float *XGhi, *XGlo;      /* A operand  [bin][kg][rows][4]  (frames x (input, re/im)), tf32 hi / lo parts   */
     float *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][4] ((output, re/im) x (input, re/im))               */
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
-    float *zt;               /* inverse transforms [T][nOut][2*hop]                                             */
     int capFrames, capTpad, capRows, packed;
     int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush, fpc, opc, fftThreads;
 } scdev_offline;

@@ -28,8 +28,8 @@
  * Kernels:  offline_pack_filters_kernel  H spectra (streaming layout) -> B operand hi/lo       (once per handle)
  *           offline_fft_kernel           forward real FFT of all frames -> A operand hi/lo
  *           offline_gemm_kernel          the tcgen05 GEMM, one CTA per (256-frame tile, bin)
- *           offline_ifft_kernel          inverse real FFT per (frame, output)
- *           offline_ola_kernel           overlap-add of consecutive frames (reference .c:230-233)
+ *           offline_ifft_kernel          inverse real FFT per (frame, output) + overlap-add into the output signal
+ *                                        (reference .c:230-233)
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -435,8 +435,7 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
 /* ------------------------------------------------------------------------------------------ */
 struct OffIfftArgs {
     const float2* Ys;      /* [bin][Tpad][Nn/2] complex */
-    float* zt;             /* [T][nOut][2*hop] */
-    float* out;            /* [nOut][T*hop] */
+    float* out;            /* [nOut][(T-skip)*hop], zeroed before the launch */
     const float2* tw;
     int hop, M, logM, nOut, Nn2, Tpad, T;
     int opc;               /* outputs per inverse-FFT CTA (4 or 8): 32- or 64-byte contiguous spectrum loads */
@@ -479,31 +478,20 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
         inv_split_batch(sm, a.M, a.logM, spl, nArr);
         cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
     }
+    /* overlap-add (reference .c:230-233) straight into the output signal: out[frame t] += z[0:hop],
+     * out[frame t+1] += z[hop:2hop].  `out` is zeroed beforehand and every sample receives exactly two addends
+     * (one from each of two CTAs), so the atomic adds give a deterministic result: 0 + a + b == 0 + b + a. */
+    const int To = a.T - a.skip;
     for (int j = 0; j < OPC; ++j) {
         const int no = og * OPC + j;
         if (no >= a.nOut) break;
-        float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
         const float2* s = sm + (size_t)j * MP;
-        for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(s, i, a.logM) * a.scale;
-    }
-}
-
-/* out[no][(t-skip)*hop + i] = z_t[i] + z_{t-1}[hop + i]  for frames t >= skip (zero state before frame 0) */
-__global__ void offline_ola_kernel(OffIfftArgs a)
-{
-    const int To = a.T - a.skip;                           /* frames written */
-    const size_t n = (size_t)To * a.nOut * a.hop;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        const int i = (int)(e % a.hop);
-        size_t r = e / a.hop;
-        const int to = (int)(r % To);
-        const int no = (int)(r / To);
-        const int t = to + a.skip;
-        const float* z = a.zt + ((size_t)t * a.nOut + no) * 2 * a.hop;
-        float v = z[i];
-        if (t > 0) v += a.zt[((size_t)(t - 1) * a.nOut + no) * 2 * a.hop + a.hop + i];
-        a.out[(size_t)no * To * a.hop + (size_t)to * a.hop + i] = v;
+        float* o = a.out + (size_t)no * To * a.hop;
+        const int f0 = t - a.skip, f1 = t + 1 - a.skip;           /* output frames fed by the two halves */
+        for (int i = threadIdx.x; i < a.hop; i += blockDim.x) {
+            if (f0 >= 0)            atomicAdd(o + (size_t)f0 * a.hop + i, time_sample(s, i, a.logM) * a.scale);
+            if (f1 >= 0 && f1 < To) atomicAdd(o + (size_t)f1 * a.hop + i, time_sample(s, i + a.hop, a.logM) * a.scale);
+        }
     }
 }
 
@@ -517,8 +505,8 @@ static size_t roundup(size_t v, size_t m) { return (v + m - 1) / m * m; }
 int scdev_offline_free(scdev_offline* o)
 {
     if (!o) return 0;
-    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys); cudaFree(o->zt);
-    o->XGhi = o->XGlo = o->HGhi = o->HGlo = o->Ys = o->zt = NULL;
+    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys);
+    o->XGhi = o->XGlo = o->HGhi = o->HGlo = o->Ys = NULL;
     o->capFrames = 0; o->packed = 0;
     return 0;
 }
@@ -569,15 +557,14 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
     }
     if (T > o->capFrames) {
         SC_CHECK(cudaStreamSynchronize(st));
-        cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->Ys); cudaFree(o->zt);
-        o->XGhi = o->XGlo = o->Ys = o->zt = NULL; o->capFrames = 0;
+        cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->Ys);
+        o->XGhi = o->XGlo = o->Ys = NULL; o->capFrames = 0;
         const size_t Tpad = roundup((size_t)T, OFF_MT);
         const size_t rowsAlloc = roundup(Tpad + pl->P - 1, OFF_FPC);
         const size_t xgFloats = (size_t)pl->M * o->nKG * rowsAlloc * 4;
         SC_CHECK(cudaMalloc((void**)&o->XGhi, xgFloats * sizeof(float)));
         SC_CHECK(cudaMalloc((void**)&o->XGlo, xgFloats * sizeof(float)));
         SC_CHECK(cudaMalloc((void**)&o->Ys, (size_t)pl->M * Tpad * Nn * sizeof(float)));
-        SC_CHECK(cudaMalloc((void**)&o->zt, (size_t)T * pl->nOutLocal * 2 * pl->hop * sizeof(float)));
         /* padding k-groups (odd nIn / K padding) are never written by the FFT kernel: zero them once */
         SC_CHECK(cudaMemsetAsync(o->XGhi, 0, xgFloats * sizeof(float), st));
         SC_CHECK(cudaMemsetAsync(o->XGlo, 0, xgFloats * sizeof(float), st));
@@ -621,15 +608,14 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[2], st));
     OffIfftArgs i;
-    i.Ys = (const float2*)o->Ys; i.zt = o->zt; i.out = d_out; i.tw = (const float2*)b->tw;
+    i.Ys = (const float2*)o->Ys; i.out = d_out; i.tw = (const float2*)b->tw;
     i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
     i.Tpad = o->capTpad; i.T = T; i.skip = skip; i.scale = 1.0f / (float)pl->N;
     {
         i.opc = o->opc;
         dim3 grid((pl->nOutLocal + o->opc - 1) / o->opc, T);
+        SC_CHECK(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)pl->nOutLocal * (T - skip) * pl->hop, st));
         offline_ifft_kernel<<<grid, o->fftThreads, (size_t)(o->opc + 1) * SC_ALEN(pl->M) * 8, st>>>(i);
-        SC_CHECK(cudaGetLastError());
-        offline_ola_kernel<<<148 * 8, 256, 0, st>>>(i);
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[3], st));
