@@ -112,7 +112,7 @@ __device__ __forceinline__ void final_pass(float2* s, const int M, const int log
 }
 
 template <bool INV>
-__device__ void cfft_dif_batch(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
+__device__ void cfft_dif_batch_wide(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     int logL = logM, off = 0;
@@ -149,16 +149,142 @@ __device__ void cfft_dif_batch(float2* s, const int M, const int logM, const flo
     else if (logL == 3) final_pass<8, INV>(s, M, logM, nArr);
 }
 
+/* ---- "narrow" core: radix-4 / radix-2 passes through shared memory (4 points per thread per pass) and the last
+ * five stages as warp-shuffle butterflies.  More barriers and more instructions per point than the register
+ * radix-16 passes, but M/4 threads work on one transform -- the better choice when a CTA owns a single transform
+ * (the block-latency kernels K1 / K3 / multiConv / TVConv).  Its per-pass tables: W_L^j then W_L^2j for every
+ * radix-4 pass, W_L^j for the radix-2 pass, W_32^j (j < 16) for the shuffle stages. ---- */
 template <bool INV>
-__device__ __forceinline__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw)
+__device__ __forceinline__ float2 twd(const float2* __restrict__ tw, int idx)
 {
-    cfft_dif_batch<INV>(s, M, logM, tw, 1);
+    float2 w = tw[idx];
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+template <bool INV>
+__device__ void cfft_dif_batch_narrow(float2* s, const int M, const int logM, const float2* __restrict__ tw, const int nArr)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    int L = M;                 /* current sub-transform length */
+    int nsm = logM - 5;        /* radix-2 stages done through shared memory (spans M/2 .. 32) */
+    int off = 0;               /* start of this pass's twiddle table inside tw (see load_twiddles) */
+
+    /* two radix-2 stages fused per pass */
+    while (nsm >= 2) {
+        const int q = L >> 2;
+        const int per = M >> 2;                    /* butterflies per transform */
+        for (int it = tid; it < nArr * per; it += T) {
+            const int arr = it >> (logM - 2), i = it & (per - 1);
+            float2* sa = s + (size_t)arr * SC_ALEN(M);
+            const int j = i & (q - 1);
+            const int base = ((i - j) << 2) + j;
+            const int i0 = padi(base, logM), i1 = padi(base + q, logM), i2 = padi(base + 2 * q, logM), i3 = padi(base + 3 * q, logM);
+            const float2 a0 = sa[i0], a1 = sa[i1], a2 = sa[i2], a3 = sa[i3];
+            const float2 w1 = twd<INV>(tw, off + j);         /* W_L^j  */
+            const float2 w2 = twd<INV>(tw, off + q + j);     /* W_L^2j */
+            const float2 u0 = caddf(a0, a2);
+            const float2 u1 = caddf(a1, a3);
+            const float2 v0 = cmulf(csubf(a0, a2), w1);
+            float2 d1 = csubf(a1, a3);
+            /* W_L^(j+L/4) = W_L^j * (-i) forward, * (+i) inverse */
+            d1 = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
+            const float2 v1 = cmulf(d1, w1);
+            sa[i0] = caddf(u0, u1);
+            sa[i1] = cmulf(csubf(u0, u1), w2);
+            sa[i2] = caddf(v0, v1);
+            sa[i3] = cmulf(csubf(v0, v1), w2);
+        }
+        __syncthreads();
+        off += 2 * q;
+        L >>= 2;
+        nsm -= 2;
+    }
+    if (nsm == 1) {
+        const int half = L >> 1;
+        const int per = M >> 1;
+        for (int it = tid; it < nArr * per; it += T) {
+            const int arr = it >> (logM - 1), i = it & (per - 1);
+            float2* sa = s + (size_t)arr * SC_ALEN(M);
+            const int j = i & (half - 1);
+            const int base = ((i - j) << 1) + j;
+            const int i0 = padi(base, logM), i1 = padi(base + half, logM);
+            const float2 a = sa[i0], b = sa[i1];
+            const float2 w = twd<INV>(tw, off + j);
+            sa[i0] = caddf(a, b);
+            sa[i1] = cmulf(csubf(a, b), w);
+        }
+        __syncthreads();
+        off += half;
+        L >>= 1;
+    }
+    /* L == 32: the last five stages (spans 16,8,4,2,1) stay inside one warp; rows of 32 points of all
+     * transforms are contiguous, so the batch is just more rows.
+     * Branch-free butterflies: lane l (partner l^h) computes  t = o + sg*v  (lower half: v+o, upper half: o-v)
+     * and multiplies by its own per-lane factor (1 in the lower half, the twiddle in the upper half). */
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+        const float2 one = make_float2(1.f, 0.f);
+        /* tw + off : the 16-entry table W_32^j, j < 16 */
+        const float2 w16 = (lane & 16) ? twd<INV>(tw, off + (lane & 15))     : one;
+        const float2 w8  = (lane & 8)  ? twd<INV>(tw, off + 2 * (lane & 7)) : one;
+        const float2 w4  = (lane & 4)  ? twd<INV>(tw, off + 4 * (lane & 3)) : one;
+        const float2 w2  = (lane & 2)  ? twd<INV>(tw, off + 8 * (lane & 1)) : one;
+        const float s16 = (lane & 16) ? -1.f : 1.f, s8 = (lane & 8) ? -1.f : 1.f, s4 = (lane & 4) ? -1.f : 1.f,
+                    s2 = (lane & 2) ? -1.f : 1.f, s1 = (lane & 1) ? -1.f : 1.f;
+        for (int row = warp; row < nArr * (M >> 5); row += nwarps) {
+            const int arr = row >> (logM - 5), rr = row & ((M >> 5) - 1);
+            float2* sp = s + (size_t)arr * SC_ALEN(M) + padi(rr * 32 + lane, logM);
+            float2 v = *sp;
+#define SC_SHFL_STAGE(HALF, SG, W)                                                   \
+            {                                                                        \
+                const float ox = __shfl_xor_sync(0xffffffffu, v.x, HALF);            \
+                const float oy = __shfl_xor_sync(0xffffffffu, v.y, HALF);            \
+                const float tx = fmaf(SG, v.x, ox), ty = fmaf(SG, v.y, oy);          \
+                v.x = tx * W.x - ty * W.y;                                           \
+                v.y = tx * W.y + ty * W.x;                                           \
+            }
+            SC_SHFL_STAGE(16, s16, w16)
+            SC_SHFL_STAGE(8,  s8,  w8)
+            SC_SHFL_STAGE(4,  s4,  w4)
+            SC_SHFL_STAGE(2,  s2,  w2)
+#undef SC_SHFL_STAGE
+            {   /* span 1: twiddle is 1 */
+                const float ox = __shfl_xor_sync(0xffffffffu, v.x, 1);
+                const float oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
+                v.x = fmaf(s1, v.x, ox);
+                v.y = fmaf(s1, v.y, oy);
+            }
+            *sp = v;
+        }
+        __syncthreads();
+    }
+}
+
+
+/* which core a CTA uses: register radix-16 passes when the batch gives every thread at least one 16-point
+ * butterfly per pass, else the narrow core.  A kernel decides ONCE (nArr = the smallest batch it transforms) and
+ * hands the same `wide` to load_twiddles() and to every cfft_dif*() call: the two cores use different tables. */
+__device__ __forceinline__ bool fft_use_wide(int M, int nArr) { return nArr * (M >> 4) >= (int)blockDim.x; }
+
+template <bool INV>
+__device__ __forceinline__ void cfft_dif_batch(float2* s, const int M, const int logM, const float2* __restrict__ tw,
+                                               const int nArr, const bool wide)
+{
+    if (wide) cfft_dif_batch_wide<INV>(s, M, logM, tw, nArr);
+    else      cfft_dif_batch_narrow<INV>(s, M, logM, tw, nArr);
+}
+
+template <bool INV>
+__device__ __forceinline__ void cfft_dif(float2* s, const int M, const int logM, const float2* __restrict__ tw, const bool wide)
+{
+    cfft_dif_batch<INV>(s, M, logM, tw, 1, wide);
 }
 
 /* Build the per-pass twiddle tables of cfft_dif_batch in shared memory (fewer than M float2 in total): for every
  * radix-16 pass of sub-length L > 16 the table W_L^(j*q) at [(q-1)*(L/16) + j], q = 1..15, j < L/16, taken from the
  * global table gtw[e] = exp(-2 pi i e / 2M), e < M  (W_L^x = W_2M^(x * 2M/L); the upper half by W^(M+e) = -W^e). */
-__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M, int logM)
+__device__ __forceinline__ void load_twiddles_wide(float2* stw, const float2* __restrict__ gtw, int M, int logM)
 {
     int logL = logM, off = 0;
     while (logL >= 4) {
@@ -176,6 +302,33 @@ __device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restr
         }
         logL -= 4;
     }
+}
+
+__device__ __forceinline__ void load_twiddles_narrow(float2* stw, const float2* __restrict__ gtw, int M, int logM)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    int L = M, nsm = logM - 5, off = 0;
+    while (nsm >= 2) {
+        const int q = L >> 2, tstr = (2 * M) / L;
+        for (int j = tid; j < q; j += T) {
+            stw[off + j]     = __ldg(gtw + j * tstr);
+            stw[off + q + j] = __ldg(gtw + 2 * j * tstr);
+        }
+        off += 2 * q; L >>= 2; nsm -= 2;
+    }
+    if (nsm == 1) {
+        const int half = L >> 1, tstr = (2 * M) / L;
+        for (int j = tid; j < half; j += T) stw[off + j] = __ldg(gtw + j * tstr);
+        off += half;
+    }
+    if (tid < 16) stw[off + tid] = __ldg(gtw + tid * (M >> 4));
+}
+
+
+__device__ __forceinline__ void load_twiddles(float2* stw, const float2* __restrict__ gtw, int M, int logM, bool wide)
+{
+    if (wide) load_twiddles_wide(stw, gtw, M, logM);
+    else      load_twiddles_narrow(stw, gtw, M, logM);
 }
 
 /* The real-FFT split passes need W_N^k, k <= M/2 (unit stride).  For M <= 4096 the kernels keep a copy in shared

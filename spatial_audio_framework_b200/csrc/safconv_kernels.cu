@@ -46,7 +46,8 @@ __global__ void filter_fft_kernel(FilterArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     float2* stw = sm + SC_ALEN(a.M);
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
     const float* src;
@@ -62,7 +63,7 @@ __global__ void filter_fft_kernel(FilterArgs a)
         sm[padi(n, a.logM)] = v;
     }
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, stw);
+    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
 
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
@@ -109,11 +110,12 @@ __global__ void input_fft_kernel(InFftArgs a)
     float2* stw = sm + SC_ALEN(a.M);
     const int ni = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     load_real_block(sm, a.in + ((size_t)b * a.nIn + ni) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, stw);
+    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
         int k2 = a.M - k;
@@ -320,7 +322,8 @@ struct IfftArgs {
 __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2* Zp, int no, float2* sm, float2* stw)
 {
     const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
         const int g = ot * a.nKT + (k >> 5);
@@ -339,7 +342,7 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
     }
     __syncthreads();
     inv_split_all(sm, a.M, a.logM, spl);
-    cfft_dif<true>(sm, a.M, a.logM, stw);
+    cfft_dif<true>(sm, a.M, a.logM, stw, wide);
 }
 
 /* one block: grid (nOutLocal) */
@@ -430,11 +433,12 @@ __global__ void multi_fused_kernel(MultiArgs a)
     float2* Xc = a.X + (size_t)c * a.RS * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
 
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     load_real_block(A, a.in + (size_t)c * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
-    cfft_dif<false>(A, a.M, a.logM, stw);
+    cfft_dif<false>(A, a.M, a.logM, stw, wide);
     float2* Xnew = Xc + (size_t)head * a.M;
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
@@ -465,7 +469,7 @@ __global__ void multi_fused_kernel(MultiArgs a)
     }
     __syncthreads();
     inv_split_all(A, a.M, a.logM, spl);
-    cfft_dif<true>(A, a.M, a.logM, stw);
+    cfft_dif<true>(A, a.M, a.logM, stw, wide);
     ola_store(A, a.hop, a.logM, a.scale, a.out + (size_t)c * a.hop, a.tail + (size_t)c * a.hop);
     advance_block_counter(a.counters, gridDim.x);
 }
@@ -480,11 +484,12 @@ __global__ void multi_fft_batch_kernel(MultiArgs a)
     float2* stw = sm + SC_ALEN(a.M);
     const int c = blockIdx.x, b = blockIdx.y;
     const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     load_real_block(sm, a.in + ((size_t)b * a.nCH + c) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, stw);
+    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
     float2* Xnew = a.X + ((size_t)c * a.RS + slot) * a.M;
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
@@ -509,7 +514,8 @@ __global__ void multi_mac_ifft_batch_kernel(MultiArgs a)
     const int head = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
     const float2* Xc = a.X + (size_t)c * a.RS * a.M;
     const float2* Hc = a.H + (size_t)c * a.P * a.M;
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
         const bool packed = (k == 0);
@@ -524,7 +530,7 @@ __global__ void multi_mac_ifft_batch_kernel(MultiArgs a)
     }
     __syncthreads();
     inv_split_all(sm, a.M, a.logM, spl);
-    cfft_dif<true>(sm, a.M, a.logM, stw);
+    cfft_dif<true>(sm, a.M, a.logM, stw, wide);
     float* z = a.zt + ((size_t)b * a.nCH + c) * 2 * a.hop;
     for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
 }
@@ -597,10 +603,11 @@ __global__ void small_fused_kernel(SmallArgs a)
             }
         }
     }
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     __syncthreads();
-    cfft_dif_batch<false>(W, a.M, a.logM, stw, a.nIn);
+    cfft_dif_batch<false>(W, a.M, a.logM, stw, a.nIn, wide);
     {
         const int per = (a.M >> 1) + 1;
         for (int it = tid; it < a.nIn * per; it += T) {
@@ -661,7 +668,7 @@ __global__ void small_fused_kernel(SmallArgs a)
     }
     __syncthreads();
     inv_split_all(W, a.M, a.logM, spl);
-    cfft_dif<true>(W, a.M, a.logM, stw);
+    cfft_dif<true>(W, a.M, a.logM, stw, wide);
     {   /* overlap-add (reference .c:230-233) */
         float* out = a.out + (size_t)no * a.hop;
         float* tail = a.tail + (size_t)no * a.hop;
@@ -709,7 +716,8 @@ __global__ void tv_fused_kernel(TvArgs a)
     float2* Z2 = sm + 2 * MP;
     float2* Xs = sm + 3 * MP;        /* packed spectrum of the new block, natural order */
     float2* stw = Xs + a.M;
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
     const int no = blockIdx.x;
     const int head = (int)(a.counters[0] % (unsigned)a.P);
@@ -719,7 +727,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     /* every CTA transforms the (single) input block; CTA 0 also stores it in the ring */
     load_real_block(Z0, a.in, a.hop, a.M, a.logM);
     __syncthreads();
-    cfft_dif<false>(Z0, a.M, a.logM, stw);
+    cfft_dif<false>(Z0, a.M, a.logM, stw, wide);
     for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
         float2 Xk, Xmk;
         int k2 = a.M - k;
@@ -759,7 +767,7 @@ __global__ void tv_fused_kernel(TvArgs a)
     }
     __syncthreads();
     inv_split_batch(Z0, a.M, a.logM, spl, 3);           /* Z0, Z1, Z2 are contiguous */
-    cfft_dif_batch<true>(Z0, a.M, a.logM, stw, 3);
+    cfft_dif_batch<true>(Z0, a.M, a.logM, stw, 3, wide);
     /* cross-fade (reference .c:494-497, 605-615) */
     float* t0 = a.tail0 + (size_t)no * a.hop;
     float* t1 = a.tail1 + (size_t)no * a.hop;

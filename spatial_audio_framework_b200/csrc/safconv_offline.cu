@@ -122,7 +122,8 @@ __global__ void offline_fft_kernel(OffFftArgs a)
      * input pair on x and was bound by scattered 64-byte DRAM writes, not by the FFT) */
     const int kg = blockIdx.y;
     const int row0 = blockIdx.x * FPC;
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, 2 * FPC);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
     /* input blocks of the 2*FPC transforms (q = 2*f + j : frame f, input 2kg+j): for every chunk of samples the
      * loads of ALL transforms are issued before the first store, so one DRAM round trip covers the whole batch */
@@ -153,7 +154,7 @@ __global__ void offline_fft_kernel(OffFftArgs a)
         }
     }
     __syncthreads();
-    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * FPC);
+    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * FPC, wide);
 
     const int half = a.M >> 1;
     for (int idx = threadIdx.x; idx < (half + 1) * FPC; idx += blockDim.x) {
@@ -450,7 +451,8 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     const int OPC = a.opc;
     float2* stw = sm + (size_t)OPC * MP;
     const int og = blockIdx.x, t = blockIdx.y;
-    load_twiddles(stw, a.tw, a.M, a.logM);
+    const bool wide = fft_use_wide(a.M, OPC);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
     /* spectra of the OPC outputs of this frame: eight independent loads in flight per thread */
     {
@@ -476,7 +478,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     {
         const int nArr = min(OPC, a.nOut - og * OPC);
         inv_split_batch(sm, a.M, a.logM, spl, nArr);
-        cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr);
+        cfft_dif_batch<true>(sm, a.M, a.logM, stw, nArr, wide);
     }
     /* overlap-add (reference .c:230-233) straight into the output signal: out[frame t] += z[0:hop],
      * out[frame t+1] += z[hop:2hop].  `out` is zeroed beforehand and every sample receives exactly two addends
