@@ -56,6 +56,19 @@ typedef struct scdev_plan {
     int nIRs;
 } scdev_plan;
 
+/* one pass of the MAC over partitions [pLo, pLo + nP) of every group, with its own split-K bookkeeping and
+ * partial-tile buffer.  The full pass (0, P) lives in scdev_plan / scdev_bufs; the host layer adds a TAIL pass
+ * (1, P-1) -- everything that does not depend on the newest input block, run AHEAD of the next apply -- and a
+ * HEAD pass (0, 1) for the newest block only. */
+typedef struct scdev_macpass {
+    int pLo, nP;
+    long long totalStages;   /* nGroups * nP * SPU */
+    int grid, nSlots;
+    int*  ctaBase;           /* device int[grid+1]      */
+    int*  grpStart;          /* device int[nGroups+1]   */
+    void* Zp;                /* device float2[nSlots][OTsz][32] */
+} scdev_macpass;
+
 typedef struct scdev_bufs {
     /* all device pointers */
     void*  tw;        /* float2[M]        W_N^j                                            */
@@ -99,6 +112,8 @@ int  scdev_stream_destroy(void* s);
 int  scdev_stream_sync(void* s);
 int  scdev_event_create(void** e);
 int  scdev_event_destroy(void* e);
+int  scdev_event_create_sync(void** e);          /* no timing: cheapest to record / wait on */
+int  scdev_stream_wait_event(void* stream, void* e);
 int  scdev_event_record(void* e, void* stream);
 int  scdev_event_sync(void* e);
 int  scdev_event_elapsed_ms(void* e0, void* e1, float* ms);
@@ -119,8 +134,13 @@ int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_i
 /* K2: filter-streaming complex multiply-accumulate over partitions x inputs for blocks blk .. blk+nBlocks-1 of
  * the batch, streamed back to back inside ONE launch (every block streams the filter spectra once) */
 int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, void* stream);
+/* K2 restricted to one pass (see scdev_macpass) */
+int  scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks, void* stream);
 /* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ (one block) */
 int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
+/* K3 summing the partial tiles of pass p1 then pass p2 (NULL, NULL = the full pass) */
+int  scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, const scdev_macpass* p2,
+                           float* d_out, void* stream);
 /* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */
 int  scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream);
 /* offline path: allocate / grow the workspace for T frames (and build the filter operand on first use),

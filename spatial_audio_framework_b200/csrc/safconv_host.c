@@ -49,6 +49,15 @@ typedef struct safconv_handle {
     scdev_offline off;               /* offline (batched frames) workspace, allocated on first use */
     void*      offEv[4];
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
+    /* look-ahead (matrix, P >= 2): all partitions p >= 1 of block t+1 only need spectra that are already in the
+     * delay line when block t is done, so that TAIL pass is enqueued right behind block t and runs while the host
+     * is away; saf_matrixConv_apply(t+1) then only pays for the newest partition (HEAD pass) */
+    scdev_macpass tailPass, headPass;
+    int        lookahead;            /* option: 1 = use the tail/head split in the host-pointer apply */
+    int        tailReady;            /* a tail pass for the current block counter is enqueued on `stream` */
+    void*      evDone;               /* recorded after the output of a block is complete: apply waits on it, not on the whole stream */
+    void*      streamIn;             /* side stream: the forward FFT of the new block runs beside the tail pass */
+    void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
 } safconv_handle;
 
 static __thread int  tl_err = 0;
@@ -161,10 +170,17 @@ static void plan_mac(scdev_plan* pl, int smCount)
 /* split-K bookkeeping: CTA c streams stages [c*T/G, (c+1)*T/G); every (ot,kt) group it touches gets
  * one partial tile.  ctaBase[c] = first partial slot of CTA c; grpStart/grpList = CSR list of the
  * partial slots that K3 sums for each group.  Returns the number of slots, or -1 on malloc failure. */
+static int build_split_tables_for(long long T, long long spg, int G, int nG, int** ctaBaseOut, int** grpStartOut, int** grpListOut);
+
 static int build_split_tables(const scdev_plan* pl, int** ctaBaseOut, int** grpStartOut, int** grpListOut)
 {
-    const long long T = pl->totalStages, spg = (long long)pl->P * pl->SPU;
-    const int G = pl->macGrid, nG = pl->nGroups;
+    return build_split_tables_for(pl->totalStages, (long long)pl->P * pl->SPU, pl->macGrid, pl->nGroups,
+                                  ctaBaseOut, grpStartOut, grpListOut);
+}
+
+/* T stages in total, spg stages per group, split evenly over G CTAs */
+static int build_split_tables_for(long long T, long long spg, int G, int nG, int** ctaBaseOut, int** grpStartOut, int** grpListOut)
+{
     int* ctaBase = (int*)malloc(sizeof(int) * (size_t)(G + 1));
     int* cnt     = (int*)calloc((size_t)nG + 1, sizeof(int));
     if (!ctaBase || !cnt) { free(ctaBase); free(cnt); return -1; }
@@ -240,6 +256,11 @@ static void handle_free(safconv_handle* h)
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
     scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart);
+    scdev_free(h->tailPass.ctaBase); scdev_free(h->tailPass.grpStart); scdev_free(h->tailPass.Zp);
+    scdev_free(h->headPass.ctaBase); scdev_free(h->headPass.grpStart); scdev_free(h->headPass.Zp);
+    if (h->streamIn) scdev_stream_sync(h->streamIn);
+    scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence);
+    scdev_stream_destroy(h->streamIn);
     scdev_free(h->d_in); scdev_free(h->d_out);
     scdev_host_free(h->h_in); scdev_host_free(h->h_out);
     scdev_stream_destroy(h->streamOwn);
@@ -263,6 +284,27 @@ static int zalloc(safconv_handle* h, void** dptr, size_t bytes, const char* what
     e = scdev_memset_async(*dptr, 0, bytes ? bytes : 16, h->stream);
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, what, e);
     return 0;
+}
+
+/* split-K tables + partial-tile buffer of the MAC pass over partitions [pLo, pLo + nP) */
+static int make_pass(safconv_handle* h, scdev_macpass* ps, int pLo, int nP)
+{
+    const scdev_plan* pl = &h->pl;
+    ps->pLo = pLo; ps->nP = nP;
+    ps->totalStages = (long long)pl->nGroups * nP * pl->SPU;
+    ps->grid = (ps->totalStages < h->smCount) ? (int)ps->totalStages : h->smCount;
+    int *ctaBase = NULL, *grpStart = NULL, *grpList = NULL;
+    const int slots = build_split_tables_for(ps->totalStages, (long long)nP * pl->SPU, ps->grid, pl->nGroups,
+                                             &ctaBase, &grpStart, &grpList);
+    if (slots < 0) return h_fail(h, SAFCONV_ERR_NOMEM, "split tables (pass)", 0);
+    ps->nSlots = slots;
+    int e = upload(h, (void**)&ps->ctaBase, ctaBase, sizeof(int) * (size_t)(ps->grid + 1), "ctaBase upload (pass)");
+    if (!e) e = upload(h, (void**)&ps->grpStart, grpStart, sizeof(int) * (size_t)(pl->nGroups + 1), "grpStart upload (pass)");
+    for (int q = 0; q < slots && !e; q++)
+        if (grpList[q] != q) e = h_fail(h, SAFCONV_ERR_ARG, "internal: split-K slot order (pass)", 0);
+    free(ctaBase); free(grpStart); free(grpList);
+    if (e) return e;
+    return zalloc(h, &ps->Zp, (size_t)slots * pl->OTsz * SC_BK * 8, "partial spectra allocation (pass)");
 }
 
 /* Common constructor.  `rows` time-domain FIRs of `len` taps are given as `nChunks` host chunks
@@ -352,6 +394,14 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         h->bytesH = (size_t)nIRs * nOutLocal * P * M * 8;
         h->bytesX = P * M * 8;
         rowsTotal = (size_t)nIRs * nOutLocal;
+    }
+    if (kind == SC_KIND_MATRIX && pl->P >= 2) {
+        if (make_pass(h, &h->tailPass, 1, pl->P - 1) || make_pass(h, &h->headPass, 0, 1)) goto fail;
+        DEV_TRY(h, scdev_event_create_sync(&h->evDone), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evIn), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evFence), "cudaEventCreate");
+        DEV_TRY(h, scdev_stream_create(&h->streamIn), "cudaStreamCreate");
+        h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
     }
     DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
     h->smallOk = (kind == SC_KIND_MATRIX) ? scdev_small_fits(pl, h->maxSmem) : 0;
@@ -498,6 +548,44 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
         }
         e = scdev_graph_launch(h->graphExec, h->stream);
     } else {
+        if (h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->timingCap) {
+            /* K1 -> HEAD pass (newest partition only; the TAIL pass of this block was enqueued behind the previous
+             * block) -> K3 over both partial lists -> [event] -> TAIL pass of the NEXT block.  The host waits for the
+             * event only: the next block's tail streams the filters while the caller is away.
+             * Blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers
+             * (no copy-engine round trips), and K1 runs on a side stream so that it overlaps a tail pass that is
+             * still streaming when the caller comes back early. */
+            const scdev_plan* pl = &h->pl;
+            const int zc = h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20);
+            if (zc) {
+                if (!h->tailReady) {          /* something else may still be running on `stream`: order K1 behind it */
+                    e = scdev_event_record(h->evFence, h->stream);
+                    if (!e) e = scdev_stream_wait_event(h->streamIn, h->evFence);
+                }
+                if (!e) e = scdev_input_fft(pl, &h->b, src, 1, h->streamIn);
+                if (!e) e = scdev_event_record(h->evIn, h->streamIn);
+                if (!e) e = scdev_stream_wait_event(h->stream, h->evIn);
+            } else {
+                e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
+                if (!e) e = scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream);
+            }
+            float* kout = zc ? dst : h->d_out;
+            if (h->tailReady) {
+                if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, h->stream);
+                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, &h->headPass, kout, h->stream);
+            } else {
+                if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream);
+                if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->stream);
+            }
+            h->tailReady = 0;
+            if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
+            if (!e) e = scdev_event_record(h->evDone, h->stream);
+            if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, h->stream);
+            if (!e) { h->tailReady = 1; e = scdev_event_sync(h->evDone); }
+            if (e) { h->tailReady = 0; h_fail(h, SAFCONV_ERR_CUDA, "apply (look-ahead)", e); return; }
+            if (!direct) memcpy(out, h->h_out, h->outBytes);
+            return;
+        }
         e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
         if (!e) {
             if (h->pl.kind == SC_KIND_TV) {
@@ -655,6 +743,7 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     safconv_handle* h = as_handle(hp);
     if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
     int e = scdev_set_device(h->device);
+    h->tailReady = 0;          /* a pre-computed tail belongs to the block counter it was enqueued for */
     const size_t inStride = (size_t)h->pl.nIn * h->pl.hop, outStride = (size_t)h->pl.nOutLocal * h->pl.hop;
     const int mb = (h->batching && h->pl.maxBatch > 1) ? h->pl.maxBatch : 1;
     for (int b = 0; b < nBlocks && !e; b += mb) {
@@ -720,6 +809,7 @@ int safconv_set_stream(void* hp, void* cudaStream)
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     scdev_stream_sync(h->stream);
+    h->tailReady = 0;
     if (h->graphExec) { scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }
     h->stream = cudaStream ? cudaStream : h->streamOwn;
     return SAFCONV_OK;
@@ -745,6 +835,7 @@ int safconv_reset_state(void* hp)
     safconv_handle* h = as_handle(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
+    h->tailReady = 0;
     int e = scdev_memset_async(h->b.X, 0, h->bytesX, h->stream);
     if (!e) e = scdev_memset_async(h->b.tail, 0, sizeof(float) * (size_t)h->pl.nOutLocal * h->pl.hop, h->stream);
     if (!e && h->b.tail2) e = scdev_memset_async(h->b.tail2, 0, sizeof(float) * (size_t)h->pl.nOutLocal * h->pl.hop, h->stream);
@@ -786,6 +877,7 @@ int safconv_enable_kernel_timing(void* hp, int nGroups)
     if (!h || nGroups < 0) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     scdev_stream_sync(h->stream);
+    h->tailReady = 0;
     if (h->evRing) {
         for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]);
         free(h->evRing);
@@ -854,7 +946,9 @@ int safconv_set_option(void* hp, const char* name, int value)
     else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
     else if (!strcmp(name, "small_fused")) { h->smallFused = value ? 1 : 0; }
     else if (!strcmp(name, "detect_pinned")) { h->detectPinned = value ? 1 : 0; }
+    else if (!strcmp(name, "lookahead")) { h->lookahead = (value && h->tailPass.Zp) ? 1 : 0; }
     else return SAFCONV_ERR_ARG;
+    h->tailReady = 0;
     if (h->graphExec) { scdev_set_device(h->device); scdev_stream_sync(h->stream); scdev_graph_destroy(h->graphExec); h->graphExec = NULL; }
     return SAFCONV_OK;
 }

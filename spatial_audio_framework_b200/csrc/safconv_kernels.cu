@@ -143,6 +143,7 @@ struct MacArgs {
     const int*    ctaBase;
     long long totalStages;
     int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
+    int pLo, nP;                   /* this pass covers partitions [pLo, pLo + nP) of every group (full pass: 0, P) */
     int NS;                        /* pipeline depth (stages)                */
     int RS, blk, nB;               /* delay-line ring size; first block of this launch inside the batch; blocks in this launch */
     size_t zpStride;               /* float2 elements of Zp per block */
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     const int nIt = (int)(s1 - s0);
     /* decompose the first stage index ONCE; afterwards (sidx, p, kt) are advanced incrementally
      * (no integer division inside the streaming loop) */
-    const long long unit0 = s0 / a.SPU;
+    const long long unit0 = s0 / a.SPU;                /* unit inside this pass: grp * nP + (p - pLo) */
     const int sidx0 = (int)(s0 - unit0 * a.SPU);       /* stage inside the unit          */
-    const long long grp0 = unit0 / a.P;
-    const int p0  = (int)(unit0 - grp0 * a.P);         /* filter partition               */
+    const long long grp0 = unit0 / a.nP;
+    const int pHi = a.pLo + a.nP;
+    const int p0  = a.pLo + (int)(unit0 - grp0 * a.nP);   /* filter partition            */
     const int kt0 = (int)(grp0 % a.nKT);               /* bin tile                       */
 
     if (threadIdx.x == 0) {
@@ -186,7 +188,8 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
         if (lane == 0) {
             const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
             const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
-            const float2* srcH0 = a.H + ((size_t)unit0 * a.nIn + (size_t)sidx0 * a.SNI) * a.OTsz * SC_BK;
+            const float2* srcH0 = a.H + (((size_t)grp0 * a.P + p0) * a.nIn + (size_t)sidx0 * a.SNI) * a.OTsz * SC_BK;
+            const size_t skipH = (size_t)(a.P - a.nP) * a.nIn * a.OTsz * SC_BK;   /* partitions of a group outside this pass */
             const uint32_t rowH = (uint32_t)a.OTsz * (SC_BK * 8);
             int s = 0; uint32_t par = 1;
             /* the blocks of a batch are streamed back to back: the pipeline never drains between blocks */
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
                         tma_bulk_g2s(smX + (size_t)s * a.stageXBytes, srcX, bytesX, &full[s]);
                     }
                     srcH += (size_t)cnt * a.OTsz * SC_BK;               /* stages are contiguous in H */
-                    if (++sidx == a.SPU) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+                    if (++sidx == a.SPU) { sidx = 0; if (++p == pHi) { p = a.pLo; srcH += skipH; if (++kt == a.nKT) kt = 0; } }
                     if (++s == NS) { s = 0; par ^= 1u; }
                 }
             }
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 
             const bool last     = (i + 1 == nIt);
             const bool endUnit  = (sidx == a.SPU - 1);
-            const bool endGroup = endUnit && (p == a.P - 1);
+            const bool endGroup = endUnit && (p == pHi - 1);
             if (endUnit || last) {
                 /* two-level accumulation: per-unit sums are folded into the running total */
 #pragma unroll
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 #pragma unroll
                 for (int j = 0; j < R; ++j) tot[j] = make_float2(0.f, 0.f);
             }
-            if (endUnit) { sidx = 0; if (++p == a.P) { p = 0; if (++kt == a.nKT) kt = 0; } }
+            if (endUnit) { sidx = 0; if (++p == pHi) { p = a.pLo; if (++kt == a.nKT) kt = 0; } }
             else ++sidx;
         }
     }
@@ -308,6 +311,8 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
 struct IfftArgs {
     const float2* Zp;      /* [B][nSlots][OTsz][32] */
     const int* grpStart;   /* partial slots of group g are grpStart[g] .. grpStart[g+1]-1 (consecutive) */
+    const float2* Zp2;     /* second list of partial tiles (head pass after a pre-computed tail pass), or NULL */
+    const int* grpStart2;
     const float2* tw;
     float* out;            /* [B][nOutLocal][hop] */
     float* tail;           /* [nOutLocal][hop] */
@@ -338,6 +343,11 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
             z = caddf(caddf(caddf(caddf(z, v0), v1), v2), v3);
         }
         for (; q < q1; ++q, src += qs) z = caddf(z, src[0]);
+        if (a.Zp2) {
+            const int r0 = __ldg(a.grpStart2 + g), r1 = __ldg(a.grpStart2 + g + 1);
+            const float2* s2 = a.Zp2 + ((size_t)r0 * a.OTsz + nl) * SC_BK + (k & 31);
+            for (int r = r0; r < r1; ++r, s2 += qs) z = caddf(z, s2[0]);
+        }
         sm[padi(k, a.logM)] = z;
     }
     __syncthreads();
@@ -823,6 +833,9 @@ int scdev_stream_create(void** s)
 int scdev_stream_destroy(void* s) { return s ? (int)cudaStreamDestroy((cudaStream_t)s) : 0; }
 int scdev_stream_sync(void* s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
 int scdev_event_create(void** e) { cudaEvent_t ev; cudaError_t r = cudaEventCreate(&ev); *e = (void*)ev; return (int)r; }
+int scdev_event_create_sync(void** e)
+{ cudaEvent_t ev; cudaError_t r = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); *e = (void*)ev; return (int)r; }
+int scdev_stream_wait_event(void* stream, void* e) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)e, 0); }
 int scdev_event_destroy(void* e) { return e ? (int)cudaEventDestroy((cudaEvent_t)e) : 0; }
 int scdev_event_record(void* e, void* stream) { return (int)cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream); }
 int scdev_event_sync(void* e) { return (int)cudaEventSynchronize((cudaEvent_t)e); }
@@ -919,25 +932,33 @@ int scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_in
 
 int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, void* stream)
 {
+    scdev_macpass full;
+    full.pLo = 0; full.nP = pl->P; full.totalStages = pl->totalStages; full.grid = pl->macGrid; full.nSlots = pl->nSlots;
+    full.ctaBase = b->ctaBase; full.grpStart = b->grpStart; full.Zp = b->Zp;
+    return scdev_mac_pass(pl, b, &full, blk, nBlocks, stream);
+}
+
+int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks, void* stream)
+{
     MacArgs a;
     a.H = (const float2*)b->H; a.X = (const float2*)b->X;
-    a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
-    a.Zp = (float2*)b->Zp + (size_t)blk * a.zpStride;
+    a.zpStride = (size_t)ps->nSlots * pl->OTsz * SC_BK;
+    a.Zp = (float2*)ps->Zp + (size_t)blk * a.zpStride;
     a.nB = nBlocks;
-    a.counters = b->counters; a.ctaBase = b->ctaBase;
-    a.totalStages = pl->totalStages;
+    a.counters = b->counters; a.ctaBase = ps->ctaBase;
+    a.totalStages = ps->totalStages; a.pLo = ps->pLo; a.nP = ps->nP;
     a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.P = pl->P; a.nKT = pl->nKT;
     a.SNI = pl->SNI; a.SPU = pl->SPU; a.WGo = pl->WGo; a.WGk = pl->WGk; a.hints = pl->macHints;
     a.NS = pl->macStages; a.RS = pl->RS; a.blk = blk;
     a.stageHBytes = pl->SNI * pl->OTsz * SC_BK * 8;
     a.stageXBytes = pl->SNI * SC_BK * 8;
-    mac_fn(pl->R)<<<pl->macGrid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);
+    mac_fn(pl->R)<<<ps->grid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
 static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks)
 {
-    a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart;
+    a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart; a.Zp2 = NULL; a.grpStart2 = NULL;
     a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
     a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
@@ -947,8 +968,16 @@ static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* 
 
 int scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream)
 {
+    return scdev_ifft_ola_passes(pl, b, NULL, NULL, d_out, stream);
+}
+
+int scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, const scdev_macpass* p2,
+                          float* d_out, void* stream)
+{
     IfftArgs a;
     fill_ifft_args(a, pl, b, d_out, 1);
+    if (p1) { a.Zp = (const float2*)p1->Zp; a.grpStart = p1->grpStart; }
+    if (p2) { a.Zp2 = (const float2*)p2->Zp; a.grpStart2 = p2->grpStart; }
     ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -986,7 +1015,7 @@ int scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_
         multi_mac_ifft_batch_kernel<<<grid, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     } else {
         IfftArgs o;
-        o.Zp = NULL; o.grpStart = NULL; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
+        o.Zp = NULL; o.grpStart = NULL; o.Zp2 = NULL; o.grpStart2 = NULL; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
         o.zpStride = 0; o.hop = pl->hop; o.M = pl->M; o.logM = pl->logM; o.nKT = 0; o.OTsz = 0;
         o.nOutLocal = pl->nOutLocal; o.B = nBlocks; o.scale = 0.f;
         const size_t n = (size_t)pl->nOutLocal * pl->hop;
@@ -1055,7 +1084,8 @@ int scdev_is_pinned_host(const void* p)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    return at.type == cudaMemoryTypeHost;
+    /* page-locked AND visible to kernels under the same address (zero-copy paths read / write it directly) */
+    return at.type == cudaMemoryTypeHost && at.devicePointer == p;
 }
 
 } /* extern "C" */

@@ -240,9 +240,49 @@ def test_batched_device_blocks_equal_block_by_block(saf, orc, hop, L, nIn, nOut,
     # host-pointer API (one block per call) through the same three kernels gives the same bits as well
     mh = saf.MatrixConv(hop, H)
     mh.set_option("small_fused", 0)
+    mh.set_option("lookahead", 0)        # the tail/head split of the host API sums the partitions in another order
     assert np.array_equal(mh.run(x), outs[0])
     # ... and through the fused small-problem kernel (different summation order) the same values to rounding
     check(saf.MatrixConv(hop, H).run(x), ref, "host API, default path")
+
+
+@pytest.mark.parametrize("hop,L,nIn,nOut,nblk", [(256, 700, 5, 9, 30), (1024, 12000, 16, 8, 30), (64, 128, 2, 3, 20),
+                                                  (128, 2000, 3, 70, 25), (512, 1024, 33, 17, 12)])
+def test_lookahead_tail_head_split(saf, orc, hop, L, nIn, nOut, nblk):
+    """Host-pointer apply with the look-ahead split (default for P >= 2): partitions p >= 1 of block t+1 are
+    accumulated behind block t, the call itself only adds the newest partition.  Same result as the oracle and as
+    the plain K1 -> K2 -> K3 sequence within tolerance; deterministic; survives reset, device-pointer calls in
+    between (which drop the pre-computed tail) and option changes."""
+    import torch
+    rng = np.random.default_rng(hop + nOut)
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H)
+    mc.set_option("small_fused", 0)
+    y = mc.run(x)
+    check(y, ref, "look-ahead host API")
+    mc.reset_state()
+    assert np.array_equal(mc.run(x), y)                      # deterministic, reset drops the pending tail
+    mp = saf.MatrixConv(hop, H)
+    mp.set_option("small_fused", 0)
+    mp.set_option("lookahead", 0)
+    check(mp.run(x), y, "plain vs look-ahead")
+    # host blocks, then device-pointer blocks, then host blocks again on one handle
+    mc.reset_state()
+    n1, n2 = nblk // 3, nblk // 3
+    parts = [mc.run(x[:, :n1 * hop])]
+    xb = np.ascontiguousarray(x[:, n1 * hop:(n1 + n2) * hop].reshape(nIn, n2, hop).transpose(1, 0, 2))
+    d_in = torch.from_numpy(xb).cuda()
+    d_out = torch.empty((n2, nOut, hop), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    mc.apply_device(d_in.data_ptr(), d_out.data_ptr(), n2)
+    mc.synchronize()
+    parts.append(d_out.cpu().numpy().transpose(1, 0, 2).reshape(nOut, n2 * hop))
+    mc.set_option("lookahead", 1)
+    parts.append(mc.run(x[:, (n1 + n2) * hop:]))
+    check(np.concatenate(parts, 1), ref, "host / device / host")
+    mc.destroy(); mp.destroy()
 
 
 @pytest.mark.parametrize("hop,L,nIn,nOut,T", [(64, 200, 3, 2, 20), (128, 128, 1, 1, 5), (256, 2048, 11, 5, 300),
