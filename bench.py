@@ -322,9 +322,14 @@ def run_offline_arm(args, w):
     alg_flops = 8.0 * nOut * P * nIn * (hop + 1) * (Tr + halo)     # complex MACs as real flops, this rank's launch
     gemm_ms = float(kms[1])
     achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "offline_gemm_kernel (tcgen05 kind::tf32, 3 MMAs per product for fp32 accuracy)",
-                "achieved": achieved, "peak": bf16 / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16 / 2.0),
-                "peak_source": "tf32 dense = half of the measured bf16 peak (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1590/2",
+    f16 = os.environ.get("SAFCONV_OFF_KIND", "f16") != "tf32"
+    tc_peak = bf16 if f16 else bf16 / 2.0
+    roofline = {"bound": "tensor",
+                "kernel": "offline_gemm_kernel (tcgen05 kind::%s, hi/lo split operands, 3 MMAs per product for fp32 accuracy)" % ("f16" if f16 else "tf32"),
+                "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+                "issued_frac": 3.0 * achieved / tc_peak,
+                "peak_source": ("f16 dense = the measured bf16 peak (MEASURED_PEAKS.json bf16_tflops)" if f16 else
+                                "tf32 dense = half of the measured bf16 peak (MEASURED_PEAKS.json bf16_tflops)") if peaks else "fallback 1590",
                 "traffic": None, "alg_flops_per_launch": alg_flops, "issued_flops_per_launch": 3.0 * alg_flops,
                 "avg_launch_ms": gemm_ms, "launches_timed": args.steps, "rank": 0,
                 "kernel_ms_per_render": {"forward_fft": float(kms[0]), "gemm": gemm_ms, "ifft_ola": float(kms[2])}}
@@ -340,13 +345,13 @@ def run_offline_arm(args, w):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (tf32x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f32 (%s x3 split tensor-core products, fp32 accumulate)" % ("f16" if f16 else "tf32"), "data": "synthetic",
         "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"], "frames": T,
                    "partitions": P,
                    "sharding": (f"time: {world} GPUs x ~{Tr} frames (+{P}-frame input halo), no exchange between GPUs"
                                 if world > 1 else "single GPU"),
                    "l2": "inputs larger than L2: %.1f GB of operands per render" % ((nIn * (Tr + halo) * hop * 4 * 3 + info.bytesFilters * 2) / 1e9)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if f16 else 5) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "realtime_factor_48k": (T * hop * args.steps / (ms_total * 1e-3)) / 48000.0,
     }
     emit(line)

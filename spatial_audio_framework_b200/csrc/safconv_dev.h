@@ -87,9 +87,11 @@ typedef struct scdev_bufs {
 
 /* workspace of the offline (batched frames, tensor-core) path, see safconv_offline.cu */
 typedef struct scdev_offline {
-    float *XGhi, *XGlo;      /* A operand  [bin][kg][rows][4]  (frames x (input, re/im)), tf32 hi / lo parts   */
-    float *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][4] ((output, re/im) x (input, re/im))               */
+    void  *XGhi, *XGlo;      /* A operand  [bin][kg][rows][16 B]  (frames x (input, re/im)), hi / lo parts; a k-group = 4 tf32 or 8 fp16 */
+    void  *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][16 B] ((output, re/im) x (input, re/im))            */
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
+    float *scal;             /* fp16 operands: [0] bound on the input spectra of the current render, [1] bound on the filter spectra */
+    int f16, ipc;            /* 1: fp16 operands (default), 0: tf32; inputs per k-group (4 / 2)                 */
     int capFrames, capTpad, capRows, packed;
     int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush, fpc, opc, fftThreads;
 } scdev_offline;

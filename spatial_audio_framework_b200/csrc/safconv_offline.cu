@@ -32,8 +32,10 @@
  *                                        (reference .c:230-233)
  */
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
 
@@ -56,18 +58,90 @@ __device__ __forceinline__ float tf32_rn(float x)
 __device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
 __device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
 
+/* ---- fp16 operands (kind::f16, twice the tf32 MMA rate, half the operand bytes) -------------------------------
+ * fp16 carries the same 10 explicit mantissa bits as tf32, so the hi/lo split has the same precision -- as long as
+ * the values sit inside fp16's exponent range.  Both operands are therefore multiplied by a power of two (exact)
+ * chosen from a bound on their magnitude so that the largest value lands just below 2^15:
+ *   A (input spectra):  |X[k]| <= sum_n |x[n]|  -> the largest l1 norm over all (channel, frame) blocks
+ *   B (filter spectra): the largest |re|, |im| over the filter spectra
+ * hi = rn_f16(s x) is a normal fp16 number down to 2^-29 of the bound, lo = rn_f16(s x - hi) down to 2^-18 of it;
+ * below that lo is rounded on fp16's fixed subnormal grid (2^-24), i.e. with an ABSOLUTE error of 2^-40 of the
+ * bound -- far below the 2^-22 relative error of the large terms that dominate every output sample.
+ * The product of the two scales is divided out (exactly) when the accumulators are stored.
+ * scal[0] / scal[1] hold the two bounds as float bit patterns (written with atomicMax on the device). */
+__device__ __forceinline__ float pow2_scale(float bound)
+{
+    if (!(bound > 0.f) || bound > 3.0e38f) return 1.f;
+    int e;
+    (void)frexpf(bound, &e);                    /* bound = m 2^e, 0.5 <= m < 1  ->  bound 2^(15-e) < 2^15 */
+    int sft = 15 - e;
+    sft = sft < -60 ? -60 : (sft > 60 ? 60 : sft);
+    return ldexpf(1.f, sft);
+}
+__device__ __forceinline__ void f16_split(float x, __half& hi, __half& lo)
+{
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b)
+{
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+/* largest |v[i]| -> atomicMax on the float bit pattern (non-negative floats order like unsigned ints) */
+__global__ void offline_absmax_kernel(const float* __restrict__ v, size_t n, float* out)
+{
+    float m = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(__ldg(v + i)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m <= 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+/* largest l1 norm of a hop-sized input block: one warp per (frame, channel) block; grid (ceil(T/8), nIn), 256 threads */
+__global__ void offline_l1max_kernel(const float* __restrict__ in, size_t inStride, int hop, int T, float* out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + warp, ni = blockIdx.y;
+    float sum = 0.f;
+    if (t < T) {
+        const float* x = in + (size_t)ni * inStride + (size_t)t * hop;
+        if ((hop & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            for (int i = lane; i < (hop >> 2); i += 32) { const float4 v = __ldg(x4 + i); sum += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w); }
+        } else {
+            for (int i = lane; i < hop; i += 32) sum += fabsf(__ldg(x + i));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ float wmax[8];
+    if (lane == 0) wmax[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < 8; ++w) m = fmaxf(m, wmax[w]);
+        if (m > 0.f && m <= 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
-/*  B operand: HG[hi|lo][bin][p][kg][n][4],  n = 2*no + c_out,  k = 2*ni + c_in                  */
+/*  B operand: HG[hi|lo][bin][p][kg][n][16 bytes],  n = 2*no + c_out,  k = 2*ni + c_in              */
+/*  (a k-group = 16 bytes = 4 tf32 or 8 fp16 values along K)                                        */
 /* ------------------------------------------------------------------------------------------ */
 struct PackArgs {
     const float2* H;       /* [ot][kt][p][ni][OTsz][32] */
-    float* HGhi; float* HGlo;
+    unsigned char* HGhi; unsigned char* HGlo;
+    const float* scal;     /* F16: scal[1] = bound on the filter spectra */
     size_t total;          /* elements of H */
     int nKT, P, nIn, OTsz, nOutLocal, nKG, Nn;
 };
 
+template <bool F16>
 __global__ void offline_pack_filters_kernel(PackArgs a)
 {
+    const float sc = F16 ? pow2_scale(a.scal[1]) : 1.f;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.total; e += stride) {
         size_t r = e;
@@ -86,77 +160,127 @@ __global__ void offline_pack_filters_kernel(PackArgs a)
         if (bin == 0) { rowRe = make_float2(h.x, 0.f);  rowIm = make_float2(0.f, h.y); }
         else          { rowRe = make_float2(h.x, -h.y); rowIm = make_float2(h.y, h.x); }
         const int k = 2 * ni;
-        const size_t base = ((((size_t)bin * a.P + p) * a.nKG + (k >> 2)) * a.Nn) * 4 + (k & 3);
-        const size_t iRe = base + (size_t)(2 * no) * 4, iIm = base + (size_t)(2 * no + 1) * 4;
-        const float2 reHi = make_float2(tf32_hi(rowRe.x), tf32_hi(rowRe.y));
-        const float2 imHi = make_float2(tf32_hi(rowIm.x), tf32_hi(rowIm.y));
-        *reinterpret_cast<float2*>(a.HGhi + iRe) = reHi;
-        *reinterpret_cast<float2*>(a.HGhi + iIm) = imHi;
-        *reinterpret_cast<float2*>(a.HGlo + iRe) = make_float2(tf32_lo(rowRe.x, reHi.x), tf32_lo(rowRe.y, reHi.y));
-        *reinterpret_cast<float2*>(a.HGlo + iIm) = make_float2(tf32_lo(rowIm.x, imHi.x), tf32_lo(rowIm.y, imHi.y));
+        if (F16) {
+            const size_t base = ((((size_t)bin * a.P + p) * a.nKG + (k >> 3)) * a.Nn) * 16 + (size_t)(k & 7) * 2;
+            const size_t iRe = base + (size_t)(2 * no) * 16, iIm = base + (size_t)(2 * no + 1) * 16;
+            __half h0, l0, h1, l1;
+            f16_split(rowRe.x * sc, h0, l0); f16_split(rowRe.y * sc, h1, l1);
+            *reinterpret_cast<uint32_t*>(a.HGhi + iRe) = pack_h2(h0, h1);
+            *reinterpret_cast<uint32_t*>(a.HGlo + iRe) = pack_h2(l0, l1);
+            f16_split(rowIm.x * sc, h0, l0); f16_split(rowIm.y * sc, h1, l1);
+            *reinterpret_cast<uint32_t*>(a.HGhi + iIm) = pack_h2(h0, h1);
+            *reinterpret_cast<uint32_t*>(a.HGlo + iIm) = pack_h2(l0, l1);
+        } else {
+            const size_t base = ((((size_t)bin * a.P + p) * a.nKG + (k >> 2)) * a.Nn) * 16 + (size_t)(k & 3) * 4;
+            const size_t iRe = base + (size_t)(2 * no) * 16, iIm = base + (size_t)(2 * no + 1) * 16;
+            const float2 reHi = make_float2(tf32_hi(rowRe.x), tf32_hi(rowRe.y));
+            const float2 imHi = make_float2(tf32_hi(rowIm.x), tf32_hi(rowIm.y));
+            *reinterpret_cast<float2*>(a.HGhi + iRe) = reHi;
+            *reinterpret_cast<float2*>(a.HGhi + iIm) = imHi;
+            *reinterpret_cast<float2*>(a.HGlo + iRe) = make_float2(tf32_lo(rowRe.x, reHi.x), tf32_lo(rowRe.y, reHi.y));
+            *reinterpret_cast<float2*>(a.HGlo + iIm) = make_float2(tf32_lo(rowIm.x, imHi.x), tf32_lo(rowIm.y, imHi.y));
+        }
     }
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/*  A operand: XG[hi|lo][bin][kg][row][4], row = (P-1) + frame (P-1 leading zero rows = silence    */
-/*  before the first frame), the 4 floats = (re, im) of inputs 2kg and 2kg+1                      */
-/*  grid (rows / FPC, ceil(nIn/2))                                                                */
+/*  A operand: XG[hi|lo][bin][kg][row][16 bytes], row = (P-1) + frame (P-1 leading zero rows =     */
+/*  silence before the first frame); a k-group holds (re, im) of IPC inputs: 2 (tf32) or 4 (fp16)   */
+/*  grid (rows / FPC, ceil(nIn/IPC))                                                              */
 /* ------------------------------------------------------------------------------------------ */
 struct OffFftArgs {
     const float* in;       /* [nIn][T*hop] */
-    float* XGhi; float* XGlo;
+    unsigned char* XGhi; unsigned char* XGlo;
     const float2* tw;
+    const float* scal;     /* fp16 operands: scal[0] = bound on the input spectra */
     size_t inStride;       /* T*hop */
     int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
     int fpc;               /* frames per CTA (2 or 4): 32- or 64-byte contiguous operand stores */
+    int ipc;               /* inputs per CTA = inputs per k-group: 2 (tf32) or 4 (fp16) */
 };
 
 __global__ void offline_fft_kernel(OffFftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int MP = SC_ALEN(a.M);                       /* padded FFT work arrays */
-    const int FPC = a.fpc;
-    float2* stw = sm + (size_t)(2 * FPC) * MP;
+    const int FPC = a.fpc, IPC = a.ipc, nTr = IPC * FPC;    /* transforms of this CTA: q = IPC*f + j (frame f, input IPC*kg+j) */
+    const int logIPC = (IPC == 4) ? 2 : 1;
+    float2* stw = sm + (size_t)nTr * MP;
     /* blockIdx.x walks along the frames: CTAs that run at the same time store ADJACENT 32/64-byte pieces of the
      * same operand rows, so L2 merges them into full lines and DRAM sees long bursts (the first version had the
      * input pair on x and was bound by scattered 64-byte DRAM writes, not by the FFT) */
     const int kg = blockIdx.y;
     const int row0 = blockIdx.x * FPC;
-    const bool wide = fft_use_wide(a.M, 2 * FPC);
+    const bool wide = fft_use_wide(a.M, nTr);
     load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = a.tw;                      /* split-pass twiddles straight from the (L1/L2-resident) global table: keeps 3 CTAs per SM */
-    /* input blocks of the 2*FPC transforms (q = 2*f + j : frame f, input 2kg+j): for every chunk of samples the
-     * loads of ALL transforms are issued before the first store, so one DRAM round trip covers the whole batch */
+    /* input blocks of the transforms: for every chunk of samples the loads of (up to 8) transforms are issued
+     * before the first store, so one DRAM round trip covers the whole batch */
     {
         const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0) && ((a.inStride & 1) == 0);
+        for (int q0 = 0; q0 < nTr; q0 += 8)
         for (int n0 = 0; n0 < a.M; n0 += blockDim.x) {
             const int n = n0 + threadIdx.x;
             float2 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                v[q] = make_float2(0.f, 0.f);
-                if (q < 2 * FPC && n < a.M) {
-                    const int ni = 2 * kg + (q & 1);
-                    const int t = row0 + (q >> 1) - (a.P - 1);
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u;
+                v[u] = make_float2(0.f, 0.f);
+                if (q < nTr && n < a.M) {
+                    const int ni = IPC * kg + (q & (IPC - 1));
+                    const int t = row0 + (q >> logIPC) - (a.P - 1);
                     if (ni < a.nIn && t >= 0 && t < a.T) {
                         const float* x = a.in + (size_t)ni * a.inStride + (size_t)t * a.hop;
-                        if (vec) { if (2 * n < a.hop) v[q] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                        if (vec) { if (2 * n < a.hop) v[u] = __ldg(reinterpret_cast<const float2*>(x) + n); }
                         else {
-                            if (2 * n < a.hop)     v[q].x = __ldg(x + 2 * n);
-                            if (2 * n + 1 < a.hop) v[q].y = __ldg(x + 2 * n + 1);
+                            if (2 * n < a.hop)     v[u].x = __ldg(x + 2 * n);
+                            if (2 * n + 1 < a.hop) v[u].y = __ldg(x + 2 * n + 1);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q < 2 * FPC && n < a.M) sm[(size_t)q * MP + padi(n, a.logM)] = v[q];
+            for (int u = 0; u < 8; ++u)
+                if (q0 + u < nTr && n < a.M) sm[(size_t)(q0 + u) * MP + padi(n, a.logM)] = v[u];
         }
     }
     __syncthreads();
-    cfft_dif_batch<false>(sm, a.M, a.logM, stw, 2 * FPC, wide);
+    cfft_dif_batch<false>(sm, a.M, a.logM, stw, nTr, wide);
 
     const int half = a.M >> 1;
+    if (IPC == 4) {
+        /* fp16 operands: one 16-byte k-group = (re, im) of four inputs, scaled by a power of two (see pow2_scale) */
+        const float sc = pow2_scale(a.scal[0]);
+        for (int idx = threadIdx.x; idx < (half + 1) * FPC; idx += blockDim.x) {
+            const int f = idx & (FPC - 1), k = idx / FPC;
+            const float2* s0 = sm + (size_t)(4 * f) * MP;
+            uint32_t hiK[4], loK[4], hiM[4], loM[4];
+            int k2 = a.M - k;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2* sj = s0 + (size_t)j * MP;
+                float2 x, xm;
+                if (k == 0) { const float2 z = sj[0]; x = make_float2(z.x + z.y, z.x - z.y); xm = x; }
+                else fwd_split_pair(sj, k, a.M, a.logM, spl, x, xm);
+                __half h0, l0, h1, l1;
+                f16_split(x.x * sc, h0, l0);  f16_split(x.y * sc, h1, l1);
+                hiK[j] = pack_h2(h0, h1);  loK[j] = pack_h2(l0, l1);
+                f16_split(xm.x * sc, h0, l0); f16_split(xm.y * sc, h1, l1);
+                hiM[j] = pack_h2(h0, h1);  loM[j] = pack_h2(l0, l1);
+            }
+            if (k == 0) k2 = 0;
+            const size_t row = (size_t)row0 + f;
+            const size_t o1 = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row) * 16;
+            *reinterpret_cast<uint4*>(a.XGhi + o1) = make_uint4(hiK[0], hiK[1], hiK[2], hiK[3]);
+            *reinterpret_cast<uint4*>(a.XGlo + o1) = make_uint4(loK[0], loK[1], loK[2], loK[3]);
+            if (k2 != k) {
+                const size_t o2 = (((size_t)k2 * a.nKG + kg) * a.rowsAlloc + row) * 16;
+                *reinterpret_cast<uint4*>(a.XGhi + o2) = make_uint4(hiM[0], hiM[1], hiM[2], hiM[3]);
+                *reinterpret_cast<uint4*>(a.XGlo + o2) = make_uint4(loM[0], loM[1], loM[2], loM[3]);
+            }
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < (half + 1) * FPC; idx += blockDim.x) {
         const int f = idx & (FPC - 1), k = idx / FPC;
         const float2* s0 = sm + (size_t)(2 * f) * MP;
@@ -176,14 +300,14 @@ __global__ void offline_fft_kernel(OffFftArgs a)
         {
             const float4 v = make_float4(x0.x, x0.y, x1.x, x1.y);
             const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row) * 4;
+            const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row) * 16;
             *reinterpret_cast<float4*>(a.XGhi + o) = hi;
             *reinterpret_cast<float4*>(a.XGlo + o) = make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w));
         }
         {
             const float4 v = make_float4(x0m.x, x0m.y, x1m.x, x1m.y);
             const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            const size_t o = (((size_t)k2 * a.nKG + kg) * a.rowsAlloc + row) * 4;
+            const size_t o = (((size_t)k2 * a.nKG + kg) * a.rowsAlloc + row) * 16;
             *reinterpret_cast<float4*>(a.XGhi + o) = hi;
             *reinterpret_cast<float4*>(a.XGlo + o) = make_float4(tf32_lo(v.x, hi.x), tf32_lo(v.y, hi.y), tf32_lo(v.z, hi.z), tf32_lo(v.w, hi.w));
         }
@@ -213,13 +337,28 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int Mdim, int Ndim)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmemD, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+/* instruction descriptor: D = F32, A = B = F16, both K-major, dense, M x N (K = 16 per instruction) */
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int Mdim, int Ndim)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(tmemD), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
+}
+
+template <bool F16>
+__device__ __forceinline__ void umma_ss(uint32_t tmemD, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if (F16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmemD), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmemD), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 /* arrive on an mbarrier once all previously issued MMAs of this thread have completed */
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
@@ -260,7 +399,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 /*  the MMA thread fills the other.                                                              */
 /* ------------------------------------------------------------------------------------------ */
 struct OffGemmArgs {
-    const float *XGhi, *XGlo, *HGhi, *HGlo;
+    const unsigned char *XGhi, *XGlo, *HGhi, *HGlo;
+    const float* scal;     /* fp16 operands: the two magnitude bounds whose scales are divided out of the result */
     float* Ys;             /* [bin][Tpad][Nn] */
     int P, nKG, nKC, Nn, rowsAlloc, Tpad, rowsX, tmemCols, flush;
     uint32_t idesc;
@@ -269,6 +409,7 @@ struct OffGemmArgs {
 #define OFF_EPI_WARPS 8
 #define OFF_MAX_HALF  64     /* columns per epilogue thread and frame tile: Nn/2 <= 64 */
 
+template <bool F16>
 __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGemmArgs a)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -318,16 +459,16 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                 mbar_expect_tx(&xfull[xs], xStage);
                 for (int hl = 0; hl < 2; ++hl)
                     for (int g = 0; g < OFF_KG; ++g) {
-                        const float* src = (hl ? a.XGlo : a.XGhi)
-                                         + (((size_t)bin * a.nKG + (size_t)kc * OFF_KG + g) * a.rowsAlloc + t0) * 4;
+                        const unsigned char* src = (hl ? a.XGlo : a.XGhi)
+                                         + (((size_t)bin * a.nKG + (size_t)kc * OFF_KG + g) * a.rowsAlloc + t0) * 16;
                         tma_bulk_g2s(smX + (size_t)xs * xStage + (size_t)(hl * OFF_KG + g) * xPlane, src, xPlane, &xfull[xs]);
                     }
                 for (int p = 0; p < a.P; ++p) {
                     mbar_wait(&hempty[hs], hpar);
                     mbar_expect_tx(&hfull[hs], hStage);
                     for (int hl = 0; hl < 2; ++hl) {
-                        const float* src = (hl ? a.HGlo : a.HGhi)
-                                         + ((((size_t)bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 4;
+                        const unsigned char* src = (hl ? a.HGlo : a.HGhi)
+                                         + ((((size_t)bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 16;
                         tma_bulk_g2s(smH + (size_t)hs * hStage + (size_t)hl * OFF_KG * hPlane, src, OFF_KG * hPlane, &hfull[hs]);
                     }
                     if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
@@ -368,9 +509,9 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                             const uint64_t bHi = bDesc0 + b16, bLo = bDesc0 + b16 + OFF_KG * hPlane16;
                             const uint32_t d = tmem + (uint32_t)((tb * 2 + acc) * a.Nn);
                             /* small cross terms first, the large hi*hi term last */
-                            umma_tf32(d, aLo, bHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
-                            umma_tf32(d, aHi, bLo, a.idesc, 1u);                         /* hi*lo */
-                            umma_tf32(d, aHi, bHi, a.idesc, 1u);                         /* hi*hi */
+                            umma_ss<F16>(d, aLo, bHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
+                            umma_ss<F16>(d, aHi, bLo, a.idesc, 1u);                         /* hi*lo */
+                            umma_ss<F16>(d, aHi, bHi, a.idesc, 1u);                         /* hi*hi */
                         }
                     }
                     umma_commit(&hempty[hs]);                           /* filter stage free once these MMAs retire */
@@ -414,6 +555,8 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[tb]);
         }
+        /* fp16 operands were scaled by exact powers of two: divide them out (exact as well) */
+        const float inv = F16 ? 1.f / (pow2_scale(a.scal[0]) * pow2_scale(a.scal[1])) : 1.f;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int row = t0 + t * 128 + q * 32 + lane;
@@ -421,7 +564,7 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
 #pragma unroll
             for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 4)
                 if (c0 < halfN)
-                    *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[t][c0], sum[t][c0 + 1], sum[t][c0 + 2], sum[t][c0 + 3]);
+                    *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[t][c0] * inv, sum[t][c0 + 1] * inv, sum[t][c0 + 2] * inv, sum[t][c0 + 3] * inv);
         }
     }
     tc_fence_before();
@@ -507,8 +650,8 @@ static size_t roundup(size_t v, size_t m) { return (v + m - 1) / m * m; }
 int scdev_offline_free(scdev_offline* o)
 {
     if (!o) return 0;
-    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys);
-    o->XGhi = o->XGlo = o->HGhi = o->HGlo = o->Ys = NULL;
+    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys); cudaFree(o->scal);
+    o->XGhi = o->XGlo = o->HGhi = o->HGlo = NULL; o->Ys = NULL; o->scal = NULL;
     o->capFrames = 0; o->packed = 0;
     return 0;
 }
@@ -523,8 +666,14 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
     if (Nn > 2 * OFF_MAX_HALF) return (int)cudaErrorInvalidValue;    /* one N tile: nOutLocal <= 64 */
     if (pl->P - 1 > 1024) return (int)cudaErrorInvalidValue;
     o->Nn = Nn;
-    o->Kp = (int)roundup((size_t)2 * pl->nIn, 4 * OFF_KG);
-    o->nKG = o->Kp / 4;
+    if (!o->packed) {                                                /* operand type is fixed per handle */
+        const char* v = getenv("SAFCONV_OFF_KIND");
+        o->f16 = !(v && !strcmp(v, "tf32"));
+    }
+    const int epk = o->f16 ? 8 : 4;                                  /* values per 16-byte k-group */
+    o->ipc = epk / 2;
+    o->Kp = (int)roundup((size_t)2 * pl->nIn, (size_t)epk * OFF_KG);
+    o->nKG = o->Kp / epk;
     o->nKC = o->nKG / OFF_KG;
     o->rowsX = OFF_MT + pl->P - 1;
     o->tmemCols = 4 * Nn;                                            /* two buffer sets x two frame tiles */
@@ -533,27 +682,37 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         const char* v = getenv("SAFCONV_OFF_FLUSH");
         int fl = v ? atoi(v) : 1;
         o->flush = fl < 1 ? 1 : fl;
-        v = getenv("SAFCONV_OFF_FPC");      o->fpc = (v && atoi(v) == 2) ? 2 : 4;
+        v = getenv("SAFCONV_OFF_FPC");      o->fpc = v ? ((atoi(v) == 2) ? 2 : 4) : (o->f16 ? 2 : 4);
         v = getenv("SAFCONV_OFF_OPC");      o->opc = (v && atoi(v) == 8) ? 8 : 4;
         v = getenv("SAFCONV_OFF_THREADS");  o->fftThreads = (v && atoi(v) == 128) ? 128 : 256;
     }
     if (!o->packed) {
-        const size_t hgFloats = (size_t)pl->M * pl->P * o->nKG * Nn * 4;
-        SC_CHECK(cudaMalloc((void**)&o->HGhi, hgFloats * sizeof(float)));
-        SC_CHECK(cudaMalloc((void**)&o->HGlo, hgFloats * sizeof(float)));
-        SC_CHECK(cudaMemsetAsync(o->HGhi, 0, hgFloats * sizeof(float), st));
-        SC_CHECK(cudaMemsetAsync(o->HGlo, 0, hgFloats * sizeof(float), st));
+        const size_t hgBytes = (size_t)pl->M * pl->P * o->nKG * Nn * 16;
+        SC_CHECK(cudaMalloc((void**)&o->HGhi, hgBytes));
+        SC_CHECK(cudaMalloc((void**)&o->HGlo, hgBytes));
+        SC_CHECK(cudaMalloc((void**)&o->scal, 4 * sizeof(float)));
+        SC_CHECK(cudaMemsetAsync(o->HGhi, 0, hgBytes, st));
+        SC_CHECK(cudaMemsetAsync(o->HGlo, 0, hgBytes, st));
+        SC_CHECK(cudaMemsetAsync(o->scal, 0, 4 * sizeof(float), st));
         PackArgs a;
-        a.H = (const float2*)b->H; a.HGhi = o->HGhi; a.HGlo = o->HGlo;
+        a.H = (const float2*)b->H; a.HGhi = (unsigned char*)o->HGhi; a.HGlo = (unsigned char*)o->HGlo; a.scal = o->scal;
         a.total = (size_t)pl->nOT * pl->nKT * pl->P * pl->nIn * pl->OTsz * SC_BK;
         a.nKT = pl->nKT; a.P = pl->P; a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.nOutLocal = pl->nOutLocal;
         a.nKG = o->nKG; a.Nn = Nn;
-        offline_pack_filters_kernel<<<148 * 8, 256, 0, st>>>(a);
+        if (o->f16) {
+            offline_absmax_kernel<<<148 * 8, 256, 0, st>>>((const float*)b->H, 2 * a.total, o->scal + 1);
+            SC_CHECK(cudaGetLastError());
+            offline_pack_filters_kernel<true><<<148 * 8, 256, 0, st>>>(a);
+        } else {
+            offline_pack_filters_kernel<false><<<148 * 8, 256, 0, st>>>(a);
+        }
         SC_CHECK(cudaGetLastError());
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        const int fftSmem = (2 * OFF_FPC + 1) * SC_ALEN(pl->M) * 8, ifftSmem = (OFF_OPC + 1) * SC_ALEN(pl->M) * 8;
-        if (fftSmem > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
-        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        const int fftSmem = (4 * OFF_FPC + 1) * SC_ALEN(pl->M) * 8, ifftSmem = (OFF_OPC + 1) * SC_ALEN(pl->M) * 8;
+        if ((o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8 > 227 * 1024) o->fpc = 2;
+        if ((o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8 > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
+        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem > 227 * 1024 ? 227 * 1024 : fftSmem));
         SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ifftSmem));
         o->packed = 1;
     }
@@ -563,13 +722,13 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         o->XGhi = o->XGlo = o->Ys = NULL; o->capFrames = 0;
         const size_t Tpad = roundup((size_t)T, OFF_MT);
         const size_t rowsAlloc = roundup(Tpad + pl->P - 1, OFF_FPC);
-        const size_t xgFloats = (size_t)pl->M * o->nKG * rowsAlloc * 4;
-        SC_CHECK(cudaMalloc((void**)&o->XGhi, xgFloats * sizeof(float)));
-        SC_CHECK(cudaMalloc((void**)&o->XGlo, xgFloats * sizeof(float)));
+        const size_t xgBytes = (size_t)pl->M * o->nKG * rowsAlloc * 16;
+        SC_CHECK(cudaMalloc((void**)&o->XGhi, xgBytes));
+        SC_CHECK(cudaMalloc((void**)&o->XGlo, xgBytes));
         SC_CHECK(cudaMalloc((void**)&o->Ys, (size_t)pl->M * Tpad * Nn * sizeof(float)));
         /* padding k-groups (odd nIn / K padding) are never written by the FFT kernel: zero them once */
-        SC_CHECK(cudaMemsetAsync(o->XGhi, 0, xgFloats * sizeof(float), st));
-        SC_CHECK(cudaMemsetAsync(o->XGlo, 0, xgFloats * sizeof(float), st));
+        SC_CHECK(cudaMemsetAsync(o->XGhi, 0, xgBytes, st));
+        SC_CHECK(cudaMemsetAsync(o->XGlo, 0, xgBytes, st));
         o->capFrames = T; o->capTpad = (int)Tpad; o->capRows = (int)rowsAlloc;
     }
     return 0;
@@ -587,25 +746,35 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     const int rowsUsed = (int)roundup((size_t)Tpad + pl->P - 1, OFF_FPC);
 
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[0], st));
+    if (o->f16) {
+        /* bound on the input spectra of this render: the largest l1 norm of a block (see pow2_scale) */
+        SC_CHECK(cudaMemsetAsync(o->scal, 0, sizeof(float), st));
+        dim3 grid((T + 7) / 8, pl->nIn);
+        offline_l1max_kernel<<<grid, 256, 0, st>>>(d_in, (size_t)T * pl->hop, pl->hop, T, o->scal);
+        SC_CHECK(cudaGetLastError());
+    }
     OffFftArgs f;
-    f.in = d_in; f.XGhi = o->XGhi; f.XGlo = o->XGlo; f.tw = (const float2*)b->tw;
+    f.in = d_in; f.XGhi = (unsigned char*)o->XGhi; f.XGlo = (unsigned char*)o->XGlo; f.tw = (const float2*)b->tw; f.scal = o->scal;
     f.inStride = (size_t)T * pl->hop;
     f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
     {
-        f.fpc = o->fpc;
-        dim3 grid(rowsUsed / o->fpc, (pl->nIn + 1) / 2);
-        offline_fft_kernel<<<grid, o->fftThreads, (size_t)(2 * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
+        f.fpc = o->fpc; f.ipc = o->ipc;
+        dim3 grid(rowsUsed / o->fpc, (pl->nIn + o->ipc - 1) / o->ipc);
+        offline_fft_kernel<<<grid, o->fftThreads, (size_t)(o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[1], st));
     OffGemmArgs g;
-    g.XGhi = o->XGhi; g.XGlo = o->XGlo; g.HGhi = o->HGhi; g.HGlo = o->HGlo; g.Ys = o->Ys;
+    g.XGhi = (const unsigned char*)o->XGhi; g.XGlo = (const unsigned char*)o->XGlo;
+    g.HGhi = (const unsigned char*)o->HGhi; g.HGlo = (const unsigned char*)o->HGlo; g.Ys = o->Ys; g.scal = o->scal;
     g.P = pl->P; g.nKG = o->nKG; g.nKC = o->nKC; g.Nn = o->Nn; g.rowsAlloc = rowsAlloc; g.Tpad = o->capTpad;
-    g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush; g.idesc = umma_idesc_tf32(128, o->Nn);
+    g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush;
+    g.idesc = o->f16 ? umma_idesc_f16(128, o->Nn) : umma_idesc_tf32(128, o->Nn);
     {
         dim3 grid(Tpad / OFF_MT, pl->M);
-        offline_gemm_kernel<<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+        if (o->f16) offline_gemm_kernel<true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+        else        offline_gemm_kernel<false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[2], st));
