@@ -49,6 +49,8 @@ WORKLOADS = {
                desc="saf_multiConv 256 ch, hop 512, 4096 taps (BASELINE.json configs[2])"),
     "C5": dict(kind="offline", nIn=121, nOut=64, hop=1024, L=8192, seconds=60.0,
                desc="offline batched render: 121 SH x 64 out, 8192 taps, hop 1024, 60 s of audio in one call (BASELINE.json configs[4])"),
+    "C4o": dict(kind="offline", nIn=64, nOut=64, hop=1024, L=96000, seconds=60.0,
+                desc="configs[3] filters (64x64, 96000 taps) rendered offline: 60 s of audio in one call through the tensor-core path"),
     "C5s": dict(kind="offline", nIn=121, nOut=64, hop=1024, L=8192, seconds=6.0,
                 desc="C5 on a 6 s signal (debug)"),
     "C2": dict(kind="matrix", nIn=25, nOut=2, hop=128, L=512,

@@ -67,6 +67,7 @@ typedef struct scdev_macpass {
     int*  ctaBase;           /* device int[grid+1]      */
     int*  grpStart;          /* device int[nGroups+1]   */
     void* Zp;                /* device float2[nSlots][OTsz][32] */
+    void* ZpB;               /* second buffer (tail pass: block t+1's tail is written while K3 of block t still reads) or NULL */
 } scdev_macpass;
 
 typedef struct scdev_bufs {
@@ -110,6 +111,7 @@ int  scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream);
 int  scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream);
 int  scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes, void* stream);
 int  scdev_stream_create(void** s);
+int  scdev_stream_create_high_priority(void** s);
 int  scdev_stream_destroy(void* s);
 int  scdev_stream_sync(void* s);
 int  scdev_event_create(void** e);
@@ -137,11 +139,13 @@ int  scdev_input_fft(const scdev_plan* pl, const scdev_bufs* b, const float* d_i
  * the batch, streamed back to back inside ONE launch (every block streams the filter spectra once) */
 int  scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, void* stream);
 /* K2 restricted to one pass (see scdev_macpass) */
-int  scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks, void* stream);
+/* zpSel: 0 = ps->Zp, 1 = ps->ZpB; count >= 0: block counter supplied by the host instead of read from the device */
+int  scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks,
+                    int zpSel, long long count, void* stream);
 /* K3: sum split-K partials, inverse real FFT, 1/N, overlap-add, tail save, block counter++ (one block) */
 int  scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream);
 /* K3 summing the partial tiles of pass p1 then pass p2 (NULL, NULL = the full pass) */
-int  scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, const scdev_macpass* p2,
+int  scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, int zpSel1, const scdev_macpass* p2,
                            float* d_out, void* stream);
 /* K3 for a batch: inverse FFTs of all nBlocks blocks in one launch, then the overlap-add chain; counter += nBlocks */
 int  scdev_ifft_ola_batch(const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks, void* stream);

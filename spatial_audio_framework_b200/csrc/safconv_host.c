@@ -58,6 +58,9 @@ typedef struct safconv_handle {
     void*      evDone;               /* recorded after the output of a block is complete: apply waits on it, not on the whole stream */
     void*      streamIn;             /* side stream: the forward FFT of the new block runs beside the tail pass */
     void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
+    void*      streamOut;            /* high-priority side stream: K3 (+ D2H) of block t runs beside the tail pass of block t+1 */
+    void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
+    unsigned int count;              /* host mirror of the device block counter (counters[0]) */
 } safconv_handle;
 
 static __thread int  tl_err = 0;
@@ -259,8 +262,10 @@ static void handle_free(safconv_handle* h)
     scdev_free(h->tailPass.ctaBase); scdev_free(h->tailPass.grpStart); scdev_free(h->tailPass.Zp);
     scdev_free(h->headPass.ctaBase); scdev_free(h->headPass.grpStart); scdev_free(h->headPass.Zp);
     if (h->streamIn) scdev_stream_sync(h->streamIn);
-    scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence);
-    scdev_stream_destroy(h->streamIn);
+    if (h->streamOut) scdev_stream_sync(h->streamOut);
+    scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence); scdev_event_destroy(h->evMac);
+    scdev_stream_destroy(h->streamIn); scdev_stream_destroy(h->streamOut);
+    scdev_free(h->tailPass.ZpB);
     scdev_free(h->d_in); scdev_free(h->d_out);
     scdev_host_free(h->h_in); scdev_host_free(h->h_out);
     scdev_stream_destroy(h->streamOwn);
@@ -400,7 +405,10 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         DEV_TRY(h, scdev_event_create_sync(&h->evDone), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evIn), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evFence), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evMac), "cudaEventCreate");
         DEV_TRY(h, scdev_stream_create(&h->streamIn), "cudaStreamCreate");
+        DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
+        if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
     }
     DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
@@ -528,6 +536,7 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
         e = scdev_small_fused(&h->pl, &h->b, src, dst, h->stream);
         if (!e) e = scdev_stream_sync(h->stream);
         if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (fused)", e); return; }
+        h->count++;
         if (!direct) memcpy(out, h->h_out, h->outBytes);
         return;
     }
@@ -570,18 +579,23 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
                 if (!e) e = scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream);
             }
             float* kout = zc ? dst : h->d_out;
-            if (h->tailReady) {
-                if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, h->stream);
-                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, &h->headPass, kout, h->stream);
-            } else {
-                if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream);
-                if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->stream);
-            }
+            /* `stream`: [HEAD pass | full MAC] of this block (count c), then straight on with the TAIL pass of block
+             * c+1 (block index handed over explicitly: K3 has not bumped the device counter yet; partial tiles into
+             * the other tail buffer).  K3 of this block runs beside that tail pass on the high-priority side stream. */
+            const unsigned int c = h->count;
+            const int tb = (int)(c & 1u);
+            const int hadTail = h->tailReady;
+            if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }
+            else         { if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream); }
             h->tailReady = 0;
-            if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
-            if (!e) e = scdev_event_record(h->evDone, h->stream);
-            if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, h->stream);
-            if (!e) { h->tailReady = 1; e = scdev_event_sync(h->evDone); }
+            if (!e) e = scdev_event_record(h->evMac, h->stream);
+            if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
+            if (!e) e = scdev_stream_wait_event(h->streamOut, h->evMac);
+            if (hadTail) { if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut); }
+            else         { if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->streamOut); }
+            if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
+            if (!e) e = scdev_event_record(h->evDone, h->streamOut);
+            if (!e) { h->tailReady = 1; h->count = c + 1; e = scdev_event_sync(h->evDone); }
             if (e) { h->tailReady = 0; h_fail(h, SAFCONV_ERR_CUDA, "apply (look-ahead)", e); return; }
             if (!direct) memcpy(out, h->h_out, h->outBytes);
             return;
@@ -600,6 +614,7 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
     }
     if (!e) e = scdev_stream_sync(h->stream);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
+    h->count++;
     if (!direct) memcpy(out, h->h_out, h->outBytes);
 }
 
@@ -751,6 +766,7 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
         e = enqueue_blocks(h, d_in + (size_t)b * inStride, d_out + (size_t)b * outStride, n);
     }
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "apply_device", e);
+    h->count += (unsigned int)nBlocks;
     return SAFCONV_OK;
 }
 
@@ -841,6 +857,7 @@ int safconv_reset_state(void* hp)
     if (!e && h->b.tail2) e = scdev_memset_async(h->b.tail2, 0, sizeof(float) * (size_t)h->pl.nOutLocal * h->pl.hop, h->stream);
     if (!e) e = scdev_memset_async(h->b.counters, 0, 4 * sizeof(unsigned int), h->stream);
     if (!e) e = scdev_stream_sync(h->stream);
+    h->count = 0;
     return e ? h_fail(h, SAFCONV_ERR_CUDA, "reset_state", e) : SAFCONV_OK;
 }
 

@@ -144,6 +144,8 @@ struct MacArgs {
     long long totalStages;
     int nIn, OTsz, P, nKT, SNI, SPU, WGo, WGk, hints;
     int pLo, nP;                   /* this pass covers partitions [pLo, pLo + nP) of every group (full pass: 0, P) */
+    int useCount; unsigned int count;   /* useCount: the block counter is given by the host (`count`) instead of read from
+                                         * counters[0] -- a tail pass enqueued before the previous block's K3 has bumped it */
     int NS;                        /* pipeline depth (stages)                */
     int RS, blk, nB;               /* delay-line ring size; first block of this launch inside the batch; blocks in this launch */
     size_t zpStride;               /* float2 elements of Zp per block */
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
             int s = 0; uint32_t par = 1;
             /* the blocks of a batch are streamed back to back: the pipeline never drains between blocks */
             for (int blk = 0; blk < a.nB; ++blk) {
-                const int head = (int)((a.counters[0] + (unsigned)(a.blk + blk)) % (unsigned)a.RS);   /* newest slot */
+                const unsigned int cnt0 = a.useCount ? a.count : a.counters[0];
+                const int head = (int)((cnt0 + (unsigned)(a.blk + blk)) % (unsigned)a.RS);   /* newest slot */
                 const float2* srcH = srcH0;
                 int sidx = sidx0, p = p0, kt = kt0;
                 for (int i = 0; i < nIt; ++i) {
@@ -830,6 +833,12 @@ int scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes, void* stream)
 }
 int scdev_stream_create(void** s)
 { cudaStream_t st; cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); *s = (void*)st; return (int)e; }
+int scdev_stream_create_high_priority(void** s)
+{
+    int lo = 0, hi = 0;
+    SC_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));        /* hi = numerically lowest = greatest priority */
+    cudaStream_t st; cudaError_t e = cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi); *s = (void*)st; return (int)e;
+}
 int scdev_stream_destroy(void* s) { return s ? (int)cudaStreamDestroy((cudaStream_t)s) : 0; }
 int scdev_stream_sync(void* s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
 int scdev_event_create(void** e) { cudaEvent_t ev; cudaError_t r = cudaEventCreate(&ev); *e = (void*)ev; return (int)r; }
@@ -935,15 +944,18 @@ int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, v
     scdev_macpass full;
     full.pLo = 0; full.nP = pl->P; full.totalStages = pl->totalStages; full.grid = pl->macGrid; full.nSlots = pl->nSlots;
     full.ctaBase = b->ctaBase; full.grpStart = b->grpStart; full.Zp = b->Zp;
-    return scdev_mac_pass(pl, b, &full, blk, nBlocks, stream);
+    full.ZpB = NULL;
+    return scdev_mac_pass(pl, b, &full, blk, nBlocks, 0, -1, stream);
 }
 
-int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks, void* stream)
+int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* ps, int blk, int nBlocks,
+                   int zpSel, long long count, void* stream)
 {
     MacArgs a;
     a.H = (const float2*)b->H; a.X = (const float2*)b->X;
     a.zpStride = (size_t)ps->nSlots * pl->OTsz * SC_BK;
-    a.Zp = (float2*)ps->Zp + (size_t)blk * a.zpStride;
+    a.Zp = (float2*)(zpSel ? ps->ZpB : ps->Zp) + (size_t)blk * a.zpStride;
+    a.useCount = count >= 0; a.count = (unsigned int)(count >= 0 ? count : 0);
     a.nB = nBlocks;
     a.counters = b->counters; a.ctaBase = ps->ctaBase;
     a.totalStages = ps->totalStages; a.pLo = ps->pLo; a.nP = ps->nP;
@@ -968,15 +980,15 @@ static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* 
 
 int scdev_ifft_ola(const scdev_plan* pl, const scdev_bufs* b, float* d_out, void* stream)
 {
-    return scdev_ifft_ola_passes(pl, b, NULL, NULL, d_out, stream);
+    return scdev_ifft_ola_passes(pl, b, NULL, 0, NULL, d_out, stream);
 }
 
-int scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, const scdev_macpass* p2,
+int scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpass* p1, int zpSel1, const scdev_macpass* p2,
                           float* d_out, void* stream)
 {
     IfftArgs a;
     fill_ifft_args(a, pl, b, d_out, 1);
-    if (p1) { a.Zp = (const float2*)p1->Zp; a.grpStart = p1->grpStart; }
+    if (p1) { a.Zp = (const float2*)(zpSel1 ? p1->ZpB : p1->Zp); a.grpStart = p1->grpStart; }
     if (p2) { a.Zp2 = (const float2*)p2->Zp; a.grpStart2 = p2->grpStart; }
     ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();

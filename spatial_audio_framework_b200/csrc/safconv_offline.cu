@@ -683,8 +683,13 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         int fl = v ? atoi(v) : 1;
         o->flush = fl < 1 ? 1 : fl;
         v = getenv("SAFCONV_OFF_FPC");      o->fpc = v ? ((atoi(v) == 2) ? 2 : 4) : (o->f16 ? 2 : 4);
-        v = getenv("SAFCONV_OFF_OPC");      o->opc = (v && atoi(v) == 8) ? 8 : 4;
+        v = getenv("SAFCONV_OFF_OPC");      o->opc = (v && atoi(v) == 4) ? 4 : 8;
         v = getenv("SAFCONV_OFF_THREADS");  o->fftThreads = (v && atoi(v) == 128) ? 128 : 256;
+        /* fewer transforms per CTA when the FFT work arrays of the default batch do not fit in shared memory */
+        const size_t arr = (size_t)SC_ALEN(pl->M) * 8, cap = 227 * 1024;
+        while (o->fpc > 1 && (size_t)(o->ipc * o->fpc + 1) * arr > cap) o->fpc >>= 1;
+        if (o->opc == 8 && 9 * arr > cap) o->opc = 4;
+        if ((size_t)(o->ipc * o->fpc + 1) * arr > cap || (size_t)(o->opc + 1) * arr > cap) return (int)cudaErrorInvalidValue;
     }
     if (!o->packed) {
         const size_t hgBytes = (size_t)pl->M * pl->P * o->nKG * Nn * 16;
@@ -709,11 +714,8 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         SC_CHECK(cudaGetLastError());
         SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
         SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        const int fftSmem = (4 * OFF_FPC + 1) * SC_ALEN(pl->M) * 8, ifftSmem = (OFF_OPC + 1) * SC_ALEN(pl->M) * 8;
-        if ((o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8 > 227 * 1024) o->fpc = 2;
-        if ((o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8 > 227 * 1024 || ifftSmem > 227 * 1024) return (int)cudaErrorInvalidValue;
-        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fftSmem > 227 * 1024 ? 227 * 1024 : fftSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ifftSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         o->packed = 1;
     }
     if (T > o->capFrames) {
