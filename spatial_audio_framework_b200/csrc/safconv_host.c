@@ -540,6 +540,17 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
         if (!direct) memcpy(out, h->h_out, h->outBytes);
         return;
     }
+    if (h->pl.kind == SC_KIND_MULTI && h->smallFused && !h->useGraph && !h->timingCap &&
+        h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
+        /* latency path: the fused per-channel kernel reads / writes the page-locked host buffers directly
+         * (one launch and one synchronisation, no copy-engine round trips) */
+        e = scdev_multi_fused(&h->pl, &h->b, src, dst, h->stream);
+        if (!e) e = scdev_stream_sync(h->stream);
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (multi, zero-copy)", e); return; }
+        h->count++;
+        if (!direct) memcpy(out, h->h_out, h->outBytes);
+        return;
+    }
     if (h->useGraph && h->pl.kind != SC_KIND_TV) {
         if (h->graphExec && (h->graphIn != (void*)src || h->graphOut != (void*)dst)) {
             scdev_graph_destroy(h->graphExec);

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
 
@@ -421,6 +422,8 @@ struct MultiArgs {
     float* zt;             /* batched path: [B][nCH][2*hop] */
     unsigned int* counters;
     int hop, M, logM, P, RS, nCH;
+    int B, G;              /* batched path: blocks in the batch, consecutive blocks per CTA (MAC + inverse FFT) */
+    int Q;                 /* batched path: consecutive blocks per forward-FFT CTA */
     float scale;
 };
 
@@ -490,62 +493,125 @@ __global__ void multi_fused_kernel(MultiArgs a)
 /* ---- multiConv, batch of B device-resident blocks: every (channel, block) pair is independent once the
  * spectra of all B blocks are in the ring, so the work is two fully parallel launches + the overlap-add chain ---- */
 
-/* grid (nCH, B): forward FFT of block b of channel c into ring slot (counter + b) % RS */
+/* grid (nCH, ceil(B/Q)), Q <= SC_MULTI_FFT_Q: forward FFTs of Q consecutive blocks b of channel c into ring slots
+ * (counter + b) % RS; the Q transforms advance together (one barrier per pass for all of them) */
+#define SC_MULTI_FFT_Q 4
 __global__ void multi_fft_batch_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    float2* stw = sm + SC_ALEN(a.M);
-    const int c = blockIdx.x, b = blockIdx.y;
-    const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
-    const bool wide = fft_use_wide(a.M, 1);
+    const int MP = SC_ALEN(a.M);
+    float2* stw = sm + (size_t)a.Q * MP;
+    const int c = blockIdx.x, b0 = blockIdx.y * a.Q;
+    const int nq = min(a.Q, a.B - b0);
+    const unsigned int count = a.counters[0];
+    const bool wide = fft_use_wide(a.M, 1);            /* same core as the one-block kernel: identical bits */
     load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
-    load_real_block(sm, a.in + ((size_t)b * a.nCH + c) * a.hop, a.hop, a.M, a.logM);
+    for (int q = 0; q < nq; ++q)
+        load_real_block(sm + (size_t)q * MP, a.in + ((size_t)(b0 + q) * a.nCH + c) * a.hop, a.hop, a.M, a.logM);
     __syncthreads();
-    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
-    float2* Xnew = a.X + ((size_t)c * a.RS + slot) * a.M;
-    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+    cfft_dif_batch<false>(sm, a.M, a.logM, stw, nq, wide);
+    const int per = (a.M >> 1) + 1;
+    for (int it = threadIdx.x; it < nq * per; it += blockDim.x) {
+        const int q = it / per, k = it - q * per;
+        const float2* s = sm + (size_t)q * MP;
+        const int slot = (int)((count + (unsigned)(b0 + q)) % (unsigned)a.RS);
+        float2* Xnew = a.X + ((size_t)c * a.RS + slot) * a.M;
         float2 Xk, Xmk;
         int k2 = a.M - k;
         if (k == 0) {
-            const float2 z = sm[0];
+            const float2 z = s[0];
             Xk = make_float2(z.x + z.y, z.x - z.y);
             k2 = 0; Xmk = Xk;
         } else {
-            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
+            fwd_split_pair(s, k, a.M, a.logM, spl, Xk, Xmk);
         }
         Xnew[k] = Xk;  Xnew[k2] = Xmk;
     }
 }
 
-/* grid (nCH, B): Z = sum_p H_p * X_{t_b - p} (same order as the one-block kernel), inverse FFT -> zt[b][c][0..2*hop) */
+/* grid (nCH, ceil(B/G)): for G consecutive blocks b of channel c: Z = sum_p H_p * X_{t_b - p} (same order as the
+ * one-block kernel), inverse FFT -> zt[b][c][0..2*hop).  The blocks of a CTA share the channel's filter spectra and
+ * all but one delay-line slot with their neighbour, so after the first block the MAC reads come out of L1. */
 __global__ void multi_mac_ifft_batch_kernel(MultiArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     float2* stw = sm + SC_ALEN(a.M);
-    const int c = blockIdx.x, b = blockIdx.y;
-    const int head = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
-    const float2* Xc = a.X + (size_t)c * a.RS * a.M;
-    const float2* Hc = a.H + (size_t)c * a.P * a.M;
+    const int c = blockIdx.x;
+    const float2* __restrict__ Xc = a.X + (size_t)c * a.RS * a.M;
+    const float2* __restrict__ Hc = a.H + (size_t)c * a.P * a.M;
     const bool wide = fft_use_wide(a.M, 1);
     load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
-    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
-        const bool packed = (k == 0);
-        float2 acc = make_float2(0.f, 0.f);
-        int slot = head;
+    const unsigned int count = a.counters[0];
+    for (int b = blockIdx.y * a.G; b < min(a.B, (int)(blockIdx.y + 1) * a.G); ++b) {
+        const int head = (int)((count + (unsigned)b) % (unsigned)a.RS);
+        for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+            const bool packed = (k == 0);
+            float2 acc = make_float2(0.f, 0.f);
+            int slot = head;
 #pragma unroll 8
-        for (int p = 0; p < a.P; ++p) {
-            cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), Xc[(size_t)slot * a.M + k], packed);
-            slot = (slot == 0) ? a.RS - 1 : slot - 1;
+            for (int p = 0; p < a.P; ++p) {
+                cmac_packed(acc, __ldg(Hc + (size_t)p * a.M + k), __ldg(Xc + (size_t)slot * a.M + k), packed);
+                slot = (slot == 0) ? a.RS - 1 : slot - 1;
+            }
+            sm[padi(k, a.logM)] = acc;
         }
-        sm[padi(k, a.logM)] = acc;
+        __syncthreads();
+        inv_split_all(sm, a.M, a.logM, spl);
+        cfft_dif<true>(sm, a.M, a.logM, stw, wide);
+        float* z = a.zt + ((size_t)b * a.nCH + c) * 2 * a.hop;
+        for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
+        __syncthreads();
     }
-    __syncthreads();
-    inv_split_all(sm, a.M, a.logM, spl);
-    cfft_dif<true>(sm, a.M, a.logM, stw, wide);
-    float* z = a.zt + ((size_t)b * a.nCH + c) * 2 * a.hop;
-    for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
+}
+
+/* Same work with the operands in REGISTERS: one thread per bin (blockDim = M <= 1024), the P <= PT filter values of
+ * the bin and a sliding window of its last P delay-line values stay in registers across the G consecutive blocks
+ * of the CTA -- per block and bin one new 8-byte load instead of 2P.  Same summation order, identical bits.
+ * Used for M <= 512. */
+template <int PT>
+__global__ void __launch_bounds__(512, 1) multi_mac_ifft_batch_reg_kernel(MultiArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + SC_ALEN(a.M);
+    const int c = blockIdx.x, k = threadIdx.x;
+    const float2* __restrict__ Xc = a.X + (size_t)c * a.RS * a.M + k;
+    const float2* __restrict__ Hc = a.H + (size_t)c * a.P * a.M + k;
+    const bool wide = fft_use_wide(a.M, 1);
+    const unsigned int count = a.counters[0];
+    const int b0 = blockIdx.y * a.G, b1 = min(a.B, b0 + a.G);
+    const bool packed = (k == 0);
+    float2 h[PT], xw[PT];
+    int slot = (int)((count + (unsigned)b0) % (unsigned)a.RS);          /* newest slot of block b0 */
+    {
+        int sl = slot;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+            h[p]  = (p < a.P) ? __ldg(Hc + (size_t)p * a.M) : make_float2(0.f, 0.f);
+            xw[p] = (p >= 1 && p < a.P) ? __ldg(Xc + (size_t)sl * a.M) : make_float2(0.f, 0.f);
+            sl = (sl == 0) ? a.RS - 1 : sl - 1;
+        }
+    }
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    for (int b = b0; b < b1; ++b) {
+        xw[0] = __ldg(Xc + (size_t)slot * a.M);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < a.P) cmac_packed(acc, h[p], xw[p], packed);
+        sm[padi(k, a.logM)] = acc;
+        __syncthreads();
+        inv_split_all(sm, a.M, a.logM, spl);
+        cfft_dif<true>(sm, a.M, a.logM, stw, wide);
+        float* z = a.zt + ((size_t)b * a.nCH + c) * 2 * a.hop;
+        for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
+        __syncthreads();
+#pragma unroll
+        for (int p = PT - 1; p >= 1; --p) xw[p] = xw[p - 1];
+        slot = (slot + 1 == a.RS) ? 0 : slot + 1;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -873,6 +939,9 @@ static size_t fft_smem(const scdev_plan* pl, int nbuf)
     return ((size_t)nbuf * SC_ALEN(pl->M) + sc_split_len(pl->M)) * sizeof(float2);
 }
 
+/* forward FFTs per CTA of the batched multiConv path: 4 while the work arrays stay small enough for >= 3 CTAs per SM */
+static int multi_fft_q(const scdev_plan* pl) { return fft_smem(pl, SC_MULTI_FFT_Q + 1) <= 64 * 1024 ? SC_MULTI_FFT_Q : 1; }
+
 typedef void (*mac_fn_t)(MacArgs);
 static mac_fn_t mac_fn(int R)
 {
@@ -898,10 +967,11 @@ int scdev_prepare(const scdev_plan* pl)
         SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SC_CHECK(cudaFuncSetAttribute(ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
-    if (pl->kind == SC_KIND_MULTI && fft_smem(pl, 3) > 48 * 1024) {
-        SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 3)));
-        SC_CHECK(cudaFuncSetAttribute(multi_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
-        SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 2)));
+    if (pl->kind == SC_KIND_MULTI) {
+        const size_t need[3] = { fft_smem(pl, 3), fft_smem(pl, multi_fft_q(pl) + 1), fft_smem(pl, 2) };
+        if (need[0] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[0]));
+        if (need[1] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[1]));
+        if (need[2] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[2]));
     }
     if (pl->kind == SC_KIND_TV && fft_smem(pl, 5) > 48 * 1024)
         SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 5)));
@@ -1011,6 +1081,7 @@ static void fill_multi_args(MultiArgs& a, const scdev_plan* pl, const scdev_bufs
     a.in = d_in; a.out = d_out; a.H = (const float2*)b->H; a.X = (float2*)b->X;
     a.tw = (const float2*)b->tw; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.RS = pl->RS; a.nCH = pl->nOutLocal;
+    a.B = 1; a.G = 1; a.Q = 1;
     a.scale = 1.0f / (float)pl->N;
 }
 
@@ -1022,9 +1093,32 @@ int scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_
     const int threads = pl->M < 64 ? 64 : (pl->M > 512 ? 512 : pl->M);
     dim3 grid(pl->nOutLocal, nBlocks);
     if (which == 0) {
-        multi_fft_batch_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+        a.B = nBlocks; a.Q = multi_fft_q(pl);
+        dim3 gridQ(pl->nOutLocal, (nBlocks + a.Q - 1) / a.Q);
+        multi_fft_batch_kernel<<<gridQ, pl->fftThreads, fft_smem(pl, a.Q + 1), (cudaStream_t)stream>>>(a);
     } else if (which == 1) {
-        multi_mac_ifft_batch_kernel<<<grid, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+        /* consecutive blocks per CTA: as many as keep >= ~4 CTAs per SM in flight, at most 8 */
+        static int gEnv = -1;
+        if (gEnv < 0) { const char* v = getenv("SAFCONV_MULTI_G"); gEnv = v ? atoi(v) : 0; }
+        int G = gEnv > 0 ? gEnv : 8;
+        while (G > 1 && (long long)pl->nOutLocal * ((nBlocks + G - 1) / G) < 4 * 148) G >>= 1;
+        a.B = nBlocks; a.G = G;
+        dim3 gridG(pl->nOutLocal, (nBlocks + G - 1) / G);
+        static int regEnv = -1;
+        if (regEnv < 0) { const char* v = getenv("SAFCONV_MULTI_REG"); regEnv = v ? atoi(v) : 1; }
+        const int PT = pl->P <= 2 ? 2 : (pl->P <= 4 ? 4 : (pl->P <= 8 ? 8 : 16));
+        if (regEnv && pl->P <= 16 && pl->M <= 512) {      /* one thread per bin, <= 128 registers per thread */
+            const size_t smem = fft_smem(pl, 2);
+            cudaStream_t st = (cudaStream_t)stream;
+            switch (PT) {
+                case 2:  multi_mac_ifft_batch_reg_kernel<2><<<gridG, pl->M, smem, st>>>(a); break;
+                case 4:  multi_mac_ifft_batch_reg_kernel<4><<<gridG, pl->M, smem, st>>>(a); break;
+                case 8:  multi_mac_ifft_batch_reg_kernel<8><<<gridG, pl->M, smem, st>>>(a); break;
+                default: multi_mac_ifft_batch_reg_kernel<16><<<gridG, pl->M, smem, st>>>(a); break;
+            }
+        } else {
+            multi_mac_ifft_batch_kernel<<<gridG, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+        }
     } else {
         IfftArgs o;
         o.Zp = NULL; o.grpStart = NULL; o.Zp2 = NULL; o.grpStart2 = NULL; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
