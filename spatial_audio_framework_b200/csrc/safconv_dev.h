@@ -93,6 +93,8 @@ typedef struct scdev_offline {
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
     float *scal;             /* fp16 operands: [0] bound on the input spectra of the current render, [1] bound on the filter spectra */
     int f16, ipc;            /* 1: fp16 operands (default), 0: tf32; inputs per k-group (4 / 2)                 */
+    int wfft;                /* 1: warp-register FFT transform kernels (fp16 operands, M <= 1024)                */
+    void *wtab;              /* their two [M/32][32] twiddle tables                                              */
     int capFrames, capTpad, capRows, packed;
     int Nn, Kp, nKG, nKC, rowsX, tmemCols, gemmSmem, flush, fpc, opc, fftThreads;
 } scdev_offline;

@@ -38,6 +38,7 @@
 #include <string.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
+#include "safconv_wfft.cuh"
 
 #define OFF_MT   256     /* frames per CTA tile = two M=128 accumulators                     */
 #define OFF_KG   4       /* k-groups (of 4 floats) per pipeline chunk: K = 16 per chunk      */
@@ -197,6 +198,8 @@ struct OffFftArgs {
     int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
     int fpc;               /* frames per CTA (2 or 4): 32- or 64-byte contiguous operand stores */
     int ipc;               /* inputs per CTA = inputs per k-group: 2 (tf32) or 4 (fp16) */
+    const float2* wT1;     /* warp-FFT tables (device, [R][32] each): step-2 twiddles, split twiddles */
+    const float2* wT2;
 };
 
 __global__ void offline_fft_kernel(OffFftArgs a)
@@ -585,6 +588,7 @@ struct OffIfftArgs {
     int opc;               /* outputs per inverse-FFT CTA (4 or 8): 32- or 64-byte contiguous spectrum loads */
     int skip;              /* leading halo frames that are transformed but not written to `out` */
     float scale;
+    const float2* wT1;     /* warp-FFT step-2 twiddle table (device, [R][32]) */
 };
 
 __global__ void offline_ifft_kernel(OffIfftArgs a)
@@ -640,6 +644,206 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/*  Warp-FFT versions of the two transform kernels (fp16 operands, M = 32 R <= 1024):            */
+/*  every warp owns one transform and keeps it in registers (safconv_wfft.cuh); shared memory is  */
+/*  only the staging area that turns the per-transform results into the operand layout's          */
+/*  contiguous pieces (forward) / the contiguous spectrum reads into per-transform lanes (inverse) */
+/* ------------------------------------------------------------------------------------------ */
+#define OFFW_THREADS 256          /* 8 warps = 8 transforms per CTA */
+
+/* forward: grid (rows / 2, ceil(nIn / 4)); warp q -> frame row0 + (q >> 2), input 4 kg + (q & 3) */
+template <int R>
+__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_w_kernel(OffFftArgs a)
+{
+    constexpr int M = 32 * R, LOGR = wf_log2(R);
+    extern __shared__ __align__(16) unsigned char smw[];
+    const float2* __restrict__ T1 = a.wT1;                     /* [R][32] W_M^(l * bitrev_R(i)), read through L1   */
+    const float2* __restrict__ T2 = a.wT2;                     /* [R][32] W_N^k of the bin that (lane, slot) holds */
+    uint32_t* stgHi = reinterpret_cast<uint32_t*>(smw);        /* [k2 * 32 + k1][9]: the 8 transforms (+1 pad)     */
+    uint32_t* stgLo = stgHi + M * 9;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kg = blockIdx.y, row0 = blockIdx.x * 2;
+    const WfftLane L = wfft_lane_init<false>(a.tw, M, lane);
+    const int f = warp >> 2, ni = 4 * kg + (warp & 3);
+    const int t = row0 + f - (a.P - 1);
+    float2 v[R];
+    {
+        const bool valid = ni < a.nIn && t >= 0 && t < a.T;
+        const float* x = a.in + (size_t)(valid ? ni : 0) * a.inStride + (size_t)(valid ? t : 0) * a.hop;
+        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0) && ((a.inStride & 1) == 0);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int n = lane + 32 * i;
+            v[i] = make_float2(0.f, 0.f);
+            if (valid) {
+                if (vec) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                else {
+                    if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
+                    if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+                }
+            }
+        }
+    }
+    wfft<R, false>(v, T1, lane, L);
+
+    /* real-FFT split in registers: X[k] = (E + W_N^k O) / 2, E = a + conj b, O = -i (a - conj b), b = Z[M - k] */
+    const float sc = 0.5f * pow2_scale(a.scal[0]);
+    const int k1 = (int)(__brev((unsigned)lane) >> 27);
+    const int pl0 = (int)(__brev((unsigned)((32 - k1) & 31)) >> 27);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int k2 = wf_bitrev(i, LOGR);
+        const int ip = wf_bitrev((R - k2) % R, LOGR);
+        float2 b;
+        if (k2 == 0) { b.x = __shfl_sync(0xffffffffu, v[0].x, pl0);     b.y = __shfl_sync(0xffffffffu, v[0].y, pl0); }
+        else         { b.x = __shfl_xor_sync(0xffffffffu, v[ip].x, 31); b.y = __shfl_xor_sync(0xffffffffu, v[ip].y, 31); }
+        const float2 A = v[i];
+        const float2 E = make_float2(A.x + b.x, A.y - b.y);
+        const float2 O = make_float2(A.y + b.y, b.x - A.x);
+        const float2 tt = cmulf(__ldg(T2 + i * 32 + lane), O);
+        float2 X = make_float2((E.x + tt.x) * sc, (E.y + tt.y) * sc);
+        if (k2 == 0 && lane == 0) X = make_float2((A.x + A.y) * (2.f * sc), (A.x - A.y) * (2.f * sc));   /* packed (DC, Nyquist) */
+        __half h0, l0, h1, l1;
+        f16_split(X.x, h0, l0);  f16_split(X.y, h1, l1);
+        const int w = (k2 * 32 + k1) * 9 + warp;
+        stgHi[w] = pack_h2(h0, h1);
+        stgLo[w] = pack_h2(l0, l1);
+    }
+    __syncthreads();
+    /* one 16-byte k-group (4 inputs) per row and bin; the two rows of the CTA are adjacent in the operand and are
+     * written by adjacent lanes: one full 32-byte sector per lane pair and store instruction */
+    for (int idx = threadIdx.x; idx < 2 * M; idx += OFFW_THREADS) {
+        const int f2 = idx & 1, q = idx >> 1;
+        const int kk1 = q & 31, kk2 = q >> 5;
+        const int k = kk2 + R * kk1;
+        const uint32_t* h = stgHi + (kk2 * 32 + kk1) * 9 + 4 * f2;
+        const uint32_t* l = stgLo + (kk2 * 32 + kk1) * 9 + 4 * f2;
+        const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f2) * 16;
+        *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(a.XGlo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+/* inverse: grid (ceil(nOut / 8), T); warp o -> output 8 og + o of frame t */
+template <int R>
+__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_w_kernel(OffIfftArgs a)
+{
+    constexpr int M = 32 * R, LOGR = wf_log2(R);
+    constexpr int OS = M + 33;                                 /* float2 per output in the time-domain staging */
+    extern __shared__ __align__(16) unsigned char smw[];
+    const float2* __restrict__ T1 = a.wT1;                     /* read through L1 */
+    float2* stg = reinterpret_cast<float2*>(smw);              /* spectra [k][9] (8 outputs + pad), then time samples [8][OS] */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int og = blockIdx.x, t = blockIdx.y;
+    const WfftLane L = wfft_lane_init<true>(a.tw, M, lane);
+    /* spectra of the 8 outputs of this frame: 64-byte contiguous pieces, eight independent loads in flight per thread */
+    for (int base = threadIdx.x; base < M * 8; base += 8 * OFFW_THREADS) {
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base + q * OFFW_THREADS;
+            const int j = idx & 7, k = idx >> 3;
+            const int no = og * 8 + j;
+            u[q] = (idx < M * 8 && no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base + q * OFFW_THREADS;
+            if (idx < M * 8) stg[(idx >> 3) * 9 + (idx & 7)] = u[q];
+        }
+    }
+    __syncthreads();
+    /* inverse split while loading the transform into (lane, slot) order: Zc[k] = E + i O,
+     * E = A + conj B, O = (A - conj B) conj(W_N^k), B = Y[M - k]  (the 1/2 is folded into 1/N) */
+    float2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int k = lane + 32 * i;
+        const float2 A = stg[k * 9 + warp], B = stg[((M - k) & (M - 1)) * 9 + warp];
+        const float2 E = make_float2(A.x + B.x, A.y - B.y);
+        const float2 D = make_float2(A.x - B.x, A.y + B.y);
+        const float2 O = cmul_conjb(D, __ldg(a.tw + k));
+        v[i] = make_float2(E.x - O.y, E.y + O.x);
+        if (i == 0 && lane == 0) v[i] = make_float2(A.x + A.y, A.x - A.y);      /* (DC, Nyquist) */
+    }
+    wfft<R, true>(v, T1, lane, L);
+    __syncthreads();                                           /* every warp is done with the spectra */
+    {
+        float2* ost = stg + (size_t)warp * OS;
+        const int k1 = (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+        for (int i = 0; i < R; ++i)                            /* z[n], n = n2 + R k1, stored at n2 + (R + 1) k1 */
+            ost[wf_bitrev(i, LOGR) + (R + 1) * k1] = make_float2(v[i].x * a.scale, v[i].y * a.scale);
+    }
+    __syncthreads();
+    /* overlap-add (reference .c:230-233) with two-addend atomic adds, exactly like offline_ifft_kernel */
+    const int To = a.T - a.skip;
+    const int f0 = t - a.skip, f1 = t + 1 - a.skip;
+    for (int j = 0; j < 8; ++j) {
+        const int no = og * 8 + j;
+        if (no >= a.nOut) break;
+        const float* ost = reinterpret_cast<const float*>(stg + (size_t)j * OS);
+        float* o = a.out + (size_t)no * To * a.hop;
+        for (int i = threadIdx.x; i < a.hop; i += OFFW_THREADS) {
+            const int s1 = i + a.hop;
+            const int n0 = i >> 1, n1 = s1 >> 1;
+            const float z0 = ost[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)];
+            const float z1 = ost[2 * ((n1 & (R - 1)) + (R + 1) * (n1 >> LOGR)) + (s1 & 1)];
+            if (f0 >= 0)            atomicAdd(o + (size_t)f0 * a.hop + i, z0);
+            if (f1 >= 0 && f1 < To) atomicAdd(o + (size_t)f1 * a.hop + i, z1);
+        }
+    }
+}
+
+template <int R> static size_t offw_fft_smem()  { return (size_t)(2 * 32 * R * 9) * 4; }
+template <int R> static size_t offw_ifft_smem()
+{
+    const size_t M = 32 * R, a = M * 9, b = 8 * (M + 33);
+    return (a > b ? a : b) * 8;
+}
+
+/* the two [R][32] tables of the warp-FFT kernels, built once per handle: T1[i][l] = W_M^(l * bitrev_R(i)),
+ * T2[i][l] = W_N^k for the bin k = bitrev_R(i) + R * bitrev_5(l) that (lane l, slot i) holds after the transform */
+__global__ void offw_tables_kernel(const float2* __restrict__ gtw, float2* T1, float2* T2, int M, int logR)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    const int R = M >> 5, i = idx >> 5, l = idx & 31;
+    const int k2 = logR ? (int)(__brev((unsigned)i) >> (32 - logR)) : 0;
+    const int e = 2 * l * k2;
+    float2 w = gtw[e & (M - 1)];
+    if (e >= M) { w.x = -w.x; w.y = -w.y; }
+    T1[idx] = w;
+    T2[idx] = gtw[k2 + R * (int)(__brev((unsigned)l) >> 27)];
+}
+
+template <int R>
+static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
+{
+    if (f) {
+        SC_CHECK(cudaFuncSetAttribute(offline_fft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offw_fft_smem<R>()));
+        offline_fft_w_kernel<R><<<grid, OFFW_THREADS, offw_fft_smem<R>(), st>>>(*f);
+    } else {
+        SC_CHECK(cudaFuncSetAttribute(offline_ifft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offw_ifft_smem<R>()));
+        offline_ifft_w_kernel<R><<<grid, OFFW_THREADS, offw_ifft_smem<R>(), st>>>(*i);
+    }
+    return (int)cudaGetLastError();
+}
+
+static int offw_dispatch(int M, const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
+{
+    switch (M) {
+        case 64:   return offw_launch<2>(f, i, grid, st);
+        case 128:  return offw_launch<4>(f, i, grid, st);
+        case 256:  return offw_launch<8>(f, i, grid, st);
+        case 512:  return offw_launch<16>(f, i, grid, st);
+        case 1024: return offw_launch<32>(f, i, grid, st);
+        default:   return (int)cudaErrorInvalidValue;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /*  C-ABI                                                                                        */
 /* ------------------------------------------------------------------------------------------ */
@@ -650,8 +854,8 @@ static size_t roundup(size_t v, size_t m) { return (v + m - 1) / m * m; }
 int scdev_offline_free(scdev_offline* o)
 {
     if (!o) return 0;
-    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys); cudaFree(o->scal);
-    o->XGhi = o->XGlo = o->HGhi = o->HGlo = NULL; o->Ys = NULL; o->scal = NULL;
+    cudaFree(o->XGhi); cudaFree(o->XGlo); cudaFree(o->HGhi); cudaFree(o->HGlo); cudaFree(o->Ys); cudaFree(o->scal); cudaFree(o->wtab);
+    o->XGhi = o->XGlo = o->HGhi = o->HGlo = NULL; o->Ys = NULL; o->scal = NULL; o->wtab = NULL;
     o->capFrames = 0; o->packed = 0;
     return 0;
 }
@@ -685,6 +889,15 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         v = getenv("SAFCONV_OFF_FPC");      o->fpc = v ? ((atoi(v) == 2) ? 2 : 4) : (o->f16 ? 2 : 4);
         v = getenv("SAFCONV_OFF_OPC");      o->opc = (v && atoi(v) == 4) ? 4 : 8;
         v = getenv("SAFCONV_OFF_THREADS");  o->fftThreads = (v && atoi(v) == 128) ? 128 : 256;
+        /* warp-FFT transform kernels: fp16 operands, M = 64 .. 1024 (SAFCONV_OFF_WFFT=0 selects the shared-memory ones) */
+        v = getenv("SAFCONV_OFF_WFFT");
+        o->wfft = o->f16 && pl->M >= 64 && pl->M <= 1024 && !(v && atoi(v) == 0);
+        if (o->wfft && !o->wtab) {
+            SC_CHECK(cudaMalloc((void**)&o->wtab, (size_t)2 * pl->M * sizeof(float2)));
+            offw_tables_kernel<<<(pl->M + 255) / 256, 256, 0, st>>>((const float2*)b->tw, (float2*)o->wtab, (float2*)o->wtab + pl->M,
+                                                                     pl->M, pl->logM - 5);
+            SC_CHECK(cudaGetLastError());
+        }
         /* fewer transforms per CTA when the FFT work arrays of the default batch do not fit in shared memory */
         const size_t arr = (size_t)SC_ALEN(pl->M) * 8, cap = 227 * 1024;
         while (o->fpc > 1 && (size_t)(o->ipc * o->fpc + 1) * arr > cap) o->fpc >>= 1;
@@ -760,11 +973,17 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     f.inStride = (size_t)T * pl->hop;
     f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
+    f.wT1 = (const float2*)o->wtab; f.wT2 = o->wtab ? (const float2*)o->wtab + pl->M : NULL;
     {
         f.fpc = o->fpc; f.ipc = o->ipc;
-        dim3 grid(rowsUsed / o->fpc, (pl->nIn + o->ipc - 1) / o->ipc);
-        offline_fft_kernel<<<grid, o->fftThreads, (size_t)(o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
-        SC_CHECK(cudaGetLastError());
+        if (o->wfft) {
+            dim3 grid(rowsUsed / 2, (pl->nIn + 3) / 4);
+            { const int e_ = offw_dispatch(pl->M, &f, NULL, grid, st); if (e_) return e_; }
+        } else {
+            dim3 grid(rowsUsed / o->fpc, (pl->nIn + o->ipc - 1) / o->ipc);
+            offline_fft_kernel<<<grid, o->fftThreads, (size_t)(o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
+            SC_CHECK(cudaGetLastError());
+        }
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[1], st));
     OffGemmArgs g;
@@ -784,12 +1003,18 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     i.Ys = (const float2*)o->Ys; i.out = d_out; i.tw = (const float2*)b->tw;
     i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
     i.Tpad = o->capTpad; i.T = T; i.skip = skip; i.scale = 1.0f / (float)pl->N;
+    i.wT1 = (const float2*)o->wtab;
     {
         i.opc = o->opc;
-        dim3 grid((pl->nOutLocal + o->opc - 1) / o->opc, T);
         SC_CHECK(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)pl->nOutLocal * (T - skip) * pl->hop, st));
-        offline_ifft_kernel<<<grid, o->fftThreads, (size_t)(o->opc + 1) * SC_ALEN(pl->M) * 8, st>>>(i);
-        SC_CHECK(cudaGetLastError());
+        if (o->wfft) {
+            dim3 grid((pl->nOutLocal + 7) / 8, T);
+            { const int e_ = offw_dispatch(pl->M, NULL, &i, grid, st); if (e_) return e_; }
+        } else {
+            dim3 grid((pl->nOutLocal + o->opc - 1) / o->opc, T);
+            offline_ifft_kernel<<<grid, o->fftThreads, (size_t)(o->opc + 1) * SC_ALEN(pl->M) * 8, st>>>(i);
+            SC_CHECK(cudaGetLastError());
+        }
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[3], st));
     return 0;
