@@ -797,6 +797,125 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_w_kernel(OffIfft
     }
 }
 
+
+/* ---- M = 1024: the same two kernels on the shuffle-free 32 x 32 register FFT (wfft32t) ---- */
+
+/* forward: warp q -> frame row0 + (q >> 2), input 4 kg + (q & 3); the complex spectra Z of the 8 transforms are left
+ * in the warps' tiles in natural order, the whole CTA then does the real-FFT split, the fp16 hi/lo conversion and
+ * the operand stores (one 16-byte k-group per thread and (bin, row)) */
+__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftArgs a)
+{
+    constexpr int M = 1024;
+    extern __shared__ __align__(16) unsigned char smw[];
+    float2* tiles = reinterpret_cast<float2*>(smw);            /* [8][WFFT_TILE] */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kg = blockIdx.y, row0 = blockIdx.x * 2;
+    float2* tile = tiles + (size_t)warp * WFFT_TILE;
+    {
+        const int f = warp >> 2, ni = 4 * kg + (warp & 3);
+        const int t = row0 + f - (a.P - 1);
+        float2 v[32];
+        const bool valid = ni < a.nIn && t >= 0 && t < a.T;
+        const float* x = a.in + (size_t)(valid ? ni : 0) * a.inStride + (size_t)(valid ? t : 0) * a.hop;
+        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0) && ((a.inStride & 1) == 0);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int n = lane + 32 * i;
+            v[i] = make_float2(0.f, 0.f);
+            if (valid) {
+                if (vec) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                else {
+                    if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
+                    if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+                }
+            }
+        }
+        wfft32t<false>(v, a.wT1, lane, tile);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[lane + 32 * wf_bitrev(i, 5)] = v[i];      /* Z[k], natural order */
+    }
+    __syncthreads();
+    const float sc = 0.5f * pow2_scale(a.scal[0]);
+    for (int idx = threadIdx.x; idx < 2 * M; idx += OFFW_THREADS) {
+        const int f = idx & 1, k = idx >> 1;
+        const float2 w = __ldg(a.tw + k);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2* z = tiles + (size_t)(4 * f + j) * WFFT_TILE;
+            const float2 A = z[k], b = z[(M - k) & (M - 1)];
+            /* X[k] = (E + W_N^k O) / 2, E = a + conj b, O = -i (a - conj b) */
+            const float2 E = make_float2(A.x + b.x, A.y - b.y);
+            const float2 O = make_float2(A.y + b.y, b.x - A.x);
+            const float2 tt = cmulf(w, O);
+            float2 X = make_float2((E.x + tt.x) * sc, (E.y + tt.y) * sc);
+            if (k == 0) X = make_float2((A.x + A.y) * (2.f * sc), (A.x - A.y) * (2.f * sc));   /* packed (DC, Nyquist) */
+            __half h0, l0, h1, l1;
+            f16_split(X.x, h0, l0);  f16_split(X.y, h1, l1);
+            hi[j] = pack_h2(h0, h1);  lo[j] = pack_h2(l0, l1);
+        }
+        const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f) * 16;
+        *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a.XGlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+/* inverse: warp o -> output 8 og + o of frame t */
+__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_t_kernel(OffIfftArgs a)
+{
+    constexpr int M = 1024;
+    extern __shared__ __align__(16) unsigned char smw[];
+    float2* stg = reinterpret_cast<float2*>(smw);              /* spectra [k][9] (8 outputs + pad); then the warps' tiles */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int og = blockIdx.x, t = blockIdx.y;
+    for (int base = threadIdx.x; base < M * 8; base += 8 * OFFW_THREADS) {
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base + q * OFFW_THREADS;
+            const int j = idx & 7, k = idx >> 3;
+            const int no = og * 8 + j;
+            u[q] = (no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base + q * OFFW_THREADS;
+            stg[(idx >> 3) * 9 + (idx & 7)] = u[q];
+        }
+    }
+    __syncthreads();
+    float2 v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int k = lane + 32 * i;
+        const float2 A = stg[k * 9 + warp], B = stg[((M - k) & (M - 1)) * 9 + warp];
+        const float2 E = make_float2(A.x + B.x, A.y - B.y);
+        const float2 D = make_float2(A.x - B.x, A.y + B.y);
+        const float2 O = cmul_conjb(D, __ldg(a.tw + k));
+        v[i] = make_float2(E.x - O.y, E.y + O.x);
+        if (i == 0 && lane == 0) v[i] = make_float2(A.x + A.y, A.x - A.y);      /* (DC, Nyquist) */
+    }
+    __syncthreads();                                           /* every warp is done with the spectra */
+    float2* tile = stg + (size_t)warp * WFFT_TILE;
+    wfft32t<true>(v, a.wT1, lane, tile);
+#pragma unroll
+    for (int i = 0; i < 32; ++i)                               /* z[n], natural order */
+        tile[lane + 32 * wf_bitrev(i, 5)] = make_float2(v[i].x * a.scale, v[i].y * a.scale);
+    __syncthreads();
+    const int To = a.T - a.skip;
+    const int f0 = t - a.skip, f1 = t + 1 - a.skip;
+    for (int j = 0; j < 8; ++j) {
+        const int no = og * 8 + j;
+        if (no >= a.nOut) break;
+        const float* z = reinterpret_cast<const float*>(stg + (size_t)j * WFFT_TILE);
+        float* o = a.out + (size_t)no * To * a.hop;
+        for (int i = threadIdx.x; i < a.hop; i += OFFW_THREADS) {
+            if (f0 >= 0)            atomicAdd(o + (size_t)f0 * a.hop + i, z[i]);
+            if (f1 >= 0 && f1 < To) atomicAdd(o + (size_t)f1 * a.hop + i, z[i + a.hop]);
+        }
+    }
+}
+
 template <int R> static size_t offw_fft_smem()  { return (size_t)(2 * 32 * R * 9) * 4; }
 template <int R> static size_t offw_ifft_smem()
 {
@@ -832,8 +951,20 @@ static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cud
     return (int)cudaGetLastError();
 }
 
-static int offw_dispatch(int M, const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
+static int offw_dispatch(int M, int variant, const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
 {
+    if (M == 1024 && variant == 2) {                           /* shuffle-free 32 x 32 version */
+        if (f) {
+            const size_t smem = (size_t)8 * WFFT_TILE * 8;
+            SC_CHECK(cudaFuncSetAttribute(offline_fft_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            offline_fft_t_kernel<<<grid, OFFW_THREADS, smem, st>>>(*f);
+        } else {
+            const size_t smem = (size_t)1024 * 9 * 8;           /* >= 8 tiles */
+            SC_CHECK(cudaFuncSetAttribute(offline_ifft_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            offline_ifft_t_kernel<<<grid, OFFW_THREADS, smem, st>>>(*i);
+        }
+        return (int)cudaGetLastError();
+    }
     switch (M) {
         case 64:   return offw_launch<2>(f, i, grid, st);
         case 128:  return offw_launch<4>(f, i, grid, st);
@@ -891,7 +1022,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         v = getenv("SAFCONV_OFF_THREADS");  o->fftThreads = (v && atoi(v) == 128) ? 128 : 256;
         /* warp-FFT transform kernels: fp16 operands, M = 64 .. 1024 (SAFCONV_OFF_WFFT=0 selects the shared-memory ones) */
         v = getenv("SAFCONV_OFF_WFFT");
-        o->wfft = o->f16 && pl->M >= 64 && pl->M <= 1024 && !(v && atoi(v) == 0);
+        o->wfft = (o->f16 && pl->M >= 64 && pl->M <= 1024) ? (v ? atoi(v) : 2) : 0;     /* 2: shuffle-free version at M = 1024 */
         if (o->wfft && !o->wtab) {
             SC_CHECK(cudaMalloc((void**)&o->wtab, (size_t)2 * pl->M * sizeof(float2)));
             offw_tables_kernel<<<(pl->M + 255) / 256, 256, 0, st>>>((const float2*)b->tw, (float2*)o->wtab, (float2*)o->wtab + pl->M,
@@ -978,7 +1109,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
         f.fpc = o->fpc; f.ipc = o->ipc;
         if (o->wfft) {
             dim3 grid(rowsUsed / 2, (pl->nIn + 3) / 4);
-            { const int e_ = offw_dispatch(pl->M, &f, NULL, grid, st); if (e_) return e_; }
+            { const int e_ = offw_dispatch(pl->M, o->wfft, &f, NULL, grid, st); if (e_) return e_; }
         } else {
             dim3 grid(rowsUsed / o->fpc, (pl->nIn + o->ipc - 1) / o->ipc);
             offline_fft_kernel<<<grid, o->fftThreads, (size_t)(o->ipc * o->fpc + 1) * SC_ALEN(pl->M) * 8, st>>>(f);
@@ -1009,7 +1140,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
         SC_CHECK(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)pl->nOutLocal * (T - skip) * pl->hop, st));
         if (o->wfft) {
             dim3 grid((pl->nOutLocal + 7) / 8, T);
-            { const int e_ = offw_dispatch(pl->M, NULL, &i, grid, st); if (e_) return e_; }
+            { const int e_ = offw_dispatch(pl->M, o->wfft, NULL, &i, grid, st); if (e_) return e_; }
         } else {
             dim3 grid((pl->nOutLocal + o->opc - 1) / o->opc, T);
             offline_ifft_kernel<<<grid, o->fftThreads, (size_t)(o->opc + 1) * SC_ALEN(pl->M) * 8, st>>>(i);

@@ -145,4 +145,28 @@ __device__ __forceinline__ void wfft(float2 (&v)[R], const float2* __restrict__ 
     }
 }
 
+/* M = 1024 = 32 x 32 without shuffles: 32-point DIF in registers, twiddle, transpose through a warp-private
+ * shared-memory tile (32 x 33 float2: unit-stride writes, stride-33 reads, both conflict-free), second 32-point DIF in
+ * registers.  Lane j holds v[i] = x[j + 32 i] on entry; on exit lane l, slot i holds X[l + 32 * bitrev_5(i)].
+ * The shuffle version issues 10 SHFL per point through the same LSU data pipe that serves shared memory (ncu: the
+ * transform kernels were MIO-bound on it); this one needs 2 shared-memory accesses per point. */
+#define WFFT_TILE 1056     /* float2 per warp: 32 rows x 33 */
+template <bool INV>
+__device__ __forceinline__ void wfft32t(float2 (&v)[32], const float2* __restrict__ T1, int lane, float2* tile)
+{
+    dif_regs32<32, INV>(v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        float2 w = __ldg(T1 + i * 32 + lane);
+        if (INV) w.y = -w.y;
+        if (i) v[i] = cmulf(v[i], w);
+        tile[wf_bitrev(i, 5) * 33 + lane] = v[i];               /* row k2, column j */
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tile[lane * 33 + j];    /* lane = k2 */
+    dif_regs32<32, INV>(v);
+    __syncwarp();                                               /* the tile may be overwritten by the caller */
+}
+
 #endif /* SAFCONV_WFFT_CUH_INCLUDED */
