@@ -508,7 +508,7 @@ def run_own_arm(args, w):
                 traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per block x blocks per launch)"
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "mac_kernel (K2 filter-streaming complex MAC)" if w["kind"] == "matrix" else "multi_mac_ifft_batch_kernel (per-channel MAC + inverse FFT, batched)",
+    roofline = {"bound": "hbm", "kernel": "mac_kernel (K2 filter-streaming complex MAC)" if w["kind"] == "matrix" else "multi_mac_ifft_w_kernel (per-channel MAC with a register sliding window + warp-level inverse FFT, batched)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": mac_bytes, "avg_launch_ms": mac_ms,
                 "launches_timed": ngroups, "blocks_per_launch": blocks_per_launch, "rank": 0,

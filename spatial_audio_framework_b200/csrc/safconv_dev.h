@@ -84,6 +84,7 @@ typedef struct scdev_bufs {
     unsigned int* counters; /* [0] block counter, [1] last-CTA ticket                       */
     int*   ctaBase;   /* int[macGrid]   first partial slot of each MAC CTA                  */
     int*   grpStart;  /* int[nGroups+1] partial slots of group g: grpStart[g]..grpStart[g+1]-1 */
+    void*  wtab;      /* float2[2][M]  twiddle tables of the warp-level register FFT (multiConv batched path) or NULL */
 } scdev_bufs;
 
 /* workspace of the offline (batched frames, tensor-core) path, see safconv_offline.cu */
@@ -159,6 +160,8 @@ int  scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offl
 int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
                        const float* d_in, float* d_out, int T, int skip, void** events, void* stream);
 int  scdev_offline_free(scdev_offline* o);
+/* build b->wtab (no-op outside 64 <= M <= 1024) */
+int  scdev_wfft_tables(const scdev_plan* pl, scdev_bufs* b, void* stream);
 /* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */
 int  scdev_is_pinned_host(const void* p);
 /* small matrix problems: K1+K2+K3 in one launch, one CTA per output channel; in/out may be mapped host memory */

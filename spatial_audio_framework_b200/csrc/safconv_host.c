@@ -258,7 +258,7 @@ static void handle_free(safconv_handle* h)
     for (int i = 0; i < 4; i++) scdev_event_destroy(h->offEv[i]);
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
-    scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart);
+    scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart); scdev_free(h->b.wtab);
     scdev_free(h->tailPass.ctaBase); scdev_free(h->tailPass.grpStart); scdev_free(h->tailPass.Zp);
     scdev_free(h->headPass.ctaBase); scdev_free(h->headPass.grpStart); scdev_free(h->headPass.Zp);
     if (h->streamIn) scdev_stream_sync(h->streamIn);
@@ -411,6 +411,8 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
     }
+    if (kind == SC_KIND_MULTI && env_int("SAFCONV_MULTI_WFFT", 1, 0, 1))
+        DEV_TRY(h, scdev_wfft_tables(pl, &h->b, h->stream), "warp-FFT tables");
     DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
     h->smallOk = (kind == SC_KIND_MATRIX) ? scdev_small_fits(pl, h->maxSmem) : 0;
 

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
+#include "safconv_wfft.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /*  K0: filter partition + forward FFT                                                         */
@@ -424,6 +425,8 @@ struct MultiArgs {
     int hop, M, logM, P, RS, nCH;
     int B, G;              /* batched path: blocks in the batch, consecutive blocks per CTA (MAC + inverse FFT) */
     int Q;                 /* batched path: consecutive blocks per forward-FFT CTA */
+    const float2* wT1;     /* warp-FFT tables ([M/32][32] each, safconv_wfft.cuh) or NULL */
+    const float2* wT2;
     float scale;
 };
 
@@ -612,6 +615,140 @@ __global__ void __launch_bounds__(512, 1) multi_mac_ifft_batch_reg_kernel(MultiA
         for (int p = PT - 1; p >= 1; --p) xw[p] = xw[p - 1];
         slot = (slot + 1 == a.RS) ? 0 : slot + 1;
     }
+}
+
+
+/* ---- batched multiConv on the warp-level register FFT (safconv_wfft.cuh), 64 <= M <= 1024 ---- */
+
+/* forward: grid (nCH, ceil(B/8)), 256 threads; warp q transforms block 8 blockIdx.y + q of channel c into its ring slot.
+ * The spectrum leaves the registers through a warp-private padded tile so that the ring is written in 256-byte rows. */
+template <int R>
+__global__ void __launch_bounds__(256) multi_fft_w_kernel(MultiArgs a)
+{
+    constexpr int M = 32 * R, LOGR = wf_log2(R), TS = M + 32;
+    extern __shared__ __align__(16) float2 smt[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x, b = blockIdx.y * 8 + warp;
+    if (b >= a.B) return;
+    float2* tile = smt + (size_t)warp * TS;
+    const WfftLane L = wfft_lane_init<false>(a.tw, M, lane);
+    const float* x = a.in + ((size_t)b * a.nCH + c) * a.hop;
+    const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    float2 v[R], X[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int n = lane + 32 * i;
+        v[i] = make_float2(0.f, 0.f);
+        if (vec) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+        else {
+            if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
+            if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+        }
+    }
+    wfft<R, false>(v, a.wT1, lane, L);
+    wfft_fwd_split<R>(v, X, a.wT2, lane, 0.5f);
+    const int k1 = (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+    for (int i = 0; i < R; ++i) tile[wf_bitrev(i, LOGR) + (R + 1) * k1] = X[i];    /* bin k = k2 + R k1 at k + (k >> LOGR) */
+    __syncwarp();
+    const int slot = (int)((a.counters[0] + (unsigned)b) % (unsigned)a.RS);
+    float2* Xnew = a.X + ((size_t)c * a.RS + slot) * M;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int k = lane + 32 * i;
+        Xnew[k] = tile[k + (k >> LOGR)];
+    }
+}
+
+/* MAC + inverse: grid (nCH, ceil(B/R)), M = 32 R threads.  Phase 1, one thread per bin: the bin's P <= PT filter
+ * values and a sliding window of its last P delay-line values stay in registers across the R consecutive blocks of
+ * the CTA (one new 8-byte load per block), the R output spectra go to shared memory.  Phase 2, one warp per block:
+ * inverse split while loading, inverse FFT in registers, 1/N, time samples back through the warp's tile to zt. */
+template <int R, int PT>
+__global__ void __launch_bounds__(32 * R, 1) multi_mac_ifft_w_kernel(MultiArgs a)
+{
+    constexpr int M = 32 * R, LOGR = wf_log2(R), TS = M + 32;
+    extern __shared__ __align__(16) float2 smt[];              /* [R][TS] */
+    const int c = blockIdx.x, k = threadIdx.x;
+    const int b0 = blockIdx.y * R, nb = min(R, a.B - b0);
+    const unsigned int count = a.counters[0];
+    {
+        const float2* __restrict__ Xc = a.X + (size_t)c * a.RS * M + k;
+        const float2* __restrict__ Hc = a.H + (size_t)c * a.P * M + k;
+        const bool packed = (k == 0);
+        float2 h[PT], xw[PT];
+        int slot = (int)((count + (unsigned)b0) % (unsigned)a.RS);
+        {
+            int sl = slot;
+#pragma unroll
+            for (int p = 0; p < PT; ++p) {
+                h[p]  = (p < a.P) ? __ldg(Hc + (size_t)p * M) : make_float2(0.f, 0.f);
+                xw[p] = (p >= 1 && p < a.P) ? __ldg(Xc + (size_t)sl * M) : make_float2(0.f, 0.f);
+                sl = (sl == 0) ? a.RS - 1 : sl - 1;
+            }
+        }
+        for (int bb = 0; bb < nb; ++bb) {
+            xw[0] = __ldg(Xc + (size_t)slot * M);
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < PT; ++p)
+                if (p < a.P) cmac_packed(acc, h[p], xw[p], packed);
+            smt[(size_t)bb * TS + k] = acc;
+#pragma unroll
+            for (int p = PT - 1; p >= 1; --p) xw[p] = xw[p - 1];
+            slot = (slot + 1 == a.RS) ? 0 : slot + 1;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= nb) return;
+    float2* tile = smt + (size_t)warp * TS;
+    const WfftLane L = wfft_lane_init<true>(a.tw, M, lane);
+    float2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int kk = lane + 32 * i;
+        const float2 A = tile[kk], B = tile[(M - kk) & (M - 1)];
+        const float2 E = make_float2(A.x + B.x, A.y - B.y);
+        const float2 D = make_float2(A.x - B.x, A.y + B.y);
+        const float2 O = cmul_conjb(D, __ldg(a.tw + kk));
+        v[i] = make_float2(E.x - O.y, E.y + O.x);
+        if (i == 0 && lane == 0) v[i] = make_float2(A.x + A.y, A.x - A.y);      /* (DC, Nyquist) */
+    }
+    __syncwarp();
+    wfft<R, true>(v, a.wT1, lane, L);
+    const int k1 = (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+    for (int i = 0; i < R; ++i)                                /* z[n], n = n2 + R k1, stored at n + (n >> LOGR) */
+        tile[wf_bitrev(i, LOGR) + (R + 1) * k1] = make_float2(v[i].x * a.scale, v[i].y * a.scale);
+    __syncwarp();
+    float* z = a.zt + ((size_t)(b0 + warp) * a.nCH + c) * 2 * a.hop;
+    const float* ts = reinterpret_cast<const float*>(tile);
+    for (int s = lane; s < 2 * a.hop; s += 32) {
+        const int n = s >> 1;
+        z[s] = ts[2 * (n + (n >> LOGR)) + (s & 1)];
+    }
+}
+
+template <int R>
+static int multi_w_launch(const scdev_plan* pl, MultiArgs& a, int nBlocks, int which, cudaStream_t st)
+{
+    constexpr int M = 32 * R;
+    const size_t tile = (size_t)(M + 32) * sizeof(float2);
+    if (which == 0) {
+        dim3 grid(pl->nOutLocal, (nBlocks + 7) / 8);
+        if (8 * tile > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * tile)));
+        multi_fft_w_kernel<R><<<grid, 256, 8 * tile, st>>>(a);
+    } else {
+        dim3 grid(pl->nOutLocal, (nBlocks + R - 1) / R);
+        const size_t smem = (size_t)R * tile;
+#define SC_MW_LAUNCH(PT) do {                                                                                        \
+            if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_w_kernel<R, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            multi_mac_ifft_w_kernel<R, PT><<<grid, M, smem, st>>>(a); } while (0)
+        if (pl->P <= 2) SC_MW_LAUNCH(2); else if (pl->P <= 4) SC_MW_LAUNCH(4); else if (pl->P <= 8) SC_MW_LAUNCH(8); else SC_MW_LAUNCH(16);
+#undef SC_MW_LAUNCH
+    }
+    return (int)cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1082,6 +1219,7 @@ static void fill_multi_args(MultiArgs& a, const scdev_plan* pl, const scdev_bufs
     a.tw = (const float2*)b->tw; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.RS = pl->RS; a.nCH = pl->nOutLocal;
     a.B = 1; a.G = 1; a.Q = 1;
+    a.wT1 = (const float2*)b->wtab; a.wT2 = b->wtab ? (const float2*)b->wtab + pl->M : NULL;
     a.scale = 1.0f / (float)pl->N;
 }
 
@@ -1092,6 +1230,18 @@ int scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_
     fill_multi_args(a, pl, b, d_in, d_out);
     const int threads = pl->M < 64 ? 64 : (pl->M > 512 ? 512 : pl->M);
     dim3 grid(pl->nOutLocal, nBlocks);
+    /* warp-FFT kernels: forward for 64 <= M <= 1024; MAC + inverse for M <= 512 and P <= 16 (register window).  Both or
+     * neither, so that a handle uses one FFT algorithm throughout its batched path. */
+    if (b->wtab && which <= 1 && pl->M >= 64 && pl->M <= 512 && pl->P <= 16) {
+        a.B = nBlocks;
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (pl->M) {
+            case 64:  return multi_w_launch<2>(pl, a, nBlocks, which, st);
+            case 128: return multi_w_launch<4>(pl, a, nBlocks, which, st);
+            case 256: return multi_w_launch<8>(pl, a, nBlocks, which, st);
+            default:  return multi_w_launch<16>(pl, a, nBlocks, which, st);
+        }
+    }
     if (which == 0) {
         a.B = nBlocks; a.Q = multi_fft_q(pl);
         dim3 gridQ(pl->nOutLocal, (nBlocks + a.Q - 1) / a.Q);
@@ -1183,6 +1333,16 @@ int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in
     const size_t smem = small_smem(pl, SC_SMALL_THREADS);
     if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     small_fused_kernel<<<pl->nOutLocal, SC_SMALL_THREADS, smem, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+/* warp-FFT twiddle tables of a handle (b->wtab), 64 <= M <= 1024; b->tw must be uploaded already */
+int scdev_wfft_tables(const scdev_plan* pl, scdev_bufs* b, void* stream)
+{
+    if (pl->M < 64 || pl->M > 1024) return 0;
+    SC_CHECK(cudaMalloc(&b->wtab, (size_t)2 * pl->M * sizeof(float2)));
+    wfft_tables_kernel<<<(pl->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)b->tw, (float2*)b->wtab,
+                                                                            (float2*)b->wtab + pl->M, pl->M, pl->logM - 5);
     return (int)cudaGetLastError();
 }
 

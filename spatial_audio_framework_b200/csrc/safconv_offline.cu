@@ -923,21 +923,6 @@ template <int R> static size_t offw_ifft_smem()
     return (a > b ? a : b) * 8;
 }
 
-/* the two [R][32] tables of the warp-FFT kernels, built once per handle: T1[i][l] = W_M^(l * bitrev_R(i)),
- * T2[i][l] = W_N^k for the bin k = bitrev_R(i) + R * bitrev_5(l) that (lane l, slot i) holds after the transform */
-__global__ void offw_tables_kernel(const float2* __restrict__ gtw, float2* T1, float2* T2, int M, int logR)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M) return;
-    const int R = M >> 5, i = idx >> 5, l = idx & 31;
-    const int k2 = logR ? (int)(__brev((unsigned)i) >> (32 - logR)) : 0;
-    const int e = 2 * l * k2;
-    float2 w = gtw[e & (M - 1)];
-    if (e >= M) { w.x = -w.x; w.y = -w.y; }
-    T1[idx] = w;
-    T2[idx] = gtw[k2 + R * (int)(__brev((unsigned)l) >> 27)];
-}
-
 template <int R>
 static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
 {
@@ -1025,7 +1010,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         o->wfft = (o->f16 && pl->M >= 64 && pl->M <= 1024) ? (v ? atoi(v) : 2) : 0;     /* 2: shuffle-free version at M = 1024 */
         if (o->wfft && !o->wtab) {
             SC_CHECK(cudaMalloc((void**)&o->wtab, (size_t)2 * pl->M * sizeof(float2)));
-            offw_tables_kernel<<<(pl->M + 255) / 256, 256, 0, st>>>((const float2*)b->tw, (float2*)o->wtab, (float2*)o->wtab + pl->M,
+            wfft_tables_kernel<<<(pl->M + 255) / 256, 256, 0, st>>>((const float2*)b->tw, (float2*)o->wtab, (float2*)o->wtab + pl->M,
                                                                      pl->M, pl->logM - 5);
             SC_CHECK(cudaGetLastError());
         }

@@ -145,6 +145,47 @@ __device__ __forceinline__ void wfft(float2 (&v)[R], const float2* __restrict__ 
     }
 }
 
+/* the two [R][32] tables of the warp-FFT kernels in global memory, built once per handle (read through L1):
+ * T1[i][l] = W_M^(l * bitrev_R(i)),  T2[i][l] = W_N^k for the bin k = bitrev_R(i) + R * bitrev_5(l) that
+ * (lane l, slot i) holds after the transform */
+static __global__ void wfft_tables_kernel(const float2* __restrict__ gtw, float2* T1, float2* T2, int M, int logR)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    const int R = M >> 5, i = idx >> 5, l = idx & 31;
+    const int k2 = logR ? (int)(__brev((unsigned)i) >> (32 - logR)) : 0;
+    const int e = 2 * l * k2;
+    float2 w = gtw[e & (M - 1)];
+    if (e >= M) { w.x = -w.x; w.y = -w.y; }
+    T1[idx] = w;
+    T2[idx] = gtw[k2 + R * (int)(__brev((unsigned)l) >> 27)];
+}
+
+/* forward real-FFT split of a transform held in the wfft<R> layout: returns in X[i] the packed real spectrum value
+ * of the bin k = bitrev_R(i) + R * bitrev_5(lane) (bin 0 = (DC, Nyquist)), scaled by 2 * half:
+ * X[k] = (E + W_N^k O) / 2, E = a + conj b, O = -i (a - conj b), b = Z[M - k] fetched by shuffle */
+template <int R>
+__device__ __forceinline__ void wfft_fwd_split(const float2 (&v)[R], float2 (&X)[R], const float2* __restrict__ T2, int lane, float half)
+{
+    constexpr int LOGR = wf_log2(R);
+    const int k1 = (int)(__brev((unsigned)lane) >> 27);
+    const int pl0 = (int)(__brev((unsigned)((32 - k1) & 31)) >> 27);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int k2 = wf_bitrev(i, LOGR);
+        const int ip = wf_bitrev((R - k2) % R, LOGR);
+        float2 b;
+        if (k2 == 0) { b.x = __shfl_sync(0xffffffffu, v[0].x, pl0);     b.y = __shfl_sync(0xffffffffu, v[0].y, pl0); }
+        else         { b.x = __shfl_xor_sync(0xffffffffu, v[ip].x, 31); b.y = __shfl_xor_sync(0xffffffffu, v[ip].y, 31); }
+        const float2 A = v[i];
+        const float2 E = make_float2(A.x + b.x, A.y - b.y);
+        const float2 O = make_float2(A.y + b.y, b.x - A.x);
+        const float2 tt = cmulf(__ldg(T2 + i * 32 + lane), O);
+        X[i] = make_float2((E.x + tt.x) * half, (E.y + tt.y) * half);
+        if (k2 == 0 && lane == 0) X[i] = make_float2((A.x + A.y) * (2.f * half), (A.x - A.y) * (2.f * half));
+    }
+}
+
 /* M = 1024 = 32 x 32 without shuffles: 32-point DIF in registers, twiddle, transpose through a warp-private
  * shared-memory tile (32 x 33 float2: unit-stride writes, stride-33 reads, both conflict-free), second 32-point DIF in
  * registers.  Lane j holds v[i] = x[j + 32 i] on entry; on exit lane l, slot i holds X[l + 32 * bitrev_5(i)].

@@ -379,7 +379,8 @@ def test_offline_render_c5_shape_vs_streaming(saf):
 @pytest.mark.parametrize("hop,L,nCH,nblk", [(512, 4096, 16, 70), (64, 300, 3, 41), (2048, 9000, 2, 9)])
 def test_multiconv_batched_device_blocks(saf, orc, hop, L, nCH, nblk):
     """multiConv on device-resident blocks: all forward FFTs, then all (channel, block) MACs + inverse FFTs, then
-    the overlap-add chain -- bit-identical to one fused launch per block, across batch and ring boundaries."""
+    the overlap-add chain -- equal to one fused launch per block (bit-identical where both use the same FFT core),
+    across batch and ring boundaries."""
     import torch
     rng = np.random.default_rng(hop + nCH)
     H = rng.uniform(-1, 1, (nCH, L)).astype(np.float32)
@@ -399,8 +400,18 @@ def test_multiconv_batched_device_blocks(saf, orc, hop, L, nCH, nblk):
         mc.synchronize()
         outs.append(d_out.cpu().numpy().transpose(1, 0, 2).reshape(nCH, nblk * hop))
     check(outs[0], ref, "multiConv batched")
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
-    assert np.array_equal(saf.MultiConv(hop, H).run(x), outs[0])
+    yh = saf.MultiConv(hop, H).run(x)
+    if 2 * hop > 1024:
+        # shared-memory FFT everywhere: the batched kernels keep the summation order of the fused one-block kernel
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        assert np.array_equal(yh, outs[0])
+    else:
+        # FFT sizes up to 1024: the batched path runs on the warp-level register FFT, single blocks on the fused
+        # shared-memory kernel -- same values to rounding
+        for i, y in enumerate((outs[1], outs[2], yh)):
+            check(y, ref, f"multiConv path {i + 1}")
+            ma, l2 = err_metrics(y, outs[0])
+            assert ma <= 2e-6 and l2 <= 5e-7, (i, ma, l2)
 
 
 def test_pinned_caller_buffers_are_used_directly(saf, orc):
