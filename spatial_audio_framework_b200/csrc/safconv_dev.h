@@ -48,7 +48,7 @@ typedef struct scdev_plan {
     int nGroups, nSlots;
     int RS;                  /* delay-line ring slots = P + maxBatch            */
     int maxBatch;            /* blocks per batched launch group (>= 1)          */
-    int macHints;            /* 0/1: L2 eviction-priority hints              */
+    int macHints;            /* L2 eviction-priority hints: 0 none, 1 filters evict_first (streamed), 2 filters evict_last (fit in L2) */
     int macSmemBytes;
     int macStages;           /* TMA pipeline depth                           */
     int macStageBytes;       /* target bytes of H per stage                  */

@@ -345,7 +345,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     scdev_plan* pl = &h->pl;
     pl->kind = kind; pl->nIn = nIn; pl->nOutLocal = nOutLocal; pl->nIRs = nIRs;
     plan_fft(pl, hop, len);
-    pl->macHints = 1;
+    pl->macHints = env_int("SAFCONV_MAC_HINTS", -1, -1, 2);   /* -1: decided below from the size of the filter set */
     h->detectPinned = 1;
     h->batching = 1;
     h->smallFused = env_int("SAFCONV_SMALL_FUSED", 1, 0, 1);
@@ -383,6 +383,8 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         while (pl->maxBatch > 1 && (double)pl->maxBatch * slots * pl->OTsz * SC_BK * 8.0 > 256e6) pl->maxBatch >>= 1;
         pl->RS = pl->P + pl->maxBatch;
         h->bytesH  = (size_t)pl->nOT * pl->nKT * P * nIn * pl->OTsz * SC_BK * 8;
+        /* L2 policy of the filter stream: a filter set that fits in L2 (126 MB) is kept there between blocks */
+        if (pl->macHints < 0) pl->macHints = (h->bytesH <= ((size_t)64 << 20)) ? 2 : 1;
         h->bytesX  = (size_t)pl->nKT * pl->RS * nIn * SC_BK * 8;
         h->bytesZp = (size_t)pl->maxBatch * slots * pl->OTsz * SC_BK * 8;
         rowsTotal  = (size_t)nOutLocal * nIn;
@@ -971,7 +973,7 @@ int safconv_set_option(void* hp, const char* name, int value)
 {
     safconv_handle* h = as_handle(hp);
     if (!h || !name) return SAFCONV_ERR_ARG;
-    if (!strcmp(name, "mac_hints")) { h->pl.macHints = value ? 1 : 0; }
+    if (!strcmp(name, "mac_hints")) { h->pl.macHints = (value < 0 || value > 2) ? 1 : value; }
     else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
     else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
     else if (!strcmp(name, "small_fused")) { h->smallFused = value ? 1 : 0; }

@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(SC_MAC_THREADS, 1) mac_kernel(MacArgs a)
     if (warp == SC_MAC_CWARPS) {
         /* ===================== TMA producer (one elected lane) ===================== */
         if (lane == 0) {
-            const uint64_t polH = l2_policy_evict_first();              /* H is read exactly once per block */
+            /* H is read exactly once per block: evict_first -- unless the whole filter set fits in L2 (hints == 2),
+             * then it should stay there for the next block */
+            const uint64_t polH = (a.hints == 2) ? l2_policy_evict_last() : l2_policy_evict_first();
             const uint64_t polX = l2_policy_evict_last();               /* the FDL is re-read by every output tile */
             const float2* srcH0 = a.H + (((size_t)grp0 * a.P + p0) * a.nIn + (size_t)sidx0 * a.SNI) * a.OTsz * SC_BK;
             const size_t skipH = (size_t)(a.P - a.nP) * a.nIn * a.OTsz * SC_BK;   /* partitions of a group outside this pass */
