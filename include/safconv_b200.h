@@ -146,13 +146,29 @@ int safconv_apply_device(void* h, const float* d_in, float* d_out);
 int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nBlocks);
 
 /**
+ * Whole-signal per-channel linear convolution, the reference's fftconv / fftfilt
+ * (/root/reference/framework/modules/saf_utilities/saf_utility_fft.h:86-91, 107-112; .c:157-228):
+ * x FLAT nCH x x_len, h FLAT nCH x h_len (host pointers), y FLAT nCH x (x_len+h_len-1) for fftconv,
+ * nCH x x_len (the first x_len samples) for fftfilt.  Served by the multiConv engine (hop-sized blocks through the
+ * batched device path) instead of the reference's single nextpow2(x_len+h_len-1)-point FFT: same linear
+ * convolution, equal to fp32 rounding.  The safconv_ names return SAFCONV_OK or an error code; `fftconv` and
+ * `fftfilt` themselves are exported as WEAK symbols with the reference's void signatures, so the library can be
+ * preloaded in front of a SAF build without clashing with a statically linked saf_utility_fft.c.
+ */
+int  safconv_fftconv(const float* x, const float* h, int x_len, int h_len, int nCH, float* y);
+int  safconv_fftfilt(const float* x, const float* h, int x_len, int h_len, int nCH, float* y);
+void fftconv(float* x, float* h, int x_len, int h_len, int nCH, float* y);
+void fftfilt(float* x, float* h, int x_len, int h_len, int nCH, float* y);
+
+/**
  * Offline rendering of a whole signal (BASELINE.json configs[4]): all nFrames blocks are available at once,
  * so the per-bin sum over partitions x inputs becomes a dense contraction that re-uses every filter value
- * for all frames and runs on the tensor cores (tcgen05, tf32 operands split hi+lo, fp32 accumulation).
+ * for all frames and runs on the tensor cores (tcgen05, fp16 operands split hi+lo with exact power-of-two
+ * scaling -- or tf32 with SAFCONV_OFF_KIND=tf32 --, fp32 accumulation).
  * Equal (to fp32 rounding) to a fresh handle's saf_matrixConv_apply called nFrames times:
  * the state before the first frame is zero and the handle's streaming state is neither used nor changed.
  * Layouts are channel-major whole signals: in [nCHin][nFrames*hopSize], out [nOutLocal][nFrames*hopSize].
- * matrixConv handles only; needs nOutLocal <= 64 and hopSize <= 2048.
+ * matrixConv handles only; needs nOutLocal <= 64 and hopSize <= 4096.
  * _device: device pointers, enqueued on the handle's stream without synchronising.
  */
 int safconv_render_offline(void* h, const float* in, float* out, int nFrames);

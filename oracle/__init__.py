@@ -70,6 +70,9 @@ def load_oracle():
                                      C.POINTER(C.c_int), C.c_int, C.c_long, C.c_long, _f64p]
     lib.orc_truth_multi.argtypes = [_f32p, C.c_int, C.c_int, _f32p, C.c_long,
                                     C.POINTER(C.c_int), C.c_int, C.c_long, C.c_long, _f64p]
+    for f in (lib.orc_fftconv, lib.orc_fftfilt):
+        f.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p]
+        f.restype = None
     _oracle_lib = lib
     return lib
 
@@ -304,6 +307,28 @@ def oracle_rfft(N: int, x: np.ndarray):
     xb = np.zeros(N, np.float32)
     lib.orc_rfft_backward(N, _fp(X), _fp(xb))
     return X, xb
+
+
+def oracle_fftconv(x: np.ndarray, h: np.ndarray, filt: bool = False) -> np.ndarray:
+    """fftconv / fftfilt restatement (saf_utility_fft.c:157-228): x[nCH, x_len], h[nCH, h_len]."""
+    lib = load_oracle()
+    x = np.ascontiguousarray(x, np.float32); h = np.ascontiguousarray(h, np.float32)
+    nCH, xl = x.shape; hl = h.shape[1]
+    y = np.zeros((nCH, xl if filt else xl + hl - 1), np.float32)
+    (lib.orc_fftfilt if filt else lib.orc_fftconv)(_fp(x), _fp(h), xl, hl, nCH, _fp(y))
+    return y
+
+
+def ref_fftconv(x: np.ndarray, h: np.ndarray, filt: bool = False) -> np.ndarray:
+    """The compiled reference's own fftconv / fftfilt."""
+    lib, _ = load_reference()
+    x = np.ascontiguousarray(x, np.float32); h = np.ascontiguousarray(h, np.float32)
+    nCH, xl = x.shape; hl = h.shape[1]
+    y = np.zeros((nCH, xl if filt else xl + hl - 1), np.float32)
+    fn = lib.fftfilt if filt else lib.fftconv
+    fn.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p]; fn.restype = None
+    fn(_fp(x), _fp(h), xl, hl, nCH, _fp(y))
+    return y
 
 
 def truth_matrix(H: np.ndarray, x: np.ndarray, outs, n0: int, n1: int) -> np.ndarray:

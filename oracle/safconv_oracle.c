@@ -332,6 +332,43 @@ static void spec_mul(const cpx* a, const cpx* b, size_t n, cpx* c)
     for (size_t i = 0; i < n; i++) c[i] = c_mul(a[i], b[i]);
 }
 
+/* fftconv / fftfilt (modules/saf_utilities/saf_utility_fft.c:157-228): per-channel linear convolution through ONE
+ * real FFT of size nextpow2(x_len + h_len - 1) (saf_utility_misc.c:64-80), spectra multiplied with utility_cvvmul */
+void orc_fftconv(const float* x, const float* h, int x_len, int h_len, int nCH, float* y)
+{
+    const int y_len = x_len + h_len - 1;
+    int fftSize = 1;
+    do { fftSize *= 2; } while (fftSize < y_len);                 /* nextpow2: smallest 2^k >= y_len, k >= 1 */
+    const int nBins = fftSize / 2 + 1;
+    float* h0 = (float*)calloc((size_t)fftSize, sizeof(float));
+    float* x0 = (float*)calloc((size_t)fftSize, sizeof(float));
+    float* y0 = (float*)malloc((size_t)fftSize * sizeof(float));
+    cpx* H = (cpx*)malloc((size_t)nBins * sizeof(cpx));
+    cpx* X = (cpx*)malloc((size_t)nBins * sizeof(cpx));
+    cpx* Y = (cpx*)malloc((size_t)nBins * sizeof(cpx));
+    rfft_plan* r = rfft_plan_new(fftSize);
+    for (int i = 0; i < nCH; i++) {
+        memcpy(h0, h + (size_t)i * h_len, (size_t)h_len * sizeof(float));
+        memcpy(x0, x + (size_t)i * x_len, (size_t)x_len * sizeof(float));
+        rfft_forward(r, x0, X);
+        rfft_forward(r, h0, H);
+        spec_mul(X, H, (size_t)nBins, Y);
+        rfft_backward(r, Y, y0);
+        memcpy(y + (size_t)i * y_len, y0, (size_t)y_len * sizeof(float));
+    }
+    rfft_plan_free(r);
+    free(h0); free(x0); free(y0); free(H); free(X); free(Y);
+}
+
+void orc_fftfilt(const float* x, const float* h, int x_len, int h_len, int nCH, float* y)
+{
+    const int y_len = x_len + h_len - 1;
+    float* t = (float*)malloc((size_t)nCH * y_len * sizeof(float));
+    orc_fftconv(x, h, x_len, h_len, nCH, t);
+    for (int i = 0; i < nCH; i++) memcpy(y + (size_t)i * x_len, t + (size_t)i * y_len, (size_t)x_len * sizeof(float));
+    free(t);
+}
+
 static int ceil_div_as_ref(int num, int den)      /* (int)ceilf((float)num/(float)den), MC:102 */
 {
     return (int)ceilf((float)num / (float)den);

@@ -15,10 +15,12 @@ from ._capi import (  # noqa: F401
     MultiConv,
     TVConv,
     build,
+    fftconv,
+    fftfilt,
     lib,
     version,
 )
 from . import synth  # noqa: F401
 from . import sharding  # noqa: F401
 
-__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "lib", "version", "synth", "sharding"]
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "fftconv", "fftfilt", "lib", "version", "synth", "sharding"]

@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = [
     "safconv_set_option",
     "safconv_render_offline", "safconv_render_offline_device", "safconv_render_offline_segment_device",
     "safconv_get_offline_times",
+    "safconv_fftconv", "safconv_fftfilt", "fftconv", "fftfilt",
 ]
 
 
@@ -345,3 +346,27 @@ class TVConv(_Base):
         self._lib.saf_TVConv_apply(self._h, _fp(x), _fp(y), int(irIdx))
         self._raise_if_error()
         return y
+
+
+def fftconv(x: np.ndarray, h: np.ndarray, filt: bool = False) -> np.ndarray:
+    """fftconv / fftfilt (reference saf_utility_fft.h:86-113): x[nCH, x_len], h[nCH, h_len] ->
+    y[nCH, x_len + h_len - 1] (fftconv) or y[nCH, x_len] (fftfilt, filt=True)."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float32)
+    h = np.ascontiguousarray(h, np.float32)
+    nCH, xl = x.shape
+    assert h.shape[0] == nCH
+    hl = h.shape[1]
+    y = np.empty((nCH, xl if filt else xl + hl - 1), np.float32)
+    fn = L.safconv_fftfilt if filt else L.safconv_fftconv
+    fn.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    fn.restype = C.c_int
+    rc = fn(_fp(x), _fp(h), xl, hl, nCH, _fp(y))
+    if rc:
+        L.safconv_last_error_string.restype = C.c_char_p
+        raise RuntimeError("fftconv failed (%d): %s" % (rc, L.safconv_last_error_string(None).decode()))
+    return y
+
+
+def fftfilt(x: np.ndarray, h: np.ndarray) -> np.ndarray:
+    return fftconv(x, h, filt=True)

@@ -785,6 +785,69 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     return SAFCONV_OK;
 }
 
+/* ---- fftconv / fftfilt (reference saf_utility_fft.c:157-228) on the multiConv engine ---- */
+static int fftconv_impl(const float* x, const float* h, int x_len, int h_len, int nCH, float* y, int keep)
+{
+    if (!x || !h || !y || x_len < 1 || h_len < 1 || nCH < 1 || nCH > 65535) {
+        set_tl_error(SAFCONV_ERR_ARG, "fftconv: invalid argument%s", "");
+        return SAFCONV_ERR_ARG;
+    }
+    const long long y_len = (long long)x_len + h_len - 1;
+    /* block size: the filter in one or a few partitions, 64 <= hop <= 1024 */
+    int hop = 64;
+    while (hop < h_len && hop < 1024) hop <<= 1;
+    const long long nblk = (y_len + hop - 1) / hop;
+    if (nblk > 0x7fffffff / 2) { set_tl_error(SAFCONV_ERR_ARG, "fftconv: signal too long%s", ""); return SAFCONV_ERR_ARG; }
+    const float* chunk = h;
+    safconv_handle* hd = conv_create(SC_KIND_MULTI, hop, &chunk, 1, (size_t)nCH, h_len, nCH, nCH, nCH, 0, 0);
+    if (!hd) return tl_err ? tl_err : SAFCONV_ERR_CUDA;
+    const size_t blkElems = (size_t)nCH * hop, total = (size_t)nblk * blkElems;
+    float* hb = (float*)calloc(total, sizeof(float));           /* [nblk][nCH][hop], zero-padded */
+    float *d_in = NULL, *d_out = NULL;
+    int rc = SAFCONV_OK, e = 0;
+    if (!hb) { rc = h_fail(NULL, SAFCONV_ERR_NOMEM, "fftconv: host staging", 0); goto done; }
+    for (long long b = 0; b < nblk; b++) {
+        const long long s0 = b * hop;
+        if (s0 >= x_len) break;
+        const size_t n = (size_t)((x_len - s0 < hop) ? x_len - s0 : hop);
+        for (int c = 0; c < nCH; c++)
+            memcpy(hb + (size_t)b * blkElems + (size_t)c * hop, x + (size_t)c * x_len + s0, n * sizeof(float));
+    }
+    e = scdev_malloc((void**)&d_in, total * sizeof(float));
+    if (!e) e = scdev_malloc((void**)&d_out, total * sizeof(float));
+    if (!e) e = scdev_memcpy_h2d_sync(d_in, hb, total * sizeof(float), hd->stream);
+    if (e) { rc = h_fail(NULL, SAFCONV_ERR_CUDA, "fftconv: upload", e); goto done; }
+    rc = safconv_apply_device_blocks(hd, d_in, d_out, (int)nblk);
+    if (rc) { set_tl_error(rc, "fftconv: %.200s", hd->errmsg); goto done; }
+    e = scdev_memcpy_d2h_async(hb, d_out, total * sizeof(float), hd->stream);
+    if (!e) e = scdev_stream_sync(hd->stream);
+    if (e) { rc = h_fail(NULL, SAFCONV_ERR_CUDA, "fftconv: download", e); goto done; }
+    {
+        const long long out_len = keep ? x_len : y_len;
+        for (long long b = 0; b < nblk; b++) {
+            const long long s0 = b * hop;
+            if (s0 >= out_len) break;
+            const size_t n = (size_t)((out_len - s0 < hop) ? out_len - s0 : hop);
+            for (int c = 0; c < nCH; c++)
+                memcpy(y + (size_t)c * out_len + s0, hb + (size_t)b * blkElems + (size_t)c * hop, n * sizeof(float));
+        }
+    }
+done:
+    scdev_free(d_in); scdev_free(d_out);
+    free(hb);
+    handle_free(hd);
+    return rc;
+}
+
+int safconv_fftconv(const float* x, const float* h, int x_len, int h_len, int nCH, float* y)
+{ return fftconv_impl(x, h, x_len, h_len, nCH, y, 0); }
+int safconv_fftfilt(const float* x, const float* h, int x_len, int h_len, int nCH, float* y)
+{ return fftconv_impl(x, h, x_len, h_len, nCH, y, 1); }
+__attribute__((weak)) void fftconv(float* x, float* h, int x_len, int h_len, int nCH, float* y)
+{ (void)fftconv_impl(x, h, x_len, h_len, nCH, y, 0); }
+__attribute__((weak)) void fftfilt(float* x, float* h, int x_len, int h_len, int nCH, float* y)
+{ (void)fftconv_impl(x, h, x_len, h_len, nCH, y, 1); }
+
 /* ---- offline rendering: all frames at once, tensor-core per-bin contraction (safconv_offline.cu) ---- */
 int safconv_render_offline_segment_device(void* hp, const float* d_in, float* d_out, int nFrames, int nHaloFrames)
 {

@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def declared_symbols():
     txt = (ROOT / "include" / "safconv_b200.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    names = re.findall(r"\b((?:saf|safconv)_\w+)\s*\(", txt)
+    names = re.findall(r"\b((?:saf|safconv)_\w+|fftconv|fftfilt)\s*\(", txt)
     return sorted(set(names))
 
 

@@ -516,3 +516,23 @@ def test_c4_full_size_properties(saf):
     # zero input after reset -> exactly zero output
     mc.reset_state()
     assert not np.any(mc.apply(np.zeros((nIn, hop), np.float32)))
+
+
+@pytest.mark.parametrize("nCH,xl,hl", [(3, 1000, 129), (1, 5, 7), (2, 5000, 4096), (4, 300, 1), (6, 48000, 700)])
+def test_fftconv_fftfilt_vs_oracle(saf, orc, nCH, xl, hl):
+    """safconv_fftconv / safconv_fftfilt (drop-in for saf_utility_fft.h:86-113, served by the multiConv engine)
+    against the oracle's restatement of the reference's single-FFT implementation."""
+    import spatial_audio_framework_b200 as pkg
+    rng = np.random.default_rng(nCH * 7 + xl + hl)
+    x = rng.uniform(-1, 1, (nCH, xl)).astype(np.float32)
+    h = rng.uniform(-1, 1, (nCH, hl)).astype(np.float32)
+    check(pkg.fftconv(x, h), orc.oracle_fftconv(x, h), "fftconv")
+    check(pkg.fftfilt(x, h), orc.oracle_fftconv(x, h, True), "fftfilt")
+    # the reference-named weak symbols
+    import ctypes as C
+    L = saf.lib()
+    y = np.zeros((nCH, xl + hl - 1), np.float32)
+    fp = C.POINTER(C.c_float)
+    L.fftconv.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, fp]; L.fftconv.restype = None
+    L.fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), xl, hl, nCH, y.ctypes.data_as(fp))
+    check(y, orc.oracle_fftconv(x, h), "fftconv (reference-named symbol)")

@@ -95,3 +95,18 @@ def test_golden_close_to_fp64_truth(path):
     else:
         t = O.truth_multi(H, x, np.arange(H.shape[0]), 0, x.shape[1])
     assert np.linalg.norm(y - t) / np.linalg.norm(t) < 5e-7
+
+
+@pytest.mark.parametrize("nCH,xl,hl", [(3, 1000, 129), (1, 5, 7), (2, 4096, 4096), (4, 300, 1), (2, 1, 9)])
+def test_fftconv_fftfilt_oracle_equals_reference(nCH, xl, hl):
+    """fftconv / fftfilt (saf_utility_fft.c:157-228): restatement == compiled reference bit for bit, and both
+    close to the fp64 direct convolution."""
+    rng = np.random.default_rng(nCH + xl + hl)
+    x = rng.uniform(-1, 1, (nCH, xl)).astype(np.float32)
+    h = rng.uniform(-1, 1, (nCH, hl)).astype(np.float32)
+    for filt in (False, True):
+        a = O.oracle_fftconv(x, h, filt)
+        b = O.ref_fftconv(x, h, filt)
+        assert np.array_equal(a, b)
+        t = np.stack([np.convolve(x[i].astype(np.float64), h[i].astype(np.float64)) for i in range(nCH)])[:, :a.shape[1]]
+        assert np.abs(a - t).max() <= 2e-6 * max(np.abs(t).max(), 1e-30)
