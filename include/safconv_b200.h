@@ -172,6 +172,10 @@ void fftfilt(float* x, float* h, int x_len, int h_len, int nCH, float* y);
  * _device: device pointers, enqueued on the handle's stream without synchronising.
  */
 int safconv_render_offline(void* h, const float* in, float* out, int nFrames);
+/* host buffers with nHaloFrames leading history frames: in [nCHin][(nHaloFrames+nFrames)*hopSize], out [nOutLocal][nFrames*hopSize].
+ * Both host-buffer calls render signals longer than 512 frames in time segments through a three-stream pipeline
+ * (H2D of the next segment and D2H of the previous one beside the kernels; page-locked buffers overlap fully). */
+int safconv_render_offline_segment(void* h, const float* in, float* out, int nFrames, int nHaloFrames);
 int safconv_render_offline_device(void* h, const float* d_in, float* d_out, int nFrames);
 /**
  * One TIME SEGMENT of an offline render (multi-GPU: each GPU renders its own stretch of the signal, no

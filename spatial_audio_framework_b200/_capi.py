@@ -41,7 +41,8 @@ EXPORTED_SYMBOLS = [
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
     "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_get_kernel_totals",
     "safconv_set_option",
-    "safconv_render_offline", "safconv_render_offline_device", "safconv_render_offline_segment_device",
+    "safconv_render_offline", "safconv_render_offline_segment", "safconv_render_offline_device",
+    "safconv_render_offline_segment_device",
     "safconv_get_offline_times",
     "safconv_fftconv", "safconv_fftfilt", "fftconv", "fftfilt",
 ]
@@ -108,6 +109,7 @@ def lib():
     L.safconv_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.safconv_debug_plan_size.restype = C.c_int
     L.safconv_render_offline.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
+    L.safconv_render_offline_segment.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int]
     L.safconv_render_offline_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.safconv_render_offline_segment_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.safconv_get_offline_times.argtypes = [C.c_void_p, _f32p]
@@ -264,6 +266,12 @@ class MatrixConv(_Base):
         if self._lib.safconv_render_offline(self._h, _fp(x), _fp(y), nfr):
             self._raise_if_error()
         return y
+
+    def render_offline_host(self, in_ptr: int, out_ptr: int, n_frames: int, n_halo: int = 0):
+        """Host pointers (ideally page-locked): in [nCHin][(n_halo+n_frames)*hop] -> out [nOutLocal][n_frames*hop]."""
+        fp = C.POINTER(C.c_float)
+        if self._lib.safconv_render_offline_segment(self._h, C.cast(in_ptr, fp), C.cast(out_ptr, fp), n_frames, n_halo):
+            self._raise_if_error()
 
     def render_offline_device(self, d_in_ptr: int, d_out_ptr: int, n_frames: int):
         if self._lib.safconv_render_offline_device(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr), n_frames):

@@ -113,6 +113,8 @@ int  scdev_memset_async(void* p, int v, size_t bytes, void* stream);
 int  scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream);
 int  scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream);
 int  scdev_memcpy_h2d_sync(void* d, const void* h, size_t bytes, void* stream);
+int  scdev_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, size_t height,
+                          int toHost, void* stream);
 int  scdev_stream_create(void** s);
 int  scdev_stream_create_high_priority(void** s);
 int  scdev_stream_destroy(void* s);

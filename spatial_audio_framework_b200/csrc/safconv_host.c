@@ -48,6 +48,8 @@ typedef struct safconv_handle {
     void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
     scdev_offline off;               /* offline (batched frames) workspace, allocated on first use */
     void*      offEv[4];
+    void      *offIn, *offOut;       /* copy streams of the pipelined host-buffer render */
+    void*      offPipeEv[6];         /* per double-buffer slot: input landed, segment rendered, output copied back */
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
     /* look-ahead (matrix, P >= 2): all partitions p >= 1 of block t+1 only need spectra that are already in the
      * delay line when block t is done, so that TAIL pass is enqueued right behind block t and runs while the host
@@ -256,6 +258,8 @@ static void handle_free(safconv_handle* h)
     free(h->evBlocks);
     scdev_offline_free(&h->off);
     for (int i = 0; i < 4; i++) scdev_event_destroy(h->offEv[i]);
+    for (int i = 0; i < 6; i++) scdev_event_destroy(h->offPipeEv[i]);
+    scdev_stream_destroy(h->offIn); scdev_stream_destroy(h->offOut);
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
     scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart); scdev_free(h->b.wtab);
@@ -867,23 +871,87 @@ int safconv_render_offline_device(void* hp, const float* d_in, float* d_out, int
     return safconv_render_offline_segment_device(hp, d_in, d_out, nFrames, 0);
 }
 
+/* Host-buffer render.  Signals longer than one segment are rendered in TIME SEGMENTS (each with a P frame input
+ * halo, bit-identical to the whole render up to the fp16 operand scale of the segment) through a three-stream
+ * pipeline: the strided H2D copy of segment s+1 and the D2H copy of segment s-1 run beside the kernels of segment s,
+ * on double-buffered device staging.  PCIe is full duplex, so the render costs about max(H2D, D2H, kernels) instead
+ * of their sum -- and the device workspace is that of one segment.  (Overlap needs page-locked caller buffers;
+ * pageable ones work, staged by the driver.) */
+#define SC_OFF_SEG_TOTAL 512         /* frames per segment incl. halo: a multiple of the GEMM's 256-frame tiles */
 int safconv_render_offline(void* hp, const float* in, float* out, int nFrames)
 {
+    return safconv_render_offline_segment(hp, in, out, nFrames, 0);
+}
+
+/* in [nIn][(nHaloFrames + nFrames) * hop] (the first nHaloFrames frames are history only), out [nOutLocal][nFrames * hop] */
+int safconv_render_offline_segment(void* hp, const float* in, float* out, int nFrames, int nHaloFrames)
+{
     safconv_handle* h = as_handle(hp);
-    if (!h || !in || !out || nFrames < 1 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
+    if (!h || !in || !out || nFrames < 1 || nHaloFrames < 0 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
     int e = scdev_set_device(h->device);
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e);
-    const size_t nIn = (size_t)h->pl.nIn, nOut = (size_t)h->pl.nOutLocal, len = (size_t)nFrames * h->pl.hop;
-    float *d_in = NULL, *d_out = NULL;
-    e = scdev_malloc((void**)&d_in, sizeof(float) * nIn * len);
-    if (!e) e = scdev_malloc((void**)&d_out, sizeof(float) * nOut * len);
-    if (!e) e = scdev_memcpy_h2d_async(d_in, in, sizeof(float) * nIn * len, h->stream);
+    const size_t nIn = (size_t)h->pl.nIn, nOut = (size_t)h->pl.nOutLocal, hop = (size_t)h->pl.hop;
+    const size_t len = (size_t)nFrames * hop;                    /* output row length */
+    const size_t lenIn = (size_t)(nFrames + nHaloFrames) * hop;  /* input row length  */
     int rc = SAFCONV_OK;
-    if (!e) rc = safconv_render_offline_device(hp, d_in, d_out, nFrames);
-    if (!e && !rc) e = scdev_memcpy_d2h_async(out, d_out, sizeof(float) * nOut * len, h->stream);
-    if (!e && !rc) e = scdev_stream_sync(h->stream); else scdev_stream_sync(h->stream);
-    scdev_free(d_in); scdev_free(d_out);
-    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (host buffers)", e);
+    /* output frame t = first half of block t + second half of block t-1 (overlap-add), and block t-1 reaches back
+     * to input frame t-P: P history frames per segment */
+    const int halo = h->pl.P;
+    const int pipelined = env_int("SAFCONV_OFF_PIPELINE", 1, 0, 1) && nFrames > SC_OFF_SEG_TOTAL && halo < SC_OFF_SEG_TOTAL / 2;
+    if (!pipelined) {
+        float *d_in = NULL, *d_out = NULL;
+        e = scdev_malloc((void**)&d_in, sizeof(float) * nIn * lenIn);
+        if (!e) e = scdev_malloc((void**)&d_out, sizeof(float) * nOut * len);
+        if (!e) e = scdev_memcpy_h2d_async(d_in, in, sizeof(float) * nIn * lenIn, h->stream);
+        if (!e) rc = safconv_render_offline_segment_device(hp, d_in, d_out, nFrames, nHaloFrames);
+        if (!e && !rc) e = scdev_memcpy_d2h_async(out, d_out, sizeof(float) * nOut * len, h->stream);
+        if (!e && !rc) e = scdev_stream_sync(h->stream); else scdev_stream_sync(h->stream);
+        scdev_free(d_in); scdev_free(d_out);
+        if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (host buffers)", e);
+        return rc;
+    }
+    if (!h->offIn)  e = scdev_stream_create(&h->offIn);
+    if (!e && !h->offOut) e = scdev_stream_create(&h->offOut);
+    for (int i = 0; i < 6 && !e; i++) if (!h->offPipeEv[i]) e = scdev_event_create_sync(&h->offPipeEv[i]);
+    if (!e) e = scdev_offline_prepare(&h->pl, &h->b, &h->off, SC_OFF_SEG_TOTAL, h->stream);     /* one workspace for all segments */
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (pipeline setup)", e);
+    const int seg = SC_OFF_SEG_TOTAL - halo;                    /* new frames per segment */
+    float *d_in[2] = { NULL, NULL }, *d_out[2] = { NULL, NULL };
+    for (int b = 0; b < 2 && !e; b++) {
+        e = scdev_malloc((void**)&d_in[b], sizeof(float) * nIn * SC_OFF_SEG_TOTAL * hop);
+        if (!e) e = scdev_malloc((void**)&d_out[b], sizeof(float) * nOut * (size_t)seg * hop);
+    }
+    int s = 0;
+    for (int t0 = 0; t0 < nFrames && !e && !rc; t0 += seg, s++) {
+        const int b = s & 1;
+        const int t1 = (t0 + seg < nFrames) ? t0 + seg : nFrames;
+        const int hl = (t0 + nHaloFrames < halo) ? t0 + nHaloFrames : halo;     /* history frames that exist */
+        const size_t inW = (size_t)(t1 - t0 + hl) * hop, outW = (size_t)(t1 - t0) * hop;
+        void *evIn = h->offPipeEv[b], *evR = h->offPipeEv[2 + b], *evOut = h->offPipeEv[4 + b];
+        /* input of segment s into slot b: the render of segment s-2 must be done with it */
+        e = scdev_stream_wait_event(h->offIn, evR);
+        if (!e) e = scdev_memcpy2d_async(d_in[b], inW * sizeof(float), in + (size_t)(nHaloFrames + t0 - hl) * hop, lenIn * sizeof(float),
+                                         inW * sizeof(float), nIn, 0, h->offIn);
+        if (!e) e = scdev_event_record(evIn, h->offIn);
+        /* render: input landed, and the copy-back of segment s-2 has drained the output slot */
+        if (!e) e = scdev_stream_wait_event(h->stream, evIn);
+        if (!e) e = scdev_stream_wait_event(h->stream, evOut);
+        if (!e) rc = safconv_render_offline_segment_device(hp, d_in[b], d_out[b], t1 - t0, hl);
+        if (!e && !rc) e = scdev_event_record(evR, h->stream);
+        /* copy back */
+        if (!e && !rc) e = scdev_stream_wait_event(h->offOut, evR);
+        if (!e && !rc) e = scdev_memcpy2d_async(out + (size_t)t0 * hop, len * sizeof(float), d_out[b], outW * sizeof(float),
+                                                outW * sizeof(float), nOut, 1, h->offOut);
+        if (!e && !rc) e = scdev_event_record(evOut, h->offOut);
+    }
+    {
+        int e2 = scdev_stream_sync(h->offIn);
+        int e3 = scdev_stream_sync(h->stream);
+        int e4 = scdev_stream_sync(h->offOut);
+        if (!e) e = e2 ? e2 : (e3 ? e3 : e4);
+    }
+    for (int b = 0; b < 2; b++) { scdev_free(d_in[b]); scdev_free(d_out[b]); }
+    if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (pipelined)", e);
     return rc;
 }
 

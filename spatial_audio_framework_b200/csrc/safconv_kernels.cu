@@ -1028,6 +1028,13 @@ int scdev_memcpy_h2d_async(void* d, const void* h, size_t bytes, void* stream)
 { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream); }
 int scdev_memcpy_d2h_async(void* h, const void* d, size_t bytes, void* stream)
 { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream); }
+/* strided (pitched) copies: `height` rows of `widthBytes`; toHost = 0: host -> device, 1: device -> host */
+int scdev_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, size_t height,
+                         int toHost, void* stream)
+{
+    return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, height,
+                                  toHost ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
 /* Stream-ordered upload that has fully landed on return.  (A plain cudaMemcpy from pageable memory may
  * return while the last staged chunk is still in flight and is only ordered against the legacy default
  * stream -- not against the handle's non-blocking stream that the create-time kernels run on.) */

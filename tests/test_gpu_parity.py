@@ -333,6 +333,41 @@ def test_offline_operand_kinds_and_dynamic_range(saf, orc, kind, monkeypatch):
     mc.destroy()
 
 
+def test_offline_pipelined_host_render(saf, orc):
+    """safconv_render_offline on host buffers longer than one 512-frame segment: time segments pipelined over three
+    streams (strided H2D / kernels / strided D2H) -- against the oracle, against the one-piece device render, with
+    page-locked and pageable buffers, and with leading halo frames."""
+    import torch
+    rng = np.random.default_rng(33)
+    hop, L, nIn, nOut, T = 64, 300, 3, 4, 1300              # P = 5: three segments of 507 new frames
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * T)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H)
+    y = mc.render_offline(x)                                 # pageable numpy buffers
+    check(y, ref, "pipelined host render (pageable)")
+    xin = torch.from_numpy(x).pin_memory(); yout = torch.empty((nOut, hop * T)).pin_memory()
+    mc.render_offline_host(xin.data_ptr(), yout.data_ptr(), T)
+    check(yout.numpy(), ref, "pipelined host render (page-locked)")
+    assert np.array_equal(yout.numpy(), y)
+    # one-piece device render of the same signal
+    xd = torch.from_numpy(x).cuda(); yd = torch.empty((nOut, hop * T), device="cuda")
+    torch.cuda.synchronize()
+    mc.render_offline_device(xd.data_ptr(), yd.data_ptr(), T)
+    mc.synchronize()
+    ma, l2 = err_metrics(yd.cpu().numpy(), y)
+    assert ma <= 1e-6 and l2 <= 2e-7, (ma, l2)
+    # leading halo frames: render frames [200, T) given frames [190, T)
+    h0 = 10
+    xs = np.ascontiguousarray(x[:, (200 - h0) * hop:])
+    ys = np.empty((nOut, (T - 200) * hop), np.float32)
+    fp = C.POINTER(C.c_float)
+    rc = saf.lib().safconv_render_offline_segment(mc.handle, xs.ctypes.data_as(fp), ys.ctypes.data_as(fp), T - 200, h0)
+    assert rc == 0
+    check(ys, ref[:, 200 * hop:], "pipelined host render with halo")
+    mc.destroy()
+
+
 def test_offline_time_segments_equal_full_render(saf):
     """Multi-GPU offline sharding is by time: every segment rendered on its own (with a P-frame input halo,
     sharding.time_segment) reproduces the full render exactly -- no exchange between the GPUs is needed."""
