@@ -619,6 +619,19 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
             if (!direct) memcpy(out, h->h_out, h->outBytes);
             return;
         }
+        if (h->pl.kind == SC_KIND_MATRIX && !h->timingCap && h->smallFused &&
+            h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
+            /* single-partition (or look-ahead disabled) matrix convolver, blocks of up to 1 MB: K1 reads and K3 writes the
+             * page-locked host buffers directly -- three launches and one synchronisation, no copy-engine round trips */
+            e = scdev_input_fft(&h->pl, &h->b, src, 1, h->stream);
+            if (!e) e = scdev_mac(&h->pl, &h->b, 0, 1, h->stream);
+            if (!e) e = scdev_ifft_ola(&h->pl, &h->b, dst, h->stream);
+            if (!e) e = scdev_stream_sync(h->stream);
+            if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (zero-copy)", e); return; }
+            h->count++;
+            if (!direct) memcpy(out, h->h_out, h->outBytes);
+            return;
+        }
         e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
         if (!e) {
             if (h->pl.kind == SC_KIND_TV) {
