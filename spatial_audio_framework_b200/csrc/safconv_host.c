@@ -50,6 +50,7 @@ typedef struct safconv_handle {
     void*      offEv[4];
     void      *offIn, *offOut;       /* copy streams of the pipelined host-buffer render */
     void*      offPipeEv[6];         /* per double-buffer slot: input landed, segment rendered, output copied back */
+    float     *offStageIn[2], *offStageOut[2];   /* device staging of the pipelined render (kept between calls) */
     int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
     /* look-ahead (matrix, P >= 2): all partitions p >= 1 of block t+1 only need spectra that are already in the
      * delay line when block t is done, so that TAIL pass is enqueued right behind block t and runs while the host
@@ -260,6 +261,7 @@ static void handle_free(safconv_handle* h)
     for (int i = 0; i < 4; i++) scdev_event_destroy(h->offEv[i]);
     for (int i = 0; i < 6; i++) scdev_event_destroy(h->offPipeEv[i]);
     scdev_stream_destroy(h->offIn); scdev_stream_destroy(h->offOut);
+    for (int i = 0; i < 2; i++) { scdev_free(h->offStageIn[i]); scdev_free(h->offStageOut[i]); }
     scdev_free(h->b.tw); scdev_free(h->b.H); scdev_free(h->b.X); scdev_free(h->b.Zp); scdev_free(h->b.zt);
     scdev_free(h->b.tail); scdev_free(h->b.tail2); scdev_free(h->b.counters);
     scdev_free(h->b.ctaBase); scdev_free(h->b.grpStart); scdev_free(h->b.wtab);
@@ -930,9 +932,10 @@ int safconv_render_offline_segment(void* hp, const float* in, float* out, int nF
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (pipeline setup)", e);
     const int seg = SC_OFF_SEG_TOTAL - halo;                    /* new frames per segment */
     float *d_in[2] = { NULL, NULL }, *d_out[2] = { NULL, NULL };
-    for (int b = 0; b < 2 && !e; b++) {
-        e = scdev_malloc((void**)&d_in[b], sizeof(float) * nIn * SC_OFF_SEG_TOTAL * hop);
-        if (!e) e = scdev_malloc((void**)&d_out[b], sizeof(float) * nOut * (size_t)seg * hop);
+    for (int b = 0; b < 2 && !e; b++) {                         /* sizes depend on the handle only: allocated once */
+        if (!h->offStageIn[b])  e = scdev_malloc((void**)&h->offStageIn[b], sizeof(float) * nIn * SC_OFF_SEG_TOTAL * hop);
+        if (!e && !h->offStageOut[b]) e = scdev_malloc((void**)&h->offStageOut[b], sizeof(float) * nOut * SC_OFF_SEG_TOTAL * hop);
+        d_in[b] = h->offStageIn[b]; d_out[b] = h->offStageOut[b];
     }
     int s = 0;
     for (int t0 = 0; t0 < nFrames && !e && !rc; t0 += seg, s++) {
@@ -963,7 +966,6 @@ int safconv_render_offline_segment(void* hp, const float* in, float* out, int nF
         int e4 = scdev_stream_sync(h->offOut);
         if (!e) e = e2 ? e2 : (e3 ? e3 : e4);
     }
-    for (int b = 0; b < 2; b++) { scdev_free(d_in[b]); scdev_free(d_out[b]); }
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "render_offline (pipelined)", e);
     return rc;
 }

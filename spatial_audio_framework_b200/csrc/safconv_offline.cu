@@ -412,7 +412,12 @@ struct OffGemmArgs {
 #define OFF_EPI_WARPS 8
 #define OFF_MAX_HALF  64     /* columns per epilogue thread and frame tile: Nn/2 <= 64 */
 
-template <bool F16>
+/* NT = true (Nn == 128): the operand roles are swapped -- filters on the UMMA M axis (A, 128 rows), the 256 frames of
+ * the tile on the N axis (B) -- so one M128 x N256 x K16 instruction replaces two M128 x N128 ones.  At N = 128 an MMA
+ * reads 8 KB of shared memory per 64 tensor-pipe cycles, which is the whole shared-memory read bandwidth of the SM
+ * (TMA fills and everything else contend with it); at N = 256 it is 12 KB per 128 cycles.  The Toeplitz row shift
+ * works on the B descriptor exactly as on the A descriptor. */
+template <bool F16, bool NT>
 __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGemmArgs a)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -502,6 +507,19 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                 if (leader) {
                     const uint32_t hBase16 = smem_u32(smH + (size_t)hs * hStage) >> 4;
                     const uint32_t rowShift = (uint32_t)(a.P - 1 - p);  /* frame t-p = tile row +(P-1-p); 16 B per row */
+                    if (NT) {
+#pragma unroll
+                        for (int ks = 0; ks < OFF_KG / 2; ++ks) {
+                            const uint32_t x16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + rowShift;
+                            const uint32_t h16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
+                            const uint64_t xHi = aDesc0 + x16, xLo = aDesc0 + x16 + OFF_KG * xPlane16;
+                            const uint64_t hHi = bDesc0 + h16, hLo = bDesc0 + h16 + OFF_KG * hPlane16;
+                            const uint32_t d = tmem + (uint32_t)(tb * 256);
+                            umma_ss<F16>(d, hLo, xHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
+                            umma_ss<F16>(d, hHi, xLo, a.idesc, 1u);                         /* hi*lo */
+                            umma_ss<F16>(d, hHi, xHi, a.idesc, 1u);                         /* hi*hi */
+                        }
+                    } else
 #pragma unroll
                     for (int acc = 0; acc < 2; ++acc) {
 #pragma unroll
@@ -548,7 +566,10 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                 for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 16) {
                     if (c0 < halfN) {
                         float v[16];
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0), v);
+                        /* NT: lane = filter row n = 32 q + lane, columns = frames; this thread owns frames hh*128 + t*64 + c0 .. */
+                        const uint32_t col = NT ? (uint32_t)(tb * 256 + hh * 128 + t * 64 + c0)
+                                                : (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0);
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + col, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sum[t][c0 + i] += v[i];
                     }
@@ -560,6 +581,17 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
         }
         /* fp16 operands were scaled by exact powers of two: divide them out (exact as well) */
         const float inv = F16 ? 1.f / (pow2_scale(a.scal[0]) * pow2_scale(a.scal[1])) : 1.f;
+        if (NT) {
+            /* sum[t][c] = output row n = 32 q + lane of frame t0 + hh*128 + t*64 + c: a warp stores 32 consecutive n */
+            const int n = q * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int c = 0; c < OFF_MAX_HALF; ++c) {
+                    const int row = t0 + hh * 128 + t * 64 + c;
+                    a.Ys[((size_t)bin * a.Tpad + row) * a.Nn + n] = sum[t][c] * inv;
+                }
+        } else
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int row = t0 + t * 128 + q * 32 + lane;
@@ -1041,8 +1073,10 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
             offline_pack_filters_kernel<false><<<148 * 8, 256, 0, st>>>(a);
         }
         SC_CHECK(cudaGetLastError());
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
+        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
         SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         o->packed = 1;
@@ -1107,11 +1141,18 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     g.HGhi = (const unsigned char*)o->HGhi; g.HGlo = (const unsigned char*)o->HGlo; g.Ys = o->Ys; g.scal = o->scal;
     g.P = pl->P; g.nKG = o->nKG; g.nKC = o->nKC; g.Nn = o->Nn; g.rowsAlloc = rowsAlloc; g.Tpad = o->capTpad;
     g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush;
-    g.idesc = o->f16 ? umma_idesc_f16(128, o->Nn) : umma_idesc_tf32(128, o->Nn);
+    /* frames on the UMMA N axis (one M128 x N256 instruction per product term) when the filter rows fill M = 128 */
+    static int ntEnv = -1;
+    if (ntEnv < 0) { const char* v = getenv("SAFCONV_OFF_NT"); ntEnv = v ? atoi(v) : 1; }
+    const int nt = ntEnv && o->Nn == 128;
+    const int mm = nt ? 128 : 128, nn = nt ? 256 : o->Nn;
+    g.idesc = o->f16 ? umma_idesc_f16(mm, nn) : umma_idesc_tf32(mm, nn);
     {
         dim3 grid(Tpad / OFF_MT, pl->M);
-        if (o->f16) offline_gemm_kernel<true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
-        else        offline_gemm_kernel<false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+        if (o->f16) { if (nt) offline_gemm_kernel<true, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+                      else    offline_gemm_kernel<true, false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g); }
+        else        { if (nt) offline_gemm_kernel<false, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
+                      else    offline_gemm_kernel<false, false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g); }
         SC_CHECK(cudaGetLastError());
     }
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[2], st));
