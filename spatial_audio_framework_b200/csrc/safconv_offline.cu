@@ -379,6 +379,40 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+/* two 16-column loads in flight, one wait */
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v)
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+/* 64 consecutive columns: four 16-column loads in flight, one wait */
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v)
+{
+    uint32_t r[64];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[16 * g + 0]), "=r"(r[16 * g + 1]), "=r"(r[16 * g + 2]), "=r"(r[16 * g + 3]), "=r"(r[16 * g + 4]),
+                       "=r"(r[16 * g + 5]), "=r"(r[16 * g + 6]), "=r"(r[16 * g + 7]), "=r"(r[16 * g + 8]), "=r"(r[16 * g + 9]),
+                       "=r"(r[16 * g + 10]), "=r"(r[16 * g + 11]), "=r"(r[16 * g + 12]), "=r"(r[16 * g + 13]), "=r"(r[16 * g + 14]),
+                       "=r"(r[16 * g + 15])
+                     : "r"(taddr + 16u * g));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 {
     uint32_t r[16];
@@ -563,13 +597,26 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
 #pragma unroll
-                for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 16) {
-                    if (c0 < halfN) {
+                for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 32) {
+                    /* NT: lane = filter row n = 32 q + lane, columns = frames; this thread owns frames hh*128 + t*64 + c0 .. */
+                    const uint32_t col = NT ? (uint32_t)(tb * 256 + hh * 128 + t * 64 + c0)
+                                            : (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0);
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col;
+                    if (halfN == 64) {                       /* full tile: all 64 columns of this half with one wait */
+                        if (c0 == 0) {
+                            float v[64];
+                            tmem_ld64(ta, v);
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) sum[t][i] += v[i];
+                        }
+                    } else if (c0 + 16 < halfN) {
+                        float v[32];
+                        tmem_ld16x2(ta, ta + 16, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[t][c0 + i] += v[i];
+                    } else if (c0 < halfN) {
                         float v[16];
-                        /* NT: lane = filter row n = 32 q + lane, columns = frames; this thread owns frames hh*128 + t*64 + c0 .. */
-                        const uint32_t col = NT ? (uint32_t)(tb * 256 + hh * 128 + t * 64 + c0)
-                                                : (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0);
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+                        tmem_ld16(ta, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sum[t][c0 + i] += v[i];
                     }
