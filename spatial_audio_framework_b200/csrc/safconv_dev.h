@@ -123,6 +123,7 @@ int  scdev_event_create(void** e);
 int  scdev_event_destroy(void* e);
 int  scdev_event_create_sync(void** e);          /* no timing: cheapest to record / wait on */
 int  scdev_stream_wait_event(void* stream, void* e);
+int  scdev_event_done(void* e);                 /* 1 complete / never recorded, 0 pending, < 0 error */
 int  scdev_event_record(void* e, void* stream);
 int  scdev_event_sync(void* e);
 int  scdev_event_elapsed_ms(void* e0, void* e1, float* ms);

@@ -63,7 +63,10 @@ typedef struct safconv_handle {
     void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
     void*      streamOut;            /* high-priority side stream: K3 (+ D2H) of block t runs beside the tail pass of block t+1 */
     void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
+    void*      evTail;               /* end of the most recent tail pass */
     unsigned int count;              /* host mirror of the device block counter (counters[0]) */
+    int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
+    void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
 } safconv_handle;
 
 static __thread int  tl_err = 0;
@@ -269,9 +272,10 @@ static void handle_free(safconv_handle* h)
     scdev_free(h->headPass.ctaBase); scdev_free(h->headPass.grpStart); scdev_free(h->headPass.Zp);
     if (h->streamIn) scdev_stream_sync(h->streamIn);
     if (h->streamOut) scdev_stream_sync(h->streamOut);
-    scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence); scdev_event_destroy(h->evMac);
+    scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence); scdev_event_destroy(h->evMac); scdev_event_destroy(h->evTail);
     scdev_stream_destroy(h->streamIn); scdev_stream_destroy(h->streamOut);
     scdev_free(h->tailPass.ZpB);
+    for (int i = 0; i < 6; i++) scdev_event_destroy(h->trEv[i]);
     scdev_free(h->d_in); scdev_free(h->d_out);
     scdev_host_free(h->h_in); scdev_host_free(h->h_out);
     scdev_stream_destroy(h->streamOwn);
@@ -414,10 +418,13 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         DEV_TRY(h, scdev_event_create_sync(&h->evIn), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evFence), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evMac), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evTail), "cudaEventCreate");
         DEV_TRY(h, scdev_stream_create(&h->streamIn), "cudaStreamCreate");
         DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
+        h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
+        for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
     }
     if (kind == SC_KIND_MULTI && env_int("SAFCONV_MULTI_WFFT", 1, 0, 1))
         DEV_TRY(h, scdev_wfft_tables(pl, &h->b, h->stream), "warp-FFT tables");
@@ -606,17 +613,47 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
             const unsigned int c = h->count;
             const int tb = (int)(c & 1u);
             const int hadTail = h->tailReady;
+            const int tr = h->trace && hadTail;
+            /* Is the caller coming back faster than the GPU streams the filters (the previous tail pass is still
+             * running)?  Then throughput counts: K3 of this block shares the GPU with the next tail pass.  Otherwise
+             * (real-time pacing) latency counts: K3 runs alone and the next tail pass starts behind it. */
+            const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
+            if (tr) scdev_event_record(h->trEv[0], h->stream);
             if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }
             else         { if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream); }
             h->tailReady = 0;
+            if (tr) scdev_event_record(h->trEv[1], h->stream);
             if (!e) e = scdev_event_record(h->evMac, h->stream);
-            if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
+            if (!e && backToBack) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
             if (!e) e = scdev_stream_wait_event(h->streamOut, h->evMac);
+            if (tr) scdev_event_record(h->trEv[3], h->streamOut);
             if (hadTail) { if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut); }
             else         { if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->streamOut); }
             if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
+            if (tr) scdev_event_record(h->trEv[4], h->streamOut);
             if (!e) e = scdev_event_record(h->evDone, h->streamOut);
+            if (!backToBack) {
+                if (!e) e = scdev_stream_wait_event(h->stream, h->evDone);
+                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
+            }
+            if (!e) e = scdev_event_record(h->evTail, h->stream);
             if (!e) { h->tailReady = 1; h->count = c + 1; e = scdev_event_sync(h->evDone); }
+            if (tr && !e) {
+                /* trEv[2] = end of the tail pass enqueued by the PREVIOUS call (recorded there as trEv[5], swapped below) */
+                float gap = 0.f, head = 0.f, k3wait = 0.f, k3 = 0.f;
+                if (h->trEv[2] && h->count > 3) {
+                    scdev_event_elapsed_ms(h->trEv[2], h->trEv[0], &gap);
+                    scdev_event_elapsed_ms(h->trEv[0], h->trEv[1], &head);
+                    scdev_event_elapsed_ms(h->trEv[1], h->trEv[3], &k3wait);
+                    scdev_event_elapsed_ms(h->trEv[3], h->trEv[4], &k3);
+                    fprintf(stderr, "[safconv trace] block %u: prev tail end -> head start %.1f us, head %.1f us, head end -> K3 start %.1f us, K3 %.1f us\n",
+                            c, 1e3f * gap, 1e3f * head, 1e3f * k3wait, 1e3f * k3);
+                }
+            }
+            if (h->trace && !e) {                           /* end of the tail pass just enqueued: read by the next call */
+                void* t = h->trEv[2]; h->trEv[2] = h->trEv[5]; h->trEv[5] = t;
+                scdev_event_record(h->trEv[2], h->stream);
+            }
             if (e) { h->tailReady = 0; h_fail(h, SAFCONV_ERR_CUDA, "apply (look-ahead)", e); return; }
             if (!direct) memcpy(out, h->h_out, h->outBytes);
             return;

@@ -1057,6 +1057,14 @@ int scdev_event_create(void** e) { cudaEvent_t ev; cudaError_t r = cudaEventCrea
 int scdev_event_create_sync(void** e)
 { cudaEvent_t ev; cudaError_t r = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); *e = (void*)ev; return (int)r; }
 int scdev_stream_wait_event(void* stream, void* e) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)e, 0); }
+/* 1: the event's work has completed (or it was never recorded), 0: still pending, < 0: error */
+int scdev_event_done(void* e)
+{
+    const cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) { (void)cudaGetLastError(); return 0; }
+    return -1;
+}
 int scdev_event_destroy(void* e) { return e ? (int)cudaEventDestroy((cudaEvent_t)e) : 0; }
 int scdev_event_record(void* e, void* stream) { return (int)cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream); }
 int scdev_event_sync(void* e) { return (int)cudaEventSynchronize((cudaEvent_t)e); }
@@ -1121,8 +1129,15 @@ int scdev_prepare(const scdev_plan* pl)
     }
     if (pl->kind == SC_KIND_TV && fft_smem(pl, 5) > 48 * 1024)
         SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 5)));
-    if (pl->kind == SC_KIND_MATRIX)
+    if (pl->kind == SC_KIND_MATRIX) {
         SC_CHECK(cudaFuncSetAttribute(mac_fn(pl->R), cudaFuncAttributeMaxDynamicSharedMemorySize, pl->macSmemBytes));
+        /* The look-ahead apply runs K1 (next block) and K3 (this block) BESIDE a resident tail pass of the MAC.  CTAs
+         * of kernels whose shared-memory carve-outs differ cannot share an SM (measured: with the driver's per-kernel
+         * choice K1 / K3 waited for the whole 0.43 ms tail pass), so all three ask for the same, largest one. */
+        SC_CHECK(cudaFuncSetAttribute(mac_fn(pl->R), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SC_CHECK(cudaFuncSetAttribute(input_fft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     return 0;
 }
 
