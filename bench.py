@@ -512,6 +512,15 @@ def run_own_arm(args, w):
                                 "achieved_GBps": float(info.algBytesPerBlock) * B * args.steps / (ms_total * 1e-3) / 1e9},
                 "kernel_ms_per_block": {"input_fft": kms[0], "mac": kms[1], "ifft_ola": kms[2]}}
     roofline["whole_block"]["frac"] = roofline["whole_block"]["achieved_GBps"] / peak
+    # north_star quotes "roughly 8 TB/s": the same achieved rate against the nominal HBM3e figure
+    if w["kind"] == "multi" or info.bytesFilters <= (64 << 20):
+        roofline["note"] = ("the filter set fits in L2 (126 MB) and the batched blocks of a step re-use it from L2 / registers: "
+                            "DRAM traffic is far below the algorithmic bytes, so frac can exceed 1")
+    else:
+        roofline["note"] = ("peak is the measured COPY bandwidth (read + write); this kernel is a read-only stream, which runs "
+                            "above a copy on HBM3e -- see frac_of_nominal and traffic (ncu DRAM bytes = 0.986 x algorithmic)")
+    roofline["peak_nominal"] = 8000.0
+    roofline["frac_of_nominal"] = achieved / 8000.0
 
     if rank != 0:
         if dist:

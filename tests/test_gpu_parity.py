@@ -247,7 +247,8 @@ def test_batched_device_blocks_equal_block_by_block(saf, orc, hop, L, nIn, nOut,
 
 
 @pytest.mark.parametrize("hop,L,nIn,nOut,nblk", [(256, 700, 5, 9, 30), (1024, 12000, 16, 8, 30), (64, 128, 2, 3, 20),
-                                                  (128, 2000, 3, 70, 25), (512, 1024, 33, 17, 12)])
+                                                  (128, 2000, 3, 70, 25), (512, 1024, 33, 17, 12),
+                                                  (8192, 20000, 40, 2, 5)])      # 1.3 MB input blocks: copy-engine path
 def test_lookahead_tail_head_split(saf, orc, hop, L, nIn, nOut, nblk):
     """Host-pointer apply with the look-ahead split (default for P >= 2): partitions p >= 1 of block t+1 are
     accumulated behind block t, the call itself only adds the newest partition.  Same result as the oracle and as
