@@ -146,6 +146,17 @@ int safconv_apply_device(void* h, const float* d_in, float* d_out);
 int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nBlocks);
 
 /**
+ * The device real-FFT pair of the convolvers on its own, with the reference's saf_rfft conventions
+ * (/root/reference/framework/modules/saf_utilities/saf_utility_fft.h saf_rfft_forward / saf_rfft_backward,
+ * .c:531-753; KissFFT resources/kissFFT/kiss_fftr.c:69-161): x [nBatch][N] real <-> X [nBatch][N/2+1] interleaved
+ * complex, forward unscaled, backward scaled by 1/N and ignoring the imaginary parts of DC and Nyquist.
+ * Host pointers; power-of-two 64 <= N <= 16384 (the sizes the convolver engine uses).  Stateless utility /
+ * parity-test entry points: every call uploads, transforms and downloads.
+ */
+int  safconv_rfft_forward(int N, int nBatch, const float* x, float* X);
+int  safconv_rfft_backward(int N, int nBatch, const float* X, float* x);
+
+/**
  * Whole-signal per-channel linear convolution, the reference's fftconv / fftfilt
  * (/root/reference/framework/modules/saf_utilities/saf_utility_fft.h:86-91, 107-112; .c:157-228):
  * x FLAT nCH x x_len, h FLAT nCH x h_len (host pointers), y FLAT nCH x (x_len+h_len-1) for fftconv,

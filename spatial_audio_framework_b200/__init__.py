@@ -18,9 +18,11 @@ from ._capi import (  # noqa: F401
     fftconv,
     fftfilt,
     lib,
+    rfft_backward,
+    rfft_forward,
     version,
 )
 from . import synth  # noqa: F401
 from . import sharding  # noqa: F401
 
-__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "fftconv", "fftfilt", "lib", "version", "synth", "sharding"]
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "fftconv", "fftfilt", "rfft_forward", "rfft_backward", "lib", "version", "synth", "sharding"]

@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = [
     "safconv_render_offline_segment_device",
     "safconv_get_offline_times",
     "safconv_fftconv", "safconv_fftfilt", "fftconv", "fftfilt",
+    "safconv_rfft_forward", "safconv_rfft_backward",
 ]
 
 
@@ -378,3 +379,31 @@ def fftconv(x: np.ndarray, h: np.ndarray, filt: bool = False) -> np.ndarray:
 
 def fftfilt(x: np.ndarray, h: np.ndarray) -> np.ndarray:
     return fftconv(x, h, filt=True)
+
+
+def rfft_forward(x: np.ndarray) -> np.ndarray:
+    """x[batch, N] real -> X[batch, N/2+1] complex64 (saf_rfft_forward conventions, power-of-two N)."""
+    L = lib()
+    x = np.ascontiguousarray(np.atleast_2d(x), np.float32)
+    nb, N = x.shape
+    X = np.empty((nb, N // 2 + 1, 2), np.float32)
+    L.safconv_rfft_forward.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    rc = L.safconv_rfft_forward(N, nb, _fp(x), _fp(X))
+    if rc:
+        raise RuntimeError("rfft_forward failed (%d)" % rc)
+    return X[..., 0] + 1j * X[..., 1]
+
+
+def rfft_backward(X: np.ndarray) -> np.ndarray:
+    """X[batch, N/2+1] complex -> x[batch, N] real, scaled by 1/N (saf_rfft_backward conventions)."""
+    L = lib()
+    X = np.atleast_2d(np.asarray(X, np.complex64))
+    nb, nbins = X.shape
+    N = 2 * (nbins - 1)
+    Xi = np.ascontiguousarray(np.stack([X.real, X.imag], -1), np.float32)
+    x = np.empty((nb, N), np.float32)
+    L.safconv_rfft_backward.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    rc = L.safconv_rfft_backward(N, nb, _fp(Xi), _fp(x))
+    if rc:
+        raise RuntimeError("rfft_backward failed (%d)" % rc)
+    return x

@@ -163,6 +163,8 @@ int  scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offl
 int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
                        const float* d_in, float* d_out, int T, int skip, void** events, void* stream);
 int  scdev_offline_free(scdev_offline* o);
+/* batch of stand-alone real FFTs (saf_rfft conventions) on device buffers; dir 0 forward, 1 backward */
+int  scdev_rfft(int N, int logM, int nBatch, int dir, const float* d_in, float* d_out, const void* d_tw, void* stream);
 /* build b->wtab (no-op outside 64 <= M <= 1024) */
 int  scdev_wfft_tables(const scdev_plan* pl, scdev_bufs* b, void* stream);
 /* 1 if p is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister), else 0 */

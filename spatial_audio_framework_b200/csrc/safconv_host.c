@@ -841,6 +841,51 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     return SAFCONV_OK;
 }
 
+/* ---- stand-alone real FFT (reference saf_rfft_*, saf_utility_fft.c:531-753), power-of-two N ---- */
+static int rfft_impl(int N, int nBatch, const float* in, float* out, int dir)
+{
+    tl_err = 0; tl_msg[0] = 0;
+    if (N < 64 || N > 2 * SC_MAX_M || (N & (N - 1)) || nBatch < 1 || !in || !out) {
+        set_tl_error(SAFCONV_ERR_ARG, "rfft: need a power-of-two 64 <= N <= 16384, nBatch >= 1%s", "");
+        return SAFCONV_ERR_ARG;
+    }
+    int ndev = 0;
+    if (scdev_device_count(&ndev) != 0 || ndev < 1) {
+        set_tl_error(SAFCONV_ERR_NO_DEVICE, "no usable CUDA device%s (libsafconv_b200 has no CPU fallback)", "");
+        return SAFCONV_ERR_NO_DEVICE;
+    }
+    if (tl_device >= 0) scdev_set_device(tl_device);
+    const int M = N / 2, logM = ilog2(M);
+    const size_t inElems  = (size_t)nBatch * (dir == 0 ? (size_t)N : (size_t)2 * (M + 1));
+    const size_t outElems = (size_t)nBatch * (dir == 0 ? (size_t)2 * (M + 1) : (size_t)N);
+    float* tw = (float*)malloc(sizeof(float) * 2 * (size_t)M);
+    void *stream = NULL, *d_tw = NULL; float *d_in = NULL, *d_out = NULL;
+    int e = tw ? 0 : -1;
+    if (!e) {
+        for (int j = 0; j < M; j++) {                       /* evaluated in double like kiss_fft.c:358-364 */
+            const double ph = -2.0 * 3.141592653589793238462643383279502884 * (double)j / (double)N;
+            tw[2 * j] = (float)cos(ph); tw[2 * j + 1] = (float)sin(ph);
+        }
+        e = scdev_stream_create(&stream);
+    }
+    if (!e) e = scdev_malloc(&d_tw, sizeof(float) * 2 * (size_t)M);
+    if (!e) e = scdev_malloc((void**)&d_in, sizeof(float) * inElems);
+    if (!e) e = scdev_malloc((void**)&d_out, sizeof(float) * outElems);
+    if (!e) e = scdev_memcpy_h2d_async(d_tw, tw, sizeof(float) * 2 * (size_t)M, stream);
+    if (!e) e = scdev_memcpy_h2d_async(d_in, in, sizeof(float) * inElems, stream);
+    if (!e) e = scdev_rfft(N, logM, nBatch, dir, d_in, d_out, d_tw, stream);
+    if (!e) e = scdev_memcpy_d2h_async(out, d_out, sizeof(float) * outElems, stream);
+    if (!e) e = scdev_stream_sync(stream); else if (stream) scdev_stream_sync(stream);
+    scdev_free(d_tw); scdev_free(d_in); scdev_free(d_out);
+    scdev_stream_destroy(stream);
+    free(tw);
+    if (e) return h_fail(NULL, e < 0 ? SAFCONV_ERR_NOMEM : SAFCONV_ERR_CUDA, "rfft", e < 0 ? 0 : e);
+    return SAFCONV_OK;
+}
+
+int safconv_rfft_forward(int N, int nBatch, const float* x, float* X)  { return rfft_impl(N, nBatch, x, X, 0); }
+int safconv_rfft_backward(int N, int nBatch, const float* X, float* x) { return rfft_impl(N, nBatch, X, x, 1); }
+
 /* ---- fftconv / fftfilt (reference saf_utility_fft.c:157-228) on the multiConv engine ---- */
 static int fftconv_impl(const float* x, const float* h, int x_len, int h_len, int nCH, float* y, int keep)
 {

@@ -1003,6 +1003,65 @@ __global__ void tv_fused_kernel(TvArgs a)
     advance_block_counter(a.counters, gridDim.x);
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/*  Stand-alone real FFT pair with the reference's saf_rfft conventions (saf_utility_fft.c:531-753: */
+/*  N/2+1 interleaved complex bins, forward unscaled, backward x 1/N, Im of DC and Nyquist ignored   */
+/*  by the backward transform -- kiss_fftr.c:137-138).  Same device code as the convolver kernels     */
+/*  (load_real_block, cfft_dif, split passes); one CTA per transform, grid = batch.                  */
+/* ------------------------------------------------------------------------------------------ */
+struct RfftArgs {
+    const float* in;       /* forward: [batch][N] real;            backward: [batch][N/2+1] complex */
+    float* out;            /* forward: [batch][N/2+1] complex;     backward: [batch][N] real        */
+    const float2* tw;
+    int N, M, logM;
+};
+
+__global__ void rfft_forward_kernel(RfftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + SC_ALEN(a.M);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    load_real_block(sm, a.in + (size_t)blockIdx.x * a.N, a.N, a.M, a.logM);
+    __syncthreads();
+    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
+    float2* X = reinterpret_cast<float2*>(a.out) + (size_t)blockIdx.x * (a.M + 1);
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        if (k == 0) {
+            const float2 z = sm[0];
+            X[0]   = make_float2(z.x + z.y, 0.f);
+            X[a.M] = make_float2(z.x - z.y, 0.f);
+        } else {
+            float2 Xk, Xmk;
+            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
+            X[k] = Xk;  X[a.M - k] = Xmk;
+        }
+    }
+}
+
+__global__ void rfft_backward_kernel(RfftArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + SC_ALEN(a.M);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    const float2* X = reinterpret_cast<const float2*>(a.in) + (size_t)blockIdx.x * (a.M + 1);
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        float2 v = __ldg(X + k);
+        if (k == 0) v = make_float2(v.x, __ldg(X + a.M).x);     /* packed (DC, Nyquist): real parts only */
+        sm[padi(k, a.logM)] = v;
+    }
+    __syncthreads();
+    inv_split_all(sm, a.M, a.logM, spl);
+    cfft_dif<true>(sm, a.M, a.logM, stw, wide);
+    float* x = a.out + (size_t)blockIdx.x * a.N;
+    const float scale = 1.0f / (float)a.N;
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) x[i] = time_sample(sm, i, a.logM) * scale;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /*  C-ABI: plumbing                                                                             */
 /* ------------------------------------------------------------------------------------------ */
@@ -1367,6 +1426,24 @@ int scdev_wfft_tables(const scdev_plan* pl, scdev_bufs* b, void* stream)
     SC_CHECK(cudaMalloc(&b->wtab, (size_t)2 * pl->M * sizeof(float2)));
     wfft_tables_kernel<<<(pl->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)b->tw, (float2*)b->wtab,
                                                                             (float2*)b->wtab + pl->M, pl->M, pl->logM - 5);
+    return (int)cudaGetLastError();
+}
+
+/* batch of real FFTs on device buffers; d_tw = W_N^j, j < N/2 (float2); dir 0 forward, 1 backward */
+int scdev_rfft(int N, int logM, int nBatch, int dir, const float* d_in, float* d_out, const void* d_tw, void* stream)
+{
+    RfftArgs a;
+    a.in = d_in; a.out = d_out; a.tw = (const float2*)d_tw; a.N = N; a.M = N / 2; a.logM = logM;
+    const int M = a.M;
+    int threads = M / 4; if (threads < 32) threads = 32; if (threads > 256) threads = 256;
+    const size_t smem = ((size_t)2 * SC_ALEN(M) + sc_split_len(M)) * sizeof(float2);
+    if (dir == 0) {
+        if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(rfft_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rfft_forward_kernel<<<nBatch, threads, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(rfft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rfft_backward_kernel<<<nBatch, threads, smem, (cudaStream_t)stream>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 

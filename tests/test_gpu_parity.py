@@ -572,3 +572,37 @@ def test_fftconv_fftfilt_vs_oracle(saf, orc, nCH, xl, hl):
     L.fftconv.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, fp]; L.fftconv.restype = None
     L.fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), xl, hl, nCH, y.ctypes.data_as(fp))
     check(y, orc.oracle_fftconv(x, h), "fftconv (reference-named symbol)")
+
+
+def test_rfft_pair_vs_golden_and_oracle(saf, orc):
+    """The device real-FFT pair on its own (safconv_rfft_forward / _backward) against the
+    reference's saf_rfft golden vectors (tests/golden/rfft_*.npz, power-of-two sizes) and the oracle's KissFFT
+    restatement on random batches; round trip like the reference's own test__saf_rfft (<= 1e-5)."""
+    import spatial_audio_framework_b200 as pkg
+    from conftest import golden_files
+    seen = 0
+    for f in golden_files("rfft"):
+        g = np.load(f)
+        N = int(g["N"])
+        if N & (N - 1) or N < 64:
+            continue
+        seen += 1
+        Xref = g["X"].astype(np.float32).reshape(-1, 2)
+        X = pkg.rfft_forward(g["x"][None, :])[0]
+        err = np.abs(X - (Xref[:, 0] + 1j * Xref[:, 1])).max() / np.abs(Xref).max()
+        assert err <= 1e-6, (f, err)
+        xb = pkg.rfft_backward((Xref[:, 0] + 1j * Xref[:, 1])[None, :])[0]
+        assert np.abs(xb - g["xb"]).max() <= 1e-6 * max(np.abs(g["xb"]).max(), 1.0), f
+    assert seen >= 3
+    rng = np.random.default_rng(12)
+    for N in (64, 128, 512, 1024, 2048, 4096, 16384):
+        x = rng.uniform(-1, 1, (5, N)).astype(np.float32)
+        X = pkg.rfft_forward(x)
+        for b in (0, 4):
+            Xo, _ = orc.oracle_rfft(N, x[b])
+            Xo = Xo.reshape(-1, 2)
+            Xo = Xo[:, 0] + 1j * Xo[:, 1]
+            l2 = np.linalg.norm(X[b] - Xo) / np.linalg.norm(Xo)
+            assert l2 <= 1e-6, (N, b, l2)
+        xr = pkg.rfft_backward(X)
+        assert np.abs(xr - x).max() <= 1e-5, N              # the reference's own criterion (test__utilities_module.c:381-404)
