@@ -239,15 +239,25 @@ int safconv_get_kernel_totals(void* h, float msTotal[3], int* nLaunchGroups, int
 int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
 
 /** Tuning knobs (mostly for benchmarks / tests). Returns 0 on success.
- *    "mac_hints"    0/1 L2 eviction-priority hints on the H / delay-line streams
+ *    "mac_hints"    L2 eviction-priority hints of the MAC: 0 none, 1 filters evict_first (streamed once per block),
+ *                   2 filters evict_last (a filter set that fits in L2); default: 2 up to 64 MB of spectra, else 1
+ *    "lookahead"    0/1 (default 1 for matrix convolvers with more than one partition): saf_matrixConv_apply returns
+ *                   when the block's output is on the host while the GPU already accumulates the partitions of the
+ *                   NEXT block that do not depend on it; 0 = plain forward FFT -> MAC -> inverse FFT per call
  *    "use_graph"    0/1 replay the per-block launch sequence of saf_*_apply from a CUDA graph
  *    "batching"     0/1 (default 1) safconv_apply_device_blocks shares one forward-FFT and one inverse-FFT
  *                   launch across the blocks handed over together (outputs are bit-identical either way)
  *    "small_fused"  0/1 (default 1) saf_matrixConv_apply of a small problem (few inputs x outputs, filter spectra
  *                   that stay in L2) runs as ONE fused kernel that reads / writes the page-locked host buffers
- *                   directly: one launch + one synchronisation per block (real-time latency path)
+ *                   directly: one launch + one synchronisation per block (real-time latency path); also gates the other
+ *                   zero-copy host paths (multiConv single launch, single-partition matrix convolvers)
  *    "detect_pinned" 0/1 (default 1) saf_*_apply copies straight from/to caller buffers that are already
  *                   page-locked instead of going through the handle's own pinned staging buffers
+ * Environment variables read at create / first use (benchmark and debugging knobs, all optional):
+ *    SAFCONV_LOOKAHEAD, SAFCONV_SMALL_FUSED, SAFCONV_MAC_HINTS, SAFCONV_MAC_STAGES, SAFCONV_MAC_STAGE_KB, SAFCONV_MAX_BATCH,
+ *    SAFCONV_MULTI_WFFT, SAFCONV_TRACE (device timeline of the look-ahead apply on stderr);
+ *    offline path: SAFCONV_OFF_KIND (f16 | tf32), SAFCONV_OFF_NT, SAFCONV_OFF_WFFT, SAFCONV_OFF_FLUSH, SAFCONV_OFF_PIPELINE,
+ *    SAFCONV_OFF_FPC, SAFCONV_OFF_OPC, SAFCONV_OFF_THREADS.
  */
 int safconv_set_option(void* h, const char* name, int value);
 
