@@ -68,6 +68,7 @@ typedef struct scdev_macpass {
     int*  grpStart;          /* device int[nGroups+1]   */
     void* Zp;                /* device float2[nSlots][OTsz][32] */
     void* ZpB;               /* second buffer (tail pass: block t+1's tail is written while K3 of block t still reads) or NULL */
+    int   stages;            /* > 0: TMA pipeline depth of this launch (shallower than the plan's -> less shared memory) */
 } scdev_macpass;
 
 typedef struct scdev_bufs {

@@ -618,21 +618,42 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
              * running)?  Then throughput counts: K3 of this block shares the GPU with the next tail pass.  Otherwise
              * (real-time pacing) latency counts: K3 runs alone and the next tail pass starts behind it. */
             const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
-            if (tr) scdev_event_record(h->trEv[0], h->stream);
-            if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }
-            else         { if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream); }
-            h->tailReady = 0;
-            if (tr) scdev_event_record(h->trEv[1], h->stream);
-            if (!e) e = scdev_event_record(h->evMac, h->stream);
-            if (!e && backToBack) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
-            if (!e) e = scdev_stream_wait_event(h->streamOut, h->evMac);
-            if (tr) scdev_event_record(h->trEv[3], h->streamOut);
-            if (hadTail) { if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut); }
-            else         { if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->streamOut); }
-            if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
-            if (tr) scdev_event_record(h->trEv[4], h->streamOut);
-            if (!e) e = scdev_event_record(h->evDone, h->streamOut);
-            if (!backToBack) {
+            if (backToBack) {
+                /* throughput regime: `stream` carries nothing but tail passes, back to back.  The head pass of this
+                 * block runs on the side stream with a two-stage pipeline (69 KB of shared memory: its CTAs fit on
+                 * the SMs beside the resident tail CTAs) while the block's own tail pass is still streaming; K3
+                 * follows as soon as that tail pass is done, beside the tail pass of the next block. */
+                scdev_macpass hp2 = h->headPass;
+                hp2.stages = 2;
+                if (!e && !zc) e = scdev_event_record(h->evMac, h->stream);         /* K1 ran on `stream`: its spectrum is ready here */
+                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
+                void* evTailC = h->evTail;                                          /* end of the tail pass of block c */
+                if (!e) e = scdev_stream_wait_event(h->streamOut, zc ? h->evIn : h->evMac);
+                if (tr) scdev_event_record(h->trEv[0], h->streamOut);
+                if (!e) e = scdev_mac_pass(pl, &h->b, &hp2, 0, 1, 0, -1, h->streamOut);   /* beside the tail pass of block c */
+                if (tr) scdev_event_record(h->trEv[1], h->streamOut);
+                if (!e) e = scdev_stream_wait_event(h->streamOut, evTailC);         /* K3 needs both */
+                if (tr) scdev_event_record(h->trEv[3], h->streamOut);
+                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut);
+                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
+                if (tr) scdev_event_record(h->trEv[4], h->streamOut);
+                if (!e) e = scdev_event_record(h->evDone, h->streamOut);
+                h->tailReady = 0;
+            } else {
+                if (tr) scdev_event_record(h->trEv[0], h->stream);
+                if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }
+                else         { if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream); }
+                h->tailReady = 0;
+                if (tr) scdev_event_record(h->trEv[1], h->stream);
+                if (!e) e = scdev_event_record(h->evMac, h->stream);
+                if (!e) e = scdev_stream_wait_event(h->streamOut, h->evMac);
+                if (tr) scdev_event_record(h->trEv[3], h->streamOut);
+                if (hadTail) { if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut); }
+                else         { if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->streamOut); }
+                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
+                if (tr) scdev_event_record(h->trEv[4], h->streamOut);
+                if (!e) e = scdev_event_record(h->evDone, h->streamOut);
+                /* latency regime: K3 runs alone, the next tail pass starts behind it */
                 if (!e) e = scdev_stream_wait_event(h->stream, h->evDone);
                 if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
             }

@@ -1234,7 +1234,7 @@ int scdev_mac(const scdev_plan* pl, const scdev_bufs* b, int blk, int nBlocks, v
     scdev_macpass full;
     full.pLo = 0; full.nP = pl->P; full.totalStages = pl->totalStages; full.grid = pl->macGrid; full.nSlots = pl->nSlots;
     full.ctaBase = b->ctaBase; full.grpStart = b->grpStart; full.Zp = b->Zp;
-    full.ZpB = NULL;
+    full.ZpB = NULL; full.stages = 0;
     return scdev_mac_pass(pl, b, &full, blk, nBlocks, 0, -1, stream);
 }
 
@@ -1254,7 +1254,12 @@ int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpas
     a.NS = pl->macStages; a.RS = pl->RS; a.blk = blk;
     a.stageHBytes = pl->SNI * pl->OTsz * SC_BK * 8;
     a.stageXBytes = pl->SNI * SC_BK * 8;
-    mac_fn(pl->R)<<<ps->grid, SC_MAC_THREADS, pl->macSmemBytes, (cudaStream_t)stream>>>(a);
+    int smem = pl->macSmemBytes;
+    if (ps->stages > 0 && ps->stages < pl->macStages) {        /* shallower pipeline: fits on an SM beside a full-depth pass */
+        a.NS = ps->stages;
+        smem = a.NS * (a.stageHBytes + a.stageXBytes) + SC_MAC_CWARPS * pl->R * 32 * 8 + 2 * a.NS * 8;
+    }
+    mac_fn(pl->R)<<<ps->grid, SC_MAC_THREADS, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
