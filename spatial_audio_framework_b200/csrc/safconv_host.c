@@ -692,6 +692,17 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
             if (!direct) memcpy(out, h->h_out, h->outBytes);
             return;
         }
+        if (h->pl.kind == SC_KIND_TV && h->smallFused && h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
+            /* TVConv latency path: the fused kernel reads / writes the page-locked host buffers directly */
+            e = scdev_tv_fused(&h->pl, &h->b, src, dst, irIdx, h->tvLast, h->tvLast2, h->stream);
+            h->tvLast2 = h->tvLast;                          /* reference .c:618-619 */
+            h->tvLast  = irIdx;
+            if (!e) e = scdev_stream_sync(h->stream);
+            if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (TVConv, zero-copy)", e); return; }
+            h->count++;
+            if (!direct) memcpy(out, h->h_out, h->outBytes);
+            return;
+        }
         e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
         if (!e) {
             if (h->pl.kind == SC_KIND_TV) {

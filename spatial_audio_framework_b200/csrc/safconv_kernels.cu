@@ -971,6 +971,7 @@ __global__ void tv_fused_kernel(TvArgs a)
         const bool packed = (k == 0);
         float2 z0 = make_float2(0.f, 0.f), z1 = z0, z2 = z0;
         int slot = head;
+#pragma unroll 8
         for (int p = 0; p < a.P; ++p) {
             const float2 x = (p == 0) ? Xs[k] : a.X[(size_t)slot * a.M + k];
             cmac_packed(z0, __ldg(H0 + (size_t)p * a.M + k), x, packed);

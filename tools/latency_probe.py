@@ -48,3 +48,14 @@ for wn in sys.argv[1:] or ["C1", "C2"]:
 # floor: empty-stream synchronise and a trivial torch kernel + sync
 x = torch.zeros(32, device="cuda")
 print("torch add_ + synchronize p50/p99 us:", p50(lambda: (x.add_(1), torch.cuda.synchronize())))
+
+# TVConv (reference saf_utility_matrixConv.h:157-190): 1 input, nOut outputs, IR set switched every few blocks
+hop, L, nIRs, nOut = 512, 24000, 16, 4
+Htv = (np.random.default_rng(1).uniform(-1, 1, (nIRs, nOut, L)) * np.exp(-6.9 * np.arange(L) / L)).astype(np.float32)
+tv = saf.TVConv(hop, Htv, 0)
+xtv = np.random.rand(hop).astype(np.float32)
+state = {"i": 0}
+def tv_call():
+    state["i"] += 1
+    tv.apply(xtv, (state["i"] // 7) % nIRs)
+print("TVConv 1 x %d, hop %d, %d taps, %d IR sets: host-API p50/p99 us:" % (nOut, hop, L, nIRs), p50(tv_call))
