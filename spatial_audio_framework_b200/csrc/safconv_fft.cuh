@@ -347,7 +347,16 @@ __device__ __forceinline__ const float2* load_split_twiddles(float2* stw, const 
 __device__ __forceinline__ void load_real_block(float2* s, const float* __restrict__ x, int hop, int M, int logM)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    if ((hop & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
+    if ((hop & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+        /* 16-byte loads: two complex points (four samples) per thread and load */
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int h4 = hop >> 2;
+        for (int n2 = tid; n2 < (M >> 1); n2 += T) {
+            const float4 v = (n2 < h4) ? __ldg(x4 + n2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s[padi(2 * n2, logM)]     = make_float2(v.x, v.y);
+            s[padi(2 * n2 + 1, logM)] = make_float2(v.z, v.w);
+        }
+    } else if ((hop & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
         const float2* x2 = reinterpret_cast<const float2*>(x);
         const int h2 = hop >> 1;
         for (int n = tid; n < M; n += T) s[padi(n, logM)] = (n < h2) ? __ldg(x2 + n) : make_float2(0.f, 0.f);

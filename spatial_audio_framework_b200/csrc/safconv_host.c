@@ -65,6 +65,7 @@ typedef struct safconv_handle {
     void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
     void*      evTail;               /* end of the most recent tail pass */
     unsigned int count;              /* host mirror of the device block counter (counters[0]) */
+    int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
     int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
     void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
 } safconv_handle;
@@ -423,6 +424,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
+        h->headInK3 = env_int("SAFCONV_HEAD_IN_K3", 1, 0, 1);
         h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
         for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
     }
@@ -639,6 +641,16 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
                 if (tr) scdev_event_record(h->trEv[4], h->streamOut);
                 if (!e) e = scdev_event_record(h->evDone, h->streamOut);
                 h->tailReady = 0;
+            } else if (hadTail && h->headInK3) {
+                /* latency regime, short version: no head pass at all -- K3 adds the newest partition itself while it
+                 * gathers the tail's partial tiles (each CTA streams its output's 1/P of the filters) */
+                if (tr) { scdev_event_record(h->trEv[0], h->stream); scdev_event_record(h->trEv[1], h->stream); scdev_event_record(h->trEv[3], h->stream); }
+                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, NULL, kout, h->stream);
+                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
+                if (tr) scdev_event_record(h->trEv[4], h->stream);
+                if (!e) e = scdev_event_record(h->evDone, h->stream);
+                h->tailReady = 0;
+                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
             } else {
                 if (tr) scdev_event_record(h->trEv[0], h->stream);
                 if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }

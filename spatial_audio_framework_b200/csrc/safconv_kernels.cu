@@ -320,6 +320,9 @@ struct IfftArgs {
     const int* grpStart;   /* partial slots of group g are grpStart[g] .. grpStart[g+1]-1 (consecutive) */
     const float2* Zp2;     /* second list of partial tiles (head pass after a pre-computed tail pass), or NULL */
     const int* grpStart2;
+    const float2* headH;   /* != NULL: K3 adds the newest partition itself, sum_ni H_0[no][ni][k] * X_t[ni][k], straight from */
+    const float2* headX;   /*          the filter / delay-line arrays (look-ahead latency path: no separate head pass)      */
+    int P, nIn, RS;
     const float2* tw;
     float* out;            /* [B][nOutLocal][hop] */
     float* tail;           /* [nOutLocal][hop] */
@@ -329,6 +332,17 @@ struct IfftArgs {
     int hop, M, logM, nKT, OTsz, nOutLocal, B;
     float scale;           /* 1/N */
 };
+
+/* packed-bin-aware complex multiply-accumulate */
+__device__ __forceinline__ void cmac_packed(float2& acc, float2 h, float2 x, bool packed)
+{
+    const float xb = packed ? 0.f : x.y;
+    const float xd = packed ? x.y : x.x;
+    acc.x = fmaf(h.x, x.x, acc.x);
+    acc.x = fmaf(-h.y, xb, acc.x);
+    acc.y = fmaf(h.x, xb, acc.y);
+    acc.y = fmaf(h.y, xd, acc.y);
+}
 
 /* sum the split-K partial tiles of output `no` into sm[0..M) and run the inverse real FFT (bit-reversed result) */
 __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2* Zp, int no, float2* sm, float2* stw)
@@ -354,6 +368,18 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
             const int r0 = __ldg(a.grpStart2 + g), r1 = __ldg(a.grpStart2 + g + 1);
             const float2* s2 = a.Zp2 + ((size_t)r0 * a.OTsz + nl) * SC_BK + (k & 31);
             for (int r = r0; r < r1; ++r, s2 += qs) z = caddf(z, s2[0]);
+        }
+        if (a.headH) {
+            /* partition 0 of group (ot, kt): rows [ni][OTsz][32] of H, row ni of the newest delay-line slot */
+            const int head = (int)(a.counters[0] % (unsigned)a.RS);
+            const float2* __restrict__ Hk = a.headH + ((size_t)g * a.P * a.nIn * a.OTsz + nl) * SC_BK + (k & 31);
+            const float2* __restrict__ Xk = a.headX + ((size_t)(k >> 5) * a.RS + head) * a.nIn * SC_BK + (k & 31);
+            const bool packed = (k == 0);
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 16
+            for (int ni = 0; ni < a.nIn; ++ni)
+                cmac_packed(acc, __ldg(Hk + (size_t)ni * qs), __ldg(Xk + (size_t)ni * SC_BK), packed);
+            z = caddf(z, acc);
         }
         sm[padi(k, a.logM)] = z;
     }
@@ -432,16 +458,6 @@ struct MultiArgs {
     float scale;
 };
 
-/* packed-bin-aware complex multiply-accumulate */
-__device__ __forceinline__ void cmac_packed(float2& acc, float2 h, float2 x, bool packed)
-{
-    const float xb = packed ? 0.f : x.y;
-    const float xd = packed ? x.y : x.x;
-    acc.x = fmaf(h.x, x.x, acc.x);
-    acc.x = fmaf(-h.y, xb, acc.x);
-    acc.y = fmaf(h.x, xb, acc.y);
-    acc.y = fmaf(h.y, xd, acc.y);
-}
 
 __global__ void multi_fused_kernel(MultiArgs a)
 {
@@ -1267,6 +1283,7 @@ int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpas
 static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks)
 {
     a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart; a.Zp2 = NULL; a.grpStart2 = NULL;
+    a.headH = NULL; a.headX = NULL; a.P = pl->P; a.nIn = pl->nIn; a.RS = pl->RS;
     a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
     a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
@@ -1286,6 +1303,12 @@ int scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev
     fill_ifft_args(a, pl, b, d_out, 1);
     if (p1) { a.Zp = (const float2*)(zpSel1 ? p1->ZpB : p1->Zp); a.grpStart = p1->grpStart; }
     if (p2) { a.Zp2 = (const float2*)p2->Zp; a.grpStart2 = p2->grpStart; }
+    if (p1 && !p2 && p1->pLo == 1) {                 /* tail pass only: K3 adds partition 0 itself, with twice the threads in flight */
+        a.headH = (const float2*)b->H; a.headX = (const float2*)b->X;
+        int threads = 2 * pl->fftThreads; if (threads > 512) threads = 512;
+        ifft_ola_kernel<<<pl->nOutLocal, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
+        return (int)cudaGetLastError();
+    }
     ifft_ola_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -1360,7 +1383,7 @@ int scdev_multi_batch(const scdev_plan* pl, const scdev_bufs* b, const float* d_
         }
     } else {
         IfftArgs o;
-        o.Zp = NULL; o.grpStart = NULL; o.Zp2 = NULL; o.grpStart2 = NULL; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
+        o.Zp = NULL; o.grpStart = NULL; o.Zp2 = NULL; o.grpStart2 = NULL; o.headH = NULL; o.headX = NULL; o.P = 0; o.nIn = 0; o.RS = 0; o.tw = NULL; o.out = d_out; o.tail = b->tail; o.zt = b->zt; o.counters = b->counters;
         o.zpStride = 0; o.hop = pl->hop; o.M = pl->M; o.logM = pl->logM; o.nKT = 0; o.OTsz = 0;
         o.nOutLocal = pl->nOutLocal; o.B = nBlocks; o.scale = 0.f;
         const size_t n = (size_t)pl->nOutLocal * pl->hop;

@@ -12,6 +12,8 @@ lib = saf.lib(); fp = C.POINTER(C.c_float)
 xin = torch.rand((w["nIn"], w["hop"])).pin_memory(); yout = torch.empty((w["nOut"], w["hop"])).pin_memory()
 xp, yp = C.cast(xin.data_ptr(), fp), C.cast(yout.data_ptr(), fp)
 ts = []
+pace = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0      # seconds between calls (0 = back to back)
 for i in range(14):
+    if pace: time.sleep(pace)
     t0 = time.perf_counter(); lib.saf_matrixConv_apply(mc.handle, xp, yp); ts.append(1e6 * (time.perf_counter() - t0))
 print("host us per call:", [round(t) for t in ts])
