@@ -287,7 +287,8 @@ def test_lookahead_tail_head_split(saf, orc, hop, L, nIn, nOut, nblk):
 
 
 @pytest.mark.parametrize("hop,L,nIn,nOut,T", [(64, 200, 3, 2, 20), (128, 128, 1, 1, 5), (256, 2048, 11, 5, 300),
-                                               (32, 1000, 2, 3, 270), (512, 3000, 4, 9, 40), (4096, 6000, 2, 3, 5)])
+                                               (32, 1000, 2, 3, 270), (512, 3000, 4, 9, 40), (4096, 6000, 2, 3, 5),
+                                               (96, 500, 3, 2, 40), (300, 1000, 5, 7, 30), (1024, 2500, 6, 64, 12)])
 def test_offline_tensor_core_render_vs_oracle(saf, orc, hop, L, nIn, nOut, T):
     """safconv_render_offline (tcgen05 per-bin GEMM, 3xTF32 split, fp32 accumulate in TMEM) == the reference's
     block-by-block convolution from a zero state, within the north_star tolerance."""
@@ -412,7 +413,8 @@ def test_offline_render_c5_shape_vs_streaming(saf):
     print("C5-shape offline vs streaming", ma, l2, mc.offline_times_ms())
 
 
-@pytest.mark.parametrize("hop,L,nCH,nblk", [(512, 4096, 16, 70), (64, 300, 3, 41), (2048, 9000, 2, 9)])
+@pytest.mark.parametrize("hop,L,nCH,nblk", [(512, 4096, 16, 70), (64, 300, 3, 41), (2048, 9000, 2, 9),
+                                            (100, 450, 5, 37), (256, 5000, 3, 20), (128, 128, 40, 35)])
 def test_multiconv_batched_device_blocks(saf, orc, hop, L, nCH, nblk):
     """multiConv on device-resident blocks: all forward FFTs, then all (channel, block) MACs + inverse FFTs, then
     the overlap-add chain -- equal to one fused launch per block (bit-identical where both use the same FFT core),
@@ -437,13 +439,17 @@ def test_multiconv_batched_device_blocks(saf, orc, hop, L, nCH, nblk):
         outs.append(d_out.cpu().numpy().transpose(1, 0, 2).reshape(nCH, nblk * hop))
     check(outs[0], ref, "multiConv batched")
     yh = saf.MultiConv(hop, H).run(x)
-    if 2 * hop > 1024:
+    N = 64
+    while N < 2 * hop:
+        N *= 2
+    warp_fft = 64 <= N // 2 <= 512 and -(-L // hop) <= 16        # the batched path's own condition (scdev_multi_batch)
+    if not warp_fft:
         # shared-memory FFT everywhere: the batched kernels keep the summation order of the fused one-block kernel
         assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
         assert np.array_equal(yh, outs[0])
     else:
-        # FFT sizes up to 1024: the batched path runs on the warp-level register FFT, single blocks on the fused
-        # shared-memory kernel -- same values to rounding
+        # FFT sizes up to 1024 and up to 16 partitions: the batched path runs on the warp-level register FFT, single
+        # blocks on the fused shared-memory kernel -- same values to rounding
         for i, y in enumerate((outs[1], outs[2], yh)):
             check(y, ref, f"multiConv path {i + 1}")
             ma, l2 = err_metrics(y, outs[0])
