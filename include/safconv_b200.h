@@ -179,7 +179,7 @@ void fftfilt(float* x, float* h, int x_len, int h_len, int nCH, float* y);
  * Equal (to fp32 rounding) to a fresh handle's saf_matrixConv_apply called nFrames times:
  * the state before the first frame is zero and the handle's streaming state is neither used nor changed.
  * Layouts are channel-major whole signals: in [nCHin][nFrames*hopSize], out [nOutLocal][nFrames*hopSize].
- * matrixConv handles only; needs nOutLocal <= 64 and hopSize <= 4096.
+ * matrixConv handles only; hopSize <= 4096 (more than 64 local outputs are rendered as tiles of 64).
  * _device: device pointers, enqueued on the handle's stream without synchronising.
  */
 int safconv_render_offline(void* h, const float* in, float* out, int nFrames);

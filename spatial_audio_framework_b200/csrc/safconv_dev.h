@@ -94,6 +94,7 @@ typedef struct scdev_offline {
     void  *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][16 B] ((output, re/im) x (input, re/im))            */
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
     float *scal;             /* fp16 operands: [0] bound on the input spectra of the current render, [1] bound on the filter spectra */
+    int nTiles;              /* output tiles of Nn/2 (<= 64) outputs: grid.z of the GEMM                          */
     int f16, ipc;            /* 1: fp16 operands (default), 0: tf32; inputs per k-group (4 / 2)                 */
     int wfft;                /* 1: warp-register FFT transform kernels (fp16 operands, M <= 1024)                */
     void *wtab;              /* their two [M/32][32] twiddle tables                                              */

@@ -137,6 +137,7 @@ struct PackArgs {
     const float* scal;     /* F16: scal[1] = bound on the filter spectra */
     size_t total;          /* elements of H */
     int nKT, P, nIn, OTsz, nOutLocal, nKG, Nn;
+    size_t tileBytes;      /* bytes of one output tile (Nn/2 outputs) of HG: output tiles are the outermost dimension */
 };
 
 template <bool F16>
@@ -152,8 +153,11 @@ __global__ void offline_pack_filters_kernel(PackArgs a)
         const int p  = (int)(r % a.P);    r /= a.P;
         const int kt = (int)(r % a.nKT);  r /= a.nKT;
         const int ot = (int)r;
-        const int no = ot * a.OTsz + nl;
-        if (no >= a.nOutLocal) continue;
+        const int noAll = ot * a.OTsz + nl;
+        if (noAll >= a.nOutLocal) continue;
+        const int tile = noAll / (a.Nn >> 1), no = noAll - tile * (a.Nn >> 1);      /* output tile of the GEMM, output inside it */
+        unsigned char* HGhi = a.HGhi + (size_t)tile * a.tileBytes;
+        unsigned char* HGlo = a.HGlo + (size_t)tile * a.tileBytes;
         const int bin = kt * 32 + b;
         const float2 h = a.H[e];
         /* complex product as a real 2x2 block; bin 0 is the packed (DC, Nyquist) pair: two real products */
@@ -166,20 +170,20 @@ __global__ void offline_pack_filters_kernel(PackArgs a)
             const size_t iRe = base + (size_t)(2 * no) * 16, iIm = base + (size_t)(2 * no + 1) * 16;
             __half h0, l0, h1, l1;
             f16_split(rowRe.x * sc, h0, l0); f16_split(rowRe.y * sc, h1, l1);
-            *reinterpret_cast<uint32_t*>(a.HGhi + iRe) = pack_h2(h0, h1);
-            *reinterpret_cast<uint32_t*>(a.HGlo + iRe) = pack_h2(l0, l1);
+            *reinterpret_cast<uint32_t*>(HGhi + iRe) = pack_h2(h0, h1);
+            *reinterpret_cast<uint32_t*>(HGlo + iRe) = pack_h2(l0, l1);
             f16_split(rowIm.x * sc, h0, l0); f16_split(rowIm.y * sc, h1, l1);
-            *reinterpret_cast<uint32_t*>(a.HGhi + iIm) = pack_h2(h0, h1);
-            *reinterpret_cast<uint32_t*>(a.HGlo + iIm) = pack_h2(l0, l1);
+            *reinterpret_cast<uint32_t*>(HGhi + iIm) = pack_h2(h0, h1);
+            *reinterpret_cast<uint32_t*>(HGlo + iIm) = pack_h2(l0, l1);
         } else {
             const size_t base = ((((size_t)bin * a.P + p) * a.nKG + (k >> 2)) * a.Nn) * 16 + (size_t)(k & 3) * 4;
             const size_t iRe = base + (size_t)(2 * no) * 16, iIm = base + (size_t)(2 * no + 1) * 16;
             const float2 reHi = make_float2(tf32_hi(rowRe.x), tf32_hi(rowRe.y));
             const float2 imHi = make_float2(tf32_hi(rowIm.x), tf32_hi(rowIm.y));
-            *reinterpret_cast<float2*>(a.HGhi + iRe) = reHi;
-            *reinterpret_cast<float2*>(a.HGhi + iIm) = imHi;
-            *reinterpret_cast<float2*>(a.HGlo + iRe) = make_float2(tf32_lo(rowRe.x, reHi.x), tf32_lo(rowRe.y, reHi.y));
-            *reinterpret_cast<float2*>(a.HGlo + iIm) = make_float2(tf32_lo(rowIm.x, imHi.x), tf32_lo(rowIm.y, imHi.y));
+            *reinterpret_cast<float2*>(HGhi + iRe) = reHi;
+            *reinterpret_cast<float2*>(HGhi + iIm) = imHi;
+            *reinterpret_cast<float2*>(HGlo + iRe) = make_float2(tf32_lo(rowRe.x, reHi.x), tf32_lo(rowRe.y, reHi.y));
+            *reinterpret_cast<float2*>(HGlo + iIm) = make_float2(tf32_lo(rowIm.x, imHi.x), tf32_lo(rowIm.y, imHi.y));
         }
     }
 }
@@ -437,6 +441,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 /* ------------------------------------------------------------------------------------------ */
 struct OffGemmArgs {
     const unsigned char *XGhi, *XGlo, *HGhi, *HGlo;
+    size_t hgTileBytes;    /* output tile blockIdx.z: HG + z * hgTileBytes, Ys + z * ysTileFloats */
+    size_t ysTileFloats;
     const float* scal;     /* fp16 operands: the two magnitude bounds whose scales are divided out of the result */
     float* Ys;             /* [bin][Tpad][Nn] */
     int P, nKG, nKC, Nn, rowsAlloc, Tpad, rowsX, tmemCols, flush;
@@ -457,6 +463,7 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
     extern __shared__ __align__(128) unsigned char smraw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * OFF_MT, bin = blockIdx.y;
+
     const uint32_t xPlane = (uint32_t)a.rowsX * 16u;        /* one k-group column of the frame tile   */
     const uint32_t xStage = 2u * OFF_KG * xPlane;           /* hi + lo                                */
     const uint32_t hPlane = (uint32_t)a.Nn * 16u;
@@ -509,7 +516,7 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                     mbar_wait(&hempty[hs], hpar);
                     mbar_expect_tx(&hfull[hs], hStage);
                     for (int hl = 0; hl < 2; ++hl) {
-                        const unsigned char* src = (hl ? a.HGlo : a.HGhi)
+                        const unsigned char* src = (hl ? a.HGlo : a.HGhi) + (size_t)blockIdx.z * a.hgTileBytes
                                          + ((((size_t)bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 16;
                         tma_bulk_g2s(smH + (size_t)hs * hStage + (size_t)hl * OFF_KG * hPlane, src, OFF_KG * hPlane, &hfull[hs]);
                     }
@@ -628,6 +635,7 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
         }
         /* fp16 operands were scaled by exact powers of two: divide them out (exact as well) */
         const float inv = F16 ? 1.f / (pow2_scale(a.scal[0]) * pow2_scale(a.scal[1])) : 1.f;
+        float* Ys = a.Ys + (size_t)blockIdx.z * a.ysTileFloats;
         if (NT) {
             /* sum[t][c] = output row n = 32 q + lane of frame t0 + hh*128 + t*64 + c: a warp stores 32 consecutive n */
             const int n = q * 32 + lane;
@@ -636,13 +644,13 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
 #pragma unroll
                 for (int c = 0; c < OFF_MAX_HALF; ++c) {
                     const int row = t0 + hh * 128 + t * 64 + c;
-                    a.Ys[((size_t)bin * a.Tpad + row) * a.Nn + n] = sum[t][c] * inv;
+                    Ys[((size_t)bin * a.Tpad + row) * a.Nn + n] = sum[t][c] * inv;
                 }
         } else
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int row = t0 + t * 128 + q * 32 + lane;
-            float* dst = a.Ys + ((size_t)bin * a.Tpad + row) * a.Nn + hh * halfN;
+            float* dst = Ys + ((size_t)bin * a.Tpad + row) * a.Nn + hh * halfN;
 #pragma unroll
             for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 4)
                 if (c0 < halfN)
@@ -664,6 +672,8 @@ struct OffIfftArgs {
     float* out;            /* [nOut][(T-skip)*hop], zeroed before the launch */
     const float2* tw;
     int hop, M, logM, nOut, Nn2, Tpad, T;
+    size_t ysTileC;        /* complex elements of one output tile of Ys ([tile][bin][Tpad][Nn2]) */
+    int logNn2;            /* Nn2 = outputs per tile, a power of two */
     int opc;               /* outputs per inverse-FFT CTA (4 or 8): 32- or 64-byte contiguous spectrum loads */
     int skip;              /* leading halo frames that are transformed but not written to `out` */
     float scale;
@@ -691,7 +701,7 @@ __global__ void offline_ifft_kernel(OffIfftArgs a)
                 const int idx = base + u * blockDim.x;
                 const int j = idx & (OPC - 1), k = idx >> logOPC;
                 const int no = og * OPC + j;
-                v[u] = (idx < total && no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+                v[u] = (idx < total && no < a.nOut) ? __ldg(a.Ys + (size_t)(no >> a.logNn2) * a.ysTileC + (((size_t)k * a.Tpad + t) << a.logNn2) + (no & (a.Nn2 - 1))) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -825,7 +835,7 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_w_kernel(OffIfft
             const int idx = base + q * OFFW_THREADS;
             const int j = idx & 7, k = idx >> 3;
             const int no = og * 8 + j;
-            u[q] = (idx < M * 8 && no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+            u[q] = (idx < M * 8 && no < a.nOut) ? __ldg(a.Ys + (size_t)(no >> a.logNn2) * a.ysTileC + (((size_t)k * a.Tpad + t) << a.logNn2) + (no & (a.Nn2 - 1))) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -954,7 +964,7 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_t_kernel(OffIfft
             const int idx = base + q * OFFW_THREADS;
             const int j = idx & 7, k = idx >> 3;
             const int no = og * 8 + j;
-            u[q] = (no < a.nOut) ? __ldg(a.Ys + ((size_t)k * a.Tpad + t) * a.Nn2 + no) : make_float2(0.f, 0.f);
+            u[q] = (no < a.nOut) ? __ldg(a.Ys + (size_t)(no >> a.logNn2) * a.ysTileC + (((size_t)k * a.Tpad + t) << a.logNn2) + (no & (a.Nn2 - 1))) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1062,7 +1072,8 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
     if (pl->kind != SC_KIND_MATRIX) return (int)cudaErrorInvalidValue;
     int Nn = 32;                                                     /* UMMA N: 2*nOut padded to 32 / 64 / 128 */
     while (Nn < 2 * pl->nOutLocal) Nn <<= 1;
-    if (Nn > 2 * OFF_MAX_HALF) return (int)cudaErrorInvalidValue;    /* one N tile: nOutLocal <= 64 */
+    if (Nn > 2 * OFF_MAX_HALF) Nn = 2 * OFF_MAX_HALF;                /* more than 64 outputs: tiles of 64 (grid.z of the GEMM) */
+    o->nTiles = (2 * pl->nOutLocal + Nn - 1) / Nn;
     if (pl->P - 1 > 1024) return (int)cudaErrorInvalidValue;
     o->Nn = Nn;
     if (!o->packed) {                                                /* operand type is fixed per handle */
@@ -1100,7 +1111,8 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         if ((size_t)(o->ipc * o->fpc + 1) * arr > cap || (size_t)(o->opc + 1) * arr > cap) return (int)cudaErrorInvalidValue;
     }
     if (!o->packed) {
-        const size_t hgBytes = (size_t)pl->M * pl->P * o->nKG * Nn * 16;
+        const size_t hgTile = (size_t)pl->M * pl->P * o->nKG * Nn * 16;
+        const size_t hgBytes = hgTile * o->nTiles;
         SC_CHECK(cudaMalloc((void**)&o->HGhi, hgBytes));
         SC_CHECK(cudaMalloc((void**)&o->HGlo, hgBytes));
         SC_CHECK(cudaMalloc((void**)&o->scal, 4 * sizeof(float)));
@@ -1111,7 +1123,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         a.H = (const float2*)b->H; a.HGhi = (unsigned char*)o->HGhi; a.HGlo = (unsigned char*)o->HGlo; a.scal = o->scal;
         a.total = (size_t)pl->nOT * pl->nKT * pl->P * pl->nIn * pl->OTsz * SC_BK;
         a.nKT = pl->nKT; a.P = pl->P; a.nIn = pl->nIn; a.OTsz = pl->OTsz; a.nOutLocal = pl->nOutLocal;
-        a.nKG = o->nKG; a.Nn = Nn;
+        a.nKG = o->nKG; a.Nn = Nn; a.tileBytes = hgTile;
         if (o->f16) {
             offline_absmax_kernel<<<148 * 8, 256, 0, st>>>((const float*)b->H, 2 * a.total, o->scal + 1);
             SC_CHECK(cudaGetLastError());
@@ -1137,7 +1149,7 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
         const size_t xgBytes = (size_t)pl->M * o->nKG * rowsAlloc * 16;
         SC_CHECK(cudaMalloc((void**)&o->XGhi, xgBytes));
         SC_CHECK(cudaMalloc((void**)&o->XGlo, xgBytes));
-        SC_CHECK(cudaMalloc((void**)&o->Ys, (size_t)pl->M * Tpad * Nn * sizeof(float)));
+        SC_CHECK(cudaMalloc((void**)&o->Ys, (size_t)o->nTiles * pl->M * Tpad * Nn * sizeof(float)));
         /* padding k-groups (odd nIn / K padding) are never written by the FFT kernel: zero them once */
         SC_CHECK(cudaMemsetAsync(o->XGhi, 0, xgBytes, st));
         SC_CHECK(cudaMemsetAsync(o->XGlo, 0, xgBytes, st));
@@ -1188,6 +1200,8 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     g.HGhi = (const unsigned char*)o->HGhi; g.HGlo = (const unsigned char*)o->HGlo; g.Ys = o->Ys; g.scal = o->scal;
     g.P = pl->P; g.nKG = o->nKG; g.nKC = o->nKC; g.Nn = o->Nn; g.rowsAlloc = rowsAlloc; g.Tpad = o->capTpad;
     g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush;
+    g.hgTileBytes = (size_t)pl->M * pl->P * o->nKG * o->Nn * 16;
+    g.ysTileFloats = (size_t)pl->M * o->capTpad * o->Nn;
     /* frames on the UMMA N axis (one M128 x N256 instruction per product term) when the filter rows fill M = 128 */
     static int ntEnv = -1;
     if (ntEnv < 0) { const char* v = getenv("SAFCONV_OFF_NT"); ntEnv = v ? atoi(v) : 1; }
@@ -1195,7 +1209,7 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     const int mm = nt ? 128 : 128, nn = nt ? 256 : o->Nn;
     g.idesc = o->f16 ? umma_idesc_f16(mm, nn) : umma_idesc_tf32(mm, nn);
     {
-        dim3 grid(Tpad / OFF_MT, pl->M);
+        dim3 grid(Tpad / OFF_MT, pl->M, o->nTiles);
         if (o->f16) { if (nt) offline_gemm_kernel<true, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
                       else    offline_gemm_kernel<true, false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g); }
         else        { if (nt) offline_gemm_kernel<false, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
@@ -1207,6 +1221,8 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     i.Ys = (const float2*)o->Ys; i.out = d_out; i.tw = (const float2*)b->tw;
     i.hop = pl->hop; i.M = pl->M; i.logM = pl->logM; i.nOut = pl->nOutLocal; i.Nn2 = o->Nn / 2;
     i.Tpad = o->capTpad; i.T = T; i.skip = skip; i.scale = 1.0f / (float)pl->N;
+    i.ysTileC = (size_t)pl->M * o->capTpad * (o->Nn / 2);
+    i.logNn2 = 0; while ((1 << i.logNn2) < o->Nn / 2) i.logNn2++;
     i.wT1 = (const float2*)o->wtab;
     {
         i.opc = o->opc;

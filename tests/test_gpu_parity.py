@@ -288,7 +288,8 @@ def test_lookahead_tail_head_split(saf, orc, hop, L, nIn, nOut, nblk):
 
 @pytest.mark.parametrize("hop,L,nIn,nOut,T", [(64, 200, 3, 2, 20), (128, 128, 1, 1, 5), (256, 2048, 11, 5, 300),
                                                (32, 1000, 2, 3, 270), (512, 3000, 4, 9, 40), (4096, 6000, 2, 3, 5),
-                                               (96, 500, 3, 2, 40), (300, 1000, 5, 7, 30), (1024, 2500, 6, 64, 12)])
+                                               (96, 500, 3, 2, 40), (300, 1000, 5, 7, 30), (1024, 2500, 6, 64, 12),
+                                               (128, 600, 3, 70, 20), (256, 700, 2, 130, 9)])      # > 64 outputs: GEMM output tiles
 def test_offline_tensor_core_render_vs_oracle(saf, orc, hop, L, nIn, nOut, T):
     """safconv_render_offline (tcgen05 per-bin GEMM, 3xTF32 split, fp32 accumulate in TMEM) == the reference's
     block-by-block convolution from a zero state, within the north_star tolerance."""
