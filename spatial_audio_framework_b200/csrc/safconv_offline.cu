@@ -998,6 +998,14 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_t_kernel(OffIfft
         if (no >= a.nOut) break;
         const float* z = reinterpret_cast<const float*>(stg + (size_t)j * WFFT_TILE);
         float* o = a.out + (size_t)no * To * a.hop;
+        if ((a.hop & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0)) {
+            /* 16-byte vector reductions (red.global.add.v4.f32): a quarter of the atomic operations; every component
+             * still receives exactly its two addends */
+            for (int i = 4 * threadIdx.x; i < a.hop; i += 4 * OFFW_THREADS) {
+                if (f0 >= 0)            atomicAdd(reinterpret_cast<float4*>(o + (size_t)f0 * a.hop + i), *reinterpret_cast<const float4*>(z + i));
+                if (f1 >= 0 && f1 < To) atomicAdd(reinterpret_cast<float4*>(o + (size_t)f1 * a.hop + i), *reinterpret_cast<const float4*>(z + i + a.hop));
+            }
+        } else
         for (int i = threadIdx.x; i < a.hop; i += OFFW_THREADS) {
             if (f0 >= 0)            atomicAdd(o + (size_t)f0 * a.hop + i, z[i]);
             if (f1 >= 0 && f1 < To) atomicAdd(o + (size_t)f1 * a.hop + i, z[i + a.hop]);
