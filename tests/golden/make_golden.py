@@ -69,5 +69,20 @@ def main():
         np.savez(OUT / f"rfft_{N}.npz", kind="rfft", N=N, x=xx, X=X, xb=xb)
 
 
+def fftconv_fixtures():
+    """fftconv / fftfilt (saf_utility_fft.c:157-228) of the compiled reference; own seed so that adding them leaves
+    the fixtures above untouched."""
+    rng = np.random.default_rng(20261019)
+    for name, nCH, xl, hl in (("fftconv_a", 3, 700, 129), ("fftconv_b", 2, 2048, 2048), ("fftconv_c", 1, 5, 7)):
+        x = rng.uniform(-1, 1, (nCH, xl)).astype(np.float32)
+        h = rng.uniform(-1, 1, (nCH, hl)).astype(np.float32)
+        np.savez(OUT / f"{name}.npz", kind="fftconv", x=x, h=h, y=O.ref_fftconv(x, h), yfilt=O.ref_fftconv(x, h, True))
+        print(name, nCH, xl, hl)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fftconv":
+        fftconv_fixtures()
+    else:
+        main()
+        fftconv_fixtures()

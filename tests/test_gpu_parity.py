@@ -110,6 +110,15 @@ def test_against_reference_golden(saf, path):
     check(y, g["y"], path.stem)
 
 
+@pytest.mark.parametrize("path", golden_files("fftconv"), ids=lambda p: p.stem)
+def test_fftconv_against_reference_golden(saf, path):
+    """fftconv / fftfilt fixtures produced by the compiled reference (tests/golden/make_golden.py fftconv)."""
+    import spatial_audio_framework_b200 as pkg
+    g = np.load(path)
+    check(pkg.fftconv(g["x"], g["h"]), g["y"], path.stem)
+    check(pkg.fftfilt(g["x"], g["h"]), g["yfilt"], path.stem + " (fftfilt)")
+
+
 def test_closer_to_truth_than_needed(saf, orc):
     """Three-way distances on a mid-size case: |gpu-ref|, |gpu-truth64|, |ref-truth64|."""
     rng = np.random.default_rng(99)

@@ -78,6 +78,10 @@ def test_oracle_matches_golden(path):
         hop = int(g["hop"])
         tv = O.OracleTVConv(hop, g["H"], int(g["initIdx"]))
         y = np.concatenate([tv.apply(g["x"][0, i * hop:(i + 1) * hop], int(ir)) for i, ir in enumerate(g["seq"])], axis=1)
+    elif kind == "fftconv":
+        assert np.array_equal(O.oracle_fftconv(g["x"], g["h"]), g["y"])
+        assert np.array_equal(O.oracle_fftconv(g["x"], g["h"], True), g["yfilt"])
+        return
     else:
         X, xb = O.oracle_rfft(int(g["N"]), g["x"])
         assert np.array_equal(X, g["X"]) and np.array_equal(xb, g["xb"])
