@@ -539,197 +539,212 @@ static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, in
 
 static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out) { return enqueue_blocks(h, d_in, d_out, 1); }
 
-/* host-pointer apply: pinned staging -> H2D -> kernels -> D2H -> sync (reference semantics: synchronous) */
+/* ---- look-ahead apply (matrix, P >= 2; DESIGN.md §4 "Look-ahead apply") --------------------------------------
+ * Streams:  stream     tail passes (+ head pass / K3 in the latency regime)
+ *           streamIn   K1 of the new block (overlaps a tail pass that is still streaming)
+ *           streamOut  high priority: head pass and K3 in the throughput regime, K3 of the first block
+ * State:    tailReady  a tail pass for block `count` has been enqueued (partial tiles in tail buffer count & 1)
+ *           evTail     end of the most recent tail pass;  evDone  this block's output is complete */
+
+#define LA_TRY(call) do { if (!e) e = (call); } while (0)
+#define LA_TRACE(i, st) do { if (tr) scdev_event_record(h->trEv[i], (st)); } while (0)
+
+/* K1 of the new block; returns with `stream` ordered behind it.  zc: straight from the page-locked host buffer. */
+static int la_input(safconv_handle* h, const float* src, int zc)
+{
+    const scdev_plan* pl = &h->pl;
+    int e = 0;
+    if (!zc) {
+        e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
+        LA_TRY(scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream));
+        return e;
+    }
+    if (!h->tailReady) {                  /* something else may still be running on `stream`: order K1 behind it */
+        e = scdev_event_record(h->evFence, h->stream);
+        LA_TRY(scdev_stream_wait_event(h->streamIn, h->evFence));
+    }
+    LA_TRY(scdev_input_fft(pl, &h->b, src, 1, h->streamIn));
+    LA_TRY(scdev_event_record(h->evIn, h->streamIn));
+    LA_TRY(scdev_stream_wait_event(h->stream, h->evIn));
+    return e;
+}
+
+/* Throughput regime (the previous tail pass is still running when the caller comes back): `stream` carries nothing
+ * but tail passes, back to back.  The head pass of block c runs on the side stream with a two-stage pipeline (69 KB of
+ * shared memory: its CTAs fit on the SMs beside the resident tail CTAs) while the block's own tail pass is still
+ * streaming; K3 follows as soon as that tail pass is done, beside the tail pass of block c+1. */
+static int la_throughput(safconv_handle* h, unsigned int c, int zc, float* kout, float* dst, int tr)
+{
+    const scdev_plan* pl = &h->pl;
+    const int tb = (int)(c & 1u);
+    scdev_macpass head2 = h->headPass;
+    head2.stages = 2;
+    int e = 0;
+    if (!zc) e = scdev_event_record(h->evMac, h->stream);                 /* K1 ran on `stream`: its spectrum is ready here */
+    LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream));
+    LA_TRY(scdev_stream_wait_event(h->streamOut, zc ? h->evIn : h->evMac));
+    LA_TRACE(0, h->streamOut);
+    LA_TRY(scdev_mac_pass(pl, &h->b, &head2, 0, 1, 0, -1, h->streamOut));
+    LA_TRACE(1, h->streamOut);
+    LA_TRY(scdev_stream_wait_event(h->streamOut, h->evTail));             /* tail pass of block c: K3 needs both */
+    LA_TRACE(3, h->streamOut);
+    LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut));
+    if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut));
+    LA_TRACE(4, h->streamOut);
+    LA_TRY(scdev_event_record(h->evDone, h->streamOut));
+    return e;
+}
+
+/* Latency regime (real-time pacing: the GPU is idle when the block arrives).  With a pre-computed tail there is no
+ * head-pass launch at all: K3 adds the newest partition itself while it gathers the tail's partial tiles (or, with
+ * SAFCONV_HEAD_IN_K3=0, head pass then K3 on the side stream).  Without one (first block, or after any other call on the
+ * handle) the full MAC runs.  The next tail pass is ordered behind K3. */
+static int la_latency(safconv_handle* h, unsigned int c, int hadTail, int zc, float* kout, float* dst, int tr)
+{
+    const scdev_plan* pl = &h->pl;
+    const int tb = (int)(c & 1u);
+    int e = 0;
+    if (hadTail && h->headInK3) {
+        LA_TRACE(0, h->stream); LA_TRACE(1, h->stream); LA_TRACE(3, h->stream);
+        LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, NULL, kout, h->stream));
+        if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream));
+        LA_TRACE(4, h->stream);
+        LA_TRY(scdev_event_record(h->evDone, h->stream));
+    } else {
+        LA_TRACE(0, h->stream);
+        if (hadTail) LA_TRY(scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream));
+        else         LA_TRY(scdev_mac(pl, &h->b, 0, 1, h->stream));
+        LA_TRACE(1, h->stream);
+        LA_TRY(scdev_event_record(h->evMac, h->stream));
+        LA_TRY(scdev_stream_wait_event(h->streamOut, h->evMac));
+        LA_TRACE(3, h->streamOut);
+        if (hadTail) LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut));
+        else         LA_TRY(scdev_ifft_ola(pl, &h->b, kout, h->streamOut));
+        if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut));
+        LA_TRACE(4, h->streamOut);
+        LA_TRY(scdev_event_record(h->evDone, h->streamOut));
+        LA_TRY(scdev_stream_wait_event(h->stream, h->evDone));
+    }
+    LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream));
+    return e;
+}
+
+/* SAFCONV_TRACE=1: device timeline of this call on stderr (trEv[2] = end of the tail pass enqueued by the previous call) */
+static void la_trace_report(safconv_handle* h, unsigned int c, int tr)
+{
+    if (tr && h->count > 3) {
+        float gap = 0.f, head = 0.f, k3wait = 0.f, k3 = 0.f;
+        scdev_event_elapsed_ms(h->trEv[2], h->trEv[0], &gap);
+        scdev_event_elapsed_ms(h->trEv[0], h->trEv[1], &head);
+        scdev_event_elapsed_ms(h->trEv[1], h->trEv[3], &k3wait);
+        scdev_event_elapsed_ms(h->trEv[3], h->trEv[4], &k3);
+        fprintf(stderr, "[safconv trace] block %u: prev tail end -> head start %.1f us, head %.1f us, head end -> K3 start %.1f us, K3 %.1f us\n",
+                c, 1e3f * gap, 1e3f * head, 1e3f * k3wait, 1e3f * k3);
+    }
+    if (h->trace) scdev_event_record(h->trEv[2], h->stream);      /* end of the tail pass just enqueued: read by the next call */
+}
+
+/* One block through the look-ahead sequence; on return the output is in `dst` (a page-locked host buffer). */
+static int apply_lookahead(safconv_handle* h, const float* src, float* dst)
+{
+    /* blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers */
+    const int zc = h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20);
+    float* kout = zc ? dst : h->d_out;
+    const unsigned int c = h->count;
+    const int hadTail = h->tailReady;
+    const int tr = h->trace && hadTail;
+    /* is the caller coming back faster than the GPU streams the filters? */
+    const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
+    int e = la_input(h, src, zc);
+    h->tailReady = 0;
+    if (backToBack) LA_TRY(la_throughput(h, c, zc, kout, dst, tr));
+    else            LA_TRY(la_latency(h, c, hadTail, zc, kout, dst, tr));
+    LA_TRY(scdev_event_record(h->evTail, h->stream));
+    if (!e) { h->tailReady = 1; h->count = c + 1; e = scdev_event_sync(h->evDone); }
+    if (!e) la_trace_report(h, c, tr);
+    if (e) h->tailReady = 0;
+    return e;
+}
+
+/* Blocks of up to 1 MB without look-ahead: the kernels read / write the page-locked host buffers directly -- no
+ * copy-engine round trips, one synchronisation.  Returns -1 if the handle has no such path. */
+static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int irIdx)
+{
+    const scdev_plan* pl = &h->pl;
+    if (!h->smallFused || h->useGraph || h->timingCap) return -1;
+    if (pl->kind == SC_KIND_MATRIX && h->smallOk)                 /* small problem: K1 + K2 + K3 in ONE launch */
+        return scdev_small_fused(pl, &h->b, src, dst, h->stream);
+    if (h->inBytes > (1u << 20) || h->outBytes > (1u << 20)) return -1;
+    if (pl->kind == SC_KIND_MULTI)                                /* one fused launch, one CTA per channel */
+        return scdev_multi_fused(pl, &h->b, src, dst, h->stream);
+    if (pl->kind == SC_KIND_TV) {
+        const int e = scdev_tv_fused(pl, &h->b, src, dst, irIdx, h->tvLast, h->tvLast2, h->stream);
+        h->tvLast2 = h->tvLast;                                   /* reference .c:618-619 */
+        h->tvLast  = irIdx;
+        return e;
+    }
+    if (h->lookahead) return -1;                                  /* matrix, P >= 2: apply_lookahead */
+    int e = scdev_input_fft(pl, &h->b, src, 1, h->stream);        /* single partition (or look-ahead switched off) */
+    LA_TRY(scdev_mac(pl, &h->b, 0, 1, h->stream));
+    LA_TRY(scdev_ifft_ola(pl, &h->b, dst, h->stream));
+    return e;
+}
+
+/* host-pointer apply (reference semantics: synchronous).  Caller buffers that are already page-locked
+ * (cudaHostAlloc / cudaHostRegister) are used directly; ordinary malloc'd buffers go through the handle's pinned
+ * staging buffers. */
 static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
 {
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
-    /* caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are DMA'd directly;
-     * ordinary malloc'd buffers go through the handle's pinned staging buffers */
     const int direct = h->detectPinned && scdev_is_pinned_host(in) && scdev_is_pinned_host(out);
     const float* src = direct ? in : h->h_in;
     float*       dst = direct ? out : h->h_out;
     if (!direct) memcpy(h->h_in, in, h->inBytes);
-    if (h->smallFused && h->smallOk && !h->useGraph && !h->timingCap) {
-        /* latency path: one launch, the kernel reads / writes the page-locked host buffers directly */
-        e = scdev_small_fused(&h->pl, &h->b, src, dst, h->stream);
+
+    e = apply_zero_copy(h, src, dst, irIdx);
+    if (e >= 0) {
         if (!e) e = scdev_stream_sync(h->stream);
-        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (fused)", e); return; }
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (zero-copy)", e); return; }
         h->count++;
-        if (!direct) memcpy(out, h->h_out, h->outBytes);
-        return;
-    }
-    if (h->pl.kind == SC_KIND_MULTI && h->smallFused && !h->useGraph && !h->timingCap &&
-        h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
-        /* latency path: the fused per-channel kernel reads / writes the page-locked host buffers directly
-         * (one launch and one synchronisation, no copy-engine round trips) */
-        e = scdev_multi_fused(&h->pl, &h->b, src, dst, h->stream);
-        if (!e) e = scdev_stream_sync(h->stream);
-        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (multi, zero-copy)", e); return; }
-        h->count++;
-        if (!direct) memcpy(out, h->h_out, h->outBytes);
-        return;
-    }
-    if (h->useGraph && h->pl.kind != SC_KIND_TV) {
-        if (h->graphExec && (h->graphIn != (void*)src || h->graphOut != (void*)dst)) {
-            scdev_graph_destroy(h->graphExec);
-            h->graphExec = NULL;
-        }
-        if (!h->graphExec) {
-            e = scdev_graph_begin(h->stream);
-            if (!e) e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
-            if (!e) e = enqueue_block(h, h->d_in, h->d_out);
-            if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
-            int e2 = scdev_graph_end(h->stream, &h->graphExec);
-            if (!e) e = e2;
-            if (e) { h->graphExec = NULL; h->useGraph = 0; h_fail(h, SAFCONV_ERR_CUDA, "graph capture", e); return; }
-            h->graphIn = (void*)src; h->graphOut = (void*)dst;
-        }
-        e = scdev_graph_launch(h->graphExec, h->stream);
+    } else if (h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->useGraph && !h->timingCap) {
+        e = apply_lookahead(h, src, dst);                         /* advances h->count itself */
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (look-ahead)", e); return; }
     } else {
-        if (h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->timingCap) {
-            /* K1 -> HEAD pass (newest partition only; the TAIL pass of this block was enqueued behind the previous
-             * block) -> K3 over both partial lists -> [event] -> TAIL pass of the NEXT block.  The host waits for the
-             * event only: the next block's tail streams the filters while the caller is away.
-             * Blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers
-             * (no copy-engine round trips), and K1 runs on a side stream so that it overlaps a tail pass that is
-             * still streaming when the caller comes back early. */
-            const scdev_plan* pl = &h->pl;
-            const int zc = h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20);
-            if (zc) {
-                if (!h->tailReady) {          /* something else may still be running on `stream`: order K1 behind it */
-                    e = scdev_event_record(h->evFence, h->stream);
-                    if (!e) e = scdev_stream_wait_event(h->streamIn, h->evFence);
-                }
-                if (!e) e = scdev_input_fft(pl, &h->b, src, 1, h->streamIn);
-                if (!e) e = scdev_event_record(h->evIn, h->streamIn);
-                if (!e) e = scdev_stream_wait_event(h->stream, h->evIn);
-            } else {
-                e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
-                if (!e) e = scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream);
+        if (h->useGraph && h->pl.kind != SC_KIND_TV) {
+            if (h->graphExec && (h->graphIn != (void*)src || h->graphOut != (void*)dst)) {
+                scdev_graph_destroy(h->graphExec);
+                h->graphExec = NULL;
             }
-            float* kout = zc ? dst : h->d_out;
-            /* `stream`: [HEAD pass | full MAC] of this block (count c), then straight on with the TAIL pass of block
-             * c+1 (block index handed over explicitly: K3 has not bumped the device counter yet; partial tiles into
-             * the other tail buffer).  K3 of this block runs beside that tail pass on the high-priority side stream. */
-            const unsigned int c = h->count;
-            const int tb = (int)(c & 1u);
-            const int hadTail = h->tailReady;
-            const int tr = h->trace && hadTail;
-            /* Is the caller coming back faster than the GPU streams the filters (the previous tail pass is still
-             * running)?  Then throughput counts: K3 of this block shares the GPU with the next tail pass.  Otherwise
-             * (real-time pacing) latency counts: K3 runs alone and the next tail pass starts behind it. */
-            const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
-            if (backToBack) {
-                /* throughput regime: `stream` carries nothing but tail passes, back to back.  The head pass of this
-                 * block runs on the side stream with a two-stage pipeline (69 KB of shared memory: its CTAs fit on
-                 * the SMs beside the resident tail CTAs) while the block's own tail pass is still streaming; K3
-                 * follows as soon as that tail pass is done, beside the tail pass of the next block. */
-                scdev_macpass hp2 = h->headPass;
-                hp2.stages = 2;
-                if (!e && !zc) e = scdev_event_record(h->evMac, h->stream);         /* K1 ran on `stream`: its spectrum is ready here */
-                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
-                void* evTailC = h->evTail;                                          /* end of the tail pass of block c */
-                if (!e) e = scdev_stream_wait_event(h->streamOut, zc ? h->evIn : h->evMac);
-                if (tr) scdev_event_record(h->trEv[0], h->streamOut);
-                if (!e) e = scdev_mac_pass(pl, &h->b, &hp2, 0, 1, 0, -1, h->streamOut);   /* beside the tail pass of block c */
-                if (tr) scdev_event_record(h->trEv[1], h->streamOut);
-                if (!e) e = scdev_stream_wait_event(h->streamOut, evTailC);         /* K3 needs both */
-                if (tr) scdev_event_record(h->trEv[3], h->streamOut);
-                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut);
-                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
-                if (tr) scdev_event_record(h->trEv[4], h->streamOut);
-                if (!e) e = scdev_event_record(h->evDone, h->streamOut);
-                h->tailReady = 0;
-            } else if (hadTail && h->headInK3) {
-                /* latency regime, short version: no head pass at all -- K3 adds the newest partition itself while it
-                 * gathers the tail's partial tiles (each CTA streams its output's 1/P of the filters) */
-                if (tr) { scdev_event_record(h->trEv[0], h->stream); scdev_event_record(h->trEv[1], h->stream); scdev_event_record(h->trEv[3], h->stream); }
-                if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, NULL, kout, h->stream);
-                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
-                if (tr) scdev_event_record(h->trEv[4], h->stream);
-                if (!e) e = scdev_event_record(h->evDone, h->stream);
-                h->tailReady = 0;
-                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
-            } else {
-                if (tr) scdev_event_record(h->trEv[0], h->stream);
-                if (hadTail) { if (!e) e = scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream); }
-                else         { if (!e) e = scdev_mac(pl, &h->b, 0, 1, h->stream); }
-                h->tailReady = 0;
-                if (tr) scdev_event_record(h->trEv[1], h->stream);
-                if (!e) e = scdev_event_record(h->evMac, h->stream);
-                if (!e) e = scdev_stream_wait_event(h->streamOut, h->evMac);
-                if (tr) scdev_event_record(h->trEv[3], h->streamOut);
-                if (hadTail) { if (!e) e = scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut); }
-                else         { if (!e) e = scdev_ifft_ola(pl, &h->b, kout, h->streamOut); }
-                if (!e && !zc) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut);
-                if (tr) scdev_event_record(h->trEv[4], h->streamOut);
-                if (!e) e = scdev_event_record(h->evDone, h->streamOut);
-                /* latency regime: K3 runs alone, the next tail pass starts behind it */
-                if (!e) e = scdev_stream_wait_event(h->stream, h->evDone);
-                if (!e) e = scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream);
+            if (!h->graphExec) {
+                e = scdev_graph_begin(h->stream);
+                if (!e) e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
+                if (!e) e = enqueue_block(h, h->d_in, h->d_out);
+                if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
+                int e2 = scdev_graph_end(h->stream, &h->graphExec);
+                if (!e) e = e2;
+                if (e) { h->graphExec = NULL; h->useGraph = 0; h_fail(h, SAFCONV_ERR_CUDA, "graph capture", e); return; }
+                h->graphIn = (void*)src; h->graphOut = (void*)dst;
             }
-            if (!e) e = scdev_event_record(h->evTail, h->stream);
-            if (!e) { h->tailReady = 1; h->count = c + 1; e = scdev_event_sync(h->evDone); }
-            if (tr && !e) {
-                /* trEv[2] = end of the tail pass enqueued by the PREVIOUS call (recorded there as trEv[5], swapped below) */
-                float gap = 0.f, head = 0.f, k3wait = 0.f, k3 = 0.f;
-                if (h->trEv[2] && h->count > 3) {
-                    scdev_event_elapsed_ms(h->trEv[2], h->trEv[0], &gap);
-                    scdev_event_elapsed_ms(h->trEv[0], h->trEv[1], &head);
-                    scdev_event_elapsed_ms(h->trEv[1], h->trEv[3], &k3wait);
-                    scdev_event_elapsed_ms(h->trEv[3], h->trEv[4], &k3);
-                    fprintf(stderr, "[safconv trace] block %u: prev tail end -> head start %.1f us, head %.1f us, head end -> K3 start %.1f us, K3 %.1f us\n",
-                            c, 1e3f * gap, 1e3f * head, 1e3f * k3wait, 1e3f * k3);
+            e = scdev_graph_launch(h->graphExec, h->stream);
+        } else {
+            /* copy-engine path: H2D -> kernels -> D2H */
+            e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
+            if (!e) {
+                if (h->pl.kind == SC_KIND_TV) {
+                    e = scdev_tv_fused(&h->pl, &h->b, h->d_in, h->d_out, irIdx, h->tvLast, h->tvLast2, h->stream);
+                    h->tvLast2 = h->tvLast;                      /* reference .c:618-619 */
+                    h->tvLast  = irIdx;
+                } else {
+                    e = enqueue_block(h, h->d_in, h->d_out);
                 }
             }
-            if (h->trace && !e) {                           /* end of the tail pass just enqueued: read by the next call */
-                void* t = h->trEv[2]; h->trEv[2] = h->trEv[5]; h->trEv[5] = t;
-                scdev_event_record(h->trEv[2], h->stream);
-            }
-            if (e) { h->tailReady = 0; h_fail(h, SAFCONV_ERR_CUDA, "apply (look-ahead)", e); return; }
-            if (!direct) memcpy(out, h->h_out, h->outBytes);
-            return;
+            if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
         }
-        if (h->pl.kind == SC_KIND_MATRIX && !h->timingCap && h->smallFused &&
-            h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
-            /* single-partition (or look-ahead disabled) matrix convolver, blocks of up to 1 MB: K1 reads and K3 writes the
-             * page-locked host buffers directly -- three launches and one synchronisation, no copy-engine round trips */
-            e = scdev_input_fft(&h->pl, &h->b, src, 1, h->stream);
-            if (!e) e = scdev_mac(&h->pl, &h->b, 0, 1, h->stream);
-            if (!e) e = scdev_ifft_ola(&h->pl, &h->b, dst, h->stream);
-            if (!e) e = scdev_stream_sync(h->stream);
-            if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (zero-copy)", e); return; }
-            h->count++;
-            if (!direct) memcpy(out, h->h_out, h->outBytes);
-            return;
-        }
-        if (h->pl.kind == SC_KIND_TV && h->smallFused && h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20)) {
-            /* TVConv latency path: the fused kernel reads / writes the page-locked host buffers directly */
-            e = scdev_tv_fused(&h->pl, &h->b, src, dst, irIdx, h->tvLast, h->tvLast2, h->stream);
-            h->tvLast2 = h->tvLast;                          /* reference .c:618-619 */
-            h->tvLast  = irIdx;
-            if (!e) e = scdev_stream_sync(h->stream);
-            if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (TVConv, zero-copy)", e); return; }
-            h->count++;
-            if (!direct) memcpy(out, h->h_out, h->outBytes);
-            return;
-        }
-        e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
-        if (!e) {
-            if (h->pl.kind == SC_KIND_TV) {
-                e = scdev_tv_fused(&h->pl, &h->b, h->d_in, h->d_out, irIdx, h->tvLast, h->tvLast2, h->stream);
-                h->tvLast2 = h->tvLast;                      /* reference .c:618-619 */
-                h->tvLast  = irIdx;
-            } else {
-                e = enqueue_block(h, h->d_in, h->d_out);
-            }
-        }
-        if (!e) e = scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream);
+        if (!e) e = scdev_stream_sync(h->stream);
+        if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
+        h->count++;
     }
-    if (!e) e = scdev_stream_sync(h->stream);
-    if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
-    h->count++;
     if (!direct) memcpy(out, h->h_out, h->outBytes);
 }
 
