@@ -249,6 +249,32 @@ int safconv_debug_plan(int kind, int hop, int len, int nIn, int nOutLocal, int s
     return 0;
 }
 
+/* host-logic unit tests: the split tables of a MAC pass over partitions [pLo, pLo + nP) exactly as make_pass() builds
+ * them for the look-ahead apply (tail pass (1, P-1), head pass (0, 1)).  Returns the number of partial slots or < 0. */
+int safconv_debug_pass_tables(int hop, int len, int nIn, int nOutLocal, int smCount, int pLo, int nP,
+                              long long* totalStages, int* grid, int* ctaBase, int* grpStart, int* grpList, int cap)
+{
+    scdev_plan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.kind = SC_KIND_MATRIX; pl.nIn = nIn; pl.nOutLocal = nOutLocal;
+    plan_fft(&pl, hop, len);
+    plan_mac(&pl, smCount);
+    if (pLo < 0 || nP < 1 || pLo + nP > pl.P) return -2;
+    const long long T = (long long)pl.nGroups * nP * pl.SPU;
+    const int G = (T < smCount) ? (int)T : smCount;
+    int *a = NULL, *b = NULL, *c = NULL;
+    const int slots = build_split_tables_for(T, (long long)nP * pl.SPU, G, pl.nGroups, &a, &b, &c);
+    if (slots < 0) return -1;
+    if (slots <= cap && pl.nGroups + 1 <= cap && G + 1 <= cap) {
+        memcpy(ctaBase, a, sizeof(int) * (size_t)(G + 1));
+        memcpy(grpStart, b, sizeof(int) * (size_t)(pl.nGroups + 1));
+        memcpy(grpList, c, sizeof(int) * (size_t)slots);
+    }
+    free(a); free(b); free(c);
+    *totalStages = T; *grid = G;
+    return slots;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /*  create / destroy                                                                            */
 /* ------------------------------------------------------------------------------------------ */

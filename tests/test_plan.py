@@ -86,3 +86,59 @@ def test_mac_tiling_and_split_tables(saf, hop, L, nIn, nOut, sms):
     # the slots of a group are consecutive: K3 sums slots grpStart[g] .. grpStart[g+1]-1 in ascending order
     assert grpList.tolist() == list(range(pl.nSlots))
     assert pl.maxBatch >= 1 and pl.RS == pl.P + pl.maxBatch
+
+
+@pytest.mark.parametrize("hop,L,nIn,nOut", [(1024, 96000, 64, 64), (256, 3000, 6, 10), (128, 2000, 3, 70), (512, 1024, 33, 17),
+                                           (64, 128, 2, 3)])
+@pytest.mark.parametrize("which", ["tail", "head"])
+def test_lookahead_pass_tables(saf, hop, L, nIn, nOut, which):
+    """Split tables of the look-ahead passes (tail = partitions 1..P-1, head = partition 0): emulate the MAC kernel's
+    walk over a pass -- stage -> (group, partition, stage in unit) with the filter pointer skipping the partitions
+    outside the pass -- and check that every (group, partition, stage) of the pass is streamed exactly once, that the
+    filter offsets are the ones of the full layout, and that the gather table lists each group's slots consecutively."""
+    lib = saf.lib()
+    pl, *_ = plan(saf, hop, L, nIn, nOut)
+    P, SPU, nG = pl.P, pl.SPU, pl.nGroups
+    pLo, nP = (1, P - 1) if which == "tail" else (0, 1)
+    cap = 1 << 16
+    cta = (C.c_int * cap)(); gs = (C.c_int * cap)(); gl = (C.c_int * cap)()
+    T = C.c_longlong(); G = C.c_int()
+    slots = lib.safconv_debug_pass_tables(hop, L, nIn, nOut, 148, pLo, nP, C.byref(T), C.byref(G), cta, gs, gl, cap)
+    assert slots > 0
+    T, G = T.value, G.value
+    assert T == nG * nP * SPU and 1 <= G <= min(148, T)
+    ctaBase = np.array(cta[:G + 1]); grpStart = np.array(gs[:nG + 1]); grpList = np.array(gl[:slots])
+    unit_elems = nIn * pl.OTsz * 32                      # float2 elements of one (group, partition) unit of H
+    seen = set()
+    slot_group = {}
+    for c in range(G):
+        s0, s1 = T * c // G, T * (c + 1) // G
+        unit0 = s0 // SPU
+        sidx, grp0 = s0 - unit0 * SPU, unit0 // nP
+        p = pLo + (unit0 - grp0 * nP)
+        g = grp0
+        srcH = (grp0 * P + p) * unit_elems + sidx * pl.SNI * pl.OTsz * 32       # kernel: srcH0
+        slot = ctaBase[c]
+        for _ in range(s1 - s0):
+            ni0 = sidx * pl.SNI
+            cnt = min(pl.SNI, nIn - ni0)
+            assert srcH == (g * P + p) * unit_elems + ni0 * pl.OTsz * 32         # offset in the full [group][P][nIn][OTsz][32] layout
+            assert (g, p, sidx) not in seen
+            seen.add((g, p, sidx))
+            slot_group.setdefault(slot, g)
+            assert slot_group[slot] == g
+            srcH += cnt * pl.OTsz * 32
+            sidx += 1
+            if sidx == SPU:
+                sidx = 0
+                p += 1
+                if p == pLo + nP:
+                    p = pLo
+                    srcH += (P - nP) * unit_elems        # skip the partitions outside the pass
+                    g += 1
+                    slot += 1                            # kernel: dst advances at the end of a group
+    assert len(seen) == nG * nP * SPU
+    assert grpStart[0] == 0 and grpStart[-1] == slots and grpList.tolist() == list(range(slots))
+    for g in range(nG):
+        for sl in range(grpStart[g], grpStart[g + 1]):
+            assert slot_group.get(sl, g) == g
