@@ -17,11 +17,20 @@
  *                           output channel (the reference does P*nIn of them, .c:220-222),
  *                           1/N, overlap-add, tail save                        (.c:230-233)
  *   multi_fused_kernel      multiConv: K1+K2+K3 in one launch, one CTA per channel
+ *   multi_fft_w_kernel /    multiConv, batches of device-resident blocks on the warp-level register FFT
+ *   multi_mac_ifft_w_kernel (safconv_wfft.cuh): register sliding window over the delay line per bin
+ *   small_fused_kernel      small matrix problems: K1+K2+K3 in one launch on mapped host buffers
  *   tv_fused_kernel         TVConv: one CTA per output channel, up to three IR sets + cross-fade
+ *   rfft_forward/backward   the FFT pair on its own (saf_rfft conventions), parity-test entry points
  *
- * The real FFT of size N is an M = N/2 point complex FFT (radix-4/2 decimation-in-frequency
- * passes in shared memory, the last five radix-2 stages as warp-shuffle butterflies) plus a
- * split pass; spectra are kept PACKED (M complex values, bin 0 = (DC, Nyquist)).
+ * K2 runs over a PASS = partitions [pLo, pLo+nP) of every group: the full pass, and for the look-ahead
+ * apply of the host layer a tail pass (1, P-1) that is enqueued ahead of the next block and a head pass
+ * (0, 1); K3 can also add the newest partition itself (headH).
+ *
+ * The real FFT of size N is an M = N/2 point complex FFT (safconv_fft.cuh: radix-4/2 decimation-in-
+ * frequency passes in shared memory with the last five radix-2 stages as warp-shuffle butterflies, or
+ * register radix-16 passes for batches) plus a split pass; spectra are kept PACKED (M complex values,
+ * bin 0 = (DC, Nyquist)).
  *
  * No CPU fallback exists: every entry point returns a CUDA error code if the device path fails.
  */
