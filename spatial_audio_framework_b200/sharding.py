@@ -75,9 +75,10 @@ class ShardedStep:
         self.latency_ms = []
         self.host_api_name = ("saf_matrixConv_apply" if kind == "matrix" else "saf_multiConv_apply") + \
             " (one synchronous host-pointer call per block)"
+        self.sub_compute = compute_fn is None            # sub-batches of a step can be computed one by one
         if compute_fn is None:
-            def compute_fn(x, y, _c=conv, _B=B):
-                _c.apply_device(x.data_ptr(), y.data_ptr(), _B)
+            def compute_fn(x, y, _c=conv):
+                _c.apply_device(x.data_ptr(), y.data_ptr(), int(x.shape[0]))
         self.compute_fn = compute_fn
         f32 = torch.float32
         nbuf = 2 if world > 1 else 1
@@ -93,6 +94,17 @@ class ShardedStep:
             self.ev_c = [torch.cuda.Event() for _ in range(nbuf)] if self.cuda else None
             self.ev_g = [torch.cuda.Event() for _ in range(nbuf)] if self.cuda else None
             self.pending_bcast = False
+            # host-buffer steps: the B blocks of a step travel as S sub-batches so that the H2D copy / broadcast of
+            # sub-batch i+1 and the all-gather / D2H copy of sub-batch i-1 overlap the convolution of sub-batch i
+            import os
+            S = int(os.environ.get("SAFCONV_SHARD_SUBBATCHES", "4"))
+            self.S = S if (self.cuda and self.sub_compute and self.equal and S > 1 and B % S == 0) else 1
+            if self.S > 1:
+                bs = B // self.S
+                self.h2d = torch.cuda.Stream(device=device)
+                self.d2h = torch.cuda.Stream(device=device)
+                self.y_sub = [torch.empty((bs * n_out * hop,), dtype=f32, device=device) for _ in range(self.S)]
+                self.ev_sub = [[torch.cuda.Event() for _ in range(self.S)] for _ in range(4)]   # h2d, bcast, compute, gather
 
     # ------------------------------------------------------------------ single-GPU paths
     def load_input(self, x_host):
@@ -195,6 +207,10 @@ class ShardedStep:
         cs = self.stream
         self.pending_bcast = False                          # host steps are not pipelined across steps
         buf = self.t % 2
+        if self.cuda and self.S > 1:
+            self._step_host_pipelined(x_host, y_host, buf)
+            self.t += 1
+            return
         if self.cuda:
             with torch.cuda.stream(cs):
                 if self.rank == 0:
@@ -215,6 +231,56 @@ class ShardedStep:
             if self.rank == 0:
                 y_host.copy_(self.last_output_from(buf))
         self.t += 1
+
+    def _step_host_pipelined(self, x_host, y_host, buf):
+        """One host step as S sub-batches over four streams (rank 0: H2D and D2H; all ranks: NCCL on `comm`, the
+        convolution on the compute stream).  Collectives are issued in the same order on every rank:
+        bcast(0), bcast(1), gather(0), bcast(2), gather(1), ...  Synchronous: y_host is complete on return."""
+        torch, dist = self.torch, self.dist
+        cs, comm, S = self.stream, self.comm, self.S
+        bs = self.B // S
+        ev_h, ev_b, ev_c, ev_g = self.ev_sub
+        x, y = self.x[buf], self.y[buf]
+        # everything queued earlier on the compute stream (e.g. a previous step) comes first
+        for st in (self.h2d, comm, self.d2h):
+            st.wait_stream(cs)
+
+        def bcast(i):
+            if self.rank == 0:
+                with torch.cuda.stream(self.h2d):
+                    x[i * bs:(i + 1) * bs].copy_(x_host[i * bs:(i + 1) * bs], non_blocking=True)
+                    ev_h[i].record(self.h2d)
+            with torch.cuda.stream(comm):
+                if self.rank == 0:
+                    comm.wait_event(ev_h[i])
+                dist.broadcast(x[i * bs:(i + 1) * bs], src=0)
+                ev_b[i].record(comm)
+
+        def gather(i):
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_c[i])
+                dist.all_gather_into_tensor(self.y_sub[i], y[i * bs:(i + 1) * bs].reshape(-1))
+                ev_g[i].record(comm)
+            if self.rank == 0:
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(ev_g[i])
+                    out = gathered_to_channel_major({"flat": self.y_sub[i], "B": bs, "hop": self.hop}, self.n_out, self.world)
+                    y_host[i * bs:(i + 1) * bs].copy_(out, non_blocking=True)
+
+        bcast(0)
+        for i in range(S):
+            if i + 1 < S:
+                bcast(i + 1)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev_b[i])
+                if self.count > 0:
+                    self.compute_fn(x[i * bs:(i + 1) * bs], y[i * bs:(i + 1) * bs])
+                ev_c[i].record(cs)
+            gather(i)
+        cs.wait_stream(comm)
+        if self.rank == 0:
+            self.d2h.synchronize()
+        cs.synchronize()
 
     def last_output_from(self, buf):
         return gathered_to_channel_major({"flat": self.y_all[buf], "B": self.B, "hop": self.hop}, self.n_out, self.world)
