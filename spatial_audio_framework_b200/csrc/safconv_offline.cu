@@ -88,6 +88,15 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b)
 {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
+/* the same split for a (re, im) pair with packed conversions: one cvt.rn.f16x2.f32 per part */
+__device__ __forceinline__ void f16_split2(float2 x, uint32_t& hi, uint32_t& lo)
+{
+    const __half2 h = __floats2half2_rn(x.x, x.y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 /* largest |v[i]| -> atomicMax on the float bit pattern (non-negative floats order like unsigned ints) */
 __global__ void offline_absmax_kernel(const float* __restrict__ v, size_t n, float* out)
@@ -939,9 +948,7 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftAr
             const float2 tt = cmulf(w, O);
             float2 X = make_float2((E.x + tt.x) * sc, (E.y + tt.y) * sc);
             if (k == 0) X = make_float2((A.x + A.y) * (2.f * sc), (A.x - A.y) * (2.f * sc));   /* packed (DC, Nyquist) */
-            __half h0, l0, h1, l1;
-            f16_split(X.x, h0, l0);  f16_split(X.y, h1, l1);
-            hi[j] = pack_h2(h0, h1);  lo[j] = pack_h2(l0, l1);
+            f16_split2(X, hi[j], lo[j]);
         }
         const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f) * 16;
         *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
