@@ -72,6 +72,33 @@ def test_no_cpu_fallback_without_device(saf):
         saf.MultiConv(64, np.zeros((1, 64), np.float32))
 
 
+def test_helpers_fail_loudly_without_device(saf):
+    """fftconv / fftfilt / rfft have no CPU path either: error code + message, output untouched; bad arguments are
+    rejected before any device work."""
+    import torch
+    import spatial_audio_framework_b200 as pkg
+    lib = saf.lib()
+    x = np.ones((2, 100), np.float32); h = np.ones((2, 9), np.float32)
+    fp = C.POINTER(C.c_float)
+    lib.safconv_fftconv.restype = C.c_int
+    lib.safconv_rfft_forward.restype = C.c_int
+    lib.safconv_last_error_string.restype = C.c_char_p
+    y = np.full((2, 108), 7.0, np.float32)
+    # invalid arguments
+    assert lib.safconv_fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), 0, 9, 2, y.ctypes.data_as(fp)) == 1
+    X = np.zeros((1, 49, 2), np.float32)
+    assert lib.safconv_rfft_forward(96, 1, x.ctypes.data_as(fp), X.ctypes.data_as(fp)) == 1      # not a power of two
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rc = lib.safconv_fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), 100, 9, 2, y.ctypes.data_as(fp))
+    assert rc != 0 and b"CUDA device" in lib.safconv_last_error_string(None)
+    assert np.all(y == 7.0)
+    with pytest.raises(RuntimeError):
+        pkg.fftconv(x, h)
+    with pytest.raises(RuntimeError):
+        pkg.rfft_forward(np.zeros((1, 64), np.float32))
+
+
 def test_product_does_not_reference_oracle():
     """The product sources must not import/link anything under oracle/."""
     pkg = ROOT / "spatial_audio_framework_b200"
