@@ -570,6 +570,62 @@ def test_c4_full_size_properties(saf):
     assert not np.any(mc.apply(np.zeros((nIn, hop), np.float32)))
 
 
+def test_c3_full_size_properties(saf):
+    """configs[2] at full size (256 channels, hop 512, 4096 taps): delayed-impulse filters give an exactly known
+    output; host API (one fused launch per block) and the batched device path (warp-FFT kernels)."""
+    import torch
+    hop, L, nCH, nblk = 512, 4096, 256, 24
+    rng = np.random.default_rng(31)
+    H = np.zeros((nCH, L), np.float32)
+    delays = rng.integers(0, L, size=nCH)
+    gains = rng.uniform(-1, 1, size=nCH).astype(np.float32)
+    H[np.arange(nCH), delays] = gains
+    x = rng.uniform(-1, 1, (nCH, hop * nblk)).astype(np.float32)
+    T = hop * nblk
+    exp = np.zeros((nCH, T), np.float64)
+    for c in range(nCH):
+        exp[c, delays[c]:] = gains[c] * x[c, :T - delays[c]].astype(np.float64)
+    mc = saf.MultiConv(hop, H)
+    ma, l2 = err_metrics(mc.run(x), exp)
+    assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
+    mc.reset_state()
+    d_in = torch.from_numpy(np.ascontiguousarray(x.reshape(nCH, nblk, hop).transpose(1, 0, 2))).cuda()
+    d_out = torch.zeros((nblk, nCH, hop), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    mc.apply_device(d_in.data_ptr(), d_out.data_ptr(), nblk)
+    mc.synchronize()
+    ma, l2 = err_metrics(d_out.cpu().numpy().transpose(1, 0, 2).reshape(nCH, T), exp)
+    assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
+
+
+def test_c5_full_channels_offline_properties(saf):
+    """configs[4] channel counts and filter length (121 x 64, 8192 taps, hop 1024) on 1.3 s of audio through the
+    offline tensor-core path: delayed-impulse filters -> exactly known mix of delayed inputs; linearity."""
+    hop, L, nIn, nOut, T = 1024, 8192, 121, 64, 60
+    rng = np.random.default_rng(41)
+    H = np.zeros((nOut, nIn, L), np.float32)
+    delays = rng.integers(0, L, size=(nOut, nIn))
+    gains = rng.uniform(-1, 1, size=(nOut, nIn)).astype(np.float32)
+    for no in range(nOut):
+        H[no, np.arange(nIn), delays[no]] = gains[no]
+    x = rng.uniform(-1, 1, (nIn, hop * T)).astype(np.float32)
+    n = hop * T
+    exp = np.zeros((nOut, n), np.float64)
+    for no in range(nOut):
+        for ni in range(nIn):
+            d = delays[no, ni]
+            exp[no, d:] += gains[no, ni] * x[ni, :n - d].astype(np.float64)
+    mc = saf.MatrixConv(hop, H)
+    y = mc.render_offline(x)
+    ma, l2 = err_metrics(y, exp)
+    assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
+    x2 = rng.uniform(-1, 1, x.shape).astype(np.float32)
+    y2 = mc.render_offline(x2)
+    y3 = mc.render_offline((0.5 * x + x2).astype(np.float32))
+    ma, l2 = err_metrics(y3, 0.5 * y.astype(np.float64) + y2)
+    assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
+
+
 @pytest.mark.parametrize("nCH,xl,hl", [(3, 1000, 129), (1, 5, 7), (2, 5000, 4096), (4, 300, 1), (6, 48000, 700)])
 def test_fftconv_fftfilt_vs_oracle(saf, orc, nCH, xl, hl):
     """safconv_fftconv / safconv_fftfilt (drop-in for saf_utility_fft.h:86-113, served by the multiConv engine)
