@@ -86,6 +86,100 @@ def filters_for(w, out_begin, out_count, seed=0x5AF0C0DE):
     return H
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def pct(a, q):
+    return float(np.percentile(a, q)) if len(a) else None
+
+
+def call_loop(fn, hdl, xin, yout, n, in_stride=0, out_stride=0, nbuf=1, period=None):
+    """n synchronous drop-in calls fn(hdl, in, out) on ctypes float pointers (buffer b % nbuf of a ring of blocks);
+    period != None paces the calls like an audio callback.  Returns (per-call ms list, total seconds)."""
+    import ctypes as C
+    fp = C.POINTER(C.c_float)
+    ins = [C.cast(xin + (b % nbuf) * in_stride, fp) for b in range(nbuf)]
+    outs = [C.cast(yout + (b % nbuf) * out_stride, fp) for b in range(nbuf)]
+    lat = []
+    pc = time.perf_counter
+    t_begin = pc()
+    t_next = t_begin + (period or 0.0)
+    for k in range(n):
+        if period:
+            while pc() < t_next:
+                pass
+            t_next += period
+        t0 = pc()
+        fn(hdl, ins[k % nbuf], outs[k % nbuf])
+        lat.append(1e3 * (pc() - t0))
+    return lat, pc() - t_begin
+
+
+def host_api_latency(conv, kind, x_host, y_host, nbuf, in_elems, out_elems, hop, blocks=2000, warm=100, paced_calls=200):
+    """p50 / p99 of the synchronous host-pointer call (>= 2000 blocks after 100 warm-up), with the caller's
+    buffers page-locked and pageable, and paced (GPU idle between calls)."""
+    lib, hdl = conv._lib, conv.handle
+    fn = lib.saf_matrixConv_apply if kind == "matrix" else lib.saf_multiConv_apply
+    out = {}
+    call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), warm, in_elems * 4, out_elems * 4, nbuf)
+    lat, dt = call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), blocks, in_elems * 4, out_elems * 4, nbuf)
+    out["blocks"] = blocks
+    out["warmup_blocks"] = warm
+    out["pinned"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "blocks_per_s": blocks / dt}
+    # pageable caller buffers (the reference's hosts pass malloc'd frames: matrixconv.c:137-149)
+    xp = np.array(x_host.numpy()[0:1]).reshape(-1).copy()
+    yp = np.empty(out_elems, np.float32)
+    call_loop(fn, hdl, xp.ctypes.data, yp.ctypes.data, warm)
+    lat, dt = call_loop(fn, hdl, xp.ctypes.data, yp.ctypes.data, blocks)
+    out["pageable"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "blocks_per_s": blocks / dt}
+    if paced_calls:
+        period = min(hop / 48000.0, 0.005)
+        lat, _ = call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), paced_calls + 20, in_elems * 4, out_elems * 4, nbuf, period)
+        lat = lat[20:]
+        out["paced"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "period_ms": 1e3 * period, "calls": paced_calls,
+                        "note": "real-time block period hop/48000 s, capped at 5 ms (the GPU is idle long before)"}
+    return out
+
+
+def parity_check(conv, w, B, dev, blocks=6):
+    """--check: the batched device path that `value` times (safconv_apply_device_blocks from a reset state) against the
+    oracle on output channel 0, same seeded input.  Only the first `blocks` blocks are compared (the CPU checker needs
+    ~0.2 s per block and output channel at C4)."""
+    import torch
+    import oracle as O
+    hop, nIn = w["hop"], w["nIn"]
+    rng = np.random.default_rng(4321)
+    x = rng.uniform(-1, 1, (B, nIn, hop)).astype(np.float32)
+    conv.synchronize()
+    conv.reset_state()
+    d_in = torch.from_numpy(x).to(dev)
+    d_out = torch.empty((B, conv.nOutLocal, hop), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    conv.apply_device(d_in.data_ptr(), d_out.data_ptr(), B)
+    conv.synchronize()
+    y = d_out[:blocks, 0].cpu().numpy().reshape(-1)
+    H0 = filters_for(w, 0, 1)
+    if w["kind"] == "matrix":
+        ref = O.OracleMatrixConv(hop, H0, 1)
+        r = np.concatenate([ref.apply(x[b])[0] for b in range(blocks)])
+    else:
+        ref = O.OracleMultiConv(hop, H0, 1)
+        r = np.concatenate([ref.apply(np.ascontiguousarray(x[b, 0:1]))[0] for b in range(blocks)])
+    fs = float(np.abs(r).max())
+    conv.reset_state()
+    return {"parity_rel_l2": float(np.linalg.norm(y - r) / np.linalg.norm(r)),
+            "parity_max_abs_fs": float(np.abs(y - r).max() / fs),
+            "what": f"output channel 0, first {blocks} of {B} blocks of one batched step from a reset state vs the CPU oracle (same input)",
+            "tolerance": "rel L2 <= 1e-6, max abs <= 1e-5 of full scale"}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi, during the timed region)
 # ------------------------------------------------------------------------------------------------
@@ -217,9 +311,6 @@ def run_reference_arm(args, w):
 # ------------------------------------------------------------------------------------------------
 def run_offline_arm(args, w):
     import torch
-    import spatial_audio_framework_b200 as saf
-    from spatial_audio_framework_b200 import sharding
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,6 +322,19 @@ def run_offline_arm(args, w):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_offline(args, w, world, rank, local, dist)
+    if line is not None:
+        emit(line)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_offline(args, w, world, rank, local, dist):
+    """One offline workload (configs[4]) on this rank; returns the JSON line on rank 0, None elsewhere."""
+    import torch
+    import spatial_audio_framework_b200 as saf
+    from spatial_audio_framework_b200 import sharding
     dev = torch.device("cuda", local)
     hop, nIn, nOut = w["hop"], w["nIn"], w["nOut"]
     T = int(np.ceil(w["seconds"] * 48000.0 / hop))
@@ -332,14 +436,12 @@ def run_offline_arm(args, w):
                 "avg_launch_ms": gemm_ms, "launches_timed": args.steps, "rank": 0,
                 "kernel_ms_per_render": {"forward_fft": float(kms[0]), "gemm": gemm_ms, "ifft_ola": float(kms[2])}}
     if rank != 0:
-        if dist:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
     cpu = None
     if world == 1 and not args.no_cpu:
         c = cpu_reference_run(w, steps=args.cpu_steps, warmup=1)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    conv.destroy()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -352,15 +454,113 @@ def run_offline_arm(args, w):
         "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if f16 else 5) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "realtime_factor_48k": (T * hop * args.steps / (ms_total * 1e-3)) / 48000.0,
     }
-    emit(line)
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def make_conv(saf, w, H, devices=None, device=None, shard=None):
+    if w["kind"] == "matrix":
+        if shard is not None:
+            return saf.MatrixConv.from_shard(w["hop"], H, w["nOut"], shard, device=device)
+        return saf.MatrixConv(w["hop"], H, 1, device=device, devices=devices)
+    return saf.MultiConv(w["hop"], H, 1, device=device, devices=devices)
+
+
+def e2e_multi_gpu(args, w, world, x_host, y_host, B):
+    """N > 1, rank 0: the SAME per-block synchronous drop-in call as at N = 1, on ONE handle that spans all N GPUs
+    (safconv_matrixConv_create_multi: single host process, a worker thread per device, no torch in the data path)."""
+    import spatial_audio_framework_b200 as saf
+    hop, nIn, nOut = w["hop"], w["nIn"], w["nOut"]
+    t0 = time.perf_counter()
+    H = filters_for(w, 0, nOut)
+    conv = make_conv(saf, w, H, devices=list(range(world)))
+    del H
+    create_s = time.perf_counter() - t0
+    lib, hdl = conv._lib, conv.handle
+    fn = lib.saf_matrixConv_apply if w["kind"] == "matrix" else lib.saf_multiConv_apply
+    xin, yout = x_host.data_ptr(), y_host.data_ptr()
+    sx, sy = nIn * hop * 4, nOut * hop * 4
+    blocks = max(args.e2e_blocks, B)
+    res = {}
+    for name, tr in (("host", 0), ("nccl", 1)):
+        try:
+            conv.set_option("transport", tr)
+        except Exception as ex:                       # NCCL missing: say so, keep the other transport
+            res[name] = {"unavailable": str(ex)}
+            continue
+        conv.set_option("worker_spin_us", 200)
+        call_loop(fn, hdl, xin, yout, 100, sx, sy, B)
+        lat, dt = call_loop(fn, hdl, xin, yout, blocks, sx, sy, B)
+        if lib.safconv_last_error(hdl):
+            raise SystemExit("bench.py: multi-GPU apply failed: " + lib.safconv_last_error_string(hdl).decode())
+        r = {"value": float(nOut) * hop * blocks / dt, "blocks": blocks, "warmup_blocks": 100,
+             "block_latency_ms_p50": pct(lat, 50), "block_latency_ms_p99": pct(lat, 99)}
+        period = min(hop / 48000.0, 0.005)
+        pl, _ = call_loop(fn, hdl, xin, yout, 220, sx, sy, B, period)
+        r["block_latency_paced_ms_p50"], r["block_latency_paced_ms_p99"] = pct(pl[20:], 50), pct(pl[20:], 99)
+        conv.set_option("worker_spin_us", int(2e6 * period))          # workers keep spinning through the period
+        pl, _ = call_loop(fn, hdl, xin, yout, 220, sx, sy, B, period)
+        r["block_latency_paced_spinning_workers_ms_p50"], r["block_latency_paced_spinning_workers_ms_p99"] = pct(pl[20:], 50), pct(pl[20:], 99)
+        r["paced_period_ms"] = 1e3 * period
+        res[name] = r
+    shards = [conv.shard_info(i) for i in range(len(conv.multi_devices()))]
+    out = {"devices": conv.multi_devices(), "create_seconds": create_s,
+           "outputs_per_device": [int(i.nOutLocal) for i in shards], "transports": res}
+    conv.destroy()
+    return out
+
+
+def latency_config(name, args, dev):
+    """secondary block: one BASELINE.json config through the host-pointer drop-in call (p50 / p99) + device-resident rate"""
+    import torch
+    import spatial_audio_framework_b200 as saf
+    w = WORKLOADS[name]
+    hop, nIn, nOut = w["hop"], w["nIn"], w["nOut"]
+    H = filters_for(w, 0, nOut)
+    conv = make_conv(saf, w, H, device=dev.index)
+    info = conv.info()
+    nbuf = 8
+    g = torch.Generator(device="cpu").manual_seed(77)
+    x_host = (torch.rand((nbuf, nIn, hop), generator=g) * 2 - 1).pin_memory()
+    y_host = torch.empty((nbuf, nOut, hop), dtype=torch.float32).pin_memory()
+    lat = host_api_latency(conv, w["kind"], x_host, y_host, nbuf, nIn * hop, nOut * hop, hop,
+                           blocks=args.lat_blocks, warm=100)
+    # device-resident batched rate
+    B = 32
+    d_in = (torch.rand((B, nIn, hop), generator=g) * 2 - 1).to(dev)
+    d_out = torch.empty((B, nOut, hop), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    conv.set_stream(stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        conv.apply_device(d_in.data_ptr(), d_out.data_ptr(), B)
+    steps = 20
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(steps):
+            conv.apply_device(d_in.data_ptr(), d_out.data_ptr(), B)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (steps * B)
+    conv.set_stream(None)
+    chk = parity_check(conv, w, B, dev, blocks=B) if args.check else None
+    cpu = None
+    if not args.no_cpu:
+        c = cpu_reference_run(w, steps=3, warmup=1, threads=1, ch_per_thread=nOut)
+        cpu = {"value": c["value"], "unit": UNIT, "cores": 1, "kind": c["kind"], "ms_per_block": 1e3 * hop * nOut / c["value"],
+               "sample": "the whole problem on ONE core, as the reference ships (single-threaded): " + c["sample"]}
+    conv.destroy()
+    small = info.bytesFilters <= (64 << 20)
+    return {"workload": w["desc"], "host_api": lat,
+            "device_resident": {"us_per_block": 1e3 * ms, "value": nOut * hop / (ms * 1e-3), "unit": UNIT, "blocks_per_step": B},
+            "bound": ("latency (launch + PCIe round trip); filters and delay line are L2-resident: an HBM fraction is not a roofline here"
+                      if small else "hbm"),
+            "alg_bytes_per_block": float(info.algBytesPerBlock), "filter_bytes": int(info.bytesFilters),
+            "parity": chk, "cpu_baseline": cpu}
+
+
 def run_own_arm(args, w):
     if w["kind"] == "offline":
         return run_offline_arm(args, w)
@@ -375,10 +575,12 @@ def run_own_arm(args, w):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
+    idle = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idle = dist.new_group(backend="gloo")           # ranks that have nothing to do wait here WITHOUT spinning
     dev = torch.device("cuda", local)
 
     hop, nIn, nOut, B = w["hop"], w["nIn"], w["nOut"], args.blocks
@@ -395,7 +597,6 @@ def run_own_arm(args, w):
     info = conv.info()
     stream = torch.cuda.Stream(device=dev)
     conv.set_stream(stream.cuda_stream)
-    nInLocal = nIn if w["kind"] == "matrix" else oc
 
     g = torch.Generator(device="cpu").manual_seed(1234)
     x_host = (torch.rand((B, nIn, hop), generator=g) * 2 - 1).pin_memory()          # one step of input, pinned
@@ -403,10 +604,10 @@ def run_own_arm(args, w):
     engine = sharding.ShardedStep(conv, w["kind"], nIn, nOut, hop, B, world, rank, dev, stream, dist)
 
     # ---------------- device-resident timing (value) ----------------
-    engine.load_input(x_host)                      # inputs resident in HBM before the timed region
+    engine.load_input(x_host)                      # inputs (both double-buffer slots) resident in HBM before the timed region
     torch.cuda.synchronize()
     for _ in range(args.warmup):
-        engine.step_device()
+        engine.step_device(prefetch=True)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -418,7 +619,7 @@ def run_own_arm(args, w):
     with torch.cuda.stream(stream):
         e0.record()
         for _ in range(args.steps):
-            engine.step_device()
+            engine.step_device(prefetch=True)
         engine.drain()
         e1.record()
     torch.cuda.synchronize()
@@ -434,58 +635,62 @@ def run_own_arm(args, w):
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total_max = float(t.item())
+    per_rank = None
+    if dist:                                         # per-rank step time and MAC time: rules out imbalance between shards
+        mine = torch.tensor([ms_total / (args.steps * B), kms[1]], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_block": [float(a[0]) for a in allr], "mac_ms_per_block": [float(a[1]) for a in allr]}
+    ms_total = ms_total_max
     units = float(nOut) * hop * B * args.steps
     value = units / (ms_total * 1e-3)
 
+    # ---------------- parity of what was just timed ----------------
+    check = None
+    if args.check and rank == 0:
+        conv.set_stream(None)
+        check = parity_check(conv, w, B, dev)
+        conv.set_stream(stream.cuda_stream)
+
     # ---------------- end-to-end through the host-pointer API ----------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(2, args.warmup)):
-        engine.step_host(x_host, y_host)
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        engine.step_host(x_host, y_host)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = float(nOut) * hop * B * e2e_steps / float(t.item())
-    lat = engine.latency_ms
-    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(B * nIn * hop * 4),
-           "d2h_bytes_per_step": int(B * nOut * hop * 4), "steps": e2e_steps,
-           "api": engine.host_api_name}
-    if lat:
-        e2e["block_latency_ms_p50"] = float(np.percentile(lat, 50))
-        e2e["block_latency_ms_p99"] = float(np.percentile(lat, 99))
+    # the SAME contract at every N: one synchronous saf_matrixConv_apply(handle, in, out) per block on host buffers
+    e2e = None
     if world == 1:
-        # the same synchronous call issued at the real-time block rate (one block every hop/48000 s, like an audio
-        # callback): between two calls the GPU pre-computes every partition that does not need the next block
-        import ctypes as C
-        lib, hdl = conv._lib, conv.handle
-        fn = lib.saf_matrixConv_apply if w["kind"] == "matrix" else lib.saf_multiConv_apply
-        fp = C.POINTER(C.c_float)
-        xin, yout = C.cast(x_host.data_ptr(), fp), C.cast(y_host.data_ptr(), fp)
-        period = min(hop / 48000.0, 0.025)
-        paced = []
-        t_next = time.perf_counter() + period
-        for k in range(120):
-            while time.perf_counter() < t_next:
-                pass
-            t0 = time.perf_counter()
-            fn(hdl, xin, yout)
-            paced.append(1e3 * (time.perf_counter() - t0))
-            t_next += period
-        paced = paced[20:]
-        e2e["block_latency_paced_ms_p50"] = float(np.percentile(paced, 50))
-        e2e["block_latency_paced_ms_p99"] = float(np.percentile(paced, 99))
-        e2e["paced_period_ms"] = 1e3 * period
+        conv.set_stream(None)
+        lat = host_api_latency(conv, w["kind"], x_host, y_host, B, nIn * hop, nOut * hop, hop,
+                               blocks=max(args.e2e_blocks, B), warm=100, paced_calls=200)
+        conv.set_stream(stream.cuda_stream)
+        e2e = {"value": float(nOut) * hop * lat["pinned"]["blocks_per_s"], "unit": UNIT,
+               "h2d_bytes_per_step": int(B * nIn * hop * 4), "d2h_bytes_per_step": int(B * nOut * hop * 4),
+               "blocks": lat["blocks"], "warmup_blocks": lat["warmup_blocks"],
+               "api": ("saf_matrixConv_apply" if w["kind"] == "matrix" else "saf_multiConv_apply") +
+                      " (one synchronous host-pointer call per block, page-locked caller buffers)",
+               "block_latency_ms_p50": lat["pinned"]["p50_ms"], "block_latency_ms_p99": lat["pinned"]["p99_ms"],
+               "block_latency_paced_ms_p50": lat["paced"]["p50_ms"], "block_latency_paced_ms_p99": lat["paced"]["p99_ms"],
+               "paced_period_ms": lat["paced"]["period_ms"],
+               "pageable_caller_buffers": {"value": float(nOut) * hop * lat["pageable"]["blocks_per_s"],
+                                           "block_latency_ms_p50": lat["pageable"]["p50_ms"],
+                                           "block_latency_ms_p99": lat["pageable"]["p99_ms"],
+                                           "note": "malloc'd in / out frames like the reference's hosts (matrixconv.c:137-149): staged through the handle's pinned buffers"}}
+    else:
         torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            mg = e2e_multi_gpu(args, w, world, x_host, y_host, B)
+            best = max((k for k in mg["transports"] if "value" in mg["transports"][k]), key=lambda k: mg["transports"][k]["value"])
+            r = mg["transports"][best]
+            e2e = {"value": r["value"], "unit": UNIT,
+                   "h2d_bytes_per_step": int(B * nIn * hop * 4) * (world if best == "host" else 1),
+                   "d2h_bytes_per_step": int(B * nOut * hop * 4),
+                   "blocks": r["blocks"], "warmup_blocks": r["warmup_blocks"], "transport": best,
+                   "api": ("saf_matrixConv_apply" if w["kind"] == "matrix" else "saf_multiConv_apply") +
+                          f" on ONE handle over {world} GPUs (safconv_matrixConv_create_multi): one synchronous host-pointer call per block, "
+                          "single host process, one worker thread per device, page-locked caller buffers -- the same contract as N = 1",
+                   "block_latency_ms_p50": r["block_latency_ms_p50"], "block_latency_ms_p99": r["block_latency_ms_p99"],
+                   "block_latency_paced_ms_p50": r["block_latency_paced_ms_p50"], "block_latency_paced_ms_p99": r["block_latency_paced_ms_p99"],
+                   "paced_period_ms": r["paced_period_ms"], "multi_gpu_handle": mg}
+        dist.barrier(group=idle)                       # gloo: blocking socket wait, the other ranks do not burn host cores
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peak_gbs()
@@ -497,13 +702,16 @@ def run_own_arm(args, w):
     # DRAM traffic of the same kernel from the committed ncu --set full capture (per block; a launch covers blocks_per_launch)
     traffic, traffic_src = args.traffic, "--traffic" if args.traffic else None
     if traffic is None and world == 1:
-        try:
-            tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(args.workload)
-            if tj:
-                traffic = float(tj["dram_bytes_per_block"]) * blocks_per_launch
-                traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per block x blocks per launch)"
-        except Exception:
-            pass
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.loads((ROOT / "profiles" / tf).read_text()).get(args.workload)
+                if tj:
+                    traffic = float(tj["dram_bytes_per_block"]) * blocks_per_launch
+                    traffic_src = f"profiles/{tf} (ncu dram__bytes_read.sum + dram__bytes_write.sum per block x blocks per launch)"
+                    break
+            except Exception:
+                pass
+    small = w["kind"] == "multi" or info.bytesFilters <= (64 << 20)
     roofline = {"bound": "hbm", "kernel": "mac_kernel (K2 filter-streaming complex MAC)" if w["kind"] == "matrix" else "multi_mac_ifft_w_kernel (per-channel MAC with a register sliding window + warp-level inverse FFT, batched)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": mac_bytes, "avg_launch_ms": mac_ms,
@@ -512,10 +720,13 @@ def run_own_arm(args, w):
                                 "achieved_GBps": float(info.algBytesPerBlock) * B * args.steps / (ms_total * 1e-3) / 1e9},
                 "kernel_ms_per_block": {"input_fft": kms[0], "mac": kms[1], "ifft_ola": kms[2]}}
     roofline["whole_block"]["frac"] = roofline["whole_block"]["achieved_GBps"] / peak
-    # north_star quotes "roughly 8 TB/s": the same achieved rate against the nominal HBM3e figure
-    if w["kind"] == "multi" or info.bytesFilters <= (64 << 20):
-        roofline["note"] = ("the filter set fits in L2 (126 MB) and the batched blocks of a step re-use it from L2 / registers: "
-                            "DRAM traffic is far below the algorithmic bytes, so frac can exceed 1")
+    if per_rank:
+        roofline["per_rank"] = per_rank
+    if small:
+        roofline["bound"] = "l2"
+        roofline["note"] = ("the filter set fits in L2 (126 MB) and the batched blocks of a step re-use it from L2 / registers: DRAM "
+                            "traffic is far below the algorithmic bytes, so this is NOT an HBM roofline (frac can exceed 1); the bound "
+                            "is L2 bandwidth / launch latency -- see profiles/ for the L2 counters")
     else:
         roofline["note"] = ("peak is the measured COPY bandwidth (read + write); this kernel is a read-only stream, which runs "
                             "above a copy on HBM3e -- see frac_of_nominal and traffic (ncu DRAM bytes = 0.986 x algorithmic)")
@@ -524,7 +735,7 @@ def run_own_arm(args, w):
 
     if rank != 0:
         if dist:
-            dist.barrier()
+            dist.barrier(group=idle)
             dist.destroy_process_group()
         return
 
@@ -533,6 +744,32 @@ def run_own_arm(args, w):
     if world == 1 and not args.no_cpu:
         c = cpu_reference_run(w, steps=args.cpu_steps, warmup=1)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["host_threads"] = os.cpu_count()
+        cpu["cpu_model"] = cpu_model()
+        c1 = cpu_reference_run(w, steps=3, warmup=1, threads=1)
+        cpu["as_shipped_1_core"] = {"value": c1["value"], "unit": UNIT, "cores": 1,
+                                    "sample": "the reference convolver is single-threaded (SURVEY.md 8d): " + c1["sample"]}
+        cpu["note"] = ("GPU / CPU ratios depend on the HOST of the box (the all-threads figure scales with its core count); "
+                       "they say nothing about kernel quality -- the roofline fraction does")
+
+    # ---------------- secondary block: the other BASELINE.json configs, bounded ----------------
+    secondary = None
+    if world == 1 and args.secondary and args.workload == "C4":
+        conv.destroy()
+        del engine
+        torch.cuda.empty_cache()
+        secondary = {}
+        for name in ("C1", "C2", "C3", "UT"):
+            try:
+                secondary[name] = latency_config(name, args, dev)
+            except Exception as ex:
+                secondary[name] = {"failed": repr(ex)}
+        try:
+            a5 = argparse.Namespace(**vars(args))
+            a5.steps, a5.warmup, a5.e2e_steps, a5.cpu_steps = 5, 3, 2, 3
+            secondary["C5"] = measure_offline(a5, WORKLOADS["C5"], 1, 0, local, None)
+        except Exception as ex:
+            secondary["C5"] = {"failed": repr(ex)}
 
     # matrix: per launch group (= one step of B blocks): forward FFT, MAC, inverse FFT, overlap-add chain
     launches_per_step = (4 if B > 1 else 3) * ((B + int(info.maxBatch) - 1) // int(info.maxBatch)) if w["kind"] == "matrix" else B
@@ -542,7 +779,7 @@ def run_own_arm(args, w):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"],
                    "blocks_per_step": B, "partitions": int(info.numFilterBlocks),
-                   "sharding": f"output channels over {world} GPU(s), {oc} per GPU; input batch NCCL-broadcast, output shards all-gathered" if world > 1 else "single GPU",
+                   "sharding": f"output channels over {world} GPU(s), {oc} per GPU; value: one process per GPU, input batch NCCL-broadcast, output shards all-gathered; e2e: one multi-GPU handle in rank 0" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: %.0f MB of filter spectra streamed per block per GPU (L2 = 126 MB)" % (info.bytesFilters / 1e6),
                    "filters": "exponentially decaying uniform noise (-60 dB at the last tap), seeded per output channel",
                    "create_seconds_rank0": create_s},
@@ -551,9 +788,13 @@ def run_own_arm(args, w):
         "ms_per_block": ms_total / (args.steps * B),
         "realtime_factor_48k": (hop * B * args.steps / (ms_total * 1e-3)) / 48000.0,
     }
+    if check:
+        line["parity_rel_l2"] = check["parity_rel_l2"]
+        line["parity"] = check
+    if secondary:
+        line["secondary"] = secondary
     emit(line)
     if dist:
-        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -584,6 +825,11 @@ def main():
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--blocks", type=int, default=32, help="hop-sized blocks per step")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-blocks", type=int, default=2000, help="synchronous host-pointer calls timed for e2e / p50 (after 100 warm-up calls)")
+    ap.add_argument("--lat-blocks", type=int, default=2000, help="calls per latency measurement of the secondary configs")
+    ap.add_argument("--no-check", dest="check", action="store_false", help="skip the parity check of the timed path against the oracle")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the secondary block (C1/C2/C3/UT latency and the offline C5 render) of the default N=1 line")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic", type=float, default=None,

@@ -133,6 +133,36 @@ void safconv_multiConv_create_shard(void** const phMC, int hopSize, const float*
                                     int nCH, int chBegin, int chCount);
 
 /**
+ * ONE handle over several GPUs of a box (single host process; csrc/safconv_multi.c).  Output channels are independent
+ * in the reference (saf_utility_matrixConv.c:218-234; multiConv channels: .c:388-413), so device g of nDevices owns a
+ * contiguous range of output channels (its rows of the filter spectra, its overlap tails and a replica of the
+ * frequency-domain delay line); no partial sums cross GPUs.  The handle is used with the UNCHANGED drop-in calls
+ * saf_matrixConv_apply / saf_matrixConv_destroy (saf_multiConv_apply / _destroy): host pointers, one block per
+ * call, synchronous -- the reference's contract (saf_utility_matrixConv.c:209-235).  A persistent worker thread per
+ * device drives that device's shard (look-ahead apply included).  Exchange per block, option "transport":
+ *   0 (default)  every device reads the page-locked input block and writes its rows of the page-locked output block
+ *                directly over its own PCIe link (pageable caller buffers are staged once): no inter-GPU traffic
+ *   1            device 0 uploads the block, ncclBroadcast over NVLink, ncclSend/ncclRecv gather of the output shards
+ *                into a channel-major buffer on device 0, one download -- on a per-device side stream.  NCCL
+ *                (libnccl.so.2) is loaded with dlopen when this transport is first selected.
+ * Further options of a multi-GPU handle: "worker_spin_us" (how long an idle worker spins before it sleeps on a
+ * condition variable; default 200), "detect_pinned"; any other option is forwarded to every shard.
+ * Environment: SAFCONV_DEVICES="0,1,2,3" | "all" makes the plain saf_matrixConv_create / saf_multiConv_create build
+ * such a handle (no source change in the SAF host at all); SAFCONV_MULTI_TRANSPORT, SAFCONV_MULTI_SPIN_US set the defaults.
+ * On failure *phMC = NULL and safconv_last_error_string(NULL) says why.  Works with safconv_last_error[_string],
+ * safconv_get_info (totals over all devices), safconv_set_option, safconv_reset_state, safconv_synchronize.
+ */
+void safconv_matrixConv_create_multi(void** const phMC, int hopSize, const float* H, int length_h, int nCHin, int nCHout,
+                                     const int* devices, int nDevices);
+/** As above for saf_multiConv (H FLAT nCH x length_h): channels are sharded, nothing is replicated. */
+void safconv_multiConv_create_multi(void** const phMC, int hopSize, const float* H, int length_h, int nCH,
+                                    const int* devices, int nDevices);
+/** Devices of a multi-GPU handle: fills devices[0..min(cap, n)) and returns n (0 if h is not such a handle). */
+int   safconv_multi_get_devices(void* h, int* devices, int cap);
+/** The single-device handle that serves device i of a multi-GPU handle (introspection: safconv_get_info etc.). */
+void* safconv_multi_get_shard(void* h, int i);
+
+/**
  * Device-pointer apply: d_in (nCHin x hop) and d_out (nOutLocal x hop) are device
  * pointers on the handle's device.  Enqueues on the handle's stream and returns
  * without synchronising.  Works for matrixConv and multiConv handles.

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "saf_TVConv_create", "saf_TVConv_destroy", "saf_TVConv_apply",
     "safconv_last_error", "safconv_last_error_string", "safconv_version", "safconv_set_device",
     "safconv_matrixConv_create_shard", "safconv_matrixConv_create_from_shard", "safconv_multiConv_create_shard",
+    "safconv_matrixConv_create_multi", "safconv_multiConv_create_multi", "safconv_multi_get_devices", "safconv_multi_get_shard",
     "safconv_apply_device", "safconv_apply_device_blocks",
     "safconv_set_stream", "safconv_get_stream", "safconv_synchronize", "safconv_reset_state",
     "safconv_get_info", "safconv_enable_kernel_timing", "safconv_get_kernel_times", "safconv_get_kernel_totals",
@@ -96,6 +97,14 @@ def lib():
     L.safconv_matrixConv_create_from_shard.restype = None
     L.safconv_multiConv_create_shard.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.safconv_multiConv_create_shard.restype = None
+    _ip = C.POINTER(C.c_int)
+    L.safconv_matrixConv_create_multi.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _ip, C.c_int]
+    L.safconv_matrixConv_create_multi.restype = None
+    L.safconv_multiConv_create_multi.argtypes = [_vpp, C.c_int, _f32p, C.c_int, C.c_int, _ip, C.c_int]
+    L.safconv_multiConv_create_multi.restype = None
+    L.safconv_multi_get_devices.argtypes = [C.c_void_p, _ip, C.c_int]
+    L.safconv_multi_get_shard.argtypes = [C.c_void_p, C.c_int]
+    L.safconv_multi_get_shard.restype = C.c_void_p
     L.safconv_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.safconv_apply_device_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.safconv_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -169,6 +178,20 @@ class _Base:
             raise SafConvError("safconv_get_info failed")
         return i
 
+    def multi_devices(self):
+        """Devices of a multi-GPU handle ([] for a single-device handle)."""
+        buf = (C.c_int * 16)()
+        n = self._lib.safconv_multi_get_devices(self._h, buf, 16)
+        return [buf[i] for i in range(n)]
+
+    def shard_info(self, i: int) -> SafConvInfo:
+        """safconv_get_info of device i's shard of a multi-GPU handle."""
+        sh = self._lib.safconv_multi_get_shard(self._h, int(i))
+        info = SafConvInfo()
+        if not sh or self._lib.safconv_get_info(C.c_void_p(sh), C.byref(info)):
+            raise SafConvError("not a multi-GPU handle / no such shard")
+        return info
+
     def set_stream(self, cuda_stream_ptr: int | None):
         self._lib.safconv_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0))
 
@@ -230,14 +253,20 @@ class MatrixConv(_Base):
     _destroy_name = "saf_matrixConv_destroy"
 
     def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None,
-                 _from_shard=None):
+                 _from_shard=None, devices=None):
         super().__init__()
         H = np.ascontiguousarray(H, np.float32)
         self.nCHout, self.nCHin, self.length_h = H.shape
         self.hop = int(hopSize)
         if device is not None:
             self._lib.safconv_set_device(int(device))
-        if _from_shard is not None:
+        if devices is not None:
+            # one handle over several GPUs (safconv_matrixConv_create_multi); used with the unchanged apply / destroy
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.nOutLocal = self.nCHout
+            self._lib.safconv_matrixConv_create_multi(C.byref(self._h), self.hop, _fp(H), self.length_h,
+                                                      self.nCHin, self.nCHout, devs, len(devices))
+        elif _from_shard is not None:
             nOutTotal, ob = _from_shard
             self.nOutLocal, self.nCHout = H.shape[0], int(nOutTotal)
             self._lib.safconv_matrixConv_create_from_shard(C.byref(self._h), self.hop, _fp(H), self.length_h,
@@ -303,14 +332,20 @@ class MultiConv(_Base):
 
     _destroy_name = "saf_multiConv_destroy"
 
-    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None):
+    def __init__(self, hopSize: int, H: np.ndarray, usePartFLAG: int = 1, shard=None, device: int | None = None,
+                 devices=None):
         super().__init__()
         H = np.ascontiguousarray(H, np.float32)
         self.nCH, self.length_h = H.shape
         self.hop = int(hopSize)
         if device is not None:
             self._lib.safconv_set_device(int(device))
-        if shard is None:
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.nOutLocal = self.nCH
+            self._lib.safconv_multiConv_create_multi(C.byref(self._h), self.hop, _fp(H), self.length_h, self.nCH,
+                                                     devs, len(devices))
+        elif shard is None:
             self.nOutLocal = self.nCH
             self._lib.saf_multiConv_create(C.byref(self._h), self.hop, _fp(H), self.length_h, self.nCH, int(usePartFLAG))
         else:

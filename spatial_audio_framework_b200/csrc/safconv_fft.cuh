@@ -11,6 +11,26 @@
 
 #define SC_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+/* Opt-in to more than 48 KB of dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is a LIMIT that is
+ * global per (function, device): a plan-specific value set by one handle would be lowered by the next handle that
+ * shares the kernel instantiation, and the first handle's launches would then fail.  So the limit is only ever set
+ * to the device's opt-in maximum (227 KB on sm_100) -- monotone by construction, whatever handles are alive. */
+template <class F>
+static inline cudaError_t sc_optin_smem(F fn)
+{
+    static int optin[64];                           /* per device, 0 = not queried yet */
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int mx = (dev >= 0 && dev < 64) ? optin[dev] : 0;
+    if (!mx) {
+        e = cudaDeviceGetAttribute(&mx, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) optin[dev] = mx;
+    }
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /*  small device helpers                                                                      */
 /* ------------------------------------------------------------------------------------------ */

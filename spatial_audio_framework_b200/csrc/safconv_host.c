@@ -10,65 +10,13 @@
  * the per-block launches.  There is no CPU compute path: if the device layer fails,
  * the error is recorded and create() leaves *phMC == NULL.
  */
-#include "../../include/safconv_b200.h"
-#include "safconv_dev.h"
+#include "safconv_host_internal.h"
 
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-
-#define SAFCONV_MAGIC 0x5AFC0B20u
-#define SAFCONV_VERSION_STRING "safconv-b200 0.1 (sm_100a; matrixConv/multiConv/TVConv)"
-
-typedef struct safconv_handle {
-    uint32_t   magic;
-    int        err;
-    char       errmsg[256];
-    scdev_plan pl;
-    scdev_bufs b;
-    int        device, smCount, maxSmem;
-    int        nCHoutTotal, outBegin;
-    void*      streamOwn;
-    void*      stream;
-    float     *d_in, *d_out;         /* device staging for the host-pointer API  */
-    float     *h_in, *h_out;         /* pinned host staging                      */
-    size_t     inBytes, outBytes;
-    size_t     bytesH, bytesX, bytesZp;
-    int        useGraph;
-    int        smallOk;              /* the plan qualifies for the fused small-problem kernel */
-    int        smallFused;           /* 1: saf_matrixConv_apply of a small problem = ONE fused kernel on mapped host buffers */
-    int        batching;             /* 1: safconv_apply_device_blocks shares the FFT launches across a batch */
-    int        detectPinned;         /* 1: DMA straight from/to caller buffers that are already page-locked */
-    void*      graphExec;
-    int        timingCap, timingCount;   /* 4 CUDA events per enqueued launch group while kernel timing is enabled */
-    void**     evRing;
-    int*       evBlocks;             /* blocks covered by each launch group */
-    void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
-    scdev_offline off;               /* offline (batched frames) workspace, allocated on first use */
-    void*      offEv[4];
-    void      *offIn, *offOut;       /* copy streams of the pipelined host-buffer render */
-    void*      offPipeEv[6];         /* per double-buffer slot: input landed, segment rendered, output copied back */
-    float     *offStageIn[2], *offStageOut[2];   /* device staging of the pipelined render (kept between calls) */
-    int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
-    /* look-ahead (matrix, P >= 2): all partitions p >= 1 of block t+1 only need spectra that are already in the
-     * delay line when block t is done, so that TAIL pass is enqueued right behind block t and runs while the host
-     * is away; saf_matrixConv_apply(t+1) then only pays for the newest partition (HEAD pass) */
-    scdev_macpass tailPass, headPass;
-    int        lookahead;            /* option: 1 = use the tail/head split in the host-pointer apply */
-    int        tailReady;            /* a tail pass for the current block counter is enqueued on `stream` */
-    void*      evDone;               /* recorded after the output of a block is complete: apply waits on it, not on the whole stream */
-    void*      streamIn;             /* side stream: the forward FFT of the new block runs beside the tail pass */
-    void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
-    void*      streamOut;            /* high-priority side stream: K3 (+ D2H) of block t runs beside the tail pass of block t+1 */
-    void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
-    void*      evTail;               /* end of the most recent tail pass */
-    unsigned int count;              /* host mirror of the device block counter (counters[0]) */
-    int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
-    int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
-    void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
-} safconv_handle;
 
 static __thread int  tl_err = 0;
 static __thread char tl_msg[256] = "";
@@ -90,13 +38,21 @@ static int h_fail(safconv_handle* h, int code, const char* what, int cudaErr)
     return code;
 }
 
+void sch_set_tl_error(int code, const char* fmt, const char* detail) { set_tl_error(code, fmt, detail); }
+int  sch_fail(safconv_handle* h, int code, const char* what, int cudaErr) { return h_fail(h, code, what, cudaErr); }
+
 #define DEV_TRY(h, call, what) do { int e__ = (call); if (e__) { h_fail((h), SAFCONV_ERR_CUDA, (what), e__); goto fail; } } while (0)
+
+/* "last error" semantics: every apply / extension call starts with a clean slate, so one transient failure
+ * (e.g. an out-of-range irIdx) does not make later, correct calls look failed */
+static void h_clear(safconv_handle* h) { h->err = SAFCONV_OK; h->errmsg[0] = 0; }
 
 static safconv_handle* as_handle(void* p)
 {
     safconv_handle* h = (safconv_handle*)p;
     return (h && h->magic == SAFCONV_MAGIC) ? h : NULL;
 }
+safconv_handle* sch_as_handle(void* p) { return as_handle(p); }
 
 /* ------------------------------------------------------------------------------------------ */
 /*  planning                                                                                    */
@@ -130,6 +86,8 @@ static int env_int(const char* name, int dflt, int lo, int hi)
     int x = atoi(v);
     return (x < lo || x > hi) ? dflt : x;
 }
+
+int sch_env_int(const char* name, int dflt, int lo, int hi) { return env_int(name, dflt, lo, hi); }
 
 static void plan_mac(scdev_plan* pl, int smCount)
 {
@@ -496,9 +454,15 @@ fail:
     return NULL;
 }
 
+safconv_handle* sch_conv_create(int kind, int hop, const float* const* chunks, int nChunks, size_t rowsPerChunk,
+                                int len, int nIn, int nOutLocal, int nOutTotal, int outBegin, int nIRs)
+{ return conv_create(kind, hop, chunks, nChunks, rowsPerChunk, len, nIn, nOutLocal, nOutTotal, outBegin, nIRs); }
+void sch_handle_free(safconv_handle* h) { handle_free(h); }
+
 static void conv_destroy(void** const ph)
 {
     if (!ph) return;
+    if (scm_is_multi(*ph)) { scm_destroy(ph); return; }
     safconv_handle* h = as_handle(*ph);
     if (h) handle_free(h);
     *ph = NULL;
@@ -575,13 +539,15 @@ static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out) { r
 #define LA_TRY(call) do { if (!e) e = (call); } while (0)
 #define LA_TRACE(i, st) do { if (tr) scdev_event_record(h->trEv[i], (st)); } while (0)
 
-/* K1 of the new block; returns with `stream` ordered behind it.  zc: straight from the page-locked host buffer. */
-static int la_input(safconv_handle* h, const float* src, int zc)
+/* K1 of the new block; returns with `stream` ordered behind it.  Three sources (sch_la_io): a copy-engine upload into
+ * h->d_in (K1 then runs on `stream`), or K1 on the side stream straight from a page-locked host buffer / from a device
+ * buffer that a foreign stream fills (evSrc). */
+static int la_input(safconv_handle* h, const sch_la_io* io)
 {
     const scdev_plan* pl = &h->pl;
     int e = 0;
-    if (!zc) {
-        e = scdev_memcpy_h2d_async(h->d_in, src, h->inBytes, h->stream);
+    if (io->h2dSrc) {
+        e = scdev_memcpy_h2d_async(h->d_in, io->h2dSrc, h->inBytes, h->stream);
         LA_TRY(scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream));
         return e;
     }
@@ -589,7 +555,8 @@ static int la_input(safconv_handle* h, const float* src, int zc)
         e = scdev_event_record(h->evFence, h->stream);
         LA_TRY(scdev_stream_wait_event(h->streamIn, h->evFence));
     }
-    LA_TRY(scdev_input_fft(pl, &h->b, src, 1, h->streamIn));
+    if (io->evSrc) LA_TRY(scdev_stream_wait_event(h->streamIn, io->evSrc));
+    LA_TRY(scdev_input_fft(pl, &h->b, io->k1src, 1, h->streamIn));
     LA_TRY(scdev_event_record(h->evIn, h->streamIn));
     LA_TRY(scdev_stream_wait_event(h->stream, h->evIn));
     return e;
@@ -599,12 +566,14 @@ static int la_input(safconv_handle* h, const float* src, int zc)
  * but tail passes, back to back.  The head pass of block c runs on the side stream with a two-stage pipeline (69 KB of
  * shared memory: its CTAs fit on the SMs beside the resident tail CTAs) while the block's own tail pass is still
  * streaming; K3 follows as soon as that tail pass is done, beside the tail pass of block c+1. */
-static int la_throughput(safconv_handle* h, unsigned int c, int zc, float* kout, float* dst, int tr)
+static int la_throughput(safconv_handle* h, unsigned int c, const sch_la_io* io, int tr)
 {
     const scdev_plan* pl = &h->pl;
     const int tb = (int)(c & 1u);
     scdev_macpass head2 = h->headPass;
     head2.stages = 2;
+    const int zc = (io->h2dSrc == NULL);                                  /* K1 ran on the side stream */
+    float* const kout = io->kout;
     int e = 0;
     if (!zc) e = scdev_event_record(h->evMac, h->stream);                 /* K1 ran on `stream`: its spectrum is ready here */
     LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream));
@@ -615,7 +584,7 @@ static int la_throughput(safconv_handle* h, unsigned int c, int zc, float* kout,
     LA_TRY(scdev_stream_wait_event(h->streamOut, h->evTail));             /* tail pass of block c: K3 needs both */
     LA_TRACE(3, h->streamOut);
     LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut));
-    if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut));
+    if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->streamOut));
     LA_TRACE(4, h->streamOut);
     LA_TRY(scdev_event_record(h->evDone, h->streamOut));
     return e;
@@ -625,15 +594,16 @@ static int la_throughput(safconv_handle* h, unsigned int c, int zc, float* kout,
  * head-pass launch at all: K3 adds the newest partition itself while it gathers the tail's partial tiles (or, with
  * SAFCONV_HEAD_IN_K3=0, head pass then K3 on the side stream).  Without one (first block, or after any other call on the
  * handle) the full MAC runs.  The next tail pass is ordered behind K3. */
-static int la_latency(safconv_handle* h, unsigned int c, int hadTail, int zc, float* kout, float* dst, int tr)
+static int la_latency(safconv_handle* h, unsigned int c, int hadTail, const sch_la_io* io, int tr)
 {
     const scdev_plan* pl = &h->pl;
     const int tb = (int)(c & 1u);
+    float* const kout = io->kout;
     int e = 0;
     if (hadTail && h->headInK3) {
         LA_TRACE(0, h->stream); LA_TRACE(1, h->stream); LA_TRACE(3, h->stream);
         LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, NULL, kout, h->stream));
-        if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->stream));
+        if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->stream));
         LA_TRACE(4, h->stream);
         LA_TRY(scdev_event_record(h->evDone, h->stream));
     } else {
@@ -646,7 +616,7 @@ static int la_latency(safconv_handle* h, unsigned int c, int hadTail, int zc, fl
         LA_TRACE(3, h->streamOut);
         if (hadTail) LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut));
         else         LA_TRY(scdev_ifft_ola(pl, &h->b, kout, h->streamOut));
-        if (!zc) LA_TRY(scdev_memcpy_d2h_async(dst, h->d_out, h->outBytes, h->streamOut));
+        if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->streamOut));
         LA_TRACE(4, h->streamOut);
         LA_TRY(scdev_event_record(h->evDone, h->streamOut));
         LA_TRY(scdev_stream_wait_event(h->stream, h->evDone));
@@ -670,26 +640,40 @@ static void la_trace_report(safconv_handle* h, unsigned int c, int tr)
     if (h->trace) scdev_event_record(h->trEv[2], h->stream);      /* end of the tail pass just enqueued: read by the next call */
 }
 
-/* One block through the look-ahead sequence; on return the output is in `dst` (a page-locked host buffer). */
-static int apply_lookahead(safconv_handle* h, const float* src, float* dst)
+/* One block through the look-ahead sequence described by `io`; with io->sync the output is complete on return,
+ * otherwise evDone is recorded behind it. */
+int sch_apply_lookahead_io(safconv_handle* h, const sch_la_io* io)
 {
-    /* blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers */
-    const int zc = h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20);
-    float* kout = zc ? dst : h->d_out;
     const unsigned int c = h->count;
     const int hadTail = h->tailReady;
     const int tr = h->trace && hadTail;
     /* is the caller coming back faster than the GPU streams the filters? */
     const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
-    int e = la_input(h, src, zc);
+    int e = la_input(h, io);
     h->tailReady = 0;
-    if (backToBack) LA_TRY(la_throughput(h, c, zc, kout, dst, tr));
-    else            LA_TRY(la_latency(h, c, hadTail, zc, kout, dst, tr));
+    if (backToBack) LA_TRY(la_throughput(h, c, io, tr));
+    else            LA_TRY(la_latency(h, c, hadTail, io, tr));
     LA_TRY(scdev_event_record(h->evTail, h->stream));
-    if (!e) { h->tailReady = 1; h->count = c + 1; e = scdev_event_sync(h->evDone); }
-    if (!e) la_trace_report(h, c, tr);
+    if (!e) { h->tailReady = 1; h->count = c + 1; if (io->sync) e = scdev_event_sync(h->evDone); }
+    if (!e && io->sync) la_trace_report(h, c, tr);
     if (e) h->tailReady = 0;
     return e;
+}
+
+/* host-pointer form: `src` / `dst` are page-locked host buffers */
+static int apply_lookahead(safconv_handle* h, const float* src, float* dst)
+{
+    /* blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers */
+    const int zc = h->inBytes <= (1u << 20) && h->outBytes <= (1u << 20);
+    sch_la_io io;
+    io.k1src = zc ? src : h->d_in;  io.h2dSrc = zc ? NULL : src;  io.evSrc = NULL;
+    io.kout  = zc ? dst : h->d_out; io.d2hDst = zc ? NULL : dst;  io.sync = 1;
+    return sch_apply_lookahead_io(h, &io);
+}
+
+int sch_uses_lookahead(const safconv_handle* h)
+{
+    return h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->useGraph && !h->timingCap && !(h->smallFused && h->smallOk);
 }
 
 /* Blocks of up to 1 MB without look-ahead: the kernels read / write the page-locked host buffers directly -- no
@@ -721,13 +705,24 @@ static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int 
  * staging buffers. */
 static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
 {
+    h_clear(h);
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
-    const int direct = h->detectPinned && scdev_is_pinned_host(in) && scdev_is_pinned_host(out);
+    /* first AND last byte: a caller buffer that is only partly registered must take the staging path */
+    const int direct = h->detectPinned && scdev_is_pinned_host(in) && scdev_is_pinned_host(out)
+                    && scdev_is_pinned_host((const char*)in + h->inBytes - 1) && scdev_is_pinned_host((const char*)out + h->outBytes - 1);
     const float* src = direct ? in : h->h_in;
     float*       dst = direct ? out : h->h_out;
     if (!direct) memcpy(h->h_in, in, h->inBytes);
+    sch_apply_pinned(h, src, dst, irIdx);
+    if (!direct && !h->err) memcpy(out, h->h_out, h->outBytes);
+}
 
+/* one block, src / dst page-locked and visible to the handle's device */
+void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx)
+{
+    int e = scdev_set_device(h->device);
+    if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
     e = apply_zero_copy(h, src, dst, irIdx);
     if (e >= 0) {
         if (!e) e = scdev_stream_sync(h->stream);
@@ -771,7 +766,6 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
         if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply", e); return; }
         h->count++;
     }
-    if (!direct) memcpy(out, h->h_out, h->outBytes);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -782,6 +776,7 @@ void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_
 {
     (void)usePartFLAG;   /* both reference modes compute the same linear convolution; one engine serves both */
     if (!phMC) return;
+    if (H && getenv("SAFCONV_DEVICES") && (*phMC = scm_create_from_env(SC_KIND_MATRIX, hopSize, H, length_h, nCHin, nCHout)) != NULL) return;
     const float* chunk = H;
     *phMC = conv_create(SC_KIND_MATRIX, hopSize, H ? &chunk : NULL, 1,
                         (size_t)(nCHout > 0 ? nCHout : 0) * (size_t)(nCHin > 0 ? nCHin : 0),
@@ -820,6 +815,7 @@ void saf_matrixConv_destroy(void** const phMC) { conv_destroy(phMC); }
 
 void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 {
+    if (scm_is_multi(hMC)) { scm_apply(hMC, SC_KIND_MATRIX, inputSigs, outputSigs); return; }
     safconv_handle* h = as_handle(hMC);
     if (!h || h->pl.kind != SC_KIND_MATRIX || !inputSigs || !outputSigs) return;
     conv_apply_host(h, inputSigs, outputSigs, 0);
@@ -829,6 +825,7 @@ void saf_multiConv_create(void** const phMC, int hopSize, float* H, int length_h
 {
     (void)usePartFLAG;
     if (!phMC) return;
+    if (H && getenv("SAFCONV_DEVICES") && (*phMC = scm_create_from_env(SC_KIND_MULTI, hopSize, H, length_h, nCH, nCH)) != NULL) return;
     const float* chunk = H;
     *phMC = conv_create(SC_KIND_MULTI, hopSize, H ? &chunk : NULL, 1, (size_t)(nCH > 0 ? nCH : 0),
                         length_h, nCH, nCH, nCH, 0, 0);
@@ -851,6 +848,7 @@ void saf_multiConv_destroy(void** const phMC) { conv_destroy(phMC); }
 
 void saf_multiConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 {
+    if (scm_is_multi(hMC)) { scm_apply(hMC, SC_KIND_MULTI, inputSigs, outputSigs); return; }
     safconv_handle* h = as_handle(hMC);
     if (!h || h->pl.kind != SC_KIND_MULTI || !inputSigs || !outputSigs) return;
     conv_apply_host(h, inputSigs, outputSigs, 0);
@@ -874,6 +872,7 @@ void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int
 {
     safconv_handle* h = as_handle(hTVC);
     if (!h || h->pl.kind != SC_KIND_TV || !inputSigs || !outputSigs) return;
+    h_clear(h);
     if (irIdx < 0 || irIdx >= h->pl.nIRs) { h_fail(h, SAFCONV_ERR_ARG, "irIdx out of range", 0); return; }
     conv_apply_host(h, inputSigs, outputSigs, irIdx);
 }
@@ -884,12 +883,14 @@ void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int
 
 int safconv_last_error(void* hp)
 {
+    if (scm_is_multi(hp)) return scm_last_error(hp);
     safconv_handle* h = as_handle(hp);
     return h ? h->err : tl_err;
 }
 
 const char* safconv_last_error_string(void* hp)
 {
+    if (scm_is_multi(hp)) return scm_last_error_string(hp);
     safconv_handle* h = as_handle(hp);
     return h ? h->errmsg : tl_msg;
 }
@@ -913,6 +914,7 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
 {
     safconv_handle* h = as_handle(hp);
     if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
+    h_clear(h);
     int e = scdev_set_device(h->device);
     h->tailReady = 0;          /* a pre-computed tail belongs to the block counter it was enqueued for */
     const size_t inStride = (size_t)h->pl.nIn * h->pl.hop, outStride = (size_t)h->pl.nOutLocal * h->pl.hop;
@@ -974,7 +976,7 @@ int safconv_rfft_backward(int N, int nBatch, const float* X, float* x) { return 
 /* ---- fftconv / fftfilt (reference saf_utility_fft.c:157-228) on the multiConv engine ---- */
 static int fftconv_impl(const float* x, const float* h, int x_len, int h_len, int nCH, float* y, int keep)
 {
-    if (!x || !h || !y || x_len < 1 || h_len < 1 || nCH < 1 || nCH > 65535) {
+    if (!x || !h || !y || x_len < 1 || h_len < 1 || nCH < 1) {
         set_tl_error(SAFCONV_ERR_ARG, "fftconv: invalid argument%s", "");
         return SAFCONV_ERR_ARG;
     }
@@ -1167,6 +1169,7 @@ void* safconv_get_stream(void* hp)
 
 int safconv_synchronize(void* hp)
 {
+    if (scm_is_multi(hp)) return scm_synchronize(hp);
     safconv_handle* h = as_handle(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
@@ -1176,6 +1179,7 @@ int safconv_synchronize(void* hp)
 
 int safconv_reset_state(void* hp)
 {
+    if (scm_is_multi(hp)) return scm_reset_state(hp);
     safconv_handle* h = as_handle(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
@@ -1191,6 +1195,7 @@ int safconv_reset_state(void* hp)
 
 int safconv_get_info(void* hp, safconv_info* info)
 {
+    if (scm_is_multi(hp)) return scm_get_info(hp, info);
     safconv_handle* h = as_handle(hp);
     if (!h || !info) return SAFCONV_ERR_ARG;
     const scdev_plan* pl = &h->pl;
@@ -1284,6 +1289,7 @@ int safconv_get_kernel_times(void* hp, float ms[3], int* nBlocksOut)
 
 int safconv_set_option(void* hp, const char* name, int value)
 {
+    if (scm_is_multi(hp)) return scm_set_option(hp, name, value);
     safconv_handle* h = as_handle(hp);
     if (!h || !name) return SAFCONV_ERR_ARG;
     if (!strcmp(name, "mac_hints")) { h->pl.macHints = (value < 0 || value > 2) ? 1 : value; }

@@ -1,0 +1,104 @@
+/*
+ * safconv_host_internal.h -- private to the C host layer of libsafconv_b200.so (safconv_host.c: single-device handles,
+ * safconv_multi.c: one handle spanning several GPUs of a box).  Not installed, not part of the C ABI.
+ */
+#ifndef SAFCONV_HOST_INTERNAL_H_INCLUDED
+#define SAFCONV_HOST_INTERNAL_H_INCLUDED
+
+#include "../../include/safconv_b200.h"
+#include "safconv_dev.h"
+
+#include <stdint.h>
+
+#define SC_HIDDEN __attribute__((visibility("hidden")))
+
+#define SAFCONV_MAGIC 0x5AFC0B20u
+#define SAFCONV_MAGIC_MULTI 0x5AFC0B28u     /* safconv_multi.c: a handle that spans several devices */
+#define SAFCONV_VERSION_STRING "safconv-b200 0.2 (sm_100a; matrixConv/multiConv/TVConv; multi-GPU handles)"
+
+typedef struct safconv_handle {
+    uint32_t   magic;
+    int        err;
+    char       errmsg[256];
+    scdev_plan pl;
+    scdev_bufs b;
+    int        device, smCount, maxSmem;
+    int        nCHoutTotal, outBegin;
+    void*      streamOwn;
+    void*      stream;
+    float     *d_in, *d_out;         /* device staging for the host-pointer API  */
+    float     *h_in, *h_out;         /* pinned host staging                      */
+    size_t     inBytes, outBytes;
+    size_t     bytesH, bytesX, bytesZp;
+    int        useGraph;
+    int        smallOk;              /* the plan qualifies for the fused small-problem kernel */
+    int        smallFused;           /* 1: saf_matrixConv_apply of a small problem = ONE fused kernel on mapped host buffers */
+    int        batching;             /* 1: safconv_apply_device_blocks shares the FFT launches across a batch */
+    int        detectPinned;         /* 1: DMA straight from/to caller buffers that are already page-locked */
+    void*      graphExec;
+    int        timingCap, timingCount;   /* 4 CUDA events per enqueued launch group while kernel timing is enabled */
+    void**     evRing;
+    int*       evBlocks;             /* blocks covered by each launch group */
+    void      *graphIn, *graphOut;   /* host pointers captured in graphExec */
+    scdev_offline off;               /* offline (batched frames) workspace, allocated on first use */
+    void*      offEv[4];
+    void      *offIn, *offOut;       /* copy streams of the pipelined host-buffer render */
+    void*      offPipeEv[6];         /* per double-buffer slot: input landed, segment rendered, output copied back */
+    float     *offStageIn[2], *offStageOut[2];   /* device staging of the pipelined render (kept between calls) */
+    int        tvLast, tvLast2;      /* posIdx_last, posIdx_last2 (reference .c:438, 618-619) */
+    /* look-ahead (matrix, P >= 2): all partitions p >= 1 of block t+1 only need spectra that are already in the
+     * delay line when block t is done, so that TAIL pass is enqueued right behind block t and runs while the host
+     * is away; saf_matrixConv_apply(t+1) then only pays for the newest partition (HEAD pass) */
+    scdev_macpass tailPass, headPass;
+    int        lookahead;            /* option: 1 = use the tail/head split in the host-pointer apply */
+    int        tailReady;            /* a tail pass for the current block counter is enqueued on `stream` */
+    void*      evDone;               /* recorded after the output of a block is complete: apply waits on it, not on the whole stream */
+    void*      streamIn;             /* side stream: the forward FFT of the new block runs beside the tail pass */
+    void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
+    void*      streamOut;            /* high-priority side stream: K3 (+ D2H) of block t runs beside the tail pass of block t+1 */
+    void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
+    void*      evTail;               /* end of the most recent tail pass */
+    unsigned int count;              /* host mirror of the device block counter (counters[0]) */
+    int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
+    int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
+    void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
+} safconv_handle;
+
+
+/* where one block of the look-ahead apply comes from and goes to (safconv_host.c: apply_lookahead) */
+typedef struct sch_la_io {
+    const float* k1src;   /* what K1 reads: a page-locked host block (zero-copy) or a device buffer                     */
+    const float* h2dSrc;  /* != NULL: copy-engine upload of this host block into h->d_in first (K1 then reads h->d_in)  */
+    void*        evSrc;   /* != NULL: K1 waits for this event (the input was produced on a foreign stream)              */
+    float*       kout;    /* what K3 writes: a page-locked host block (zero-copy) or a device buffer                    */
+    float*       d2hDst;  /* != NULL: copy-engine download of h->d_out into this host block behind K3                   */
+    int          sync;    /* 1: wait until the output is complete (evDone) before returning                             */
+} sch_la_io;
+
+/* internals shared with safconv_multi.c */
+SC_HIDDEN safconv_handle* sch_as_handle(void* p);
+SC_HIDDEN void sch_set_tl_error(int code, const char* fmt, const char* detail);
+SC_HIDDEN int  sch_fail(safconv_handle* h, int code, const char* what, int cudaErr);
+SC_HIDDEN int  sch_env_int(const char* name, int dflt, int lo, int hi);
+SC_HIDDEN safconv_handle* sch_conv_create(int kind, int hop, const float* const* chunks, int nChunks, size_t rowsPerChunk,
+                                          int len, int nIn, int nOutLocal, int nOutTotal, int outBegin, int nIRs);
+SC_HIDDEN void sch_handle_free(safconv_handle* h);
+/* one block, in / out page-locked host memory visible to the handle's device (synchronous) */
+SC_HIDDEN void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx);
+/* one block of a matrix handle with look-ahead through an explicit io description; returns a CUDA error code */
+SC_HIDDEN int  sch_apply_lookahead_io(safconv_handle* h, const sch_la_io* io);
+SC_HIDDEN int  sch_uses_lookahead(const safconv_handle* h);
+
+/* safconv_multi.c */
+SC_HIDDEN int   scm_is_multi(const void* p);
+SC_HIDDEN void  scm_apply(void* p, int kind, const float* in, float* out);
+SC_HIDDEN void  scm_destroy(void** pp);
+SC_HIDDEN void* scm_create_from_env(int kind, int hop, const float* H, int len, int nIn, int nOut);
+SC_HIDDEN int   scm_last_error(void* p);
+SC_HIDDEN const char* scm_last_error_string(void* p);
+SC_HIDDEN int   scm_get_info(void* p, safconv_info* info);
+SC_HIDDEN int   scm_set_option(void* p, const char* name, int value);
+SC_HIDDEN int   scm_reset_state(void* p);
+SC_HIDDEN int   scm_synchronize(void* p);
+
+#endif

@@ -44,13 +44,16 @@
 
 /* ------------------------------------------------------------------------------------------ */
 /*  K0: filter partition + forward FFT                                                         */
-/*  grid (P, nIn or 1, nOutLocal), one CTA per (partition, input, output)                       */
+/*  one CTA per (row, input, partition), row = output (matrix), channel (multi) or IR x output  */
+/*  (TV); the CTA index is linear over grid.x (+ grid.y beyond 2^30 CTAs): no 65535 limits     */
 /* ------------------------------------------------------------------------------------------ */
 struct FilterArgs {
     const float* h;        /* time-domain filters */
     float2*      H;
     const float2* tw;
     int kind, hop, len, nIn, M, logM, P, nKT, OTsz;
+    int nInGrid;           /* nIn (matrix) or 1 */
+    long long total;       /* rows * nInGrid * P */
 };
 
 __global__ void filter_fft_kernel(FilterArgs a)
@@ -60,7 +63,11 @@ __global__ void filter_fft_kernel(FilterArgs a)
     const bool wide = fft_use_wide(a.M, 1);
     load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
-    const int p = blockIdx.x, ni = blockIdx.y, no = blockIdx.z;
+    const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta >= a.total) return;                         /* block-uniform */
+    const int p = (int)(cta % a.P);
+    const long long rowIn = cta / a.P;
+    const int ni = (int)(rowIn % a.nInGrid), no = (int)(rowIn / a.nInGrid);
     const float* src;
     if (a.kind == SC_KIND_MATRIX) src = a.h + ((size_t)no * a.nIn + ni) * a.len;
     else                          src = a.h + (size_t)no * a.len;        /* multi: [ch][len]; tv: [ir*nOut+no][len] */
@@ -764,13 +771,13 @@ static int multi_w_launch(const scdev_plan* pl, MultiArgs& a, int nBlocks, int w
     const size_t tile = (size_t)(M + 32) * sizeof(float2);
     if (which == 0) {
         dim3 grid(pl->nOutLocal, (nBlocks + 7) / 8);
-        if (8 * tile > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * tile)));
+        if (8 * tile > 48 * 1024) SC_CHECK(sc_optin_smem(multi_fft_w_kernel<R>));
         multi_fft_w_kernel<R><<<grid, 256, 8 * tile, st>>>(a);
     } else {
         dim3 grid(pl->nOutLocal, (nBlocks + R - 1) / R);
         const size_t smem = (size_t)R * tile;
 #define SC_MW_LAUNCH(PT) do {                                                                                        \
-            if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_w_kernel<R, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(multi_mac_ifft_w_kernel<R, PT>)); \
             multi_mac_ifft_w_kernel<R, PT><<<grid, M, smem, st>>>(a); } while (0)
         if (pl->P <= 2) SC_MW_LAUNCH(2); else if (pl->P <= 4) SC_MW_LAUNCH(4); else if (pl->P <= 8) SC_MW_LAUNCH(8); else SC_MW_LAUNCH(16);
 #undef SC_MW_LAUNCH
@@ -1198,24 +1205,24 @@ static mac_fn_t mac_fn(int R)
 
 int scdev_prepare(const scdev_plan* pl)
 {
-    /* FFT kernels hold the data and the twiddle table in shared memory: 2*M float2 (<= 128 KB) */
-    if (fft_smem(pl, 2) > 48 * 1024) {
-        const int big = (int)fft_smem(pl, 2);
-        SC_CHECK(cudaFuncSetAttribute(filter_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        SC_CHECK(cudaFuncSetAttribute(input_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        SC_CHECK(cudaFuncSetAttribute(ifft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        SC_CHECK(cudaFuncSetAttribute(ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    }
+    /* FFT kernels hold the data and the twiddle table in shared memory: 2*M float2 (<= 128 KB).  The limit is raised to
+     * the device maximum for every kernel this kind of handle can launch (see sc_optin_smem: never plan-specific). */
+    SC_CHECK(sc_optin_smem(filter_fft_kernel));
+    SC_CHECK(sc_optin_smem(input_fft_kernel));
+    SC_CHECK(sc_optin_smem(ifft_ola_kernel));
+    SC_CHECK(sc_optin_smem(ifft_batch_kernel));
     if (pl->kind == SC_KIND_MULTI) {
-        const size_t need[3] = { fft_smem(pl, 3), fft_smem(pl, multi_fft_q(pl) + 1), fft_smem(pl, 2) };
-        if (need[0] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[0]));
-        if (need[1] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[1]));
-        if (need[2] > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(multi_mac_ifft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[2]));
+        SC_CHECK(sc_optin_smem(multi_fused_kernel));
+        SC_CHECK(sc_optin_smem(multi_fft_batch_kernel));
+        SC_CHECK(sc_optin_smem(multi_mac_ifft_batch_kernel));
+        SC_CHECK(sc_optin_smem(multi_mac_ifft_batch_reg_kernel<2>));
+        SC_CHECK(sc_optin_smem(multi_mac_ifft_batch_reg_kernel<4>));
+        SC_CHECK(sc_optin_smem(multi_mac_ifft_batch_reg_kernel<8>));
+        SC_CHECK(sc_optin_smem(multi_mac_ifft_batch_reg_kernel<16>));
     }
-    if (pl->kind == SC_KIND_TV && fft_smem(pl, 5) > 48 * 1024)
-        SC_CHECK(cudaFuncSetAttribute(tv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem(pl, 5)));
+    if (pl->kind == SC_KIND_TV) SC_CHECK(sc_optin_smem(tv_fused_kernel));
     if (pl->kind == SC_KIND_MATRIX) {
-        SC_CHECK(cudaFuncSetAttribute(mac_fn(pl->R), cudaFuncAttributeMaxDynamicSharedMemorySize, pl->macSmemBytes));
+        SC_CHECK(sc_optin_smem(mac_fn(pl->R)));
         /* The look-ahead apply runs K1 (next block) and K3 (this block) BESIDE a resident tail pass of the MAC.  CTAs
          * of kernels whose shared-memory carve-outs differ cannot share an SM (measured: with the driver's per-kernel
          * choice K1 / K3 waited for the whole 0.43 ms tail pass), so all three ask for the same, largest one. */
@@ -1232,16 +1239,14 @@ int scdev_filter_transform(const scdev_plan* pl, const scdev_bufs* b, const floa
     a.h = d_h; a.H = (float2*)b->H; a.tw = (const float2*)b->tw;
     a.kind = pl->kind; a.hop = pl->hop; a.len = pl->len; a.nIn = pl->nIn;
     a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
-    if (pl->kind == SC_KIND_MATRIX) {
-        if (pl->nOutLocal > 65535 || pl->nIn > 65535) return (int)cudaErrorInvalidValue;   /* grid.y / grid.z limits */
-        dim3 grid(pl->P, pl->nIn, pl->nOutLocal);
-        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
-    } else {
-        const int rows = (pl->kind == SC_KIND_TV) ? pl->nIRs * pl->nOutLocal : pl->nOutLocal;
-        if (rows > 65535) return (int)cudaErrorInvalidValue;
-        dim3 grid(pl->P, 1, rows);
-        filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
-    }
+    const long long rows = (pl->kind == SC_KIND_TV) ? (long long)pl->nIRs * pl->nOutLocal : pl->nOutLocal;
+    a.nInGrid = (pl->kind == SC_KIND_MATRIX) ? pl->nIn : 1;
+    a.total = rows * a.nInGrid * pl->P;
+    const long long gx = a.total < (1ll << 30) ? a.total : (1ll << 30);
+    const long long gy = (a.total + gx - 1) / gx;
+    if (gy > 65535) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    filter_fft_kernel<<<grid, pl->fftThreads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -1452,7 +1457,7 @@ int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in
     a.OTsz = pl->OTsz; a.RS = pl->RS;
     a.scale = 1.0f / (float)pl->N;
     const size_t smem = small_smem(pl, SC_SMALL_THREADS);
-    if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(small_fused_kernel));
     small_fused_kernel<<<pl->nOutLocal, SC_SMALL_THREADS, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -1476,10 +1481,10 @@ int scdev_rfft(int N, int logM, int nBatch, int dir, const float* d_in, float* d
     int threads = M / 4; if (threads < 32) threads = 32; if (threads > 256) threads = 256;
     const size_t smem = ((size_t)2 * SC_ALEN(M) + sc_split_len(M)) * sizeof(float2);
     if (dir == 0) {
-        if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(rfft_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(rfft_forward_kernel));
         rfft_forward_kernel<<<nBatch, threads, smem, (cudaStream_t)stream>>>(a);
     } else {
-        if (smem > 48 * 1024) SC_CHECK(cudaFuncSetAttribute(rfft_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(rfft_backward_kernel));
         rfft_backward_kernel<<<nBatch, threads, smem, (cudaStream_t)stream>>>(a);
     }
     return (int)cudaGetLastError();

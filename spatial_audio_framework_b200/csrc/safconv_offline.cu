@@ -1031,10 +1031,10 @@ template <int R>
 static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
 {
     if (f) {
-        SC_CHECK(cudaFuncSetAttribute(offline_fft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offw_fft_smem<R>()));
+        SC_CHECK(sc_optin_smem(offline_fft_w_kernel<R>));
         offline_fft_w_kernel<R><<<grid, OFFW_THREADS, offw_fft_smem<R>(), st>>>(*f);
     } else {
-        SC_CHECK(cudaFuncSetAttribute(offline_ifft_w_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offw_ifft_smem<R>()));
+        SC_CHECK(sc_optin_smem(offline_ifft_w_kernel<R>));
         offline_ifft_w_kernel<R><<<grid, OFFW_THREADS, offw_ifft_smem<R>(), st>>>(*i);
     }
     return (int)cudaGetLastError();
@@ -1045,11 +1045,11 @@ static int offw_dispatch(int M, int variant, const OffFftArgs* f, const OffIfftA
     if (M == 1024 && variant == 2) {                           /* shuffle-free 32 x 32 version */
         if (f) {
             const size_t smem = (size_t)8 * WFFT_TILE * 8;
-            SC_CHECK(cudaFuncSetAttribute(offline_fft_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SC_CHECK(sc_optin_smem(offline_fft_t_kernel));
             offline_fft_t_kernel<<<grid, OFFW_THREADS, smem, st>>>(*f);
         } else {
             const size_t smem = (size_t)1024 * 9 * 8;           /* >= 8 tiles */
-            SC_CHECK(cudaFuncSetAttribute(offline_ifft_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SC_CHECK(sc_optin_smem(offline_ifft_t_kernel));
             offline_ifft_t_kernel<<<grid, OFFW_THREADS, smem, st>>>(*i);
         }
         return (int)cudaGetLastError();
@@ -1147,12 +1147,12 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
             offline_pack_filters_kernel<false><<<148 * 8, 256, 0, st>>>(a);
         }
         SC_CHECK(cudaGetLastError());
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->gemmSmem));
-        SC_CHECK(cudaFuncSetAttribute(offline_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SC_CHECK(cudaFuncSetAttribute(offline_ifft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SC_CHECK(sc_optin_smem(offline_gemm_kernel<true, false>));
+        SC_CHECK(sc_optin_smem(offline_gemm_kernel<false, false>));
+        SC_CHECK(sc_optin_smem(offline_gemm_kernel<true, true>));
+        SC_CHECK(sc_optin_smem(offline_gemm_kernel<false, true>));
+        SC_CHECK(sc_optin_smem(offline_fft_kernel));
+        SC_CHECK(sc_optin_smem(offline_ifft_kernel));
         o->packed = 1;
     }
     if (T > o->capFrames) {

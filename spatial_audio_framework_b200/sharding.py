@@ -108,10 +108,17 @@ class ShardedStep:
 
     # ------------------------------------------------------------------ single-GPU paths
     def load_input(self, x_host):
-        """Make one step of input resident on the device (rank 0's copy is the source of truth)."""
+        """Make one step of input resident on the device, in BOTH double-buffer slots (rank 0's copy is the source of
+        truth).  Waits for every outstanding exchange first, so it never races with a broadcast in flight."""
+        if self.world > 1 and self.cuda:
+            self.torch.cuda.current_stream().wait_stream(self.comm)
+            self.stream.wait_stream(self.comm)
+            self.pending_bcast = False
         self.x[0].copy_(x_host)
         if self.world > 1:
             self.x[1].copy_(x_host)
+            if self.cuda:
+                self.comm.wait_stream(self.torch.cuda.current_stream())
 
     def _compute(self, buf):
         if self.count > 0:
@@ -139,8 +146,13 @@ class ShardedStep:
                 self.y_all[buf][off:off + n] = piece[:n]
                 off += n
 
-    def step_device(self):
-        """Inputs already resident in HBM (on rank 0 for world > 1)."""
+    def step_device(self, prefetch=False):
+        """Inputs already resident in HBM (on rank 0 for world > 1).
+
+        prefetch=True additionally issues the broadcast of the NEXT step's slot while this step computes.  That is only
+        meaningful when the next step's input is already in that slot -- the benchmark's case (load_input fills both
+        slots before the timed region); a streaming caller that loads step t+1 after step t must leave it False, then
+        the broadcast of a slot is issued at the start of its own step, ordered behind load_input."""
         torch = self.torch
         if self.world == 1:
             self._compute(0)
@@ -158,13 +170,14 @@ class ShardedStep:
             with torch.cuda.stream(comm):
                 self._bcast(buf)
                 self.ev_b[buf].record(comm)
-        # prefetch the next step's input while this step computes (x[nxt] was last read by compute t-1)
-        with torch.cuda.stream(comm):
-            if self.t > 0:
-                comm.wait_event(self.ev_c[nxt])
-            self._bcast(nxt)
-            self.ev_b[nxt].record(comm)
-        self.pending_bcast = True
+        if prefetch:
+            # the next step's input while this step computes (x[nxt] was last read by compute t-1)
+            with torch.cuda.stream(comm):
+                if self.t > 0:
+                    comm.wait_event(self.ev_c[nxt])
+                self._bcast(nxt)
+                self.ev_b[nxt].record(comm)
+        self.pending_bcast = bool(prefetch)
         with torch.cuda.stream(cs):
             cs.wait_event(self.ev_b[buf])
             if self.t > 1:

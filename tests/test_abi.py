@@ -72,6 +72,33 @@ def test_no_cpu_fallback_without_device(saf):
         saf.MultiConv(64, np.zeros((1, 64), np.float32))
 
 
+def test_multi_gpu_create_argument_checks_and_no_device(saf, monkeypatch):
+    """safconv_matrixConv_create_multi: bad arguments are rejected before any device work; without a CUDA device it
+    fails loudly like the single-device create; the extension calls reject a NULL / foreign handle."""
+    import torch
+    lib = saf.lib()
+    H = np.zeros((2, 2, 16), np.float32)
+    hp = H.ctypes.data_as(C.POINTER(C.c_float))
+    devs = (C.c_int * 2)(0, 1)
+    for args in [(64, None, 16, 2, 2, devs, 2), (64, hp, 16, 2, 2, None, 2), (64, hp, 16, 2, 2, devs, 0),
+                 (64, hp, 16, 2, 2, devs, 17), (0, hp, 16, 2, 2, devs, 2), (64, hp, 0, 2, 2, devs, 2)]:
+        h = C.c_void_p(123)
+        lib.safconv_matrixConv_create_multi(C.byref(h), *args)
+        assert not h.value
+        assert lib.safconv_last_error(None) == 1 and b"invalid" in lib.safconv_last_error_string(None)
+    assert lib.safconv_multi_get_devices(None, devs, 2) == 0
+    assert not lib.safconv_multi_get_shard(None, 0)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        saf.MatrixConv(64, H, devices=[0, 1])
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        saf.MultiConv(64, H[0], devices=[0])
+    monkeypatch.setenv("SAFCONV_DEVICES", "all")           # the env route falls through to the ordinary failure
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        saf.MatrixConv(64, H)
+
+
 def test_helpers_fail_loudly_without_device(saf):
     """fftconv / fftfilt / rfft have no CPU path either: error code + message, output untouched; bad arguments are
     rejected before any device work."""
