@@ -735,7 +735,6 @@ def run_own_arm(args, w):
 
     if rank != 0:
         if dist:
-            dist.barrier(group=idle)
             dist.destroy_process_group()
         return
 

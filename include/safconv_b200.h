@@ -175,13 +175,36 @@ int safconv_apply_device(void* h, const float* d_in, float* d_out);
  */
 int safconv_apply_device_blocks(void* h, const float* d_in, float* d_out, int nBlocks);
 
+/* ========================================================================== */
+/*   Drop-in block 2 (reference: saf_utility_fft.h:240-276, real FFT wrapper)  */
+/* ========================================================================== */
+
 /**
- * The device real-FFT pair of the convolvers on its own, with the reference's saf_rfft conventions
- * (/root/reference/framework/modules/saf_utilities/saf_utility_fft.h saf_rfft_forward / saf_rfft_backward,
- * .c:531-753; KissFFT resources/kissFFT/kiss_fftr.c:69-161): x [nBatch][N] real <-> X [nBatch][N/2+1] interleaved
- * complex, forward unscaled, backward scaled by 1/N and ignoring the imaginary parts of DC and Nyquist.
- * Host pointers; power-of-two 64 <= N <= 16384 (the sizes the convolver engine uses).  Stateless utility /
- * parity-test entry points: every call uploads, transforms and downloads.
+ * Real <-> half-complex FFT of ANY even size N >= 2, replaces saf_rfft_create / _destroy / _forward / _backward
+ * (/root/reference/framework/modules/saf_utilities/saf_utility_fft.h:240-276, .c:531-753; default backend KissFFT:
+ * resources/kissFFT/kiss_fftr.c:69-161, kiss_fft.c:93-331).  inputTD / outputTD: N floats; outputFD / inputFD: N/2+1
+ * interleaved (re, im) pairs = the reference's float_complex* (declared void* here so that C and C++ callers need no
+ * complex type).  Forward unscaled, backward scaled by 1/N and ignoring the imaginary parts of DC and Nyquist.
+ * The handle is a resident device plan (radices 4, 2, 3, 5 + any remaining primes; twiddle tables, work arrays,
+ * page-locked staging, its own stream): a transform call allocates and uploads nothing.  Host pointers, synchronous.
+ * Without a CUDA device *phFFT = NULL (safconv_last_error_string(NULL) says why); forward / backward on NULL are no-ops.
+ */
+void saf_rfft_create(void** const phFFT, int N);
+void saf_rfft_destroy(void** const phFFT);
+void saf_rfft_forward(void* const hFFT, float* inputTD, void* outputFD);
+void saf_rfft_backward(void* const hFFT, void* inputFD, float* outputTD);
+
+/** Extension: nBatch transforms in one call on a saf_rfft handle (dir 0: in [nBatch][N] real -> out [nBatch][N/2+1] complex;
+ *  dir 1: the inverse); the handle's buffers grow to the largest batch seen.  Returns SAFCONV_OK or an error code. */
+int safconv_rfft_batch(void* hFFT, int dir, int nBatch, const float* in, float* out);
+int         safconv_rfft_last_error(void* hFFT);
+const char* safconv_rfft_last_error_string(void* hFFT);
+/** Radices of the handle's plan in pass order (fills fac[0..min(cap, n))), returns n. */
+int safconv_rfft_get_factors(void* hFFT, int* fac, int cap);
+
+/**
+ * Stateless convenience forms (create a plan, transform nBatch signals, destroy): x [nBatch][N] real <-> X [nBatch][N/2+1]
+ * interleaved complex, saf_rfft conventions, host pointers, any even N.
  */
 int  safconv_rfft_forward(int N, int nBatch, const float* x, float* X);
 int  safconv_rfft_backward(int N, int nBatch, const float* X, float* x);

@@ -13,6 +13,8 @@ from ._capi import (  # noqa: F401
     SafConvError,
     MatrixConv,
     MultiConv,
+    RFFT,
+    convolver_rfft,
     TVConv,
     build,
     fftconv,
@@ -25,4 +27,4 @@ from ._capi import (  # noqa: F401
 from . import synth  # noqa: F401
 from . import sharding  # noqa: F401
 
-__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "build", "fftconv", "fftfilt", "rfft_forward", "rfft_backward", "lib", "version", "synth", "sharding"]
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "RFFT", "convolver_rfft", "build", "fftconv", "fftfilt", "rfft_forward", "rfft_backward", "lib", "version", "synth", "sharding"]

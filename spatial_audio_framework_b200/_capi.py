@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = [
     "safconv_get_offline_times",
     "safconv_fftconv", "safconv_fftfilt", "fftconv", "fftfilt",
     "safconv_rfft_forward", "safconv_rfft_backward",
+    "saf_rfft_create", "saf_rfft_destroy", "saf_rfft_forward", "saf_rfft_backward",
+    "safconv_rfft_batch", "safconv_rfft_last_error", "safconv_rfft_last_error_string", "safconv_rfft_get_factors",
 ]
 
 
@@ -123,6 +125,19 @@ def lib():
     L.safconv_render_offline_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.safconv_render_offline_segment_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.safconv_get_offline_times.argtypes = [C.c_void_p, _f32p]
+    L.saf_rfft_create.argtypes = [_vpp, C.c_int]
+    L.saf_rfft_destroy.argtypes = [_vpp]
+    L.saf_rfft_forward.argtypes = [C.c_void_p, _f32p, C.c_void_p]
+    L.saf_rfft_backward.argtypes = [C.c_void_p, C.c_void_p, _f32p]
+    for f in ("saf_rfft_create", "saf_rfft_destroy", "saf_rfft_forward", "saf_rfft_backward"):
+        getattr(L, f).restype = None
+    L.safconv_rfft_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p]
+    L.safconv_rfft_last_error.argtypes = [C.c_void_p]
+    L.safconv_rfft_last_error_string.argtypes = [C.c_void_p]
+    L.safconv_rfft_last_error_string.restype = C.c_char_p
+    L.safconv_rfft_get_factors.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    L.safconv_debug_fft_factors.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.safconv_debug_convolver_rfft.argtypes = [C.c_int, C.c_int, _f32p, _f32p, C.c_int]
     _lib = L
     return L
 
@@ -442,3 +457,86 @@ def rfft_backward(X: np.ndarray) -> np.ndarray:
     if rc:
         raise RuntimeError("rfft_backward failed (%d)" % rc)
     return x
+
+
+class RFFT:
+    """saf_rfft_create / forward / backward / destroy (reference saf_utility_fft.h:240-276): any even N, resident plan."""
+
+    def __init__(self, N: int, device: int | None = None):
+        self._lib = lib()
+        self.N = int(N)
+        self._h = C.c_void_p()
+        if device is not None:
+            self._lib.safconv_set_device(int(device))
+        self._lib.saf_rfft_create(C.byref(self._h), self.N)
+        if not self._h:
+            raise SafConvError("saf_rfft_create failed: " + self._lib.safconv_last_error_string(None).decode())
+
+    def factors(self):
+        buf = (C.c_int * 32)()
+        n = self._lib.safconv_rfft_get_factors(self._h, buf, 32)
+        return [buf[i] for i in range(n)]
+
+    def forward(self, x: np.ndarray) -> np.ndarray:
+        """x [N] or [batch, N] real -> complex64 [N/2+1] or [batch, N/2+1]"""
+        x2 = np.ascontiguousarray(np.atleast_2d(x), np.float32)
+        nb = x2.shape[0]
+        assert x2.shape[1] == self.N
+        X = np.empty((nb, self.N // 2 + 1, 2), np.float32)
+        if nb == 1:
+            self._lib.saf_rfft_forward(self._h, _fp(x2), X.ctypes.data_as(C.c_void_p))
+            rc = self._lib.safconv_rfft_last_error(self._h)
+        else:
+            rc = self._lib.safconv_rfft_batch(self._h, 0, nb, _fp(x2), _fp(X))
+        if rc:
+            raise SafConvError(self._lib.safconv_rfft_last_error_string(self._h).decode())
+        Xc = X[..., 0] + 1j * X[..., 1]
+        return Xc[0] if np.ndim(x) == 1 else Xc
+
+    def backward(self, X: np.ndarray) -> np.ndarray:
+        X2 = np.atleast_2d(np.asarray(X, np.complex64))
+        nb = X2.shape[0]
+        assert X2.shape[1] == self.N // 2 + 1
+        Xi = np.ascontiguousarray(np.stack([X2.real, X2.imag], -1), np.float32)
+        x = np.empty((nb, self.N), np.float32)
+        if nb == 1:
+            self._lib.saf_rfft_backward(self._h, Xi.ctypes.data_as(C.c_void_p), _fp(x))
+            rc = self._lib.safconv_rfft_last_error(self._h)
+        else:
+            rc = self._lib.safconv_rfft_batch(self._h, 1, nb, _fp(Xi), _fp(x))
+        if rc:
+            raise SafConvError(self._lib.safconv_rfft_last_error_string(self._h).decode())
+        return x[0] if np.ndim(X) == 1 else x
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            self._lib.saf_rfft_destroy(C.byref(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def convolver_rfft(x: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """The convolvers' own power-of-two FFT cores on their own (test entry point; N = 64..16384)."""
+    L = lib()
+    if not inverse:
+        x = np.ascontiguousarray(np.atleast_2d(x), np.float32)
+        nb, N = x.shape
+        X = np.empty((nb, N // 2 + 1, 2), np.float32)
+        rc = L.safconv_debug_convolver_rfft(N, nb, _fp(x), _fp(X), 0)
+        if rc:
+            raise RuntimeError("convolver rfft failed (%d)" % rc)
+        return X[..., 0] + 1j * X[..., 1]
+    X = np.atleast_2d(np.asarray(x, np.complex64))
+    nb, nbins = X.shape
+    N = 2 * (nbins - 1)
+    Xi = np.ascontiguousarray(np.stack([X.real, X.imag], -1), np.float32)
+    out = np.empty((nb, N), np.float32)
+    rc = L.safconv_debug_convolver_rfft(N, nb, _fp(Xi), _fp(out), 1)
+    if rc:
+        raise RuntimeError("convolver rfft failed (%d)" % rc)
+    return out

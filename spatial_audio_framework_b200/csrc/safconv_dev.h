@@ -165,6 +165,21 @@ int  scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offl
 int  scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* o,
                        const float* d_in, float* d_out, int T, int skip, void** events, void* stream);
 int  scdev_offline_free(scdev_offline* o);
+/* general-size real FFT (any even N): M = N/2 point mixed-radix Stockham FFT + real split (safconv_gfft.cu) */
+#define SC_GFFT_MAX_FACTORS 32
+#define SC_GFFT_SMEM_M      8192     /* up to this M a transform runs inside one CTA (two M-point arrays in shared memory) */
+typedef struct scdev_gfft_plan {
+    int N, M;
+    int nf, fac[SC_GFFT_MAX_FACTORS];   /* radices in pass order, product = M (M = 1: the single "radix" 1)          */
+    void* tw;                           /* device float2[M]      W_M^e                                             */
+    void* stw;                          /* device float2[M/2+1]  W_N^k                                             */
+    void *w0, *w1;                      /* M > SC_GFFT_SMEM_M: device float2[maxBatch][M] ping-pong work arrays     */
+    int maxBatch;
+} scdev_gfft_plan;
+int  scdev_gfft_smem_ok(int M);
+/* dir 0: in [nBatch][N] real -> out [nBatch][N/2+1] complex (unscaled); dir 1: the inverse, scaled by 1/N, imaginary
+ * parts of DC and Nyquist ignored.  Device pointers (one-CTA path: page-locked host memory works too). */
+int  scdev_gfft_run(const scdev_gfft_plan* p, int dir, int nBatch, const float* in, float* out, void* stream);
 /* batch of stand-alone real FFTs (saf_rfft conventions) on device buffers; dir 0 forward, 1 backward */
 int  scdev_rfft(int N, int logM, int nBatch, int dir, const float* d_in, float* d_out, const void* d_tw, void* stream);
 /* build b->wtab (no-op outside 64 <= M <= 1024) */

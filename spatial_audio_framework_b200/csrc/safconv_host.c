@@ -53,6 +53,7 @@ static safconv_handle* as_handle(void* p)
     return (h && h->magic == SAFCONV_MAGIC) ? h : NULL;
 }
 safconv_handle* sch_as_handle(void* p) { return as_handle(p); }
+int sch_thread_device(void) { return tl_device; }
 
 /* ------------------------------------------------------------------------------------------ */
 /*  planning                                                                                    */
@@ -928,8 +929,9 @@ int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int n
     return SAFCONV_OK;
 }
 
-/* ---- stand-alone real FFT (reference saf_rfft_*, saf_utility_fft.c:531-753), power-of-two N ---- */
-static int rfft_impl(int N, int nBatch, const float* in, float* out, int dir)
+/* ---- the CONVOLVERS' FFT cores on their own (power-of-two N, saf_rfft conventions): test entry point, not in the public
+ * header.  The public saf_rfft_* / safconv_rfft_* API (any even N) lives in safconv_rfft.c. ---- */
+int safconv_debug_convolver_rfft(int N, int nBatch, const float* in, float* out, int dir)
 {
     tl_err = 0; tl_msg[0] = 0;
     if (N < 64 || N > 2 * SC_MAX_M || (N & (N - 1)) || nBatch < 1 || !in || !out) {
@@ -970,8 +972,6 @@ static int rfft_impl(int N, int nBatch, const float* in, float* out, int dir)
     return SAFCONV_OK;
 }
 
-int safconv_rfft_forward(int N, int nBatch, const float* x, float* X)  { return rfft_impl(N, nBatch, x, X, 0); }
-int safconv_rfft_backward(int N, int nBatch, const float* X, float* x) { return rfft_impl(N, nBatch, X, x, 1); }
 
 /* ---- fftconv / fftfilt (reference saf_utility_fft.c:157-228) on the multiConv engine ---- */
 static int fftconv_impl(const float* x, const float* h, int x_len, int h_len, int nCH, float* y, int keep)

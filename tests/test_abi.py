@@ -114,7 +114,10 @@ def test_helpers_fail_loudly_without_device(saf):
     # invalid arguments
     assert lib.safconv_fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), 0, 9, 2, y.ctypes.data_as(fp)) == 1
     X = np.zeros((1, 49, 2), np.float32)
-    assert lib.safconv_rfft_forward(96, 1, x.ctypes.data_as(fp), X.ctypes.data_as(fp)) == 1      # not a power of two
+    assert lib.safconv_rfft_forward(97, 1, x.ctypes.data_as(fp), X.ctypes.data_as(fp)) == 1      # odd sizes are illegal (reference .c:542)
+    hf = C.c_void_p(9)
+    lib.saf_rfft_create(C.byref(hf), 97)
+    assert not hf.value and b"even" in lib.safconv_last_error_string(None)
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     rc = lib.safconv_fftconv(x.ctypes.data_as(fp), h.ctypes.data_as(fp), 100, 9, 2, y.ctypes.data_as(fp))
@@ -124,6 +127,8 @@ def test_helpers_fail_loudly_without_device(saf):
         pkg.fftconv(x, h)
     with pytest.raises(RuntimeError):
         pkg.rfft_forward(np.zeros((1, 64), np.float32))
+    with pytest.raises(saf.SafConvError, match="no usable CUDA device"):
+        pkg.RFFT(1280)
 
 
 def test_product_does_not_reference_oracle():

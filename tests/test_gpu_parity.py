@@ -647,9 +647,10 @@ def test_fftconv_fftfilt_vs_oracle(saf, orc, nCH, xl, hl):
 
 
 def test_rfft_pair_vs_golden_and_oracle(saf, orc):
-    """The device real-FFT pair on its own (safconv_rfft_forward / _backward) against the
+    """The CONVOLVERS' own power-of-two FFT cores on their own (safconv_fft.cuh through the debug entry point) against the
     reference's saf_rfft golden vectors (tests/golden/rfft_*.npz, power-of-two sizes) and the oracle's KissFFT
-    restatement on random batches; round trip like the reference's own test__saf_rfft (<= 1e-5)."""
+    restatement on random batches; round trip like the reference's own test__saf_rfft (<= 1e-5).  The public saf_rfft_*
+    API (any even N, general mixed-radix engine) is tested in tests/test_gpu_rfft.py."""
     import spatial_audio_framework_b200 as pkg
     from conftest import golden_files
     seen = 0
@@ -660,21 +661,21 @@ def test_rfft_pair_vs_golden_and_oracle(saf, orc):
             continue
         seen += 1
         Xref = g["X"].astype(np.float32).reshape(-1, 2)
-        X = pkg.rfft_forward(g["x"][None, :])[0]
+        X = pkg.convolver_rfft(g["x"][None, :])[0]
         err = np.abs(X - (Xref[:, 0] + 1j * Xref[:, 1])).max() / np.abs(Xref).max()
         assert err <= 1e-6, (f, err)
-        xb = pkg.rfft_backward((Xref[:, 0] + 1j * Xref[:, 1])[None, :])[0]
+        xb = pkg.convolver_rfft((Xref[:, 0] + 1j * Xref[:, 1])[None, :], inverse=True)[0]
         assert np.abs(xb - g["xb"]).max() <= 1e-6 * max(np.abs(g["xb"]).max(), 1.0), f
     assert seen >= 3
     rng = np.random.default_rng(12)
     for N in (64, 128, 512, 1024, 2048, 4096, 16384):
         x = rng.uniform(-1, 1, (5, N)).astype(np.float32)
-        X = pkg.rfft_forward(x)
+        X = pkg.convolver_rfft(x)
         for b in (0, 4):
             Xo, _ = orc.oracle_rfft(N, x[b])
             Xo = Xo.reshape(-1, 2)
             Xo = Xo[:, 0] + 1j * Xo[:, 1]
             l2 = np.linalg.norm(X[b] - Xo) / np.linalg.norm(Xo)
             assert l2 <= 1e-6, (N, b, l2)
-        xr = pkg.rfft_backward(X)
+        xr = pkg.convolver_rfft(X, inverse=True)
         assert np.abs(xr - x).max() <= 1e-5, N              # the reference's own criterion (test__utilities_module.c:381-404)
