@@ -92,6 +92,16 @@ void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int
 /*                 Extension block (not present in the reference)             */
 /* ========================================================================== */
 
+/**
+ * usePartFLAG = 0 with the reference's TRUE non-partitioned semantics (saf_utility_matrixConv.c:71-96, 174-207; multi
+ * :277-298, 368-386): one FFT of numOvrlpAddBlocks * hopSize points (generally not a power of two) per block and channel
+ * and a fftSize-long shifting overlap-add buffer, on the general-size device FFT.  Off by default -- the partitioned
+ * engine then serves both flags (same causal linear convolution, equal to rounding).  Process-wide switch read by the next
+ * saf_matrixConv_create / saf_multiConv_create; also SAFCONV_TRUE_MODE0=1 in the environment.  Handles built this way
+ * work with apply / destroy, safconv_last_error[_string], safconv_get_info, safconv_reset_state.
+ */
+int safconv_set_true_mode0(int enable);
+
 /** Error codes stored per handle / per thread. 0 means OK. */
 enum {
     SAFCONV_OK            = 0,

@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = [
     "safconv_get_offline_times",
     "safconv_fftconv", "safconv_fftfilt", "fftconv", "fftfilt",
     "safconv_rfft_forward", "safconv_rfft_backward",
+    "safconv_set_true_mode0",
     "saf_rfft_create", "saf_rfft_destroy", "saf_rfft_forward", "saf_rfft_backward",
     "safconv_rfft_batch", "safconv_rfft_last_error", "safconv_rfft_last_error_string", "safconv_rfft_get_factors",
 ]

@@ -180,6 +180,10 @@ int  scdev_gfft_smem_ok(int M);
 /* dir 0: in [nBatch][N] real -> out [nBatch][N/2+1] complex (unscaled); dir 1: the inverse, scaled by 1/N, imaginary
  * parts of DC and Nyquist ignored.  Device pointers (one-CTA path: page-locked host memory works too). */
 int  scdev_gfft_run(const scdev_gfft_plan* p, int dir, int nBatch, const float* in, float* out, void* stream);
+/* true non-partitioned convolvers: zero-pad rows, per-bin products (matrix: summed over inputs), shifting overlap-add */
+int  scdev_np_pad(const float* in, float* xpad, int rows, int len, int F, size_t inStride, void* stream);
+int  scdev_np_mac(const void* H, const void* X, void* Z, int nOut, int nIn, int nBins, int multi, void* stream);
+int  scdev_np_ola(const float* z, const float* ovOld, float* ovNew, float* out, int nOut, int hop, int F, void* stream);
 /* batch of stand-alone real FFTs (saf_rfft conventions) on device buffers; dir 0 forward, 1 backward */
 int  scdev_rfft(int N, int logM, int nBatch, int dir, const float* d_in, float* d_out, const void* d_tw, void* stream);
 /* build b->wtab (no-op outside 64 <= M <= 1024) */

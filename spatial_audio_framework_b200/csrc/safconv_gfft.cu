@@ -144,7 +144,80 @@ static int gfft_launch_pass(const GfftPassArgs& p, int nBatch, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/*  true non-partitioned convolvers (reference saf_utility_matrixConv.c:174-207, 368-386): ONE FFT of      */
+/*  fftSize = numOvrlpAddBlocks * hop per block and channel, per-bin products, fftSize-long overlap-add    */
+/* ------------------------------------------------------------------------------------------ */
+
+/* rows of `len` samples (row r at in + r*inStride) -> zero-padded rows of F samples (.c:177, .c:91, .c:371) */
+__global__ void np_pad_kernel(const float* __restrict__ in, float* __restrict__ xpad, int len, int F, size_t inStride)
+{
+    const float* src = in + (size_t)blockIdx.y * inStride;
+    float* dst = xpad + (size_t)blockIdx.y * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) dst[i] = (i < len) ? src[i] : 0.f;
+}
+
+/* Z[no][k] = sum_ni H[no][ni][k] * X[ni][k]  (matrix; the reference multiplies (.c:186) and sums AFTER nIn inverse
+ * FFTs (.c:192-195) -- the inverse FFT is linear, so summing per bin first gives the same result with one inverse FFT
+ * per output);  multi: Z[c][k] = H[c][k] * X[c][k] (.c:378).  grid (ceil(nBins/256), nOut) */
+__global__ void np_mac_kernel(const float2* __restrict__ H, const float2* __restrict__ X, float2* __restrict__ Z,
+                              int nIn, int nBins, int multi)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nBins) return;
+    const int no = blockIdx.y;
+    if (multi) {
+        Z[(size_t)no * nBins + k] = gf_mul(H[(size_t)no * nBins + k], X[(size_t)no * nBins + k]);
+        return;
+    }
+    const float2* h = H + (size_t)no * nIn * nBins + k;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int ni = 0; ni < nIn; ++ni) {
+        const float2 a = h[(size_t)ni * nBins], x = X[(size_t)ni * nBins + k];
+        acc.x = fmaf(a.x, x.x, acc.x); acc.x = fmaf(-a.y, x.y, acc.x);
+        acc.y = fmaf(a.x, x.y, acc.y); acc.y = fmaf(a.y, x.x, acc.y);
+    }
+    Z[(size_t)no * nBins + k] = acc;
+}
+
+/* shift the overlap-add buffer by one hop, add the new fftSize-long block, emit the first hop samples (.c:198-205):
+ * ovNew[i] = (i + hop < F ? ovOld[i + hop] : 0) + z[i];  out[i < hop] = ovNew[i].  grid (ceil(F/256), nOut) */
+__global__ void np_ola_kernel(const float* __restrict__ z, const float* __restrict__ ovOld, float* __restrict__ ovNew,
+                              float* __restrict__ out, int hop, int F)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    const size_t row = (size_t)blockIdx.y * F;
+    const float v = ((i + hop < F) ? ovOld[row + i + hop] : 0.f) + z[row + i];
+    ovNew[row + i] = v;
+    if (i < hop) out[(size_t)blockIdx.y * hop + i] = v;
+}
+
 extern "C" {
+
+int scdev_np_pad(const float* in, float* xpad, int rows, int len, int F, size_t inStride, void* stream)
+{
+    if (rows < 1) return 0;
+    if (rows > 65535) return (int)cudaErrorInvalidValue;
+    int gx = (F + 255) / 256; if (gx > 64) gx = 64;
+    np_pad_kernel<<<dim3(gx, rows), 256, 0, (cudaStream_t)stream>>>(in, xpad, len, F, inStride);
+    return (int)cudaGetLastError();
+}
+
+int scdev_np_mac(const void* H, const void* X, void* Z, int nOut, int nIn, int nBins, int multi, void* stream)
+{
+    if (nOut > 65535) return (int)cudaErrorInvalidValue;
+    np_mac_kernel<<<dim3((nBins + 255) / 256, nOut), 256, 0, (cudaStream_t)stream>>>((const float2*)H, (const float2*)X, (float2*)Z, nIn, nBins, multi);
+    return (int)cudaGetLastError();
+}
+
+int scdev_np_ola(const float* z, const float* ovOld, float* ovNew, float* out, int nOut, int hop, int F, void* stream)
+{
+    if (nOut > 65535) return (int)cudaErrorInvalidValue;
+    np_ola_kernel<<<dim3((F + 255) / 256, nOut), 256, 0, (cudaStream_t)stream>>>(z, ovOld, ovNew, out, hop, F);
+    return (int)cudaGetLastError();
+}
 
 int scdev_gfft_smem_ok(int M) { return M >= 1 && M <= SC_GFFT_SMEM_M; }
 

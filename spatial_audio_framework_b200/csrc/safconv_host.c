@@ -464,6 +464,7 @@ static void conv_destroy(void** const ph)
 {
     if (!ph) return;
     if (scm_is_multi(*ph)) { scm_destroy(ph); return; }
+    if (scn_is_np(*ph)) { scn_destroy(ph); return; }
     safconv_handle* h = as_handle(*ph);
     if (h) handle_free(h);
     *ph = NULL;
@@ -775,8 +776,13 @@ void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx
 
 void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCHin, int nCHout, int usePartFLAG)
 {
-    (void)usePartFLAG;   /* both reference modes compute the same linear convolution; one engine serves both */
+    /* both reference modes compute the same linear convolution; the partitioned engine serves both unless the true
+     * big-FFT semantics of mode 0 are asked for (safconv_np.c) */
     if (!phMC) return;
+    if (!usePartFLAG && scn_enabled()) {
+        *phMC = scn_create(SC_KIND_MATRIX, hopSize, H, length_h, nCHin, nCHout);
+        if (*phMC || tl_err) return;                     /* built, or failed for a real reason; odd fftSize falls through */
+    }
     if (H && getenv("SAFCONV_DEVICES") && (*phMC = scm_create_from_env(SC_KIND_MATRIX, hopSize, H, length_h, nCHin, nCHout)) != NULL) return;
     const float* chunk = H;
     *phMC = conv_create(SC_KIND_MATRIX, hopSize, H ? &chunk : NULL, 1,
@@ -817,6 +823,7 @@ void saf_matrixConv_destroy(void** const phMC) { conv_destroy(phMC); }
 void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 {
     if (scm_is_multi(hMC)) { scm_apply(hMC, SC_KIND_MATRIX, inputSigs, outputSigs); return; }
+    if (scn_is_np(hMC)) { scn_apply(hMC, SC_KIND_MATRIX, inputSigs, outputSigs); return; }
     safconv_handle* h = as_handle(hMC);
     if (!h || h->pl.kind != SC_KIND_MATRIX || !inputSigs || !outputSigs) return;
     conv_apply_host(h, inputSigs, outputSigs, 0);
@@ -824,8 +831,11 @@ void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 
 void saf_multiConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCH, int usePartFLAG)
 {
-    (void)usePartFLAG;
     if (!phMC) return;
+    if (!usePartFLAG && scn_enabled()) {
+        *phMC = scn_create(SC_KIND_MULTI, hopSize, H, length_h, nCH, nCH);
+        if (*phMC || tl_err) return;
+    }
     if (H && getenv("SAFCONV_DEVICES") && (*phMC = scm_create_from_env(SC_KIND_MULTI, hopSize, H, length_h, nCH, nCH)) != NULL) return;
     const float* chunk = H;
     *phMC = conv_create(SC_KIND_MULTI, hopSize, H ? &chunk : NULL, 1, (size_t)(nCH > 0 ? nCH : 0),
@@ -850,6 +860,7 @@ void saf_multiConv_destroy(void** const phMC) { conv_destroy(phMC); }
 void saf_multiConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 {
     if (scm_is_multi(hMC)) { scm_apply(hMC, SC_KIND_MULTI, inputSigs, outputSigs); return; }
+    if (scn_is_np(hMC)) { scn_apply(hMC, SC_KIND_MULTI, inputSigs, outputSigs); return; }
     safconv_handle* h = as_handle(hMC);
     if (!h || h->pl.kind != SC_KIND_MULTI || !inputSigs || !outputSigs) return;
     conv_apply_host(h, inputSigs, outputSigs, 0);
@@ -885,6 +896,7 @@ void saf_TVConv_apply(void* const hTVC, float* inputSigs, float* outputSigs, int
 int safconv_last_error(void* hp)
 {
     if (scm_is_multi(hp)) return scm_last_error(hp);
+    if (scn_is_np(hp)) return scn_last_error(hp);
     safconv_handle* h = as_handle(hp);
     return h ? h->err : tl_err;
 }
@@ -892,6 +904,7 @@ int safconv_last_error(void* hp)
 const char* safconv_last_error_string(void* hp)
 {
     if (scm_is_multi(hp)) return scm_last_error_string(hp);
+    if (scn_is_np(hp)) return scn_last_error_string(hp);
     safconv_handle* h = as_handle(hp);
     return h ? h->errmsg : tl_msg;
 }
@@ -1170,6 +1183,7 @@ void* safconv_get_stream(void* hp)
 int safconv_synchronize(void* hp)
 {
     if (scm_is_multi(hp)) return scm_synchronize(hp);
+    if (scn_is_np(hp)) return SAFCONV_OK;                /* its apply is synchronous and nothing else enqueues work */
     safconv_handle* h = as_handle(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
@@ -1180,6 +1194,7 @@ int safconv_synchronize(void* hp)
 int safconv_reset_state(void* hp)
 {
     if (scm_is_multi(hp)) return scm_reset_state(hp);
+    if (scn_is_np(hp)) return scn_reset_state(hp);
     safconv_handle* h = as_handle(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
@@ -1196,6 +1211,7 @@ int safconv_reset_state(void* hp)
 int safconv_get_info(void* hp, safconv_info* info)
 {
     if (scm_is_multi(hp)) return scm_get_info(hp, info);
+    if (scn_is_np(hp)) return scn_get_info(hp, info);
     safconv_handle* h = as_handle(hp);
     if (!h || !info) return SAFCONV_ERR_ARG;
     const scdev_plan* pl = &h->pl;

@@ -90,6 +90,23 @@ SC_HIDDEN void sch_apply_pinned(safconv_handle* h, const float* src, float* dst,
 SC_HIDDEN int  sch_apply_lookahead_io(safconv_handle* h, const sch_la_io* io);
 SC_HIDDEN int  sch_uses_lookahead(const safconv_handle* h);
 
+/* safconv_rfft.c: plans of the general-size real FFT */
+SC_HIDDEN int  scr_plan_init(scdev_gfft_plan* pl, int N, void* stream);
+SC_HIDDEN int  scr_plan_reserve(scdev_gfft_plan* pl, int nBatch);
+SC_HIDDEN void scr_plan_free(scdev_gfft_plan* pl);
+int safconv_debug_fft_factors(int M, int* fac, int cap);
+
+/* safconv_np.c: true non-partitioned convolvers (one big FFT per block) */
+SC_HIDDEN int   scn_is_np(const void* p);
+SC_HIDDEN int   scn_enabled(void);
+SC_HIDDEN void* scn_create(int kind, int hop, const float* H, int len, int nIn, int nOut);
+SC_HIDDEN void  scn_apply(void* p, int kind, const float* in, float* out);
+SC_HIDDEN void  scn_destroy(void** pp);
+SC_HIDDEN int   scn_last_error(void* p);
+SC_HIDDEN const char* scn_last_error_string(void* p);
+SC_HIDDEN int   scn_get_info(void* p, safconv_info* info);
+SC_HIDDEN int   scn_reset_state(void* p);
+
 /* safconv_multi.c */
 SC_HIDDEN int   scm_is_multi(const void* p);
 SC_HIDDEN void  scm_apply(void* p, int kind, const float* in, float* out);

@@ -70,12 +70,62 @@ int safconv_debug_fft_factors(int M, int* fac, int cap)
     return nf;
 }
 
+/* plan of an N-point real FFT: radices of N/2 + the two twiddle tables on the current device.  Returns 0, a CUDA error
+ * code, or -1 (host memory / more than SC_GFFT_MAX_FACTORS prime factors). */
+int scr_plan_init(scdev_gfft_plan* pl, int N, void* stream)
+{
+    const int M = N / 2;
+    memset(pl, 0, sizeof *pl);
+    pl->N = N; pl->M = M;
+    pl->nf = safconv_debug_fft_factors(M, pl->fac, SC_GFFT_MAX_FACTORS);
+    if (pl->nf < 1) return -1;
+    /* tables: W_M^e (e < M) and W_N^k (k <= M/2), evaluated in double like kiss_fft.c:358-364 / kiss_fftr.c:59-65 */
+    const size_t nS = (size_t)M / 2 + 1;
+    float* t = (float*)malloc(sizeof(float) * 2 * ((size_t)M + nS));
+    if (!t) return -1;
+    const double pi = 3.141592653589793238462643383279502884;
+    for (int i = 0; i < M; i++) {
+        const double ph = -2.0 * pi * (double)i / (double)M;
+        t[2 * i] = (float)cos(ph); t[2 * i + 1] = (float)sin(ph);
+    }
+    float* s = t + 2 * (size_t)M;
+    for (size_t k = 0; k < nS; k++) {
+        const double ph = -2.0 * pi * (double)k / (double)N;
+        s[2 * k] = (float)cos(ph); s[2 * k + 1] = (float)sin(ph);
+    }
+    int e = scdev_malloc(&pl->tw, sizeof(float) * 2 * (size_t)M);
+    if (!e) e = scdev_malloc(&pl->stw, sizeof(float) * 2 * nS);
+    if (!e) e = scdev_memcpy_h2d_sync(pl->tw, t, sizeof(float) * 2 * (size_t)M, stream);
+    if (!e) e = scdev_memcpy_h2d_sync(pl->stw, s, sizeof(float) * 2 * nS, stream);
+    free(t);
+    return e;
+}
+
+/* work arrays of the multi-launch path for batches of up to nBatch transforms (no-op for one-CTA sizes) */
+int scr_plan_reserve(scdev_gfft_plan* pl, int nBatch)
+{
+    if (scdev_gfft_smem_ok(pl->M)) { if (nBatch > pl->maxBatch) pl->maxBatch = nBatch; return 0; }
+    if (nBatch <= pl->maxBatch) return 0;
+    scdev_free(pl->w0); scdev_free(pl->w1);
+    pl->w0 = pl->w1 = NULL; pl->maxBatch = 0;
+    int e = scdev_malloc(&pl->w0, sizeof(float) * 2 * (size_t)pl->M * nBatch);
+    if (!e) e = scdev_malloc(&pl->w1, sizeof(float) * 2 * (size_t)pl->M * nBatch);
+    if (!e) pl->maxBatch = nBatch;
+    return e;
+}
+
+void scr_plan_free(scdev_gfft_plan* pl)
+{
+    scdev_free(pl->tw); scdev_free(pl->stw); scdev_free(pl->w0); scdev_free(pl->w1);
+    memset(pl, 0, sizeof *pl);
+}
+
 static void rfft_free(safconv_rfft* h)
 {
     if (!h) return;
     if (h->device >= 0) scdev_set_device(h->device);
     if (h->stream) scdev_stream_sync(h->stream);
-    scdev_free(h->pl.tw); scdev_free(h->pl.stw); scdev_free(h->pl.w0); scdev_free(h->pl.w1);
+    scr_plan_free(&h->pl);
     scdev_free(h->d_td); scdev_free(h->d_fd);
     scdev_host_free(h->h_td); scdev_host_free(h->h_fd);
     scdev_stream_destroy(h->stream);
@@ -90,18 +140,14 @@ static int rfft_reserve(safconv_rfft* h, int nBatch)
     const size_t N = (size_t)h->pl.N, M = (size_t)h->pl.M;
     scdev_stream_sync(h->stream);
     scdev_free(h->d_td); scdev_free(h->d_fd); scdev_host_free(h->h_td); scdev_host_free(h->h_fd);
-    scdev_free(h->pl.w0); scdev_free(h->pl.w1);
-    h->d_td = h->d_fd = h->h_td = h->h_fd = NULL; h->pl.w0 = h->pl.w1 = NULL; h->capBatch = 0; h->pl.maxBatch = 0;
+    h->d_td = h->d_fd = h->h_td = h->h_fd = NULL; h->capBatch = 0;
     int e = scdev_malloc((void**)&h->d_td, sizeof(float) * N * nBatch);
     if (!e) e = scdev_malloc((void**)&h->d_fd, sizeof(float) * 2 * (M + 1) * nBatch);
     if (!e) e = scdev_host_alloc((void**)&h->h_td, sizeof(float) * N * nBatch);
     if (!e) e = scdev_host_alloc((void**)&h->h_fd, sizeof(float) * 2 * (M + 1) * nBatch);
-    if (!e && !scdev_gfft_smem_ok(h->pl.M)) {
-        e = scdev_malloc(&h->pl.w0, sizeof(float) * 2 * M * nBatch);
-        if (!e) e = scdev_malloc(&h->pl.w1, sizeof(float) * 2 * M * nBatch);
-    }
+    if (!e) e = scr_plan_reserve(&h->pl, nBatch);
     if (e) return r_fail(h, SAFCONV_ERR_NOMEM, "rfft buffers", e);
-    h->capBatch = nBatch; h->pl.maxBatch = nBatch;
+    h->capBatch = nBatch;
     return 0;
 }
 
@@ -127,34 +173,10 @@ static safconv_rfft* rfft_create(int N, int nBatch)
     if (!e) e = scdev_set_device(dev);
     if (e) { r_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); rfft_free(h); return NULL; }
     h->device = dev;
-    const int M = N / 2;
-    h->pl.N = N; h->pl.M = M;
-    h->pl.nf = safconv_debug_fft_factors(M, h->pl.fac, SC_GFFT_MAX_FACTORS);
-    if (h->pl.nf < 1) { r_fail(h, SAFCONV_ERR_ARG, "rfft: too many prime factors", 0); rfft_free(h); return NULL; }
     e = scdev_stream_create(&h->stream);
     if (e) { r_fail(h, SAFCONV_ERR_CUDA, "cudaStreamCreate", e); rfft_free(h); return NULL; }
-    /* tables: W_M^e (e < M) and W_N^k (k <= M/2), evaluated in double like kiss_fft.c:358-364 / kiss_fftr.c:59-65 */
-    {
-        const size_t nS = (size_t)M / 2 + 1;
-        float* t = (float*)malloc(sizeof(float) * 2 * ((size_t)M + nS));
-        if (!t) { r_fail(h, SAFCONV_ERR_NOMEM, "rfft twiddle tables", 0); rfft_free(h); return NULL; }
-        const double pi = 3.141592653589793238462643383279502884;
-        for (int i = 0; i < M; i++) {
-            const double ph = -2.0 * pi * (double)i / (double)M;
-            t[2 * i] = (float)cos(ph); t[2 * i + 1] = (float)sin(ph);
-        }
-        float* s = t + 2 * (size_t)M;
-        for (size_t k = 0; k < nS; k++) {
-            const double ph = -2.0 * pi * (double)k / (double)N;
-            s[2 * k] = (float)cos(ph); s[2 * k + 1] = (float)sin(ph);
-        }
-        e = scdev_malloc(&h->pl.tw, sizeof(float) * 2 * (size_t)M);
-        if (!e) e = scdev_malloc(&h->pl.stw, sizeof(float) * 2 * nS);
-        if (!e) e = scdev_memcpy_h2d_sync(h->pl.tw, t, sizeof(float) * 2 * (size_t)M, h->stream);
-        if (!e) e = scdev_memcpy_h2d_sync(h->pl.stw, s, sizeof(float) * 2 * nS, h->stream);
-        free(t);
-        if (e) { r_fail(h, SAFCONV_ERR_CUDA, "rfft twiddle upload", e); rfft_free(h); return NULL; }
-    }
+    e = scr_plan_init(&h->pl, N, h->stream);
+    if (e) { r_fail(h, e < 0 ? SAFCONV_ERR_NOMEM : SAFCONV_ERR_CUDA, "rfft plan (factors / twiddle tables)", e < 0 ? 0 : e); rfft_free(h); return NULL; }
     if (rfft_reserve(h, nBatch)) { rfft_free(h); return NULL; }
     return h;
 }
