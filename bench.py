@@ -561,6 +561,37 @@ def latency_config(name, args, dev):
             "parity": chk, "cpu_baseline": cpu}
 
 
+def tvconv_latency(args, dev):
+    """secondary block: saf_TVConv_apply (reference saf_utility_matrixConv.c:546-620) through the host-pointer drop-in call,
+    the impulse-response set switching every 7 blocks (cross-fades), page-locked caller buffers"""
+    import ctypes as C
+    import torch
+    import spatial_audio_framework_b200 as saf
+    from spatial_audio_framework_b200 import synth
+    out = {}
+    fp = C.POINTER(C.c_float)
+    for name, hop, L, nIRs, nOut, calls in (("hop512", 512, 24000, 16, 4, args.lat_blocks), ("hop8192", 8192, 24000, 16, 4, 300)):
+        H = np.stack([synth.decaying_rir((nOut, L), seed=100 + i) for i in range(nIRs)])
+        tv = saf.TVConv(hop, H, 0, device=dev.index)
+        x = (torch.rand((hop,)) * 2 - 1).pin_memory()
+        y = torch.empty((nOut, hop), dtype=torch.float32).pin_memory()
+        xin, yout = C.cast(x.data_ptr(), fp), C.cast(y.data_ptr(), fp)
+        fn, hdl = tv._lib.saf_TVConv_apply, tv.handle
+        lat = []
+        for k in range(calls + 100):
+            t0 = time.perf_counter()
+            fn(hdl, xin, yout, (k // 7) % nIRs)
+            lat.append(1e3 * (time.perf_counter() - t0))
+        if tv._lib.safconv_last_error(hdl):
+            raise RuntimeError(tv._lib.safconv_last_error_string(hdl).decode())
+        lat = lat[100:]
+        out[name] = {"workload": f"saf_TVConv 1 x {nOut}, hop {hop}, {L} taps, {nIRs} IR sets switched every 7 blocks",
+                     "p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "blocks": calls, "warmup_blocks": 100,
+                     "value": nOut * hop / (1e-3 * float(np.mean(lat))), "unit": UNIT}
+        tv.destroy()
+    return out
+
+
 def run_own_arm(args, w):
     if w["kind"] == "offline":
         return run_offline_arm(args, w)
@@ -763,6 +794,10 @@ def run_own_arm(args, w):
                 secondary[name] = latency_config(name, args, dev)
             except Exception as ex:
                 secondary[name] = {"failed": repr(ex)}
+        try:
+            secondary["TVConv"] = tvconv_latency(args, dev)
+        except Exception as ex:
+            secondary["TVConv"] = {"failed": repr(ex)}
         try:
             a5 = argparse.Namespace(**vars(args))
             a5.steps, a5.warmup, a5.e2e_steps, a5.cpu_steps = 5, 3, 2, 3

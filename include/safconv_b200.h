@@ -40,7 +40,8 @@ extern "C" {
  * (implementation saf_utility_matrixConv.c:49-130).
  *
  * @param phMC        (&) handle; overwritten (NULL on failure)
- * @param hopSize     block length in samples (1..8192; TVConv: 1..4096)
+ * @param hopSize     block length in samples (1..8192 for all three convolvers; larger values are rejected with an
+ *                    error string -- the reference's own hosts clamp their frames to 8192)
  * @param H           time-domain filters, FLAT nCHout x nCHin x length_h; only
  *                    read during this call (caller may free it afterwards)
  * @param usePartFLAG 0/1 as in the reference.  Both modes produce the same causal

@@ -314,7 +314,12 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
                                    int len, int nIn, int nOutLocal, int nOutTotal, int outBegin, int nIRs)
 {
     tl_err = 0; tl_msg[0] = 0;
-    if (hop < 1 || hop > SC_MAX_M || (kind == SC_KIND_TV && hop > SC_MAX_M / 2) || len < 1 || nIn < 1 || nOutLocal < 1 || !chunks) {
+    if (hop > SC_MAX_M) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s: hopSize > 8192 is not supported by this engine (one block's FFT lives in one CTA's "
+                     "shared memory); the reference's own hosts clamp to 8192 (matrixconv_internal.h:40-41, tvconv_internal.h:43-44)", "");
+        return NULL;
+    }
+    if (hop < 1 || len < 1 || nIn < 1 || nOutLocal < 1 || !chunks) {
         set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s (need 1 <= hopSize <= 8192, length_h >= 1, channels >= 1, H != NULL)", "");
         return NULL;
     }
@@ -425,6 +430,8 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         zalloc(h, (void**)&h->b.zt, sizeof(float) * (size_t)pl->maxBatch * nOutLocal * 2 * hop, "batched inverse-transform buffer")) goto fail;
     if (zalloc(h, (void**)&h->b.tail, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails")) goto fail;
     if (kind == SC_KIND_TV && zalloc(h, (void**)&h->b.tail2, sizeof(float) * (size_t)nOutLocal * hop, "overlap tails (last)")) goto fail;
+    if (kind == SC_KIND_TV && pl->M > 4096 &&       /* hop > 4096: the three-launch path keeps its inverse transforms in global memory */
+        zalloc(h, (void**)&h->b.zt, sizeof(float) * 3 * (size_t)nOutLocal * 2 * hop, "TVConv inverse-transform scratch")) goto fail;
     if (zalloc(h, (void**)&h->b.counters, 4 * sizeof(unsigned int), "counters")) goto fail;
 
     h->inBytes  = sizeof(float) * (size_t)nIn * hop;

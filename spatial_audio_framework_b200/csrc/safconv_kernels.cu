@@ -1037,6 +1037,94 @@ __global__ void tv_fused_kernel(TvArgs a)
 }
 
 
+/* ---- TVConv, hop > 4096 (M = 8192): the five work arrays of tv_fused_kernel no longer fit in shared memory, so the
+ * block runs as three launches through a global scratch zt[3][nOut][2*hop] (a block is >= 85 ms of audio here: launch
+ * gaps are irrelevant).  Same arithmetic per bin / per sample as the fused kernel. ---- */
+
+/* grid (1): forward FFT of the input block into ring slot `head` */
+__global__ void tv_input_kernel(TvArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    float2* stw = sm + SC_ALEN(a.M);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    const int head = (int)(a.counters[0] % (unsigned)a.P);
+    load_real_block(sm, a.in, a.hop, a.M, a.logM);
+    __syncthreads();
+    cfft_dif<false>(sm, a.M, a.logM, stw, wide);
+    float2* Xn = a.X + (size_t)head * a.M;
+    for (int k = threadIdx.x; k <= (a.M >> 1); k += blockDim.x) {
+        float2 Xk, Xmk;
+        int k2 = a.M - k;
+        if (k == 0) {
+            const float2 z = sm[0];
+            Xk = make_float2(z.x + z.y, z.x - z.y);
+            k2 = 0; Xmk = Xk;
+        } else {
+            fwd_split_pair(sm, k, a.M, a.logM, spl, Xk, Xmk);
+        }
+        Xn[k] = Xk;  Xn[k2] = Xmk;
+    }
+}
+
+/* grid (nOut, 3): which = 0 / 1 / 2 -> IR set irIdx / posIdx_last / posIdx_last2; sets equal to the previous one are
+ * skipped (reference .c:587, .c:601: the consumer re-uses the earlier result) */
+__global__ void tv_mac_ifft_kernel(TvArgs a, float* zt)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int no = blockIdx.x, which = blockIdx.y;
+    if ((which == 1 && a.ir0 == a.ir1) || (which == 2 && a.ir1 == a.ir2)) return;
+    float2* stw = sm + SC_ALEN(a.M);
+    const bool wide = fft_use_wide(a.M, 1);
+    load_twiddles(stw, a.tw, a.M, a.logM, wide);
+    const float2* spl = load_split_twiddles(stw, a.tw, a.M);
+    const int ir = (which == 0) ? a.ir0 : (which == 1 ? a.ir1 : a.ir2);
+    const int head = (int)(a.counters[0] % (unsigned)a.P);
+    const float2* Hc = a.H + ((size_t)ir * a.nOut + no) * a.P * a.M;
+    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+        const bool packed = (k == 0);
+        float2 z = make_float2(0.f, 0.f);
+        int slot = head;
+#pragma unroll 8
+        for (int p = 0; p < a.P; ++p) {
+            cmac_packed(z, __ldg(Hc + (size_t)p * a.M + k), a.X[(size_t)slot * a.M + k], packed);
+            slot = (slot == 0) ? a.P - 1 : slot - 1;
+        }
+        sm[padi(k, a.logM)] = z;
+    }
+    __syncthreads();
+    inv_split_all(sm, a.M, a.logM, spl);
+    cfft_dif<true>(sm, a.M, a.logM, stw, wide);
+    float* z = zt + ((size_t)which * a.nOut + no) * 2 * a.hop;
+    for (int i = threadIdx.x; i < 2 * a.hop; i += blockDim.x) z[i] = time_sample(sm, i, a.logM) * a.scale;
+}
+
+/* cross-fade + tails (reference .c:494-497, 605-615), one thread per (output, sample); last CTA bumps the counter */
+__global__ void tv_xfade_kernel(TvArgs a, const float* zt)
+{
+    const size_t n = (size_t)a.nOut * a.hop;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) {
+        const int no = (int)(idx / a.hop), i = (int)(idx - (size_t)no * a.hop);
+        const int s1 = (a.ir0 != a.ir1) ? 1 : 0;
+        const int s2 = (a.ir1 != a.ir2) ? 2 : s1;
+        const float* z0 = zt + ((size_t)0 * a.nOut + no) * 2 * a.hop;
+        const float* z1 = zt + ((size_t)s1 * a.nOut + no) * 2 * a.hop;
+        const float* z2 = zt + ((size_t)s2 * a.nOut + no) * 2 * a.hop;
+        const float den = (float)(a.hop - 1);
+        const float fin  = (float)i / den;
+        const float fout = (float)(a.hop - 1 - i) / den;
+        const float o1 = z1[i] + a.tail0[idx];
+        const float o2 = z2[i] + a.tail1[idx];
+        a.out[idx]   = o1 * fin + o2 * fout;
+        a.tail0[idx] = z0[i + a.hop];
+        a.tail1[idx] = z1[i + a.hop];
+    }
+    advance_block_counter(a.counters, gridDim.x);
+}
+
+
 /* ------------------------------------------------------------------------------------------ */
 /*  Stand-alone real FFT pair with the reference's saf_rfft conventions (saf_utility_fft.c:531-753: */
 /*  N/2+1 interleaved complex bins, forward unscaled, backward x 1/N, Im of DC and Nyquist ignored   */
@@ -1425,6 +1513,20 @@ int scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in,
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.P = pl->P; a.nOut = pl->nOutLocal;
     a.ir0 = irIdx; a.ir1 = irLast; a.ir2 = irLast2;
     a.scale = 1.0f / (float)pl->N;
+    if (pl->M > 4096) {
+        /* five M-point arrays do not fit in one CTA's shared memory: input FFT, (output, IR set) transforms, cross-fade */
+        if (!b->zt) return (int)cudaErrorInvalidValue;
+        cudaStream_t st = (cudaStream_t)stream;
+        SC_CHECK(sc_optin_smem(tv_input_kernel));
+        SC_CHECK(sc_optin_smem(tv_mac_ifft_kernel));
+        tv_input_kernel<<<1, pl->fftThreads, fft_smem(pl, 2), st>>>(a);
+        SC_CHECK(cudaGetLastError());
+        tv_mac_ifft_kernel<<<dim3(pl->nOutLocal, 3), 512, fft_smem(pl, 2), st>>>(a, b->zt);
+        SC_CHECK(cudaGetLastError());
+        const size_t n = (size_t)pl->nOutLocal * pl->hop;
+        tv_xfade_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b->zt);
+        return (int)cudaGetLastError();
+    }
     tv_fused_kernel<<<pl->nOutLocal, pl->fftThreads, fft_smem(pl, 5), (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }

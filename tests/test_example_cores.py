@@ -1,5 +1,5 @@
 """Drop-in integration test: the reference's OWN plug-in cores
-examples/src/matrixconv/matrixconv.c and examples/src/multiconv/multiconv.c, compiled UNMODIFIED by
+examples/src/matrixconv/matrixconv.c, examples/src/multiconv/multiconv.c and examples/src/tvconv/tvconv.c, compiled UNMODIFIED by
 oracle/Makefile, once linked with the reference's saf_utility_matrixConv.c (libsaf_ref_examples_ref.so) and
 once with saf_matrixConv_* / saf_multiConv_* resolved from libsafconv_b200.so (libsaf_ref_examples_b200.so).
 Both are driven like a plug-in host would (per-host-block float** audio, FIFO re-blocking to the clamped
@@ -101,16 +101,74 @@ def test_reference_multiconv_core_runs_on_the_b200_library(saf, host_block, part
     assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
 
 
+def _drive_tvconv(lib, irs, positions, host_block, x, walk):
+    """tvconv_create -> (test shim: load IRs + listener positions) -> init -> process host blocks while the target
+    position walks along `walk` (one entry per host block); returns y[nCh, T] and the position index per block."""
+    nPos, nCh, L = irs.shape
+    h = C.c_void_p()
+    lib.tvconv_create.argtypes = [C.POINTER(C.c_void_p)]
+    lib.tvconv_create(C.byref(h))
+    lib.tvconv_testload.argtypes = [C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+    irs = np.ascontiguousarray(irs, np.float32)
+    positions = np.ascontiguousarray(positions, np.float32)
+    lib.tvconv_testload(h, irs.ctypes.data_as(fp), nPos, nCh, L, 48000, positions.ctypes.data_as(fp))
+    lib.tvconv_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.tvconv_init(h, 48000, host_block)
+    lib.tvconv_setTargetPosition.argtypes = [C.c_void_p, C.c_float, C.c_int]
+    lib.tvconv_getListenerPositionIdx.argtypes = [C.c_void_p]
+    lib.tvconv_process.argtypes = [C.c_void_p, fpp, fpp, C.c_int, C.c_int, C.c_int]
+    T = x.shape[1]
+    y = np.zeros((nCh, T), np.float32)
+    idx = []
+    for b in range(T // host_block):
+        lib.tvconv_setTargetPosition(h, float(walk[b]), 0)
+        idx.append(lib.tvconv_getListenerPositionIdx(h))
+        ip, ik = _rows(x[:, b * host_block:(b + 1) * host_block])
+        ob = np.zeros((nCh, host_block), np.float32)
+        op, ok = _rows(ob)
+        lib.tvconv_process(h, ip, op, 1, nCh, host_block)
+        y[:, b * host_block:(b + 1) * host_block] = ok
+    lib.tvconv_destroy.argtypes = [C.POINTER(C.c_void_p)]
+    lib.tvconv_destroy(C.byref(h))
+    return y, idx
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_block,L,nblk", [(512, 3000, 24), (2048, 9000, 10), (8192, 20000, 6), (16384, 5000, 3)])
+def test_reference_tvconv_core_runs_on_the_b200_library(saf, host_block, L, nblk):
+    """examples/src/tvconv/tvconv.c UNMODIFIED on saf_TVConv_* from libsafconv_b200.so vs the same core on the
+    reference's own convolver: frames clamp to [512, 8192] (tvconv_internal.h:43-44) -- 8192-sample frames included --,
+    the listener position (= impulse-response set) changes while audio runs (3-way cross-fade, .c:577-611)."""
+    if not (REF_SO.exists() and B200_SO.exists()):
+        pytest.skip("oracle/_ref example cores not built (need /root/reference at build time)")
+    rng = np.random.default_rng(host_block)
+    nPos, nCh = 6, 4
+    irs = (rng.uniform(-1, 1, (nPos, nCh, L)) * np.exp(-4.0 * np.arange(L) / L)).astype(np.float32)
+    positions = np.zeros((nPos, 3), np.float32)
+    positions[:, 0] = np.arange(nPos)                      # listeners on a line along x
+    T = host_block * nblk
+    x = rng.uniform(-1, 1, (1, T)).astype(np.float32)
+    walk = rng.uniform(-0.4, nPos - 0.6, nblk)
+    walk[1] = walk[0]                                      # a repeated position: no cross-fade for that block
+    y_ref, i_ref = _drive_tvconv(C.CDLL(str(REF_SO)), irs, positions, host_block, x, walk)
+    y_gpu, i_gpu = _drive_tvconv(C.CDLL(str(B200_SO)), irs, positions, host_block, x, walk)
+    assert i_ref == i_gpu and len(set(i_ref)) > 1          # the position really moved
+    assert np.abs(y_ref).max() > 0.5                        # the convolver really ran
+    ma, l2 = err_metrics(y_gpu, y_ref)
+    assert ma <= TOL_MAXABS_FS and l2 <= TOL_REL_L2, (ma, l2)
+
+
 def test_example_core_libraries_export_the_reference_api():
     if not (REF_SO.exists() and B200_SO.exists()):
         pytest.skip("oracle/_ref example cores not built")
     import subprocess
     for so in (REF_SO, B200_SO):
         syms = subprocess.run(["nm", "-D", str(so)], capture_output=True, text=True).stdout
-        for s in ("matrixconv_create", "matrixconv_process", "matrixconv_setFilters", "multiconv_create", "multiconv_process"):
+        for s in ("matrixconv_create", "matrixconv_process", "matrixconv_setFilters", "multiconv_create", "multiconv_process",
+                  "tvconv_create", "tvconv_process", "tvconv_setTargetPosition"):
             assert s in syms
     # the b200 flavour takes the convolver from the product library, the ref flavour carries its own
     u = subprocess.run(["nm", "-D", "--undefined-only", str(B200_SO)], capture_output=True, text=True).stdout
-    assert "saf_matrixConv_apply" in u and "saf_multiConv_apply" in u
+    assert "saf_matrixConv_apply" in u and "saf_multiConv_apply" in u and "saf_TVConv_apply" in u
     r = subprocess.run(["nm", "-D", "--undefined-only", str(REF_SO)], capture_output=True, text=True).stdout
     assert "saf_matrixConv_apply" not in r
