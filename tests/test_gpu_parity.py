@@ -81,7 +81,9 @@ def test_multiconv_vs_oracle(saf, orc, hop, L, nCH, part, nblk):
     mc.destroy()
 
 
-@pytest.mark.parametrize("hop,L,nIRs,nOut", [(128, 700, 4, 3), (512, 3000, 3, 8), (100, 64, 2, 1)])
+@pytest.mark.parametrize("hop,L,nIRs,nOut", [(128, 700, 4, 3), (512, 3000, 3, 8), (100, 64, 2, 1),
+                                             (4096, 9000, 3, 2),                       # largest hop of the one-launch kernel
+                                             (8192, 20000, 3, 2), (5000, 12000, 2, 3)])  # hop > 4096: three-launch path
 def test_tvconv_vs_oracle(saf, orc, hop, L, nIRs, nOut):
     rng = np.random.default_rng(hop + L)
     H = rng.uniform(-1, 1, (nIRs, nOut, L)).astype(np.float32)
