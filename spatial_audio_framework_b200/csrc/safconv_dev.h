@@ -93,7 +93,9 @@ typedef struct scdev_offline {
     void  *XGhi, *XGlo;      /* A operand  [bin][kg][rows][16 B]  (frames x (input, re/im)), hi / lo parts; a k-group = 4 tf32 or 8 fp16 */
     void  *HGhi, *HGlo;      /* B operand  [bin][p][kg][Nn][16 B] ((output, re/im) x (input, re/im))            */
     float *Ys;               /* output spectra [bin][Tpad][Nn]                                                  */
-    float *scal;             /* fp16 operands: [0] bound on the input spectra of the current render, [1] bound on the filter spectra */
+    float *scal;             /* fp16 operands: [0] bound on the input spectra of the current render, [1] bound on the filter spectra;
+                                [2] (as int) the GEMM's tile ticket, zeroed before every launch */
+    int smCount;             /* CTAs of the persistent GEMM */
     int nTiles;              /* output tiles of Nn/2 (<= 64) outputs: grid.z of the GEMM                          */
     int f16, ipc;            /* 1: fp16 operands (default), 0: tf32; inputs per k-group (4 / 2)                 */
     int wfft;                /* 1: warp-register FFT transform kernels (fp16 operands, M <= 1024)                */

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 static __thread int  tl_err = 0;
 static __thread char tl_msg[256] = "";
@@ -241,6 +242,9 @@ int safconv_debug_pass_tables(int hop, int len, int nIn, int nOutLocal, int smCo
 static void handle_free(safconv_handle* h)
 {
     if (!h) return;
+    if (h->hostTrace && h->htN)
+        fprintf(stderr, "safconv host trace: %u zero-copy applies, us per call: checks %.2f, launch %.2f, wait %.2f\n", h->htN,
+                h->htAcc[0] / h->htN * 1e-3, h->htAcc[1] / h->htN * 1e-3, h->htAcc[2] / h->htN * 1e-3);
     if (h->device >= 0) scdev_set_device(h->device);
     if (h->stream) scdev_stream_sync(h->stream);
     scdev_graph_destroy(h->graphExec);
@@ -350,6 +354,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     h->detectPinned = 1;
     h->batching = 1;
     h->smallFused = env_int("SAFCONV_SMALL_FUSED", 1, 0, 1);
+    h->hostTrace = env_int("SAFCONV_HOSTTRACE", 0, 0, 1);
 
     const size_t M = (size_t)pl->M, P = (size_t)pl->P;
     /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
@@ -418,10 +423,10 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
         for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
     }
-    if (kind == SC_KIND_MULTI && env_int("SAFCONV_MULTI_WFFT", 1, 0, 1))
-        DEV_TRY(h, scdev_wfft_tables(pl, &h->b, h->stream), "warp-FFT tables");
-    DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
     h->smallOk = (kind == SC_KIND_MATRIX) ? scdev_small_fits(pl, h->maxSmem) : 0;
+    if ((kind == SC_KIND_MULTI && env_int("SAFCONV_MULTI_WFFT", 1, 0, 1)) || (kind == SC_KIND_MATRIX && h->smallOk))
+        DEV_TRY(h, scdev_wfft_tables(pl, &h->b, h->stream), "warp-FFT tables");     /* the latency kernel of small matrix problems uses them too */
+    DEV_TRY(h, scdev_prepare(pl), "kernel attribute setup");
 
     if (zalloc(h, &h->b.H, h->bytesH, "filter spectra allocation")) goto fail;
     if (zalloc(h, &h->b.X, h->bytesX, "delay line allocation")) goto fail;
@@ -712,8 +717,16 @@ static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int 
 /* host-pointer apply (reference semantics: synchronous).  Caller buffers that are already page-locked
  * (cudaHostAlloc / cudaHostRegister) are used directly; ordinary malloc'd buffers go through the handle's pinned
  * staging buffers. */
+static inline double now_ns(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e9 + (double)ts.tv_nsec;
+}
+
 static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
 {
+    const double t0 = h->hostTrace ? now_ns() : 0.0;
     h_clear(h);
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
@@ -723,6 +736,7 @@ static void conv_apply_host(safconv_handle* h, const float* in, float* out, int 
     const float* src = direct ? in : h->h_in;
     float*       dst = direct ? out : h->h_out;
     if (!direct) memcpy(h->h_in, in, h->inBytes);
+    if (h->hostTrace) h->htAcc[0] += now_ns() - t0;
     sch_apply_pinned(h, src, dst, irIdx);
     if (!direct && !h->err) memcpy(out, h->h_out, h->outBytes);
 }
@@ -732,9 +746,12 @@ void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx
 {
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
+    const double t1 = h->hostTrace ? now_ns() : 0.0;
     e = apply_zero_copy(h, src, dst, irIdx);
     if (e >= 0) {
+        const double t2 = h->hostTrace ? now_ns() : 0.0;
         if (!e) e = scdev_stream_sync(h->stream);
+        if (h->hostTrace) { const double t3 = now_ns(); h->htAcc[1] += t2 - t1; h->htAcc[2] += t3 - t2; h->htN++; }
         if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (zero-copy)", e); return; }
         h->count++;
     } else if (h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->useGraph && !h->timingCap) {

@@ -38,6 +38,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
 #include "safconv_wfft.cuh"
@@ -940,6 +941,238 @@ __global__ void small_fused_kernel(SmallArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/*  small_cluster_kernel<R>: the same block (K1 + K2 + K3 in one launch, mapped host buffers      */
+/*  allowed) for M = 32 R = 64 .. 1024 on ONE thread-block cluster of C CTAs, without redundant    */
+/*  work and without block-wide FFT passes:                                                       */
+/*    A  forward FFTs: input ni -> CTA ni % C, warp ni / C; one WARP per transform on the         */
+/*       register FFT (safconv_wfft.cuh: compile-time M, no shared memory, no barriers), real     */
+/*       split in registers, spectrum into the delay-line ring (global, L2)                       */
+/*       -- cluster barrier (release / acquire: the ring slot is visible to all CTAs) --          */
+/*    B  per-bin sums: unit (output, 32-bin tile) u -> CTA u % C; the P*nIn terms of a unit are    */
+/*       split over the warps of the CTA (lane = bin: 256-byte coalesced rows of H and of the     */
+/*       ring), fixed-order reduction through shared memory, the tile is written into the shared  */
+/*       memory of the CTA that owns the output (distributed shared memory)                       */
+/*       -- cluster barrier --                                                                    */
+/*    C  output no -> CTA no % C, warp no / C: inverse split, register inverse FFT, overlap-add,  */
+/*       coalesced stores of out / tail.                                                          */
+/*  ncu (profiles/r02_C2_full_summary.csv): small_fused_kernel at C2 = 2 CTAs, 90 k warp           */
+/*  instructions, 30 % issue-active, 25 us cold -- every CTA repeats all 25 input FFTs on the     */
+/*  shared-memory core and walks the 100 terms of its output with 4 thread groups.                */
+/* ------------------------------------------------------------------------------------------ */
+#define SC_CL_THREADS 512
+#define SC_CL_WARPS   (SC_CL_THREADS / 32)
+#define SC_CL_MAXC    8
+
+struct SmallCArgs {
+    const float* in;       /* [nIn][hop]       (device or mapped host) */
+    float* out;            /* [nOutLocal][hop] (device or mapped host) */
+    const float2* H;       /* [ot][kt][p][ni][OTsz][32] */
+    float2* X;             /* [kt][RS][nIn][32] ring */
+    const float2* tw;      /* W_N^e, e < M */
+    const float2* wT1;     /* warp-FFT tables [R][32] */
+    const float2* wT2;
+    float* tail;
+    unsigned int* counters;
+    int hop, P, nIn, nOut, nKT, OTsz, RS;
+    float scale;
+};
+
+__device__ __forceinline__ uint32_t cl_ctarank()  { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cl_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_store_f2(const void* localSmem, uint32_t rank, float2 v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(localSmem)), "r"(rank));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" :: "r"(remote), "f"(v.x), "f"(v.y) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCArgs a)
+{
+    constexpr int M = 32 * R, LOGR = wf_log2(R);
+    constexpr int ZS = M + 33;                                  /* float2 per owned output: spectrum, then time-domain staging */
+    extern __shared__ __align__(16) float2 smc[];
+    float2* Zs  = smc;                                          /* [owned outputs][ZS] */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = (int)cl_ctarank(), C = (int)cl_nctarank();
+    const int nOwn = (a.nOut - c + C - 1) / C;                  /* outputs c, c + C, ... */
+    const int nOwnMax = (a.nOut + C - 1) / C;
+    float2* red = smc + (size_t)nOwnMax * ZS;                   /* [warps][32] partial sums */
+    const unsigned int count = a.counters[0];
+    const int head = (int)(count % (unsigned)a.RS);
+    const WfftLane Lf = wfft_lane_init<false>(a.tw, M, lane);
+    WfftLane Li = Lf;
+    Li.w16.y = -Li.w16.y; Li.w8.y = -Li.w8.y; Li.w4.y = -Li.w4.y; Li.w2.y = -Li.w2.y;
+    const int k1 = (int)(__brev((unsigned)lane) >> 27);
+    /* overlap tail of the output this warp owns: fetched now, used at the very end (hop <= M) */
+    const int noMine = c + C * warp;
+    float tl[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int i = lane + 32 * u;
+        tl[u] = (warp < nOwn && i < a.hop) ? a.tail[(size_t)noMine * a.hop + i] : 0.f;
+    }
+
+    /* ---- A: forward FFTs of the inputs this CTA owns ---- */
+    {
+        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
+        for (int ni = c + C * warp; ni < a.nIn; ni += C * SC_CL_WARPS) {
+            const float* x = a.in + (size_t)ni * a.hop;
+            float2 v[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int n = lane + 32 * i;
+                v[i] = make_float2(0.f, 0.f);
+                if (vec) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+                else {
+                    if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
+                    if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+                }
+            }
+            wfft<R, false>(v, a.wT1, lane, Lf);
+            float2 Xs[R];
+            wfft_fwd_split<R>(v, Xs, a.wT2, lane, 0.5f);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int k = wf_bitrev(i, LOGR) + R * k1;
+                a.X[(((size_t)(k >> 5) * a.RS + head) * a.nIn + ni) * SC_BK + (k & 31)] = Xs[i];
+            }
+        }
+    }
+    cl_sync();
+    if (c == 0 && threadIdx.x == 0) a.counters[0] = count + 1u;     /* every CTA has read it before the barrier */
+
+    /* ---- B: Z[no][k] = sum_p sum_ni H_p[no][ni][k] * X_{t-p}[ni][k] ---- */
+    {
+        const int nUnits = a.nOut * a.nKT;                       /* unit u = kt * nOut + no */
+        const int nuLocal = (nUnits - c + C - 1) / C;
+        const int perRound = nuLocal < SC_CL_WARPS ? (nuLocal > 0 ? nuLocal : 1) : SC_CL_WARPS;
+        const int wpu = SC_CL_WARPS / perRound;                  /* warps per unit */
+        const int nTerms = a.P * a.nIn;
+        for (int base = 0; base < nuLocal; base += perRound) {
+            const int lu = base + warp / wpu, g = warp % wpu;
+            const bool valid = (warp / wpu) < perRound && lu < nuLocal;
+            int no = 0, kt = 0;
+            if (valid) {
+                const int u = c + C * lu;
+                kt = u / a.nOut; no = u - kt * a.nOut;
+                const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+                const bool packed = (kt == 0 && lane == 0);
+                const int t0 = (int)(((long long)nTerms * g) / wpu), t1 = (int)(((long long)nTerms * (g + 1)) / wpu);
+                int p = t0 / a.nIn, ni = t0 - p * a.nIn;
+                int slot = head - p; if (slot < 0) slot += a.RS;
+                const float2* Hk = a.H + ((size_t)(ot * a.nKT + kt) * a.P * a.nIn * a.OTsz + nl) * SC_BK + lane;
+                const float2* Xk = a.X + (size_t)kt * a.RS * a.nIn * SC_BK + lane;
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 8
+                for (int t = t0; t < t1; ++t) {
+                    const float2 h = __ldg(Hk + (size_t)(p * a.nIn + ni) * a.OTsz * SC_BK);
+                    const float2 x = __ldcg(Xk + ((size_t)slot * a.nIn + ni) * SC_BK);   /* written by other CTAs of this launch: L2 */
+                    cmac_packed(acc, h, x, packed);
+                    if (++ni == a.nIn) { ni = 0; ++p; slot = (slot == 0) ? a.RS - 1 : slot - 1; }
+                }
+                red[warp * 32 + lane] = acc;
+            }
+            __syncthreads();
+            if (valid && g == 0) {
+                float2 z = red[warp * 32 + lane];
+                for (int gg = 1; gg < wpu; ++gg) z = caddf(z, red[(warp + gg) * 32 + lane]);
+                cl_store_f2(Zs + (size_t)(no / C) * ZS + kt * 32 + lane, (uint32_t)(no % C), z);
+            }
+            __syncthreads();
+        }
+    }
+    cl_sync();
+
+    /* ---- C: inverse FFT + overlap-add of the outputs this CTA owns (reference .c:230-233) ---- */
+    if (warp < nOwn) {
+        float2* z = Zs + (size_t)warp * ZS;
+        float2 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int k = lane + 32 * i;
+            const float2 A = z[k], B = z[(M - k) & (M - 1)];
+            const float2 E = make_float2(A.x + B.x, A.y - B.y);
+            const float2 D = make_float2(A.x - B.x, A.y + B.y);
+            const float2 O = cmul_conjb(D, __ldg(a.tw + k));
+            v[i] = make_float2(E.x - O.y, E.y + O.x);
+            if (i == 0 && lane == 0) v[i] = make_float2(A.x + A.y, A.x - A.y);      /* (DC, Nyquist) */
+        }
+        wfft<R, true>(v, a.wT1, lane, Li);
+        __syncwarp();                                           /* the spectrum has been read by every lane */
+#pragma unroll
+        for (int i = 0; i < R; ++i)                             /* z[n], n = n2 + R k1, stored at n2 + (R + 1) k1 */
+            z[wf_bitrev(i, LOGR) + (R + 1) * k1] = make_float2(v[i].x * a.scale, v[i].y * a.scale);
+        __syncwarp();
+        const float* zf = reinterpret_cast<const float*>(z);
+        float* out = a.out + (size_t)noMine * a.hop;
+        float* tail = a.tail + (size_t)noMine * a.hop;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const int i = lane + 32 * u;
+            if (i < a.hop) {
+                const int s1 = i + a.hop;
+                const int n0 = i >> 1, n1 = s1 >> 1;
+                out[i]  = zf[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)] + tl[u];
+                tail[i] = zf[2 * ((n1 & (R - 1)) + (R + 1) * (n1 >> LOGR)) + (s1 & 1)];
+            }
+        }
+    }
+}
+
+/* the cluster version: M = 64 .. 1024, at most 16 inputs / outputs per CTA of the cluster */
+static int small_cluster_ok(const scdev_plan* pl, const scdev_bufs* b)
+{
+    static int env = -1;
+    if (env < 0) { const char* v = getenv("SAFCONV_SMALL_CLUSTER"); env = v ? atoi(v) : 1; }
+    if (!env || !b->wtab || pl->kind != SC_KIND_MATRIX) return 0;
+    if (pl->M < 64 || pl->M > 1024 || pl->hop > pl->M) return 0;
+    if (pl->nIn > SC_CL_MAXC * SC_CL_WARPS || pl->nOutLocal > SC_CL_MAXC * SC_CL_WARPS) return 0;
+    return 1;
+}
+
+template <int R>
+static int small_cluster_launch(const SmallCArgs& a, int C, cudaStream_t st)
+{
+    const int nOwnMax = (a.nOut + C - 1) / C;
+    const size_t smem = ((size_t)nOwnMax * (32 * R + 33) + SC_CL_WARPS * 32) * sizeof(float2);
+    if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(small_cluster_kernel<R>));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(SC_CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, small_cluster_kernel<R>, a);
+}
+
+static int scdev_small_cluster(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, cudaStream_t st)
+{
+    SmallCArgs a;
+    a.in = in; a.out = out; a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
+    a.wT1 = (const float2*)b->wtab; a.wT2 = (const float2*)b->wtab + pl->M;
+    a.tail = b->tail; a.counters = b->counters;
+    a.hop = pl->hop; a.P = pl->P; a.nIn = pl->nIn; a.nOut = pl->nOutLocal; a.nKT = pl->nKT; a.OTsz = pl->OTsz; a.RS = pl->RS;
+    a.scale = 1.0f / (float)pl->N;
+    int work = pl->nOutLocal * pl->nKT;
+    if (pl->nIn > work) work = pl->nIn;
+    const int C = work < SC_CL_MAXC ? work : SC_CL_MAXC;
+    switch (pl->M) {
+        case 64:   return small_cluster_launch<2>(a, C, st);
+        case 128:  return small_cluster_launch<4>(a, C, st);
+        case 256:  return small_cluster_launch<8>(a, C, st);
+        case 512:  return small_cluster_launch<16>(a, C, st);
+        case 1024: return small_cluster_launch<32>(a, C, st);
+        default:   return (int)cudaErrorInvalidValue;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /*  TVConv: one CTA per output channel (reference .c:546-620)                                   */
 /*  shared memory: 5*M float2  (X spectrum, three output frames, twiddles)                       */
 /* ------------------------------------------------------------------------------------------ */
@@ -1552,6 +1785,7 @@ int scdev_small_fits(const scdev_plan* pl, int maxSmemOptin)
 
 int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream)
 {
+    if (small_cluster_ok(pl, b)) return scdev_small_cluster(pl, b, in, out, (cudaStream_t)stream);
     SmallArgs a;
     a.in = in; a.out = out; a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
     a.tail = b->tail; a.counters = b->counters;

@@ -209,6 +209,7 @@ struct OffFftArgs {
     const float* scal;     /* fp16 operands: scal[0] = bound on the input spectra */
     size_t inStride;       /* T*hop */
     int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
+    int rowsUsed;          /* operand rows this launch fills (persistent kernel) */
     int fpc;               /* frames per CTA (2 or 4): 32- or 64-byte contiguous operand stores */
     int ipc;               /* inputs per CTA = inputs per k-group: 2 (tf32) or 4 (fp16) */
     const float2* wT1;     /* warp-FFT tables (device, [R][32] each): step-2 twiddles, split twiddles */
@@ -450,28 +451,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 /* ------------------------------------------------------------------------------------------ */
 struct OffGemmArgs {
     const unsigned char *XGhi, *XGlo, *HGhi, *HGlo;
-    size_t hgTileBytes;    /* output tile blockIdx.z: HG + z * hgTileBytes, Ys + z * ysTileFloats */
+    size_t hgTileBytes;    /* output tile z: HG + z * hgTileBytes, Ys + z * ysTileFloats */
     size_t ysTileFloats;
     const float* scal;     /* fp16 operands: the two magnitude bounds whose scales are divided out of the result */
+    int* ticket;           /* tile counter of the dynamic scheduler (zeroed before the launch) */
     float* Ys;             /* [bin][Tpad][Nn] */
     int P, nKG, nKC, Nn, rowsAlloc, Tpad, rowsX, tmemCols, flush;
-    uint32_t idesc;
+    int T;                 /* frames of this render: the last frame tile is cut to roundup16(T - t0) columns / one accumulator */
+    int nFT, nBins, nTilesTotal;   /* frame tiles, bins, all tiles = nOutTiles * nBins * nFT (frame tile fastest) */
+    uint32_t idesc;        /* instruction descriptor with the N field left empty (NT) / complete (frames on M) */
 };
 
 #define OFF_EPI_WARPS 8
 #define OFF_MAX_HALF  64     /* columns per epilogue thread and frame tile: Nn/2 <= 64 */
 
+struct OffTile { int t0, bin, z, nFr; };
+__device__ __forceinline__ OffTile off_tile_decode(const OffGemmArgs& a, int tile)
+{
+    OffTile r;
+    const int ft = tile % a.nFT; tile /= a.nFT;
+    r.bin = tile % a.nBins; r.z = tile / a.nBins;
+    r.t0 = ft * OFF_MT;
+    const int left = a.T - r.t0;
+    r.nFr = left >= OFF_MT ? OFF_MT : ((left + 15) & ~15);
+    return r;
+}
+
 /* NT = true (Nn == 128): the operand roles are swapped -- filters on the UMMA M axis (A, 128 rows), the 256 frames of
  * the tile on the N axis (B) -- so one M128 x N256 x K16 instruction replaces two M128 x N128 ones.  At N = 128 an MMA
  * reads 8 KB of shared memory per 64 tensor-pipe cycles, which is the whole shared-memory read bandwidth of the SM
  * (TMA fills and everything else contend with it); at N = 256 it is 12 KB per 128 cycles.  The Toeplitz row shift
- * works on the B descriptor exactly as on the A descriptor. */
+ * works on the B descriptor exactly as on the A descriptor.
+ *
+ * PERSISTENT: one CTA per SM walks over (frame tile, bin, output tile) work items handed out by a global ticket
+ * (frame tile fastest, so the CTAs that run at the same time share a bin's filter operand in L2, exactly like the
+ * hardware block scheduler did).  TMEM allocation, barrier set-up and the pipeline ramp are paid once per CTA, and the
+ * final promotion + store of tile i overlaps the first chains of tile i+1 (the MMA warp only waits for the TMEM buffer
+ * set to be drained, not for the global stores).  The LAST frame tile of a render is cut to roundup16(T - t0) columns
+ * (NT: the UMMA N of its instructions; frames on M: one accumulator instead of two when <= 128 frames are left), so a
+ * short time shard (multi-GPU: 2813 / 8 + halo = 360 frames) costs 256 + 112 columns, not 512. */
 template <bool F16, bool NT>
 __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGemmArgs a)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * OFF_MT, bin = blockIdx.y;
 
     const uint32_t xPlane = (uint32_t)a.rowsX * 16u;        /* one k-group column of the frame tile   */
     const uint32_t xStage = 2u * OFF_KG * xPlane;           /* hi + lo                                */
@@ -485,14 +508,18 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
     uint64_t* hempty  = hfull + OFF_NH;
     uint64_t* tfull   = hempty + OFF_NH;                    /* TMEM buffer set b holds a finished chain */
     uint64_t* tempty  = tfull + 2;                          /* ... has been drained by all epilogue warps */
-    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(tempty + 2);
-    const int steps = a.nKC * a.P;                          /* partition steps of this tile           */
+    uint64_t* sfull   = tempty + 2;                         /* scheduler slot s holds the next tile id */
+    uint64_t* sempty  = sfull + 2;                          /* ... has been read by the MMA warp and all epilogue warps */
+    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(sempty + 2);
+    volatile int* sched = reinterpret_cast<volatile int*>(tmemPtr + 2);
+    const int steps = a.nKC * a.P;                          /* partition steps of a tile              */
     const int nFlush = (steps + a.flush - 1) / a.flush;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1);
             mbar_init(&tfull[i], 1); mbar_init(&tempty[i], OFF_EPI_WARPS);
+            mbar_init(&sfull[i], 1); mbar_init(&sempty[i], OFF_EPI_WARPS + 1);
         }
         for (int i = 0; i < OFF_NH; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -508,28 +535,42 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
     const uint32_t tmem = *tmemPtr;
 
     if (warp == OFF_EPI_WARPS) {
-        /* ===================== TMA producer ===================== */
+        /* ===================== scheduler + TMA producer ===================== */
         if (lane == 0) {
             int hs = 0; uint32_t hpar = 1;
-            for (int kc = 0; kc < a.nKC; ++kc) {
-                const int xs = kc & 1;
-                mbar_wait(&xempty[xs], (((uint32_t)kc >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(&xfull[xs], xStage);
-                for (int hl = 0; hl < 2; ++hl)
-                    for (int g = 0; g < OFF_KG; ++g) {
-                        const unsigned char* src = (hl ? a.XGlo : a.XGhi)
-                                         + (((size_t)bin * a.nKG + (size_t)kc * OFF_KG + g) * a.rowsAlloc + t0) * 16;
-                        tma_bulk_g2s(smX + (size_t)xs * xStage + (size_t)(hl * OFF_KG + g) * xPlane, src, xPlane, &xfull[xs]);
+            uint32_t xc = 0;                                /* frame-tile loads issued so far (all tiles) */
+            int next = atomicAdd(a.ticket, 1);              /* the ticket of tile q+1 is drawn while tile q is being loaded */
+            for (uint32_t q = 0; ; ++q) {
+                const int sl = (int)(q & 1u);
+                mbar_wait(&sempty[sl], ((q >> 1) & 1u) ^ 1u);
+                const int tile = next < a.nTilesTotal ? next : -1;
+                sched[sl] = tile;
+                mbar_arrive(&sfull[sl]);                    /* release: the slot is visible to the waiters */
+                if (tile < 0) break;
+                next = atomicAdd(a.ticket, 1);
+                const OffTile tl = off_tile_decode(a, tile);
+                /* rows of the frame tile that are needed (frames on M: whole 128-row accumulators) */
+                const uint32_t xBytes = (uint32_t)((NT ? tl.nFr : (tl.nFr > 128 ? OFF_MT : 128)) + a.P - 1) * 16u;
+                for (int kc = 0; kc < a.nKC; ++kc, ++xc) {
+                    const int xs = (int)(xc & 1u);
+                    mbar_wait(&xempty[xs], ((xc >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&xfull[xs], 2u * OFF_KG * xBytes);
+                    for (int hl = 0; hl < 2; ++hl)
+                        for (int g = 0; g < OFF_KG; ++g) {
+                            const unsigned char* src = (hl ? a.XGlo : a.XGhi)
+                                             + (((size_t)tl.bin * a.nKG + (size_t)kc * OFF_KG + g) * a.rowsAlloc + tl.t0) * 16;
+                            tma_bulk_g2s(smX + (size_t)xs * xStage + (size_t)(hl * OFF_KG + g) * xPlane, src, xBytes, &xfull[xs]);
+                        }
+                    for (int p = 0; p < a.P; ++p) {
+                        mbar_wait(&hempty[hs], hpar);
+                        mbar_expect_tx(&hfull[hs], hStage);
+                        for (int hl = 0; hl < 2; ++hl) {
+                            const unsigned char* src = (hl ? a.HGlo : a.HGhi) + (size_t)tl.z * a.hgTileBytes
+                                             + ((((size_t)tl.bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 16;
+                            tma_bulk_g2s(smH + (size_t)hs * hStage + (size_t)hl * OFF_KG * hPlane, src, OFF_KG * hPlane, &hfull[hs]);
+                        }
+                        if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
                     }
-                for (int p = 0; p < a.P; ++p) {
-                    mbar_wait(&hempty[hs], hpar);
-                    mbar_expect_tx(&hfull[hs], hStage);
-                    for (int hl = 0; hl < 2; ++hl) {
-                        const unsigned char* src = (hl ? a.HGlo : a.HGhi) + (size_t)blockIdx.z * a.hgTileBytes
-                                         + ((((size_t)bin * a.P + p) * a.nKG + (size_t)kc * OFF_KG) * a.Nn) * 16;
-                        tma_bulk_g2s(smH + (size_t)hs * hStage + (size_t)hl * OFF_KG * hPlane, src, OFF_KG * hPlane, &hfull[hs]);
-                    }
-                    if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
                 }
             }
         }
@@ -543,127 +584,162 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
         const uint64_t bDesc0 = umma_sdesc(0, hPlane, 128);
         const uint32_t xPlane16 = xPlane >> 4, hPlane16 = hPlane >> 4;
         int hs = 0; uint32_t hpar = 0;
-        int inChain = 0, nf = 0, step = 0;
-        for (int kc = 0; kc < a.nKC; ++kc) {
-            const int xs = kc & 1;
-            mbar_wait(&xfull[xs], ((uint32_t)kc >> 1) & 1u);
-            const uint32_t xBase16 = smem_u32(smX + (size_t)xs * xStage) >> 4;
-            for (int p = 0; p < a.P; ++p, ++step) {
-                const int tb = nf & 1;
-                if (inChain == 0)                                       /* new chain: its TMEM buffer set must be drained */
-                    mbar_wait(&tempty[tb], (((uint32_t)nf >> 1) & 1u) ^ 1u);
-                mbar_wait(&hfull[hs], hpar);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t hBase16 = smem_u32(smH + (size_t)hs * hStage) >> 4;
-                    const uint32_t rowShift = (uint32_t)(a.P - 1 - p);  /* frame t-p = tile row +(P-1-p); 16 B per row */
-                    if (NT) {
+        uint32_t nf = 0, xc = 0;                            /* chains / frame-tile loads consumed so far (all tiles) */
+        for (uint32_t q = 0; ; ++q) {
+            const int sl = (int)(q & 1u);
+            mbar_wait(&sfull[sl], (q >> 1) & 1u);
+            const int tile = sched[sl];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sl]);
+            if (tile < 0) break;
+            const OffTile tl = off_tile_decode(a, tile);
+            const uint32_t idesc = NT ? (a.idesc | ((uint32_t)(tl.nFr >> 3) << 17)) : a.idesc;
+            const int nAcc = NT ? 1 : (tl.nFr > 128 ? 2 : 1);
+            int inChain = 0, step = 0;
+            for (int kc = 0; kc < a.nKC; ++kc, ++xc) {
+                const int xs = (int)(xc & 1u);
+                mbar_wait(&xfull[xs], (xc >> 1) & 1u);
+                const uint32_t xBase16 = smem_u32(smX + (size_t)xs * xStage) >> 4;
+                for (int p = 0; p < a.P; ++p, ++step) {
+                    const int tb = (int)(nf & 1u);
+                    if (inChain == 0)                                       /* new chain: its TMEM buffer set must be drained */
+                        mbar_wait(&tempty[tb], ((nf >> 1) & 1u) ^ 1u);
+                    mbar_wait(&hfull[hs], hpar);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t hBase16 = smem_u32(smH + (size_t)hs * hStage) >> 4;
+                        const uint32_t rowShift = (uint32_t)(a.P - 1 - p);  /* frame t-p = tile row +(P-1-p); 16 B per row */
+                        if (NT) {
 #pragma unroll
-                        for (int ks = 0; ks < OFF_KG / 2; ++ks) {
-                            const uint32_t x16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + rowShift;
-                            const uint32_t h16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
-                            const uint64_t xHi = aDesc0 + x16, xLo = aDesc0 + x16 + OFF_KG * xPlane16;
-                            const uint64_t hHi = bDesc0 + h16, hLo = bDesc0 + h16 + OFF_KG * hPlane16;
-                            const uint32_t d = tmem + (uint32_t)(tb * 256);
-                            umma_ss<F16>(d, hLo, xHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
-                            umma_ss<F16>(d, hHi, xLo, a.idesc, 1u);                         /* hi*lo */
-                            umma_ss<F16>(d, hHi, xHi, a.idesc, 1u);                         /* hi*hi */
+                            for (int ks = 0; ks < OFF_KG / 2; ++ks) {
+                                const uint32_t x16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + rowShift;
+                                const uint32_t h16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
+                                const uint64_t xHi = aDesc0 + x16, xLo = aDesc0 + x16 + OFF_KG * xPlane16;
+                                const uint64_t hHi = bDesc0 + h16, hLo = bDesc0 + h16 + OFF_KG * hPlane16;
+                                const uint32_t d = tmem + (uint32_t)(tb * 256);
+                                umma_ss<F16>(d, hLo, xHi, idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
+                                umma_ss<F16>(d, hHi, xLo, idesc, 1u);                         /* hi*lo */
+                                umma_ss<F16>(d, hHi, xHi, idesc, 1u);                         /* hi*hi */
+                            }
+                        } else
+                        for (int acc = 0; acc < nAcc; ++acc) {
+#pragma unroll
+                            for (int ks = 0; ks < OFF_KG / 2; ++ks) {
+                                const uint32_t a16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + (uint32_t)acc * 128u + rowShift;
+                                const uint32_t b16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
+                                const uint64_t aHi = aDesc0 + a16, aLo = aDesc0 + a16 + OFF_KG * xPlane16;
+                                const uint64_t bHi = bDesc0 + b16, bLo = bDesc0 + b16 + OFF_KG * hPlane16;
+                                const uint32_t d = tmem + (uint32_t)((tb * 2 + acc) * a.Nn);
+                                /* small cross terms first, the large hi*hi term last */
+                                umma_ss<F16>(d, aLo, bHi, idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
+                                umma_ss<F16>(d, aHi, bLo, idesc, 1u);                         /* hi*lo */
+                                umma_ss<F16>(d, aHi, bHi, idesc, 1u);                         /* hi*hi */
+                            }
                         }
-                    } else
-#pragma unroll
-                    for (int acc = 0; acc < 2; ++acc) {
-#pragma unroll
-                        for (int ks = 0; ks < OFF_KG / 2; ++ks) {
-                            const uint32_t a16 = xBase16 + (uint32_t)(2 * ks) * xPlane16 + (uint32_t)acc * 128u + rowShift;
-                            const uint32_t b16 = hBase16 + (uint32_t)(2 * ks) * hPlane16;
-                            const uint64_t aHi = aDesc0 + a16, aLo = aDesc0 + a16 + OFF_KG * xPlane16;
-                            const uint64_t bHi = bDesc0 + b16, bLo = bDesc0 + b16 + OFF_KG * hPlane16;
-                            const uint32_t d = tmem + (uint32_t)((tb * 2 + acc) * a.Nn);
-                            /* small cross terms first, the large hi*hi term last */
-                            umma_ss<F16>(d, aLo, bHi, a.idesc, (inChain | ks) ? 1u : 0u);   /* lo*hi */
-                            umma_ss<F16>(d, aHi, bLo, a.idesc, 1u);                         /* hi*lo */
-                            umma_ss<F16>(d, aHi, bHi, a.idesc, 1u);                         /* hi*hi */
-                        }
+                        umma_commit(&hempty[hs]);                           /* filter stage free once these MMAs retire */
                     }
-                    umma_commit(&hempty[hs]);                           /* filter stage free once these MMAs retire */
+                    if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
+                    if (++inChain == a.flush || step + 1 == steps) {
+                        if (leader) umma_commit(&tfull[tb]);                /* chain complete -> epilogue may drain it */
+                        ++nf; inChain = 0;
+                    }
+                    __syncwarp();
                 }
-                if (++hs == OFF_NH) { hs = 0; hpar ^= 1u; }
-                if (++inChain == a.flush || step + 1 == steps) {
-                    if (leader) umma_commit(&tfull[tb]);                /* chain complete -> epilogue may drain it */
-                    ++nf; inChain = 0;
-                }
+                if (leader) umma_commit(&xempty[xs]);
                 __syncwarp();
             }
-            if (leader) umma_commit(&xempty[xs]);
-            __syncwarp();
         }
     } else {
         /* ===================== epilogue warps: promote TMEM chains into fp32 register sums ===================== */
-        const int q = warp & 3, hh = warp >> 2;            /* TMEM lane quarter (= warp % 4), column half */
+        const int q4 = warp & 3, hh = warp >> 2;           /* TMEM lane quarter (= warp % 4), column half */
         const int halfN = a.Nn >> 1;
+        /* fp16 operands were scaled by exact powers of two: divide them out (exact as well) */
+        const float inv = F16 ? 1.f / (pow2_scale(a.scal[0]) * pow2_scale(a.scal[1])) : 1.f;
         float sum[2][OFF_MAX_HALF];
 #pragma unroll
         for (int t = 0; t < 2; ++t)
 #pragma unroll
             for (int c = 0; c < OFF_MAX_HALF; ++c) sum[t][c] = 0.f;
-        for (int f = 0; f < nFlush; ++f) {
-            const int tb = f & 1;
-            mbar_wait(&tfull[tb], ((uint32_t)f >> 1) & 1u);
-            tc_fence_after();
+        uint32_t g = 0;                                     /* chains drained so far (all tiles) */
+        for (uint32_t q = 0; ; ++q) {
+            const int sl = (int)(q & 1u);
+            mbar_wait(&sfull[sl], (q >> 1) & 1u);
+            const int tile = sched[sl];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sl]);
+            if (tile < 0) break;
+            const OffTile tl = off_tile_decode(a, tile);
+            for (int f = 0; f < nFlush; ++f, ++g) {
+                const int tb = (int)(g & 1u);
+                mbar_wait(&tfull[tb], (g >> 1) & 1u);
+                tc_fence_after();
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
+                for (int t = 0; t < 2; ++t) {
+                    /* NT: this thread owns frames (columns) hh*128 + t*64 .. +63; frames on M: accumulator t = frames t*128 .. */
+                    if (NT ? (hh * 128 + t * 64 >= tl.nFr) : (t * 128 >= tl.nFr)) continue;     /* warp-uniform */
 #pragma unroll
-                for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 32) {
-                    /* NT: lane = filter row n = 32 q + lane, columns = frames; this thread owns frames hh*128 + t*64 + c0 .. */
-                    const uint32_t col = NT ? (uint32_t)(tb * 256 + hh * 128 + t * 64 + c0)
-                                            : (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0);
-                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col;
-                    if (halfN == 64) {                       /* full tile: all 64 columns of this half with one wait */
-                        if (c0 == 0) {
-                            float v[64];
-                            tmem_ld64(ta, v);
+                    for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 32) {
+                        /* NT: lane = filter row n = 32 q4 + lane, columns = frames */
+                        const uint32_t col = NT ? (uint32_t)(tb * 256 + hh * 128 + t * 64 + c0)
+                                                : (uint32_t)((tb * 2 + t) * a.Nn + hh * halfN + c0);
+                        const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + col;
+                        if (halfN == 64) {                       /* full tile: all 64 columns of this half with one wait */
+                            if (c0 == 0) {
+                                float v[64];
+                                tmem_ld64(ta, v);
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) sum[t][i] += v[i];
+                                for (int i = 0; i < 64; ++i) sum[t][i] += v[i];
+                            }
+                        } else if (c0 + 16 < halfN) {
+                            float v[32];
+                            tmem_ld16x2(ta, ta + 16, v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sum[t][c0 + i] += v[i];
+                        } else if (c0 < halfN) {
+                            float v[16];
+                            tmem_ld16(ta, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[t][c0 + i] += v[i];
                         }
-                    } else if (c0 + 16 < halfN) {
-                        float v[32];
-                        tmem_ld16x2(ta, ta + 16, v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) sum[t][c0 + i] += v[i];
-                    } else if (c0 < halfN) {
-                        float v[16];
-                        tmem_ld16(ta, v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) sum[t][c0 + i] += v[i];
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[tb]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[tb]);
-        }
-        /* fp16 operands were scaled by exact powers of two: divide them out (exact as well) */
-        const float inv = F16 ? 1.f / (pow2_scale(a.scal[0]) * pow2_scale(a.scal[1])) : 1.f;
-        float* Ys = a.Ys + (size_t)blockIdx.z * a.ysTileFloats;
-        if (NT) {
-            /* sum[t][c] = output row n = 32 q + lane of frame t0 + hh*128 + t*64 + c: a warp stores 32 consecutive n */
-            const int n = q * 32 + lane;
+            /* the MMA warp is already filling the buffer sets with the next tile's chains while these stores drain */
+            float* Ys = a.Ys + (size_t)tl.z * a.ysTileFloats;
+            if (NT) {
+                /* sum[t][c] = output row n = 32 q4 + lane of frame t0 + hh*128 + t*64 + c: a warp stores 32 consecutive n.
+                 * NT implies Nn == 128, so all store offsets are immediates off one base pointer per tile. */
+                float* dst = Ys + ((size_t)tl.bin * a.Tpad + tl.t0 + hh * 128) * 128 + (q4 * 32 + lane);
+                if (tl.nFr == OFF_MT) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+                    for (int t = 0; t < 2; ++t)
 #pragma unroll
-                for (int c = 0; c < OFF_MAX_HALF; ++c) {
-                    const int row = t0 + hh * 128 + t * 64 + c;
-                    Ys[((size_t)bin * a.Tpad + row) * a.Nn + n] = sum[t][c] * inv;
+                        for (int c = 0; c < OFF_MAX_HALF; ++c) { dst[(t * 64 + c) * 128] = sum[t][c] * inv; sum[t][c] = 0.f; }
+                } else {
+                    const int left = tl.nFr - hh * 128;            /* columns of this half that exist */
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int c = 0; c < OFF_MAX_HALF; ++c) {
+                            if (t * 64 + c < left) dst[(t * 64 + c) * 128] = sum[t][c] * inv;
+                            sum[t][c] = 0.f;
+                        }
                 }
-        } else
+            } else
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int row = t0 + t * 128 + q * 32 + lane;
-            float* dst = Ys + ((size_t)bin * a.Tpad + row) * a.Nn + hh * halfN;
+            for (int t = 0; t < 2; ++t) {
+                const int fr = t * 128 + q4 * 32 + lane;
+                float* dst = Ys + ((size_t)tl.bin * a.Tpad + tl.t0 + fr) * a.Nn + hh * halfN;
 #pragma unroll
-            for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 4)
-                if (c0 < halfN)
-                    *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[t][c0] * inv, sum[t][c0 + 1] * inv, sum[t][c0 + 2] * inv, sum[t][c0 + 3] * inv);
+                for (int c0 = 0; c0 < OFF_MAX_HALF; c0 += 4) {
+                    if (c0 < halfN && t * 128 < tl.nFr)
+                        *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[t][c0] * inv, sum[t][c0 + 1] * inv, sum[t][c0 + 2] * inv, sum[t][c0 + 3] * inv);
+                    sum[t][c0] = sum[t][c0 + 1] = sum[t][c0 + 2] = sum[t][c0 + 3] = 0.f;
+                }
+            }
         }
     }
     tc_fence_before();
@@ -956,6 +1032,97 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftAr
     }
 }
 
+/* The same forward kernel, PERSISTENT with the next tile's input blocks prefetched by TMA: every warp owns a 4 KB
+ * shared-memory slot; one lane issues a bulk copy (cp.async.bulk) of its next input block as soon as the warp has moved
+ * the current one into registers, so the DRAM round trip of tile i+1 runs under the transform + split + stores of tile i
+ * (ncu, r01/r02: the one-shot kernel is 55 % issue-active at 25 % occupancy -- 128 registers per thread leave two CTAs per
+ * SM, and both sit in their load phase for a good part of their life).  The input is a zero-padded block (hop <= M real
+ * samples = at most M/2 complex points), so the first radix-2 stage of the transform needs no additions (ZPAD).
+ * Needs 16-byte aligned input rows (hop % 4 == 0, 16-byte aligned base and channel stride).  grid = min(tiles, 2 * SMs),
+ * tile = row pair (fastest, so CTAs that run together store adjacent operand rows) x input group. */
+__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_p_kernel(OffFftArgs a)
+{
+    constexpr int M = 1024;
+    extern __shared__ __align__(128) unsigned char smw[];
+    float2* tiles = reinterpret_cast<float2*>(smw);                               /* [8][WFFT_TILE] */
+    float2* pre   = tiles + (size_t)8 * WFFT_TILE;                                /* [8][512] prefetched input blocks */
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pre + (size_t)8 * 512);           /* [8] one per warp */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = tiles + (size_t)warp * WFFT_TILE;
+    float2* mypre = pre + (size_t)warp * 512;
+    const int nRowPairs = a.rowsUsed >> 1, nKGin = (a.nIn + 3) >> 2;
+    const int nTiles = nRowPairs * nKGin;
+    const uint32_t bytes = (uint32_t)a.hop * 4u;
+    if (threadIdx.x < 8) mbar_init(&bar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    /* input block of this warp's transform in tile `tl`, or NULL (zero rows before the first / after the last frame, padding inputs) */
+    auto src_of = [&](int tl) -> const float* {
+        const int rp = tl % nRowPairs, kg = tl / nRowPairs;
+        const int ni = 4 * kg + (warp & 3);
+        const int t = 2 * rp + (warp >> 2) - (a.P - 1);
+        return (ni < a.nIn && t >= 0 && t < a.T) ? a.in + (size_t)ni * a.inStride + (size_t)t * a.hop : (const float*)0;
+    };
+    uint32_t ph = 0;
+    int cur = blockIdx.x;
+    if (cur < nTiles && lane == 0) {
+        const float* x = src_of(cur);
+        if (x) { mbar_expect_tx(&bar[warp], bytes); tma_bulk_g2s(mypre, x, bytes, &bar[warp]); }
+    }
+    const float sc = 0.5f * pow2_scale(a.scal[0]);
+    for (; cur < nTiles; cur += gridDim.x) {
+        const int rp = cur % nRowPairs, kg = cur / nRowPairs;
+        const int row0 = 2 * rp;
+        {
+            float2 v[32];
+            const bool valid = src_of(cur) != 0;                                   /* warp-uniform */
+            if (valid) { mbar_wait(&bar[warp], ph); ph ^= 1u; }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = lane + 32 * i;
+                v[i] = (valid && 2 * n < a.hop) ? mypre[n] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 16; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
+            __syncwarp();
+            const int nxt = cur + gridDim.x;
+            if (nxt < nTiles && lane == 0) {
+                const float* x = src_of(nxt);
+                if (x) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* generic reads of the slot before the async write */
+                    mbar_expect_tx(&bar[warp], bytes);
+                    tma_bulk_g2s(mypre, x, bytes, &bar[warp]);
+                }
+            }
+            wfft32t<false, true>(v, a.wT1, lane, tile);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tile[lane + 32 * wf_bitrev(i, 5)] = v[i];      /* Z[k], natural order */
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 2 * M; idx += OFFW_THREADS) {
+            const int f = idx & 1, k = idx >> 1;
+            const float2 w = __ldg(a.tw + k);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2* z = tiles + (size_t)(4 * f + j) * WFFT_TILE;
+                const float2 A = z[k], b = z[(M - k) & (M - 1)];
+                /* X[k] = (E + W_N^k O) / 2, E = a + conj b, O = -i (a - conj b) */
+                const float2 E = make_float2(A.x + b.x, A.y - b.y);
+                const float2 O = make_float2(A.y + b.y, b.x - A.x);
+                const float2 tt = cmulf(w, O);
+                float2 X = make_float2((E.x + tt.x) * sc, (E.y + tt.y) * sc);
+                if (k == 0) X = make_float2((A.x + A.y) * (2.f * sc), (A.x - A.y) * (2.f * sc));   /* packed (DC, Nyquist) */
+                f16_split2(X, hi[j], lo[j]);
+            }
+            const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f) * 16;
+            *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a.XGlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        __syncthreads();                                                          /* the tiles are rewritten by the next transform */
+    }
+}
+
 /* inverse: warp o -> output 8 og + o of frame t */
 __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_t_kernel(OffIfftArgs a)
 {
@@ -964,19 +1131,22 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_ifft_t_kernel(OffIfft
     float2* stg = reinterpret_cast<float2*>(smw);              /* spectra [k][9] (8 outputs + pad); then the warps' tiles */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int og = blockIdx.x, t = blockIdx.y;
-    for (int base = threadIdx.x; base < M * 8; base += 8 * OFFW_THREADS) {
-        float2 u[8];
+    {
+        /* all 32 loads of a thread are in flight before the first store: ONE DRAM round trip per CTA for the 64 KB of
+         * spectra (the registers are free here: the transform has not started) */
+        float2 u[32];
+        const int j = threadIdx.x & 7, no = og * 8 + j;
+        const float2* src = a.Ys + (size_t)(no >> a.logNn2) * a.ysTileC + ((size_t)t << a.logNn2) + (no & (a.Nn2 - 1));
+        const size_t kStride = (size_t)a.Tpad << a.logNn2;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int idx = base + q * OFFW_THREADS;
-            const int j = idx & 7, k = idx >> 3;
-            const int no = og * 8 + j;
-            u[q] = (no < a.nOut) ? __ldg(a.Ys + (size_t)(no >> a.logNn2) * a.ysTileC + (((size_t)k * a.Tpad + t) << a.logNn2) + (no & (a.Nn2 - 1))) : make_float2(0.f, 0.f);
+        for (int q = 0; q < 32; ++q) {
+            const int k = (threadIdx.x >> 3) + q * (OFFW_THREADS / 8);
+            u[q] = (no < a.nOut) ? __ldg(src + (size_t)k * kStride) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int idx = base + q * OFFW_THREADS;
-            stg[(idx >> 3) * 9 + (idx & 7)] = u[q];
+        for (int q = 0; q < 32; ++q) {
+            const int k = (threadIdx.x >> 3) + q * (OFFW_THREADS / 8);
+            stg[k * 9 + j] = u[q];
         }
     }
     __syncthreads();
@@ -1043,6 +1213,17 @@ static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cud
 static int offw_dispatch(int M, int variant, const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
 {
     if (M == 1024 && variant == 2) {                           /* shuffle-free 32 x 32 version */
+        if (f && f->rowsUsed > 0) {                            /* persistent + TMA-prefetched inputs (16-byte aligned rows) */
+            const size_t smem = (size_t)8 * WFFT_TILE * 8 + (size_t)8 * 512 * 8 + 64;
+            int dev = 0, sms = 0;
+            SC_CHECK(cudaGetDevice(&dev));
+            SC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            SC_CHECK(sc_optin_smem(offline_fft_p_kernel));
+            const int nTiles = (f->rowsUsed >> 1) * ((f->nIn + 3) >> 2);
+            const int ctas = nTiles < 2 * sms ? nTiles : 2 * sms;
+            offline_fft_p_kernel<<<ctas, OFFW_THREADS, smem, st>>>(*f);
+            return (int)cudaGetLastError();
+        }
         if (f) {
             const size_t smem = (size_t)8 * WFFT_TILE * 8;
             SC_CHECK(sc_optin_smem(offline_fft_t_kernel));
@@ -1102,7 +1283,12 @@ int scdev_offline_prepare(const scdev_plan* pl, const scdev_bufs* b, scdev_offli
     o->nKC = o->nKG / OFF_KG;
     o->rowsX = OFF_MT + pl->P - 1;
     o->tmemCols = 4 * Nn;                                            /* two buffer sets x two frame tiles */
-    o->gemmSmem = 2 * (2 * OFF_KG * o->rowsX * 16) + OFF_NH * (2 * OFF_KG * Nn * 16) + (8 + 2 * OFF_NH) * 8 + 16;
+    o->gemmSmem = 2 * (2 * OFF_KG * o->rowsX * 16) + OFF_NH * (2 * OFF_KG * Nn * 16) + (12 + 2 * OFF_NH) * 8 + 16;
+    if (!o->smCount) {
+        int dev = 0;
+        SC_CHECK(cudaGetDevice(&dev));
+        SC_CHECK(cudaDeviceGetAttribute(&o->smCount, cudaDevAttrMultiProcessorCount, dev));
+    }
     {
         const char* v = getenv("SAFCONV_OFF_FLUSH");
         int fl = v ? atoi(v) : 1;
@@ -1182,7 +1368,9 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     if (T < 1 || T > o->capFrames || skip < 0 || skip >= T) return (int)cudaErrorInvalidValue;
     const int Tpad = (int)roundup((size_t)T, OFF_MT);
     const int rowsAlloc = o->capRows;           /* row stride of the operand as allocated */
-    const int rowsUsed = (int)roundup((size_t)Tpad + pl->P - 1, OFF_FPC);
+    /* operand rows that hold this render's frames (row = P-1 + frame); rows up to the end of the last 256-frame tile
+     * keep whatever an earlier render left there: they only reach GEMM columns >= T, which are never read */
+    const int rowsUsed = (int)roundup((size_t)T + pl->P - 1, OFF_FPC);
 
     if (events) SC_CHECK(cudaEventRecord((cudaEvent_t)events[0], st));
     if (o->f16) {
@@ -1197,6 +1385,12 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     f.inStride = (size_t)T * pl->hop;
     f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
+    {   /* the persistent forward kernel needs 16-byte aligned input rows; SAFCONV_OFF_FFTP=0 selects the one-shot kernel */
+        static int pEnv = -1;
+        if (pEnv < 0) { const char* v = getenv("SAFCONV_OFF_FFTP"); pEnv = v ? atoi(v) : 1; }
+        const bool al = (pl->hop % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && ((((size_t)T * pl->hop) & 3) == 0);
+        f.rowsUsed = (pEnv && al) ? rowsUsed : 0;
+    }
     f.wT1 = (const float2*)o->wtab; f.wT2 = o->wtab ? (const float2*)o->wtab + pl->M : NULL;
     {
         f.fpc = o->fpc; f.ipc = o->ipc;
@@ -1215,16 +1409,23 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     g.HGhi = (const unsigned char*)o->HGhi; g.HGlo = (const unsigned char*)o->HGlo; g.Ys = o->Ys; g.scal = o->scal;
     g.P = pl->P; g.nKG = o->nKG; g.nKC = o->nKC; g.Nn = o->Nn; g.rowsAlloc = rowsAlloc; g.Tpad = o->capTpad;
     g.rowsX = o->rowsX; g.tmemCols = o->tmemCols; g.flush = o->flush;
+    g.T = T; g.nFT = (T + OFF_MT - 1) / OFF_MT; g.nBins = pl->M; g.nTilesTotal = g.nFT * pl->M * o->nTiles;
+    g.ticket = reinterpret_cast<int*>(o->scal + 2);
+    SC_CHECK(cudaMemsetAsync(g.ticket, 0, sizeof(int), st));
     g.hgTileBytes = (size_t)pl->M * pl->P * o->nKG * o->Nn * 16;
     g.ysTileFloats = (size_t)pl->M * o->capTpad * o->Nn;
     /* frames on the UMMA N axis (one M128 x N256 instruction per product term) when the filter rows fill M = 128 */
     static int ntEnv = -1;
     if (ntEnv < 0) { const char* v = getenv("SAFCONV_OFF_NT"); ntEnv = v ? atoi(v) : 1; }
     const int nt = ntEnv && o->Nn == 128;
-    const int mm = nt ? 128 : 128, nn = nt ? 256 : o->Nn;
-    g.idesc = o->f16 ? umma_idesc_f16(mm, nn) : umma_idesc_tf32(mm, nn);
+    const int mm = 128, nn = nt ? 0 : o->Nn;
+    g.idesc = o->f16 ? umma_idesc_f16(mm, nn) : umma_idesc_tf32(mm, nn);      /* NT: the N field is filled in per tile */
     {
-        dim3 grid(Tpad / OFF_MT, pl->M, o->nTiles);
+        static int ctasEnv = -1;
+        if (ctasEnv < 0) { const char* v = getenv("SAFCONV_OFF_CTAS"); ctasEnv = v ? atoi(v) : 0; }
+        int ctas = ctasEnv > 0 ? ctasEnv : o->smCount;
+        if (ctas > g.nTilesTotal) ctas = g.nTilesTotal;
+        dim3 grid(ctas);
         if (o->f16) { if (nt) offline_gemm_kernel<true, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);
                       else    offline_gemm_kernel<true, false><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g); }
         else        { if (nt) offline_gemm_kernel<false, true><<<grid, OFF_GEMM_THREADS, o->gemmSmem, st>>>(g);

@@ -71,6 +71,26 @@ __device__ __forceinline__ void dif_regs32(float2 (&v)[R])
     }
 }
 
+/* the same for an input whose upper half v[16..31] is zero (a zero-padded block: hop <= M real samples = M/2 complex
+ * points): the first stage degenerates to v[i+16] = v[i] * W_32^i -- no additions */
+template <bool INV>
+__device__ __forceinline__ void dif_regs32_zpad(float2 (&v)[32])
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i + 16] = mul_w32<INV>(v[i], i);
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if ((i & h) == 0) {
+                const float2 a = v[i], b = v[i + h];
+                v[i] = caddf(a, b);
+                v[i + h] = mul_w32<INV>(csubf(a, b), (i & (h - 1)) * (16 / h));
+            }
+        }
+    }
+}
+
 /* per-lane constants of the five shuffle stages */
 struct WfftLane {
     float2 w16, w8, w4, w2;
@@ -192,10 +212,10 @@ __device__ __forceinline__ void wfft_fwd_split(const float2 (&v)[R], float2 (&X)
  * The shuffle version issues 10 SHFL per point through the same LSU data pipe that serves shared memory (ncu: the
  * transform kernels were MIO-bound on it); this one needs 2 shared-memory accesses per point. */
 #define WFFT_TILE 1056     /* float2 per warp: 32 rows x 33 */
-template <bool INV>
+template <bool INV, bool ZPAD = false>
 __device__ __forceinline__ void wfft32t(float2 (&v)[32], const float2* __restrict__ T1, int lane, float2* tile)
 {
-    dif_regs32<32, INV>(v);
+    if (ZPAD) dif_regs32_zpad<INV>(v); else dif_regs32<32, INV>(v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         float2 w = __ldg(T1 + i * 32 + lane);

@@ -323,6 +323,24 @@ def test_offline_tensor_core_render_vs_oracle(saf, orc, hop, L, nIn, nOut, T):
     check(ys, y, "streaming vs offline")
 
 
+@pytest.mark.parametrize("nOut", [2, 64])          # frames on the UMMA M axis (Nn = 32) / on the N axis (Nn = 128)
+def test_offline_tail_tile_widths(saf, orc, nOut):
+    """The persistent GEMM cuts the last 256-frame tile of a render to roundup16(T - t0) columns (frames on N) or to one
+    128-row accumulator (frames on M): every width class, on ONE handle whose workspace keeps the rows of the longer
+    renders that came before (stale operand rows beyond T must never reach an output)."""
+    rng = np.random.default_rng(77 + nOut)
+    hop, L, nIn = 32, 100, 3
+    Ts = [513, 1, 15, 16, 17, 127, 128, 129, 255, 256, 257, 383, 400]
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * max(Ts))).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H)
+    for T in Ts:
+        y = mc.render_offline(x[:, :hop * T])
+        check(y, ref[:, :hop * T], f"offline render, T = {T}")
+    mc.destroy()
+
+
 @pytest.mark.parametrize("kind", ["f16", "tf32"])
 def test_offline_operand_kinds_and_dynamic_range(saf, orc, kind, monkeypatch):
     """Both tensor-core operand types of the offline path (fp16 hi/lo with power-of-two scaling = default, tf32 hi/lo)
