@@ -267,7 +267,7 @@ static void handle_free(safconv_handle* h)
     scdev_free(h->tailPass.ZpB);
     for (int i = 0; i < 6; i++) scdev_event_destroy(h->trEv[i]);
     scdev_free(h->d_in); scdev_free(h->d_out);
-    scdev_host_free(h->h_in); scdev_host_free(h->h_out);
+    scdev_host_free(h->h_in); scdev_host_free(h->h_out); scdev_host_free((void*)h->doneWord);
     scdev_stream_destroy(h->streamOwn);
     h->magic = 0;
     free(h);
@@ -355,6 +355,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     h->batching = 1;
     h->smallFused = env_int("SAFCONV_SMALL_FUSED", 1, 0, 1);
     h->hostTrace = env_int("SAFCONV_HOSTTRACE", 0, 0, 1);
+    h->flagWait = env_int("SAFCONV_FLAG_WAIT", 1, 0, 1);
 
     const size_t M = (size_t)pl->M, P = (size_t)pl->P;
     /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
@@ -446,6 +447,10 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     if (zalloc(h, (void**)&h->d_out, h->outBytes, "output staging")) goto fail;
     DEV_TRY(h, scdev_host_alloc((void**)&h->h_in, h->inBytes), "pinned input staging");
     DEV_TRY(h, scdev_host_alloc((void**)&h->h_out, h->outBytes), "pinned output staging");
+    if (h->smallOk) {
+        DEV_TRY(h, scdev_host_alloc((void**)&h->doneWord, 64), "completion word");
+        *h->doneWord = 0;
+    }
 
     /* K0: upload the time-domain filters once and transform them on the device (reference .c:116-125) */
     {
@@ -495,7 +500,7 @@ static int enqueue_blocks(safconv_handle* h, const float* d_in, float* d_out, in
     void** ev = NULL;
     int e = 0;
     if (pl->kind == SC_KIND_MATRIX && nBlocks == 1 && h->smallFused && h->smallOk && !h->useGraph && !h->timingCap) {
-        return scdev_small_fused(pl, &h->b, d_in, d_out, h->stream);     /* one launch instead of three */
+        return scdev_small_fused(pl, &h->b, d_in, d_out, h->stream, NULL, 0, NULL);     /* one launch instead of three */
     }
     if (pl->kind == SC_KIND_MATRIX) {
         if (h->timingCap && h->timingCount < h->timingCap) {
@@ -692,12 +697,13 @@ int sch_uses_lookahead(const safconv_handle* h)
 
 /* Blocks of up to 1 MB without look-ahead: the kernels read / write the page-locked host buffers directly -- no
  * copy-engine round trips, one synchronisation.  Returns -1 if the handle has no such path. */
-static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int irIdx)
+static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int irIdx, int* signalled)
 {
     const scdev_plan* pl = &h->pl;
+    *signalled = 0;
     if (!h->smallFused || h->useGraph || h->timingCap) return -1;
     if (pl->kind == SC_KIND_MATRIX && h->smallOk)                 /* small problem: K1 + K2 + K3 in ONE launch */
-        return scdev_small_fused(pl, &h->b, src, dst, h->stream);
+        return scdev_small_fused(pl, &h->b, src, dst, h->stream, (h->flagWait && h->doneWord) ? h->doneWord : NULL, ++h->doneSeq, signalled);
     if (h->inBytes > (1u << 20) || h->outBytes > (1u << 20)) return -1;
     if (pl->kind == SC_KIND_MULTI)                                /* one fused launch, one CTA per channel */
         return scdev_multi_fused(pl, &h->b, src, dst, h->stream);
@@ -747,10 +753,22 @@ void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx
     int e = scdev_set_device(h->device);
     if (e) { h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e); return; }
     const double t1 = h->hostTrace ? now_ns() : 0.0;
-    e = apply_zero_copy(h, src, dst, irIdx);
+    int signalled = 0;
+    e = apply_zero_copy(h, src, dst, irIdx, &signalled);
     if (e >= 0) {
         const double t2 = h->hostTrace ? now_ns() : 0.0;
-        if (!e) e = scdev_stream_sync(h->stream);
+        if (!e && signalled) {
+            /* the kernel writes the call's sequence number behind its last output store (system-scope fences): poll that
+             * word; after 2 ms without it (device busy elsewhere, or a fault) fall back to the stream, which also reports errors */
+            const unsigned int want = h->doneSeq;
+            const double tEnd = now_ns() + 2.0e6;
+            unsigned int spins = 0;
+            while (*h->doneWord != want) {
+                __builtin_ia32_pause();
+                if ((++spins & 1023u) == 0 && now_ns() > tEnd) { e = scdev_stream_sync(h->stream); break; }
+            }
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        } else if (!e) e = scdev_stream_sync(h->stream);
         if (h->hostTrace) { const double t3 = now_ns(); h->htAcc[1] += t2 - t1; h->htAcc[2] += t3 - t2; h->htN++; }
         if (e) { h_fail(h, SAFCONV_ERR_CUDA, "apply (zero-copy)", e); return; }
         h->count++;
@@ -1336,6 +1354,7 @@ int safconv_set_option(void* hp, const char* name, int value)
     else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
     else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
     else if (!strcmp(name, "small_fused")) { h->smallFused = value ? 1 : 0; }
+    else if (!strcmp(name, "flag_wait")) { h->flagWait = value ? 1 : 0; }
     else if (!strcmp(name, "detect_pinned")) { h->detectPinned = value ? 1 : 0; }
     else if (!strcmp(name, "lookahead")) { h->lookahead = (value && h->tailPass.Zp) ? 1 : 0; }
     else return SAFCONV_ERR_ARG;

@@ -62,6 +62,9 @@ typedef struct safconv_handle {
     int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
     int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
     void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
+    volatile unsigned int* doneWord; /* page-locked word the cluster latency kernel writes its sequence number into when the block's output is complete */
+    unsigned int doneSeq;
+    int        flagWait;             /* option "flag_wait" / SAFCONV_FLAG_WAIT: poll doneWord instead of synchronising the stream */
     int        hostTrace;            /* SAFCONV_HOSTTRACE=1: host-side time of the zero-copy apply by segment, printed at destroy */
     double     htAcc[3];             /* ns: argument / pinned checks, launch, wait for completion */
     unsigned   htN;

@@ -975,8 +975,16 @@ struct SmallCArgs {
     unsigned int* counters;
     int hop, P, nIn, nOut, nKT, OTsz, RS;
     float scale;
+    volatile unsigned int* done;   /* != NULL: page-locked host word that receives `seq` once every output sample has been written */
+    unsigned int seq;
+    unsigned long long* stamps;    /* debugging (SAFCONV_KSTAMPS=1): %globaltimer of CTA 0 at the phase boundaries */
 };
+__device__ __forceinline__ void cl_stamp(unsigned long long* stamps, int i)
+{
+    if (stamps && threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamps[i] = t; }
+}
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint32_t cl_ctarank()  { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cl_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cl_sync()
@@ -1002,48 +1010,85 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
     const int nOwn = (a.nOut - c + C - 1) / C;                  /* outputs c, c + C, ... */
     const int nOwnMax = (a.nOut + C - 1) / C;
     float2* red = smc + (size_t)nOwnMax * ZS;                   /* [warps][32] partial sums */
+    cl_stamp(a.stamps, 0);
+    /* the input block of this warp's (first) transform: its PCIe round trip (mapped host memory) is the longest latency
+     * of the kernel, so these loads are issued before anything else */
+    const bool vecIn = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
+    float2 v[R];
+    int niA = c + C * warp;
+    auto load_block = [&](int ni) {
+        const float* x = a.in + (size_t)ni * a.hop;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int n = lane + 32 * i;
+            v[i] = make_float2(0.f, 0.f);
+            if (vecIn) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+            else {
+                if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
+                if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+            }
+        }
+    };
+    if (R <= 16 && niA < a.nIn) load_block(niA);                /* R = 32 keeps its registers for the prologue: loaded in phase A */
     const unsigned int count = a.counters[0];
     const int head = (int)(count % (unsigned)a.RS);
     const WfftLane Lf = wfft_lane_init<false>(a.tw, M, lane);
     WfftLane Li = Lf;
     Li.w16.y = -Li.w16.y; Li.w8.y = -Li.w8.y; Li.w4.y = -Li.w4.y; Li.w2.y = -Li.w2.y;
     const int k1 = (int)(__brev((unsigned)lane) >> 27);
+    /* the twiddle tables of both transforms (L2 -> L1 while the input block is still on its way over PCIe) */
+    for (int l = threadIdx.x; l < (2 * M) / 16; l += SC_CL_THREADS) prefetch_l1(a.wT1 + 16 * l);     /* T1 and T2 are one array */
+    for (int l = threadIdx.x; l < M / 16; l += SC_CL_THREADS) prefetch_l1(a.tw + 16 * l);
     /* overlap tail of the output this warp owns: fetched now, used at the very end (hop <= M) */
     const int noMine = c + C * warp;
-    float tl[R];
+    constexpr bool TLPRE = (R <= 16);                           /* R = 32: the registers are needed by the transform itself */
+    float tl[TLPRE ? R : 1];
+    if (TLPRE) {
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
-        const int i = lane + 32 * u;
-        tl[u] = (warp < nOwn && i < a.hop) ? a.tail[(size_t)noMine * a.hop + i] : 0.f;
+        for (int u = 0; u < R; ++u) {
+            const int i = lane + 32 * u;
+            tl[TLPRE ? u : 0] = (warp < nOwn && i < a.hop) ? a.tail[(size_t)noMine * a.hop + i] : 0.f;
+        }
     }
 
-    /* ---- A: forward FFTs of the inputs this CTA owns ---- */
+    /* the rows phase B of this CTA will read -- its units' filter rows and the delay-line rows of the OLDER blocks -- are
+     * pulled into L1 now: lane = row (256 bytes = two 128-byte lines) */
     {
-        const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
-        for (int ni = c + C * warp; ni < a.nIn; ni += C * SC_CL_WARPS) {
-            const float* x = a.in + (size_t)ni * a.hop;
-            float2 v[R];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int n = lane + 32 * i;
-                v[i] = make_float2(0.f, 0.f);
-                if (vec) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
-                else {
-                    if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
-                    if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+        const int nUnits = a.nOut * a.nKT, nTerms = a.P * a.nIn;
+        for (int u = c; u < nUnits; u += C) {
+            const int kt = u / a.nOut, no = u - kt * a.nOut;
+            const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
+            const float2* Hk = a.H + ((size_t)(ot * a.nKT + kt) * a.P * a.nIn * a.OTsz + nl) * SC_BK;
+            const float2* Xk = a.X + (size_t)kt * a.RS * a.nIn * SC_BK;
+            for (int t = threadIdx.x; t < nTerms; t += SC_CL_THREADS) {
+                const int p = t / a.nIn, ni = t - p * a.nIn;
+                const float2* h = Hk + (size_t)t * a.OTsz * SC_BK;
+                prefetch_l1(h); prefetch_l1(h + 16);
+                if (p > 0) {
+                    int slot = head - p; if (slot < 0) slot += a.RS;
+                    const float2* x = Xk + ((size_t)slot * a.nIn + ni) * SC_BK;
+                    prefetch_l1(x); prefetch_l1(x + 16);
                 }
-            }
-            wfft<R, false>(v, a.wT1, lane, Lf);
-            float2 Xs[R];
-            wfft_fwd_split<R>(v, Xs, a.wT2, lane, 0.5f);
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int k = wf_bitrev(i, LOGR) + R * k1;
-                a.X[(((size_t)(k >> 5) * a.RS + head) * a.nIn + ni) * SC_BK + (k & 31)] = Xs[i];
             }
         }
     }
+    /* ---- A: forward FFTs of the inputs this CTA owns ---- */
+    if (R > 16 && niA < a.nIn) load_block(niA);
+    while (niA < a.nIn) {                                       /* warp-uniform */
+        wfft<R, false>(v, a.wT1, lane, Lf);
+        float2 Xs[R];
+        wfft_fwd_split<R>(v, Xs, a.wT2, lane, 0.5f);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int k = wf_bitrev(i, LOGR) + R * k1;
+            a.X[(((size_t)(k >> 5) * a.RS + head) * a.nIn + niA) * SC_BK + (k & 31)] = Xs[i];
+        }
+        niA += C * SC_CL_WARPS;
+        if (niA < a.nIn) load_block(niA);
+    }
+    cl_stamp(a.stamps, 1);
     cl_sync();
+    cl_stamp(a.stamps, 2);
     if (c == 0 && threadIdx.x == 0) a.counters[0] = count + 1u;     /* every CTA has read it before the barrier */
 
     /* ---- B: Z[no][k] = sum_p sum_ni H_p[no][ni][k] * X_{t-p}[ni][k] ---- */
@@ -1063,17 +1108,31 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
                 const int ot = no / a.OTsz, nl = no - ot * a.OTsz;
                 const bool packed = (kt == 0 && lane == 0);
                 const int t0 = (int)(((long long)nTerms * g) / wpu), t1 = (int)(((long long)nTerms * (g + 1)) / wpu);
-                int p = t0 / a.nIn, ni = t0 - p * a.nIn;
-                int slot = head - p; if (slot < 0) slot += a.RS;
                 const float2* Hk = a.H + ((size_t)(ot * a.nKT + kt) * a.P * a.nIn * a.OTsz + nl) * SC_BK + lane;
                 const float2* Xk = a.X + (size_t)kt * a.RS * a.nIn * SC_BK + lane;
                 float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 8
-                for (int t = t0; t < t1; ++t) {
-                    const float2 h = __ldg(Hk + (size_t)(p * a.nIn + ni) * a.OTsz * SC_BK);
-                    const float2 x = __ldcg(Xk + ((size_t)slot * a.nIn + ni) * SC_BK);   /* written by other CTAs of this launch: L2 */
-                    cmac_packed(acc, h, x, packed);
-                    if (++ni == a.nIn) { ni = 0; ++p; slot = (slot == 0) ? a.RS - 1 : slot - 1; }
+                /* eight terms per trip, all sixteen loads issued before the first use (a warp typically owns fewer than eight
+                 * terms: a plain loop would walk them one L2 round trip at a time); same summation order as a plain loop */
+                int p = t0 / a.nIn, ni = t0 - p * a.nIn;             /* walked incrementally: no division per term */
+                int slot = head - p; if (slot < 0) slot += a.RS;
+                const unsigned hStep = (unsigned)a.OTsz * SC_BK;
+                for (int tb = t0; tb < t1; tb += 8) {
+                    float2 hv[8], xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = tb + u;
+                        hv[u] = make_float2(0.f, 0.f); xv[u] = hv[u];
+                        if (t < t1) {
+                            hv[u] = __ldg(Hk + (unsigned)t * hStep);
+                            const float2* xp = Xk + (unsigned)(slot * a.nIn + ni) * SC_BK;
+                            xv[u] = (p == 0) ? __ldcg(xp)         /* written by other CTAs of this launch: L2 */
+                                             : __ldg(xp);         /* older blocks: prefetched into L1 above */
+                            if (++ni == a.nIn) { ni = 0; ++p; slot = (slot == 0) ? a.RS - 1 : slot - 1; }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (tb + u < t1) cmac_packed(acc, hv[u], xv[u], packed);
                 }
                 red[warp * 32 + lane] = acc;
             }
@@ -1086,7 +1145,9 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
             __syncthreads();
         }
     }
+    cl_stamp(a.stamps, 3);
     cl_sync();
+    cl_stamp(a.stamps, 4);
 
     /* ---- C: inverse FFT + overlap-add of the outputs this CTA owns (reference .c:230-233) ---- */
     if (warp < nOwn) {
@@ -1117,8 +1178,24 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
             if (i < a.hop) {
                 const int s1 = i + a.hop;
                 const int n0 = i >> 1, n1 = s1 >> 1;
-                out[i]  = zf[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)] + tl[u];
+                out[i]  = zf[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)] + (TLPRE ? tl[TLPRE ? u : 0] : tail[i]);
                 tail[i] = zf[2 * ((n1 & (R - 1)) + (R + 1) * (n1 >> LOGR)) + (s1 & 1)];
+            }
+        }
+        if (warp == 0) cl_stamp(a.stamps, 5);
+        if (a.done) {
+            /* host-visible completion: every owner warp fences its output stores at system scope and takes a ticket; the last
+             * one writes the sequence number into the host word the caller is polling (saves the end-of-kernel
+             * signalling + cudaStreamSynchronize wake-up of a few microseconds per block) */
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int t = atomicAdd(&a.counters[2], 1u);
+                if (t == (unsigned)a.nOut - 1u) {
+                    a.counters[2] = 0;
+                    __threadfence_system();
+                    *a.done = a.seq;
+                }
             }
         }
     }
@@ -1151,9 +1228,16 @@ static int small_cluster_launch(const SmallCArgs& a, int C, cudaStream_t st)
     return (int)cudaLaunchKernelEx(&cfg, small_cluster_kernel<R>, a);
 }
 
-static int scdev_small_cluster(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, cudaStream_t st)
+static int scdev_small_cluster(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, cudaStream_t st,
+                               volatile unsigned int* done, unsigned int seq)
 {
     SmallCArgs a;
+    a.done = done; a.seq = seq; a.stamps = NULL;
+    static int ks = -1;
+    static unsigned long long* d_st = NULL;
+    static double acc[5]; static int nAcc = 0;
+    if (ks < 0) { const char* v = getenv("SAFCONV_KSTAMPS"); ks = v ? atoi(v) : 0; if (ks && cudaMalloc(&d_st, 64) != cudaSuccess) ks = 0; }
+    if (ks) a.stamps = d_st;
     a.in = in; a.out = out; a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
     a.wT1 = (const float2*)b->wtab; a.wT2 = (const float2*)b->wtab + pl->M;
     a.tail = b->tail; a.counters = b->counters;
@@ -1162,14 +1246,27 @@ static int scdev_small_cluster(const scdev_plan* pl, const scdev_bufs* b, const 
     int work = pl->nOutLocal * pl->nKT;
     if (pl->nIn > work) work = pl->nIn;
     const int C = work < SC_CL_MAXC ? work : SC_CL_MAXC;
+    int e;
     switch (pl->M) {
-        case 64:   return small_cluster_launch<2>(a, C, st);
-        case 128:  return small_cluster_launch<4>(a, C, st);
-        case 256:  return small_cluster_launch<8>(a, C, st);
-        case 512:  return small_cluster_launch<16>(a, C, st);
-        case 1024: return small_cluster_launch<32>(a, C, st);
+        case 64:   e = small_cluster_launch<2>(a, C, st); break;
+        case 128:  e = small_cluster_launch<4>(a, C, st); break;
+        case 256:  e = small_cluster_launch<8>(a, C, st); break;
+        case 512:  e = small_cluster_launch<16>(a, C, st); break;
+        case 1024: e = small_cluster_launch<32>(a, C, st); break;
         default:   return (int)cudaErrorInvalidValue;
     }
+    if (ks && !e) {                                             /* debugging only: phase durations of CTA 0, averaged */
+        unsigned long long h[6];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_st, sizeof h, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 5; ++i) acc[i] += (double)(h[i + 1] - h[i]);
+        if (++nAcc == 1000) {
+            fprintf(stderr, "small_cluster phases (us): A %.2f, barrier %.2f, B %.2f, barrier %.2f, C %.2f\n",
+                    acc[0] * 1e-6, acc[1] * 1e-6, acc[2] * 1e-6, acc[3] * 1e-6, acc[4] * 1e-6);
+            nAcc = 0; for (int i = 0; i < 5; ++i) acc[i] = 0;
+        }
+    }
+    return e;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1783,9 +1880,16 @@ int scdev_small_fits(const scdev_plan* pl, int maxSmemOptin)
     return 1;
 }
 
-int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream)
+/* done / seq: optional host-visible completion word (page-locked, mapped) -- only the cluster kernel signals it; *signalled
+ * tells the caller whether it may poll the word instead of synchronising the stream */
+int scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream,
+                      volatile unsigned int* done, unsigned int seq, int* signalled)
 {
-    if (small_cluster_ok(pl, b)) return scdev_small_cluster(pl, b, in, out, (cudaStream_t)stream);
+    if (signalled) *signalled = 0;
+    if (small_cluster_ok(pl, b)) {
+        if (signalled) *signalled = done != NULL;
+        return scdev_small_cluster(pl, b, in, out, (cudaStream_t)stream, done, seq);
+    }
     SmallArgs a;
     a.in = in; a.out = out; a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
     a.tail = b->tail; a.counters = b->counters;

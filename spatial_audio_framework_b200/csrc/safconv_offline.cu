@@ -209,7 +209,6 @@ struct OffFftArgs {
     const float* scal;     /* fp16 operands: scal[0] = bound on the input spectra */
     size_t inStride;       /* T*hop */
     int hop, nIn, M, logM, P, T, rowsAlloc, nKG;
-    int rowsUsed;          /* operand rows this launch fills (persistent kernel) */
     int fpc;               /* frames per CTA (2 or 4): 32- or 64-byte contiguous operand stores */
     int ipc;               /* inputs per CTA = inputs per k-group: 2 (tf32) or 4 (fp16) */
     const float2* wT1;     /* warp-FFT tables (device, [R][32] each): step-2 twiddles, split twiddles */
@@ -993,7 +992,7 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftAr
         const float* x = a.in + (size_t)(valid ? ni : 0) * a.inStride + (size_t)(valid ? t : 0) * a.hop;
         const bool vec = ((a.hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0) && ((a.inStride & 1) == 0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
             const int n = lane + 32 * i;
             v[i] = make_float2(0.f, 0.f);
             if (valid) {
@@ -1004,7 +1003,10 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftAr
                 }
             }
         }
-        wfft32t<false>(v, a.wT1, lane, tile);
+#pragma unroll
+        for (int i = 16; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
+        /* hop <= M real samples = at most M/2 complex points: v[16..31] are zero, the first stage needs no additions */
+        wfft32t<false, true>(v, a.wT1, lane, tile);
 #pragma unroll
         for (int i = 0; i < 32; ++i) tile[lane + 32 * wf_bitrev(i, 5)] = v[i];      /* Z[k], natural order */
     }
@@ -1029,97 +1031,6 @@ __global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_t_kernel(OffFftAr
         const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f) * 16;
         *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(a.XGlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-
-/* The same forward kernel, PERSISTENT with the next tile's input blocks prefetched by TMA: every warp owns a 4 KB
- * shared-memory slot; one lane issues a bulk copy (cp.async.bulk) of its next input block as soon as the warp has moved
- * the current one into registers, so the DRAM round trip of tile i+1 runs under the transform + split + stores of tile i
- * (ncu, r01/r02: the one-shot kernel is 55 % issue-active at 25 % occupancy -- 128 registers per thread leave two CTAs per
- * SM, and both sit in their load phase for a good part of their life).  The input is a zero-padded block (hop <= M real
- * samples = at most M/2 complex points), so the first radix-2 stage of the transform needs no additions (ZPAD).
- * Needs 16-byte aligned input rows (hop % 4 == 0, 16-byte aligned base and channel stride).  grid = min(tiles, 2 * SMs),
- * tile = row pair (fastest, so CTAs that run together store adjacent operand rows) x input group. */
-__global__ void __launch_bounds__(OFFW_THREADS, 2) offline_fft_p_kernel(OffFftArgs a)
-{
-    constexpr int M = 1024;
-    extern __shared__ __align__(128) unsigned char smw[];
-    float2* tiles = reinterpret_cast<float2*>(smw);                               /* [8][WFFT_TILE] */
-    float2* pre   = tiles + (size_t)8 * WFFT_TILE;                                /* [8][512] prefetched input blocks */
-    uint64_t* bar = reinterpret_cast<uint64_t*>(pre + (size_t)8 * 512);           /* [8] one per warp */
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* tile = tiles + (size_t)warp * WFFT_TILE;
-    float2* mypre = pre + (size_t)warp * 512;
-    const int nRowPairs = a.rowsUsed >> 1, nKGin = (a.nIn + 3) >> 2;
-    const int nTiles = nRowPairs * nKGin;
-    const uint32_t bytes = (uint32_t)a.hop * 4u;
-    if (threadIdx.x < 8) mbar_init(&bar[threadIdx.x], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    /* input block of this warp's transform in tile `tl`, or NULL (zero rows before the first / after the last frame, padding inputs) */
-    auto src_of = [&](int tl) -> const float* {
-        const int rp = tl % nRowPairs, kg = tl / nRowPairs;
-        const int ni = 4 * kg + (warp & 3);
-        const int t = 2 * rp + (warp >> 2) - (a.P - 1);
-        return (ni < a.nIn && t >= 0 && t < a.T) ? a.in + (size_t)ni * a.inStride + (size_t)t * a.hop : (const float*)0;
-    };
-    uint32_t ph = 0;
-    int cur = blockIdx.x;
-    if (cur < nTiles && lane == 0) {
-        const float* x = src_of(cur);
-        if (x) { mbar_expect_tx(&bar[warp], bytes); tma_bulk_g2s(mypre, x, bytes, &bar[warp]); }
-    }
-    const float sc = 0.5f * pow2_scale(a.scal[0]);
-    for (; cur < nTiles; cur += gridDim.x) {
-        const int rp = cur % nRowPairs, kg = cur / nRowPairs;
-        const int row0 = 2 * rp;
-        {
-            float2 v[32];
-            const bool valid = src_of(cur) != 0;                                   /* warp-uniform */
-            if (valid) { mbar_wait(&bar[warp], ph); ph ^= 1u; }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = lane + 32 * i;
-                v[i] = (valid && 2 * n < a.hop) ? mypre[n] : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
-            __syncwarp();
-            const int nxt = cur + gridDim.x;
-            if (nxt < nTiles && lane == 0) {
-                const float* x = src_of(nxt);
-                if (x) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* generic reads of the slot before the async write */
-                    mbar_expect_tx(&bar[warp], bytes);
-                    tma_bulk_g2s(mypre, x, bytes, &bar[warp]);
-                }
-            }
-            wfft32t<false, true>(v, a.wT1, lane, tile);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tile[lane + 32 * wf_bitrev(i, 5)] = v[i];      /* Z[k], natural order */
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < 2 * M; idx += OFFW_THREADS) {
-            const int f = idx & 1, k = idx >> 1;
-            const float2 w = __ldg(a.tw + k);
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2* z = tiles + (size_t)(4 * f + j) * WFFT_TILE;
-                const float2 A = z[k], b = z[(M - k) & (M - 1)];
-                /* X[k] = (E + W_N^k O) / 2, E = a + conj b, O = -i (a - conj b) */
-                const float2 E = make_float2(A.x + b.x, A.y - b.y);
-                const float2 O = make_float2(A.y + b.y, b.x - A.x);
-                const float2 tt = cmulf(w, O);
-                float2 X = make_float2((E.x + tt.x) * sc, (E.y + tt.y) * sc);
-                if (k == 0) X = make_float2((A.x + A.y) * (2.f * sc), (A.x - A.y) * (2.f * sc));   /* packed (DC, Nyquist) */
-                f16_split2(X, hi[j], lo[j]);
-            }
-            const size_t o = (((size_t)k * a.nKG + kg) * a.rowsAlloc + row0 + f) * 16;
-            *reinterpret_cast<uint4*>(a.XGhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(a.XGlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        __syncthreads();                                                          /* the tiles are rewritten by the next transform */
     }
 }
 
@@ -1213,17 +1124,6 @@ static int offw_launch(const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cud
 static int offw_dispatch(int M, int variant, const OffFftArgs* f, const OffIfftArgs* i, dim3 grid, cudaStream_t st)
 {
     if (M == 1024 && variant == 2) {                           /* shuffle-free 32 x 32 version */
-        if (f && f->rowsUsed > 0) {                            /* persistent + TMA-prefetched inputs (16-byte aligned rows) */
-            const size_t smem = (size_t)8 * WFFT_TILE * 8 + (size_t)8 * 512 * 8 + 64;
-            int dev = 0, sms = 0;
-            SC_CHECK(cudaGetDevice(&dev));
-            SC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            SC_CHECK(sc_optin_smem(offline_fft_p_kernel));
-            const int nTiles = (f->rowsUsed >> 1) * ((f->nIn + 3) >> 2);
-            const int ctas = nTiles < 2 * sms ? nTiles : 2 * sms;
-            offline_fft_p_kernel<<<ctas, OFFW_THREADS, smem, st>>>(*f);
-            return (int)cudaGetLastError();
-        }
         if (f) {
             const size_t smem = (size_t)8 * WFFT_TILE * 8;
             SC_CHECK(sc_optin_smem(offline_fft_t_kernel));
@@ -1385,12 +1285,6 @@ int scdev_offline_run(const scdev_plan* pl, const scdev_bufs* b, scdev_offline* 
     f.inStride = (size_t)T * pl->hop;
     f.hop = pl->hop; f.nIn = pl->nIn; f.M = pl->M; f.logM = pl->logM; f.P = pl->P; f.T = T;
     f.rowsAlloc = rowsAlloc; f.nKG = o->nKG;
-    {   /* the persistent forward kernel needs 16-byte aligned input rows; SAFCONV_OFF_FFTP=0 selects the one-shot kernel */
-        static int pEnv = -1;
-        if (pEnv < 0) { const char* v = getenv("SAFCONV_OFF_FFTP"); pEnv = v ? atoi(v) : 1; }
-        const bool al = (pl->hop % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && ((((size_t)T * pl->hop) & 3) == 0);
-        f.rowsUsed = (pEnv && al) ? rowsUsed : 0;
-    }
     f.wT1 = (const float2*)o->wtab; f.wT2 = o->wtab ? (const float2*)o->wtab + pl->M : NULL;
     {
         f.fpc = o->fpc; f.ipc = o->ipc;
