@@ -43,6 +43,8 @@ WORKLOADS = {
                desc="saf_matrixConv 64-in x 64-out, hop 1024, 96000-tap RIRs (BASELINE.json configs[3])"),
     "C4s": dict(kind="matrix", nIn=64, nOut=64, hop=1024, L=8192,
                 desc="C4 scaled down to 8192 taps (debug only)"),
+    "C4g8": dict(kind="matrix", nIn=64, nOut=8, hop=1024, L=96000,
+                 desc="one GPU's share of configs[3] at 8 GPUs: 64-in x 8-out, hop 1024, 96000 taps (debug: per-block call overhead at 62 us of filter stream)"),
     "UT": dict(kind="matrix", nIn=32, nOut=40, hop=2048, L=512,
                desc="test__saf_matrixConv shape 32x40, hop 2048, 512 taps"),
     "C3": dict(kind="multi", nIn=256, nOut=256, hop=512, L=4096,

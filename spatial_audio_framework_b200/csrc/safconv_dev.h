@@ -130,6 +130,7 @@ int  scdev_stream_wait_event(void* stream, void* e);
 int  scdev_event_done(void* e);                 /* 1 complete / never recorded, 0 pending, < 0 error */
 int  scdev_event_record(void* e, void* stream);
 int  scdev_event_sync(void* e);
+int  scdev_last_error_clear(void);             /* returns and clears the runtime's last (non-sticky) error */
 int  scdev_event_elapsed_ms(void* e0, void* e1, float* ms);
 int  scdev_graph_begin(void* stream);
 int  scdev_graph_end(void* stream, void** graphExec);

@@ -60,6 +60,13 @@ int sch_thread_device(void) { return tl_device; }
 /*  planning                                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 
+static inline double now_ns(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e9 + (double)ts.tv_nsec;
+}
+
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 /* FFT size: the reference uses exactly 2*hop (saf_utility_matrixConv.c:100); we need a power of two,
@@ -263,6 +270,9 @@ static void handle_free(safconv_handle* h)
     if (h->streamIn) scdev_stream_sync(h->streamIn);
     if (h->streamOut) scdev_stream_sync(h->streamOut);
     scdev_event_destroy(h->evDone); scdev_event_destroy(h->evIn); scdev_event_destroy(h->evFence); scdev_event_destroy(h->evMac); scdev_event_destroy(h->evTail);
+    scdev_event_destroy(h->evTailB[0]); scdev_event_destroy(h->evTailB[1]);
+    if (h->tlEv) for (int i = 0; i < 8 * h->tlCap; i++) scdev_event_destroy(h->tlEv[i]);
+    free(h->tlEv); free(h->tlHost); free(h->tlReg);
     scdev_stream_destroy(h->streamIn); scdev_stream_destroy(h->streamOut);
     scdev_free(h->tailPass.ZpB);
     for (int i = 0; i < 6; i++) scdev_event_destroy(h->trEv[i]);
@@ -410,19 +420,34 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         rowsTotal = (size_t)nIRs * nOutLocal;
     }
     if (kind == SC_KIND_MATRIX && pl->P >= 2) {
-        if (make_pass(h, &h->tailPass, 1, pl->P - 1) || make_pass(h, &h->headPass, 0, 1)) goto fail;
+        /* look-ahead depth D: the tail pass of block b covers partitions p >= D (it reads X(b-D) and older, so it can be
+         * enqueued D calls ahead), the head pass partitions p < D.  D = 2 (SAFCONV_LA_DEPTH=2) keeps TWO tail passes queued,
+         * which makes back-to-back call times very even (C4: p99 0.47 ms instead of 0.89 ms) at the price of a head pass
+         * twice as long (paced p50 63 instead of 55 us); measured on both, D = 1 stays the default */
+        h->laDepth = (pl->P >= 3) ? env_int("SAFCONV_LA_DEPTH", 1, 1, 2) : 1;
+        if (make_pass(h, &h->tailPass, h->laDepth, pl->P - h->laDepth) || make_pass(h, &h->headPass, 0, h->laDepth)) goto fail;
         DEV_TRY(h, scdev_event_create_sync(&h->evDone), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evIn), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evFence), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evMac), "cudaEventCreate");
         DEV_TRY(h, scdev_event_create_sync(&h->evTail), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evTailB[0]), "cudaEventCreate");
+        DEV_TRY(h, scdev_event_create_sync(&h->evTailB[1]), "cudaEventCreate");
         DEV_TRY(h, scdev_stream_create(&h->streamIn), "cudaStreamCreate");
         DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
-        h->headInK3 = env_int("SAFCONV_HEAD_IN_K3", 1, 0, 1);
+        h->headInK3 = env_int("SAFCONV_HEAD_IN_K3", 0, 0, 1);   /* since K3 gathers in three load rounds, head pass + K3 (55 us) beats K3 adding the partition itself (62 us) */
         h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
         for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
+        h->tlCap = env_int("SAFCONV_TIMELINE", 0, 0, 256);
+        if (h->tlCap) {
+            h->tlEv = (void**)calloc((size_t)8 * h->tlCap, sizeof(void*));
+            h->tlHost = (double*)calloc((size_t)2 * h->tlCap, sizeof(double));
+            h->tlReg = (char*)calloc((size_t)h->tlCap, 1);
+            if (!h->tlEv || !h->tlHost || !h->tlReg) { h_fail(h, SAFCONV_ERR_NOMEM, "timeline buffers", 0); goto fail; }
+            for (int i = 0; i < 8 * h->tlCap; i++) DEV_TRY(h, scdev_event_create(&h->tlEv[i]), "cudaEventCreate");
+        }
     }
     h->smallOk = (kind == SC_KIND_MATRIX) ? scdev_small_fits(pl, h->maxSmem) : 0;
     if ((kind == SC_KIND_MULTI && env_int("SAFCONV_MULTI_WFFT", 1, 0, 1)) || (kind == SC_KIND_MATRIX && h->smallOk))
@@ -556,6 +581,7 @@ static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out) { r
  *           evTail     end of the most recent tail pass;  evDone  this block's output is complete */
 
 #define LA_TRY(call) do { if (!e) e = (call); } while (0)
+#define LA_TL(i, st) do { if (h->tlEv && h->tlN < h->tlCap) scdev_event_record(h->tlEv[8 * h->tlN + (i)], (st)); } while (0)
 #define LA_TRACE(i, st) do { if (tr) scdev_event_record(h->trEv[i], (st)); } while (0)
 
 /* K1 of the new block; returns with `stream` ordered behind it.  Three sources (sch_la_io): a copy-engine upload into
@@ -575,7 +601,9 @@ static int la_input(safconv_handle* h, const sch_la_io* io)
         LA_TRY(scdev_stream_wait_event(h->streamIn, h->evFence));
     }
     if (io->evSrc) LA_TRY(scdev_stream_wait_event(h->streamIn, io->evSrc));
+    LA_TL(0, h->streamIn);
     LA_TRY(scdev_input_fft(pl, &h->b, io->k1src, 1, h->streamIn));
+    LA_TL(1, h->streamIn);
     LA_TRY(scdev_event_record(h->evIn, h->streamIn));
     LA_TRY(scdev_stream_wait_event(h->stream, h->evIn));
     return e;
@@ -595,16 +623,15 @@ static int la_throughput(safconv_handle* h, unsigned int c, const sch_la_io* io,
     float* const kout = io->kout;
     int e = 0;
     if (!zc) e = scdev_event_record(h->evMac, h->stream);                 /* K1 ran on `stream`: its spectrum is ready here */
-    LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream));
     LA_TRY(scdev_stream_wait_event(h->streamOut, zc ? h->evIn : h->evMac));
-    LA_TRACE(0, h->streamOut);
+    LA_TRACE(0, h->streamOut); LA_TL(2, h->streamOut);
     LA_TRY(scdev_mac_pass(pl, &h->b, &head2, 0, 1, 0, -1, h->streamOut));
-    LA_TRACE(1, h->streamOut);
-    LA_TRY(scdev_stream_wait_event(h->streamOut, h->evTail));             /* tail pass of block c: K3 needs both */
-    LA_TRACE(3, h->streamOut);
+    LA_TRACE(1, h->streamOut); LA_TL(3, h->streamOut);
+    LA_TRY(scdev_stream_wait_event(h->streamOut, h->evTailB[tb]));        /* tail pass of block c: K3 needs both */
+    LA_TRACE(3, h->streamOut); LA_TL(4, h->streamOut);
     LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->streamOut));
     if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->streamOut));
-    LA_TRACE(4, h->streamOut);
+    LA_TRACE(4, h->streamOut); LA_TL(5, h->streamOut);
     LA_TRY(scdev_event_record(h->evDone, h->streamOut));
     return e;
 }
@@ -620,10 +647,10 @@ static int la_latency(safconv_handle* h, unsigned int c, int hadTail, const sch_
     float* const kout = io->kout;
     int e = 0;
     if (hadTail && h->headInK3) {
-        LA_TRACE(0, h->stream); LA_TRACE(1, h->stream); LA_TRACE(3, h->stream);
+        LA_TRACE(0, h->stream); LA_TRACE(1, h->stream); LA_TRACE(3, h->stream); LA_TL(2, h->stream); LA_TL(3, h->stream); LA_TL(4, h->stream);
         LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, NULL, kout, h->stream));
         if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->stream));
-        LA_TRACE(4, h->stream);
+        LA_TRACE(4, h->stream); LA_TL(5, h->stream);
         LA_TRY(scdev_event_record(h->evDone, h->stream));
     } else {
         LA_TRACE(0, h->stream);
@@ -640,7 +667,6 @@ static int la_latency(safconv_handle* h, unsigned int c, int hadTail, const sch_
         LA_TRY(scdev_event_record(h->evDone, h->streamOut));
         LA_TRY(scdev_stream_wait_event(h->stream, h->evDone));
     }
-    LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, tb ^ 1, (long long)c + 1, h->stream));
     return e;
 }
 
@@ -653,33 +679,79 @@ static void la_trace_report(safconv_handle* h, unsigned int c, int tr)
         scdev_event_elapsed_ms(h->trEv[0], h->trEv[1], &head);
         scdev_event_elapsed_ms(h->trEv[1], h->trEv[3], &k3wait);
         scdev_event_elapsed_ms(h->trEv[3], h->trEv[4], &k3);
-        fprintf(stderr, "[safconv trace] block %u: prev tail end -> head start %.1f us, head %.1f us, head end -> K3 start %.1f us, K3 %.1f us\n",
-                c, 1e3f * gap, 1e3f * head, 1e3f * k3wait, 1e3f * k3);
+        fprintf(stderr, "[safconv trace] block %u (%s): prev tail end -> head start %.1f us, head %.1f us, head end -> K3 start %.1f us, K3 %.1f us\n",
+                c, h->trRegime ? "throughput" : "latency", 1e3f * gap, 1e3f * head, 1e3f * k3wait, 1e3f * k3);
     }
     if (h->trace) scdev_event_record(h->trEv[2], h->stream);      /* end of the tail pass just enqueued: read by the next call */
+}
+
+/* SAFCONV_TIMELINE=n: the device timeline of the first n look-ahead calls, microseconds since K1 of the first one
+ * (missing stages -- no head pass in the latency regime, cold start -- print as '-') */
+static void la_timeline_print(safconv_handle* h)
+{
+    scdev_stream_sync(h->stream); scdev_stream_sync(h->streamOut); scdev_stream_sync(h->streamIn);
+    static const char* name[4] = { "K1", "head", "K3", "tail" };
+    fprintf(stderr, "[safconv timeline] call regime host(in..out) |");
+    for (int i = 0; i < 4; i++) fprintf(stderr, " %s(start..end)", name[i]);
+    fprintf(stderr, "   (us; device times relative to the first K1, host times to the first call)\n");
+    for (int n = 0; n < h->tlN; n++) {
+        fprintf(stderr, "[safconv timeline] %3d %c %8.1f..%-8.1f |", n, h->tlReg[n], (h->tlHost[2 * n] - h->tlHost[0]) * 1e-3,
+                (h->tlHost[2 * n + 1] - h->tlHost[0]) * 1e-3);
+        for (int i = 0; i < 4; i++) {
+            float a = 0.f, b = 0.f;
+            const int ea = scdev_event_elapsed_ms(h->tlEv[0], h->tlEv[8 * n + 2 * i], &a);
+            const int eb = scdev_event_elapsed_ms(h->tlEv[0], h->tlEv[8 * n + 2 * i + 1], &b);
+            if (ea || eb) { (void)scdev_last_error_clear(); fprintf(stderr, "        -        "); }
+            else fprintf(stderr, " %8.1f..%-8.1f", 1e3f * a, 1e3f * b);
+        }
+        fprintf(stderr, "\n");
+    }
 }
 
 /* One block through the look-ahead sequence described by `io`; with io->sync the output is complete on return,
  * otherwise evDone is recorded behind it. */
 int sch_apply_lookahead_io(safconv_handle* h, const sch_la_io* io)
 {
+    const scdev_plan* pl = &h->pl;
     const unsigned int c = h->count;
-    const int hadTail = h->tailReady;
+    const int D = h->laDepth;
+    const int hadTail = h->tailReady;                         /* tail passes of blocks c .. tailUpTo are enqueued */
+    const unsigned int upTo = hadTail ? h->tailUpTo : c;      /* (c itself only counts with hadTail) */
     const int tr = h->trace && hadTail;
-    /* is the caller coming back faster than the GPU streams the filters? */
-    const int backToBack = hadTail && scdev_event_done(h->evTail) == 0;
+    const int tl = h->tlEv && h->tlN < h->tlCap;
+    if (tl) h->tlHost[2 * h->tlN] = now_ns();
+    /* is a tail pass still running, i.e. is the caller coming back faster than the GPU streams the filters? */
+    int backToBack = 0;
+    if (hadTail) {
+        backToBack = scdev_event_done(h->evTailB[c & 1u]) == 0;
+        if (!backToBack && upTo > c) backToBack = scdev_event_done(h->evTailB[(c + 1u) & 1u]) == 0;
+    }
     int e = la_input(h, io);
     h->tailReady = 0;
+    h->trRegime = backToBack;
     if (backToBack) LA_TRY(la_throughput(h, c, io, tr));
     else            LA_TRY(la_latency(h, c, hadTail, io, tr));
-    LA_TRY(scdev_event_record(h->evTail, h->stream));
-    if (!e) { h->tailReady = 1; h->count = c + 1; if (io->sync) e = scdev_event_sync(h->evDone); }
+    /* the tail passes that are not queued yet, up to block c + D.  `stream` is ordered behind K1 of this block (la_input)
+     * and, in the latency regime, behind K3.  The pass of block c + 2 re-uses the partial-tile buffer K3 of this block
+     * reads: it waits for K3 (which ends long before the pass of block c + 1, queued in front of it, does). */
+    for (unsigned int b = (hadTail ? upTo : c) + 1u; !e && b <= c + (unsigned)D; ++b) {
+        if (b == c + 2u) LA_TRY(scdev_stream_wait_event(h->stream, h->evDone));
+        LA_TL(6, h->stream);
+        LA_TRY(scdev_mac_pass(pl, &h->b, &h->tailPass, 0, 1, (int)(b & 1u), (long long)b, h->stream));
+        LA_TL(7, h->stream);
+        LA_TRY(scdev_event_record(h->evTailB[b & 1u], h->stream));
+    }
+    if (!e) { h->tailReady = 1; h->tailUpTo = c + (unsigned)D; h->count = c + 1; if (io->sync) e = scdev_event_sync(h->evDone); }
     if (!e && io->sync) la_trace_report(h, c, tr);
     if (e) h->tailReady = 0;
+    if (tl) {
+        h->tlHost[2 * h->tlN + 1] = now_ns();
+        h->tlReg[h->tlN] = backToBack ? 'T' : (hadTail ? 'L' : 'C');
+        if (++h->tlN == h->tlCap) la_timeline_print(h);
+    }
     return e;
 }
 
-/* host-pointer form: `src` / `dst` are page-locked host buffers */
 static int apply_lookahead(safconv_handle* h, const float* src, float* dst)
 {
     /* blocks of up to 1 MB are read / written by K1 / K3 straight from / to the page-locked host buffers */
@@ -723,13 +795,6 @@ static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int 
 /* host-pointer apply (reference semantics: synchronous).  Caller buffers that are already page-locked
  * (cudaHostAlloc / cudaHostRegister) are used directly; ordinary malloc'd buffers go through the handle's pinned
  * staging buffers. */
-static inline double now_ns(void)
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (double)ts.tv_sec * 1e9 + (double)ts.tv_nsec;
-}
-
 static void conv_apply_host(safconv_handle* h, const float* in, float* out, int irIdx)
 {
     const double t0 = h->hostTrace ? now_ns() : 0.0;

@@ -57,7 +57,15 @@ typedef struct safconv_handle {
     void       *evIn, *evFence;      /* streamIn -> stream, stream -> streamIn */
     void*      streamOut;            /* high-priority side stream: K3 (+ D2H) of block t runs beside the tail pass of block t+1 */
     void*      evMac;                /* stream -> streamOut: the partial tiles of the current block are complete */
-    void*      evTail;               /* end of the most recent tail pass */
+    void*      evTail;               /* (unused since the two-deep look-ahead) */
+    void*      evTailB[2];           /* end of the tail pass of block b, indexed by b & 1 */
+    int        tlCap, tlN;           /* SAFCONV_TIMELINE=n: device timeline of the first n look-ahead calls (8 events each), printed once */
+    void**     tlEv;                 /* [tlCap][8]: K1 start/end, head start/end, K3 start/end, tail pass start/end */
+    double*    tlHost;               /* [tlCap][2]: host time at entry / return (ns) */
+    char*      tlReg;
+    int        trRegime;             /* trace: regime of the current call */
+    int        laDepth;              /* look-ahead depth D: tail passes cover partitions p >= D and are queued D blocks ahead */
+    unsigned int tailUpTo;           /* with tailReady: tail passes of blocks count .. tailUpTo are enqueued */
     unsigned int count;              /* host mirror of the device block counter (counters[0]) */
     int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
     int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */

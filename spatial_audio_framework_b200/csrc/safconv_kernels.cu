@@ -339,6 +339,7 @@ struct IfftArgs {
     const int* grpStart2;
     const float2* headH;   /* != NULL: K3 adds the newest partition itself, sum_ni H_0[no][ni][k] * X_t[ni][k], straight from */
     const float2* headX;   /*          the filter / delay-line arrays (look-ahead latency path: no separate head pass)      */
+    int nHead;             /* partitions K3 adds itself: p = 0 .. nHead-1 (the look-ahead depth) */
     int P, nIn, RS;
     const float2* tw;
     float* out;            /* [B][nOutLocal][hop] */
@@ -368,45 +369,87 @@ __device__ __forceinline__ void gather_and_ifft(const IfftArgs& a, const float2*
     const bool wide = fft_use_wide(a.M, 1);
     load_twiddles(stw, a.tw, a.M, a.logM, wide);
     const float2* spl = load_split_twiddles(stw, a.tw, a.M);
-    for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
-        const int g = ot * a.nKT + (k >> 5);
-        const int q0 = __ldg(a.grpStart + g), q1 = __ldg(a.grpStart + g + 1);
-        const float2* src = Zp + ((size_t)q0 * a.OTsz + nl) * SC_BK + (k & 31);
-        const size_t qs = (size_t)a.OTsz * SC_BK;
-        float2 z = make_float2(0.f, 0.f);
-        int q = q0;
-        /* fixed summation order (ascending slot), four independent loads in flight */
-        for (; q + 4 <= q1; q += 4, src += 4 * qs) {
-            const float2 v0 = src[0], v1 = src[qs], v2 = src[2 * qs], v3 = src[3 * qs];
-            z = caddf(caddf(caddf(caddf(z, v0), v1), v2), v3);
+    /* Four bins of a thread at a time, in three rounds of independent loads: the slot ranges of the four groups, then up to
+     * GQ partial tiles per bin and list, then whatever is left.  Beside a tail pass that saturates HBM (look-ahead,
+     * throughput regime) a DRAM round trip takes 2-3 us: the first version walked the bins one after the other, ~5
+     * dependent round trips each, and K3 took 50 us there instead of 15 us alone.  Summation order per bin is unchanged:
+     * ascending slot of list 1, then ascending slot of list 2, then the newest partition. */
+    constexpr int GK = 4, GQ = 6;
+    const size_t qs = (size_t)a.OTsz * SC_BK;
+    for (int kb = threadIdx.x; kb < a.M; kb += GK * blockDim.x) {
+        int q0[GK], q1[GK], r0[GK], r1[GK];
+#pragma unroll
+        for (int j = 0; j < GK; ++j) {
+            const int k = kb + j * blockDim.x;
+            q0[j] = q1[j] = r0[j] = r1[j] = 0;
+            if (k < a.M) {
+                const int g = ot * a.nKT + (k >> 5);
+                q0[j] = __ldg(a.grpStart + g); q1[j] = __ldg(a.grpStart + g + 1);
+                if (a.Zp2) { r0[j] = __ldg(a.grpStart2 + g); r1[j] = __ldg(a.grpStart2 + g + 1); }
+            }
         }
-        for (; q < q1; ++q, src += qs) z = caddf(z, src[0]);
-        if (a.Zp2) {
-            const int r0 = __ldg(a.grpStart2 + g), r1 = __ldg(a.grpStart2 + g + 1);
-            const float2* s2 = a.Zp2 + ((size_t)r0 * a.OTsz + nl) * SC_BK + (k & 31);
-            for (int r = r0; r < r1; ++r, s2 += qs) z = caddf(z, s2[0]);
+        float2 zz[GK];
+        /* one list after the other through the same registers (K3 must stay small enough to share an SM with a MAC CTA) */
+#pragma unroll 1
+        for (int list = 0; list < 2; ++list) {
+            const float2* base = list ? a.Zp2 : Zp;
+            if (!base) break;
+            float2 v[GK][GQ];
+#pragma unroll
+            for (int j = 0; j < GK; ++j) {
+                const int k = kb + j * blockDim.x;
+                const int b0 = list ? r0[j] : q0[j], b1 = list ? r1[j] : q1[j];
+                const float2* src = base + ((size_t)b0 * a.OTsz + nl) * SC_BK + (k & 31);
+#pragma unroll
+                for (int u = 0; u < GQ; ++u) v[j][u] = (b0 + u < b1) ? src[(size_t)u * qs] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < GK; ++j) {
+                const int k = kb + j * blockDim.x;
+                const int b0 = list ? r0[j] : q0[j], b1 = list ? r1[j] : q1[j];
+                float2 z = list ? zz[j] : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < GQ; ++u) if (b0 + u < b1) z = caddf(z, v[j][u]);
+                const float2* src = base + ((size_t)(b0 + GQ) * a.OTsz + nl) * SC_BK + (k & 31);
+                for (int q = b0 + GQ; q < b1; ++q, src += qs) z = caddf(z, src[0]);
+                zz[j] = z;
+            }
         }
-        if (a.headH) {
-            /* partition 0 of group (ot, kt): rows [ni][OTsz][32] of H, row ni of the newest delay-line slot */
-            const int head = (int)(a.counters[0] % (unsigned)a.RS);
+#pragma unroll
+        for (int j = 0; j < GK; ++j) {
+            const int k = kb + j * blockDim.x;
+            if (k < a.M) sm[padi(k, a.logM)] = zz[j];
+        }
+    }
+    if (a.headH) {
+        /* look-ahead latency path: the newest partition is added here (no separate head pass).  Partition 0 of group
+         * (ot, kt): rows [ni][OTsz][32] of H, row ni of the newest delay-line slot */
+        const int head = (int)(a.counters[0] % (unsigned)a.RS);
+        for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+            const int g = ot * a.nKT + (k >> 5);
             const float2* __restrict__ Hk = a.headH + ((size_t)g * a.P * a.nIn * a.OTsz + nl) * SC_BK + (k & 31);
             const float2* __restrict__ Xk = a.headX + ((size_t)(k >> 5) * a.RS + head) * a.nIn * SC_BK + (k & 31);
             const bool packed = (k == 0);
             float2 acc = make_float2(0.f, 0.f);
+            for (int p = 0; p < a.nHead; ++p) {                 /* partition p: rows p * nIn .. of the unit, ring slot head - p */
+                int slot = head - p; if (slot < 0) slot += a.RS;
+                const float2* __restrict__ Hp = Hk + (size_t)p * a.nIn * qs;
+                const float2* __restrict__ Xp = Xk + ((ptrdiff_t)slot - head) * a.nIn * SC_BK;
 #pragma unroll 16
-            for (int ni = 0; ni < a.nIn; ++ni)
-                cmac_packed(acc, __ldg(Hk + (size_t)ni * qs), __ldg(Xk + (size_t)ni * SC_BK), packed);
-            z = caddf(z, acc);
+                for (int ni = 0; ni < a.nIn; ++ni)
+                    cmac_packed(acc, __ldg(Hp + (size_t)ni * qs), __ldg(Xp + (size_t)ni * SC_BK), packed);
+            }
+            sm[padi(k, a.logM)] = caddf(sm[padi(k, a.logM)], acc);      /* same thread wrote it above */
         }
-        sm[padi(k, a.logM)] = z;
     }
     __syncthreads();
     inv_split_all(sm, a.M, a.logM, spl);
     cfft_dif<true>(sm, a.M, a.logM, stw, wide);
 }
 
-/* one block: grid (nOutLocal) */
-__global__ void ifft_ola_kernel(IfftArgs a)
+/* one block: grid (nOutLocal); 256 threads (512 when it adds the newest partition itself), <= 128 registers so that a
+ * 256-thread CTA fits beside a MAC CTA */
+__global__ void __launch_bounds__(512, 1) ifft_ola_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x;
@@ -416,7 +459,7 @@ __global__ void ifft_ola_kernel(IfftArgs a)
 }
 
 /* batch of B blocks, step 1: grid (nOutLocal, B) -> zt[b][no][0..2*hop) = z/N */
-__global__ void ifft_batch_kernel(IfftArgs a)
+__global__ void __launch_bounds__(512, 1) ifft_batch_kernel(IfftArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int no = blockIdx.x, b = blockIdx.y;
@@ -1578,6 +1621,7 @@ int scdev_event_done(void* e)
 int scdev_event_destroy(void* e) { return e ? (int)cudaEventDestroy((cudaEvent_t)e) : 0; }
 int scdev_event_record(void* e, void* stream) { return (int)cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream); }
 int scdev_event_sync(void* e) { return (int)cudaEventSynchronize((cudaEvent_t)e); }
+int scdev_last_error_clear(void) { return (int)cudaGetLastError(); }
 int scdev_event_elapsed_ms(void* e0, void* e1, float* ms) { return (int)cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1); }
 int scdev_graph_begin(void* stream) { return (int)cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal); }
 int scdev_graph_end(void* stream, void** graphExec)
@@ -1715,7 +1759,7 @@ int scdev_mac_pass(const scdev_plan* pl, const scdev_bufs* b, const scdev_macpas
 static void fill_ifft_args(IfftArgs& a, const scdev_plan* pl, const scdev_bufs* b, float* d_out, int nBlocks)
 {
     a.Zp = (const float2*)b->Zp; a.grpStart = b->grpStart; a.Zp2 = NULL; a.grpStart2 = NULL;
-    a.headH = NULL; a.headX = NULL; a.P = pl->P; a.nIn = pl->nIn; a.RS = pl->RS;
+    a.headH = NULL; a.headX = NULL; a.nHead = 0; a.P = pl->P; a.nIn = pl->nIn; a.RS = pl->RS;
     a.tw = (const float2*)b->tw; a.out = d_out; a.tail = b->tail; a.zt = b->zt; a.counters = b->counters;
     a.zpStride = (size_t)pl->nSlots * pl->OTsz * SC_BK;
     a.hop = pl->hop; a.M = pl->M; a.logM = pl->logM; a.nKT = pl->nKT; a.OTsz = pl->OTsz;
@@ -1735,8 +1779,8 @@ int scdev_ifft_ola_passes(const scdev_plan* pl, const scdev_bufs* b, const scdev
     fill_ifft_args(a, pl, b, d_out, 1);
     if (p1) { a.Zp = (const float2*)(zpSel1 ? p1->ZpB : p1->Zp); a.grpStart = p1->grpStart; }
     if (p2) { a.Zp2 = (const float2*)p2->Zp; a.grpStart2 = p2->grpStart; }
-    if (p1 && !p2 && p1->pLo == 1) {                 /* tail pass only: K3 adds partition 0 itself, with twice the threads in flight */
-        a.headH = (const float2*)b->H; a.headX = (const float2*)b->X;
+    if (p1 && !p2 && p1->pLo >= 1) {                 /* tail pass only: K3 adds the newest partition(s) itself, with twice the threads in flight */
+        a.headH = (const float2*)b->H; a.headX = (const float2*)b->X; a.nHead = p1->pLo;
         int threads = 2 * pl->fftThreads; if (threads > 512) threads = 512;
         ifft_ola_kernel<<<pl->nOutLocal, threads, fft_smem(pl, 2), (cudaStream_t)stream>>>(a);
         return (int)cudaGetLastError();
