@@ -308,6 +308,17 @@ static int make_pass(safconv_handle* h, scdev_macpass* ps, int pLo, int nP)
     ps->pLo = pLo; ps->nP = nP;
     ps->totalStages = (long long)pl->nGroups * nP * pl->SPU;
     ps->grid = (ps->totalStages < h->smCount) ? (int)ps->totalStages : h->smCount;
+    if (pLo >= 1) {
+        /* A tail pass runs while the caller comes back with the next block, whose K1 -> head pass -> K3 chain is the
+         * latency of the call.  On an SM shared with a MAC CTA those kernels run 3-5x slower (issue slots, not HBM: the
+         * device timeline, SAFCONV_TIMELINE, shows K3 16 us alone and 60-70 us beside a tail pass), and the tail pass is
+         * HBM-bound long before it needs every SM -- so it leaves 32 SMs free (SAFCONV_TAIL_RESERVE_SMS).  Measured on
+         * one GPU's share of configs[3] at 8 GPUs (64 x 8, 59 us of filter stream per block): back-to-back p50 85 -> 63 us;
+         * configs[3] on one GPU: p50 0.459 -> 0.449 ms, p99 0.88 -> 0.48 ms. */
+        int reserve = env_int("SAFCONV_TAIL_RESERVE_SMS", 32, 0, 64);
+        if (reserve > h->smCount / 2) reserve = h->smCount / 2;
+        if (reserve && ps->grid > h->smCount - reserve) ps->grid = h->smCount - reserve;
+    }
     int *ctaBase = NULL, *grpStart = NULL, *grpList = NULL;
     const int slots = build_split_tables_for(ps->totalStages, (long long)nP * pl->SPU, ps->grid, pl->nGroups,
                                              &ctaBase, &grpStart, &grpList);
