@@ -1244,16 +1244,18 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
     }
 }
 
-/* the cluster version: M = 64 .. 1024, at most 16 inputs / outputs per CTA of the cluster */
-static int small_cluster_ok(const scdev_plan* pl, const scdev_bufs* b)
+/* the cluster version: M = 64 .. 1024, at most 16 inputs / outputs per CTA of the cluster, filters that stay in L2 */
+static int small_cluster_plan_ok(const scdev_plan* pl)
 {
     static int env = -1;
     if (env < 0) { const char* v = getenv("SAFCONV_SMALL_CLUSTER"); env = v ? atoi(v) : 1; }
-    if (!env || !b->wtab || pl->kind != SC_KIND_MATRIX) return 0;
+    if (!env || pl->kind != SC_KIND_MATRIX) return 0;
     if (pl->M < 64 || pl->M > 1024 || pl->hop > pl->M) return 0;
     if (pl->nIn > SC_CL_MAXC * SC_CL_WARPS || pl->nOutLocal > SC_CL_MAXC * SC_CL_WARPS) return 0;
+    if ((double)pl->P * pl->nIn * pl->nOutLocal * pl->M * 8.0 > 4.0 * 1024 * 1024) return 0;     /* one cluster = 8 SMs: more than this belongs on the whole GPU */
     return 1;
 }
+static int small_cluster_ok(const scdev_plan* pl, const scdev_bufs* b) { return b->wtab && small_cluster_plan_ok(pl); }
 
 template <int R>
 static int small_cluster_launch(const SmallCArgs& a, int C, cudaStream_t st)
@@ -1917,6 +1919,7 @@ static size_t small_smem(const scdev_plan* pl, int threads)
 int scdev_small_fits(const scdev_plan* pl, int maxSmemOptin)
 {
     if (pl->kind != SC_KIND_MATRIX) return 0;
+    if (small_cluster_plan_ok(pl)) return 1;
     if (small_smem(pl, SC_SMALL_THREADS) > (size_t)maxSmemOptin || small_smem(pl, SC_SMALL_THREADS) > 160 * 1024) return 0;
     if (pl->hop > 4 * SC_SMALL_THREADS) return 0;
     if ((long long)pl->nOutLocal * pl->nIn > 256) return 0;                       /* redundant forward FFTs stay cheap */

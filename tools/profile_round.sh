@@ -16,7 +16,7 @@ ncu --set full --clock-control none --import-source on -k regex:offline_ -s 6 -c
 for W in C2 C3; do
   CMDW="python bench.py --workload $W --steps 2 --warmup 3 $FAST"
   $CMDW > gpurun_out/plain_$W.log 2>&1 || continue
-  ncu --set full --clock-control none --import-source on -k regex:'small_fused|multi_' -s 8 -c 6 -f -o gpurun_out/${R}_${W}_full $CMDW > gpurun_out/ncu_f_$W.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'small_|multi_' -s 8 -c 6 -f -o gpurun_out/${R}_${W}_full $CMDW > gpurun_out/ncu_f_$W.log 2>&1
 done
 for f in gpurun_out/${R}_*_full.ncu-rep; do
   ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2>/dev/null
