@@ -147,6 +147,21 @@ def host_api_latency(conv, kind, x_host, y_host, nbuf, in_elems, out_elems, hop,
         lat = lat[20:]
         out["paced"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "period_ms": 1e3 * period, "calls": paced_calls,
                         "note": "real-time block period hop/48000 s, capped at 5 ms (the GPU is idle long before)"}
+    if kind == "matrix" and hop <= 1024:
+        # opt-in resident latency kernel (no launch per call: the host rings a doorbell in page-locked memory); only small
+        # matrix problems have one -- for anything else the option changes nothing
+        conv.set_option("resident_us", 20000)
+        call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), warm, in_elems * 4, out_elems * 4, nbuf)
+        lat, dt = call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), blocks, in_elems * 4, out_elems * 4, nbuf)
+        out["resident"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99), "blocks_per_s": blocks / dt, "idle_timeout_us": 20000,
+                           "note": "safconv_set_option(h, \"resident_us\", 20000): same synchronous saf_matrixConv_apply, page-locked buffers"}
+        if paced_calls:
+            period = min(hop / 48000.0, 0.005)
+            lat, _ = call_loop(fn, hdl, x_host.data_ptr(), y_host.data_ptr(), paced_calls + 20, in_elems * 4, out_elems * 4, nbuf, period)
+            lat = lat[20:]
+            out["resident"]["paced_p50_ms"] = pct(lat, 50)
+            out["resident"]["paced_p99_ms"] = pct(lat, 99)
+        conv.set_option("resident_us", 0)
     return out
 
 

@@ -317,9 +317,23 @@ int safconv_get_kernel_times(void* h, float ms[3], int* nBlocksAveraged);
  *                   zero-copy host paths (multiConv single launch, single-partition matrix convolvers)
  *    "detect_pinned" 0/1 (default 1) saf_*_apply copies straight from/to caller buffers that are already
  *                   page-locked instead of going through the handle's own pinned staging buffers
+ *    "flag_wait"    0/1 (default 1) the one-launch latency kernel writes the call's sequence number into a page-locked word
+ *                   behind its last output store and saf_matrixConv_apply polls that word instead of synchronising the
+ *                   stream (falls back to the stream after 2 ms, which also reports errors)
+ *    "resident_us"  N > 0: RESIDENT latency kernel for small matrix problems (the ones "small_fused" serves with the
+ *                   thread-block-cluster kernel: FFT size 128 .. 2048).  The kernel stays on 8 SMs and serves one block per
+ *                   doorbell -- saf_matrixConv_apply writes the buffer addresses + a sequence number into a page-locked
+ *                   mailbox and polls the completion word: no kernel launch per call (configs[1]: p50 20 -> 15 us).  It
+ *                   leaves by itself after N microseconds without a call (the next call starts it again), and every other
+ *                   call on the handle (device-pointer apply, reset, options, destroy) stops it first.  While it polls,
+ *                   the handle's stream is busy: cudaDeviceSynchronize() in the host blocks for up to N us.  Default 0 (off);
+ *                   SAFCONV_RESIDENT_US sets the default.  Results are bit-identical to the one-launch kernel.
  * Environment variables read at create / first use (benchmark and debugging knobs, all optional):
  *    SAFCONV_LOOKAHEAD, SAFCONV_SMALL_FUSED, SAFCONV_MAC_HINTS, SAFCONV_MAC_STAGES, SAFCONV_MAC_STAGE_KB, SAFCONV_MAX_BATCH,
- *    SAFCONV_MULTI_WFFT, SAFCONV_TRACE (device timeline of the look-ahead apply on stderr);
+ *    SAFCONV_MULTI_WFFT, SAFCONV_TRACE / SAFCONV_TIMELINE=n (device timeline of the look-ahead apply on stderr),
+ *    SAFCONV_LA_DEPTH (1 | 2: tail passes queued ahead), SAFCONV_HEAD_IN_K3, SAFCONV_TAIL_RESERVE_SMS (default 32: SMs a
+ *    tail pass leaves to the kernels of the caller's critical path), SAFCONV_SMALL_CLUSTER, SAFCONV_FLAG_WAIT,
+ *    SAFCONV_HOSTTRACE, SAFCONV_KSTAMPS (host / in-kernel phase times of the latency kernel);
  *    offline path: SAFCONV_OFF_KIND (f16 | tf32), SAFCONV_OFF_NT, SAFCONV_OFF_WFFT, SAFCONV_OFF_FLUSH, SAFCONV_OFF_PIPELINE,
  *    SAFCONV_OFF_FPC, SAFCONV_OFF_OPC, SAFCONV_OFF_THREADS.
  */

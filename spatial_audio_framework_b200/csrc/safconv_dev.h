@@ -195,6 +195,9 @@ int  scdev_wfft_tables(const scdev_plan* pl, scdev_bufs* b, void* stream);
 int  scdev_is_pinned_host(const void* p);
 /* small matrix problems: K1+K2+K3 in one launch, one CTA per output channel; in/out may be mapped host memory */
 int  scdev_small_fits(const scdev_plan* pl, int maxSmemOptin);
+int  scdev_small_resident_start(const scdev_plan* pl, const scdev_bufs* b, void* mailbox, unsigned int lastSeq, unsigned int idleUs,
+                                void* stream);
+int  scdev_small_resident_stamps(unsigned long long out[8]);
 int  scdev_small_fused(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, void* stream,
                        volatile unsigned int* done, unsigned int seq, int* signalled);
 /* multiConv, nBlocks device-resident blocks d_in [nBlocks][nCH][hop] -> d_out [nBlocks][nCH][hop]:

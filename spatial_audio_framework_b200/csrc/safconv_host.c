@@ -54,6 +54,14 @@ static safconv_handle* as_handle(void* p)
     return (h && h->magic == SAFCONV_MAGIC) ? h : NULL;
 }
 safconv_handle* sch_as_handle(void* p) { return as_handle(p); }
+static void res_stop(safconv_handle* h);
+/* for every entry point except the host-pointer apply: a resident latency kernel owns the stream, stop it first */
+static safconv_handle* as_handle_q(void* p)
+{
+    safconv_handle* h = as_handle(p);
+    if (h) res_stop(h);
+    return h;
+}
 int sch_thread_device(void) { return tl_device; }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -253,6 +261,7 @@ static void handle_free(safconv_handle* h)
         fprintf(stderr, "safconv host trace: %u zero-copy applies, us per call: checks %.2f, launch %.2f, wait %.2f\n", h->htN,
                 h->htAcc[0] / h->htN * 1e-3, h->htAcc[1] / h->htN * 1e-3, h->htAcc[2] / h->htN * 1e-3);
     if (h->device >= 0) scdev_set_device(h->device);
+    if (h->resActive && h->mailbox) { h->mailbox->bell = (unsigned long long)SC_RES_EXIT; __atomic_thread_fence(__ATOMIC_SEQ_CST); }   /* resident kernel: leave */
     if (h->stream) scdev_stream_sync(h->stream);
     scdev_graph_destroy(h->graphExec);
     if (h->evRing) { for (int i = 0; i < 4 * h->timingCap; i++) scdev_event_destroy(h->evRing[i]); free(h->evRing); }
@@ -277,7 +286,7 @@ static void handle_free(safconv_handle* h)
     scdev_free(h->tailPass.ZpB);
     for (int i = 0; i < 6; i++) scdev_event_destroy(h->trEv[i]);
     scdev_free(h->d_in); scdev_free(h->d_out);
-    scdev_host_free(h->h_in); scdev_host_free(h->h_out); scdev_host_free((void*)h->doneWord);
+    scdev_host_free(h->h_in); scdev_host_free(h->h_out); scdev_host_free((void*)h->mailbox);
     scdev_stream_destroy(h->streamOwn);
     h->magic = 0;
     free(h);
@@ -377,6 +386,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     h->smallFused = env_int("SAFCONV_SMALL_FUSED", 1, 0, 1);
     h->hostTrace = env_int("SAFCONV_HOSTTRACE", 0, 0, 1);
     h->flagWait = env_int("SAFCONV_FLAG_WAIT", 1, 0, 1);
+    h->residentUs = env_int("SAFCONV_RESIDENT_US", 0, 0, 2000000);
 
     const size_t M = (size_t)pl->M, P = (size_t)pl->P;
     /* twiddles W_N^j, j < M, evaluated in double like the reference's KissFFT tables (kiss_fft.c:358-364) */
@@ -484,8 +494,9 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     DEV_TRY(h, scdev_host_alloc((void**)&h->h_in, h->inBytes), "pinned input staging");
     DEV_TRY(h, scdev_host_alloc((void**)&h->h_out, h->outBytes), "pinned output staging");
     if (h->smallOk) {
-        DEV_TRY(h, scdev_host_alloc((void**)&h->doneWord, 64), "completion word");
-        *h->doneWord = 0;
+        DEV_TRY(h, scdev_host_alloc((void**)&h->mailbox, sizeof(sc_mailbox)), "completion word / mailbox");
+        memset((void*)h->mailbox, 0, sizeof(sc_mailbox));
+        h->doneWord = &h->mailbox->done;
     }
 
     /* K0: upload the time-domain filters once and transform them on the device (reference .c:116-125) */
@@ -778,15 +789,101 @@ int sch_uses_lookahead(const safconv_handle* h)
     return h->lookahead && h->pl.kind == SC_KIND_MATRIX && !h->useGraph && !h->timingCap && !(h->smallFused && h->smallOk);
 }
 
+/* ---- resident latency kernel (option "resident_us") ----------------------------------------------
+ * While it is active the handle's stream is busy with it: every other entry point stops it first (res_stop). */
+static void res_stop(safconv_handle* h)
+{
+    if (!h || !h->resActive) return;
+    if (env_int("SAFCONV_KSTAMPS", 0, 0, 1)) {                     /* debugging: phases of the last block served */
+        unsigned long long t[8];
+        if (scdev_small_resident_stamps(t) == 0)
+            fprintf(stderr, "resident kernel, last block (us): doorbell -> start %.2f, A %.2f, barrier %.2f, B %.2f, barrier %.2f, C %.2f\n",
+                    (double)(long long)(t[0] - t[6]) * 1e-3, (double)(long long)(t[1] - t[0]) * 1e-3, (double)(long long)(t[2] - t[1]) * 1e-3,
+                    (double)(long long)(t[3] - t[2]) * 1e-3, (double)(long long)(t[4] - t[3]) * 1e-3, (double)(long long)(t[5] - t[4]) * 1e-3);
+    }
+    h->mailbox->bell = (unsigned long long)SC_RES_EXIT;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    scdev_stream_sync(h->stream);
+    h->mailbox->bell = (unsigned long long)h->doneSeq;
+    h->mailbox->alive = 0;
+    h->resActive = 0;
+}
+
+/* ring the doorbell for block (src -> dst); starts the kernel if none is polling.  Returns a CUDA error code. */
+static int res_post(safconv_handle* h, const float* src, float* dst)
+{
+    sc_mailbox* mb = h->mailbox;
+    int e = 0;
+    if (h->resActive && !mb->alive) { e = scdev_stream_sync(h->stream); h->resActive = 0; }     /* it left on its idle timer */
+    if (!e && !h->resActive) {
+        mb->bell = (unsigned long long)h->doneSeq; mb->alive = 1;
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        e = scdev_small_resident_start(&h->pl, &h->b, (void*)mb, h->doneSeq, (unsigned)h->residentUs, h->stream);
+        if (e) { mb->alive = 0; return e; }
+        h->resActive = 1;
+    }
+    /* the block's buffers: a slot of the mailbox's table (callers re-use a handful of buffers; a new pair replaces a slot
+     * and bumps the generation, which makes the kernel re-read the table once) */
+    int slot = -1;
+    for (int i = 0; i < 8; i++)
+        if (mb->buf[2 * i] == (unsigned long long)(uintptr_t)src && mb->buf[2 * i + 1] == (unsigned long long)(uintptr_t)dst && src) { slot = i; break; }
+    if (slot < 0) {
+        slot = (int)(h->resNext++ & 7u);
+        mb->buf[2 * slot] = (unsigned long long)(uintptr_t)src; mb->buf[2 * slot + 1] = (unsigned long long)(uintptr_t)dst;
+        h->resGen = (h->resGen + 1u) & 0xFFFFFFu;
+    }
+    ++h->doneSeq;
+    if (h->doneSeq == SC_RES_EXIT) h->doneSeq = 1;
+    __atomic_thread_fence(__ATOMIC_RELEASE);                   /* table and input block before the doorbell */
+    mb->bell = ((unsigned long long)((h->resGen << 8) | (unsigned)slot) << 32) | (unsigned long long)h->doneSeq;
+    return e;
+}
+
+/* wait for the completion word of the block posted last; the kernel may have left on its idle timer in the same instant:
+ * then it is started again (it sees the pending doorbell at once) */
+static int res_wait(safconv_handle* h)
+{
+    sc_mailbox* mb = h->mailbox;
+    const unsigned int want = h->doneSeq;
+    const double tEnd = now_ns() + 2.0e9;
+    unsigned int spins = 0;
+    while (mb->done != want) {
+        __builtin_ia32_pause();
+        if ((++spins & 255u) == 0) {
+            if (!mb->alive) {
+                int e = scdev_stream_sync(h->stream);
+                h->resActive = 0;
+                if (e) return e;
+                if (mb->done == want) break;
+                mb->alive = 1;
+                __atomic_thread_fence(__ATOMIC_SEQ_CST);
+                e = scdev_small_resident_start(&h->pl, &h->b, (void*)mb, want - 1u, (unsigned)h->residentUs, h->stream);     /* it sees the pending doorbell at once */
+                if (e) { mb->alive = 0; return e; }
+                h->resActive = 1;
+            }
+            if (now_ns() > tEnd) { res_stop(h); return 702 /* cudaErrorLaunchTimeout */; }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return 0;
+}
+
 /* Blocks of up to 1 MB without look-ahead: the kernels read / write the page-locked host buffers directly -- no
  * copy-engine round trips, one synchronisation.  Returns -1 if the handle has no such path. */
 static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int irIdx, int* signalled)
 {
     const scdev_plan* pl = &h->pl;
     *signalled = 0;
+    const int small = h->smallFused && !h->useGraph && !h->timingCap && pl->kind == SC_KIND_MATRIX && h->smallOk;
+    if (!(small && h->residentUs > 0)) res_stop(h);
     if (!h->smallFused || h->useGraph || h->timingCap) return -1;
-    if (pl->kind == SC_KIND_MATRIX && h->smallOk)                 /* small problem: K1 + K2 + K3 in ONE launch */
+    if (small) {                                                  /* small problem: K1 + K2 + K3 in ONE launch */
+        if (h->residentUs > 0 && h->mailbox && h->b.wtab) {       /* ... or no launch at all: the resident kernel's doorbell */
+            const int e = res_post(h, src, dst);
+            if (e != 801 /* cudaErrorNotSupported: not a cluster-kernel plan */) { *signalled = 2; return e; }
+        }
         return scdev_small_fused(pl, &h->b, src, dst, h->stream, (h->flagWait && h->doneWord) ? h->doneWord : NULL, ++h->doneSeq, signalled);
+    }
     if (h->inBytes > (1u << 20) || h->outBytes > (1u << 20)) return -1;
     if (pl->kind == SC_KIND_MULTI)                                /* one fused launch, one CTA per channel */
         return scdev_multi_fused(pl, &h->b, src, dst, h->stream);
@@ -833,7 +930,8 @@ void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx
     e = apply_zero_copy(h, src, dst, irIdx, &signalled);
     if (e >= 0) {
         const double t2 = h->hostTrace ? now_ns() : 0.0;
-        if (!e && signalled) {
+        if (!e && signalled == 2) e = res_wait(h);
+        else if (!e && signalled) {
             /* the kernel writes the call's sequence number behind its last output store (system-scope fences): poll that
              * word; after 2 ms without it (device busy elsewhere, or a fault) fall back to the stream, which also reports errors */
             const unsigned int want = h->doneSeq;
@@ -1044,7 +1142,7 @@ int safconv_apply_device(void* hp, const float* d_in, float* d_out)
 
 int safconv_apply_device_blocks(void* hp, const float* d_in, float* d_out, int nBlocks)
 {
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h || !d_in || !d_out || nBlocks < 1 || h->pl.kind == SC_KIND_TV) return SAFCONV_ERR_ARG;
     h_clear(h);
     int e = scdev_set_device(h->device);
@@ -1170,7 +1268,7 @@ __attribute__((weak)) void fftfilt(float* x, float* h, int x_len, int h_len, int
 /* ---- offline rendering: all frames at once, tensor-core per-bin contraction (safconv_offline.cu) ---- */
 int safconv_render_offline_segment_device(void* hp, const float* d_in, float* d_out, int nFrames, int nHaloFrames)
 {
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h || !d_in || !d_out || nFrames < 1 || nHaloFrames < 0 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
     const int T = nFrames + nHaloFrames;
     int e = scdev_set_device(h->device);
@@ -1201,7 +1299,7 @@ int safconv_render_offline(void* hp, const float* in, float* out, int nFrames)
 /* in [nIn][(nHaloFrames + nFrames) * hop] (the first nHaloFrames frames are history only), out [nOutLocal][nFrames * hop] */
 int safconv_render_offline_segment(void* hp, const float* in, float* out, int nFrames, int nHaloFrames)
 {
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h || !in || !out || nFrames < 1 || nHaloFrames < 0 || h->pl.kind != SC_KIND_MATRIX) return SAFCONV_ERR_ARG;
     int e = scdev_set_device(h->device);
     if (e) return h_fail(h, SAFCONV_ERR_CUDA, "cudaSetDevice", e);
@@ -1282,7 +1380,7 @@ int safconv_get_offline_times(void* hp, float ms[3])
 
 int safconv_set_stream(void* hp, void* cudaStream)
 {
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     scdev_stream_sync(h->stream);
@@ -1302,7 +1400,7 @@ int safconv_synchronize(void* hp)
 {
     if (scm_is_multi(hp)) return scm_synchronize(hp);
     if (scn_is_np(hp)) return SAFCONV_OK;                /* its apply is synchronous and nothing else enqueues work */
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     int e = scdev_stream_sync(h->stream);
@@ -1313,7 +1411,7 @@ int safconv_reset_state(void* hp)
 {
     if (scm_is_multi(hp)) return scm_reset_state(hp);
     if (scn_is_np(hp)) return scn_reset_state(hp);
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     h->tailReady = 0;
@@ -1357,7 +1455,7 @@ int safconv_get_info(void* hp, safconv_info* info)
 
 int safconv_enable_kernel_timing(void* hp, int nGroups)
 {
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h || nGroups < 0) return SAFCONV_ERR_ARG;
     scdev_set_device(h->device);
     scdev_stream_sync(h->stream);
@@ -1424,13 +1522,14 @@ int safconv_get_kernel_times(void* hp, float ms[3], int* nBlocksOut)
 int safconv_set_option(void* hp, const char* name, int value)
 {
     if (scm_is_multi(hp)) return scm_set_option(hp, name, value);
-    safconv_handle* h = as_handle(hp);
+    safconv_handle* h = as_handle_q(hp);
     if (!h || !name) return SAFCONV_ERR_ARG;
     if (!strcmp(name, "mac_hints")) { h->pl.macHints = (value < 0 || value > 2) ? 1 : value; }
     else if (!strcmp(name, "use_graph")) { h->useGraph = value ? 1 : 0; }
     else if (!strcmp(name, "batching")) { h->batching = value ? 1 : 0; }
     else if (!strcmp(name, "small_fused")) { h->smallFused = value ? 1 : 0; }
     else if (!strcmp(name, "flag_wait")) { h->flagWait = value ? 1 : 0; }
+    else if (!strcmp(name, "resident_us")) { h->residentUs = value < 0 ? 0 : (value > 2000000 ? 2000000 : value); }
     else if (!strcmp(name, "detect_pinned")) { h->detectPinned = value ? 1 : 0; }
     else if (!strcmp(name, "lookahead")) { h->lookahead = (value && h->tailPass.Zp) ? 1 : 0; }
     else return SAFCONV_ERR_ARG;

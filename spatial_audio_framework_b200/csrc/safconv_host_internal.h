@@ -16,6 +16,17 @@
 #define SAFCONV_MAGIC_MULTI 0x5AFC0B28u     /* safconv_multi.c: a handle that spans several devices */
 #define SAFCONV_VERSION_STRING "safconv-b200 0.2 (sm_100a; matrixConv/multiConv/TVConv; multi-GPU handles)"
 
+/* mailbox of the resident latency kernel (page-locked host memory; the device side is ScMailbox in safconv_kernels.cu) */
+#define SC_RES_EXIT 0xFFFFFFFFu
+typedef struct sc_mailbox {
+    volatile unsigned int done;          /* completion word: sequence number of the last finished block */
+    unsigned int pad0[15];
+    volatile unsigned long long bell;    /* doorbell, ONE 8-byte word: low half = sequence number, high half = (generation << 8) | slot */
+    volatile unsigned int alive;         /* 1 while a resident kernel is polling */
+    unsigned int pad1[13];
+    volatile unsigned long long buf[16]; /* table of (in, out) buffer addresses, 8 slots */
+} sc_mailbox;
+
 typedef struct safconv_handle {
     uint32_t   magic;
     int        err;
@@ -70,7 +81,12 @@ typedef struct safconv_handle {
     int        headInK3;             /* latency regime: the newest partition is added inside K3 (no head-pass launch) */
     int        trace;                /* SAFCONV_TRACE=1: per-call device timeline of the look-ahead apply on stderr (debugging) */
     void*      trEv[6];              /* head start, head end, previous tail end, K3 start, K3 end, tail end */
-    volatile unsigned int* doneWord; /* page-locked word the cluster latency kernel writes its sequence number into when the block's output is complete */
+    volatile unsigned int* doneWord; /* page-locked word the cluster latency kernel writes its sequence number into when the block's output is complete
+                                        (= &mailbox->done: the first word of the resident kernel's mailbox) */
+    struct sc_mailbox* mailbox;      /* page-locked: completion word, doorbell, alive flag, buffer addresses (layout = ScMailbox in safconv_kernels.cu) */
+    int        residentUs;           /* option "resident_us" / SAFCONV_RESIDENT_US: > 0 keeps the cluster latency kernel resident; it leaves after this idle time */
+    int        resActive;            /* a resident kernel has been started on `stream` */
+    unsigned int resGen, resNext;    /* generation of the mailbox's buffer table, next slot to replace */
     unsigned int doneSeq;
     int        flagWait;             /* option "flag_wait" / SAFCONV_FLAG_WAIT: poll doneWord instead of synchronising the stream */
     int        hostTrace;            /* SAFCONV_HOSTTRACE=1: host-side time of the zero-copy apply by segment, printed at destroy */

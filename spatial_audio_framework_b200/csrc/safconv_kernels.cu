@@ -1041,12 +1041,27 @@ __device__ __forceinline__ void cl_store_f2(const void* localSmem, uint32_t rank
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" :: "r"(remote), "f"(v.x), "f"(v.y) : "memory");
 }
 
-template <int R>
-__global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCArgs a)
+/* system-scope loads: data the HOST rewrites while a resident kernel is running (input blocks, the doorbell) */
+__device__ __forceinline__ unsigned int ld_sys_u32(const volatile unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* One block on the cluster.  RES = true: called from the resident kernel's loop -- nothing that changes between blocks may
+ * come through a non-coherent or L1-cached path (input: system scope; ring, counter, tails: L2). */
+template <int R, bool RES>
+__device__ __forceinline__ void small_cluster_block(const SmallCArgs& a, float2* smc)
 {
     constexpr int M = 32 * R, LOGR = wf_log2(R);
     constexpr int ZS = M + 33;                                  /* float2 per owned output: spectrum, then time-domain staging */
-    extern __shared__ __align__(16) float2 smc[];
     float2* Zs  = smc;                                          /* [owned outputs][ZS] */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = (int)cl_ctarank(), C = (int)cl_nctarank();
@@ -1065,15 +1080,16 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
         for (int i = 0; i < R; ++i) {
             const int n = lane + 32 * i;
             v[i] = make_float2(0.f, 0.f);
-            if (vecIn) { if (2 * n < a.hop) v[i] = __ldg(reinterpret_cast<const float2*>(x) + n); }
+            /* RES: ld.global.cv -- fetched again on every execution (the host rewrites the block between doorbells), coalesced like any load */
+            if (vecIn) { if (2 * n < a.hop) v[i] = RES ? __ldcv(reinterpret_cast<const float2*>(x) + n) : __ldg(reinterpret_cast<const float2*>(x) + n); }
             else {
-                if (2 * n < a.hop)     v[i].x = __ldg(x + 2 * n);
-                if (2 * n + 1 < a.hop) v[i].y = __ldg(x + 2 * n + 1);
+                if (2 * n < a.hop)     v[i].x = RES ? __ldcv(x + 2 * n) : __ldg(x + 2 * n);
+                if (2 * n + 1 < a.hop) v[i].y = RES ? __ldcv(x + 2 * n + 1) : __ldg(x + 2 * n + 1);
             }
         }
     };
     if (R <= 16 && niA < a.nIn) load_block(niA);                /* R = 32 keeps its registers for the prologue: loaded in phase A */
-    const unsigned int count = a.counters[0];
+    const unsigned int count = RES ? __ldcg(a.counters) : a.counters[0];
     const int head = (int)(count % (unsigned)a.RS);
     const WfftLane Lf = wfft_lane_init<false>(a.tw, M, lane);
     WfftLane Li = Lf;
@@ -1090,7 +1106,7 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
 #pragma unroll
         for (int u = 0; u < R; ++u) {
             const int i = lane + 32 * u;
-            tl[TLPRE ? u : 0] = (warp < nOwn && i < a.hop) ? a.tail[(size_t)noMine * a.hop + i] : 0.f;
+            tl[TLPRE ? u : 0] = (warp < nOwn && i < a.hop) ? __ldcg(a.tail + (size_t)noMine * a.hop + i) : 0.f;
         }
     }
 
@@ -1107,7 +1123,7 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
                 const int p = t / a.nIn, ni = t - p * a.nIn;
                 const float2* h = Hk + (size_t)t * a.OTsz * SC_BK;
                 prefetch_l1(h); prefetch_l1(h + 16);
-                if (p > 0) {
+                if (!RES && p > 0) {
                     int slot = head - p; if (slot < 0) slot += a.RS;
                     const float2* x = Xk + ((size_t)slot * a.nIn + ni) * SC_BK;
                     prefetch_l1(x); prefetch_l1(x + 16);
@@ -1168,8 +1184,8 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
                         if (t < t1) {
                             hv[u] = __ldg(Hk + (unsigned)t * hStep);
                             const float2* xp = Xk + (unsigned)(slot * a.nIn + ni) * SC_BK;
-                            xv[u] = (p == 0) ? __ldcg(xp)         /* written by other CTAs of this launch: L2 */
-                                             : __ldg(xp);         /* older blocks: prefetched into L1 above */
+                            xv[u] = (RES || p == 0) ? __ldcg(xp)  /* written by other CTAs of this launch: L2 */
+                                                    : __ldg(xp);  /* older blocks: prefetched into L1 above */
                             if (++ni == a.nIn) { ni = 0; ++p; slot = (slot == 0) ? a.RS - 1 : slot - 1; }
                         }
                     }
@@ -1221,7 +1237,7 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
             if (i < a.hop) {
                 const int s1 = i + a.hop;
                 const int n0 = i >> 1, n1 = s1 >> 1;
-                out[i]  = zf[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)] + (TLPRE ? tl[TLPRE ? u : 0] : tail[i]);
+                out[i]  = zf[2 * ((n0 & (R - 1)) + (R + 1) * (n0 >> LOGR)) + (i & 1)] + (TLPRE ? tl[TLPRE ? u : 0] : __ldcg(tail + i));
                 tail[i] = zf[2 * ((n1 & (R - 1)) + (R + 1) * (n1 >> LOGR)) + (s1 & 1)];
             }
         }
@@ -1241,6 +1257,88 @@ __global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCA
                 }
             }
         }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_kernel(SmallCArgs a)
+{
+    extern __shared__ __align__(16) float2 smc[];
+    small_cluster_block<R, false>(a, smc);
+}
+
+/* RESIDENT version (option "resident_us"): the cluster stays on its SMs and serves one block per DOORBELL -- the host writes
+ * the block's buffer addresses and a sequence number into a page-locked mailbox, CTA 0 polls it at system scope, the cluster
+ * runs the block and writes the sequence number into the completion word.  A call then costs two PCIe hops and the block
+ * itself; the launch + completion path of a kernel (9.2 us for an EMPTY kernel on this pool, tools/lat_floor.cu) is gone.
+ * The kernel leaves on its own after `idleNs` without a doorbell (alive = 0: the host starts a new one with the next block),
+ * or when the host rings SC_RES_EXIT (any other call on the handle, destroy). */
+#define SC_RES_EXIT 0xFFFFFFFFu
+struct ScMailbox {                       /* page-locked host memory; layout shared with safconv_host.c (sc_mailbox) */
+    volatile unsigned int done;          /* completion word: sequence number of the last finished block */
+    unsigned int pad0[15];
+    volatile unsigned long long bell;    /* doorbell, ONE 8-byte word: low half = sequence number, high half = (generation << 8) | slot */
+    volatile unsigned int alive;         /* 1 while a resident kernel is polling */
+    unsigned int pad1[13];
+    volatile unsigned long long buf[16]; /* table of (in, out) buffer addresses, 8 slots; `generation` changes whenever the host rewrites it */
+};
+
+template <int R>
+__global__ void __launch_bounds__(SC_CL_THREADS, 1) small_cluster_resident_kernel(SmallCArgs a, ScMailbox* mb, unsigned int lastSeq,
+                                                                                  unsigned long long idleNs)
+{
+    extern __shared__ __align__(16) float2 smc[];
+    __shared__ unsigned long long s_cmd[3];                    /* CTA 0: seq, in, out of the next block */
+    __shared__ unsigned long long s_tab[16];                   /* CTA 0, thread 0: its copy of the buffer table */
+    const int c = (int)cl_ctarank();
+    unsigned int tabGen = 0xFFFFFFFFu;                         /* generation of s_tab (thread 0 of CTA 0) */
+    for (;;) {
+        if (c == 0 && threadIdx.x == 0) {
+            unsigned long long t0, t, bell;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            unsigned int seq;
+            for (;;) {
+                bell = ld_sys_u64(&mb->bell);                  /* one PCIe read: sequence number, slot and table generation together */
+                seq = (unsigned int)bell;
+                if (seq != lastSeq) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > idleNs) { seq = SC_RES_EXIT; break; }
+            }
+            cl_stamp(a.stamps, 6);
+            s_cmd[0] = seq;
+            if (seq != SC_RES_EXIT) {
+                const unsigned int hi = (unsigned int)(bell >> 32), slot = hi & 7u, gen = hi >> 8;
+                if (gen != tabGen) {                           /* the host rewrote the table (new caller buffers): one more round trip, 16 loads in flight */
+                    unsigned long long v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = ld_sys_u64(&mb->buf[i]);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s_tab[i] = v[i];
+                    tabGen = gen;
+                }
+                s_cmd[1] = s_tab[2 * slot]; s_cmd[2] = s_tab[2 * slot + 1];
+            }
+        }
+        cl_sync();                                              /* CTA 0's command is visible to the whole cluster */
+        unsigned long long cmd[3];
+        {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(s_cmd)), "r"(0));
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(cmd[i]) : "r"(remote + 8u * i) : "memory");
+        }
+        const unsigned int seq = (unsigned int)cmd[0];
+        if (seq == SC_RES_EXIT) {
+            cl_sync();                                          /* nobody reads CTA 0's shared memory after it has left */
+            if (c == 0 && threadIdx.x == 0) { __threadfence_system(); mb->alive = 0u; }
+            return;
+        }
+        SmallCArgs b = a;
+        b.in = reinterpret_cast<const float*>(cmd[1]); b.out = reinterpret_cast<float*>(cmd[2]);
+        b.done = &mb->done; b.seq = seq;
+        small_cluster_block<R, true>(b, smc);
+        lastSeq = seq;
     }
 }
 
@@ -1271,6 +1369,58 @@ static int small_cluster_launch(const SmallCArgs& a, int C, cudaStream_t st)
     at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return (int)cudaLaunchKernelEx(&cfg, small_cluster_kernel<R>, a);
+}
+
+static void small_cluster_fill(SmallCArgs& a, const scdev_plan* pl, const scdev_bufs* b, int* C)
+{
+    a.in = NULL; a.out = NULL; a.done = NULL; a.seq = 0; a.stamps = NULL;
+    a.H = (const float2*)b->H; a.X = (float2*)b->X; a.tw = (const float2*)b->tw;
+    a.wT1 = (const float2*)b->wtab; a.wT2 = (const float2*)b->wtab + pl->M;
+    a.tail = b->tail; a.counters = b->counters;
+    a.hop = pl->hop; a.P = pl->P; a.nIn = pl->nIn; a.nOut = pl->nOutLocal; a.nKT = pl->nKT; a.OTsz = pl->OTsz; a.RS = pl->RS;
+    a.scale = 1.0f / (float)pl->N;
+    int work = pl->nOutLocal * pl->nKT;
+    if (pl->nIn > work) work = pl->nIn;
+    *C = work < SC_CL_MAXC ? work : SC_CL_MAXC;
+}
+
+static unsigned long long* g_resStamps = NULL;
+template <int R>
+static int small_resident_launch(const SmallCArgs& a, int C, ScMailbox* mb, unsigned int lastSeq, unsigned long long idleNs, cudaStream_t st)
+{
+    const int nOwnMax = (a.nOut + C - 1) / C;
+    const size_t smem = ((size_t)nOwnMax * (32 * R + 33) + SC_CL_WARPS * 32) * sizeof(float2);
+    if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(small_cluster_resident_kernel<R>));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(SC_CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, small_cluster_resident_kernel<R>, a, mb, lastSeq, idleNs);
+}
+
+static int small_resident_start(const scdev_plan* pl, const scdev_bufs* b, void* mailbox, unsigned int lastSeq, unsigned int idleUs,
+                                cudaStream_t st)
+{
+    if (!small_cluster_ok(pl, b)) return (int)cudaErrorNotSupported;
+    SmallCArgs a; int C;
+    small_cluster_fill(a, pl, b, &C);
+    {   /* debugging (SAFCONV_KSTAMPS=1): %globaltimer of CTA 0 -- [6] doorbell seen, [0..5] phase boundaries of the block; read with scdev_small_resident_stamps */
+        const char* v = getenv("SAFCONV_KSTAMPS");
+        if (v && atoi(v)) { if (!g_resStamps) cudaMalloc(&g_resStamps, 64); a.stamps = g_resStamps; }
+    }
+    ScMailbox* mb = (ScMailbox*)mailbox;
+    const unsigned long long idleNs = (unsigned long long)idleUs * 1000ull;
+    switch (pl->M) {
+        case 64:   return small_resident_launch<2>(a, C, mb, lastSeq, idleNs, st);
+        case 128:  return small_resident_launch<4>(a, C, mb, lastSeq, idleNs, st);
+        case 256:  return small_resident_launch<8>(a, C, mb, lastSeq, idleNs, st);
+        case 512:  return small_resident_launch<16>(a, C, mb, lastSeq, idleNs, st);
+        case 1024: return small_resident_launch<32>(a, C, mb, lastSeq, idleNs, st);
+        default:   return (int)cudaErrorInvalidValue;
+    }
 }
 
 static int scdev_small_cluster(const scdev_plan* pl, const scdev_bufs* b, const float* in, float* out, cudaStream_t st,
@@ -1925,6 +2075,21 @@ int scdev_small_fits(const scdev_plan* pl, int maxSmemOptin)
     if ((long long)pl->nOutLocal * pl->nIn > 256) return 0;                       /* redundant forward FFTs stay cheap */
     if ((double)pl->P * pl->nIn * pl->M * 8.0 > 4.0 * 1024 * 1024) return 0;       /* per-output filter bytes: L2-resident */
     return 1;
+}
+
+/* start the resident version of the cluster latency kernel on `stream` (returns cudaErrorNotSupported if the plan is not
+ * served by the cluster kernel); mailbox: page-locked, layout ScMailbox */
+int scdev_small_resident_start(const scdev_plan* pl, const scdev_bufs* b, void* mailbox, unsigned int lastSeq, unsigned int idleUs,
+                               void* stream)
+{
+    return small_resident_start(pl, b, mailbox, lastSeq, idleUs, (cudaStream_t)stream);
+}
+
+/* debugging: the last block's stamps of the resident kernel (call when the device is idle or between blocks) */
+int scdev_small_resident_stamps(unsigned long long out[8])
+{
+    if (!g_resStamps) return -1;
+    return (int)cudaMemcpy(out, g_resStamps, 64, cudaMemcpyDeviceToHost);
 }
 
 /* done / seq: optional host-visible completion word (page-locked, mapped) -- only the cluster kernel signals it; *signalled

@@ -9,6 +9,7 @@
 
 Tolerance (north_star): max abs error <= 1e-5 of full scale AND relative L2 <= 1e-6 vs the reference.
 """
+import ctypes as C
 import time
 
 import numpy as np
@@ -88,3 +89,55 @@ def test_lookahead_knobs_vs_oracle(saf, orc, monkeypatch, hop, L, nIn, nOut, nbl
         time.sleep(0.003)                                # every pending tail pass has finished: latency regime
     check(yp, ref, "look-ahead, paced")
     mc.destroy()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("hop,L,nIn,nOut,nblk", [(128, 512, 25, 2, 14), (256, 1024, 4, 2, 12), (50, 333, 5, 3, 17),
+                                                   (512, 2000, 9, 17, 9), (1024, 3000, 6, 4, 6)])
+def test_resident_latency_kernel(saf, orc, hop, L, nIn, nOut, nblk):
+    """Option "resident_us": the cluster kernel stays on its SMs and serves one block per doorbell (no launch per call).
+    Same results as the one-launch path bit for bit (same code, other load instructions); it leaves on its idle timer and
+    comes back with the next block; every other call on the handle stops it first; destroy while it polls is clean."""
+    import torch
+    rng = np.random.default_rng(hop + nIn * 3 + nOut)
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    plain = saf.MatrixConv(hop, H, 1)
+    y0 = plain.run(x)
+    plain.destroy()
+    mc = saf.MatrixConv(hop, H, 1)
+    mc.set_option("resident_us", 3000)                   # 3 ms idle timer
+    y = mc.run(x)                                        # pageable numpy blocks: staged through the handle's pinned buffers
+    check(y, ref, "resident kernel")
+    assert np.array_equal(y, y0)
+    # idle longer than the timer between blocks: the kernel has left, the next call starts a new one
+    mc.reset_state()                                     # (stops the resident kernel, zeroes the state)
+    yp = np.empty_like(y)
+    for b in range(nblk):
+        yp[:, b * hop:(b + 1) * hop] = mc.apply(np.ascontiguousarray(x[:, b * hop:(b + 1) * hop]))
+        if b % 3 == 0:
+            time.sleep(0.02)
+    assert np.array_equal(yp, y0)
+    # page-locked caller buffers, other calls in between (device-pointer block, option change)
+    mc.reset_state()
+    n1 = nblk // 2
+    fp = C.POINTER(C.c_float)
+    parts = []
+    for b in range(n1):
+        xb = torch.from_numpy(np.ascontiguousarray(x[:, b * hop:(b + 1) * hop])).pin_memory()
+        yb = torch.empty((nOut, hop)).pin_memory()
+        saf.lib().saf_matrixConv_apply(mc.handle, C.cast(xb.data_ptr(), fp), C.cast(yb.data_ptr(), fp))     # zero-copy: the kernel reads / writes these
+        assert saf.lib().safconv_last_error(mc.handle) == 0
+        parts.append(yb.numpy().copy())
+    d_in = torch.from_numpy(np.ascontiguousarray(x[:, n1 * hop:(n1 + 1) * hop])).cuda()
+    d_out = torch.empty((nOut, hop), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    mc.apply_device(d_in.data_ptr(), d_out.data_ptr(), 1)     # stops the resident kernel, runs on the stream
+    mc.synchronize()
+    parts.append(d_out.cpu().numpy())
+    mc.set_option("flag_wait", 0)
+    for b in range(n1 + 1, nblk):
+        parts.append(mc.apply(np.ascontiguousarray(x[:, b * hop:(b + 1) * hop])))
+    check(np.concatenate(parts, 1), ref, "resident / device-pointer / resident")
+    mc.destroy()                                         # while the kernel is polling
