@@ -306,6 +306,21 @@ def cpu_reference_run(w, steps, warmup, threads=None, blocks_per_step=None, ch_p
                 ms_per_step=1e3 * dt / steps)
 
 
+def workload_config(w, world):
+    """`config` of the JSON line: what defines the workload, identical in both arms (the driver compares the two dicts);
+    everything that describes HOW an arm ran it goes to `config_detail`."""
+    hop, L = w["hop"], w["L"]
+    P = int(np.ceil(np.float32(L) / np.float32(hop)))
+    M = 32
+    while M < hop:
+        M *= 2
+    per_gpu_mb = ((w["nOut"] + world - 1) // world) * w["nIn"] * P * M * 8 / 1e6
+    return {"workload": w["desc"], "nIn": w["nIn"], "nOut": w["nOut"], "hop": hop, "length_h": L, "partitions": P,
+            "l2": "inputs larger than L2: %.0f MB of filter spectra streamed per block per GPU (L2 = 126 MB)" % per_gpu_mb
+                  if per_gpu_mb > 126 else "filter spectra (%.1f MB per GPU) fit in L2: L2 is not flushed between blocks, the real-time use keeps them there" % per_gpu_mb,
+            "filters": "exponentially decaying uniform noise (-60 dB at the last tap), seeded per output channel"}
+
+
 def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -315,7 +330,7 @@ def run_reference_arm(args, w):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "nIn": w["nIn"], "nOut": w["nOut"], "hop": w["hop"], "length_h": w["L"]},
+        "config": workload_config(w, max(1, args.gpus)),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -828,12 +843,10 @@ def run_own_arm(args, w):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "nIn": nIn, "nOut": nOut, "hop": hop, "length_h": w["L"],
-                   "blocks_per_step": B, "partitions": int(info.numFilterBlocks),
-                   "sharding": f"output channels over {world} GPU(s), {oc} per GPU; value: one process per GPU, input batch NCCL-broadcast, output shards all-gathered; e2e: one multi-GPU handle in rank 0" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2: %.0f MB of filter spectra streamed per block per GPU (L2 = 126 MB)" % (info.bytesFilters / 1e6),
-                   "filters": "exponentially decaying uniform noise (-60 dB at the last tap), seeded per output channel",
-                   "create_seconds_rank0": create_s},
+        "config": workload_config(w, world),
+        "config_detail": {"blocks_per_step": B, "partitions": int(info.numFilterBlocks), "filter_spectra_bytes_this_gpu": int(info.bytesFilters),
+                          "sharding": f"output channels over {world} GPU(s), {oc} per GPU; value: one process per GPU, input batch NCCL-broadcast, output shards all-gathered; e2e: one multi-GPU handle in rank 0" if world > 1 else "single GPU",
+                          "create_seconds_rank0": create_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
         "ms_per_block": ms_total / (args.steps * B),
