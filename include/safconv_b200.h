@@ -40,8 +40,10 @@ extern "C" {
  * (implementation saf_utility_matrixConv.c:49-130).
  *
  * @param phMC        (&) handle; overwritten (NULL on failure)
- * @param hopSize     block length in samples (1..8192 for all three convolvers; larger values are rejected with an
- *                    error string -- the reference's own hosts clamp their frames to 8192)
+ * @param hopSize     block length in samples, any positive value for saf_matrixConv / saf_multiConv (up to 8192 on the
+ *                    partitioned engine; larger blocks on the big-FFT engine of csrc/safconv_np.c, same linear convolution --
+ *                    only an ODD numOvrlpAddBlocks * hopSize above 8192 is rejected); saf_TVConv: 1..8192, larger values are
+ *                    rejected with an error string (the reference's tvconv host clamps its frames to 8192)
  * @param H           time-domain filters, FLAT nCHout x nCHin x length_h; only
  *                    read during this call (caller may free it afterwards)
  * @param usePartFLAG 0/1 as in the reference.  Both modes produce the same causal
@@ -106,7 +108,7 @@ int safconv_set_true_mode0(int enable);
 /** Error codes stored per handle / per thread. 0 means OK. */
 enum {
     SAFCONV_OK            = 0,
-    SAFCONV_ERR_ARG       = 1,  /* invalid argument (sizes <= 0, NULL pointers, hop > 8192 ...) */
+    SAFCONV_ERR_ARG       = 1,  /* invalid argument (sizes <= 0, NULL pointers, TVConv hop > 8192 ...) */
     SAFCONV_ERR_NO_DEVICE = 2,  /* no usable CUDA device / driver */
     SAFCONV_ERR_CUDA      = 3,  /* a CUDA runtime call or kernel failed */
     SAFCONV_ERR_NOMEM     = 4   /* host or device allocation failed */

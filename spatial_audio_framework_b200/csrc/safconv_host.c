@@ -990,11 +990,25 @@ void sch_apply_pinned(safconv_handle* h, const float* src, float* dst, int irIdx
 /*  drop-in API                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 
+/* Blocks longer than 8192 samples: the partitioned engine keeps one block's FFT inside one CTA's shared memory and
+ * stops there, but the reference takes any hop (saf_utility_matrixConv.c:100: fftSize = 2 * hopSize).  Such handles are
+ * served by the big-FFT engine of safconv_np.c (one numOvrlpAddBlocks * hopSize-point transform per channel and block on
+ * the general-size device FFT, which runs sizes beyond shared memory as one launch per pass): the same causal linear
+ * convolution for either usePartFLAG.  Not possible only if that FFT size is odd (odd hop with an odd block count). */
+static void* create_big_hop(int kind, int hopSize, const float* H, int length_h, int nIn, int nOut)
+{
+    void* h = scn_create(kind, hopSize, H, length_h, nIn, nOut);
+    if (!h && !tl_err)
+        set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s: hopSize > 8192 needs an even numOvrlpAddBlocks * hopSize (the big-FFT engine serves these block sizes)", "");
+    return h;
+}
+
 void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCHin, int nCHout, int usePartFLAG)
 {
     /* both reference modes compute the same linear convolution; the partitioned engine serves both unless the true
      * big-FFT semantics of mode 0 are asked for (safconv_np.c) */
     if (!phMC) return;
+    if (hopSize > SC_MAX_M) { *phMC = create_big_hop(SC_KIND_MATRIX, hopSize, H, length_h, nCHin, nCHout); return; }
     if (!usePartFLAG && scn_enabled()) {
         *phMC = scn_create(SC_KIND_MATRIX, hopSize, H, length_h, nCHin, nCHout);
         if (*phMC || tl_err) return;                     /* built, or failed for a real reason; odd fftSize falls through */
@@ -1048,6 +1062,7 @@ void saf_matrixConv_apply(void* const hMC, float* inputSigs, float* outputSigs)
 void saf_multiConv_create(void** const phMC, int hopSize, float* H, int length_h, int nCH, int usePartFLAG)
 {
     if (!phMC) return;
+    if (hopSize > SC_MAX_M) { *phMC = create_big_hop(SC_KIND_MULTI, hopSize, H, length_h, nCH, nCH); return; }
     if (!usePartFLAG && scn_enabled()) {
         *phMC = scn_create(SC_KIND_MULTI, hopSize, H, length_h, nCH, nCH);
         if (*phMC || tl_err) return;

@@ -53,7 +53,8 @@ def test_invalid_arguments_leave_null_handle(saf):
     H = np.zeros((2, 2, 16), np.float32)
     hp = H.ctypes.data_as(C.POINTER(C.c_float))
     for args in [(0, hp, 16, 2, 2, 1), (64, hp, 0, 2, 2, 1), (64, hp, 16, 0, 2, 1), (64, hp, 16, 2, 0, 1),
-                 (16384, hp, 16, 2, 2, 1), (64, None, 16, 2, 2, 1)]:
+                 (64, None, 16, 2, 2, 1), (16384, None, 16, 2, 2, 1),
+                 (16385, hp, 1, 2, 2, 1)]:      # hop > 8192 goes to the big-FFT engine, which needs an even numOvrlpAddBlocks * hop (here 1 x 16385)
         h = C.c_void_p(123)
         lib.saf_matrixConv_create(C.byref(h), *args)
         assert not h.value

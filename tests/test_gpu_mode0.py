@@ -96,3 +96,24 @@ def test_true_mode0_odd_fft_size_falls_back_to_the_partitioned_engine(saf, orc, 
     assert mc.info().fftSize == 64
     check(mc.run(x), orc.OracleMatrixConv(hop, H, 1).run(x), "odd fftSize")
     mc.destroy()
+
+
+@pytest.mark.parametrize("part", [1, 0])
+@pytest.mark.parametrize("hop,L,nIn,nOut,nblk", [(16384, 20000, 2, 3, 4), (12000, 5000, 3, 2, 5), (10000, 30000, 1, 2, 6)])
+def test_block_sizes_above_8192(saf, orc, hop, L, nIn, nOut, nblk, part):
+    """The reference takes any hopSize (saf_utility_matrixConv.c:100); the partitioned engine stops at 8192 (one block's FFT
+    in one CTA's shared memory), larger blocks are served by the big-FFT engine for EITHER usePartFLAG -- same causal linear
+    convolution as the reference's partitioned mode."""
+    rng = np.random.default_rng(hop + L)
+    H = rng.uniform(-1, 1, (nOut, nIn, L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nIn, hop * nblk)).astype(np.float32)
+    ref = orc.OracleMatrixConv(hop, H, 1).run(x)
+    mc = saf.MatrixConv(hop, H, part)
+    assert mc.info().fftSize == ref_fft_size(hop, L)
+    check(mc.run(x), ref, f"matrixConv, hop {hop}")
+    mc.destroy()
+    Hm = rng.uniform(-1, 1, (nIn + 1, L)).astype(np.float32)
+    xm = rng.uniform(-1, 1, (nIn + 1, hop * nblk)).astype(np.float32)
+    mm = saf.MultiConv(hop, Hm, part)
+    check(mm.run(xm), orc.OracleMultiConv(hop, Hm, 1).run(xm), f"multiConv, hop {hop}")
+    mm.destroy()
