@@ -19,13 +19,19 @@
  *   multi_fused_kernel      multiConv: K1+K2+K3 in one launch, one CTA per channel
  *   multi_fft_w_kernel /    multiConv, batches of device-resident blocks on the warp-level register FFT
  *   multi_mac_ifft_w_kernel (safconv_wfft.cuh): register sliding window over the delay line per bin
- *   small_fused_kernel      small matrix problems: K1+K2+K3 in one launch on mapped host buffers
- *   tv_fused_kernel         TVConv: one CTA per output channel, up to three IR sets + cross-fade
- *   rfft_forward/backward   the FFT pair on its own (saf_rfft conventions), parity-test entry points
+ *   small_cluster_kernel<R> small matrix problems (M = 32 R = 64 .. 1024): K1+K2+K3 in one launch on ONE thread-block
+ *                           cluster of up to 8 CTAs (one warp per FFT on the register FFT, per-bin sums spread over the
+ *                           CTAs, distributed-shared-memory gather), mapped host buffers; and its RESIDENT version
+ *                           small_cluster_resident_kernel<R>: one block per doorbell, no launch per call
+ *   small_fused_kernel      the same for the remaining small shapes: one CTA per output
+ *   tv_fused_kernel         TVConv: one CTA per output channel, up to three IR sets + cross-fade; hops above 4096 as
+ *                           tv_input_kernel / tv_mac_ifft_kernel / tv_xfade_kernel
+ *   rfft_forward/backward   the power-of-two FFT pair on its own (saf_rfft conventions), parity-test entry points
+ *   (general-size FFT: safconv_gfft.cu; offline tensor-core path: safconv_offline.cu)
  *
  * K2 runs over a PASS = partitions [pLo, pLo+nP) of every group: the full pass, and for the look-ahead
- * apply of the host layer a tail pass (1, P-1) that is enqueued ahead of the next block and a head pass
- * (0, 1); K3 can also add the newest partition itself (headH).
+ * apply of the host layer a tail pass (D, P-D) that is enqueued ahead of the next block(s) and a head pass
+ * (0, D), D = 1 or 2; K3 can also add the newest partition(s) itself (headH).
  *
  * The real FFT of size N is an M = N/2 point complex FFT (safconv_fft.cuh: radix-4/2 decimation-in-
  * frequency passes in shared memory with the last five radix-2 stages as warp-shuffle butterflies, or
