@@ -45,7 +45,10 @@
 #define OFF_NH   4       /* filter-operand pipeline stages                                   */
 #define OFF_FPC  4       /* frames per forward-FFT CTA (64-byte contiguous operand writes)    */
 #define OFF_OPC  8       /* outputs per inverse-FFT CTA (64-byte contiguous spectrum reads)   */
-#define OFF_GEMM_THREADS 320   /* warps 0-7 epilogue (accumulator promotion), warp 8 TMA producer, warp 9 MMA issuer */
+#define OFF_GEMM_THREADS 384   /* three warpgroups: warps 0-7 epilogue (accumulator promotion), warp 8 TMA producer, warp 9 MMA issuer,
+                                  warps 10-11 idle (they only fill the third warpgroup, which hands its registers to the other two) */
+#define OFF_EPI_REGS  232      /* setmaxnreg: 256 epilogue threads x 232 + 128 x 40 = the 384 x 168 the kernel is launched with */
+#define OFF_AUX_REGS  40
 
 /* round-to-nearest tf32 (10 explicit mantissa bits) of an fp32 value, returned in an fp32 container */
 __device__ __forceinline__ float tf32_rn(float x)
@@ -426,6 +429,15 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v)
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+/* 32 consecutive columns, NO wait (the caller overlaps the load with the additions of the previous batch) */
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 {
     uint32_t r[16];
@@ -532,7 +544,10 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmemPtr;
-
+    /* register re-allocation between the warpgroups: the epilogue warps keep 128 running sums AND two 32-column batches of a
+     * chain in registers (the load of batch i+1 in flight while batch i is added); producer and MMA issuer need very few */
+    if (warp >= OFF_EPI_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(OFF_AUX_REGS));
     if (warp == OFF_EPI_WARPS) {
         /* ===================== scheduler + TMA producer ===================== */
         if (lane == 0) {
@@ -648,7 +663,9 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                 __syncwarp();
             }
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(OFF_EPI_REGS));
         /* ===================== epilogue warps: promote TMEM chains into fp32 register sums ===================== */
         const int q4 = warp & 3, hh = warp >> 2;           /* TMEM lane quarter (= warp % 4), column half */
         const int halfN = a.Nn >> 1;
@@ -672,6 +689,29 @@ __global__ void __launch_bounds__(OFF_GEMM_THREADS, 1) offline_gemm_kernel(OffGe
                 const int tb = (int)(g & 1u);
                 mbar_wait(&tfull[tb], (g >> 1) & 1u);
                 tc_fence_after();
+                /* full tile: the 128 columns of this thread as four 32-column batches, the load of batch i+1 in flight while
+                 * batch i is added -- a chain's pace is this drain (wake-up, load latency, adds, arrive), not the MMA */
+                const bool fullDrain = (halfN == 64) && (NT ? (hh * 128 + 128 <= tl.nFr) : (tl.nFr > 128));
+                if (fullDrain) {
+                    const uint32_t lane16 = (uint32_t)(q4 * 32) << 16;
+                    const uint32_t c_t0 = NT ? (uint32_t)(tb * 256 + hh * 128) : (uint32_t)((tb * 2 + 0) * a.Nn + hh * halfN);
+                    const uint32_t c_t1 = NT ? c_t0 + 64u                      : (uint32_t)((tb * 2 + 1) * a.Nn + hh * halfN);
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32_nowait(tmem + lane16 + c_t0, ra);
+                    tmem_ld32_nowait(tmem + lane16 + c_t0 + 32u, rb);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum[0][i] += __uint_as_float(ra[i]);
+                    tmem_ld32_nowait(tmem + lane16 + c_t1, ra);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum[0][32 + i] += __uint_as_float(rb[i]);
+                    tmem_ld32_nowait(tmem + lane16 + c_t1 + 32u, rb);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum[1][i] += __uint_as_float(ra[i]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum[1][32 + i] += __uint_as_float(rb[i]);
+                } else
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     /* NT: this thread owns frames (columns) hh*128 + t*64 .. +63; frames on M: accumulator t = frames t*128 .. */
