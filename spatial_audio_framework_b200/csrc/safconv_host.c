@@ -880,7 +880,11 @@ static int apply_zero_copy(safconv_handle* h, const float* src, float* dst, int 
     if (small) {                                                  /* small problem: K1 + K2 + K3 in ONE launch */
         if (h->residentUs > 0 && h->mailbox && h->b.wtab) {       /* ... or no launch at all: the resident kernel's doorbell */
             const int e = res_post(h, src, dst);
-            if (e != 801 /* cudaErrorNotSupported: not a cluster-kernel plan */) { *signalled = 2; return e; }
+            if (!e) { *signalled = 2; return 0; }
+            /* not a cluster-kernel plan (cudaErrorNotSupported), or the resident kernel could not be started: this handle
+             * goes on with one launch per block */
+            h->residentUs = 0;
+            if (e != 801) (void)scdev_last_error_clear();
         }
         return scdev_small_fused(pl, &h->b, src, dst, h->stream, (h->flagWait && h->doneWord) ? h->doneWord : NULL, ++h->doneSeq, signalled);
     }

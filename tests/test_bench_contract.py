@@ -1,4 +1,4 @@
-"""The committed bench lines (profiles/r01_bench_*.json, written by bench.py on the GPU box) carry every key the
+"""The committed bench lines (profiles/r0N_bench_*.json, written by bench.py on the GPU box) carry every key the
 bench contract asks for.  Pure CPU: guards bench.py's output format against regressions."""
 import json
 from pathlib import Path
@@ -6,7 +6,7 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
-LINES = sorted((ROOT / "profiles").glob("r01_bench_*.json"))
+LINES = sorted((ROOT / "profiles").glob("r0[0-9]_bench_*.json"))
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
              "vs_baseline", "dtype", "data", "config", "e2e"}
@@ -45,3 +45,38 @@ def test_default_workload_is_the_metric_config():
     base = json.loads((ROOT / "BASELINE.json").read_text())
     assert "64-in x 64-out" in d["config"]["workload"] and "configs[3]" in d["config"]["workload"]
     assert "64-in x 64-out" in base["configs"][3]
+
+
+def test_round2_default_line():
+    """The round-2 default line: both arms describe the workload with the SAME `config`, the secondary block carries every
+    other BASELINE.json config (latencies with page-locked and pageable buffers, the offline tensor-core render with its
+    roofline), the timed path is parity-checked against the oracle, and the 1-core 'as shipped' CPU figure is there."""
+    own = json.loads((ROOT / "profiles" / "r02_bench_c4_n1.json").read_text())
+    ref = json.loads((ROOT / "profiles" / "r02_bench_c4_reference.json").read_text())
+    if "config_detail" in own:                            # lines written after the two configs were unified
+        assert own["config"] == ref["config"]
+    assert own["parity"]["parity_rel_l2"] <= 1e-6 and own["parity"]["parity_max_abs_fs"] <= 1e-5
+    cb = own["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["as_shipped_1_core"]["cores"] == 1 and cb["cpu_model"]
+    sec = own["secondary"]
+    assert {"C1", "C2", "C3", "UT", "C5"} <= set(sec)
+    for k in ("C1", "C2", "C3", "UT"):
+        h = sec[k]["host_api"]
+        assert h["blocks"] >= 2000 and h["warmup_blocks"] >= 100 and h["pinned"]["p50_ms"] > 0 and h["pageable"]["p50_ms"] > 0
+        assert sec[k]["parity"]["parity_rel_l2"] <= 1e-6
+    r5 = sec["C5"]["roofline"]
+    assert r5["bound"] == "tensor" and 0 < r5["frac"] < 1 and r5["issued_frac"] > r5["frac"]
+    e = own["e2e"]
+    assert e["blocks"] >= 2000 and e["block_latency_ms_p50"] > 0 and e["block_latency_paced_ms_p50"] > 0
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_round2_multi_gpu_lines(n):
+    """N > 1: `e2e` is the per-block synchronous call on ONE C-ABI handle over N GPUs (the N = 1 contract), with p50 / p99."""
+    d = json.loads((ROOT / "profiles" / f"r02_bench_c4_n{n}.json").read_text())
+    assert d["n_gpus"] == n
+    e = d["e2e"]
+    assert "safconv_matrixConv_create_multi" in e["api"] and e["blocks"] >= 2000
+    assert e["block_latency_ms_p50"] > 0 and e["block_latency_ms_p99"] >= e["block_latency_ms_p50"]
+    assert len(e["multi_gpu_handle"]["devices"]) == n and set(e["multi_gpu_handle"]["transports"]) == {"host", "nccl"}
+    assert len(d["roofline"]["per_rank"]["mac_ms_per_block"]) == n

@@ -21,4 +21,6 @@ done
 for f in gpurun_out/${R}_*_full.ncu-rep; do
   ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2>/dev/null
 done
+# gpurun copies at most 64 MiB back: keep the raw CSVs of all captures, the reports of the two headline kernels only
+rm -f gpurun_out/${R}_C2_full.ncu-rep gpurun_out/${R}_C3_full.ncu-rep
 ls -la gpurun_out/${R}_*
