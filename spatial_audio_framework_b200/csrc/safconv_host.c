@@ -458,6 +458,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
+        h->oneStreamLatency = env_int("SAFCONV_ONE_STREAM", 1, 0, 1);
         h->headInK3 = env_int("SAFCONV_HEAD_IN_K3", 0, 0, 1);   /* since K3 gathers in three load rounds, head pass + K3 (55 us) beats K3 adding the partition itself (62 us) */
         h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
         for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
@@ -609,13 +610,22 @@ static int enqueue_block(safconv_handle* h, const float* d_in, float* d_out) { r
 /* K1 of the new block; returns with `stream` ordered behind it.  Three sources (sch_la_io): a copy-engine upload into
  * h->d_in (K1 then runs on `stream`), or K1 on the side stream straight from a page-locked host buffer / from a device
  * buffer that a foreign stream fills (evSrc). */
-static int la_input(safconv_handle* h, const sch_la_io* io)
+static int la_input(safconv_handle* h, const sch_la_io* io, int idle)
 {
     const scdev_plan* pl = &h->pl;
     int e = 0;
     if (io->h2dSrc) {
         e = scdev_memcpy_h2d_async(h->d_in, io->h2dSrc, h->inBytes, h->stream);
         LA_TRY(scdev_input_fft(pl, &h->b, h->d_in, 1, h->stream));
+        return e;
+    }
+    if (idle && !io->evSrc) {
+        /* latency regime: nothing is running, so there is nothing to overlap -- K1, head pass and K3 go down ONE stream
+         * (a kernel-to-kernel hand-over on a stream costs ~1.5 us, an event hop between streams 3-4 us) */
+        LA_TL(0, h->stream);
+        e = scdev_input_fft(pl, &h->b, io->k1src, 1, h->stream);
+        LA_TL(1, h->stream);
+        LA_TRY(scdev_event_record(h->evIn, h->stream));
         return e;
     }
     if (!h->tailReady) {                  /* something else may still be running on `stream`: order K1 behind it */
@@ -679,6 +689,15 @@ static int la_latency(safconv_handle* h, unsigned int c, int hadTail, const sch_
         if (hadTail) LA_TRY(scdev_mac_pass(pl, &h->b, &h->headPass, 0, 1, 0, -1, h->stream));
         else         LA_TRY(scdev_mac(pl, &h->b, 0, 1, h->stream));
         LA_TRACE(1, h->stream);
+        if (h->oneStreamLatency && io->sync && !io->evSrc) {
+            LA_TRACE(3, h->stream); LA_TL(2, h->stream); LA_TL(3, h->stream); LA_TL(4, h->stream);
+            if (hadTail) LA_TRY(scdev_ifft_ola_passes(pl, &h->b, &h->tailPass, tb, &h->headPass, kout, h->stream));
+            else         LA_TRY(scdev_ifft_ola(pl, &h->b, kout, h->stream));
+            if (io->d2hDst) LA_TRY(scdev_memcpy_d2h_async(io->d2hDst, h->d_out, h->outBytes, h->stream));
+            LA_TRACE(4, h->stream); LA_TL(5, h->stream);
+            LA_TRY(scdev_event_record(h->evDone, h->stream));
+            return e;
+        }
         LA_TRY(scdev_event_record(h->evMac, h->stream));
         LA_TRY(scdev_stream_wait_event(h->streamOut, h->evMac));
         LA_TRACE(3, h->streamOut);
@@ -748,7 +767,7 @@ int sch_apply_lookahead_io(safconv_handle* h, const sch_la_io* io)
         backToBack = scdev_event_done(h->evTailB[c & 1u]) == 0;
         if (!backToBack && upTo > c) backToBack = scdev_event_done(h->evTailB[(c + 1u) & 1u]) == 0;
     }
-    int e = la_input(h, io);
+    int e = la_input(h, io, !backToBack && h->oneStreamLatency && io->sync);
     h->tailReady = 0;
     h->trRegime = backToBack;
     if (backToBack) LA_TRY(la_throughput(h, c, io, tr));

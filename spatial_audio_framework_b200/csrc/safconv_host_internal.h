@@ -74,6 +74,7 @@ typedef struct safconv_handle {
     void**     tlEv;                 /* [tlCap][8]: K1 start/end, head start/end, K3 start/end, tail pass start/end */
     double*    tlHost;               /* [tlCap][2]: host time at entry / return (ns) */
     char*      tlReg;
+    int        oneStreamLatency;     /* latency regime: K1, head pass and K3 on one stream (no event hops between streams) */
     int        trRegime;             /* trace: regime of the current call */
     int        laDepth;              /* look-ahead depth D: tail passes cover partitions p >= D and are queued D blocks ahead */
     unsigned int tailUpTo;           /* with tailReady: tail passes of blocks count .. tailUpTo are enqueued */
