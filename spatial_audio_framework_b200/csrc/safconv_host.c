@@ -458,7 +458,7 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
         DEV_TRY(h, scdev_stream_create_high_priority(&h->streamOut), "cudaStreamCreate");
         if (zalloc(h, &h->tailPass.ZpB, (size_t)h->tailPass.nSlots * pl->OTsz * SC_BK * 8, "partial spectra allocation (tail, second buffer)")) goto fail;
         h->lookahead = env_int("SAFCONV_LOOKAHEAD", 1, 0, 1);
-        h->oneStreamLatency = env_int("SAFCONV_ONE_STREAM", 1, 0, 1);
+        h->oneStreamLatency = env_int("SAFCONV_ONE_STREAM", 0, 0, 1);   /* measured: 55.3 vs 54.9 us paced p50 at configs[3] -- the event hops are not what the call waits for; off */
         h->headInK3 = env_int("SAFCONV_HEAD_IN_K3", 0, 0, 1);   /* since K3 gathers in three load rounds, head pass + K3 (55 us) beats K3 adding the partition itself (62 us) */
         h->trace = env_int("SAFCONV_TRACE", 0, 0, 1);
         for (int i = 0; i < 6 && h->trace; i++) DEV_TRY(h, scdev_event_create(&h->trEv[i]), "cudaEventCreate");
