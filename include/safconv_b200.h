@@ -237,6 +237,100 @@ int  safconv_fftfilt(const float* x, const float* h, int x_len, int h_len, int n
 void fftconv(float* x, float* h, int x_len, int h_len, int nCH, float* y);
 void fftfilt(float* x, float* h, int x_len, int h_len, int nCH, float* y);
 
+/* ========================================================================== */
+/*  Filter producers in front of the convolvers          */
+/* ========================================================================== */
+
+/**
+ * Convolver from a filter bank that already lies in DEVICE memory: d_H FLAT nCHout x nCHin x length_h on the device the
+ * handle is created on (safconv_set_device / current device).  Same handle as saf_matrixConv_create (partitioned engine,
+ * hopSize <= 8192); d_H is only read during the call.  This is how the two producers below hand their result over
+ * without a device -> host -> device round trip.
+ */
+void safconv_matrixConv_create_device(void** const phMC, int hopSize, const float* d_H, int length_h, int nCHin, int nCHout);
+
+/**
+ * Binaural Ambisonic decoder design on the GPU -- the reference's getBinauralAmbiDecoderMtx / getBinauralAmbiDecoderFilters
+ * (/root/reference/framework/modules/saf_hoa/saf_hoa.h:401-471, saf_hoa.c:393-497), same arguments and layouts:
+ *   hrtfs          FLAT N_bands x 2 x N_dirs, interleaved (re, im) fp32 (the reference's float_complex*)
+ *   hrtf_dirs_deg  FLAT N_dirs x 2, [azimuth, elevation] in degrees
+ *   method         BINAURAL_AMBI_DECODER_METHODS (saf_hoa.h:131-171): 0 default (= LS), 1 LS, 2 LSDIFFEQ, 3 SPR, 4 TA, 5 MAGLS
+ *   weights        N_dirs integration weights or NULL (uniform 1 / N_dirs)
+ *   decMtx         FLAT N_bands x 2 x (order+1)^2 complex;  decFilters FLAT 2 x (order+1)^2 x fftSize real -- the
+ *                  nCHout x nCHin x length_h layout saf_matrixConv_create takes (N_bands = fftSize/2 + 1 for the filters)
+ * LS, LSDIFFEQ, TA and MAGLS are built, with max-rE weighting and diffuse-field covariance matching; SPR (which needs
+ * the reference's t-design tables) returns SAFCONV_ERR_ARG and leaves the output untouched, as does order > 10.
+ * itd_s is accepted and, as in the reference (whose TA phase term is exp(0 * itd), saf_hoa_internal.c:494-497), has no
+ * influence on the result.  The safconv_ names return SAFCONV_OK or an error code (text: safconv_last_error_string(NULL));
+ * the reference's own names are exported as WEAK void functions.
+ */
+int  safconv_getBinauralAmbiDecoderMtx(const void* hrtfs, const float* hrtf_dirs_deg, int N_dirs, int N_bands, int method,
+                                       int order, const float* freqVector, const float* itd_s, const float* weights,
+                                       int enableDiffCovMatching, int enableMaxReWeighting, void* decMtx);
+int  safconv_getBinauralAmbiDecoderFilters(const void* hrtfs, const float* hrtf_dirs_deg, int N_dirs, int fftSize, float fs,
+                                           int method, int order, const float* itd_s, const float* weights,
+                                           int enableDiffCovMatching, int enableMaxReWeighting, float* decFilters);
+void getBinauralAmbiDecoderMtx(void* hrtfs, float* hrtf_dirs_deg, int N_dirs, int N_bands, int method, int order,
+                               float* freqVector, float* itd_s, float* weights, int enableDiffCovMatching,
+                               int enableMaxReWeighting, void* decMtx);
+void getBinauralAmbiDecoderFilters(void* hrtfs, float* hrtf_dirs_deg, int N_dirs, int fftSize, float fs, int method,
+                                   int order, float* itd_s, float* weights, int enableDiffCovMatching,
+                                   int enableMaxReWeighting, float* decFilters);
+/** The same design straight into a (order+1)^2-in, 2-out matrix convolver; the filters never leave the device. */
+int  safconv_binauralDecoder_create_matrixConv(void** const phMC, int hopSize, const void* hrtfs, const float* hrtf_dirs_deg,
+                                               int N_dirs, int fftSize, float fs, int method, int order, const float* weights,
+                                               int enableDiffCovMatching, int enableMaxReWeighting);
+
+/**
+ * Shoebox image-source simulator, RIR path -- the reference's ims_shoebox_* API
+ * (/root/reference/framework/modules/saf_reverb/saf_reverb.h:93-230, saf_reverb.c:36-295, 541-856): same arguments, same
+ * ID assignment, same refresh rules.  ims_shoebox_renderRIRs enumerates the image sources of every pending
+ * source / receiver pair on the GPU and accumulates them straight into the RIR taps (tap positions bit-identical to the
+ * reference; fractionalDelaysFLAG must be 0, as in the reference).  As in the reference, the band RIRs are summed
+ * WITHOUT the octave filterbank (saf_reverb_internal.c:697-702 filters into a scratch buffer that is never read).
+ * Receivers up to SH order 10; ims_shoebox_applyEchogramTD (the time-domain renderer) is not part of this path.
+ * The reference's names are exported as WEAK symbols that forward to the safconv_ims_shoebox_ ones.
+ */
+void safconv_ims_shoebox_create(void** phIms, float roomDimensions[3], float* abs_wall, float lowestOctaveBand, int nOctBands,
+                                float c_ms, float fs);
+void safconv_ims_shoebox_destroy(void** phIms);
+void safconv_ims_shoebox_computeEchograms(void* hIms, int maxN, float maxTime_s);
+void safconv_ims_shoebox_renderRIRs(void* hIms, int fractionalDelaysFLAG);
+void safconv_ims_shoebox_setRoomDimensions(void* hIms, float new_roomDimensions[3]);
+void safconv_ims_shoebox_setWallAbsCoeffs(void* hIms, float* abs_wall);
+int  safconv_ims_shoebox_addSource(void* hIms, float position_xyz[3], float** pSrc_sig);
+int  safconv_ims_shoebox_addReceiverSH(void* hIms, int sh_order, float position_xyz[3], float*** pSH_sigs);
+void safconv_ims_shoebox_updateSource(void* hIms, int sourceID, float position_xyz[3]);
+void safconv_ims_shoebox_updateReceiver(void* hIms, int receiverID, float position_xyz[3]);
+void safconv_ims_shoebox_removeSource(void* hIms, int sourceID);
+void safconv_ims_shoebox_removeReceiver(void* hIms, int receiverID);
+void ims_shoebox_create(void** phIms, float roomDimensions[3], float* abs_wall, float lowestOctaveBand, int nOctBands, float c_ms, float fs);
+void ims_shoebox_destroy(void** phIms);
+void ims_shoebox_computeEchograms(void* hIms, int maxN, float maxTime_s);
+void ims_shoebox_renderRIRs(void* hIms, int fractionalDelaysFLAG);
+void ims_shoebox_setRoomDimensions(void* hIms, float new_roomDimensions[3]);
+void ims_shoebox_setWallAbsCoeffs(void* hIms, float* abs_wall);
+int  ims_shoebox_addSource(void* hIms, float position_xyz[3], float** pSrc_sig);
+int  ims_shoebox_addReceiverSH(void* hIms, int sh_order, float position_xyz[3], float*** pSH_sigs);
+void ims_shoebox_updateSource(void* hIms, int sourceID, float position_xyz[3]);
+void ims_shoebox_updateReceiver(void* hIms, int receiverID, float position_xyz[3]);
+void ims_shoebox_removeSource(void* hIms, int sourceID);
+void ims_shoebox_removeReceiver(void* hIms, int receiverID);
+/**
+ * Accessors (the reference keeps the rendered RIRs inside its handle, ims_scene_data::rirs, without a getter):
+ * the RIR of (receiverID, sourceID), FLAT nChannels x length -- a host copy owned by the handle (valid until the pair
+ * is rendered again or removed) or the device array itself -- and the number of image sources that went into it.
+ */
+int  safconv_ims_get_rir(void* hIms, int receiverID, int sourceID, const float** data, int* length, int* nChannels);
+int  safconv_ims_get_rir_device(void* hIms, int receiverID, int sourceID, const float** d_data, int* length, int* nChannels);
+int  safconv_ims_get_num_images(void* hIms, int receiverID, int sourceID);
+/**
+ * The rendered RIRs of one receiver as a matrix convolver (configs[3] is such a bank): input channel = source (the
+ * active sources in slot order), output channel = SH channel of the receiver, length_h = the longest RIR.  The bank is
+ * assembled and transformed on the device.
+ */
+int  safconv_ims_create_matrixConv(void* hIms, int receiverID, int hopSize, void** const phMC);
+
 /**
  * Offline rendering of a whole signal (BASELINE.json configs[4]): all nFrames blocks are available at once,
  * so the per-bin sum over partitions x inputs becomes a dense contraction that re-uses every filter value

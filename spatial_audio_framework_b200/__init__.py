@@ -26,5 +26,6 @@ from ._capi import (  # noqa: F401
 )
 from . import synth  # noqa: F401
 from . import sharding  # noqa: F401
+from . import producers  # noqa: F401
 
-__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "RFFT", "convolver_rfft", "build", "fftconv", "fftfilt", "rfft_forward", "rfft_backward", "lib", "version", "synth", "sharding"]
+__all__ = ["LIB_PATH", "SafConvError", "MatrixConv", "MultiConv", "TVConv", "RFFT", "convolver_rfft", "build", "fftconv", "fftfilt", "rfft_forward", "rfft_backward", "lib", "version", "synth", "sharding", "producers"]

@@ -209,6 +209,29 @@ int  scdev_multi_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d
 int  scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in, float* d_out,
                     int irIdx, int irLast, int irLast2, void* stream);
 
+
+/* --- filter producers (safconv_producers.cu): binaural Ambisonic decoder design, shoebox image-source RIRs --- */
+/* Y [nSH][nD] = getRSH of the directions d_dirs [nD][2] (azimuth, elevation in degrees) */
+int  scdev_prod_rsh(int order, const float* d_dirs, int nD, float* d_Y, void* stream);
+/* G [nSH][nD] = (Y W Y^T)^-1 Y W; d_aug: double [nSH][2 nSH] scratch, d_flag: 1 if the Gram matrix is singular */
+int  scdev_prod_lsmatrix(const float* d_Y, const float* d_w, int nD, int n, double* d_aug, float* d_G, int* d_flag, void* stream);
+/* D [nB][2][nSH] complex = H [nB][2][nD] complex times G^T; ta: bands >= bc use the HRTFs of band bc */
+int  scdev_prod_ls(const void* d_H, const float* d_G, int nB, int nD, int n, int ta, int bc, void* d_D, void* stream);
+int  scdev_prod_diffeq(const void* d_H, const float* d_Y, const float* d_w, int nB, int nD, int n, void* d_D, void* stream);
+int  scdev_prod_magls(const void* d_H, const float* d_Y, const float* d_G, int nB, int nD, int n, int bc, void* d_D, void* d_hm, void* stream);
+int  scdev_prod_scale(void* d_D, const float* d_a, int n, size_t total, void* stream);
+int  scdev_prod_diffcov(const void* d_H, const float* d_Y, const float* d_w, int nB, int nD, int n, void* d_D, void* stream);
+/* D [nB][rows] -> Dt [rows][nB] (complex) */
+int  scdev_prod_pack(const void* d_D, int nB, int rows, void* d_Dt, void* stream);
+/* image sources: d_pairs = ScpImsPair[nPairs] (safconv_prod_core.cuh); count pass -> d_stats [nPairs][2] = (images, bits of the
+ * largest distance); render pass -> fp64 taps d_acc; finish: fp64 -> fp32; bank: RIRs of one receiver -> [nCh][nSrc][L] */
+int  scdev_ims_count(const void* d_pairs, int nPairs, long long maxLengthVec, unsigned int* d_stats, int smCount, void* stream);
+int  scdev_ims_render(const void* d_pairs, int nPairs, long long maxLengthVec, int maxOrder, const float* d_absTab, int nBands, int maxW,
+                      const float* d_norms, double* d_acc, size_t totalTaps, int smCount, void* stream);
+int  scdev_ims_finish(const double* d_acc, float* d_rir, size_t total, void* stream);
+int  scdev_ims_bank(const float* const* d_rirPtrs, const int* d_len, int nSrc, int nCh, int L, float* d_H, void* stream);
+int  scdev_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

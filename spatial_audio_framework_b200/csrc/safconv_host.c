@@ -22,6 +22,7 @@
 static __thread int  tl_err = 0;
 static __thread char tl_msg[256] = "";
 static __thread int  tl_device = -1;
+static __thread int  tl_filters_on_device = 0;   /* safconv_matrixConv_create_device: `chunks[0]` already is the device-resident bank */
 
 static void set_tl_error(int code, const char* fmt, const char* detail)
 {
@@ -63,6 +64,7 @@ static safconv_handle* as_handle_q(void* p)
     return h;
 }
 int sch_thread_device(void) { return tl_device; }
+void sch_set_thread_device(int device) { tl_device = device; }
 
 /* ------------------------------------------------------------------------------------------ */
 /*  planning                                                                                    */
@@ -504,13 +506,20 @@ static safconv_handle* conv_create(int kind, int hop, const float* const* chunks
     {
         float* d_h = NULL;
         const size_t rowBytes = sizeof(float) * (size_t)len;
-        int e = scdev_malloc((void**)&d_h, rowsTotal * rowBytes);
-        if (e) { h_fail(h, SAFCONV_ERR_NOMEM, "time-domain filter upload buffer", e); goto fail; }
-        for (int c = 0; c < nChunks && !e; c++)
-            e = scdev_memcpy_h2d_sync((char*)d_h + (size_t)c * rowsPerChunk * rowBytes, chunks[c], rowsPerChunk * rowBytes, h->stream);
-        if (!e) e = scdev_filter_transform(pl, &h->b, d_h, h->stream);
-        if (!e) e = scdev_stream_sync(h->stream);
-        scdev_free(d_h);
+        int e = 0;
+        if (tl_filters_on_device) {
+            /* the bank was produced on this device (safconv_producers.c): transform it where it lies */
+            e = scdev_filter_transform(pl, &h->b, chunks[0], h->stream);
+            if (!e) e = scdev_stream_sync(h->stream);
+        } else {
+            e = scdev_malloc((void**)&d_h, rowsTotal * rowBytes);
+            if (e) { h_fail(h, SAFCONV_ERR_NOMEM, "time-domain filter upload buffer", e); goto fail; }
+            for (int c = 0; c < nChunks && !e; c++)
+                e = scdev_memcpy_h2d_sync((char*)d_h + (size_t)c * rowsPerChunk * rowBytes, chunks[c], rowsPerChunk * rowBytes, h->stream);
+            if (!e) e = scdev_filter_transform(pl, &h->b, d_h, h->stream);
+            if (!e) e = scdev_stream_sync(h->stream);
+            scdev_free(d_h);
+        }
         if (e) { h_fail(h, SAFCONV_ERR_CUDA, "filter transform", e); goto fail; }
     }
     return h;
@@ -1041,6 +1050,22 @@ void saf_matrixConv_create(void** const phMC, int hopSize, float* H, int length_
     *phMC = conv_create(SC_KIND_MATRIX, hopSize, H ? &chunk : NULL, 1,
                         (size_t)(nCHout > 0 ? nCHout : 0) * (size_t)(nCHin > 0 ? nCHin : 0),
                         length_h, nCHin, nCHout, nCHout, 0, 0);
+}
+
+void safconv_matrixConv_create_device(void** const phMC, int hopSize, const float* d_H, int length_h, int nCHin, int nCHout)
+{
+    if (!phMC) return;
+    if (hopSize > SC_MAX_M) {
+        set_tl_error(SAFCONV_ERR_ARG, "invalid argument%s: safconv_matrixConv_create_device serves hopSize <= 8192", "");
+        *phMC = NULL;
+        return;
+    }
+    const float* chunk = d_H;
+    tl_filters_on_device = 1;
+    *phMC = conv_create(SC_KIND_MATRIX, hopSize, d_H ? &chunk : NULL, 1,
+                        (size_t)(nCHout > 0 ? nCHout : 0) * (size_t)(nCHin > 0 ? nCHin : 0),
+                        length_h, nCHin, nCHout, nCHout, 0, 0);
+    tl_filters_on_device = 0;
 }
 
 void safconv_matrixConv_create_shard(void** const phMC, int hopSize, const float* H, int length_h,

@@ -112,6 +112,7 @@ SC_HIDDEN void sch_set_tl_error(int code, const char* fmt, const char* detail);
 SC_HIDDEN int  sch_fail(safconv_handle* h, int code, const char* what, int cudaErr);
 SC_HIDDEN int  sch_env_int(const char* name, int dflt, int lo, int hi);
 SC_HIDDEN int  sch_thread_device(void);      /* device chosen with safconv_set_device on this thread, or -1 */
+SC_HIDDEN void sch_set_thread_device(int device);
 SC_HIDDEN safconv_handle* sch_conv_create(int kind, int hop, const float* const* chunks, int nChunks, size_t rowsPerChunk,
                                           int len, int nIn, int nOutLocal, int nOutTotal, int outBegin, int nIRs);
 SC_HIDDEN void sch_handle_free(safconv_handle* h);

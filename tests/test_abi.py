@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def declared_symbols():
     txt = (ROOT / "include" / "safconv_b200.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    names = re.findall(r"\b((?:saf|safconv)_\w+|fftconv|fftfilt)\s*\(", txt)
+    names = re.findall(r"\b((?:saf|safconv|ims_shoebox)_\w+|fftconv|fftfilt|getBinauralAmbiDecoder\w+)\s*\(", txt)
     return sorted(set(names))
 
 
@@ -24,7 +24,8 @@ def test_header_symbols_all_exported(saf):
         assert hasattr(lib, s), f"{s} declared in include/safconv_b200.h but not exported"
     # and the binding's own list agrees with the header
     from spatial_audio_framework_b200._capi import EXPORTED_SYMBOLS
-    assert sorted(EXPORTED_SYMBOLS) == syms
+    from spatial_audio_framework_b200.producers import PRODUCER_SYMBOLS
+    assert sorted(EXPORTED_SYMBOLS + PRODUCER_SYMBOLS) == syms
 
 
 def test_reference_signatures_are_drop_in(saf):
