@@ -624,6 +624,83 @@ def tvconv_latency(args, dev):
     return out
 
 
+def producers_block(args, dev):
+    """secondary block: the filter producers in front of the convolver -- the binaural Ambisonic decoder
+    design (reference saf_hoa.c:452-497) and the shoebox image-source RIR bank (saf_reverb.c:184-295) -- timed through their
+    C-ABI calls (wall clock; every call ends in a stream synchronisation), checked against the numpy fp64 restatement
+    (oracle/producers.py) and timed against the compiled reference on ONE core on a bounded sample of the same work."""
+    import spatial_audio_framework_b200 as saf
+    from spatial_audio_framework_b200 import synth
+    from oracle import producers as PR
+    P = saf.producers
+    saf.lib().safconv_set_device(dev.index)
+    out = {}
+
+    def best(f, n=3):
+        b, r = 1e30, None
+        for _ in range(n):
+            t0 = time.perf_counter(); r = f(); b = min(b, time.perf_counter() - t0)
+        return b, r
+
+    # decoder design: order 7 (64 SH channels -> 2 ears), a KU100-sized grid, 513 bands
+    H, d, itd = synth.synthetic_hrtfs(836, 1024, 48000.0)
+    P.decoder_filters(H, d, 1024, 48000.0, P.DECODER_LS, 1)
+    dec = {"workload": "getBinauralAmbiDecoderFilters: order 7, 836 directions, fftSize 1024 (513 bands)"}
+    for name, m, dc, mr in (("LS", PR.LS, 0, 0), ("MAGLS_diffCM_maxRE", PR.MAGLS, 1, 1)):
+        t, f = best(lambda: P.decoder_filters(H, d, 1024, 48000.0, m, 7, itd, None, dc, mr))
+        truth = PR.np_decoder_filters(H, d, 1024, 48000.0, m, 7, itd, None, dc, mr)
+        ent = {"gpu_ms": 1e3 * t, "parity_rel_l2_vs_fp64": float(np.linalg.norm(f - truth) / np.linalg.norm(truth))}
+        if PR.producers_reference_available():
+            R = PR.load_producers_reference()
+            tr, fr = best(lambda: R.decoder_filters(H, d, 1024, 48000.0, m, 7, itd, None, dc, mr), 1)
+            ent["reference_1_core_ms"] = 1e3 * tr
+            ent["reference_rel_l2_vs_fp64"] = float(np.linalg.norm(fr - truth) / np.linalg.norm(truth))
+        dec[name] = ent
+    out["decoder"] = dec
+
+    # image sources: the 64 x 64 x 96 000 bank of configs[3] = 64 sources, one 7th-order receiver, 2 s at 48 kHz
+    nsrc, order, tmax = 64, 7, 2.0
+    rng = np.random.default_rng(0)
+    s = P.ImsShoebox(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL, 125.0, 7, 343.0, 48e3)
+    pos = [[rng.uniform(0.5, 9.5), rng.uniform(0.5, 6.5), rng.uniform(0.5, 2.5)] for _ in range(nsrc)]
+    sids = [s.add_source(q) for q in pos]
+    rec = [8.8, 5.5, 0.9]
+    rid = s.add_receiver_sh(order, rec)
+    s.compute_echograms(-1, 0.05); s.render_rirs(0)
+    t0 = time.perf_counter()
+    s.compute_echograms(-1, tmax); s.render_rirs(0)
+    t_render = time.perf_counter() - t0
+    images = sum(s.num_images(rid, k) for k in sids)
+    t0 = time.perf_counter()
+    h = s.matrixconv(rid, 1024)
+    t_conv = time.perf_counter() - t0
+    P.destroy_raw(h)
+    # parity on a bounded sample: the first 0.25 s of source 0 against the restatement (same image set -> same taps)
+    s2 = P.ImsShoebox(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL, 125.0, 7, 343.0, 48e3)
+    sid2 = s2.add_source(pos[0]); rid2 = s2.add_receiver_sh(order, rec)
+    s2.compute_echograms(-1, 0.25); s2.render_rirs(0)
+    r2 = s2.rir(rid2, sid2)
+    ref, idx = PR.np_ims_rir(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL, 7, 343.0, 48e3, pos[0], rec, order, -1, 0.25)
+    ims = {"workload": f"ims_shoebox_renderRIRs: {nsrc} sources x one SH receiver of order {order} (64 ch), {tmax} s at 48 kHz "
+                       "(the 64 x 64 x 96000 filter bank of configs[3]), 7 absorption bands, room 10 x 7 x 3 m",
+           "image_sources": int(images), "render_s": t_render, "image_sources_per_s": images / t_render,
+           "tap_updates_per_s": images * 64 / t_render, "bank_to_convolver_s": t_conv,
+           "parity_sample": "source 0, first 0.25 s", "parity_same_image_count": bool(s2.num_images(rid2, sid2) == idx.size),
+           "parity_same_taps": bool(np.array_equal(r2[0] != 0, ref[0] != 0)),
+           "parity_rel_l2": float(np.linalg.norm(r2 - ref) / np.linalg.norm(ref))}
+    s2.destroy(); s.destroy()
+    if PR.producers_reference_available():
+        R = PR.load_producers_reference()
+        rs = R.ims(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL, 125.0, 7, 343.0, 48e3)
+        sidr = rs.add_source(pos[0]); ridr = rs.add_receiver_sh(order, rec)
+        t0 = time.perf_counter(); rs.compute_echograms(-1, 0.4); rs.render_rirs(0); tr = time.perf_counter() - t0
+        nr = int(rs.echogram_times(ridr, sidr).size)
+        rs.destroy()
+        ims["reference_1_core"] = {"sample": "1 source, 0.4 s", "image_sources": nr, "s": tr, "image_sources_per_s": nr / tr}
+    out["ims"] = ims
+    return out
+
+
 def run_own_arm(args, w):
     if w["kind"] == "offline":
         return run_offline_arm(args, w)
@@ -836,6 +913,10 @@ def run_own_arm(args, w):
             secondary["C5"] = measure_offline(a5, WORKLOADS["C5"], 1, 0, local, None)
         except Exception as ex:
             secondary["C5"] = {"failed": repr(ex)}
+        try:
+            secondary["producers"] = producers_block(args, dev)
+        except Exception as ex:
+            secondary["producers"] = {"failed": repr(ex)}
 
     # matrix: per launch group (= one step of B blocks): forward FFT, MAC, inverse FFT, overlap-add chain
     launches_per_step = (4 if B > 1 else 3) * ((B + int(info.maxBatch) - 1) // int(info.maxBatch)) if w["kind"] == "matrix" else B

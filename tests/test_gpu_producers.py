@@ -9,7 +9,7 @@
 Tolerance.  Decoder filters: the north_star bar (max-abs <= 1e-5 of full scale, rel-L2 <= 1e-6) against the fp64 truth;
 against the reference's fp32 LAPACK result the same bar OR "at least as close to the truth as the reference is" (the
 reference itself is up to 1e-6 (MagLS: 2e-5) from the truth).  MagLS chains one fp32 decoder per band into the next
-band's phases, so its own bar against the truth is 5e-6.  Image-source RIRs: tap positions identical, values 1e-6.
+band's phases, so its own bar against the truth is 5e-6.  Image-source RIRs: same image count, same occupied taps, values to the north_star bar (observed: 1e-7 ... 4e-7 rel-L2).
 """
 import ctypes as C
 
@@ -138,7 +138,7 @@ def check_rir(rir, ref, what=""):
     assert rir.shape == ref.shape, f"{what}: shape {rir.shape} vs {ref.shape}"
     assert np.array_equal(rir[0] != 0, ref[0] != 0), f"{what}: different taps are occupied"      # omni channel: all terms positive
     ma, l2 = err_metrics(rir, ref)
-    assert l2 <= TOL_REL_L2 and ma <= 1e-6, f"{what}: {l2:.3g} / {ma:.3g}"
+    assert l2 <= TOL_REL_L2 and ma <= TOL_MAXABS_FS, f"{what}: {l2:.3g} / {ma:.3g}"
 
 
 @pytest.mark.parametrize("names", [False, True])
