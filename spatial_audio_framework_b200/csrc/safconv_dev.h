@@ -229,6 +229,10 @@ int  scdev_ims_count(const void* d_pairs, int nPairs, long long maxLengthVec, un
 int  scdev_ims_render(const void* d_pairs, int nPairs, long long maxLengthVec, int maxOrder, const float* d_absTab, int nBands, int maxW,
                       const float* d_norms, double* d_acc, size_t totalTaps, int smCount, void* stream);
 int  scdev_ims_finish(const double* d_acc, float* d_rir, size_t total, void* stream);
+/* render pass, windowed version: one CTA per (pair, window of pairs[].tw taps), taps in shared memory, fp32 RIRs written
+ * directly to d_rirPtrs[pair]; maxWindows = max ceil(len / tw), accDoubles = max nSH * tw over the pairs */
+int  scdev_ims_render_windows(const void* d_pairs, int nPairs, int maxWindows, int accDoubles, int maxOrder, const float* d_absTab,
+                              int nBands, int maxW, const float* d_norms, float* const* d_rirPtrs, void* stream);
 int  scdev_ims_bank(const float* const* d_rirPtrs, const int* d_len, int nSrc, int nCh, int L, float* d_H, void* stream);
 int  scdev_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
 

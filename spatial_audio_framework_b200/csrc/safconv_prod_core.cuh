@@ -46,7 +46,9 @@ typedef struct ScpImsPair {
     long long lengthVec;    /* (2Nx+1)(2Ny+1)(2Nz+1)                                                                */
     int   order, nSH;       /* receiver SH order / channels                                                          */
     int   len;              /* RIR length in samples (known after the count pass)                                   */
-    long long accOff;       /* offset of this pair's [nSH][len] block in the fp64 accumulator / fp32 RIR arrays     */
+    long long accOff;       /* offset of this pair's [nSH][len] block in the fp64 accumulator (global-atomics render) */
+    int   tw;               /* taps per window of the windowed render (a multiple of 32)                            */
+    int   pad_;
 } ScpImsPair;
 
 /* lattice point q -> reflection orders (i fastest, then j, then k: the order of :304-321 / :431-449) */
@@ -99,6 +101,60 @@ SCP_HD void scp_ims_direction(float sx, float sy, float sz, float* azi, float* i
     *azi = atan2f(sy, sx);
     const float elev = atan2f(sz, SCP_SQRT(SCP_ADD(SCP_MUL(sx, sx), SCP_MUL(sy, sy))));
     *incl = SCP_SUB(3.14159265358979323846264338327950288f / 2.0f, elev);
+}
+
+/* ---- windowed render: which lattice points can land in the taps [w0, w0 + tw) --------------------------------------
+ * tap = (int)(d / c * fs + 0.5f) in fp32, so an image of the window has (w0 - 0.5) c / fs <= d < (w0 + tw - 0.5) c / fs up
+ * to a few fp32 roundings (relative 1e-7; the + 0.5f at 96 000 taps rounds by up to 0.004 taps = 4e-8 of d).  The range
+ * returned here is widened by 1e-5 relative + 1e-4 m: CONSERVATIVE -- every image of the window is inside, a few outside
+ * are too, and the exact tap test of the caller decides. */
+SCP_HD void scp_ims_window_range(const ScpImsPair* p, int w0, int tw, double* dlo, double* dhi)
+{
+    const double k = (double)p->c_ms / (double)p->fs;
+    double lo = ((double)w0 - 0.5) * k, hi = ((double)(w0 + tw) - 0.5) * k;
+    lo = lo * (1.0 - 1e-5) - 1e-4; hi = hi * (1.0 + 1e-5) + 1e-4;
+    *dlo = lo > 0.0 ? lo : 0.0; *dhi = hi;
+}
+
+/* rows (jj, kk) that can hold an image closer than dhi: |jj| <= *jr, |kk| <= *kr (clamped to the lattice) */
+SCP_HD void scp_ims_window_rows(const ScpImsPair* p, double dhi, int* jr, int* kr)
+{
+    const double ey = fabs((double)p->so[1]) + fabs((double)p->ro[1]), ez = fabs((double)p->so[2]) + fabs((double)p->ro[2]);
+    int j = (int)ceil((dhi + ey) / (double)p->room[1]) + 1, k = (int)ceil((dhi + ez) / (double)p->room[2]) + 1;
+    *jr = j < p->Ny ? j : p->Ny; *kr = k < p->Nz ? k : p->Nz;
+}
+
+/* candidates of lattice row (jj, kk) for the distance range [dlo, dhi): up to FOUR inclusive ii ranges of stride 2
+ * (lo[s] > hi[s]: empty), pairwise disjoint, clamped to the lattice -- the even and the odd reflection orders are two
+ * arithmetic progressions in x (x = ii Lx + so.x - ro.x for even ii, ii Lx - so.x - ro.x for odd ii), and the shell cuts
+ * the row in one interval (|x| < xb) or two (xa <= |x| < xb).  Returns the number of ranges written (0, 2 or 4). */
+SCP_HD int scp_ims_row_ranges(const ScpImsPair* p, int jj, int kk, double dlo, double dhi, int lo[4], int hi[4])
+{
+    const float sgy = (jj & 1) ? -1.0f : 1.0f, sgz = (kk & 1) ? -1.0f : 1.0f;
+    const double y = (double)SCP_SUB(SCP_ADD(SCP_MUL((float)jj, p->room[1]), SCP_MUL(sgy, p->so[1])), p->ro[1]);
+    const double z = (double)SCP_SUB(SCP_ADD(SCP_MUL((float)kk, p->room[2]), SCP_MUL(sgz, p->so[2])), p->ro[2]);
+    const double r2 = y * y + z * z;
+    const double hi2 = dhi * dhi - r2;
+    if (!(hi2 > 0.0)) return 0;
+    const double xb = sqrt(hi2) * (1.0 + 1e-7) + 1e-7;
+    const double lo2 = dlo * dlo - r2;
+    double xa = lo2 > 0.0 ? sqrt(lo2) * (1.0 - 1e-7) - 1e-7 : 0.0;
+    if (xa < 1e-3) xa = 0.0;                        /* the two intervals would (nearly) touch: one interval */
+    const double Lx = (double)p->room[0];
+    const int N = p->Nx;
+    int n = 0;
+    for (int par = 0; par < 2; par++) {
+        const double off = (par ? -(double)p->so[0] : (double)p->so[0]) - (double)p->ro[0];
+        for (int side = 0; side < (xa > 0.0 ? 2 : 1); side++) {
+            const double xl = (xa > 0.0) ? (side ? xa : -xb) : -xb, xh = (xa > 0.0) ? (side ? xb : -xa) : xb;
+            int a = (int)ceil((xl - off) / Lx), b = (int)floor((xh - off) / Lx);
+            if (a < -N) a = -N;
+            if (b > N) b = N;
+            if ((a & 1) != par) a++;
+            lo[n] = a; hi[n] = b; n++;
+        }
+    }
+    return n;
 }
 
 /* ---- 2 x 2 diffuse-field covariance matching (fp64) ------------------------------------------------------------ */

@@ -560,10 +560,11 @@ void safconv_ims_shoebox_renderRIRs(void* hIms, int fractionalDelaysFLAG)
 
     ScpImsPair* hp = (ScpImsPair*)calloc((size_t)nP, sizeof *hp);
     unsigned int* stats = (unsigned int*)calloc((size_t)nP * 2, sizeof *stats);
-    void *d_pairs = NULL, *d_stats = NULL;
+    void *d_pairs = NULL, *d_stats = NULL, *d_ptrs = NULL;
     float* d_abs = NULL; float* absTab = NULL;
     double* d_acc = NULL;
-    if (!hp || !stats) { rc = prod_fail(SAFCONV_ERR_NOMEM, "out of host memory", 0); goto done; }
+    float** rirPtrs = (float**)calloc((size_t)nP, sizeof *rirPtrs);
+    if (!hp || !stats || !rirPtrs) { rc = prod_fail(SAFCONV_ERR_NOMEM, "out of host memory", 0); goto done; }
 
     /* lattice (saf_reverb_internal.c:299-303 / :426) */
     int Nx, Ny, Nz; float dmax = 0.0f;
@@ -608,34 +609,59 @@ void safconv_ims_shoebox_renderRIRs(void* hIms, int fractionalDelaysFLAG)
     PROD_TRY(scdev_memcpy_d2h_async(stats, d_stats, sizeof(unsigned int) * 2 * (size_t)nP, s->stream), "image count download");
     PROD_TRY(scdev_stream_sync(s->stream), "image count");
     size_t total = 0;
+    int maxWindows = 0, accDoubles = 0;
     for (int i = 0; i < nP; i++) {
         float dLast; memcpy(&dLast, &stats[2 * i + 1], sizeof dLast);
         if (stats[2 * i] == 0) { rc = prod_fail(SAFCONV_ERR_ARG, "ims_shoebox_renderRIRs: an echogram is empty (maxTime_s shorter than the direct path)", 0); goto done; }
         hp[i].len = scp_ims_length(&hp[i], dLast);
         hp[i].accOff = (long long)total;
         total += (size_t)hp[i].nSH * (size_t)hp[i].len;
+        /* taps per window: the window's fp64 taps of all channels fit in 48 KB of shared memory */
+        int tw = (6144 / hp[i].nSH) & ~31;
+        if (tw < 32) tw = 32;
+        if (tw > 1024) tw = 1024;
+        hp[i].tw = tw;
+        const int nw = (hp[i].len + tw - 1) / tw;
+        if (nw > maxWindows) maxWindows = nw;
+        if (hp[i].nSH * tw > accDoubles) accDoubles = hp[i].nSH * tw;
     }
-    e = scdev_malloc((void**)&d_acc, sizeof(double) * total);
-    if (e) { rc = prod_fail(SAFCONV_ERR_NOMEM, "ims_shoebox_renderRIRs: tap accumulator", e); goto done; }
-    PROD_TRY(scdev_memcpy_h2d_async(d_pairs, hp, sizeof(ScpImsPair) * (size_t)nP, s->stream), "pair upload");
-    /* pass 2: every image source into its taps */
-    PROD_TRY(scdev_ims_render(d_pairs, nP, lengthVec, maxOrder, d_abs, s->nBands, maxW, s->d_norms, d_acc, total, s->smCount, s->stream), "image render");
     for (int i = 0; i < nP; i++) {
         ims_pair* p = &s->pair[idxR[i]][idxS[i]];
-        const size_t cnt = (size_t)hp[i].nSH * (size_t)hp[i].len;
         scdev_free(p->d_rir); p->d_rir = NULL;
         free(p->h_rir); p->h_rir = NULL;
-        e = scdev_malloc((void**)&p->d_rir, sizeof(float) * cnt);
+        e = scdev_malloc((void**)&p->d_rir, sizeof(float) * (size_t)hp[i].nSH * (size_t)hp[i].len);
         if (e) { rc = prod_fail(SAFCONV_ERR_NOMEM, "ims_shoebox_renderRIRs: RIR allocation", e); goto done; }
-        PROD_TRY(scdev_ims_finish(d_acc + hp[i].accOff, p->d_rir, cnt, s->stream), "RIR conversion");
+        rirPtrs[i] = p->d_rir;
+    }
+    PROD_TRY(scdev_memcpy_h2d_async(d_pairs, hp, sizeof(ScpImsPair) * (size_t)nP, s->stream), "pair upload");
+    /* (a lattice row must fit the window kernel's hit queue: 2 Nx + 1 <= 2048 -- rooms narrower than c * maxTime / 1000) */
+    if (sch_env_int("SAFCONV_IMS_WINDOWS", 1, 0, 1) && 2 * Nx + 1 <= 2048) {
+        /* pass 2, windowed: one CTA per (pair, window of taps), taps accumulated in shared memory */
+        e = scdev_malloc(&d_ptrs, sizeof(float*) * (size_t)nP);
+        if (e) { rc = prod_fail(SAFCONV_ERR_NOMEM, "ims_shoebox_renderRIRs: pointer table", e); goto done; }
+        PROD_TRY(scdev_memcpy_h2d_async(d_ptrs, rirPtrs, sizeof(float*) * (size_t)nP, s->stream), "pointer table upload");
+        PROD_TRY(scdev_ims_render_windows(d_pairs, nP, maxWindows, accDoubles, maxOrder, d_abs, s->nBands, maxW, s->d_norms,
+                                          (float* const*)d_ptrs, s->stream), "image render (windows)");
+    } else {
+        /* pass 2, global atomics: every lattice point into fp64 taps in HBM, then fp64 -> fp32 per pair */
+        e = scdev_malloc((void**)&d_acc, sizeof(double) * total);
+        if (e) { rc = prod_fail(SAFCONV_ERR_NOMEM, "ims_shoebox_renderRIRs: tap accumulator", e); goto done; }
+        PROD_TRY(scdev_ims_render(d_pairs, nP, lengthVec, maxOrder, d_abs, s->nBands, maxW, s->d_norms, d_acc, total, s->smCount, s->stream), "image render");
+        for (int i = 0; i < nP; i++)
+            PROD_TRY(scdev_ims_finish(d_acc + hp[i].accOff, rirPtrs[i], (size_t)hp[i].nSH * (size_t)hp[i].len, s->stream), "RIR conversion");
+    }
+    for (int i = 0; i < nP; i++) {
+        ims_pair* p = &s->pair[idxR[i]][idxS[i]];
         p->len = hp[i].len; p->nCh = hp[i].nSH; p->nImages = (int)stats[2 * i];
         p->refreshRIR = 0;
     }
     PROD_TRY(scdev_stream_sync(s->stream), "image render");
 done:
-    free(hp); free(stats); free(absTab);
-    scdev_free(d_pairs); scdev_free(d_stats); scdev_free(d_abs); scdev_free(d_acc);
-    (void)rc;
+    if (rc && rirPtrs)           /* a failed batch leaves no half-rendered RIRs behind */
+        for (int i = 0; i < nP; i++)
+            if (rirPtrs[i]) { ims_pair* p = &s->pair[idxR[i]][idxS[i]]; scdev_free(p->d_rir); p->d_rir = NULL; p->len = 0; }
+    free(hp); free(stats); free(absTab); free(rirPtrs);
+    scdev_free(d_pairs); scdev_free(d_stats); scdev_free(d_abs); scdev_free(d_acc); scdev_free(d_ptrs);
 }
 
 /* ---- accessors (the reference keeps the RIRs inside its handle, ims_scene_data::rirs, without a getter) ---------- */

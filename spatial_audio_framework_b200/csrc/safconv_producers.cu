@@ -305,13 +305,33 @@ __global__ void ims_count_kernel(ImsArgs a)
     if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(&a.stats[2 * blockIdx.y], cnt); atomicMax(&a.stats[2 * blockIdx.y + 1], dmaxBits); }
 }
 
-/* pass 2: every image source straight into the RIR taps.  grid (x, nPairs) */
+/* one image source -> its nSH tap contributions: wall absorption (saf_reverb_internal.c:589-633: product over the three
+ * axes per band, summed over the bands -- renderRIR adds the band RIRs without filtering them, :697-702), direction, SH
+ * encoding (:556-569); add(ch, value) receives them */
+template <int NMAX, class Add>
+__device__ __forceinline__ void ims_image_to_taps(const ScpImsPair& p, const ImsArgs& a, int ii, int jj, int kk,
+                                                  float sx, float sy, float sz, float att, Add add)
+{
+    const float* tx = a.absTab, *ty = a.absTab + (size_t)a.nBands * a.maxW, *tz = a.absTab + 2 * (size_t)a.nBands * a.maxW;
+    double tot = 0.0;
+    for (int b = 0; b < a.nBands; b++)
+        tot += (double)(tx[b * a.maxW + ii + p.Nx] * ty[b * a.maxW + jj + p.Ny] * tz[b * a.maxW + kk + p.Nz]);
+    if (p.order == 0) { add(0, (double)att * tot); return; }
+    float azi, incl;
+    scp_ims_direction(sx, sy, sz, &azi, &incl);
+    float Yv[(NMAX + 1) * (NMAX + 1)];
+    scsh_shreal_recur_dir<NMAX>(p.order, azi, incl, a.norms, Yv);
+#pragma unroll
+    for (int ch = 0; ch < (NMAX + 1) * (NMAX + 1); ch++)
+        if (ch < p.nSH) add(ch, (double)(Yv[ch] * att) * tot);
+}
+
+/* pass 2, global-atomics version: every lattice point straight into the fp64 taps in HBM.  grid (x, nPairs) */
 template <int NMAX>
 __global__ void __launch_bounds__(128) ims_render_kernel(ImsArgs a)
 {
     const ScpImsPair p = a.pairs[blockIdx.y];
     double* acc = a.acc + p.accOff;
-    const float* tx = a.absTab, *ty = a.absTab + (size_t)a.nBands * a.maxW, *tz = a.absTab + 2 * (size_t)a.nBands * a.maxW;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < p.lengthVec; q += (long long)gridDim.x * blockDim.x) {
         int ii, jj, kk; float sx, sy, sz, d;
         scp_ims_lattice(&p, q, &ii, &jj, &kk);
@@ -319,19 +339,78 @@ __global__ void __launch_bounds__(128) ims_render_kernel(ImsArgs a)
         float time, att;
         const int tap = scp_ims_tap(&p, d, &time, &att);
         if (tap < 0 || tap >= p.len) continue;
-        /* wall absorption (saf_reverb_internal.c:589-633): product over the three axes per band, summed over the bands
-         * (renderRIR adds the band RIRs without filtering them, :697-702) */
-        double tot = 0.0;
-        for (int b = 0; b < a.nBands; b++)
-            tot += (double)(tx[b * a.maxW + ii + p.Nx] * ty[b * a.maxW + jj + p.Ny] * tz[b * a.maxW + kk + p.Nz]);
-        if (p.order == 0) { atomicAdd(&acc[tap], (double)att * tot); continue; }
-        float azi, incl;
-        scp_ims_direction(sx, sy, sz, &azi, &incl);
-        float Yv[(NMAX + 1) * (NMAX + 1)];
-        scsh_shreal_recur_dir<NMAX>(p.order, azi, incl, a.norms, Yv);
+        ims_image_to_taps<NMAX>(p, a, ii, jj, kk, sx, sy, sz, att,
+                                [&](int ch, double v) { atomicAdd(&acc[(size_t)ch * p.len + tap], v); });
+    }
+}
+
+/* pass 2, windowed version: one CTA owns the taps [w0, w0 + tw) of one pair.  It intersects the lattice rows with the
+ * window's spherical shell (scp_ims_row_ranges: a handful of candidates per row instead of a scan of the whole lattice),
+ * decides every candidate with the exact fp32 geometry, queues the hits in shared memory so that the expensive part --
+ * SH encoding, one thread per image -- runs with full warps, accumulates the taps in SHARED memory (fp64 atomics that
+ * never leave the SM) and writes its window of the fp32 RIR once: no atomics in HBM, no fp64 accumulator array, no
+ * conversion pass, no memset.  grid (windows, nPairs); dynamic shared memory: double [nSH][tw] + long long [qcap]. */
+#define IMS_ROWS_PER_ROUND 8192
+template <int NMAX>
+__global__ void __launch_bounds__(128) ims_window_kernel(ImsArgs a, float* const* __restrict__ rirPtrs, int accDoubles, int qcap)
+{
+    extern __shared__ __align__(16) unsigned char ims_smem[];
+    __shared__ int qn;
+    const ScpImsPair p = a.pairs[blockIdx.y];
+    const int tw = p.tw, w0 = blockIdx.x * tw;
+    if (w0 >= p.len) return;
+    double* sacc = reinterpret_cast<double*>(ims_smem);
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(sacc + accDoubles);
+    const int nAcc = p.nSH * tw;
+    for (int e = threadIdx.x; e < nAcc; e += blockDim.x) sacc[e] = 0.0;
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+    double dlo, dhi; int jr, kr;
+    scp_ims_window_range(&p, w0, tw, &dlo, &dhi);
+    scp_ims_window_rows(&p, dhi, &jr, &kr);
+    const int wj = 2 * jr + 1, nRows = wj * (2 * kr + 1);
+    /* rounds of `rows` lattice rows: enumerate into the queue, then drain it with full warps.  A round whose hits do not
+     * fit the queue is enumerated again with half the rows (uniform decision, nothing was processed yet); one row never
+     * has more than 2 Nx + 1 <= qcap hits (the host layer checks that before choosing this kernel). */
+    int rows = IMS_ROWS_PER_ROUND;
+    for (int base = 0; base < nRows;) {
+        const int end = min(nRows, base + rows);
+        for (int r = base + threadIdx.x; r < end; r += blockDim.x) {
+            const int jj = r % wj - jr, kk = r / wj - kr;
+            int lo[4], hi[4];
+            const int nr = scp_ims_row_ranges(&p, jj, kk, dlo, dhi, lo, hi);
 #pragma unroll
-        for (int ch = 0; ch < (NMAX + 1) * (NMAX + 1); ch++)
-            if (ch < p.nSH) atomicAdd(&acc[(size_t)ch * p.len + tap], (double)(Yv[ch] * att) * tot);
+            for (int s = 0; s < 4; s++)
+                for (int ii = (s < nr) ? lo[s] : 1; ii <= ((s < nr) ? hi[s] : 0); ii += 2) {
+                    float sx, sy, sz, d, time, att;
+                    if (!scp_ims_image(&p, ii, jj, kk, &sx, &sy, &sz, &d)) continue;
+                    const int tap = scp_ims_tap(&p, d, &time, &att);
+                    if (tap < w0 || tap >= w0 + tw || tap >= p.len) continue;
+                    const int slot = atomicAdd(&qn, 1);
+                    if (slot < qcap) queue[slot] = ((unsigned long long)(kk + p.Nz) << 42) | ((unsigned long long)(jj + p.Ny) << 21) | (unsigned long long)(ii + p.Nx);
+                }
+        }
+        __syncthreads();
+        const int n = qn;
+        __syncthreads();
+        if (threadIdx.x == 0) qn = 0;
+        if (n > qcap && rows > 1) { rows >>= 1; __syncthreads(); continue; }       /* too many hits: same rows again, half as many */
+        for (int e = threadIdx.x; e < min(n, qcap); e += blockDim.x) {
+            const unsigned long long v = queue[e];
+            const int ii = (int)(v & 0x1fffffu) - p.Nx, jj = (int)((v >> 21) & 0x1fffffu) - p.Ny, kk = (int)(v >> 42) - p.Nz;
+            float sx, sy, sz, d, time, att;
+            scp_ims_image(&p, ii, jj, kk, &sx, &sy, &sz, &d);
+            const int t = scp_ims_tap(&p, d, &time, &att) - w0;
+            ims_image_to_taps<NMAX>(p, a, ii, jj, kk, sx, sy, sz, att, [&](int ch, double v2) { atomicAdd(&sacc[ch * tw + t], v2); });
+        }
+        __syncthreads();
+        base = end;
+        if (rows < IMS_ROWS_PER_ROUND && 4 * n < qcap) rows <<= 1;
+    }
+    float* rir = rirPtrs[blockIdx.y];
+    for (int e = threadIdx.x; e < nAcc; e += blockDim.x) {
+        const int ch = e / tw, t = e - ch * tw;
+        if (w0 + t < p.len) rir[(size_t)ch * p.len + w0 + t] = (float)sacc[e];
     }
 }
 
@@ -442,6 +521,30 @@ int scdev_ims_render(const void* d_pairs, int nPairs, long long maxLengthVec, in
     if (maxOrder <= 3)      ims_render_kernel<3><<<grid, 128, 0, st>>>(a);
     else if (maxOrder <= 7) ims_render_kernel<7><<<grid, 128, 0, st>>>(a);
     else                    ims_render_kernel<SCSH_MAX_ORDER><<<grid, 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+/* windowed render: d_rirPtrs[pair] = that pair's fp32 RIR [nSH][len]; maxWindows = max over pairs of ceil(len / tw);
+ * accDoubles = max over pairs of nSH * tw */
+int scdev_ims_render_windows(const void* d_pairs, int nPairs, int maxWindows, int accDoubles, int maxOrder, const float* d_absTab,
+                             int nBands, int maxW, const float* d_norms, float* const* d_rirPtrs, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ImsArgs a = {};
+    a.pairs = (const ScpImsPair*)d_pairs; a.absTab = d_absTab; a.nBands = nBands; a.maxW = maxW; a.norms = d_norms;
+    const int qcap = 2048;
+    const size_t smem = sizeof(double) * (size_t)accDoubles + sizeof(unsigned long long) * qcap;
+    const dim3 grid(maxWindows, nPairs);
+    if (maxOrder <= 3) {
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(ims_window_kernel<3>));
+        ims_window_kernel<3><<<grid, 128, smem, st>>>(a, d_rirPtrs, accDoubles, qcap);
+    } else if (maxOrder <= 7) {
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(ims_window_kernel<7>));
+        ims_window_kernel<7><<<grid, 128, smem, st>>>(a, d_rirPtrs, accDoubles, qcap);
+    } else {
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(ims_window_kernel<SCSH_MAX_ORDER>));
+        ims_window_kernel<SCSH_MAX_ORDER><<<grid, 128, smem, st>>>(a, d_rirPtrs, accDoubles, qcap);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "../../spatial_audio_framework_b200/csrc/safconv_sh.cuh"
 #include "../../spatial_audio_framework_b200/csrc/safconv_prod_core.cuh"
 
@@ -87,6 +88,56 @@ int ph_ims_pair(ScpImsPair* pair, const float* absTab, int nBands, int maxW, flo
     for (size_t e = 0; e < acc.size(); e++) rir[e] = (float)acc[e];
     *nImages = n;
     return p.len;
+}
+
+/* The windowed render (ims_window_kernel), one "CTA" after the other: every window of pair->tw taps enumerates its
+ * candidates with scp_ims_window_range / _rows / scp_ims_row_ranges, decides them with the exact geometry and adds them to
+ * its own taps.  Returns the number of images processed over all windows (must equal the count pass: every image is
+ * found by exactly one window); candidates = lattice points the windows looked at (efficiency of the enumeration). */
+long long ph_ims_pair_windows(const ScpImsPair* pair, const float* absTab, int nBands, int maxW, float* rir, long long* candidates)
+{
+    const ScpImsPair p = *pair;
+    float c[SCSH_MAX_ORDER + 1][SCSH_MAX_ORDER + 1];
+    scsh_recur_norms(SCSH_MAX_ORDER, c);
+    const float *tx = absTab, *ty = absTab + (size_t)nBands * maxW, *tz = absTab + 2 * (size_t)nBands * maxW;
+    long long nImg = 0, nCand = 0;
+    const int tw = p.tw;
+    std::vector<double> sacc((size_t)p.nSH * tw);
+    for (int w0 = 0; w0 < p.len; w0 += tw) {
+        std::fill(sacc.begin(), sacc.end(), 0.0);
+        double dlo, dhi; int jr, kr;
+        scp_ims_window_range(&p, w0, tw, &dlo, &dhi);
+        scp_ims_window_rows(&p, dhi, &jr, &kr);
+        const int wj = 2 * jr + 1, nRows = wj * (2 * kr + 1);
+        for (int r = 0; r < nRows; r++) {
+            const int jj = r % wj - jr, kk = r / wj - kr;
+            int lo[4], hi[4];
+            const int nr = scp_ims_row_ranges(&p, jj, kk, dlo, dhi, lo, hi);
+            for (int s = 0; s < nr; s++)
+                for (int ii = lo[s]; ii <= hi[s]; ii += 2) {
+                    nCand++;
+                    float sx, sy, sz, d, time, att;
+                    if (!scp_ims_image(&p, ii, jj, kk, &sx, &sy, &sz, &d)) continue;
+                    const int tap = scp_ims_tap(&p, d, &time, &att);
+                    if (tap < w0 || tap >= w0 + tw || tap >= p.len) continue;
+                    nImg++;
+                    const int t = tap - w0;
+                    double tot = 0.0;
+                    for (int b = 0; b < nBands; b++) tot += (double)(tx[b * maxW + ii + p.Nx] * ty[b * maxW + jj + p.Ny] * tz[b * maxW + kk + p.Nz]);
+                    if (p.order == 0) { sacc[t] += (double)att * tot; continue; }
+                    float azi, incl, Yv[(SCSH_MAX_ORDER + 1) * (SCSH_MAX_ORDER + 1)];
+                    scp_ims_direction(sx, sy, sz, &azi, &incl);
+                    if (p.order <= 3)      scsh_shreal_recur_dir<3>(p.order, azi, incl, &c[0][0], Yv);
+                    else if (p.order <= 7) scsh_shreal_recur_dir<7>(p.order, azi, incl, &c[0][0], Yv);
+                    else                   scsh_shreal_recur_dir<SCSH_MAX_ORDER>(p.order, azi, incl, &c[0][0], Yv);
+                    for (int ch = 0; ch < p.nSH; ch++) sacc[(size_t)ch * tw + t] += (double)(Yv[ch] * att) * tot;
+                }
+        }
+        for (int ch = 0; ch < p.nSH; ch++)
+            for (int t = 0; t < tw && w0 + t < p.len; t++) rir[(size_t)ch * p.len + w0 + t] = (float)sacc[(size_t)ch * tw + t];
+    }
+    if (candidates) *candidates = nCand;
+    return nImg;
 }
 
 int ph_sizeof_pair(void) { return (int)sizeof(ScpImsPair); }

@@ -141,9 +141,17 @@ def check_rir(rir, ref, what=""):
     assert l2 <= TOL_REL_L2 and ma <= TOL_MAXABS_FS, f"{what}: {l2:.3g} / {ma:.3g}"
 
 
+@pytest.fixture(params=["windows", "global_atomics"])
+def render_path(request, monkeypatch):
+    """both render kernels: ims_window_kernel (default: taps of a window in shared memory) and ims_render_kernel (lattice
+    scan with fp64 atomics in HBM, SAFCONV_IMS_WINDOWS=0)"""
+    monkeypatch.setenv("SAFCONV_IMS_WINDOWS", "1" if request.param == "windows" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("names", [False, True])
 @pytest.mark.parametrize("name", sorted(IMS_CASES))
-def test_ims_rir_vs_reference_golden(saf, name, names):
+def test_ims_rir_vs_reference_golden(saf, name, names, render_path):
     g = gold("ims")
     order, maxN, maxT, nB, src, rec = IMS_CASES[name]
     s = saf.producers.ImsShoebox(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL[:nB], 125.0, nB, 343.0, 48e3, reference_names=names)
@@ -169,7 +177,7 @@ def test_ims_reference_unit_test_sequence(saf):
         check_rir(r, g[f"ut_rir_r{rid}_s{sid}"], f"unit test r{rid} s{sid}")
 
 
-def test_ims_many_pairs_one_batch_and_refresh_rules(saf):
+def test_ims_many_pairs_one_batch_and_refresh_rules(saf, render_path):
     """2 receivers (orders 1 and 4) x 3 sources rendered by one renderRIRs call; then the refresh rules of
     saf_reverb.c:184-257 in order-limited mode: only what changed is rendered again"""
     room, aw = [6.0, 5.0, 2.8], synth.IMS_TEST_ABS_WALL[:5]
@@ -212,7 +220,7 @@ def test_ims_many_pairs_one_batch_and_refresh_rules(saf):
     s.destroy()
 
 
-def test_ims_broadband_and_order_10(saf):
+def test_ims_broadband_and_order_10(saf, render_path):
     """nBands = 1 (the reference's own renderRIRs crashes there) and the largest receiver order, vs the restatement"""
     room, aw = [7.0, 4.0, 3.5], synth.IMS_TEST_ABS_WALL[3:4]
     s = saf.producers.ImsShoebox(room, aw, 125.0, 1, 343.0, 44100.0)
@@ -223,7 +231,7 @@ def test_ims_broadband_and_order_10(saf):
     s.destroy()
 
 
-def test_ims_long_response_properties_and_checksum(saf):
+def test_ims_long_response_properties_and_checksum(saf, render_path):
     """A 1 s response (1.7 M lattice points, ~0.9 M image sources, 48 001 taps, 16 channels): tap positions from an
     independent numpy pass over the lattice, the omni channel's checksum, silence before the direct sound."""
     room, nB = synth.IMS_TEST_ROOM, 7
@@ -241,6 +249,26 @@ def test_ims_long_response_properties_and_checksum(saf):
     assert abs(rir[0].astype(np.float64).sum() - ref[0].sum()) <= 1e-6 * ref[0].sum()
     check_rir(rir, ref, "1 s response")
     s.destroy()
+
+
+def test_ims_both_render_kernels_agree_on_a_full_length_bank(saf, monkeypatch):
+    """4 sources x a 7th-order receiver x 2 s (configs[3]'s filter length: 96 001 taps, 64 channels, 25.8 M image sources):
+    the windowed kernel and the lattice-scan kernel find the same images and agree to fp32 rounding of the same fp64 sums"""
+    rng = np.random.default_rng(0)
+    pos = [[rng.uniform(0.5, 9.5), rng.uniform(0.5, 6.5), rng.uniform(0.5, 2.5)] for _ in range(4)]
+    out = {}
+    for path in ("1", "0"):
+        monkeypatch.setenv("SAFCONV_IMS_WINDOWS", path)
+        s = saf.producers.ImsShoebox(synth.IMS_TEST_ROOM, synth.IMS_TEST_ABS_WALL, 125.0, 7, 343.0, 48e3)
+        sids = [s.add_source(q) for q in pos]
+        rid = s.add_receiver_sh(7, [8.8, 5.5, 0.9])
+        s.compute_echograms(-1, 2.0); s.render_rirs(0)
+        out[path] = ([s.num_images(rid, k) for k in sids], [s.rir(rid, k) for k in sids])
+        s.destroy()
+    assert out["1"][0] == out["0"][0] and sum(out["1"][0]) > 25_000_000
+    for a, b in zip(out["1"][1], out["0"][1]):
+        assert a.shape == b.shape == (64, 96001)
+        assert np.allclose(a, b, rtol=3e-7, atol=0) and (a == b).mean() > 0.99
 
 
 def test_ims_straight_into_a_convolver(saf, orc):

@@ -130,7 +130,8 @@ class ScpImsPair(C.Structure):      # csrc/safconv_prod_core.cuh
     _fields_ = [("room", C.c_float * 3), ("so", C.c_float * 3), ("ro", C.c_float * 3),
                 ("c_ms", C.c_float), ("fs", C.c_float), ("dmax", C.c_float), ("mode", C.c_int),
                 ("Nx", C.c_int), ("Ny", C.c_int), ("Nz", C.c_int), ("lengthVec", C.c_longlong),
-                ("order", C.c_int), ("nSH", C.c_int), ("len", C.c_int), ("accOff", C.c_longlong)]
+                ("order", C.c_int), ("nSH", C.c_int), ("len", C.c_int), ("accOff", C.c_longlong),
+                ("tw", C.c_int), ("pad_", C.c_int)]
 
 
 @pytest.fixture(scope="module")
@@ -150,6 +151,8 @@ def host_lib():
     L.ph_legendre.argtypes = [C.c_int, C.c_double]; L.ph_legendre.restype = C.c_double
     L.ph_diffcov_M.argtypes = [dp, dp, dp]
     L.ph_ims_pair.argtypes = [C.POINTER(ScpImsPair), fp, C.c_int, C.c_int, fp, ip, ip]
+    L.ph_ims_pair_windows.argtypes = [C.POINTER(ScpImsPair), fp, C.c_int, C.c_int, fp, C.POINTER(C.c_longlong)]
+    L.ph_ims_pair_windows.restype = C.c_longlong
     assert L.ph_sizeof_pair() == C.sizeof(ScpImsPair)
     return L
 
@@ -280,6 +283,44 @@ def test_device_ims_pair_vs_reference_golden(host_lib, name):
     ma, l2 = err_metrics(rir, ref)
     assert l2 < 1e-6 and ma < 1e-6, (ma, l2)
     assert np.array_equal(rir[0] != 0, ref[0] != 0)              # omni channel: all terms positive
+
+
+def window_taps(nSH):
+    """the host layer's choice of taps per window (safconv_producers.c)"""
+    return max(32, min(1024, (6144 // nSH) & ~31))
+
+
+WINDOW_CASES = dict(IMS_CASES)
+WINDOW_CASES.update({
+    "t_o2_long": (2, -1, 0.45, 7, [5.1, 6.0, 1.1], [8.8, 5.5, 0.9]),          # 73 000 images, 21 601 taps
+    "t_o10": (10, -1, 0.05, 3, [1.0, 1.5, 1.2], [5.5, 2.5, 1.8]),             # 32-tap windows
+    "t_close": (1, -1, 0.03, 2, [5.0, 3.5, 1.5], [5.0, 3.5, 1.5]),            # source ON the receiver: d = 0 image, symmetric rows
+    "t_wall": (3, -1, 0.07, 7, [0.0, 0.0, 0.0], [10.0, 7.0, 3.0]),            # source and receiver in opposite corners (coincident images)
+    "n_o1_big": (1, 9, -1.0, 4, [2.2, 6.1, 0.3], [7.7, 0.9, 2.6]),            # order-limited lattice, 1 500 images
+})
+
+
+@pytest.mark.parametrize("name", sorted(WINDOW_CASES))
+def test_device_ims_windowed_render_equals_lattice_scan(host_lib, name):
+    """the windowed render (one CTA per window of taps, candidates from the window's spherical shell) finds exactly the
+    images of the full lattice scan, each once, and produces the same RIR"""
+    order, maxN, maxT, nB, src, rec = WINDOW_CASES[name]
+    p = host_pair(synth.IMS_TEST_ROOM, 343.0, 48e3, src, rec, order, maxN, maxT)
+    tab, maxW = wall_tables(synth.IMS_TEST_ABS_WALL[:nB], (p.Nx, p.Ny, p.Nz))
+    n = C.c_int()
+    length = host_lib.ph_ims_pair(C.byref(p), _fp(tab), nB, maxW, None, C.byref(n), None)
+    scan = np.zeros((p.nSH, length), np.float32)
+    host_lib.ph_ims_pair(C.byref(p), _fp(tab), nB, maxW, _fp(scan), C.byref(n), None)
+    p.tw = window_taps(p.nSH)
+    win = np.full((p.nSH, length), np.nan, np.float32)
+    cand = C.c_longlong()
+    found = host_lib.ph_ims_pair_windows(C.byref(p), _fp(tab), nB, maxW, _fp(win), C.byref(cand))
+    assert found == n.value, (found, n.value)                                  # every image, exactly once
+    assert not np.isnan(win).any()                                             # every tap of every window written
+    # the same fp64 sums in a different order: equal to fp32 rounding of the fp64 result (almost always bit-equal)
+    assert np.allclose(win, scan, rtol=3e-7, atol=0) and (win == scan).mean() > 0.999
+    assert p.lengthVec >= found
+    print(name, "images", found, "candidates looked at", cand.value, "lattice", p.lengthVec)
 
 
 def test_device_ims_broadband_vs_restatement(host_lib):
