@@ -25,6 +25,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "safconv_dev.h"
 #include "safconv_fft.cuh"
 #include "safconv_sh.cuh"
@@ -207,6 +209,89 @@ __global__ void prod_magls_kernel(const float2* __restrict__ H, const float* __r
         }
         __syncthreads();
     }
+}
+
+/* MagLS recurrence on a thread-block CLUSTER: the directions are cut into one slice per CTA; every CTA keeps its slice of
+ * Y and G in SHARED memory for the whole walk over the bands (the single-CTA kernel re-reads both from L2 for every band:
+ * 27 us per band), computes per band (A) the target responses of its directions from the previous band's decoder and
+ * (B) its slice's contribution to the new decoder, and hands the 2 nSH partial sums to ALL CTAs through distributed
+ * shared memory (st.shared::cluster); after one cluster barrier per band every CTA adds the C partials in rank order --
+ * the same fp64 sum in every CTA, so all of them hold the same new decoder and go on.  The partial buffers are
+ * double-buffered by band parity (a CTA can be at most one barrier ahead).  grid = one cluster of C CTAs. */
+struct MaglsArgs { const float2* H; const float* Y; const float* G; float2* D; int nB, nD, n, bc, S; };
+
+__device__ __forceinline__ uint32_t pcl_ctarank()  { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t pcl_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pcl_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pcl_store_d2(const void* localSmem, uint32_t rank, double x, double y)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(localSmem)), "r"(rank));
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" :: "r"(remote), "d"(x), "d"(y) : "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1) prod_magls_cluster_kernel(MaglsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char msm[];
+    const int C = (int)pcl_nctarank(), rank = (int)pcl_ctarank();
+    const int n = a.n, S = a.S, nD = a.nD, d0 = rank * S;
+    const int ns = max(0, min(nD, d0 + S) - d0);
+    double2* part = reinterpret_cast<double2*>(msm);                 /* [2][C][2 n] */
+    float2*  sD   = reinterpret_cast<float2*>(part + 2 * C * 2 * n); /* [2 n]       */
+    float2*  hm   = sD + 2 * n;                                      /* [2][S]      */
+    float*   Ys   = reinterpret_cast<float*>(hm + 2 * S);            /* [n][S]      */
+    float*   Gs   = Ys + (size_t)n * S;                              /* [n][S]      */
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < n * S; e += blockDim.x) {
+        const int i = e / S, dl = e - i * S;
+        const bool in = dl < ns;
+        Ys[e] = in ? a.Y[(size_t)i * nD + d0 + dl] : 0.0f;
+        Gs[e] = in ? a.G[(size_t)i * nD + d0 + dl] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) sD[e] = a.D[(size_t)a.bc * 2 * n + e];
+    __syncthreads();
+    pcl_sync();                                  /* every CTA of the cluster is running: its shared memory may be written */
+    const int t = threadIdx.x;
+    const bool act = t < 2 * ns;
+    const int ear = act ? t / ns : 0, dl = act ? t - ear * ns : 0;
+    float2 hcur = (act && a.bc + 1 < a.nB) ? a.H[((size_t)(a.bc + 1) * 2 + ear) * nD + d0 + dl] : make_float2(0.f, 0.f);
+    for (int band = a.bc + 1; band < a.nB; band++) {
+        /* the next band's HRTF magnitudes are requested now and used one band later */
+        const float2 hnext = (act && band + 1 < a.nB) ? a.H[((size_t)(band + 1) * 2 + ear) * nD + d0 + dl] : make_float2(0.f, 0.f);
+        if (act) {
+            double re = 0.0, im = 0.0;
+            const float2* dd = sD + ear * n;
+            for (int i = 0; i < n; i++) { const double y = (double)Ys[i * S + dl]; re += y * dd[i].x; im += y * dd[i].y; }
+            const double mag = sqrt((double)hcur.x * hcur.x + (double)hcur.y * hcur.y);
+            const double nr = sqrt(re * re + im * im);
+            hm[ear * S + dl] = (nr > 0.0) ? make_float2((float)(mag * re / nr), (float)(mag * im / nr)) : make_float2((float)mag, 0.0f);
+        }
+        __syncthreads();
+        const int buf = band & 1;
+        for (int o = w; o < 2 * n; o += nw) {
+            const int eo = o / n, i = o - eo * n;
+            const float* g = Gs + (size_t)i * S;
+            const float2* hh = hm + eo * S;
+            double re = 0.0, im = 0.0;
+            for (int d = lane; d < ns; d += 32) { const float2 hv = hh[d]; const double gv = (double)g[d]; re += gv * (double)hv.x; im += gv * (double)hv.y; }
+            re = warp_sum(re); im = warp_sum(im);
+            if (lane < C) pcl_store_d2(&part[((size_t)buf * C + rank) * 2 * n + o], (uint32_t)lane, re, im);
+        }
+        pcl_sync();
+        for (int o = threadIdx.x; o < 2 * n; o += blockDim.x) {
+            double re = 0.0, im = 0.0;
+            for (int r = 0; r < C; r++) { const double2 v = part[((size_t)buf * C + r) * 2 * n + o]; re += v.x; im += v.y; }
+            const float2 res = make_float2((float)re, (float)im);
+            sD[o] = res;
+            if (rank == 0) a.D[(size_t)band * 2 * n + o] = res;
+        }
+        __syncthreads();
+        hcur = hnext;
+    }
+    pcl_sync();                                  /* no CTA leaves while a neighbour could still write into it */
 }
 
 /* max-rE weighting (saf_hoa.c:427-445): D[band][ear][i] *= a[i] */
@@ -469,6 +554,23 @@ int scdev_prod_diffeq(const void* d_H, const float* d_Y, const float* d_w, int n
 int scdev_prod_magls(const void* d_H, const float* d_Y, const float* d_G, int nB, int nD, int n, int bc, void* d_D, void* d_hm, void* stream)
 {
     if (bc + 1 >= nB) return 0;
+    /* cluster version: 8 CTAs, each with its direction slice of Y and G in shared memory (needs 2 S <= 1024 threads' worth of
+     * directions per CTA and the slices + partial buffers within the opt-in shared memory); else one CTA streaming from L2 */
+    const int C = 8, S = (nD + C - 1) / C;
+    const size_t smem = sizeof(double) * 2 * ((size_t)2 * C * 2 * n) + sizeof(float) * 2 * ((size_t)2 * n + 2 * S) + sizeof(float) * 2 * (size_t)n * S;
+    const char* env = getenv("SAFCONV_MAGLS_CLUSTER");
+    if (!(env && env[0] == '0') && 2 * S <= 1024 && smem <= 222 * 1024) {
+        MaglsArgs a = { (const float2*)d_H, d_Y, d_G, (float2*)d_D, nB, nD, n, bc, S };
+        if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(prod_magls_cluster_kernel));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(2 * S <= 512 ? 512 : 1024); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, prod_magls_cluster_kernel, a);
+    }
     prod_magls_kernel<<<1, 1024, 2 * n * sizeof(float2), (cudaStream_t)stream>>>((const float2*)d_H, d_Y, d_G, nB, nD, n, bc, (float2*)d_D, (float2*)d_hm);
     return (int)cudaGetLastError();
 }

@@ -83,6 +83,21 @@ def test_decoder_filters_vs_truth_other_shapes(saf, order, nD, fftSize, m, dc, m
         check_decoder(mine, ref, truth, m == PR.MAGLS, "live reference")
 
 
+@pytest.mark.parametrize("order,nD,fftSize", [(7, 836, 1024), (3, 146, 128), (10, 1202, 256), (1, 12, 64), (5, 2702, 512)])
+def test_magls_cluster_kernel_vs_single_cta_kernel(saf, monkeypatch, order, nD, fftSize):
+    """the MagLS band recurrence on a thread-block cluster (direction slices of Y / G in the shared memory of 8 CTAs, partial
+    decoders exchanged through distributed shared memory) against the one-CTA kernel and the fp64 truth"""
+    H, d, itd = synth.synthetic_hrtfs(nD, fftSize, 48000.0, seed=nD)
+    monkeypatch.setenv("SAFCONV_MAGLS_CLUSTER", "1")
+    a = saf.producers.decoder_filters(H, d, fftSize, 48000.0, PR.MAGLS, order, itd)
+    monkeypatch.setenv("SAFCONV_MAGLS_CLUSTER", "0")
+    b = saf.producers.decoder_filters(H, d, fftSize, 48000.0, PR.MAGLS, order, itd)
+    truth = PR.np_decoder_filters(H, d, fftSize, 48000.0, PR.MAGLS, order, itd)
+    (ma_a, l2_a), (ma_b, l2_b), (ma_ab, l2_ab) = err_metrics(a, truth), err_metrics(b, truth), err_metrics(a, b)
+    print(f"order {order} nD {nD} fft {fftSize}: cluster {l2_a:.2e}, one CTA {l2_b:.2e} from truth; cluster vs one CTA {l2_ab:.2e}")
+    assert l2_a <= 5e-6 and l2_b <= 5e-6 and l2_ab <= 5e-6
+
+
 def test_decoder_mtx_arbitrary_bands(saf):
     """getBinauralAmbiDecoderMtx with a caller-supplied band grid (the hybrid-filterbank use of ambi_bin.c:284-305)"""
     H, d, itd = synth.synthetic_hrtfs(300, 264, 48000.0, seed=5)          # 133 "bands"
