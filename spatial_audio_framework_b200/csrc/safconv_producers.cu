@@ -434,18 +434,18 @@ __global__ void __launch_bounds__(128) ims_render_kernel(ImsArgs a)
  * decides every candidate with the exact fp32 geometry, queues the hits in shared memory so that the expensive part --
  * SH encoding, one thread per image -- runs with full warps, accumulates the taps in SHARED memory (fp64 atomics that
  * never leave the SM) and writes its window of the fp32 RIR once: no atomics in HBM, no fp64 accumulator array, no
- * conversion pass, no memset.  grid (windows, nPairs); dynamic shared memory: double [nSH][tw] + long long [qcap]. */
+ * conversion pass, no memset.  grid (windows, nPairs); dynamic shared memory: double [nSH][tw] + long long [qcap] + the queue counter. */
 #define IMS_ROWS_PER_ROUND 8192
 template <int NMAX>
 __global__ void __launch_bounds__(128) ims_window_kernel(ImsArgs a, float* const* __restrict__ rirPtrs, int accDoubles, int qcap)
 {
-    extern __shared__ __align__(16) unsigned char ims_smem[];
-    __shared__ int qn;
+    extern __shared__ __align__(16) unsigned char ims_smem[];     /* no static shared memory: the opt-in limit is for dynamic + static */
     const ScpImsPair p = a.pairs[blockIdx.y];
     const int tw = p.tw, w0 = blockIdx.x * tw;
     if (w0 >= p.len) return;
     double* sacc = reinterpret_cast<double*>(ims_smem);
     unsigned long long* queue = reinterpret_cast<unsigned long long*>(sacc + accDoubles);
+    int& qn = *reinterpret_cast<int*>(queue + qcap);
     const int nAcc = p.nSH * tw;
     for (int e = threadIdx.x; e < nAcc; e += blockDim.x) sacc[e] = 0.0;
     if (threadIdx.x == 0) qn = 0;
@@ -635,7 +635,7 @@ int scdev_ims_render_windows(const void* d_pairs, int nPairs, int maxWindows, in
     ImsArgs a = {};
     a.pairs = (const ScpImsPair*)d_pairs; a.absTab = d_absTab; a.nBands = nBands; a.maxW = maxW; a.norms = d_norms;
     const int qcap = 2048;
-    const size_t smem = sizeof(double) * (size_t)accDoubles + sizeof(unsigned long long) * qcap;
+    const size_t smem = sizeof(double) * (size_t)accDoubles + sizeof(unsigned long long) * qcap + 16;     /* + the queue counter */
     const dim3 grid(maxWindows, nPairs);
     if (maxOrder <= 3) {
         if (smem > 48 * 1024) SC_CHECK(sc_optin_smem(ims_window_kernel<3>));

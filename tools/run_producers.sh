@@ -14,8 +14,6 @@ print(json.dumps(bench.producers_block(argparse.Namespace(), torch.device('cuda:
 echo "bench block rc=$?"; cut -c1-1500 gpurun_out/${TAG}_bench_producers_block.json; tail -3 gpurun_out/${TAG}_bench_producers_block.err
 timeout 120 python tools/producers_bench.py --sources 64 --cpu --out gpurun_out/${TAG}_producers_bench_s64.json > gpurun_out/${TAG}_producers_bench_s64.log 2>&1
 echo "bench s64 (windows) rc=$?"; tail -1 gpurun_out/${TAG}_producers_bench_s64.log
-SAFCONV_IMS_WINDOWS=0 SAFCONV_MAGLS_CLUSTER=0 timeout 120 python tools/producers_bench.py --sources 64 --out gpurun_out/${TAG}_producers_bench_s64_v1.json > gpurun_out/${TAG}_producers_bench_s64_v1.log 2>&1
-echo "bench s64 (global atomics, one-CTA MagLS) rc=$?"; tail -1 gpurun_out/${TAG}_producers_bench_s64_v1.log
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_producers.csv \
     python tools/producers_bench.py --sources 8 --max-time 1.0 > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
