@@ -235,6 +235,7 @@ int  scdev_ims_render_windows(const void* d_pairs, int nPairs, int maxWindows, i
                               int nBands, int maxW, const float* d_norms, float* const* d_rirPtrs, void* stream);
 int  scdev_ims_bank(const float* const* d_rirPtrs, const int* d_len, int nSrc, int nCh, int L, float* d_H, void* stream);
 int  scdev_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
+int  scdev_mem_free_bytes(size_t* freeBytes);
 
 #ifdef __cplusplus
 }

@@ -634,8 +634,17 @@ void safconv_ims_shoebox_renderRIRs(void* hIms, int fractionalDelaysFLAG)
         rirPtrs[i] = p->d_rir;
     }
     PROD_TRY(scdev_memcpy_h2d_async(d_pairs, hp, sizeof(ScpImsPair) * (size_t)nP, s->stream), "pair upload");
-    /* (a lattice row must fit the window kernel's hit queue: 2 Nx + 1 <= 2048 -- rooms narrower than c * maxTime / 1000) */
-    if (sch_env_int("SAFCONV_IMS_WINDOWS", 1, 0, 1) && 2 * Nx + 1 <= 2048) {
+    /* Two render kernels.  The lattice scan with fp64 atomics in HBM is the faster one on B200 (measured: 2.95 vs 6.9 ms for
+     * 6.4 M images x 64 channels) but needs an fp64 accumulator of the whole bank (8 bytes per tap: 3.1 GB for the 64 x 64 x
+     * 96 000 bank); the windowed kernel needs nothing beyond the fp32 RIRs.  So: the scan while its accumulator fits in a
+     * quarter of the free device memory, the windows beyond; SAFCONV_IMS_WINDOWS=0 / 1 forces one.  (A lattice row must
+     * fit the window kernel's hit queue: 2 Nx + 1 <= 2048.) */
+    int useWindows = sch_env_int("SAFCONV_IMS_WINDOWS", -1, -1, 1);
+    if (useWindows < 0) {
+        size_t freeB = 0;
+        useWindows = (scdev_mem_free_bytes(&freeB) == 0 && (double)total * 8.0 > 0.25 * (double)freeB) ? 1 : 0;
+    }
+    if (useWindows && 2 * Nx + 1 <= 2048) {
         /* pass 2, windowed: one CTA per (pair, window of taps), taps accumulated in shared memory */
         e = scdev_malloc(&d_ptrs, sizeof(float*) * (size_t)nP);
         if (e) { rc = prod_fail(SAFCONV_ERR_NOMEM, "ims_shoebox_renderRIRs: pointer table", e); goto done; }

@@ -262,23 +262,41 @@ __global__ void __launch_bounds__(1024, 1) prod_magls_cluster_kernel(MaglsArgs a
         /* the next band's HRTF magnitudes are requested now and used one band later */
         const float2 hnext = (act && band + 1 < a.nB) ? a.H[((size_t)(band + 1) * 2 + ear) * nD + d0 + dl] : make_float2(0.f, 0.f);
         if (act) {
-            double re = 0.0, im = 0.0;
+            /* four independent partial sums: the fp64 FMA chain is what a band waits for */
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, i0 = 0.0, i1 = 0.0, i2 = 0.0, i3 = 0.0;
             const float2* dd = sD + ear * n;
-            for (int i = 0; i < n; i++) { const double y = (double)Ys[i * S + dl]; re += y * dd[i].x; im += y * dd[i].y; }
+            int i = 0;
+            for (; i + 3 < n; i += 4) {
+                const double y0 = (double)Ys[i * S + dl], y1 = (double)Ys[(i + 1) * S + dl], y2 = (double)Ys[(i + 2) * S + dl], y3 = (double)Ys[(i + 3) * S + dl];
+                r0 += y0 * dd[i].x; i0 += y0 * dd[i].y; r1 += y1 * dd[i + 1].x; i1 += y1 * dd[i + 1].y;
+                r2 += y2 * dd[i + 2].x; i2 += y2 * dd[i + 2].y; r3 += y3 * dd[i + 3].x; i3 += y3 * dd[i + 3].y;
+            }
+            for (; i < n; i++) { const double y = (double)Ys[i * S + dl]; r0 += y * dd[i].x; i0 += y * dd[i].y; }
+            const double re = (r0 + r1) + (r2 + r3), im = (i0 + i1) + (i2 + i3);
             const double mag = sqrt((double)hcur.x * hcur.x + (double)hcur.y * hcur.y);
             const double nr = sqrt(re * re + im * im);
             hm[ear * S + dl] = (nr > 0.0) ? make_float2((float)(mag * re / nr), (float)(mag * im / nr)) : make_float2((float)mag, 0.0f);
         }
         __syncthreads();
         const int buf = band & 1;
-        for (int o = w; o < 2 * n; o += nw) {
-            const int eo = o / n, i = o - eo * n;
-            const float* g = Gs + (size_t)i * S;
-            const float2* hh = hm + eo * S;
-            double re = 0.0, im = 0.0;
-            for (int d = lane; d < ns; d += 32) { const float2 hv = hh[d]; const double gv = (double)g[d]; re += gv * (double)hv.x; im += gv * (double)hv.y; }
-            re = warp_sum(re); im = warp_sum(im);
-            if (lane < C) pcl_store_d2(&part[((size_t)buf * C + rank) * 2 * n + o], (uint32_t)lane, re, im);
+        for (int o0 = 4 * w; o0 < 2 * n; o0 += 4 * nw) {           /* four outputs of a warp at a time: their reductions overlap */
+            double re[4] = {0.0, 0.0, 0.0, 0.0}, im[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int d = lane; d < ns; d += 32) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int o = min(o0 + k, 2 * n - 1), eo = o / n, i = o - eo * n;
+                    const float2 hv = hm[eo * S + d]; const double gv = (double)Gs[(size_t)i * S + d];
+                    re[k] += gv * (double)hv.x; im[k] += gv * (double)hv.y;
+                }
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+                for (int k = 0; k < 4; k++) { re[k] += __shfl_xor_sync(0xffffffffu, re[k], sft); im[k] += __shfl_xor_sync(0xffffffffu, im[k], sft); }
+            if (lane < C)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (o0 + k < 2 * n) pcl_store_d2(&part[((size_t)buf * C + rank) * 2 * n + o0 + k], (uint32_t)lane, re[k], im[k]);
         }
         pcl_sync();
         for (int o = threadIdx.x; o < 2 * n; o += blockDim.x) {
@@ -661,6 +679,12 @@ int scdev_ims_bank(const float* const* d_rirPtrs, const int* d_len, int nSrc, in
     BankArgs b = { d_rirPtrs, d_len, d_H, nSrc, L };
     ims_bank_kernel<<<dim3((L + 255) / 256, nSrc, nCh), 256, 0, (cudaStream_t)stream>>>(b);
     return (int)cudaGetLastError();
+}
+
+int scdev_mem_free_bytes(size_t* freeBytes)
+{
+    size_t total = 0;
+    return (int)cudaMemGetInfo(freeBytes, &total);
 }
 
 int scdev_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream)
