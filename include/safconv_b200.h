@@ -258,12 +258,18 @@ void safconv_matrixConv_create_device(void** const phMC, int hopSize, const floa
  *   weights        N_dirs integration weights or NULL (uniform 1 / N_dirs)
  *   decMtx         FLAT N_bands x 2 x (order+1)^2 complex;  decFilters FLAT 2 x (order+1)^2 x fftSize real -- the
  *                  nCHout x nCHin x length_h layout saf_matrixConv_create takes (N_bands = fftSize/2 + 1 for the filters)
- * LS, LSDIFFEQ, TA and MAGLS are built, with max-rE weighting and diffuse-field covariance matching; SPR (which needs
- * the reference's t-design tables) returns SAFCONV_ERR_ARG and leaves the output untouched, as does order > 10.
+ * All five designs are built (LS, LSDIFFEQ, SPR, TA, MAGLS), with max-rE weighting and diffuse-field covariance matching.
+ * SPR projects on SAF's minimum t-design of degree 2 * order (saf_hoa_internal.c:383-389); those tables are SAF's data and
+ * are not copied into this library: it uses what safconv_register_tdesign was given, else SAF's own
+ * __HANDLES_Tdesign_dirs_deg / __Tdesign_nPoints_per_degree if the host process carries them (weak references), else the
+ * call returns SAFCONV_ERR_ARG and leaves the output untouched -- as does order > 10.
  * itd_s is accepted and, as in the reference (whose TA phase term is exp(0 * itd), saf_hoa_internal.c:494-497), has no
  * influence on the result.  The safconv_ names return SAFCONV_OK or an error code (text: safconv_last_error_string(NULL));
  * the reference's own names are exported as WEAK void functions.
  */
+/** Hand a spherical t-design to the SPR decoder: dirs_deg FLAT nPoints x 2, [azimuth, elevation] in degrees (copied;
+ *  process-wide, thread-safe).  A SAF host passes __HANDLES_Tdesign_dirs_deg[degree-1], __Tdesign_nPoints_per_degree[degree-1]. */
+int  safconv_register_tdesign(int degree, const float* dirs_deg, int nPoints);
 int  safconv_getBinauralAmbiDecoderMtx(const void* hrtfs, const float* hrtf_dirs_deg, int N_dirs, int N_bands, int method,
                                        int order, const float* freqVector, const float* itd_s, const float* weights,
                                        int enableDiffCovMatching, int enableMaxReWeighting, void* decMtx);

@@ -69,7 +69,26 @@ class RefProducers:
         L.ims_shoebox_setWallAbsCoeffs.argtypes = [C.c_void_p, _f32p]
         L.oracle_ims_get_rir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oracle_ims_get_echogram.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
+        L.oracle_tdesign.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.oracle_tdesign.restype = _f32p
+        L.checkCondNumberSHTReal.argtypes = [C.c_int, _f32p, C.c_int, _f32p, _f32p]
         self.L = L
+
+    def tdesign(self, degree):
+        """the reference's minimum t-design of `degree` (1..21): [nPoints, 2] = (azimuth, elevation) in degrees"""
+        n = C.c_int()
+        p = self.L.oracle_tdesign(int(degree), C.byref(n))
+        if not p:
+            raise ValueError("degree must be 1..21")
+        return np.ctypeslib.as_array(p, shape=(n.value, 2)).copy()
+
+    def cond_numbers(self, order, dirs_rad, weights=None):
+        """checkCondNumberSHTReal (saf_sh.c:884-953): condition number of the SH transform per order 0..order"""
+        d = np.ascontiguousarray(dirs_rad, np.float32)
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        out = np.zeros(order + 1, np.float32)
+        self.L.checkCondNumberSHTReal(int(order), _fp(d), d.shape[0], None if w is None else _fp(w), _fp(out))
+        return out
 
     # --- saf_hoa -------------------------------------------------------------------------------------------------
     def decoder_filters(self, hrtfs, dirs_deg, fftSize, fs, method, order, itd_s=None, weights=None,
@@ -253,7 +272,24 @@ def _band_cutoff(freqs):
     return int(np.argmin(np.abs(f - np.float32(1.5e3))))
 
 
-def np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs=None, itd_s=None, weights=None, diffCM=0, maxRE=0):
+def np_spr_order(dirs_deg, n_dirs, weights=None):
+    """the SH order the SPR decoder interpolates the HRTF set with (saf_hoa_internal.c:357-371): the LAST order up to
+    min(int(sqrt(N_dirs) - 1), 20) whose SH transform has a condition number below 100 (checkCondNumberSHTReal)"""
+    nh_max = min(int(np.float32(np.sqrt(np.float32(n_dirs))) - np.float32(1.0)), 20)
+    Y = np_rsh(nh_max, dirs_deg) / math.sqrt(4.0 * math.pi)
+    w = np.ones(n_dirs) if weights is None else np.asarray(weights, np.float64)
+    conds = []
+    for n in range(nh_max + 1):
+        Yn = Y[:(n + 1) ** 2]
+        s = np.linalg.svd((Yn * w) @ Yn.T, compute_uv=False)
+        conds.append(s.max() / (s.min() + 2.23e-7))
+    nh = 0
+    for i, c in enumerate(conds):
+        nh = i if c < 100.0 else nh
+    return nh, np.array(conds)
+
+
+def np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs=None, itd_s=None, weights=None, diffCM=0, maxRE=0, tdesign_deg=None):
     """getBinauralAmbiDecoderMtx, saf_hoa.c:393-450 (+ saf_hoa_internal.c:162-623), fp64.
     hrtfs: nBands x 2 x nDirs complex.  Returns nBands x 2 x nSH complex128."""
     H = np.asarray(hrtfs, np.complex128)
@@ -287,8 +323,19 @@ def np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs=None, itd_s=None, weigh
             Hmod = D[b - 1] @ Y
             ph = np.arctan2(Hmod.imag, Hmod.real)
             D[b] = (np.abs(H[b]) * np.exp(1j * ph)) @ G.T
+    elif method == SPR:                                                   # getBinDecoder_SPR :332-430
+        if tdesign_deg is None:
+            raise ValueError("SPR needs the t-design of degree 2 * order (RefProducers.tdesign)")
+        nh, _ = np_spr_order(dirs_deg, nD, weights)
+        assert nh >= order, "Input order exceeds the modal order of the spatial grid"
+        wspr = np.full(nD, 1.0 / nD) if weights is None else np.asarray(weights, np.float64) / (4.0 * math.pi)   # :347-353
+        Ynh = np_rsh(nh, dirs_deg).astype(np.float32).astype(np.float64)
+        Ytd = np_rsh(nh, tdesign_deg).astype(np.float32).astype(np.float64)
+        K = Ytd.shape[1]
+        Htd = (H * wspr) @ (Ynh.T @ Ytd)                                  # HRTFs interpolated to the t-design, :399-412
+        D = Htd @ Ytd[:Y.shape[0]].T / K                                  # projected on the SH of the decoding order, :413-420
     else:
-        raise ValueError("SPR needs the reference's t-design tables; not restated")
+        raise ValueError("unknown method")
     if maxRE:                                                             # saf_hoa.c:427-445
         D = D * np_maxre(order)[None, None, :]
     if diffCM:                                                            # applyDiffCovMatching, saf_hoa.c:497-604
@@ -306,12 +353,12 @@ def np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs=None, itd_s=None, weigh
     return D
 
 
-def np_decoder_filters(hrtfs, dirs_deg, fftSize, fs, method, order, itd_s=None, weights=None, diffCM=0, maxRE=0):
+def np_decoder_filters(hrtfs, dirs_deg, fftSize, fs, method, order, itd_s=None, weights=None, diffCM=0, maxRE=0, tdesign_deg=None):
     """getBinauralAmbiDecoderFilters, saf_hoa.c:452-497: decoding matrix per bin, then one inverse real FFT per
     (ear, SH channel) -> FLAT 2 x nSH x fftSize = the matrixConv filter layout nCHout x nCHin x length_h."""
     nB = fftSize // 2 + 1
     freqs = (np.arange(nB, dtype=np.float32) * np.float32(fs) / np.float32(fftSize))   # getUniformFreqVector
-    D = np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs, itd_s, weights, diffCM, maxRE)
+    D = np_decoder_mtx(hrtfs, dirs_deg, method, order, freqs, itd_s, weights, diffCM, maxRE, tdesign_deg)
     Dt = np.transpose(D, (1, 2, 0)).copy()
     Dt[..., 0] = Dt[..., 0].real          # kiss_fftri uses only the real parts of DC and Nyquist (kiss_fftr.c:137-138)
     Dt[..., -1] = Dt[..., -1].real

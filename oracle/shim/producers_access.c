@@ -8,6 +8,7 @@
  */
 #include "saf_reverb.h"
 #include "saf_reverb_internal.h"
+#include "saf_utility_loudspeaker_presets.h"
 
 static int find_src(ims_scene_data* sc, int id)
 { for (int i = 0; i < IMS_MAX_NUM_SOURCES; i++) if (sc->srcs[i].ID == id) return i; return -1; }
@@ -34,4 +35,14 @@ int oracle_ims_get_echogram(void* hIms, int receiverID, int sourceID, float* tim
     echogram_data* e = (echogram_data*)w->hEchogram_abs[0];
     if (times) for (int i = 0; i < e->numImageSources && i < cap; i++) times[i] = e->time[i];
     return e->numImageSources;
+}
+
+/* the reference's minimum t-design of a given degree (1..21), [azimuth, elevation] in degrees
+ * (saf_utility_loudspeaker_presets.h:286-301): the SPR decoder projects on the one of degree 2 * order
+ * (saf_hoa_internal.c:383-389).  Tests hand it to the product through safconv_register_tdesign. */
+const float* oracle_tdesign(int degree, int* nPoints)
+{
+    if (degree < 1 || degree > 21) return 0;
+    *nPoints = __Tdesign_nPoints_per_degree[degree - 1];
+    return __HANDLES_Tdesign_dirs_deg[degree - 1];
 }

@@ -215,6 +215,11 @@ int  scdev_tv_fused(const scdev_plan* pl, const scdev_bufs* b, const float* d_in
 int  scdev_prod_rsh(int order, const float* d_dirs, int nD, float* d_Y, void* stream);
 /* G [nSH][nD] = (Y W Y^T)^-1 Y W; d_aug: double [nSH][2 nSH] scratch, d_flag: 1 if the Gram matrix is singular */
 int  scdev_prod_lsmatrix(const float* d_Y, const float* d_w, int nD, int n, double* d_aug, float* d_G, int* d_flag, void* stream);
+/* SPR decoder set-up: condition numbers of the SH transform per order 0 .. nhMax (d_Y [(nhMax+1)^2][nD]; d_aug double
+ * [nS][2 nS], nS = (nhMax+1)^2), and G [n][nD] = the t-design projection folded into one matrix (d_M: double [nA][n]) */
+int  scdev_prod_spr_cond(const float* d_Y, const float* d_w, int nD, int nhMax, double* d_aug, float* d_cond, void* stream);
+int  scdev_prod_spr_matrix(const float* d_Ynh, const float* d_Ytd, const float* d_w, int nD, int K, int nA, int n,
+                           double* d_M, float* d_G, void* stream);
 /* D [nB][2][nSH] complex = H [nB][2][nD] complex times G^T; ta: bands >= bc use the HRTFs of band bc */
 int  scdev_prod_ls(const void* d_H, const float* d_G, int nB, int nD, int n, int ta, int bc, void* d_D, void* stream);
 int  scdev_prod_diffeq(const void* d_H, const float* d_Y, const float* d_w, int nB, int nD, int n, void* d_D, void* stream);

@@ -22,6 +22,7 @@
 #include "safconv_prod_core.cuh"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +61,52 @@ static int prod_device_begin(int* device, int* smCount)
 /* methods, saf_hoa.h:131-171 */
 enum { DEC_DEFAULT = 0, DEC_LS = 1, DEC_LSDIFFEQ = 2, DEC_SPR = 3, DEC_TA = 4, DEC_MAGLS = 5 };
 
+/* ---- t-designs for the SPR decoder ------------------------------------------------------------------------------
+ * getBinDecoder_SPR projects on the reference's minimum t-design of degree 2 * order (saf_hoa_internal.c:383-389:
+ * __HANDLES_Tdesign_dirs_deg[2*order-1], tables of saf_utility_loudspeaker_presets.c).  Those tables are SAF's data and
+ * are not copied into this library; it takes them from (1) what the host registered with safconv_register_tdesign, or
+ * (2) SAF's own symbols if the process that loaded this library carries them (WEAK references: NULL otherwise). */
+extern const float* __HANDLES_Tdesign_dirs_deg[21] __attribute__((weak));
+extern const int    __Tdesign_nPoints_per_degree[21] __attribute__((weak));
+
+#define TD_MAX_DEGREE 64
+static struct { float* dirs; int n; } g_td[TD_MAX_DEGREE + 1];
+static pthread_mutex_t g_td_lock = PTHREAD_MUTEX_INITIALIZER;
+
+int safconv_register_tdesign(int degree, const float* dirs_deg, int nPoints)
+{
+    if (degree < 1 || degree > TD_MAX_DEGREE || !dirs_deg || nPoints < 1)
+        return prod_fail(SAFCONV_ERR_ARG, "safconv_register_tdesign: need 1 <= degree <= 64, a direction list and nPoints >= 1", 0);
+    float* c = (float*)malloc(sizeof(float) * 2 * (size_t)nPoints);
+    if (!c) return prod_fail(SAFCONV_ERR_NOMEM, "out of host memory", 0);
+    memcpy(c, dirs_deg, sizeof(float) * 2 * (size_t)nPoints);
+    pthread_mutex_lock(&g_td_lock);
+    free(g_td[degree].dirs);
+    g_td[degree].dirs = c; g_td[degree].n = nPoints;
+    pthread_mutex_unlock(&g_td_lock);
+    return SAFCONV_OK;
+}
+
+/* copy of the t-design of `degree` (caller frees), or NULL */
+static float* tdesign_lookup(int degree, int* nPoints)
+{
+    float* out = NULL;
+    pthread_mutex_lock(&g_td_lock);
+    if (degree >= 1 && degree <= TD_MAX_DEGREE && g_td[degree].dirs) {
+        *nPoints = g_td[degree].n;
+        out = (float*)malloc(sizeof(float) * 2 * (size_t)g_td[degree].n);
+        if (out) memcpy(out, g_td[degree].dirs, sizeof(float) * 2 * (size_t)g_td[degree].n);
+    }
+    pthread_mutex_unlock(&g_td_lock);
+    if (!out && degree >= 1 && degree <= 21 && __HANDLES_Tdesign_dirs_deg && __Tdesign_nPoints_per_degree &&
+        __HANDLES_Tdesign_dirs_deg[degree - 1]) {
+        *nPoints = __Tdesign_nPoints_per_degree[degree - 1];
+        out = (float*)malloc(sizeof(float) * 2 * (size_t)*nPoints);
+        if (out) memcpy(out, __HANDLES_Tdesign_dirs_deg[degree - 1], sizeof(float) * 2 * (size_t)*nPoints);
+    }
+    return out;
+}
+
 /* Decoding matrices of all bands on the device: *pD = float2 [nB][2][nSH] (caller frees). */
 static int decoder_mtx_device(const void* hrtfs, const float* dirs_deg, int nD, int nB, int method, int order,
                               const float* freqVector, const float* weights, int diffCM, int maxRE,
@@ -69,9 +116,11 @@ static int decoder_mtx_device(const void* hrtfs, const float* dirs_deg, int nD, 
     const int n = (order + 1) * (order + 1);
     void *d_H = NULL, *d_D = NULL, *d_hm = NULL;
     float *d_dirs = NULL, *d_Y = NULL, *d_w = NULL, *d_G = NULL, *d_a = NULL;
-    double* d_aug = NULL;
+    float *d_tdirs = NULL, *d_Ytd = NULL, *d_ws = NULL, *d_cond = NULL;
+    double *d_aug = NULL, *d_M = NULL;
     int* d_flag = NULL;
-    float* w = NULL;
+    float *w = NULL, *ws = NULL, *td = NULL;
+    int K = 0, nhMax = 0, nS = n;            /* SPR: t-design points, highest candidate interpolation order, its channel count */
     *pD = NULL;
 
     if (method < DEC_DEFAULT || method > DEC_MAGLS) method = DEC_DEFAULT;      /* the reference's `default:` label, saf_hoa.c:415 */
@@ -91,13 +140,34 @@ static int decoder_mtx_device(const void* hrtfs, const float* dirs_deg, int nD, 
     if (!w) return prod_fail(SAFCONV_ERR_NOMEM, "out of host memory", 0);
     for (int i = 0; i < nD; i++) w[i] = weights ? weights[i] : 1.0f / (float)nD;
 
+    if (method == DEC_SPR) {
+        td = tdesign_lookup(2 * order, &K);
+        if (!td) { free(w); return prod_fail(SAFCONV_ERR_ARG, "SPR: no t-design of degree 2 * order (safconv_register_tdesign)", 0); }
+        /* candidate interpolation orders 0 .. min(sqrt(N_dirs) - 1, 20) (saf_hoa_internal.c:357) */
+        nhMax = (int)(sqrtf((float)nD) - 1.0f);
+        if (nhMax > 20) nhMax = 20;
+        if (nhMax < 0) nhMax = 0;
+        nS = (nhMax + 1) * (nhMax + 1);
+        if (nS < n) nS = n;
+        /* weights of the condition check: the caller's, or none (saf_sh.c:905-914); of the projection: weights / 4 pi or 1 / N (:347-353) */
+        ws = (float*)malloc(sizeof(float) * 2 * (size_t)nD);
+        if (!ws) { free(w); free(td); return prod_fail(SAFCONV_ERR_NOMEM, "out of host memory", 0); }
+        for (int i = 0; i < nD; i++) { ws[i] = weights ? weights[i] : 1.0f; ws[nD + i] = weights ? weights[i] / (4.0f * SCSH_PI_F) : 1.0f / (float)nD; }
+    }
     const size_t bytesH = sizeof(float) * 2 * (size_t)nB * 2 * nD;
     int e = scdev_malloc(&d_H, bytesH);
     if (!e) e = scdev_malloc((void**)&d_dirs, sizeof(float) * 2 * (size_t)nD);
-    if (!e) e = scdev_malloc((void**)&d_Y, sizeof(float) * (size_t)n * nD);
+    if (!e) e = scdev_malloc((void**)&d_Y, sizeof(float) * (size_t)nS * nD);
     if (!e) e = scdev_malloc((void**)&d_w, sizeof(float) * (size_t)nD);
     if (!e) e = scdev_malloc((void**)&d_G, sizeof(float) * (size_t)n * nD);
-    if (!e) e = scdev_malloc((void**)&d_aug, sizeof(double) * 2 * (size_t)n * n);
+    if (!e) e = scdev_malloc((void**)&d_aug, sizeof(double) * 2 * (size_t)nS * nS);
+    if (!e && method == DEC_SPR) {
+        e = scdev_malloc((void**)&d_tdirs, sizeof(float) * 2 * (size_t)K);
+        if (!e) e = scdev_malloc((void**)&d_Ytd, sizeof(float) * (size_t)nS * K);
+        if (!e) e = scdev_malloc((void**)&d_ws, sizeof(float) * 2 * (size_t)nD);
+        if (!e) e = scdev_malloc((void**)&d_cond, sizeof(float) * (size_t)(nhMax + 1));
+        if (!e) e = scdev_malloc((void**)&d_M, sizeof(double) * (size_t)nS * n);
+    }
     if (!e) e = scdev_malloc((void**)&d_flag, sizeof(int));
     if (!e) e = scdev_malloc(&d_D, sizeof(float) * 2 * (size_t)nB * 2 * n);
     if (!e && method == DEC_MAGLS) e = scdev_malloc(&d_hm, sizeof(float) * 2 * 2 * (size_t)nD);
@@ -106,9 +176,26 @@ static int decoder_mtx_device(const void* hrtfs, const float* dirs_deg, int nD, 
     PROD_TRY(scdev_memcpy_h2d_async(d_H, hrtfs, bytesH, stream), "HRTF upload");
     PROD_TRY(scdev_memcpy_h2d_async(d_dirs, dirs_deg, sizeof(float) * 2 * (size_t)nD, stream), "direction upload");
     PROD_TRY(scdev_memcpy_h2d_async(d_w, w, sizeof(float) * (size_t)nD, stream), "weight upload");
-    PROD_TRY(scdev_prod_rsh(order, d_dirs, nD, d_Y, stream), "SH evaluation");
-    PROD_TRY(scdev_prod_lsmatrix(d_Y, d_w, nD, n, d_aug, d_G, d_flag, stream), "least-squares matrix");
-    {
+    if (method == DEC_SPR) {
+        /* getBinDecoder_SPR (saf_hoa_internal.c:332-430): interpolate the HRTF set with SH of the highest well-conditioned
+         * order Nh, evaluate it on the t-design of degree 2 * order, project on the SH of the decoding order -- folded
+         * into ONE matrix G, so that the decoder of every band is the same product D = H G^T as the least-squares one */
+        float cond[21];
+        int Nh = 0;
+        PROD_TRY(scdev_memcpy_h2d_async(d_ws, ws, sizeof(float) * 2 * (size_t)nD, stream), "weight upload");
+        PROD_TRY(scdev_memcpy_h2d_async(d_tdirs, td, sizeof(float) * 2 * (size_t)K, stream), "t-design upload");
+        PROD_TRY(scdev_prod_rsh(nhMax > order ? nhMax : order, d_dirs, nD, d_Y, stream), "SH evaluation");     /* rows of order <= N first (ACN) */
+        PROD_TRY(scdev_prod_spr_cond(d_Y, d_ws, nD, nhMax, d_aug, d_cond, stream), "condition numbers");
+        PROD_TRY(scdev_memcpy_d2h_async(cond, d_cond, sizeof(float) * (size_t)(nhMax + 1), stream), "condition number download");
+        PROD_TRY(scdev_stream_sync(stream), "condition numbers");
+        for (int i = 0; i <= nhMax; i++) Nh = (cond[i] < 100.0f) ? i : Nh;                                    /* :369-370 */
+        if (Nh < order) { rc = prod_fail(SAFCONV_ERR_ARG, "SPR: input order exceeds the modal order of the spatial grid (saf_hoa_internal.c:371)", 0); goto done; }
+        const int nA = (Nh + 1) * (Nh + 1);
+        PROD_TRY(scdev_prod_rsh(Nh, d_tdirs, K, d_Ytd, stream), "SH evaluation (t-design)");
+        PROD_TRY(scdev_prod_spr_matrix(d_Y, d_Ytd, d_ws + nD, nD, K, nA, n, d_M, d_G, stream), "SPR matrix");
+    } else {
+        PROD_TRY(scdev_prod_rsh(order, d_dirs, nD, d_Y, stream), "SH evaluation");
+        PROD_TRY(scdev_prod_lsmatrix(d_Y, d_w, nD, n, d_aug, d_G, d_flag, stream), "least-squares matrix");
         int flag = 0;
         PROD_TRY(scdev_memcpy_d2h_async(&flag, d_flag, sizeof(int), stream), "flag download");
         PROD_TRY(scdev_stream_sync(stream), "least-squares matrix");
@@ -134,9 +221,10 @@ static int decoder_mtx_device(const void* hrtfs, const float* dirs_deg, int nD, 
     PROD_TRY(scdev_stream_sync(stream), "decoder design");
     *pD = d_D; d_D = NULL;
 done:
-    free(w);
+    free(w); free(ws); free(td);
     scdev_free(d_H); scdev_free(d_dirs); scdev_free(d_Y); scdev_free(d_w); scdev_free(d_G); scdev_free(d_aug);
     scdev_free(d_flag); scdev_free(d_D); scdev_free(d_hm); scdev_free(d_a);
+    scdev_free(d_tdirs); scdev_free(d_Ytd); scdev_free(d_ws); scdev_free(d_cond); scdev_free(d_M);
     return rc;
 }
 
@@ -144,9 +232,17 @@ static int decoder_check(const void* hrtfs, const float* dirs, int nD, int nB, i
 {
     if (!hrtfs || !dirs || !out || nD < 1 || nB < 1 || order < 0)
         return prod_fail(SAFCONV_ERR_ARG, "getBinauralAmbiDecoder*: invalid argument", 0);
-    if (method == DEC_SPR)
-        return prod_fail(SAFCONV_ERR_ARG, "getBinauralAmbiDecoder*: BINAURAL_DECODER_SPR is not supported (it needs the reference's "
-                         "t-design tables, saf_hoa_internal.c:383-389); LS, LSDIFFEQ, TA and MAGLS are", 0);
+    if (method == DEC_SPR) {
+        /* the reference indexes its t-design table with 2 * order - 1 (saf_hoa_internal.c:384): order 0 reads before the table */
+        if (order < 1) return prod_fail(SAFCONV_ERR_ARG, "getBinauralAmbiDecoder*: BINAURAL_DECODER_SPR needs order >= 1", 0);
+        int k = 0;
+        float* td = tdesign_lookup(2 * order, &k);
+        if (!td)
+            return prod_fail(SAFCONV_ERR_ARG, "getBinauralAmbiDecoder*: BINAURAL_DECODER_SPR needs the t-design of degree 2 * order: register it with "
+                             "safconv_register_tdesign (SAF's tables are not copied into this library; a host that carries SAF's "
+                             "__HANDLES_Tdesign_dirs_deg is served without)", 0);
+        free(td);
+    }
     if (order > SCSH_MAX_ORDER)
         return prod_fail(SAFCONV_ERR_ARG, "getBinauralAmbiDecoder*: order > 10 is not supported", 0);
     return SAFCONV_OK;

@@ -125,6 +125,77 @@ __global__ void prod_g_kernel(const double* __restrict__ aug, const float* __res
     G[(size_t)i * nD + d] = (float)(s * (double)w[d]);
 }
 
+/* SPR decoder (saf_hoa_internal.c:332-430), set-up 1: condition number of the SH transform of the measurement grid per order
+ * (checkCondNumberSHTReal, saf_sh.c:884-953: largest / smallest singular value of Y_n W Y_n^T, which are its eigenvalues).
+ * The Gram matrix of the highest order holds those of all lower orders as leading blocks (ACN order nests).  One CTA per
+ * order: power iteration for the largest eigenvalue, power iteration on (sigma I - A) for the smallest -- the Rayleigh
+ * quotient converges to the VALUE long before the vector does, and only "below or above 100" is asked.
+ * aug: [nMax][2 nMax] with the Gram matrix in the left half (prod_gram_kernel); scale: undoes the 4 pi of the N3D scaling.
+ * grid (orders); dynamic shared memory: 2 nMax doubles. */
+__global__ void __launch_bounds__(512) prod_cond_kernel(const double* __restrict__ aug, int nMax, int itMax, int itMin, double scale,
+                                                        float* __restrict__ cond)
+{
+    extern __shared__ double csm[];
+    __shared__ double red[2 * 32];
+    const int m = (blockIdx.x + 1) * (blockIdx.x + 1), W = 2 * nMax;
+    double *v = csm, *u = csm + nMax;
+    double lmax = 0.0, lmin = 0.0;
+    for (int phase = 0; phase < 2; phase++) {
+        const double sigma = phase ? 1.01 * lmax : 0.0;
+        double s[2] = {0.0, 0.0};
+        for (int i = threadIdx.x; i < m; i += blockDim.x) { const double x = 1.0 + 0.37 * sin(1.3 * i + 0.5 + phase); v[i] = x; s[0] += x * x; }
+        block_sum<2>(s, red);
+        const double i0 = rsqrt(s[0]);
+        for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] *= i0;
+        __syncthreads();
+        double lambda = 0.0;
+        const int iters = phase ? itMin : itMax;
+        for (int it = 0; it < iters; it++) {
+            double d[2] = {0.0, 0.0};
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                double a0 = 0.0, a1 = 0.0;
+                int j = 0;
+                for (; j + 1 < m; j += 2) { a0 += aug[(size_t)j * W + i] * v[j]; a1 += aug[(size_t)(j + 1) * W + i] * v[j + 1]; }   /* A symmetric: column i, coalesced */
+                if (j < m) a0 += aug[(size_t)j * W + i] * v[j];
+                const double r = phase ? sigma * v[i] - (a0 + a1) : (a0 + a1);
+                u[i] = r; d[0] += v[i] * r; d[1] += r * r;
+            }
+            block_sum<2>(d, red);
+            lambda = d[0];
+            const double inv = d[1] > 0.0 ? rsqrt(d[1]) : 0.0;
+            for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = u[i] * inv;
+            __syncthreads();
+        }
+        if (phase == 0) lmax = lambda; else lmin = sigma - lambda;
+    }
+    if (lmin < 0.0) lmin = 0.0;
+    if (threadIdx.x == 0) cond[blockIdx.x] = (float)((lmax * scale) / (lmin * scale + 2.23e-7));
+}
+
+/* SPR set-up 2: M[a][i] = (1 / K) sum_k Ytd[a][k] Ytd[i][k], a < nA (interpolation order), i < n (decoding order) --
+ * the t-design quadrature of the SH products (:413-420 folded into :399-412).  grid (n, nA) */
+__global__ void prod_spr_m_kernel(const float* __restrict__ Ytd, int K, int n, double* __restrict__ M)
+{
+    __shared__ double red[32];
+    const int i = blockIdx.x, a = blockIdx.y;
+    double v[1] = {0.0};
+    for (int k = threadIdx.x; k < K; k += blockDim.x) v[0] += (double)Ytd[(size_t)a * K + k] * (double)Ytd[(size_t)i * K + k];
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) M[(size_t)a * n + i] = v[0] / (double)K;
+}
+
+/* SPR set-up 3: G[i][d] = w[d] sum_a Ynh[a][d] M[a][i]: with it the SPR decoder of every band is the same product
+ * D = H G^T as the least-squares one (prod_ls_kernel).  grid (ceil(nD / 128), n) */
+__global__ void prod_spr_g_kernel(const float* __restrict__ Ynh, const double* __restrict__ M, const float* __restrict__ w,
+                                  int nD, int nA, int n, float* __restrict__ G)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (d >= nD) return;
+    double s = 0.0;
+    for (int a = 0; a < nA; a++) s += (double)Ynh[(size_t)a * nD + d] * M[(size_t)a * n + i];
+    G[(size_t)i * nD + d] = (float)(s * (double)w[d]);
+}
+
 /* least-squares decoder of every band: D[band][ear][i] = sum_d H[src][ear][d] G[i][d], src = band, or the cut-off band
  * for band >= bc when `ta` (TA decoder as written: saf_hoa_internal.c:492-505 re-uses the cut-off band's HRTFs because
  * the phase term multiplies by exp(0)).  grid (2, nB), one warp per output i in turn. */
@@ -554,6 +625,27 @@ int scdev_prod_lsmatrix(const float* d_Y, const float* d_w, int nD, int n, doubl
     prod_gram_kernel<<<dim3(n, n), 128, 0, st>>>(d_Y, d_w, nD, n, d_aug);
     prod_spd_inverse_kernel<<<1, 1024, n * sizeof(double), st>>>(d_aug, n, d_flag);
     prod_g_kernel<<<dim3((nD + 127) / 128, n), 128, 0, st>>>(d_aug, d_Y, d_w, nD, n, d_G);
+    return (int)cudaGetLastError();
+}
+
+/* SPR: condition numbers of orders 0 .. nhMax from the Gram matrix of d_Y [(nhMax+1)^2][nD] with weights d_w (ones if the
+ * caller gave none); d_aug: double [nS][2 nS] scratch, nS = (nhMax+1)^2; d_cond: float [nhMax + 1] */
+int scdev_prod_spr_cond(const float* d_Y, const float* d_w, int nD, int nhMax, double* d_aug, float* d_cond, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nS = (nhMax + 1) * (nhMax + 1);
+    prod_gram_kernel<<<dim3(nS, nS), 128, 0, st>>>(d_Y, d_w, nD, nS, d_aug);
+    prod_cond_kernel<<<nhMax + 1, 512, 2 * nS * sizeof(double), st>>>(d_aug, nS, 200, 2000, 1.0 / (4.0 * 3.14159265358979323846), d_cond);
+    return (int)cudaGetLastError();
+}
+
+/* SPR: G [n][nD] from Ynh [nA][nD] (measurement grid, interpolation order), Ytd [nA][K] (t-design, same order), weights */
+int scdev_prod_spr_matrix(const float* d_Ynh, const float* d_Ytd, const float* d_w, int nD, int K, int nA, int n,
+                          double* d_M, float* d_G, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    prod_spr_m_kernel<<<dim3(n, nA), 64, 0, st>>>(d_Ytd, K, n, d_M);
+    prod_spr_g_kernel<<<dim3((nD + 127) / 128, n), 128, 0, st>>>(d_Ynh, d_M, d_w, nD, nA, n, d_G);
     return (int)cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ _vpp = C.POINTER(C.c_void_p)
 DECODER_DEFAULT, DECODER_LS, DECODER_LSDIFFEQ, DECODER_SPR, DECODER_TA, DECODER_MAGLS = range(6)
 
 PRODUCER_SYMBOLS = [
-    "safconv_matrixConv_create_device",
+    "safconv_matrixConv_create_device", "safconv_register_tdesign",
     "safconv_getBinauralAmbiDecoderMtx", "safconv_getBinauralAmbiDecoderFilters",
     "getBinauralAmbiDecoderMtx", "getBinauralAmbiDecoderFilters", "safconv_binauralDecoder_create_matrixConv",
     "safconv_ims_shoebox_create", "safconv_ims_shoebox_destroy", "safconv_ims_shoebox_computeEchograms",
@@ -125,6 +125,15 @@ def decoder_mtx(hrtfs, dirs_deg, method, order, freqs=None, itd_s=None, weights=
     if rc:
         raise _err("getBinauralAmbiDecoderMtx")
     return out
+
+
+def register_tdesign(degree, dirs_deg):
+    """safconv_register_tdesign: the t-design the SPR decoder of order degree / 2 projects on (dirs_deg: [nPoints, 2])"""
+    L = _L()
+    d = _f(dirs_deg)
+    L.safconv_register_tdesign.argtypes = [C.c_int, _f32p, C.c_int]
+    if L.safconv_register_tdesign(int(degree), _p(d), d.shape[0]):
+        raise _err("safconv_register_tdesign")
 
 
 def apply_raw(handle, x, nOut):

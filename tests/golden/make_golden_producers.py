@@ -5,8 +5,9 @@
 
 * producers_sh.npz       getRSH / getSHreal_recur / getMaxREweights values
                          (/root/reference/framework/modules/saf_hoa/saf_hoa.c:118-150, 235-266; saf_sh.c:255-330)
-* producers_decoder.npz  getBinauralAmbiDecoderFilters (saf_hoa.c:452-497) on a seeded synthetic HRTF set, every built
-                         method x {plain, max-rE, covariance matching, both}
+* producers_decoder.npz  getBinauralAmbiDecoderFilters (saf_hoa.c:452-497) on a seeded synthetic HRTF set, every
+                         method x {plain, max-rE, covariance matching, both} (SPR: outputs only -- the t-design it projects on
+                         is fetched from the compiled reference at test time, RefProducers.tdesign)
 * producers_ims.npz      ims_shoebox_* (saf_reverb.c): the scene and the add / remove / move sequence of the reference's
                          own unit test (test/src/test__reverb_module.c:27-96, which asserts nothing), plus time-limited and
                          order-limited echograms at SH orders 0, 3, 7
@@ -83,6 +84,10 @@ def main():
         for dc in (0, 1):
             for mr in (0, 1):
                 out[f"f_m{m}_dc{dc}_mr{mr}"] = R.decoder_filters(H, dirs, fftSize, fs, m, order, itd, None, dc, mr)
+    for dc in (0, 1):
+        for mr in (0, 1):
+            out[f"f_m3_dc{dc}_mr{mr}"] = R.decoder_filters(H, dirs, fftSize, fs, PR.SPR, order, itd, None, dc, mr)
+    out["f_m3_o1_weights"] = R.decoder_filters(H, dirs, fftSize, fs, PR.SPR, 1, itd, w * np.float32(4 * np.pi), 0, 0)
     out["f_m1_weights"] = R.decoder_filters(H, dirs, fftSize, fs, PR.LS, order, itd, w, 1, 1)
     out["f_m5_o1"] = R.decoder_filters(H, dirs, fftSize, fs, PR.MAGLS, 1, itd, None, 0, 0)
     out["f_m2_o5"] = R.decoder_filters(H, dirs, fftSize, fs, PR.LSDIFFEQ, 5, itd, None, 0, 1)

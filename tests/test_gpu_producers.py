@@ -64,6 +64,57 @@ def test_decoder_filters_weights_orders_and_reference_name(saf):
         assert np.array_equal(mine, again)
 
 
+needs_tdesign = pytest.mark.skipif(not PR.producers_reference_available(),
+                                   reason="SAF's t-design tables are not in this repo: the tests take them from oracle/_ref/libsaf_ref_producers.so")
+
+
+@needs_tdesign
+def test_spr_decoder_vs_reference_golden_and_truth(saf):
+    """BINAURAL_DECODER_SPR (saf_hoa_internal.c:332-430): condition numbers on the device pick the interpolation order, the
+    t-design of degree 2 * order is handed over with safconv_register_tdesign"""
+    g = gold("decoder")
+    R = PR.load_producers_reference()
+    H, d, itd, fftSize, fs, order = g["hrtfs"], g["dirs_deg"], g["itd_s"], int(g["fftSize"]), float(g["fs"]), int(g["order"])
+    td = R.tdesign(2 * order)
+    saf.producers.register_tdesign(2 * order, td)
+    for dc in (0, 1):
+        for mr in (0, 1):
+            mine = saf.producers.decoder_filters(H, d, fftSize, fs, PR.SPR, order, itd, None, dc, mr)
+            truth = PR.np_decoder_filters(H, d, fftSize, fs, PR.SPR, order, itd, None, dc, mr, tdesign_deg=td)
+            check_decoder(mine, g[f"f_m3_dc{dc}_mr{mr}"], truth, False, f"SPR diffCM {dc} maxRE {mr}")
+    # weights (the projection uses weights / 4 pi, the condition check the raw weights), another order
+    w = g["weights"] * np.float32(4 * np.pi)
+    saf.producers.register_tdesign(2, R.tdesign(2))
+    mine = saf.producers.decoder_filters(H, d, fftSize, fs, PR.SPR, 1, itd, w, 0, 0)
+    truth = PR.np_decoder_filters(H, d, fftSize, fs, PR.SPR, 1, itd, w, 0, 0, tdesign_deg=R.tdesign(2))
+    check_decoder(mine, g["f_m3_o1_weights"], truth, False, "SPR order 1, weights")
+
+
+@needs_tdesign
+@pytest.mark.parametrize("nD,order,fftSize", [(836, 5, 256), (64, 1, 64), (400, 7, 128), (50, 2, 32), (12, 3, 16)])
+def test_spr_decoder_other_grids_vs_live_reference(saf, nD, order, fftSize):
+    """interpolation orders up to 20 (441 SH channels at 836 directions), an irregular grid whose condition numbers cross 100
+    early, and a grid that cannot carry the requested order (the reference asserts there; here: error)"""
+    R = PR.load_producers_reference()
+    if nD == 50:
+        rng = np.random.default_rng(0)
+        d = np.stack([rng.uniform(-180, 180, nD), np.degrees(np.arcsin(rng.uniform(-1, 1, nD)))], 1).astype(np.float32)
+        H, _, itd = synth.synthetic_hrtfs(nD, fftSize, 48000.0, seed=nD)
+    else:
+        H, d, itd = synth.synthetic_hrtfs(nD, fftSize, 48000.0, seed=nD)
+    td = R.tdesign(2 * order)
+    saf.producers.register_tdesign(2 * order, td)
+    nh, conds = PR.np_spr_order(d, nD)
+    if nh < order:
+        with pytest.raises(saf.SafConvError, match="modal order"):
+            saf.producers.decoder_filters(H, d, fftSize, 48000.0, PR.SPR, order, itd)
+        return
+    mine = saf.producers.decoder_filters(H, d, fftSize, 48000.0, PR.SPR, order, itd, None, 0, 1)
+    truth = PR.np_decoder_filters(H, d, fftSize, 48000.0, PR.SPR, order, itd, None, 0, 1, tdesign_deg=td)
+    ref = R.decoder_filters(H, d, fftSize, 48000.0, PR.SPR, order, itd, None, 0, 1)
+    check_decoder(mine, ref, truth, False, f"SPR nD {nD} order {order} (Nh {nh})")
+
+
 @pytest.mark.parametrize("order,nD,fftSize,m,dc,mr", [
     (7, 836, 512, PR.LS, 1, 1),          # 64 SH channels, a KU100-sized grid, non-trivial flags
     (10, 1202, 256, PR.LSDIFFEQ, 0, 1),  # the largest supported order (121 channels)
@@ -114,7 +165,7 @@ def test_decoder_errors_on_device(saf):
     with pytest.raises(saf.SafConvError, match="singular"):
         saf.producers.decoder_filters(H, d, 16, 48000.0, PR.LS, 3)
     with pytest.raises(saf.SafConvError, match="SPR"):
-        saf.producers.decoder_filters(H, d, 16, 48000.0, PR.SPR, 1)
+        saf.producers.decoder_filters(H, d, 16, 48000.0, PR.SPR, 9)         # no t-design of degree 18 registered
     # and the next good call is clean
     saf.producers.decoder_filters(H, d, 16, 48000.0, PR.LS, 1)
 

@@ -77,6 +77,28 @@ def test_np_decoder_weights_and_orders_vs_golden():
         assert l2 < (5e-5 if kw["method"] == PR.MAGLS else 3e-6), (key, ma, l2)
 
 
+@pytest.mark.skipif(not PR.producers_reference_available(), reason="the t-design comes from oracle/_ref/libsaf_ref_producers.so")
+def test_np_spr_decoder_vs_reference_golden():
+    """SPR (saf_hoa_internal.c:332-430): interpolation order from the condition numbers, projection on the reference's t-design"""
+    g = gold("decoder")
+    R = PR.load_producers_reference()
+    H, d, itd, fftSize, fs, order = g["hrtfs"], g["dirs_deg"], g["itd_s"], int(g["fftSize"]), float(g["fs"]), int(g["order"])
+    nh, conds = PR.np_spr_order(d, d.shape[0])
+    drad = np.stack([np.radians(d[:, 0]), np.pi / 2 - np.radians(d[:, 1])], 1).astype(np.float32)
+    cref = R.cond_numbers(len(conds) - 1, drad)
+    ok = cref < 1000
+    assert np.allclose(conds[ok], cref[ok], rtol=2e-3) and nh >= order
+    for dc in (0, 1):
+        for mr in (0, 1):
+            mine = PR.np_decoder_filters(H, d, fftSize, fs, PR.SPR, order, itd, None, dc, mr, tdesign_deg=R.tdesign(2 * order))
+            ma, l2 = err_metrics(g[f"f_m3_dc{dc}_mr{mr}"], mine)
+            assert l2 < 3e-6 and ma < 3e-6, (dc, mr, ma, l2)
+    w = g["weights"] * np.float32(4 * np.pi)
+    mine = PR.np_decoder_filters(H, d, fftSize, fs, PR.SPR, 1, itd, w, 0, 0, tdesign_deg=R.tdesign(2))
+    ma, l2 = err_metrics(g["f_m3_o1_weights"], mine)
+    assert l2 < 3e-6, (ma, l2)
+
+
 IMS_CASES = {   # name: (order, maxN, maxTime_s, nBands, src, rec) -- the cases of tests/golden/make_golden_producers.py
     "t_o0": (0, -1, 0.10, 7, [5.1, 6.0, 1.1], [8.8, 5.5, 1.0]),
     "t_o3": (3, -1, 0.08, 7, [2.1, 1.0, 1.3], [8.8, 5.5, 0.9]),
@@ -346,15 +368,19 @@ def test_producer_argument_errors_need_no_device(saf):
     H, d, itd = synth.synthetic_hrtfs(50, 16)
     with pytest.raises(saf.SafConvError, match="fftSize must be even"):
         P.decoder_filters(np.zeros((8, 2, 50), np.complex64), d, 15, 48000.0, P.DECODER_LS, 1)
-    with pytest.raises(saf.SafConvError, match="SPR is not supported"):
-        P.decoder_filters(H, d, 16, 48000.0, P.DECODER_SPR, 1)
+    with pytest.raises(saf.SafConvError, match="needs the t-design of degree"):
+        P.decoder_filters(H, d, 16, 48000.0, P.DECODER_SPR, 5)                 # nothing registered for degree 10
+    with pytest.raises(saf.SafConvError, match="SPR needs order >= 1"):
+        P.decoder_filters(H, d, 16, 48000.0, P.DECODER_SPR, 0)
+    with pytest.raises(saf.SafConvError, match="safconv_register_tdesign"):
+        P.register_tdesign(0, np.zeros((4, 2), np.float32))
     with pytest.raises(saf.SafConvError, match="order > 10"):
         P.decoder_filters(H, d, 16, 48000.0, P.DECODER_LS, 11)
     L = saf.lib()
     out = np.full((2, 4, 16), 7.0, np.float32)
     # the reference-named void function leaves the output untouched on error and records the reason per thread
     P._L().getBinauralAmbiDecoderFilters(H.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.POINTER(C.c_float)), 50, 16, 48000.0,
-                                         P.DECODER_SPR, 1, None, None, 0, 0, out.ctypes.data_as(C.POINTER(C.c_float)))
+                                         P.DECODER_SPR, 5, None, None, 0, 0, out.ctypes.data_as(C.POINTER(C.c_float)))
     assert (out == 7.0).all() and L.safconv_last_error(None) == 1
     assert b"SPR" in L.safconv_last_error_string(None)
 
