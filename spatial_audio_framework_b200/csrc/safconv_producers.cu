@@ -635,7 +635,7 @@ int scdev_prod_spr_cond(const float* d_Y, const float* d_w, int nD, int nhMax, d
     cudaStream_t st = (cudaStream_t)stream;
     const int nS = (nhMax + 1) * (nhMax + 1);
     prod_gram_kernel<<<dim3(nS, nS), 128, 0, st>>>(d_Y, d_w, nD, nS, d_aug);
-    prod_cond_kernel<<<nhMax + 1, 512, 2 * nS * sizeof(double), st>>>(d_aug, nS, 200, 2000, 1.0 / (4.0 * 3.14159265358979323846), d_cond);
+    prod_cond_kernel<<<nhMax + 1, 512, 2 * nS * sizeof(double), st>>>(d_aug, nS, 100, 800, 1.0 / (4.0 * 3.14159265358979323846), d_cond);
     return (int)cudaGetLastError();
 }
 
