@@ -14,7 +14,7 @@
 
 #define SAFCONV_MAGIC 0x5AFC0B20u
 #define SAFCONV_MAGIC_MULTI 0x5AFC0B28u     /* safconv_multi.c: a handle that spans several devices */
-#define SAFCONV_VERSION_STRING "safconv-b200 0.2 (sm_100a; matrixConv/multiConv/TVConv; multi-GPU handles)"
+#define SAFCONV_VERSION_STRING "safconv-b200 0.3 (sm_100a; matrixConv/multiConv/TVConv; multi-GPU handles; filter producers)"
 
 /* mailbox of the resident latency kernel (page-locked host memory; the device side is ScMailbox in safconv_kernels.cu) */
 #define SC_RES_EXIT 0xFFFFFFFFu

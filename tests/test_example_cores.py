@@ -172,3 +172,36 @@ def test_example_core_libraries_export_the_reference_api():
     assert "saf_matrixConv_apply" in u and "saf_multiConv_apply" in u and "saf_TVConv_apply" in u
     r = subprocess.run(["nm", "-D", "--undefined-only", str(REF_SO)], capture_output=True, text=True).stdout
     assert "saf_matrixConv_apply" not in r
+
+
+REVERB_SO = ROOT / "oracle" / "_ref" / "libsaf_ref_reverbtest_b200.so"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not REVERB_SO.exists(), reason="oracle/_ref/libsaf_ref_reverbtest_b200.so not built (needs /root/reference)")
+def test_reference_ims_unit_test_runs_on_the_library(saf):
+    """The reference's own unit test of the image-source simulator, test__ims_shoebox_RIR
+    (test/src/test__reverb_module.c:27-96: add / remove / re-add sources, move a source and the receiver ten times,
+    computeEchograms + renderRIRs after every move), compiled unmodified with ims_shoebox_* resolved from
+    libsafconv_b200.so.  It asserts nothing itself; a hook in front of its final ims_shoebox_destroy
+    (oracle/shim/reverbtest_hooks.c) copies the rendered RIRs out, and they must equal the compiled reference's for the same
+    sequence (tests/golden/producers_ims.npz, ut_*)."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "producers_ims.npz")
+    L = C.CDLL(str(REVERB_SO))
+    L.test__ims_shoebox_RIR()
+    assert saf.lib().safconv_last_error(None) == 0, saf.lib().safconv_last_error_string(None)
+    n = L.reverbtest_num_captured()
+    assert n == 3
+    L.reverbtest_get.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(fp)]
+    seen = set()
+    for i in range(n):
+        rid, sid, ln, nch, data = C.c_int(), C.c_int(), C.c_int(), C.c_int(), fp()
+        assert L.reverbtest_get(i, C.byref(rid), C.byref(sid), C.byref(ln), C.byref(nch), C.byref(data)) == 0
+        rir = np.ctypeslib.as_array(data, shape=(nch.value, ln.value)).copy()
+        ref = g[f"ut_rir_r{rid.value}_s{sid.value}"]
+        assert rir.shape == ref.shape
+        ma, l2 = err_metrics(rir, ref)
+        assert l2 <= TOL_REL_L2 and ma <= TOL_MAXABS_FS, (rid.value, sid.value, ma, l2)
+        seen.add(sid.value)
+    assert len(seen) == 3

@@ -398,3 +398,34 @@ def test_producer_errors_without_a_device(saf):
     h = C.c_void_p()
     P._L().safconv_matrixConv_create_device(C.byref(h), 128, None, 100, 2, 2)
     assert not h and saf.lib().safconv_last_error(None) != 0
+
+
+def test_spr_finds_saf_tdesign_tables_in_the_host_process(tmp_path):
+    """inside a SAF host the SPR decoder needs no registration: the library's weak references to SAF's
+    __HANDLES_Tdesign_dirs_deg / __Tdesign_nPoints_per_degree resolve against the process.  A stand-in "host" library
+    defines the two symbols (a made-up degree-2 design); loaded first, it takes the call past the t-design check."""
+    import subprocess
+    import sys
+    src = tmp_path / "fakesaf.c"
+    src.write_text("static const float d2[4][2] = {{0,35.26f},{180,35.26f},{90,-35.26f},{-90,-35.26f}};\n"
+                   "const float* __HANDLES_Tdesign_dirs_deg[21] = {0, &d2[0][0]};\n"
+                   "const int __Tdesign_nPoints_per_degree[21] = {2, 4};\n")
+    so = tmp_path / "libfakesaf.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    code = f"""
+import ctypes as C, sys
+sys.path.insert(0, {str(ROOT)!r})
+if {{host}}: C.CDLL({str(so)!r}, mode=C.RTLD_GLOBAL)
+import numpy as np, spatial_audio_framework_b200 as saf
+from spatial_audio_framework_b200 import synth
+H, d, itd = synth.synthetic_hrtfs(50, 16)
+try:
+    saf.producers.decoder_filters(H, d, 16, 48000.0, saf.producers.DECODER_SPR, 1)
+    print("OK")
+except saf.SafConvError as e:
+    print("ERR", e)
+"""
+    with_host = subprocess.run([sys.executable, "-c", code.format(host=True)], capture_output=True, text=True).stdout
+    without = subprocess.run([sys.executable, "-c", code.format(host=False)], capture_output=True, text=True).stdout
+    assert "needs the t-design" in without
+    assert "needs the t-design" not in with_host and ("OK" in with_host or "no usable CUDA device" in with_host), with_host
