@@ -699,3 +699,38 @@ def test_rfft_pair_vs_golden_and_oracle(saf, orc):
             assert l2 <= 1e-6, (N, b, l2)
         xr = pkg.convolver_rfft(X, inverse=True)
         assert np.abs(xr - x).max() <= 1e-5, N              # the reference's own criterion (test__utilities_module.c:381-404)
+
+
+def test_two_live_handles_with_different_plans_share_kernels(saf, orc):
+    """Two handles alive at once whose MAC kernels are the SAME instantiation (R = 8) with different shared-memory needs
+    (64 inputs: a deep TMA stage ring; 1 input: a shallow one).  The opt-in shared-memory limit of a kernel is global per
+    device, so creating the small plan must not lower it under the large plan's launches (round-1 advisor finding):
+    create A (large), create B (small), then apply A, B, A block by block against the oracle."""
+    rng = np.random.default_rng(42)
+    hop, L, nblk = 1024, 2048, 3
+    HA = rng.uniform(-1, 1, (64, 64, L)).astype(np.float32)
+    HB = rng.uniform(-1, 1, (64, 1, L)).astype(np.float32)
+    xA = rng.uniform(-1, 1, (64, hop * nblk)).astype(np.float32)
+    xB = rng.uniform(-1, 1, (1, hop * nblk)).astype(np.float32)
+    refA = orc.OracleMatrixConv(hop, HA, 1).run(xA)
+    refB = orc.OracleMatrixConv(hop, HB, 1).run(xB)
+    A = saf.MatrixConv(hop, HA, 1)
+    B = saf.MatrixConv(hop, HB, 1)
+    for conv in (A, B):
+        conv.set_option("small_fused", 0)
+        conv.set_option("lookahead", 0)          # plain K1 -> K2 (full pass) -> K3: the launches the finding was about
+    yA = np.zeros_like(refA); yB = np.zeros_like(refB)
+    for b in range(nblk):
+        sl = slice(b * hop, (b + 1) * hop)
+        yA[:, sl] = A.apply(xA[:, sl])
+        yB[:, sl] = B.apply(xB[:, sl])
+    check(yA, refA, "large plan beside a small one")
+    check(yB, refB, "small plan beside a large one")
+    # and with the default path (look-ahead tail / head passes), a third handle created in between
+    A2 = saf.MatrixConv(hop, HA, 1)
+    C2 = saf.MatrixConv(hop, HB[:8], 1)
+    y2 = A2.run(xA)
+    check(y2, refA, "large plan, look-ahead passes")
+    check(C2.run(xB), refB[:8], "8 x 1 plan created after it")
+    for conv in (A, B, A2, C2):
+        conv.destroy()
