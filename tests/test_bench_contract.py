@@ -68,6 +68,15 @@ def test_round2_default_line():
     assert r5["bound"] == "tensor" and 0 < r5["frac"] < 1 and r5["issued_frac"] > r5["frac"]
     e = own["e2e"]
     assert e["blocks"] >= 2000 and e["block_latency_ms_p50"] > 0 and e["block_latency_paced_ms_p50"] > 0
+    # the filter producers in front of the convolver: timed, checked against the fp64 restatement, reference beside them
+    pr = sec["producers"]
+    for k in ("LS", "MAGLS_diffCM_maxRE"):
+        d = pr["decoder"][k]
+        assert d["gpu_ms"] > 0 and d["parity_rel_l2_vs_fp64"] <= 5e-6 and d["reference_1_core_ms"] > d["gpu_ms"]
+        assert d["parity_rel_l2_vs_fp64"] <= d["reference_rel_l2_vs_fp64"]          # closer to the truth than the reference
+    im = pr["ims"]
+    assert im["image_sources"] > 4e8 and im["render_s"] > 0 and im["parity_same_image_count"] and im["parity_same_taps"]
+    assert im["parity_rel_l2"] <= 1e-6 and im["reference_1_core"]["image_sources_per_s"] < im["image_sources_per_s"]
 
 
 @pytest.mark.parametrize("n", [2, 4, 8])
