@@ -198,11 +198,11 @@ __global__ void prod_spr_g_kernel(const float* __restrict__ Ynh, const double* _
 
 /* least-squares decoder of every band: D[band][ear][i] = sum_d H[src][ear][d] G[i][d], src = band, or the cut-off band
  * for band >= bc when `ta` (TA decoder as written: saf_hoa_internal.c:492-505 re-uses the cut-off band's HRTFs because
- * the phase term multiplies by exp(0)).  grid (2, nB), one warp per output i in turn. */
+ * the phase term multiplies by exp(0)).  grid (nB, 2), one warp per output i in turn. */
 __global__ void prod_ls_kernel(const float2* __restrict__ H, const float* __restrict__ G, int nB, int nD, int n,
                                int ta, int bc, float2* __restrict__ D)
 {
-    const int ear = blockIdx.x, band = blockIdx.y;
+    const int band = blockIdx.x, ear = blockIdx.y;      /* bands on grid.x: no 65535 limit */
     const int src = (ta && band >= bc) ? bc : band;
     const float2* h = H + ((size_t)src * 2 + ear) * nD;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -651,7 +651,7 @@ int scdev_prod_spr_matrix(const float* d_Ynh, const float* d_Ytd, const float* d
 
 int scdev_prod_ls(const void* d_H, const float* d_G, int nB, int nD, int n, int ta, int bc, void* d_D, void* stream)
 {
-    prod_ls_kernel<<<dim3(2, nB), 256, 0, (cudaStream_t)stream>>>((const float2*)d_H, d_G, nB, nD, n, ta, bc, (float2*)d_D);
+    prod_ls_kernel<<<dim3(nB, 2), 256, 0, (cudaStream_t)stream>>>((const float2*)d_H, d_G, nB, nD, n, ta, bc, (float2*)d_D);
     return (int)cudaGetLastError();
 }
 
