@@ -429,3 +429,54 @@ except saf.SafConvError as e:
     without = subprocess.run([sys.executable, "-c", code.format(host=False)], capture_output=True, text=True).stdout
     assert "needs the t-design" in without
     assert "needs the t-design" not in with_host and ("OK" in with_host or "no usable CUDA device" in with_host), with_host
+
+
+def test_device_rsh_up_to_order_20(host_lib):
+    """the SPR decoder evaluates the measurement grid up to SH order 20 (441 channels): the device evaluator against the
+    fp64 restatement there (no golden: the reference's own getSHreal needs factorials of 40 in double)"""
+    d = synth.fibonacci_grid_deg(300)
+    d[:2] = [[0, 90], [0, -90]]
+    Y = np.zeros((441, 300), np.float32)
+    host_lib.ph_rsh(20, _fp(np.ascontiguousarray(d)), 300, _fp(Y))
+    ref = PR.np_rsh(20, d)
+    assert np.isfinite(Y).all()
+    assert np.abs(Y - ref).max() < 2e-6 * np.abs(ref).max()
+    # orthonormality on a dense grid: (1 / N) Y Y^T = I up to the quadrature error of a Fibonacci grid at low orders
+    G = (Y[:49].astype(np.float64) @ Y[:49].T.astype(np.float64)) / 300
+    assert np.abs(G - np.eye(49)).max() < 0.1
+
+
+def test_device_ims_windowed_render_random_scenes(host_lib):
+    """randomised rooms / positions / window sizes / modes: the windowed enumeration must find every image of the lattice
+    scan exactly once (scp_ims_window_range / _rows / scp_ims_row_ranges are conservative, the exact tap test decides)"""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        room = rng.uniform(1.5, 12.0, 3).astype(np.float32)
+        src = (rng.uniform(0.02, 0.98, 3) * room).astype(np.float32)
+        rec = (rng.uniform(0.02, 0.98, 3) * room).astype(np.float32)
+        if trial % 5 == 0:
+            rec = src.copy()                                   # coincident source and receiver
+        if trial % 7 == 0:
+            src = np.array([0, 0, 0], np.float32)              # on a corner: images coincide pairwise
+        order = int(rng.integers(0, 4))
+        fs = float(rng.choice([8000.0, 44100.0, 48000.0, 96000.0]))
+        c = float(rng.uniform(300.0, 360.0))
+        if trial % 3 == 0:
+            p = host_pair(room, c, fs, src, rec, order, int(rng.integers(0, 9)), -1.0)
+        else:
+            dist = float(np.linalg.norm(src - rec))
+            p = host_pair(room, c, fs, src, rec, order, -1, (dist + float(rng.uniform(1.0, 25.0))) / c)
+        nB = int(rng.integers(1, 4))
+        tab, maxW = wall_tables(synth.IMS_TEST_ABS_WALL[:nB], (p.Nx, p.Ny, p.Nz))
+        n = C.c_int()
+        length = host_lib.ph_ims_pair(C.byref(p), _fp(tab), nB, maxW, None, C.byref(n), None)
+        if n.value == 0:
+            continue
+        scan = np.zeros((p.nSH, length), np.float32)
+        host_lib.ph_ims_pair(C.byref(p), _fp(tab), nB, maxW, _fp(scan), C.byref(n), None)
+        p.tw = int(rng.choice([32, 64, 96, 384, 1024]))
+        win = np.full((p.nSH, length), np.nan, np.float32)
+        found = host_lib.ph_ims_pair_windows(C.byref(p), _fp(tab), nB, maxW, _fp(win), None)
+        assert found == n.value, (trial, found, n.value)
+        assert not np.isnan(win).any()
+        assert np.allclose(win, scan, rtol=1e-6, atol=1e-12), trial
