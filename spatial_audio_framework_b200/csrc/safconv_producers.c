@@ -3,7 +3,7 @@
  *
  *   getBinauralAmbiDecoderFilters / getBinauralAmbiDecoderMtx
  *       /root/reference/framework/modules/saf_hoa/saf_hoa.h:401-471, saf_hoa.c:393-497; decoder designs
- *       saf_hoa_internal.c:162-228 (LS), :230-330 (LSDIFFEQ), :432-523 (TA), :525-623 (MAGLS)
+ *       saf_hoa_internal.c:162-228 (LS), :230-330 (LSDIFFEQ), :332-430 (SPR), :432-523 (TA), :525-623 (MAGLS)
  *   ims_shoebox_create / destroy / computeEchograms / renderRIRs / set* / add* / update* / remove*
  *       /root/reference/framework/modules/saf_reverb/saf_reverb.h:93-230, saf_reverb.c:36-295, 541-856
  *

@@ -4,8 +4,8 @@
  *
  *   binaural Ambisonic decoder filters   /root/reference/framework/modules/saf_hoa/saf_hoa.c:393-497
  *                                        (getBinauralAmbiDecoderMtx / getBinauralAmbiDecoderFilters) with the designs of
- *                                        saf_hoa_internal.c:162-228 (LS), :230-330 (LSDIFFEQ), :432-523 (TA),
- *                                        :525-623 (MagLS), max-rE weighting saf_hoa.c:427-445 and diffuse-field
+ *                                        saf_hoa_internal.c:162-228 (LS), :230-330 (LSDIFFEQ), :332-430 (SPR),
+ *                                        :432-523 (TA), :525-623 (MagLS), max-rE weighting saf_hoa.c:427-445 and diffuse-field
  *                                        covariance matching saf_hoa.c:497-604
  *   shoebox image-source RIRs            /root/reference/framework/modules/saf_reverb/saf_reverb.c:184-295
  *                                        (ims_shoebox_computeEchograms / ims_shoebox_renderRIRs) with
@@ -15,7 +15,8 @@
  * - The reference solves the SAME (nSH x nSH) normal equations once per band with cgesv (saf_hoa_internal.c:215-224).
  *   Here G = (Y W Y^T)^-1 Y W is formed once (fp64) and every least-squares decoder is ONE product D = H G^T over all
  *   bands (prod_ls_kernel); the per-band designs (diffuse EQ, covariance matching) are one CTA per band on top of it,
- *   MagLS -- a recurrence over the bands -- is one resident CTA walking the bands with G and Y streamed from L2.
+ *   MagLS -- a recurrence over the bands -- walks the bands on one thread-block cluster with the direction slices of Y
+ *   and G resident in shared memory; SPR folds its t-design projection into the same kind of matrix G.
  * - The reference materialises every image source of every band in echogram containers, sorts them by time, and adds
  *   them into per-band RIRs that are summed afterwards (saf_reverb_internal.c:269-710: ~13 arrays of nImages floats per
  *   band).  Here one thread per lattice point goes from reflection orders to RIR taps in registers: geometry (bit-exact
