@@ -139,3 +139,29 @@ def test_product_does_not_reference_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.c")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + list(pkg.rglob("Makefile")):
         txt = p.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, p
+
+
+def test_header_is_strict_c99_and_cxx17_and_the_c_example_builds(tmp_path):
+    """include/safconv_b200.h under -std=c99 / -std=c++17 -Wall -Wextra -pedantic -Werror, and the C example of the
+    producer -> convolver flow (examples/producers_to_convolver.c) built against the library.  Without a CUDA device
+    the example must stop at its first create with the library's error string (exit code 2), not crash."""
+    import shutil
+    import subprocess
+    import torch
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    lib_dir = ROOT / "spatial_audio_framework_b200"
+    link = ["-L" + str(lib_dir), "-lsafconv_b200", f"-Wl,-rpath,{lib_dir}", "-lm"]
+    exe = tmp_path / "example"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + str(ROOT / "include"),
+                    str(ROOT / "examples" / "producers_to_convolver.c"), "-o", str(exe)] + link, check=True)
+    cpp = tmp_path / "h.cpp"
+    cpp.write_text('#include "safconv_b200.h"\nint main() { return safconv_version() ? 0 : 1; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + str(ROOT / "include"),
+                    str(cpp), "-o", str(tmp_path / "hcpp")] + link, check=True)
+    assert subprocess.run([str(tmp_path / "hcpp")]).returncode == 0
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "energy at the ears" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 2 and "no usable CUDA device" in r.stderr
